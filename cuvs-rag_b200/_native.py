@@ -1,0 +1,345 @@
+"""ctypes binding of libb2vs.so (include/b2vs.h) and the build recipe for it.
+
+The library is the product path: every search / build / merge in this package goes through
+these entry points.  There is deliberately NO Python or CPU fallback here — if the shared
+library is missing or a call fails, a RuntimeError carrying ``b2vs_last_error()`` is raised.
+PyTorch only supplies device memory (``tensor.data_ptr()``) and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+from typing import Optional, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libb2vs.so")
+SOURCES = ["api.cu", "flat.cu", "merge.cu", "ivf.cu"]
+
+METRIC_L2, METRIC_IP = 0, 1
+F32, F16, BF16 = 0, 1, 2
+KIND_FLAT, KIND_IVF_FLAT, KIND_IVF_PQ = 0, 1, 2
+MAX_FUSED_K = 128
+
+_DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+_METRIC_CODE = {
+    "sqeuclidean": METRIC_L2, "l2": METRIC_L2, "euclidean": METRIC_L2, "L2": METRIC_L2,
+    "inner_product": METRIC_IP, "ip": METRIC_IP, "IP": METRIC_IP, "dot": METRIC_IP,
+}
+
+
+class IvfParams(ctypes.Structure):
+    _fields_ = [("n_lists", ctypes.c_int32), ("kmeans_iters", ctypes.c_int32),
+                ("train_fraction", ctypes.c_float), ("pq_dim", ctypes.c_int32),
+                ("pq_bits", ctypes.c_int32), ("seed", ctypes.c_uint64)]
+
+
+class SearchParams(ctypes.Structure):
+    _fields_ = [("n_probes", ctypes.c_int32), ("refine_ratio", ctypes.c_int32),
+                ("n_splits", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class IndexInfo(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("device", ctypes.c_int32), ("metric", ctypes.c_int32),
+                ("dtype", ctypes.c_int32), ("dim", ctypes.c_int32), ("n_lists", ctypes.c_int32),
+                ("pq_dim", ctypes.c_int32), ("pq_bits", ctypes.c_int32),
+                ("n_rows", ctypes.c_int64), ("id_offset", ctypes.c_int64),
+                ("device_bytes", ctypes.c_int64)]
+
+
+class SearchStats(ctypes.Structure):
+    _fields_ = [("launches", ctypes.c_int32), ("n_splits", ctypes.c_int32),
+                ("grid", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("algo_flops", ctypes.c_double), ("algo_bytes", ctypes.c_double)]
+
+
+# Every symbol include/b2vs.h declares; tests assert the built library exports all of them.
+EXPORTS = [
+    "b2vs_last_error", "b2vs_version", "b2vs_device_count", "b2vs_bf_create",
+    "b2vs_ivfflat_build", "b2vs_ivfpq_build", "b2vs_search", "b2vs_search_host",
+    "b2vs_merge_topk", "b2vs_kmeans_fit", "b2vs_index_info_get", "b2vs_index_last_stats",
+    "b2vs_ivf_list_sizes_host", "b2vs_ivf_centroids_host", "b2vs_index_destroy",
+]
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libb2vs.so")
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into libb2vs.so for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+        os.path.join(os.path.dirname(_HERE), "include", "b2vs.h")]
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(d) for d in deps)
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+           "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH + ".tmp"] + srcs
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Load libb2vs.so (once). Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(the CUDA extension is required; there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+        L.b2vs_last_error.restype = ctypes.c_char_p
+        L.b2vs_last_error.argtypes = []
+        L.b2vs_version.restype = i32
+        L.b2vs_device_count.argtypes = [ctypes.POINTER(i32)]
+        L.b2vs_bf_create.argtypes = [i32, i32, i32, i32, vp, i64, i64, vp, ctypes.POINTER(vp)]
+        L.b2vs_ivfflat_build.argtypes = [i32, i32, i32, i32, vp, i64, i64,
+                                         ctypes.POINTER(IvfParams), vp, ctypes.POINTER(vp)]
+        L.b2vs_ivfpq_build.argtypes = L.b2vs_ivfflat_build.argtypes
+        L.b2vs_search.argtypes = [vp, vp, i32, i32, i32, ctypes.POINTER(SearchParams), vp, vp, vp]
+        L.b2vs_search_host.argtypes = L.b2vs_search.argtypes
+        L.b2vs_merge_topk.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+        L.b2vs_kmeans_fit.argtypes = [i32, i32, i32, vp, i64, i32, i32, ctypes.c_uint64, vp, vp, vp]
+        L.b2vs_index_info_get.argtypes = [vp, ctypes.POINTER(IndexInfo)]
+        L.b2vs_index_last_stats.argtypes = [vp, ctypes.POINTER(SearchStats)]
+        L.b2vs_ivf_list_sizes_host.argtypes = [vp, vp]
+        L.b2vs_ivf_centroids_host.argtypes = [vp, vp]
+        L.b2vs_index_destroy.argtypes = [vp]
+        for name in EXPORTS:
+            if name != "b2vs_last_error":
+                getattr(L, name).restype = i32
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().b2vs_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def metric_code(metric) -> int:
+    if isinstance(metric, int):
+        return metric
+    try:
+        return _METRIC_CODE[metric]
+    except KeyError:
+        raise ValueError(f"unknown metric {metric!r}; expected one of {sorted(set(_METRIC_CODE))}")
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    try:
+        return _DTYPE_CODE[dtype]
+    except KeyError:
+        raise ValueError(f"unsupported dtype {dtype}; expected float32, float16 or bfloat16")
+
+
+def _stream_ptr(device: torch.device, stream: Optional[torch.cuda.Stream]) -> int:
+    s = stream if stream is not None else torch.cuda.current_stream(device)
+    return int(s.cuda_stream)
+
+
+def _require_cuda_matrix(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must live on a CUDA device (got {t.device})")
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2D [rows, dim] (got shape {tuple(t.shape)})")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous row-major")
+
+
+class NativeIndex:
+    """Owner of one ``b2vs_index*`` living on one GPU."""
+
+    def __init__(self, handle: int, device: torch.device, metric: int, keepalive=None):
+        self._h = ctypes.c_void_p(handle)
+        self.device = device
+        self.metric = metric
+        self._keepalive = keepalive  # borrowed database rows must outlive the index
+
+    # ------------------------------------------------------------------ constructors
+    @classmethod
+    def flat(cls, db: torch.Tensor, metric="sqeuclidean", id_offset: int = 0,
+             stream: Optional[torch.cuda.Stream] = None) -> "NativeIndex":
+        _require_cuda_matrix(db, "db")
+        L = lib()
+        out = ctypes.c_void_p()
+        m = metric_code(metric)
+        _check(L.b2vs_bf_create(db.device.index, m, dtype_code(db.dtype), db.shape[1],
+                                db.data_ptr(), db.shape[0], int(id_offset),
+                                _stream_ptr(db.device, stream), ctypes.byref(out)),
+               "b2vs_bf_create")
+        return cls(out.value, db.device, m, keepalive=db)
+
+    @classmethod
+    def ivf_flat(cls, db: torch.Tensor, n_lists: int, metric="sqeuclidean", id_offset: int = 0,
+                 kmeans_iters: int = 20, train_fraction: float = 0.5, seed: int = 0,
+                 stream: Optional[torch.cuda.Stream] = None) -> "NativeIndex":
+        return cls._ivf(db, "b2vs_ivfflat_build", n_lists, 0, 0, metric, id_offset, kmeans_iters,
+                        train_fraction, seed, stream)
+
+    @classmethod
+    def ivf_pq(cls, db: torch.Tensor, n_lists: int, pq_dim: int, pq_bits: int = 8,
+               metric="sqeuclidean", id_offset: int = 0, kmeans_iters: int = 20,
+               train_fraction: float = 0.5, seed: int = 0,
+               stream: Optional[torch.cuda.Stream] = None) -> "NativeIndex":
+        return cls._ivf(db, "b2vs_ivfpq_build", n_lists, pq_dim, pq_bits, metric, id_offset,
+                        kmeans_iters, train_fraction, seed, stream)
+
+    @classmethod
+    def _ivf(cls, db, fn, n_lists, pq_dim, pq_bits, metric, id_offset, iters, frac, seed, stream):
+        _require_cuda_matrix(db, "db")
+        L = lib()
+        out = ctypes.c_void_p()
+        m = metric_code(metric)
+        p = IvfParams(int(n_lists), int(iters), float(frac), int(pq_dim), int(pq_bits), int(seed))
+        _check(getattr(L, fn)(db.device.index, m, dtype_code(db.dtype), db.shape[1], db.data_ptr(),
+                              db.shape[0], int(id_offset), ctypes.byref(p),
+                              _stream_ptr(db.device, stream), ctypes.byref(out)), fn)
+        return cls(out.value, db.device, m, keepalive=None)
+
+    # ------------------------------------------------------------------ search
+    def search(self, queries: torch.Tensor, k: int, n_probes: int = 0, refine_ratio: int = 0,
+               n_splits: int = 0, stream: Optional[torch.cuda.Stream] = None,
+               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Device-resident search: returns (distances f32 [Q,k], ids i64 [Q,k]) on this GPU."""
+        if self._h.value is None:
+            raise RuntimeError("index has been destroyed")
+        _require_cuda_matrix(queries, "queries")
+        if queries.device != self.device:
+            raise ValueError(f"queries on {queries.device}, index on {self.device}")
+        nq = queries.shape[0]
+        if out is None:
+            d = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+            i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        else:
+            d, i = out
+        sp = SearchParams(int(n_probes), int(refine_ratio), int(n_splits), 0)
+        _check(lib().b2vs_search(self._h, queries.data_ptr(), dtype_code(queries.dtype), nq, int(k),
+                                 ctypes.byref(sp), d.data_ptr(), i.data_ptr(),
+                                 _stream_ptr(self.device, stream)), "b2vs_search")
+        return d, i
+
+    def search_host(self, queries: torch.Tensor, k: int, n_probes: int = 0, refine_ratio: int = 0,
+                    n_splits: int = 0, stream: Optional[torch.cuda.Stream] = None,
+                    out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Host-buffer search (H2D + search + D2H inside the call); CPU tensors in and out."""
+        if self._h.value is None:
+            raise RuntimeError("index has been destroyed")
+        if queries.is_cuda or queries.dim() != 2 or not queries.is_contiguous():
+            raise ValueError("search_host expects a contiguous 2D CPU tensor")
+        nq = queries.shape[0]
+        if out is None:
+            d = torch.empty((nq, k), dtype=torch.float32)
+            i = torch.empty((nq, k), dtype=torch.int64)
+        else:
+            d, i = out
+        sp = SearchParams(int(n_probes), int(refine_ratio), int(n_splits), 0)
+        _check(lib().b2vs_search_host(self._h, queries.data_ptr(), dtype_code(queries.dtype), nq,
+                                      int(k), ctypes.byref(sp), d.data_ptr(), i.data_ptr(),
+                                      _stream_ptr(self.device, stream)), "b2vs_search_host")
+        return d, i
+
+    # ------------------------------------------------------------------ introspection
+    def info(self) -> IndexInfo:
+        inf = IndexInfo()
+        _check(lib().b2vs_index_info_get(self._h, ctypes.byref(inf)), "b2vs_index_info_get")
+        return inf
+
+    def last_stats(self) -> SearchStats:
+        st = SearchStats()
+        _check(lib().b2vs_index_last_stats(self._h, ctypes.byref(st)), "b2vs_index_last_stats")
+        return st
+
+    def list_sizes(self) -> torch.Tensor:
+        inf = self.info()
+        out = torch.empty(max(inf.n_lists, 1), dtype=torch.int32)
+        _check(lib().b2vs_ivf_list_sizes_host(self._h, out.data_ptr()), "b2vs_ivf_list_sizes_host")
+        return out[: inf.n_lists]
+
+    def centroids(self) -> torch.Tensor:
+        inf = self.info()
+        out = torch.empty((max(inf.n_lists, 1), inf.dim), dtype=torch.float32)
+        _check(lib().b2vs_ivf_centroids_host(self._h, out.data_ptr()), "b2vs_ivf_centroids_host")
+        return out[: inf.n_lists]
+
+    @property
+    def descending(self) -> bool:
+        return self.metric == METRIC_IP
+
+    def destroy(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value is not None:
+            lib().b2vs_index_destroy(self._h)
+            self._h = ctypes.c_void_p()
+            self._keepalive = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def merge_topk(d_all: torch.Tensor, i_all: torch.Tensor, k: int, descending: bool = False,
+               stream: Optional[torch.cuda.Stream] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Global top-k over per-shard results stacked as [n_parts, Q, k_in] on one GPU."""
+    if d_all.dim() != 3 or d_all.shape != i_all.shape:
+        raise ValueError("d_all / i_all must be [n_parts, Q, k_in] with equal shapes")
+    if not d_all.is_cuda:
+        raise ValueError("merge_topk runs on the GPU; move the stacked results to a CUDA device")
+    d_all = d_all.contiguous().to(torch.float32)
+    i_all = i_all.contiguous().to(torch.int64)
+    g, nq, k_in = d_all.shape
+    out_d = torch.empty((nq, k), dtype=torch.float32, device=d_all.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=d_all.device)
+    _check(lib().b2vs_merge_topk(d_all.device.index, d_all.data_ptr(), i_all.data_ptr(), g, nq, k_in,
+                                 int(k), 1 if descending else 0, out_d.data_ptr(), out_i.data_ptr(),
+                                 _stream_ptr(d_all.device, stream)), "b2vs_merge_topk")
+    return out_d, out_i
+
+
+def kmeans_fit(x: torch.Tensor, n_clusters: int, iters: int = 20, seed: int = 0,
+               stream: Optional[torch.cuda.Stream] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    _require_cuda_matrix(x, "x")
+    cent = torch.empty((n_clusters, x.shape[1]), dtype=torch.float32, device=x.device)
+    labels = torch.empty((x.shape[0],), dtype=torch.int32, device=x.device)
+    _check(lib().b2vs_kmeans_fit(x.device.index, dtype_code(x.dtype), x.shape[1], x.data_ptr(),
+                                 x.shape[0], int(n_clusters), int(iters), int(seed),
+                                 cent.data_ptr(), labels.data_ptr(), _stream_ptr(x.device, stream)),
+           "b2vs_kmeans_fit")
+    return cent, labels
+
+
+def device_count() -> int:
+    c = ctypes.c_int(0)
+    _check(lib().b2vs_device_count(ctypes.byref(c)), "b2vs_device_count")
+    return c.value

@@ -1,0 +1,271 @@
+// K0 — fused brute-force distance + top-k on the tcgen05 tensor cores (sm_100a).
+//
+// Replaces the distance GEMM + select_k that cuVS/FAISS run behind
+// `ivf_flat.search` / `IndexFlat*.search` at the reference call sites
+// (improved_multi_gpu_rag.py:225-233, cuvs-2gpu-main.ipynb:L1801, faiss-main.ipynb cell 9).
+//
+// Work decomposition: item = (db split s, query block qb); a query block is 128 queries (the
+// 128 TMEM lanes), a db tile is 256 rows (256 fp32 TMEM columns), two accumulator buffers fill
+// the 512 TMEM columns so the epilogue of tile t overlaps the MMAs of tile t+1.  Items are
+// ordered split-major so the CTAs resident at one time stream the SAME db rows against
+// different query blocks and the db is read from HBM about once per batch (L2 serves the rest).
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (thread i of warp w owns query row 32*(w-4)+i).
+// The epilogue never writes distances to HBM: score = alpha*acc + beta[col] is compared with the
+// row's threshold and only candidates go to the row buffer (see topk.cuh).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "ptx.cuh"
+#include "topk.cuh"
+
+namespace b2vs {
+
+constexpr int kBM = 128;
+constexpr int kBN = 256;
+constexpr int kBK = 64;
+constexpr int kStages = 4;
+constexpr int kABytes = kBM * kBK * 2;
+constexpr int kBBytes = kBN * kBK * 2;
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kNormBytes = kBN * 4;
+constexpr int kTcThreads = 256;
+constexpr int kTcSmemBytes = kStages * kStageBytes + 2 * kNormBytes + 256 + 1024;
+
+struct BfTcParams {
+  const float* beta;    // [tiles_total*256] per db row additive term (||x||^2, 0, +inf on padding)
+  u64* cand;            // [grid][128][kCap] candidate buffers
+  u64* out_keys;        // [n_splits][q_pad][k] sorted ascending, kKeyInf padded
+  int n_qblocks;        // ceil(nq / 128)
+  int q_pad;            // n_qblocks * 128
+  int n_items;          // n_qblocks * n_splits
+  int tiles_total;      // ceil(n_db / 256)
+  int tiles_per_split;
+  int k_blocks;         // ceil(K / 64)
+  int k;                // 1..kMaxFusedK
+  float alpha;          // -2 (L2) or -1 (inner product)
+  uint32_t idesc;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
+             const BfTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - raw_addr);
+
+  const uint32_t norm_base = smem_base + kStages * kStageBytes;
+  const float* norm_ptr = reinterpret_cast<const float*>(smem + kStages * kStageBytes);
+  const uint32_t bar_base = norm_base + 2 * kNormBytes;
+  // barrier slots (8 bytes each)
+  const uint32_t bar_full = bar_base;                     // [kStages] TMA -> MMA
+  const uint32_t bar_empty = bar_base + 8 * kStages;      // [kStages] MMA -> TMA
+  const uint32_t bar_acc_full = bar_base + 16 * kStages;  // [2] MMA -> epilogue
+  const uint32_t bar_acc_empty = bar_acc_full + 16;       // [2] epilogue -> MMA
+  const uint32_t bar_norm_full = bar_acc_full + 32;       // [2] TMA -> epilogue
+  const uint32_t bar_norm_empty = bar_acc_full + 48;      // [2] epilogue -> TMA
+  const uint32_t tmem_slot = bar_acc_full + 64;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem + kStages * kStageBytes + 2 * kNormBytes +
+                                           16 * kStages + 64);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(bar_full + 8 * i, 1);
+      ptx::mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar_acc_full + 8 * i, 1);
+      ptx::mbar_init(bar_acc_empty + 8 * i, 4);
+      ptx::mbar_init(bar_norm_full + 8 * i, 1);
+      ptx::mbar_init(bar_norm_empty + 8 * i, 4);
+    }
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tm_q);
+    ptx::prefetch_tmap(&tm_x);
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, tcount = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int qb = item % p.n_qblocks;
+        const int s = item / p.n_qblocks;
+        const int t0 = s * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
+        for (int t = t0; t < t1; ++t, ++tcount) {
+          const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
+          ptx::mbar_wait(bar_norm_empty + 8 * as, aph ^ 1u);
+          ptx::mbar_arrive_expect_tx(bar_norm_full + 8 * as, kNormBytes);
+          ptx::bulk_load_1d(norm_base + as * kNormBytes, p.beta + static_cast<size_t>(t) * kBN,
+                            kNormBytes, bar_norm_full + 8 * as);
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+            ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
+            const uint32_t a_dst = smem_base + stage * kStageBytes;
+            ptx::tma_load_2d(a_dst, &tm_q, bar_full + 8 * stage, kb * kBK, qb * kBM);
+            ptx::tma_load_2d(a_dst + kABytes, &tm_x, bar_full + 8 * stage, kb * kBK, t * kBN);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, tcount = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int s = item / p.n_qblocks;
+        const int t0 = s * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
+        for (int t = t0; t < t1; ++t, ++tcount) {
+          const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
+          ptx::mbar_wait(bar_acc_empty + 8 * as, aph ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * kBN;
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            ptx::mbar_wait(bar_full + 8 * stage, phase);
+            ptx::tc_fence_after();
+            const uint32_t a_addr = smem_base + stage * kStageBytes;
+            const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+            for (int kk = 0; kk < kBK / 16; ++kk) {
+              const uint64_t adesc = ptx::make_kmajor_sw128_desc(a_addr + kk * 32);
+              const uint64_t bdesc = ptx::make_kmajor_sw128_desc(b_addr + kk * 32);
+              ptx::umma_f16(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+            }
+            ptx::umma_commit(bar_empty + 8 * stage);  // smem slot reusable once these MMAs retire
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          ptx::umma_commit(bar_acc_full + 8 * as);    // accumulator ready for the epilogue
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 4;                // TMEM lane quarter == warp % 4
+    const int row = ew * 32 + lane;         // query row inside the block
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    u64* const cand_warp = p.cand + (static_cast<size_t>(blockIdx.x) * kBM + ew * 32) * kCap;
+    u64* const my_cand = cand_warp + static_cast<size_t>(lane) * kCap;
+    const float inf = __int_as_float(0x7f800000);
+    uint32_t tcount = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int qb = item % p.n_qblocks;
+      const int s = item / p.n_qblocks;
+      const int t0 = s * p.tiles_per_split;
+      const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
+      float tau = inf;
+      int cnt = 0;
+      u64 best = kKeyInf;  // k == 1 fast path keeps the running arg-min in a register
+      for (int t = t0; t < t1; ++t, ++tcount) {
+        const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
+        ptx::mbar_wait(bar_acc_full + 8 * as, aph);
+        ptx::mbar_wait(bar_norm_full + 8 * as, aph);
+        ptx::tc_fence_after();
+        const float4* nrm4 = reinterpret_cast<const float4*>(norm_ptr + as * kBN);
+        const uint32_t col0 = static_cast<uint32_t>(t) * kBN;
+#pragma unroll 1
+        for (int c = 0; c < kBN / 32; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(lane_taddr + as * kBN + c * 32, r);
+          ptx::tmem_ld_wait();
+          if (p.k == 1) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 nb = nrm4[c * 8 + j4];
+              const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = j4 * 4 + jj;
+                const float sc = fmaf(p.alpha, __uint_as_float(r[j]), nbv[jj]);
+                if (sc < tau) {
+                  tau = sc;
+                  best = pack_key(sc, col0 + c * 32 + j);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 nb = nrm4[c * 8 + j4];
+              const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = j4 * 4 + jj;
+                const float sc = fmaf(p.alpha, __uint_as_float(r[j]), nbv[jj]);
+                if (sc < tau) {
+                  __stcg(my_cand + cnt, pack_key(sc, col0 + c * 32 + j));
+                  ++cnt;
+                }
+              }
+            }
+          }
+          if (c == kBN / 32 - 1) {
+            // all TMEM / beta reads of this tile are done: hand both buffers back
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::mbar_arrive(bar_acc_empty + 8 * as);
+              ptx::mbar_arrive(bar_norm_empty + 8 * as);
+            }
+          }
+          if (p.k != 1) {
+            // a chunk appends at most 32 keys per row: compact rows that could overflow next
+            uint32_t need = __ballot_sync(0xffffffffu, cnt > kCap - 32);
+            while (need) {
+              const int rr = __ffs(need) - 1;
+              need &= need - 1;
+              const int n_r = __shfl_sync(0xffffffffu, cnt, rr);
+              int kept;
+              u64* rb = cand_warp + static_cast<size_t>(rr) * kCap;
+              const float nt = compact_row(rb, rb, n_r, p.k, lane, &kept);
+              if (lane == rr) { cnt = kept; tau = nt; }
+            }
+          }
+        }
+      }
+      // ---- item done: emit this (split, query block)'s sorted top-k keys
+      u64* out_blk = p.out_keys + (static_cast<size_t>(s) * p.q_pad + qb * kBM + ew * 32) * p.k;
+      if (p.k == 1) {
+        out_blk[lane] = best;
+      } else {
+        __syncwarp();
+        for (int rr = 0; rr < 32; ++rr) {
+          const int n_r = __shfl_sync(0xffffffffu, cnt, rr);
+          int kept;
+          u64* dst = out_blk + static_cast<size_t>(rr) * p.k;
+          compact_row(cand_warp + static_cast<size_t>(rr) * kCap, dst, n_r, p.k, lane, &kept);
+          for (int i = kept + lane; i < p.k; i += 32) dst[i] = kKeyInf;
+        }
+        __syncwarp();
+      }
+      (void)row;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace b2vs

@@ -1,0 +1,142 @@
+// Internal definitions shared by the b2vs translation units (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/b2vs.h"
+
+namespace b2vs {
+
+using u64 = unsigned long long;
+
+void set_error(const char* fmt, ...);
+
+#define B2VS_CUDA(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      ::b2vs::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return (e__ == cudaErrorMemoryAllocation) ? B2VS_ENOMEM : B2VS_ECUDA;               \
+    }                                                                                     \
+  } while (0)
+
+#define B2VS_CHECK(cond, code, ...)  \
+  do {                               \
+    if (!(cond)) {                   \
+      ::b2vs::set_error(__VA_ARGS__); \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+#define B2VS_TRY(expr)          \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != B2VS_OK) return rc__; \
+  } while (0)
+
+// RAII device switch: every entry point runs on the device it was given and restores the
+// caller's ambient device (the reference relies on `with torch.cuda.device(g)`).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// Growable device buffer (grow-only; steady-state searches allocate nothing).
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need) {
+    if (need <= bytes) return B2VS_OK;
+    if (ptr) { cudaFree(ptr); ptr = nullptr; bytes = 0; }
+    size_t want = need + need / 8;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      e = cudaMalloc(&ptr, need);
+      want = need;
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cudaMalloc(%zu bytes) failed: %s", need, cudaGetErrorString(e));
+      ptr = nullptr;
+      return B2VS_ENOMEM;
+    }
+    bytes = want;
+    return B2VS_OK;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+inline int elem_bytes(int dtype) { return dtype == B2VS_F32 ? 4 : 2; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+int sm_count(int dev);
+
+// ------------------------------------------------------------------------------------------
+// The exact-search engine: a [n, kdim] 16-bit K-major matrix + per-row additive term.
+// Used directly by flat indexes and re-used for the coarse quantizer / k-means assignment.
+struct FlatEngine {
+  int dev = 0;
+  int metric = B2VS_METRIC_L2;
+  int src_dtype = B2VS_BF16;  // dtype the caller gave us
+  int dim = 0;                // logical dimension
+  int kdim = 0;               // GEMM K extent in 16-bit elements (dim padded to 8, x3 for fp32)
+  int ab_format = 1;          // 0 = fp16, 1 = bf16 (tensor-core operand format)
+  bool split3 = false;        // fp32 source re-encoded as bf16 [hi | hi | lo]
+  int64_t n = 0;
+  const void* mat = nullptr;  // operand matrix used by TMA (borrowed or == owned.ptr)
+  DevBuf owned;               // owned re-encoding, if any
+  DevBuf beta;                // [tiles*256] float: ||x||^2 (L2) or 0 (IP); +inf on padding
+  CUtensorMap tm_x;
+  // workspaces (grow-only)
+  DevBuf ws_cand, ws_keys, ws_q, ws_qnorm;
+  b2vs_search_stats stats{};
+
+  int init(int dev, int metric, int dtype, int dim, const void* db, int64_t n, cudaStream_t st);
+  // Top-k of queries vs this matrix. out_keys layout is internal; results are written as
+  // (dist fp32, id int64 = row + id_offset) when out_d/out_i are given, or as int32 labels
+  // (k == 1) when out_label is given.
+  int search(const void* q, int q_dtype, int nq, int k, int force_splits, int64_t id_offset,
+             float* out_d, int64_t* out_i, int32_t* out_label, cudaStream_t st);
+  size_t owned_bytes() const { return owned.bytes + beta.bytes; }
+  void destroy();
+};
+
+int encode_tmap_2d(CUtensorMap* tm, const void* base, int ab_format, int64_t rows, int64_t cols,
+                   int box_rows);
+
+// merge.cu
+int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k, int metric,
+                        const float* qnorm, int64_t id_offset, float* out_d, int64_t* out_i,
+                        int32_t* out_label, cudaStream_t st);
+
+}  // namespace b2vs
+
+struct b2vs_index {
+  int kind = B2VS_KIND_FLAT;
+  int dev = 0;
+  int metric = 0;
+  int dtype = 0;
+  int dim = 0;
+  int64_t n = 0;
+  int64_t id_offset = 0;
+  b2vs::FlatEngine flat;  // flat index, or the coarse quantizer of an IVF index
+  void* ivf = nullptr;    // b2vs::IvfData* (ivf.cu)
+};

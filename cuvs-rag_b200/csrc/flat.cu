@@ -1,0 +1,318 @@
+// Host side of the exact-search engine (K0): operand preparation, TMA descriptors, work
+// decomposition and launch of bf_tc_kernel + the split merge.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+
+#include "bf_tc.cuh"
+#include "common.h"
+
+namespace b2vs {
+
+// ------------------------------------------------------------------------------------------
+// Row preparation: one warp per row.  Produces the 16-bit K-major operand (optionally) and the
+// per-row squared norm (optionally).
+//   mode 0: convert/pad to the 16-bit operand format            out row = [x]            (kdim = dp)
+//   mode 1: fp32 -> bf16 hi/lo split, database side             out row = [hi | hi | lo] (kdim = 3dp)
+//   mode 2: fp32 -> bf16 hi/lo split, query side                out row = [hi | lo | hi] (kdim = 3dp)
+// The norm is taken over the values the contraction will see: the rounded 16-bit values in
+// mode 0, the original fp32 values in modes 1/2 (the split reproduces them to ~2^-16).
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) {
+  return __bfloat162float(v);
+}
+__device__ __forceinline__ uint16_t f32_to_op(float v, int fmt, float* back) {
+  if (fmt == 0) {
+    __half h = __float2half_rn(v);
+    *back = __half2float(h);
+    return __half_as_ushort(h);
+  }
+  __nv_bfloat16 b = __float2bfloat16_rn(v);
+  *back = __bfloat162float(b);
+  return __bfloat16_as_ushort(b);
+}
+
+template <typename T>
+__global__ void prep_rows_kernel(const T* __restrict__ src, int64_t n, int dim, int dp, int mode,
+                                 int fmt, uint16_t* __restrict__ out, float* __restrict__ norm_out,
+                                 int want_norm, int64_t n_pad, float pad_value) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int kdim = (mode == 0) ? dp : 3 * dp;
+  for (int64_t r = warp0; r < n_pad; r += nwarps) {
+    if (r >= n) {
+      if (norm_out && lane == 0) norm_out[r] = pad_value;
+      continue;
+    }
+    const T* row = src + r * dim;
+    uint16_t* orow = out ? out + r * kdim : nullptr;
+    float acc = 0.f;
+    for (int j = lane; j < dp; j += 32) {
+      const float v = (j < dim) ? to_f32<T>(row[j]) : 0.f;
+      if (mode == 0) {
+        float back;
+        const uint16_t o = f32_to_op(v, fmt, &back);
+        if (orow) orow[j] = o;
+        acc = fmaf(back, back, acc);
+      } else {
+        float hi_f, lo_f;
+        const uint16_t hi = f32_to_op(v, 1, &hi_f);
+        const uint16_t lo = f32_to_op(v - hi_f, 1, &lo_f);
+        if (orow) {
+          orow[j] = hi;
+          orow[dp + j] = (mode == 1) ? hi : lo;
+          orow[2 * dp + j] = (mode == 1) ? lo : hi;
+        }
+        acc = fmaf(v, v, acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (norm_out && lane == 0) norm_out[r] = want_norm ? acc : 0.f;
+  }
+}
+
+static int launch_prep(const void* src, int dtype, int64_t n, int dim, int dp, int mode, int fmt,
+                       uint16_t* out, float* norm_out, int want_norm, int64_t n_pad,
+                       cudaStream_t st) {
+  if (n_pad <= 0) return B2VS_OK;
+  const int threads = 256;
+  const int64_t want_blocks = ceil_div(n_pad, threads / 32);
+  const int blocks = static_cast<int>(std::min<int64_t>(want_blocks, 148 * 16));
+  const float inf = INFINITY;
+  switch (dtype) {
+    case B2VS_F32:
+      prep_rows_kernel<float><<<blocks, threads, 0, st>>>(static_cast<const float*>(src), n, dim,
+                                                          dp, mode, fmt, out, norm_out, want_norm,
+                                                          n_pad, inf);
+      break;
+    case B2VS_F16:
+      prep_rows_kernel<__half><<<blocks, threads, 0, st>>>(static_cast<const __half*>(src), n, dim,
+                                                           dp, mode, fmt, out, norm_out, want_norm,
+                                                           n_pad, inf);
+      break;
+    case B2VS_BF16:
+      prep_rows_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(src), n, dim, dp, mode, fmt, out, norm_out, want_norm,
+          n_pad, inf);
+      break;
+    default:
+      set_error("unknown dtype %d", dtype);
+      return B2VS_EINVAL;
+  }
+  B2VS_CUDA(cudaGetLastError());
+  return B2VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D map over a row-major [rows, cols] 16-bit matrix; box = [box_rows, 64], 128-byte swizzle,
+// out-of-bounds elements read as zero.
+int encode_tmap_2d(CUtensorMap* tm, const void* base, int ab_format, int64_t rows, int64_t cols,
+                   int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  B2VS_CHECK(fn != nullptr, B2VS_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  B2VS_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, B2VS_EINVAL,
+             "matrix base pointer must be 16-byte aligned");
+  B2VS_CHECK((cols * 2) % 16 == 0, B2VS_EINVAL, "row pitch must be a multiple of 16 bytes");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, ab_format == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2VS_CHECK(r == CUDA_SUCCESS, B2VS_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d",
+             static_cast<int>(r));
+  return B2VS_OK;
+}
+
+int sm_count(int dev) {
+  static int cache[64];
+  if (dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+      v = 148;
+    cache[dev] = v;
+  }
+  return cache[dev];
+}
+
+// ------------------------------------------------------------------------------------------
+int FlatEngine::init(int dev_, int metric_, int dtype, int dim_, const void* db, int64_t n_,
+                     cudaStream_t st) {
+  dev = dev_;
+  metric = metric_;
+  src_dtype = dtype;
+  dim = dim_;
+  n = n_;
+  const int dp = static_cast<int>(round_up(dim, 8));
+  split3 = (dtype == B2VS_F32);
+  ab_format = (dtype == B2VS_F16) ? 0 : 1;
+  kdim = split3 ? 3 * dp : dp;
+  const int64_t tiles = std::max<int64_t>(1, ceil_div(n, kBN));
+  B2VS_TRY(beta.reserve(static_cast<size_t>(tiles) * kBN * sizeof(float)));
+  const bool borrow = !split3 && dp == dim && (reinterpret_cast<uintptr_t>(db) & 15) == 0;
+  uint16_t* out = nullptr;
+  if (!borrow) {
+    B2VS_TRY(owned.reserve(static_cast<size_t>(std::max<int64_t>(n, 1)) * kdim * 2));
+    out = owned.as<uint16_t>();
+    mat = owned.ptr;
+  } else {
+    mat = db;
+  }
+  B2VS_TRY(launch_prep(db, dtype, n, dim, dp, split3 ? 1 : 0, ab_format, out, beta.as<float>(),
+                       metric == B2VS_METRIC_L2 ? 1 : 0, tiles * kBN, st));
+  if (n > 0) B2VS_TRY(encode_tmap_2d(&tm_x, mat, ab_format, n, kdim, kBN));
+  return B2VS_OK;
+}
+
+void FlatEngine::destroy() {
+  owned.release();
+  beta.release();
+  ws_cand.release();
+  ws_keys.release();
+  ws_q.release();
+  ws_qnorm.release();
+}
+
+__global__ void fill_missing_kernel(float* out_d, int64_t* out_i, int32_t* out_label, int64_t total,
+                                    float dval) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  if (out_d) out_d[i] = dval;
+  if (out_i) out_i[i] = -1;
+  if (out_label) out_label[i] = -1;
+}
+
+// Number of db splits: minimise waves * (tiles per split + fixed per-item cost in tile units).
+static int choose_splits(int n_qblocks, int64_t tiles, int sms, int k) {
+  const int64_t overhead = (k == 1) ? 1 : 40;
+  int64_t best_cost = INT64_MAX;
+  int best = 1;
+  const int64_t smax = std::min<int64_t>(tiles, 512);
+  for (int64_t s = 1; s <= smax; ++s) {
+    const int64_t tps = ceil_div(tiles, s);
+    const int64_t s_eff = ceil_div(tiles, tps);
+    const int64_t waves = ceil_div(static_cast<int64_t>(n_qblocks) * s_eff, sms);
+    const int64_t cost = waves * (tps + overhead);
+    if (cost < best_cost) { best_cost = cost; best = static_cast<int>(s_eff); }
+  }
+  return best;
+}
+
+int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_splits,
+                       int64_t id_offset, float* out_d, int64_t* out_i, int32_t* out_label,
+                       cudaStream_t st) {
+  B2VS_CHECK(nq > 0, B2VS_EINVAL, "nq must be positive (got %d)", nq);
+  B2VS_CHECK(k >= 1 && k <= kMaxFusedK, B2VS_EUNSUP,
+             "k=%d outside the fused top-k range [1, %d]", k, kMaxFusedK);
+  stats = b2vs_search_stats{};
+  const float missing = (metric == B2VS_METRIC_IP) ? -INFINITY : INFINITY;
+  if (n == 0) {
+    const int64_t total = static_cast<int64_t>(nq) * k;
+    fill_missing_kernel<<<static_cast<unsigned>(ceil_div(total, 256)), 256, 0, st>>>(
+        out_d, out_i, out_label, total, missing);
+    B2VS_CUDA(cudaGetLastError());
+    stats.launches = 1;
+    return B2VS_OK;
+  }
+  const int dp = static_cast<int>(round_up(dim, 8));
+  const int want_norm = (metric == B2VS_METRIC_L2) ? 1 : 0;
+  const int n_qblocks = static_cast<int>(ceil_div(nq, kBM));
+  const int q_pad = n_qblocks * kBM;
+  int launches = 0;
+
+  // ---- query operand + norms
+  const int op_dtype = ab_format == 0 ? B2VS_F16 : B2VS_BF16;
+  const bool borrow_q =
+      !split3 && q_dtype == op_dtype && dp == dim && (reinterpret_cast<uintptr_t>(q) & 15) == 0;
+  B2VS_TRY(ws_qnorm.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
+  const void* q_mat = q;
+  if (!borrow_q) {
+    B2VS_CHECK(!(split3 && q_dtype != B2VS_F32) || true, B2VS_EINVAL, "unreachable");
+    B2VS_TRY(ws_q.reserve(static_cast<size_t>(nq) * kdim * 2));
+    q_mat = ws_q.ptr;
+    B2VS_TRY(launch_prep(q, q_dtype, nq, dim, dp, split3 ? 2 : 0, ab_format, ws_q.as<uint16_t>(),
+                         ws_qnorm.as<float>(), want_norm, nq, st));
+    ++launches;
+  } else if (want_norm) {
+    B2VS_TRY(launch_prep(q, q_dtype, nq, dim, dp, 0, ab_format, nullptr, ws_qnorm.as<float>(), 1,
+                         nq, st));
+    ++launches;
+  }
+  CUtensorMap tm_q;
+  B2VS_TRY(encode_tmap_2d(&tm_q, q_mat, ab_format, nq, kdim, kBM));
+
+  // ---- decomposition
+  const int sms = sm_count(dev);
+  const int64_t tiles = ceil_div(n, kBN);
+  int n_splits = force_splits > 0 ? static_cast<int>(std::min<int64_t>(force_splits, tiles))
+                                  : choose_splits(n_qblocks, tiles, sms, k);
+  const int tps = static_cast<int>(ceil_div(tiles, n_splits));
+  n_splits = static_cast<int>(ceil_div(tiles, tps));
+  const int n_items = n_qblocks * n_splits;
+  const int grid = std::min(n_items, sms);
+
+  B2VS_TRY(ws_cand.reserve(static_cast<size_t>(grid) * kBM * kCap * sizeof(u64)));
+  B2VS_TRY(ws_keys.reserve(static_cast<size_t>(n_splits) * q_pad * k * sizeof(u64)));
+
+  BfTcParams p;
+  p.beta = beta.as<float>();
+  p.cand = ws_cand.as<u64>();
+  p.out_keys = ws_keys.as<u64>();
+  p.n_qblocks = n_qblocks;
+  p.q_pad = q_pad;
+  p.n_items = n_items;
+  p.tiles_total = static_cast<int>(tiles);
+  p.tiles_per_split = tps;
+  p.k_blocks = static_cast<int>(ceil_div(kdim, kBK));
+  p.k = k;
+  p.alpha = (metric == B2VS_METRIC_L2) ? -2.f : -1.f;
+  p.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(ab_format), kBM, kBN);
+
+  B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kTcSmemBytes));
+  bf_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(tm_q, tm_x, p);
+  B2VS_CUDA(cudaGetLastError());
+  ++launches;
+
+  B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits, q_pad, nq, k, metric,
+                               ws_qnorm.as<float>(), id_offset, out_d, out_i, out_label, st));
+  ++launches;
+
+  stats.launches = launches;
+  stats.n_splits = n_splits;
+  stats.grid = grid;
+  stats.algo_flops = 2.0 * nq * static_cast<double>(n) * dim;
+  stats.algo_bytes = 0;
+  return B2VS_OK;
+}
+
+}  // namespace b2vs

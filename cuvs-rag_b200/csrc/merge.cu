@@ -1,0 +1,145 @@
+// K8 — top-k merges.
+//  * merge_splits_kernel: folds the per-(split, query) sorted key lists produced by the fused
+//    distance kernels into the final (distance, id) rows.
+//  * merge_parts_kernel (b2vs_merge_topk): the cross-shard global top-k that replaces the
+//    reference's host-side concatenate + np.argsort(...)[:k]
+//    (improved_multi_gpu_rag.py:266-275, cuvs-2gpu-main.ipynb:L1806-1832,
+//    test_search_result_aggregator.py:308-358 for the known answers).
+// Both run one warp per query and keep a sorted 128-entry register list (4 keys per lane);
+// a new sorted run is folded in with the classic "min(a[i], b[n-1-i]) is bitonic" step plus one
+// bitonic merge pass.
+#include <cmath>
+
+#include "common.h"
+#include "topk.cuh"
+
+namespace b2vs {
+
+constexpr int kMergeE = 4;  // 32 * 4 = 128 = kMaxFusedK
+
+__global__ void merge_splits_kernel(const u64* __restrict__ keys, int n_splits, int q_pad, int nq,
+                                    int k, int metric, const float* __restrict__ qnorm,
+                                    long long id_offset, float* __restrict__ out_d,
+                                    long long* __restrict__ out_i, int* __restrict__ out_label) {
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  u64 acc[kMergeE];
+#pragma unroll
+  for (int e = 0; e < kMergeE; ++e) acc[e] = kKeyInf;
+  for (int s = 0; s < n_splits; ++s) {
+    const u64* list = keys + (static_cast<size_t>(s) * q_pad + q) * k;
+#pragma unroll
+    for (int e = 0; e < kMergeE; ++e) {
+      const int src = 32 * kMergeE - 1 - (lane * kMergeE + e);  // reversed run
+      const u64 b = (src < k) ? __ldcg(list + src) : kKeyInf;
+      acc[e] = acc[e] < b ? acc[e] : b;
+    }
+    warp_bitonic_merge<kMergeE>(acc, lane);
+  }
+  const float qn = (metric == B2VS_METRIC_L2 && qnorm) ? qnorm[q] : 0.f;
+#pragma unroll
+  for (int e = 0; e < kMergeE; ++e) {
+    const int i = lane * kMergeE + e;
+    if (i >= k) continue;
+    const u64 key = acc[e];
+    const bool valid = key != kKeyInf;
+    const float sc = key_score(key);
+    float d;
+    if (metric == B2VS_METRIC_L2) d = valid ? fmaxf(sc + qn, 0.f) : INFINITY;
+    else d = valid ? -sc : -INFINITY;
+    const size_t o = static_cast<size_t>(q) * k + i;
+    if (out_d) out_d[o] = d;
+    if (out_i) out_i[o] = valid ? static_cast<long long>(key_id(key)) + id_offset : -1ll;
+    if (out_label) out_label[o] = valid ? static_cast<int>(key_id(key)) : -1;
+  }
+}
+
+int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k, int metric,
+                        const float* qnorm, int64_t id_offset, float* out_d, int64_t* out_i,
+                        int32_t* out_label, cudaStream_t st) {
+  const int threads = 128;
+  const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(nq) * 32, threads));
+  merge_splits_kernel<<<blocks, threads, 0, st>>>(keys, n_splits, q_pad, nq, k, metric, qnorm,
+                                                  id_offset, out_d,
+                                                  reinterpret_cast<long long*>(out_i), out_label);
+  B2VS_CUDA(cudaGetLastError());
+  return B2VS_OK;
+}
+
+// Cross-shard merge.  Key = (orderable distance, position in the concatenated candidate row) so
+// equal distances keep the lower part / lower rank first, exactly like a stable argsort over the
+// concatenation.  Positions index d_all / i_all for the final gather.
+__global__ void merge_parts_kernel(const float* __restrict__ d_all, const long long* __restrict__ i_all,
+                                   int n_parts, int nq, int k_in, int k_out, int descending,
+                                   float* __restrict__ out_d, long long* __restrict__ out_i) {
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  u64 acc[kMergeE];
+#pragma unroll
+  for (int e = 0; e < kMergeE; ++e) acc[e] = kKeyInf;
+  // Walk the concatenated candidate row in chunks of 128 (any order, any k_in): sort the chunk,
+  // reverse it across the warp, min-combine with the running list, re-merge.
+  const int total = n_parts * k_in;
+  for (int c0 = 0; c0 < total; c0 += 32 * kMergeE) {
+    u64 b[kMergeE];
+#pragma unroll
+    for (int e = 0; e < kMergeE; ++e) {
+      const int pos = c0 + lane * kMergeE + e;
+      b[e] = kKeyInf;
+      if (pos < total) {
+        const size_t src = (static_cast<size_t>(pos / k_in) * nq + q) * k_in + (pos % k_in);
+        const float d = d_all[src];
+        const long long id = i_all[src];
+        if (id >= 0 && !isnan(d)) b[e] = pack_key(descending ? -d : d, static_cast<uint32_t>(pos));
+      }
+    }
+    warp_bitonic_sort<kMergeE>(b, lane);
+#pragma unroll
+    for (int e = 0; e < kMergeE; ++e) {
+      const u64 r = shfl_u64(b[kMergeE - 1 - e], 31 - lane);  // element 127 - i
+      acc[e] = acc[e] < r ? acc[e] : r;
+    }
+    warp_bitonic_merge<kMergeE>(acc, lane);
+  }
+#pragma unroll
+  for (int e = 0; e < kMergeE; ++e) {
+    const int i = lane * kMergeE + e;
+    if (i >= k_out) continue;
+    const u64 key = acc[e];
+    const size_t o = static_cast<size_t>(q) * k_out + i;
+    if (key == kKeyInf) {
+      out_d[o] = descending ? -INFINITY : INFINITY;
+      out_i[o] = -1;
+    } else {
+      const uint32_t pos = key_id(key);
+      const size_t src = (static_cast<size_t>(pos / k_in) * nq + q) * k_in + (pos % k_in);
+      out_d[o] = d_all[src];
+      out_i[o] = i_all[src];
+    }
+  }
+}
+
+}  // namespace b2vs
+
+extern "C" int b2vs_merge_topk(int dev, const float* d_all, const int64_t* i_all, int n_parts,
+                               int nq, int k_in, int k_out, int descending, float* out_d,
+                               int64_t* out_i, void* stream) {
+  using namespace b2vs;
+  B2VS_CHECK(d_all && i_all && out_d && out_i, B2VS_EINVAL, "null pointer passed to b2vs_merge_topk");
+  B2VS_CHECK(n_parts >= 1 && nq >= 1 && k_in >= 1, B2VS_EINVAL,
+             "merge shape must be positive (n_parts=%d nq=%d k_in=%d)", n_parts, nq, k_in);
+  B2VS_CHECK(k_out >= 1 && k_out <= kMaxFusedK, B2VS_EUNSUP, "k_out=%d outside [1, %d]", k_out,
+             kMaxFusedK);
+  DeviceGuard guard(dev);
+  B2VS_CHECK(guard.ok, B2VS_ECUDA, "cannot select device %d", dev);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 128;
+  const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(nq) * 32, threads));
+  merge_parts_kernel<<<blocks, threads, 0, st>>>(d_all, reinterpret_cast<const long long*>(i_all),
+                                                 n_parts, nq, k_in, k_out, descending, out_d,
+                                                 reinterpret_cast<long long*>(out_i));
+  B2VS_CUDA(cudaGetLastError());
+  return B2VS_OK;
+}

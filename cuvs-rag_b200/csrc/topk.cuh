@@ -1,0 +1,149 @@
+// Per-row streaming top-k used by the fused distance kernels.
+//
+// One thread owns one query row.  It keeps a threshold `tau` (an upper bound on the row's
+// current k-th best score) and appends every (score, id) with score < tau to the row's
+// candidate buffer (capacity kCap keys, global memory / L2 resident).  When a buffer is about
+// to overflow the owning warp sorts it cooperatively (register bitonic network across the 32
+// lanes), keeps the k best, and tightens tau.  Keys are 64-bit: order-preserving float bits in
+// the high word, the row id inside the shard in the low word, so a plain unsigned compare
+// orders by (score, id) and ties resolve to the smaller id.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b2vs {
+
+using u64 = unsigned long long;
+
+constexpr int kSortE = 8;            // keys per lane in the warp sort
+constexpr int kCap = 32 * kSortE;    // candidate buffer capacity per row (256)
+constexpr int kMaxFusedK = 128;      // largest k served by the fused path
+constexpr u64 kKeyInf = ~0ull;
+
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t b = __float_as_uint(f);
+  return b ^ ((b & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+  uint32_t b = o ^ ((o & 0x80000000u) ? 0x80000000u : 0xFFFFFFFFu);
+  return __uint_as_float(b);
+}
+__device__ __forceinline__ u64 pack_key(float score, uint32_t id) {
+  return (static_cast<u64>(f2ord(score)) << 32) | id;
+}
+__device__ __forceinline__ float key_score(u64 key) { return ord2f(static_cast<uint32_t>(key >> 32)); }
+__device__ __forceinline__ uint32_t key_id(u64 key) { return static_cast<uint32_t>(key); }
+
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int mask) {
+  uint32_t lo = static_cast<uint32_t>(v), hi = static_cast<uint32_t>(v >> 32);
+  lo = __shfl_xor_sync(0xffffffffu, lo, mask);
+  hi = __shfl_xor_sync(0xffffffffu, hi, mask);
+  return (static_cast<u64>(hi) << 32) | lo;
+}
+__device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
+  uint32_t lo = static_cast<uint32_t>(v), hi = static_cast<uint32_t>(v >> 32);
+  lo = __shfl_sync(0xffffffffu, lo, src);
+  hi = __shfl_sync(0xffffffffu, hi, src);
+  return (static_cast<u64>(hi) << 32) | lo;
+}
+
+// Ascending bitonic sort of 32*E keys held E per lane, blocked layout: lane L holds the
+// elements [L*E, L*E+E).  Strides below E are register compare-exchanges, the rest shuffles.
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort(u64 (&key)[E], int lane) {
+  constexpr int N = 32 * E;
+#pragma unroll
+  for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= E) {
+        const int lm = stride / E;
+        const bool lower = (lane & lm) == 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const u64 other = shfl_xor_u64(key[e], lm);
+          const bool up = (((lane * E + e) & size) == 0);
+          const bool keep_min = (lower == up);
+          const u64 mn = key[e] < other ? key[e] : other;
+          const u64 mx = key[e] < other ? other : key[e];
+          key[e] = keep_min ? mn : mx;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          if ((e & stride) == 0) {
+            const bool up = (((lane * E + e) & size) == 0);
+            const u64 a = key[e], b = key[e + stride];
+            const u64 mn = a < b ? a : b;
+            const u64 mx = a < b ? b : a;
+            key[e] = up ? mn : mx;
+            key[e + stride] = up ? mx : mn;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Bitonic MERGE of a sequence that is already bitonic (e.g. elementwise min of an ascending and
+// a descending run): only the last `size = N` pass of the sort network.
+template <int E>
+__device__ __forceinline__ void warp_bitonic_merge(u64 (&key)[E], int lane) {
+  constexpr int N = 32 * E;
+#pragma unroll
+  for (int stride = N >> 1; stride > 0; stride >>= 1) {
+    if (stride >= E) {
+      const int lm = stride / E;
+      const bool lower = (lane & lm) == 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const u64 other = shfl_xor_u64(key[e], lm);
+        const u64 mn = key[e] < other ? key[e] : other;
+        const u64 mx = key[e] < other ? other : key[e];
+        key[e] = lower ? mn : mx;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if ((e & stride) == 0) {
+          const u64 a = key[e], b = key[e + stride];
+          key[e] = a < b ? a : b;
+          key[e + stride] = a < b ? b : a;
+        }
+      }
+    }
+  }
+}
+
+// Warp-cooperative compaction of one row buffer: sort the first n keys, write the best
+// min(n, k) back in ascending order (to `dst`, which may be the buffer itself) and return the
+// new threshold (+inf while fewer than k candidates exist).  All 32 lanes must call it.
+__device__ __forceinline__ float compact_row(const u64* buf, u64* dst, int n, int k, int lane,
+                                             int* kept) {
+  u64 key[kSortE];
+  const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(buf + lane * kSortE);
+#pragma unroll
+  for (int e = 0; e < kSortE; e += 2) {
+    const int idx = lane * kSortE + e;
+    ulonglong2 v = make_ulonglong2(kKeyInf, kKeyInf);
+    if (idx < n) v = __ldcg(b2 + e / 2);
+    key[e] = v.x;
+    key[e + 1] = (idx + 1 < n) ? v.y : kKeyInf;
+  }
+  warp_bitonic_sort<kSortE>(key, lane);
+  const int m = n < k ? n : k;
+#pragma unroll
+  for (int e = 0; e < kSortE; ++e) {
+    const int idx = lane * kSortE + e;
+    if (idx < m) __stcg(dst + idx, key[e]);
+  }
+  u64 kth = kKeyInf;
+#pragma unroll
+  for (int e = 0; e < kSortE; ++e)
+    if (lane * kSortE + e == k - 1) kth = key[e];
+  kth = shfl_u64(kth, (k - 1) / kSortE);
+  *kept = m;
+  return (n >= k) ? key_score(kth) : __int_as_float(0x7f800000);
+}
+
+}  // namespace b2vs
