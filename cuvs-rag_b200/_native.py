@@ -41,7 +41,7 @@ class IvfParams(ctypes.Structure):
 
 class SearchParams(ctypes.Structure):
     _fields_ = [("n_probes", ctypes.c_int32), ("refine_ratio", ctypes.c_int32),
-                ("n_splits", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("n_splits", ctypes.c_int32), ("flags", ctypes.c_int32)]
 
 
 class IndexInfo(ctypes.Structure):
@@ -55,7 +55,8 @@ class IndexInfo(ctypes.Structure):
 class SearchStats(ctypes.Structure):
     _fields_ = [("launches", ctypes.c_int32), ("n_splits", ctypes.c_int32),
                 ("grid", ctypes.c_int32), ("reserved", ctypes.c_int32),
-                ("algo_flops", ctypes.c_double), ("algo_bytes", ctypes.c_double)]
+                ("algo_flops", ctypes.c_double), ("algo_bytes", ctypes.c_double),
+                ("kernel_ms", ctypes.c_double)]
 
 
 # Every symbol include/b2vs.h declares; tests assert the built library exports all of them.
@@ -228,7 +229,7 @@ class NativeIndex:
     # ------------------------------------------------------------------ search
     def search(self, queries: torch.Tensor, k: int, n_probes: int = 0, refine_ratio: int = 0,
                n_splits: int = 0, stream: Optional[torch.cuda.Stream] = None,
-               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, time_kernel: bool = False
                ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Device-resident search: returns (distances f32 [Q,k], ids i64 [Q,k]) on this GPU."""
         if self._h.value is None:
@@ -242,7 +243,7 @@ class NativeIndex:
             i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
         else:
             d, i = out
-        sp = SearchParams(int(n_probes), int(refine_ratio), int(n_splits), 0)
+        sp = SearchParams(int(n_probes), int(refine_ratio), int(n_splits), 1 if time_kernel else 0)
         _check(lib().b2vs_search(self._h, queries.data_ptr(), dtype_code(queries.dtype), nq, int(k),
                                  ctypes.byref(sp), d.data_ptr(), i.data_ptr(),
                                  _stream_ptr(self.device, stream)), "b2vs_search")

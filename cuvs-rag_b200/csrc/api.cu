@@ -95,7 +95,7 @@ extern "C" int b2vs_search(b2vs_index* index, const void* queries, int q_dtype, 
   switch (index->kind) {
     case B2VS_KIND_FLAT:
       return index->flat.search(queries, q_dtype, nq, k, sp.n_splits, index->id_offset, out_d,
-                                out_i, nullptr, st);
+                                out_i, nullptr, st, sp.flags);
     case B2VS_KIND_IVF_FLAT:
     case B2VS_KIND_IVF_PQ:
       return ivf_search(index, queries, q_dtype, nq, k, sp, out_d, out_i, st);
@@ -157,8 +157,13 @@ extern "C" int b2vs_index_info_get(const b2vs_index* index, b2vs_index_info* inf
 
 extern "C" int b2vs_index_last_stats(const b2vs_index* index, b2vs_search_stats* stats) {
   B2VS_CHECK(index && stats, B2VS_EINVAL, "NULL argument");
-  if (index->kind == B2VS_KIND_FLAT) *stats = index->flat.stats;
-  else ivf_last_stats(index, stats);
+  if (index->kind == B2VS_KIND_FLAT) {
+    DeviceGuard guard(index->dev);
+    const_cast<b2vs_index*>(index)->flat.resolve_timing();
+    *stats = index->flat.stats;
+  } else {
+    ivf_last_stats(index, stats);
+  }
   return B2VS_OK;
 }
 

@@ -108,13 +108,19 @@ struct FlatEngine {
   // workspaces (grow-only)
   DevBuf ws_cand, ws_keys, ws_q, ws_qnorm;
   b2vs_search_stats stats{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // optional timing of the dominant kernel
+  bool timing_pending = false;
 
-  int init(int dev, int metric, int dtype, int dim, const void* db, int64_t n, cudaStream_t st);
+  // force_fmt >= 0 with an fp32 source: plain conversion to that 16-bit operand format instead
+  // of the hi/lo split (used for coarse-quantizer centroids, which live in fp32).
+  int init(int dev, int metric, int dtype, int dim, const void* db, int64_t n, cudaStream_t st,
+           int force_fmt = -1);
   // Top-k of queries vs this matrix. out_keys layout is internal; results are written as
   // (dist fp32, id int64 = row + id_offset) when out_d/out_i are given, or as int32 labels
   // (k == 1) when out_label is given.
   int search(const void* q, int q_dtype, int nq, int k, int force_splits, int64_t id_offset,
-             float* out_d, int64_t* out_i, int32_t* out_label, cudaStream_t st);
+             float* out_d, int64_t* out_i, int32_t* out_label, cudaStream_t st, int flags = 0);
+  void resolve_timing();  // fills stats.kernel_ms once the timed launch has finished
   size_t owned_bytes() const { return owned.bytes + beta.bytes; }
   void destroy();
 };
@@ -123,9 +129,10 @@ int encode_tmap_2d(CUtensorMap* tm, const void* base, int ab_format, int64_t row
                    int box_rows);
 
 // merge.cu
+// `remap` (optional) translates key ids (list slots) to shard-local row ids before id_offset.
 int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k, int metric,
                         const float* qnorm, int64_t id_offset, float* out_d, int64_t* out_i,
-                        int32_t* out_label, cudaStream_t st);
+                        int32_t* out_label, cudaStream_t st, const uint32_t* remap = nullptr);
 
 }  // namespace b2vs
 

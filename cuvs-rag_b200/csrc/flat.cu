@@ -166,15 +166,16 @@ int sm_count(int dev) {
 
 // ------------------------------------------------------------------------------------------
 int FlatEngine::init(int dev_, int metric_, int dtype, int dim_, const void* db, int64_t n_,
-                     cudaStream_t st) {
+                     cudaStream_t st, int force_fmt) {
   dev = dev_;
   metric = metric_;
   src_dtype = dtype;
   dim = dim_;
   n = n_;
   const int dp = static_cast<int>(round_up(dim, 8));
-  split3 = (dtype == B2VS_F32);
+  split3 = (dtype == B2VS_F32) && force_fmt < 0;
   ab_format = (dtype == B2VS_F16) ? 0 : 1;
+  if (dtype == B2VS_F32 && force_fmt >= 0) ab_format = force_fmt;
   kdim = split3 ? 3 * dp : dp;
   const int64_t tiles = std::max<int64_t>(1, ceil_div(n, kBN));
   B2VS_TRY(beta.reserve(static_cast<size_t>(tiles) * kBN * sizeof(float)));
@@ -193,7 +194,20 @@ int FlatEngine::init(int dev_, int metric_, int dtype, int dim_, const void* db,
   return B2VS_OK;
 }
 
+void FlatEngine::resolve_timing() {
+  if (!timing_pending || !ev1) return;
+  float ms = 0.f;
+  if (cudaEventSynchronize(ev1) == cudaSuccess && cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess)
+    stats.kernel_ms = ms;
+  else
+    cudaGetLastError();
+  timing_pending = false;
+}
+
 void FlatEngine::destroy() {
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  ev0 = ev1 = nullptr;
   owned.release();
   beta.release();
   ws_cand.release();
@@ -229,7 +243,7 @@ static int choose_splits(int n_qblocks, int64_t tiles, int sms, int k) {
 
 int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_splits,
                        int64_t id_offset, float* out_d, int64_t* out_i, int32_t* out_label,
-                       cudaStream_t st) {
+                       cudaStream_t st, int flags) {
   B2VS_CHECK(nq > 0, B2VS_EINVAL, "nq must be positive (got %d)", nq);
   B2VS_CHECK(k >= 1 && k <= kMaxFusedK, B2VS_EUNSUP,
              "k=%d outside the fused top-k range [1, %d]", k, kMaxFusedK);
@@ -299,8 +313,18 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
 
   B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  kTcSmemBytes));
+  const bool timed = (flags & B2VS_FLAG_TIME_KERNEL) != 0;
+  if (timed) {
+    if (!ev0) {
+      B2VS_CUDA(cudaEventCreate(&ev0));
+      B2VS_CUDA(cudaEventCreate(&ev1));
+    }
+    B2VS_CUDA(cudaEventRecord(ev0, st));
+  }
   bf_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(tm_q, tm_x, p);
   B2VS_CUDA(cudaGetLastError());
+  if (timed) B2VS_CUDA(cudaEventRecord(ev1, st));
+  timing_pending = timed;
   ++launches;
 
   B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits, q_pad, nq, k, metric,

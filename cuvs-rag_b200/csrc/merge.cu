@@ -20,7 +20,8 @@ constexpr int kMergeE = 4;  // 32 * 4 = 128 = kMaxFusedK
 __global__ void merge_splits_kernel(const u64* __restrict__ keys, int n_splits, int q_pad, int nq,
                                     int k, int metric, const float* __restrict__ qnorm,
                                     long long id_offset, float* __restrict__ out_d,
-                                    long long* __restrict__ out_i, int* __restrict__ out_label) {
+                                    long long* __restrict__ out_i, int* __restrict__ out_label,
+                                    const uint32_t* __restrict__ remap) {
   const int lane = threadIdx.x & 31;
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= nq) return;
@@ -50,19 +51,22 @@ __global__ void merge_splits_kernel(const u64* __restrict__ keys, int n_splits, 
     else d = valid ? -sc : -INFINITY;
     const size_t o = static_cast<size_t>(q) * k + i;
     if (out_d) out_d[o] = d;
-    if (out_i) out_i[o] = valid ? static_cast<long long>(key_id(key)) + id_offset : -1ll;
-    if (out_label) out_label[o] = valid ? static_cast<int>(key_id(key)) : -1;
+    uint32_t id = key_id(key);
+    if (valid && remap) id = remap[id];
+    if (out_i) out_i[o] = valid ? static_cast<long long>(id) + id_offset : -1ll;
+    if (out_label) out_label[o] = valid ? static_cast<int>(id) : -1;
   }
 }
 
 int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k, int metric,
                         const float* qnorm, int64_t id_offset, float* out_d, int64_t* out_i,
-                        int32_t* out_label, cudaStream_t st) {
+                        int32_t* out_label, cudaStream_t st, const uint32_t* remap) {
   const int threads = 128;
   const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(nq) * 32, threads));
   merge_splits_kernel<<<blocks, threads, 0, st>>>(keys, n_splits, q_pad, nq, k, metric, qnorm,
                                                   id_offset, out_d,
-                                                  reinterpret_cast<long long*>(out_i), out_label);
+                                                  reinterpret_cast<long long*>(out_i), out_label,
+                                                  remap);
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }

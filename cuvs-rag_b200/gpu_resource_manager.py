@@ -1,0 +1,241 @@
+"""GPUResourceManager — device discovery, validation, row partitioning, streams, communicators.
+
+Drop-in for the reference's ``Attempt_1/gpu_resource_manager.py`` (same class, method and
+dataclass names, same argument meaning and error behaviour; ``test_gpu_resource_manager.py``
+there is the acceptance spec).  B200 additions the reference lacks: one
+non-blocking CUDA stream per device (``get_stream``), and the NCCL process group used for the
+cross-shard exchange (``get_communicator`` — ``torch.distributed`` when the job runs one process
+per GPU under torchrun).
+"""
+from __future__ import annotations
+
+import logging
+import os
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+logger = logging.getLogger(__name__)
+
+
+@dataclass
+class GPUConfig:
+    """What is known about one device (reference: gpu_resource_manager.py:21-28)."""
+    gpu_id: int
+    device_name: str
+    total_memory: int
+    available_memory: int
+    is_available: bool
+
+
+@dataclass
+class MultiGPUConfig:
+    """Snapshot handed to callers that plan a multi-GPU job (reference :31-36)."""
+    available_gpus: List[GPUConfig]
+    primary_gpu: int
+    distribution_strategy: str
+
+
+def partition_even(total_items: int, n_parts: int) -> List[Tuple[int, int]]:
+    """Contiguous near-equal ranges: ``total // n`` rows each, the first ``total % n`` get one more.
+
+    This is the reference's 'even' strategy (gpu_resource_manager.py:190-202) and FAISS
+    ``shard=True``; rank r of a torchrun job owns ``partition_even(N, world)[r]``.
+    """
+    if total_items <= 0:
+        raise ValueError(f"total_items must be positive, got {total_items}")
+    if n_parts <= 0:
+        raise ValueError(f"n_parts must be positive, got {n_parts}")
+    base, extra = divmod(total_items, n_parts)
+    out, start = [], 0
+    for p in range(n_parts):
+        size = base + (1 if p < extra else 0)
+        out.append((start, start + size))
+        start += size
+    return out
+
+
+class GPUResourceManager:
+    """Owns the set of usable GPUs for this process and everything keyed by GPU id."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None):
+        """Discover GPUs. ``devices`` optionally restricts the manager to a subset (e.g. the one
+        device of a torchrun rank: ``GPUResourceManager(devices=[local_rank])``)."""
+        self.available_gpus: List[int] = []
+        self.gpu_memory_info: Dict[int, Dict] = {}
+        self.gpu_configs: List[GPUConfig] = []
+        self._device_filter = None if devices is None else [int(d) for d in devices]
+        self._streams: Dict[int, Any] = {}
+        self._discover_gpus()
+
+    # ------------------------------------------------------------------ discovery
+    def _discover_gpus(self) -> None:
+        try:
+            if not torch.cuda.is_available():
+                logger.warning("CUDA is not available; no GPUs registered")
+                return
+            count = torch.cuda.device_count()
+        except Exception as exc:  # driver trouble is reported, not raised
+            logger.error("GPU discovery failed: %s", exc)
+            return
+        for gid in range(count):
+            if self._device_filter is not None and gid not in self._device_filter:
+                continue
+            try:
+                with torch.cuda.device(gid):
+                    props = torch.cuda.get_device_properties(gid)
+                    total = props.total_memory
+                    torch.cuda.empty_cache()
+                    used = torch.cuda.memory_allocated(gid)
+                free = total - used
+                self.gpu_configs.append(GPUConfig(gid, props.name, total, free, True))
+                self.available_gpus.append(gid)
+                self.gpu_memory_info[gid] = {"total": total, "available": free, "allocated": used}
+            except Exception as exc:
+                logger.warning("GPU %d cannot be used: %s", gid, exc)
+                self.gpu_configs.append(GPUConfig(gid, "Unknown", 0, 0, False))
+
+    # ------------------------------------------------------------------ validation
+    def validate_gpu_index(self, gpu_id: int) -> bool:
+        """True only for a non-negative id that was discovered AND still exists in the driver."""
+        try:
+            if not isinstance(gpu_id, int) or isinstance(gpu_id, bool) or gpu_id < 0:
+                return False
+            if gpu_id not in self.available_gpus:
+                return False
+            if not torch.cuda.is_available():
+                return False
+            return gpu_id < torch.cuda.device_count()
+        except Exception as exc:
+            logger.error("validating GPU %s failed: %s", gpu_id, exc)
+            return False
+
+    def get_safe_device_string(self, gpu_id: int) -> str:
+        if not self.validate_gpu_index(gpu_id):
+            raise ValueError(f"Invalid GPU index: {gpu_id}. Available GPUs: {self.available_gpus}")
+        return f"cuda:{gpu_id}"
+
+    def get_available_gpu_count(self) -> int:
+        return len(self.available_gpus)
+
+    def get_available_gpu_ids(self) -> List[int]:
+        return list(self.available_gpus)
+
+    # ------------------------------------------------------------------ partitioning
+    def distribute_workload(self, total_items: int, strategy: str = "even",
+                            gpu_ids: Optional[Sequence[int]] = None) -> List[Tuple[int, int, int]]:
+        """Split ``total_items`` rows over the GPUs as ``[(gpu_id, start, end)]``.
+
+        'even' gives contiguous near-equal ranges; 'memory_based' sizes ranges by each GPU's free
+        bytes.  ``gpu_ids`` restricts the split to a subset — the split is computed over THAT
+        subset so the ranges always cover [0, total_items) (the reference computes over all GPUs
+        and then filters, leaving holes: SURVEY.md §3.6 bug 2).
+        """
+        gpus = list(self.available_gpus) if gpu_ids is None else [int(g) for g in gpu_ids]
+        if not gpus:
+            raise RuntimeError("No GPUs available for workload distribution")
+        if total_items <= 0:
+            raise ValueError(f"total_items must be positive, got {total_items}")
+        if strategy == "even":
+            return [(g, s, e) for g, (s, e) in zip(gpus, partition_even(total_items, len(gpus)))]
+        if strategy == "memory_based":
+            weights = [float(self.gpu_memory_info.get(g, {}).get("available", 0)) for g in gpus]
+            if sum(weights) <= 0:
+                return self.distribute_workload(total_items, "even", gpus)
+            out, start, acc = [], 0, 0.0
+            wsum = sum(weights)
+            for pos, (g, w) in enumerate(zip(gpus, weights)):
+                acc += w
+                end = total_items if pos == len(gpus) - 1 else int(round(total_items * acc / wsum))
+                end = max(end, start)
+                out.append((g, start, end))
+                start = end
+            return out
+        raise ValueError(f"Unknown distribution strategy: {strategy}")
+
+    # ------------------------------------------------------------------ lifecycle
+    def cleanup_gpu_resources(self, gpu_ids: Optional[List[int]] = None) -> None:
+        """Release cached allocator blocks and drain outstanding work on the given GPUs."""
+        for gid in (self.available_gpus if gpu_ids is None else gpu_ids):
+            if not self.validate_gpu_index(gid):
+                logger.warning("cleanup skipped for invalid GPU %s", gid)
+                continue
+            try:
+                with torch.cuda.device(gid):
+                    torch.cuda.empty_cache()
+                    torch.cuda.synchronize()
+            except Exception as exc:
+                logger.error("cleanup of GPU %d failed: %s", gid, exc)
+
+    def get_gpu_memory_info(self, gpu_id: int) -> Dict[str, int]:
+        if not self.validate_gpu_index(gpu_id):
+            raise ValueError(f"Invalid GPU index: {gpu_id}. Available GPUs: {self.available_gpus}")
+        with torch.cuda.device(gpu_id):
+            allocated = torch.cuda.memory_allocated(gpu_id)
+            reserved = torch.cuda.memory_reserved(gpu_id)
+            total = torch.cuda.get_device_properties(gpu_id).total_memory
+        return {"allocated": allocated, "reserved": reserved, "total": total,
+                "free": total - reserved}
+
+    def get_multi_gpu_config(self, distribution_strategy: str = "even") -> MultiGPUConfig:
+        usable = [c for c in self.gpu_configs if getattr(c, "is_available", False)]
+        primary = self.available_gpus[0] if self.available_gpus else -1
+        return MultiGPUConfig(usable, primary, distribution_strategy)
+
+    def validate_tensor_distribution(self, tensor_parts: List[Any]) -> bool:
+        """One tensor per available GPU, in GPU order, each on its GPU."""
+        if len(tensor_parts) != len(self.available_gpus):
+            logger.error("%d tensor parts for %d GPUs", len(tensor_parts), len(self.available_gpus))
+            return False
+        for gid, t in zip(self.available_gpus, tensor_parts):
+            if getattr(getattr(t, "device", None), "index", None) != gid:
+                logger.error("tensor part for GPU %d lives on %s", gid, getattr(t, "device", None))
+                return False
+        return True
+
+    # ------------------------------------------------------------------ B200 additions
+    def get_stream(self, gpu_id: int):
+        """The manager's non-blocking stream for ``gpu_id`` (created on first use)."""
+        if not self.validate_gpu_index(gpu_id):
+            raise ValueError(f"Invalid GPU index: {gpu_id}. Available GPUs: {self.available_gpus}")
+        s = self._streams.get(gpu_id)
+        if s is None:
+            s = torch.cuda.Stream(device=gpu_id)
+            self._streams[gpu_id] = s
+        return s
+
+    def get_communicator(self):
+        """The NCCL process group for the cross-shard exchange, or None in single-process mode.
+
+        Under torchrun (one process per GPU) this initialises ``torch.distributed`` with the NCCL
+        backend on first use; ``gloo`` is used when CUDA is absent so the host logic is testable.
+        """
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist.group.WORLD
+        if "RANK" in os.environ and "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+            kwargs = {}
+            if backend == "nccl" and self.available_gpus:
+                kwargs["device_id"] = torch.device(f"cuda:{self.available_gpus[0]}")
+            dist.init_process_group(backend=backend, **kwargs)
+            return dist.group.WORLD
+        return None
+
+    def get_rank_info(self) -> Tuple[int, int]:
+        """(rank, world_size) of this process in the sharded job; (0, 1) when not distributed."""
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
+
+    def __str__(self) -> str:
+        return (f"GPUResourceManager(available_gpus={self.available_gpus}, "
+                f"gpu_count={len(self.available_gpus)})")
+
+    def __repr__(self) -> str:
+        return (f"GPUResourceManager(available_gpus={self.available_gpus}, "
+                f"gpu_configs={len(self.gpu_configs)})")

@@ -69,8 +69,9 @@ typedef struct b2vs_search_params {
   int32_t n_probes;       /* IVF: lists scanned per query (cuVS SearchParams.n_probes, default 20) */
   int32_t refine_ratio;   /* IVF-PQ: exact re-rank of refine_ratio*k candidates (0/1 = off) */
   int32_t n_splits;       /* flat: force the number of db splits (0 = heuristic) */
-  int32_t reserved;
+  int32_t flags;          /* bit 0: time the dominant kernel with CUDA events (see stats.kernel_ms) */
 } b2vs_search_params;
+#define B2VS_FLAG_TIME_KERNEL 1
 
 typedef struct b2vs_index_info {
   int32_t kind, device, metric, dtype, dim, n_lists, pq_dim, pq_bits;
@@ -86,6 +87,8 @@ typedef struct b2vs_search_stats {
   int32_t reserved;
   double algo_flops;       /* 2*Q*N*D for the distance contraction (flat / coarse) */
   double algo_bytes;       /* IVF: sum of probed list bytes actually scanned */
+  double kernel_ms;        /* device time of the dominant kernel (fused distance / list scan) when
+                              B2VS_FLAG_TIME_KERNEL was set, else 0 */
 } b2vs_search_stats;
 
 const char* b2vs_last_error(void);
