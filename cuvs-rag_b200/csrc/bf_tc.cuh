@@ -4,16 +4,26 @@
 // `ivf_flat.search` / `IndexFlat*.search` at the reference call sites
 // (improved_multi_gpu_rag.py:225-233, cuvs-2gpu-main.ipynb:L1801, faiss-main.ipynb cell 9).
 //
-// Work decomposition: item = (db split s, query block qb); a query block is 128 queries (the
-// 128 TMEM lanes), a db tile is 256 rows (256 fp32 TMEM columns), two accumulator buffers fill
-// the 512 TMEM columns so the epilogue of tile t overlaps the MMAs of tile t+1.  Items are
-// ordered split-major so the CTAs resident at one time stream the SAME db rows against
-// different query blocks and the db is read from HBM about once per batch (L2 serves the rest).
+// Work decomposition: item = (db split s, query block qb).  A db tile is 256 rows (256 fp32 TMEM
+// columns); two accumulator buffers fill the 512 TMEM columns so the epilogue of tile t overlaps
+// the MMAs of tile t+1.  Items are ordered split-major so the CTAs resident at one time stream
+// the SAME db rows against different query blocks and the db is read from HBM about once per
+// batch (L2 serves the rest).
+//
+// Two instantiations:
+//   G = 1  one CTA per item, query block = 128 rows, UMMA 128x256x16 (cta_group::1),
+//          4 smem stages of (16 KB queries + 32 KB db).
+//   G = 2  one CTA PAIR (cluster of 2, cta_group::2) per item, query block = 256 rows, UMMA
+//          256x256x16: each CTA stages its own 128 query rows and HALF of the db tile, so the
+//          L2->smem traffic and the smem operand reads per FLOP drop by a third / a half;
+//          6 smem stages of (16 KB + 16 KB).  The leader CTA issues the MMAs; barriers that
+//          gate it (smem full, accumulator empty) live in the leader and are signalled by both
+//          CTAs, barriers it releases (smem empty, accumulator full) are multicast to both.
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread),
-// warp 2 = TMEM allocator, warps 4-7 = epilogue (thread i of warp w owns query row 32*(w-4)+i).
-// The epilogue never writes distances to HBM: score = alpha*acc + beta[col] is compared with the
-// row's threshold and only candidates go to the row buffer (see topk.cuh).
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (thread i of warp w owns TMEM lane 32*(w-4)+i =
+// one query row).  The epilogue never writes distances to HBM: score = alpha*acc + beta[col] is
+// compared with the row's threshold and only candidates go to the row buffer (see topk.cuh).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -24,23 +34,27 @@
 
 namespace b2vs {
 
-constexpr int kBM = 128;
-constexpr int kBN = 256;
-constexpr int kBK = 64;
-constexpr int kStages = 4;
-constexpr int kABytes = kBM * kBK * 2;
-constexpr int kBBytes = kBN * kBK * 2;
-constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kBM = 128;   // query rows per CTA (TMEM lanes)
+constexpr int kBN = 256;   // db rows per tile (TMEM columns)
+constexpr int kBK = 64;    // K elements per smem stage (one 128-byte swizzle atom)
 constexpr int kNormBytes = kBN * 4;
 constexpr int kTcThreads = 256;
-constexpr int kTcSmemBytes = kStages * kStageBytes + 2 * kNormBytes + 256 + 1024;
+
+template <int G> struct TcCfg {
+  static constexpr int kBRows = kBN / G;                     // db rows staged by one CTA
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = kBRows * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (G == 1) ? 4 : 6;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kNormBytes + 256 + 1024;
+};
 
 struct BfTcParams {
   const float* beta;    // [tiles_total*256] per db row additive term (||x||^2, 0, +inf on padding)
   u64* cand;            // [grid][128][kCap] candidate buffers
   u64* out_keys;        // [n_splits][q_pad][k] sorted ascending, kKeyInf padded
-  int n_qblocks;        // ceil(nq / 128)
-  int q_pad;            // n_qblocks * 128
+  int n_qblocks;        // ceil(nq / (128*G))
+  int q_pad;            // n_qblocks * 128 * G
   int n_items;          // n_qblocks * n_splits
   int tiles_total;      // ceil(n_db / 256)
   int tiles_per_split;
@@ -50,40 +64,46 @@ struct BfTcParams {
   uint32_t idesc;
 };
 
+template <int G>
 __global__ void __launch_bounds__(kTcThreads, 1)
 bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
              const BfTcParams p) {
+  using Cfg = TcCfg<G>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kStageBytes = Cfg::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
-  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
+  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;   // same offset in both CTAs of a pair
   uint8_t* smem = smem_raw + (smem_base - raw_addr);
 
   const uint32_t norm_base = smem_base + kStages * kStageBytes;
   const float* norm_ptr = reinterpret_cast<const float*>(smem + kStages * kStageBytes);
   const uint32_t bar_base = norm_base + 2 * kNormBytes;
   // barrier slots (8 bytes each)
-  const uint32_t bar_full = bar_base;                     // [kStages] TMA -> MMA
-  const uint32_t bar_empty = bar_base + 8 * kStages;      // [kStages] MMA -> TMA
-  const uint32_t bar_acc_full = bar_base + 16 * kStages;  // [2] MMA -> epilogue
-  const uint32_t bar_acc_empty = bar_acc_full + 16;       // [2] epilogue -> MMA
-  const uint32_t bar_norm_full = bar_acc_full + 32;       // [2] TMA -> epilogue
-  const uint32_t bar_norm_empty = bar_acc_full + 48;      // [2] epilogue -> TMA
+  const uint32_t bar_full = bar_base;                     // [kStages] TMA -> MMA   (leader's is used)
+  const uint32_t bar_empty = bar_base + 8 * kStages;      // [kStages] MMA -> TMA   (per CTA)
+  const uint32_t bar_acc_full = bar_base + 16 * kStages;  // [2] MMA -> epilogue    (per CTA)
+  const uint32_t bar_acc_empty = bar_acc_full + 16;       // [2] epilogue -> MMA    (leader's is used)
+  const uint32_t bar_norm_full = bar_acc_full + 32;       // [2] TMA -> epilogue    (per CTA)
+  const uint32_t bar_norm_empty = bar_acc_full + 48;      // [2] epilogue -> TMA    (per CTA)
   const uint32_t tmem_slot = bar_acc_full + 64;
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + kStages * kStageBytes + 2 * kNormBytes +
-                                           16 * kStages + 64);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem + kStages * kStageBytes + 2 * kNormBytes + 16 * kStages + 64);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (G == 2) ? ptx::cluster_ctarank() : 0u;
+  const int unit = (G == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_units = (G == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      ptx::mbar_init(bar_full + 8 * i, 1);
+      ptx::mbar_init(bar_full + 8 * i, G);          // one arrive(+tx) per CTA of the pair
       ptx::mbar_init(bar_empty + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(bar_acc_full + 8 * i, 1);
-      ptx::mbar_init(bar_acc_empty + 8 * i, 4);
+      ptx::mbar_init(bar_acc_empty + 8 * i, 4 * G);  // every epilogue warp of the pair
       ptx::mbar_init(bar_norm_full + 8 * i, 1);
       ptx::mbar_init(bar_norm_empty + 8 * i, 4);
     }
@@ -92,11 +112,16 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     ptx::prefetch_tmap(&tm_x);
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
+    if (G == 2) {
+      ptx::tmem_alloc_2sm(tmem_slot, 512);
+      ptx::tmem_relinquish_2sm();
+    } else {
+      ptx::tmem_alloc(tmem_slot, 512);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (G == 2) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -104,33 +129,43 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, tcount = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const uint32_t full_leader = (G == 2) ? ptx::mapa_cluster(bar_full, 0) : bar_full;
+      for (int item = unit; item < p.n_items; item += n_units) {
         const int qb = item % p.n_qblocks;
         const int s = item / p.n_qblocks;
         const int t0 = s * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
+        const int q_row0 = qb * (kBM * G) + static_cast<int>(cta_rank) * kBM;
         for (int t = t0; t < t1; ++t, ++tcount) {
           const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
           ptx::mbar_wait(bar_norm_empty + 8 * as, aph ^ 1u);
           ptx::mbar_arrive_expect_tx(bar_norm_full + 8 * as, kNormBytes);
           ptx::bulk_load_1d(norm_base + as * kNormBytes, p.beta + static_cast<size_t>(t) * kBN,
                             kNormBytes, bar_norm_full + 8 * as);
+          const int x_row0 = t * kBN + static_cast<int>(cta_rank) * Cfg::kBRows;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
             const uint32_t a_dst = smem_base + stage * kStageBytes;
-            ptx::tma_load_2d(a_dst, &tm_q, bar_full + 8 * stage, kb * kBK, qb * kBM);
-            ptx::tma_load_2d(a_dst + kABytes, &tm_x, bar_full + 8 * stage, kb * kBK, t * kBN);
+            if (G == 2) {
+              const uint32_t fb = full_leader + 8 * stage;
+              ptx::mbar_arrive_expect_tx_cluster(fb, kStageBytes);
+              ptx::tma_load_2d_2sm(a_dst, &tm_q, fb, kb * kBK, q_row0);
+              ptx::tma_load_2d_2sm(a_dst + Cfg::kABytes, &tm_x, fb, kb * kBK, x_row0);
+            } else {
+              ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
+              ptx::tma_load_2d(a_dst, &tm_q, bar_full + 8 * stage, kb * kBK, q_row0);
+              ptx::tma_load_2d(a_dst + Cfg::kABytes, &tm_x, bar_full + 8 * stage, kb * kBK, x_row0);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    if (lane == 0 && cta_rank == 0) {
       uint32_t stage = 0, phase = 0, tcount = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int item = unit; item < p.n_items; item += n_units) {
         const int s = item / p.n_qblocks;
         const int t0 = s * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
@@ -143,30 +178,36 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             ptx::mbar_wait(bar_full + 8 * stage, phase);
             ptx::tc_fence_after();
             const uint32_t a_addr = smem_base + stage * kStageBytes;
-            const uint32_t b_addr = a_addr + kABytes;
+            const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
             for (int kk = 0; kk < kBK / 16; ++kk) {
               const uint64_t adesc = ptx::make_kmajor_sw128_desc(a_addr + kk * 32);
               const uint64_t bdesc = ptx::make_kmajor_sw128_desc(b_addr + kk * 32);
-              ptx::umma_f16(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+              if (G == 2) ptx::umma_f16_2sm(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+              else ptx::umma_f16(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
             }
-            ptx::umma_commit(bar_empty + 8 * stage);  // smem slot reusable once these MMAs retire
+            // smem slot reusable (in both CTAs) once these MMAs retire
+            if (G == 2) ptx::umma_commit_2sm(bar_empty + 8 * stage, 0x3);
+            else ptx::umma_commit(bar_empty + 8 * stage);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          ptx::umma_commit(bar_acc_full + 8 * as);    // accumulator ready for the epilogue
+          // accumulator ready for the epilogue warps (of both CTAs)
+          if (G == 2) ptx::umma_commit_2sm(bar_acc_full + 8 * as, 0x3);
+          else ptx::umma_commit(bar_acc_full + 8 * as);
         }
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     const int ew = warp - 4;                // TMEM lane quarter == warp % 4
-    const int row = ew * 32 + lane;         // query row inside the block
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
     u64* const cand_warp = p.cand + (static_cast<size_t>(blockIdx.x) * kBM + ew * 32) * kCap;
     u64* const my_cand = cand_warp + static_cast<size_t>(lane) * kCap;
+    const uint32_t acc_empty_leader =
+        (G == 2) ? ptx::mapa_cluster(bar_acc_empty, 0) : bar_acc_empty;
     const float inf = __int_as_float(0x7f800000);
     uint32_t tcount = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    for (int item = unit; item < p.n_items; item += n_units) {
       const int qb = item % p.n_qblocks;
       const int s = item / p.n_qblocks;
       const int t0 = s * p.tiles_per_split;
@@ -222,7 +263,8 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              ptx::mbar_arrive(bar_acc_empty + 8 * as);
+              if (G == 2) ptx::mbar_arrive_cluster(acc_empty_leader + 8 * as);
+              else ptx::mbar_arrive(bar_acc_empty + 8 * as);
               ptx::mbar_arrive(bar_norm_empty + 8 * as);
             }
           }
@@ -242,7 +284,8 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         }
       }
       // ---- item done: emit this (split, query block)'s sorted top-k keys
-      u64* out_blk = p.out_keys + (static_cast<size_t>(s) * p.q_pad + qb * kBM + ew * 32) * p.k;
+      const size_t q_row0 = static_cast<size_t>(qb) * (kBM * G) + cta_rank * kBM + ew * 32;
+      u64* out_blk = p.out_keys + (static_cast<size_t>(s) * p.q_pad + q_row0) * p.k;
       if (p.k == 1) {
         out_blk[lane] = best;
       } else {
@@ -256,15 +299,16 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         }
         __syncwarp();
       }
-      (void)row;
     }
   }
 
+  __syncwarp();  // role branches above are per-lane: reconverge before the aligned barrier
   ptx::tc_fence_before();
-  __syncthreads();
+  if (G == 2) ptx::cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if (G == 2) ptx::tmem_dealloc_2sm(tmem_base, 512);
+    else ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 

@@ -104,7 +104,8 @@ struct FlatEngine {
   const void* mat = nullptr;  // operand matrix used by TMA (borrowed or == owned.ptr)
   DevBuf owned;               // owned re-encoding, if any
   DevBuf beta;                // [tiles*256] float: ||x||^2 (L2) or 0 (IP); +inf on padding
-  CUtensorMap tm_x;
+  CUtensorMap tm_x;       // db map, box = 256 rows (single-CTA kernel)
+  CUtensorMap tm_x_half;  // db map, box = 128 rows (CTA-pair kernel: each CTA stages half a tile)
   // workspaces (grow-only)
   DevBuf ws_cand, ws_keys, ws_q, ws_qnorm;
   b2vs_search_stats stats{};

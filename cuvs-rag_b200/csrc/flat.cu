@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 
 #include "bf_tc.cuh"
@@ -179,7 +180,9 @@ int FlatEngine::init(int dev_, int metric_, int dtype, int dim_, const void* db,
   kdim = split3 ? 3 * dp : dp;
   const int64_t tiles = std::max<int64_t>(1, ceil_div(n, kBN));
   B2VS_TRY(beta.reserve(static_cast<size_t>(tiles) * kBN * sizeof(float)));
-  const bool borrow = !split3 && dp == dim && (reinterpret_cast<uintptr_t>(db) & 15) == 0;
+  // only a 16-bit source already in the operand format can be used in place
+  const bool borrow =
+      dtype != B2VS_F32 && dp == dim && (reinterpret_cast<uintptr_t>(db) & 15) == 0;
   uint16_t* out = nullptr;
   if (!borrow) {
     B2VS_TRY(owned.reserve(static_cast<size_t>(std::max<int64_t>(n, 1)) * kdim * 2));
@@ -190,7 +193,10 @@ int FlatEngine::init(int dev_, int metric_, int dtype, int dim_, const void* db,
   }
   B2VS_TRY(launch_prep(db, dtype, n, dim, dp, split3 ? 1 : 0, ab_format, out, beta.as<float>(),
                        metric == B2VS_METRIC_L2 ? 1 : 0, tiles * kBN, st));
-  if (n > 0) B2VS_TRY(encode_tmap_2d(&tm_x, mat, ab_format, n, kdim, kBN));
+  if (n > 0) {
+    B2VS_TRY(encode_tmap_2d(&tm_x, mat, ab_format, n, kdim, kBN));           // G = 1: whole tile
+    B2VS_TRY(encode_tmap_2d(&tm_x_half, mat, ab_format, n, kdim, kBN / 2));  // G = 2: half per CTA
+  }
   return B2VS_OK;
 }
 
@@ -223,6 +229,18 @@ __global__ void fill_missing_kernel(float* out_d, int64_t* out_i, int32_t* out_l
   if (out_d) out_d[i] = dval;
   if (out_i) out_i[i] = -1;
   if (out_label) out_label[i] = -1;
+}
+
+constexpr int kDefaultTcGroup = 1;
+
+// B2VS_TC_GROUP=1|2 forces the single-CTA / CTA-pair kernel (bring-up and A/B measurements).
+static int tc_group_override() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = std::getenv("B2VS_TC_GROUP");
+    cached = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
+  }
+  return cached;
 }
 
 // Number of db splits: minimise waves * (tiles per split + fixed per-item cost in tile units).
@@ -259,8 +277,14 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   }
   const int dp = static_cast<int>(round_up(dim, 8));
   const int want_norm = (metric == B2VS_METRIC_L2) ? 1 : 0;
-  const int n_qblocks = static_cast<int>(ceil_div(nq, kBM));
-  const int q_pad = n_qblocks * kBM;
+  // CTA-pair (cta_group::2) kernel for batches that fill a 256-row query block, else single CTA
+  int group = tc_group_override();
+  if (group == 0) group = (nq > kBM) ? kDefaultTcGroup : 1;
+  if (flags & B2VS_FLAG_TC_SINGLE) group = 1;
+  if (flags & B2VS_FLAG_TC_PAIR) group = 2;
+  const int qrows = kBM * group;
+  const int n_qblocks = static_cast<int>(ceil_div(nq, qrows));
+  const int q_pad = n_qblocks * qrows;
   int launches = 0;
 
   // ---- query operand + norms
@@ -270,7 +294,6 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   B2VS_TRY(ws_qnorm.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
   const void* q_mat = q;
   if (!borrow_q) {
-    B2VS_CHECK(!(split3 && q_dtype != B2VS_F32) || true, B2VS_EINVAL, "unreachable");
     B2VS_TRY(ws_q.reserve(static_cast<size_t>(nq) * kdim * 2));
     q_mat = ws_q.ptr;
     B2VS_TRY(launch_prep(q, q_dtype, nq, dim, dp, split3 ? 2 : 0, ab_format, ws_q.as<uint16_t>(),
@@ -286,13 +309,14 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
 
   // ---- decomposition
   const int sms = sm_count(dev);
+  const int units = std::max(1, sms / group);  // CTAs (G=1) or CTA pairs (G=2) that run at once
   const int64_t tiles = ceil_div(n, kBN);
   int n_splits = force_splits > 0 ? static_cast<int>(std::min<int64_t>(force_splits, tiles))
-                                  : choose_splits(n_qblocks, tiles, sms, k);
+                                  : choose_splits(n_qblocks, tiles, units, k);
   const int tps = static_cast<int>(ceil_div(tiles, n_splits));
   n_splits = static_cast<int>(ceil_div(tiles, tps));
   const int n_items = n_qblocks * n_splits;
-  const int grid = std::min(n_items, sms);
+  const int grid = std::min(n_items, units) * group;
 
   B2VS_TRY(ws_cand.reserve(static_cast<size_t>(grid) * kBM * kCap * sizeof(u64)));
   B2VS_TRY(ws_keys.reserve(static_cast<size_t>(n_splits) * q_pad * k * sizeof(u64)));
@@ -309,10 +333,8 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   p.k_blocks = static_cast<int>(ceil_div(kdim, kBK));
   p.k = k;
   p.alpha = (metric == B2VS_METRIC_L2) ? -2.f : -1.f;
-  p.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(ab_format), kBM, kBN);
+  p.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(ab_format), qrows, kBN);
 
-  B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kTcSmemBytes));
   const bool timed = (flags & B2VS_FLAG_TIME_KERNEL) != 0;
   if (timed) {
     if (!ev0) {
@@ -321,7 +343,27 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
     }
     B2VS_CUDA(cudaEventRecord(ev0, st));
   }
-  bf_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(tm_q, tm_x, p);
+  if (group == 1) {
+    B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TcCfg<1>::kSmemBytes));
+    bf_tc_kernel<1><<<grid, kTcThreads, TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_x, p);
+  } else {
+    B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TcCfg<2>::kSmemBytes));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = TcCfg<2>::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2VS_CUDA(cudaLaunchKernelEx(&cfg, bf_tc_kernel<2>, tm_q, tm_x_half, p));
+  }
   B2VS_CUDA(cudaGetLastError());
   if (timed) B2VS_CUDA(cudaEventRecord(ev1, st));
   timing_pending = timed;

@@ -131,6 +131,37 @@ def _merge_arrays(dist_list: List[np.ndarray], idx_list: List[np.ndarray], k: in
     return _host_merge(dist_list, idx_list, k, descending)
 
 
+def allgather_and_merge(d_all: torch.Tensor, i_all: torch.Tensor, k: int, descending: bool = False,
+                        world_size: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exchange step of the sharded search: ``d_all`` / ``i_all`` are this process's
+    [n_local_shards, Q, k'] results (ids already global).  With ``world_size > 1`` (one process per
+    GPU under torchrun) every rank all-gathers the other ranks' lists — NCCL over NVLink for CUDA
+    tensors — and then merges; the merge is ``b2vs_merge_topk`` (K8) on the GPU.  CPU tensors take
+    the gloo + host-merge route, which exists only so the N>1 host logic is testable without GPUs.
+    """
+    nq = d_all.shape[1]
+    if world_size > 1:
+        import torch.distributed as dist
+        g_d = torch.empty((world_size,) + tuple(d_all.shape), dtype=d_all.dtype, device=d_all.device)
+        g_i = torch.empty((world_size,) + tuple(i_all.shape), dtype=i_all.dtype, device=i_all.device)
+        if d_all.is_cuda:
+            dist.all_gather_into_tensor(g_d, d_all.contiguous())
+            dist.all_gather_into_tensor(g_i, i_all.contiguous())
+        else:
+            dist.all_gather(list(g_d.unbind(0)), d_all.contiguous())
+            dist.all_gather(list(g_i.unbind(0)), i_all.contiguous())
+        d_all = g_d.reshape(-1, nq, d_all.shape[-1])
+        i_all = g_i.reshape(-1, nq, i_all.shape[-1])
+    if d_all.shape[0] == 1 and d_all.shape[2] == k:
+        return d_all[0], i_all[0]                    # single shard: already the global top-k
+    k_eff = min(k, d_all.shape[0] * d_all.shape[2])
+    if d_all.is_cuda:
+        return _native.merge_topk(d_all, i_all, k_eff, descending)
+    md, mi = _host_merge([x.numpy() for x in d_all.unbind(0)], [x.numpy() for x in i_all.unbind(0)],
+                         k_eff, descending)
+    return torch.from_numpy(md), torch.from_numpy(mi)
+
+
 class SearchResultAggregator:
     def __init__(self, gpu_manager: GPUResourceManager):
         if gpu_manager is None or not hasattr(gpu_manager, "validate_gpu_index"):
@@ -263,22 +294,7 @@ class SearchResultAggregator:
                 torch.cuda.current_stream(primary).wait_stream(torch.cuda.current_stream(r[0].device))
         d_all = torch.stack(d_parts) if len(d_parts) > 1 else d_parts[0].unsqueeze(0)
         i_all = torch.stack(i_parts) if len(i_parts) > 1 else i_parts[0].unsqueeze(0)
-        rank, world = self.gpu_manager.get_rank_info() if hasattr(self.gpu_manager, "get_rank_info") else (0, 1)
-        if not isinstance(world, int):
-            world = 1
-        if world > 1:
-            import torch.distributed as dist
-            g_d = torch.empty((world,) + tuple(d_all.shape), dtype=d_all.dtype, device=primary)
-            g_i = torch.empty((world,) + tuple(i_all.shape), dtype=i_all.dtype, device=primary)
-            dist.all_gather_into_tensor(g_d, d_all.contiguous())
-            dist.all_gather_into_tensor(g_i, i_all.contiguous())
-            d_all = g_d.view(-1, nq, d_all.shape[-1])
-            i_all = g_i.view(-1, nq, i_all.shape[-1])
-        if d_all.shape[0] == 1 and d_all.shape[2] == k:
-            out_d, out_i = d_all[0], i_all[0]        # single shard: already the global top-k
-        else:
-            out_d, out_i = _native.merge_topk(d_all, i_all, min(k, d_all.shape[0] * d_all.shape[2]),
-                                              descending)
+        out_d, out_i = allgather_and_merge(d_all, i_all, k, descending, self._world_size())
         final_d = out_d.cpu().numpy()
         final_i = out_i.cpu().numpy()
         gpu_results = []
@@ -290,6 +306,13 @@ class SearchResultAggregator:
                 gpu_results.append(SearchResult(np.empty((nq, 0), np.float32),
                                                 np.empty((nq, 0), np.int64), g, secs, k_local, 0))
         return final_d, final_i, gpu_results
+
+    def _world_size(self) -> int:
+        try:
+            _, world = self.gpu_manager.get_rank_info()
+            return int(world) if isinstance(world, int) else 1
+        except Exception:
+            return 1
 
     # ------------------------------------------------------------------ bookkeeping
     def get_search_history(self) -> List[AggregatedSearchResult]:

@@ -72,6 +72,8 @@ typedef struct b2vs_search_params {
   int32_t flags;          /* bit 0: time the dominant kernel with CUDA events (see stats.kernel_ms) */
 } b2vs_search_params;
 #define B2VS_FLAG_TIME_KERNEL 1
+#define B2VS_FLAG_TC_SINGLE 2   /* flat: force the single-CTA (cta_group::1) kernel */
+#define B2VS_FLAG_TC_PAIR 4     /* flat: force the CTA-pair (cta_group::2) kernel */
 
 typedef struct b2vs_index_info {
   int32_t kind, device, metric, dtype, dim, n_lists, pq_dim, pq_bits;

@@ -1,0 +1,161 @@
+"""ORACLE — test infrastructure only.  CPU restatement of IVF-Flat / IVF-PQ semantics.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs may import this.
+
+Parity status: **unpinned** — the reference holds no golden ids / recall for its
+``cuvs.neighbors.ivf_flat`` / ``ivf_pq`` calls (``index_building_coordinator.py:392-404``,
+``improved_multi_gpu_rag.py:126-138, 225-233``); cuVS 25.06 itself is an un-vendored wheel
+(``Attempt_1/pip-requirements.txt:9``).  This file restates the published algorithm those calls
+implement, and the GPU path is compared with it through recall at identical
+``n_lists`` / ``n_probes`` (the north-star criterion), not bit-for-bit (k-means is seeded
+differently and sums in a different order):
+
+* coarse quantizer: Lloyd k-means (``kmeans_n_iters`` iterations, default 20) on a strided
+  subsample (``kmeans_trainset_fraction``, default 0.5), then every row joins its nearest
+  centroid's list;
+* IVF-Flat search: the ``n_probes`` best centroids per query (default 20), exact distances to
+  every row of those lists, best k;
+* IVF-PQ: residual to the list centroid, split in ``pq_dim`` sub-vectors, 256-entry codebook per
+  sub-space (k-means on residual sub-vectors), asymmetric distance via a per-(query, list) table.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+
+def kmeans(x: torch.Tensor, n_clusters: int, iters: int = 20, seed: int = 0) -> torch.Tensor:
+    x = x.to(torch.float32)
+    n = x.shape[0]
+    g = torch.Generator().manual_seed(seed)
+    cent = x[torch.randperm(n, generator=g)[:n_clusters]].clone()
+    for it in range(iters):
+        lab = assign(x, cent)
+        sums = torch.zeros_like(cent).index_add_(0, lab, x)
+        cnt = torch.bincount(lab, minlength=n_clusters).to(torch.float32)
+        empty = cnt == 0
+        cent = sums / cnt.clamp_min(1.0)[:, None]
+        if empty.any():
+            repl = torch.randint(0, n, (int(empty.sum()),), generator=g)
+            cent[empty] = x[repl]
+    return cent
+
+
+def assign(x: torch.Tensor, cent: torch.Tensor, block: int = 65536) -> torch.Tensor:
+    cn = (cent * cent).sum(1)
+    out = torch.empty(x.shape[0], dtype=torch.int64)
+    for s in range(0, x.shape[0], block):
+        xb = x[s:s + block].to(torch.float32)
+        out[s:s + block] = (cn[None, :] - 2.0 * (xb @ cent.T)).argmin(1)
+    return out
+
+
+class IvfFlatOracle:
+    def __init__(self, db: torch.Tensor, n_lists: int, metric: str = "sqeuclidean",
+                 iters: int = 20, train_fraction: float = 0.5, seed: int = 0):
+        self.metric = metric
+        self.db = db.to(torch.float32)
+        stride = max(1, int(1.0 / train_fraction + 1e-6))
+        train = self.db[::stride]
+        if train.shape[0] < n_lists:
+            train = self.db
+        self.cent = kmeans(train, n_lists, iters, seed)
+        self.labels = assign(self.db, self.cent)
+        order = torch.argsort(self.labels, stable=True)
+        self.order = order
+        counts = torch.bincount(self.labels, minlength=n_lists)
+        self.offsets = torch.zeros(n_lists + 1, dtype=torch.int64)
+        self.offsets[1:] = torch.cumsum(counts, 0)
+
+    def probes(self, q: torch.Tensor, n_probes: int) -> torch.Tensor:
+        q = q.to(torch.float32)
+        if self.metric in ("sqeuclidean", "l2", "L2"):
+            score = (self.cent * self.cent).sum(1)[None, :] - 2.0 * (q @ self.cent.T)
+        else:
+            score = -(q @ self.cent.T)
+        return torch.topk(score, min(n_probes, self.cent.shape[0]), dim=1, largest=False).indices
+
+    def search(self, q: torch.Tensor, k: int, n_probes: int = 20) -> Tuple[torch.Tensor, torch.Tensor]:
+        q = q.to(torch.float32)
+        pr = self.probes(q, n_probes)
+        out_d = torch.full((q.shape[0], k), float("inf"))
+        out_i = torch.full((q.shape[0], k), -1, dtype=torch.int64)
+        l2 = self.metric in ("sqeuclidean", "l2", "L2")
+        for qi in range(q.shape[0]):
+            rows = torch.cat([self.order[self.offsets[l]:self.offsets[l + 1]] for l in pr[qi].tolist()])
+            if rows.numel() == 0:
+                continue
+            xs = self.db[rows]
+            if l2:
+                sc = ((xs - q[qi][None, :]) ** 2).sum(1)
+            else:
+                sc = -(xs @ q[qi])
+            kk = min(k, rows.numel())
+            d, pos = torch.topk(sc, kk, largest=False, sorted=True)
+            out_d[qi, :kk] = d if l2 else -d
+            out_i[qi, :kk] = rows[pos]
+        if not l2:
+            out_d[out_i < 0] = float("-inf")
+        return out_d, out_i
+
+
+class IvfPqOracle(IvfFlatOracle):
+    def __init__(self, db: torch.Tensor, n_lists: int, pq_dim: int, metric: str = "sqeuclidean",
+                 iters: int = 20, train_fraction: float = 0.5, seed: int = 0, pq_iters: int = 10):
+        super().__init__(db, n_lists, metric, iters, train_fraction, seed)
+        d = self.db.shape[1]
+        assert d % pq_dim == 0
+        self.pq_dim, self.dsub = pq_dim, d // pq_dim
+        res = self.db - self.cent[self.labels]
+        n = res.shape[0]
+        stride = max(1, n // 131072)
+        tr = res[::stride]
+        self.codebooks = torch.stack([
+            kmeans(tr[:, m * self.dsub:(m + 1) * self.dsub], 256, pq_iters, seed + 31 * (m + 1))
+            for m in range(pq_dim)])  # [M, 256, dsub]
+        codes = torch.empty((n, pq_dim), dtype=torch.int64)
+        for m in range(pq_dim):
+            codes[:, m] = assign(res[:, m * self.dsub:(m + 1) * self.dsub], self.codebooks[m])
+        self.codes = codes
+
+    def search(self, q: torch.Tensor, k: int, n_probes: int = 20):
+        q = q.to(torch.float32)
+        pr = self.probes(q, n_probes)
+        out_d = torch.full((q.shape[0], k), float("inf"))
+        out_i = torch.full((q.shape[0], k), -1, dtype=torch.int64)
+        l2 = self.metric in ("sqeuclidean", "l2", "L2")
+        M, ds = self.pq_dim, self.dsub
+        for qi in range(q.shape[0]):
+            cand_s, cand_r = [], []
+            for l in pr[qi].tolist():
+                rows = self.order[self.offsets[l]:self.offsets[l + 1]]
+                if rows.numel() == 0:
+                    continue
+                if l2:
+                    rq = (q[qi] - self.cent[l]).view(M, 1, ds)
+                    lut = ((rq - self.codebooks) ** 2).sum(2)          # [M, 256]
+                    bias = 0.0
+                else:
+                    lut = -(self.codebooks * q[qi].view(M, 1, ds)).sum(2)
+                    bias = -float(q[qi] @ self.cent[l])
+                sc = bias + lut[torch.arange(M)[None, :], self.codes[rows]].sum(1)
+                cand_s.append(sc)
+                cand_r.append(rows)
+            if not cand_s:
+                continue
+            sc = torch.cat(cand_s)
+            rows = torch.cat(cand_r)
+            kk = min(k, rows.numel())
+            d, pos = torch.topk(sc, kk, largest=False, sorted=True)
+            out_d[qi, :kk] = d if l2 else -d
+            out_i[qi, :kk] = rows[pos]
+        return out_d, out_i
+
+
+def recall(ids: torch.Tensor, truth: torch.Tensor) -> float:
+    hits = 0
+    for a, b in zip(ids.tolist(), truth.tolist()):
+        hits += len(set(a) & set(x for x in b if x >= 0))
+    denom = int((truth >= 0).sum())
+    return hits / float(max(denom, 1))

@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG_DIR = os.path.join(ROOT, "cuvs-rag_b200")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def b2():
+    import cuvs_rag_b200
+    return cuvs_rag_b200
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN

@@ -22,6 +22,11 @@ CASES = [
     ("k128", 9000, 256, 130, 128, "fp16", "sqeuclidean", 0),
     ("k_gt_n", 50, 64, 5, 100, "bf16", "sqeuclidean", 0),
     ("big_200k", 200000, 768, 1024, 100, "bf16", "sqeuclidean", 0),
+    ("manyq_k1_d64", 256, 64, 50000, 1, "fp16", "sqeuclidean", 0),
+    ("manyq_k1_d128", 256, 128, 100000, 1, "fp16", "sqeuclidean", 0),
+    ("manyq_k1_d768", 512, 768, 60000, 1, "fp16", "sqeuclidean", 0),
+    ("manyq_k10_d128", 5000, 128, 40000, 10, "bf16", "sqeuclidean", 0),
+    ("multi_item_k100", 300000, 256, 2048, 100, "bf16", "sqeuclidean", 40),
 ]
 
 
