@@ -263,7 +263,7 @@ class SearchResultAggregator:
             raw = [self._search_single_gpu(g, indices[g], query, k_local, params) for g in gpus]
 
         on_device = all(r[3] for r in raw)
-        descending = any(getattr(indices[g], "descending", False) for g in gpus)
+        descending = any(getattr(indices[g], "descending", False) is True for g in gpus)
         if on_device:
             final_d, final_i, gpu_results = self._merge_on_device(gpus, raw, k, k_local, nq,
                                                                   descending, collect)

@@ -1,0 +1,175 @@
+"""GPU parity of the exact-search path (K0 fused tcgen05 kernel + K8 merges) through the C ABI,
+against the CPU oracle on identical seeded inputs.  Tolerance (north star): ids equal to an exact
+fp32 search except for distance ties within 1e-3 relative; distances within 1e-3 relative."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-3
+DT = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}
+
+
+def make(n, d, q, dtype, metric, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    db, qs = torch.randn(n, d, generator=g), torch.randn(q, d, generator=g)
+    if metric == "inner_product":
+        db = torch.nn.functional.normalize(db, dim=1)
+        qs = torch.nn.functional.normalize(qs, dim=1)
+    return db.to(DT[dtype]), qs.to(DT[dtype])
+
+
+def check(b2, db, qs, k, metric, id_offset=0, **kw):
+    from oracle.exact import topk_parity_report
+    ix = b2.NativeIndex.flat(db.cuda(), metric=metric, id_offset=id_offset)
+    d, i = ix.search(qs.cuda(), k, **kw)
+    torch.cuda.synchronize()
+    i = i.cpu()
+    local = torch.where(i >= 0, i - id_offset, i)
+    rep = topk_parity_report(d.cpu(), local, db.float(), qs.float(), k, metric, rtol=RTOL)
+    assert rep["ok"], rep
+    return d.cpu(), i, ix
+
+
+CASES = [
+    # n, d, q, k, dtype, metric, n_splits
+    (1000, 64, 10, 5, "bf16", "sqeuclidean", 0),
+    (256, 64, 128, 1, "bf16", "sqeuclidean", 0),
+    (20000, 768, 300, 100, "bf16", "sqeuclidean", 0),
+    (30000, 384, 257, 10, "fp16", "inner_product", 0),
+    (5000, 96, 64, 10, "fp32", "sqeuclidean", 0),
+    (3000, 100, 33, 7, "bf16", "sqeuclidean", 0),       # dim % 8 != 0: padded operand copy
+    (50000, 128, 512, 32, "bf16", "sqeuclidean", 7),    # forced db splits
+    (9000, 256, 130, 128, "fp16", "sqeuclidean", 0),    # k = fused maximum
+    (256, 128, 40000, 1, "fp16", "sqeuclidean", 0),     # many items per CTA (k-means assign shape)
+    (5000, 128, 20000, 10, "bf16", "inner_product", 0),
+]
+
+
+@pytest.mark.parametrize("n,d,q,k,dtype,metric,splits", CASES)
+def test_exact_search_parity(b2, n, d, q, k, dtype, metric, splits):
+    db, qs = make(n, d, q, dtype, metric)
+    check(b2, db, qs, k, metric, id_offset=1000, n_splits=splits)
+
+
+@pytest.mark.parametrize("group_flag", ["single", "pair"])
+def test_both_kernel_variants_agree(b2, group_flag):
+    """cta_group::1 and cta_group::2 kernels must give the same neighbours."""
+    n = b2._native
+    db, qs = make(40000, 256, 700, "bf16", "sqeuclidean")
+    ix = n.NativeIndex.flat(db.cuda())
+    import ctypes
+    flag = 2 if group_flag == "single" else 4
+    d = torch.empty((700, 50), dtype=torch.float32, device="cuda")
+    i = torch.empty((700, 50), dtype=torch.int64, device="cuda")
+    sp = n.SearchParams(0, 0, 0, flag)
+    rc = n.lib().b2vs_search(ix._h, qs.cuda().data_ptr(), n.BF16, 700, 50, ctypes.byref(sp),
+                             d.data_ptr(), i.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, n.lib().b2vs_last_error()
+    torch.cuda.synchronize()
+    from oracle.exact import topk_parity_report
+    assert topk_parity_report(d.cpu(), i.cpu(), db.float(), qs.float(), 50, rtol=RTOL)["ok"]
+
+
+def test_config_c1_full_size(b2):
+    """BASELINE configs[0]: exact inner product k=10, 100K x 384 fp32 unit-norm rows, 1K queries."""
+    g = torch.Generator().manual_seed(4321)
+    db = torch.nn.functional.normalize(torch.randn(100_000, 384, generator=g), dim=1)
+    qs = torch.nn.functional.normalize(torch.randn(1000, 384, generator=g), dim=1)
+    from oracle.exact import exact_knn
+    ix = b2.NativeIndex.flat(db.cuda(), metric="inner_product")
+    d, i = ix.search(qs.cuda(), 10)
+    torch.cuda.synchronize()
+    rd, ri = exact_knn(db, qs, 10, "inner_product")
+    match = (i.cpu() == ri).float().mean().item()
+    assert match > 0.999, match                      # ties within 1e-3 are the only allowed diffs
+    np.testing.assert_allclose(d.cpu().numpy(), rd.numpy(), rtol=RTOL, atol=1e-4)
+
+
+def test_k_larger_than_n_and_empty_tail(b2):
+    db, qs = make(50, 64, 5, "bf16", "sqeuclidean")
+    d, i, _ = check(b2, db, qs, 100, "sqeuclidean")
+    assert (i[:, 50:] == -1).all() and torch.isinf(d[:, 50:]).all()
+
+
+def test_golden_fixture_and_reference_sample_embeddings(b2, golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "knn_l2.npz"))
+    ix = b2.NativeIndex.flat(torch.from_numpy(g["db"]).cuda())
+    d, i = ix.search(torch.from_numpy(g["q"]).cuda(), 10)
+    assert (i.cpu().numpy() == g["i"]).mean() > 0.999
+    np.testing.assert_allclose(d.cpu().numpy(), g["d"], rtol=RTOL, atol=1e-3)
+    s = np.load(os.path.join(golden_dir, "sample_emb.npz"))
+    emb = torch.from_numpy(s["emb"]).cuda()
+    ix = b2.NativeIndex.flat(emb, metric="inner_product")
+    d, i = ix.search(emb, 5)
+    np.testing.assert_array_equal(i.cpu().numpy(), s["i"])
+
+
+def test_search_host_matches_device_search(b2):
+    db, qs = make(8000, 128, 300, "bf16", "sqeuclidean")
+    ix = b2.NativeIndex.flat(db.cuda(), id_offset=5)
+    d1, i1 = ix.search(qs.cuda(), 20)
+    d2, i2 = ix.search_host(qs, 20)
+    assert torch.equal(i1.cpu(), i2) and torch.allclose(d1.cpu(), d2)
+
+
+def test_error_paths_return_codes_not_crashes(b2):
+    db, qs = make(1000, 64, 4, "bf16", "sqeuclidean")
+    ix = b2.NativeIndex.flat(db.cuda())
+    with pytest.raises(RuntimeError, match="outside the fused top-k range"):
+        ix.search(qs.cuda(), 129)
+    with pytest.raises(ValueError, match="must live on a CUDA device"):
+        ix.search(qs, 5)
+    inf = ix.info()
+    assert (inf.n_rows, inf.dim, inf.kind) == (1000, 64, 0)
+    ix.destroy()
+    with pytest.raises(RuntimeError, match="destroyed"):
+        ix.search(qs.cuda(), 5)
+
+
+# ---- K8 cross-shard merge on the GPU
+def test_merge_topk_known_answers_on_gpu(b2):
+    d = torch.tensor([[[2.0, 4.0], [6.0, 8.0]], [[1.0, 3.0], [5.0, 7.0]]]).cuda()
+    i = torch.tensor([[[20, 40], [60, 80]], [[10, 30], [50, 70]]]).cuda()
+    md, mi = b2.merge_topk(d, i, 3)
+    assert mi.cpu().tolist() == [[10, 20, 30], [50, 60, 70]]
+    assert md.cpu().tolist() == [[1.0, 2.0, 3.0], [5.0, 6.0, 7.0]]
+    md, mi = b2.merge_topk(d, i, 2, descending=True)
+    assert mi.cpu().tolist() == [[40, 30], [80, 70]]
+
+
+def test_merge_topk_random_vs_oracle(b2):
+    from oracle.merge import merge_topk
+    g = torch.Generator().manual_seed(5)
+    for parts, nq, k_in, k_out in [(8, 300, 100, 100), (3, 17, 7, 10), (2, 5, 200, 128), (5, 64, 1, 4)]:
+        d = torch.sort(torch.rand(parts, nq, k_in, generator=g), dim=2).values
+        i = torch.randint(0, 10**9, (parts, nq, k_in), generator=g)
+        md, mi = b2.merge_topk(d.cuda(), i.cuda(), k_out)
+        od, oi = merge_topk(list(d.numpy()), list(i.numpy()), k_out)
+        kk = min(k_out, parts * k_in)
+        np.testing.assert_array_equal(mi.cpu().numpy()[:, :kk], oi[:, :kk])
+        np.testing.assert_array_equal(md.cpu().numpy()[:, :kk], od[:, :kk])
+
+
+def test_sharded_search_equals_single_shard(b2):
+    """Property at size: 1 shard vs 4 uneven shards + merge give identical ids (1M x 128)."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    db = torch.randn(1_000_003, 128, generator=g, device="cuda").to(torch.bfloat16)
+    qs = torch.randn(2048, 128, generator=g, device="cuda").to(torch.bfloat16)
+    d1, i1 = b2.NativeIndex.flat(db).search(qs, 100)
+    dd, ii = [], []
+    for s, e in b2.partition_even(db.shape[0], 4):
+        d, i = b2.NativeIndex.flat(db[s:e].contiguous(), id_offset=s).search(qs, 100)
+        dd.append(d); ii.append(i)
+    md, mi = b2.merge_topk(torch.stack(dd), torch.stack(ii), 100)
+    torch.cuda.synchronize()
+    same = (mi == i1).float().mean().item()
+    assert same > 0.9995, same
+    assert torch.allclose(md, d1, rtol=1e-4, atol=1e-3)
+    assert (md[:, 1:] >= md[:, :-1]).all()                      # sortedness
+    assert int((mi < 0).sum()) == 0 and int(mi.max()) < db.shape[0]
+    # split invariance: forcing a different db decomposition must not change the answer
+    d3, i3 = b2.NativeIndex.flat(db).search(qs, 100, n_splits=3)
+    assert (i3 == i1).float().mean().item() > 0.9995

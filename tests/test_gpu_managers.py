@@ -1,0 +1,75 @@
+"""The drop-in pipeline on real GPUs: GRM -> EDM -> IBC -> SRA, results against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def pipeline(b2, index_type, params, metric="sqeuclidean", dtype=torch.bfloat16, k=10, search_params=None):
+    from oracle.exact import exact_knn
+    g = torch.Generator().manual_seed(21)
+    emb = torch.randn(30001, 64, generator=g)
+    qs = torch.randn(50, 64, generator=g)
+    grm = b2.GPUResourceManager()
+    assert grm.get_available_gpu_count() >= 1
+    edm = b2.EmbeddingDistributionManager(grm)
+    dist = edm.distribute_embeddings(emb, dtype=dtype)
+    assert edm.validate_distribution(dist)
+    ibc = b2.IndexBuildingCoordinator(grm)
+    cfg = b2.IndexBuildConfig(index_type, dict(params, metric=metric), max_retries=0)
+    built = ibc.build_indices_parallel(dist, cfg)
+    assert built.success, [r.error_message for r in built.build_results]
+    sra = b2.SearchResultAggregator(grm)
+    res = sra.perform_distributed_search(qs, ibc.get_built_indices(),
+                                         b2.SearchConfig(k=k, search_params=search_params))
+    rd, ri = exact_knn(emb.to(dtype).float(), qs.to(dtype).float(), k, metric)
+    return res, rd, ri, ibc, edm
+
+
+def test_brute_force_pipeline_is_exact(b2):
+    res, rd, ri, ibc, edm = pipeline(b2, "brute_force", {})
+    assert res.final_indices.shape == (50, 10) and res.num_queries == 50
+    assert (res.final_indices == ri.numpy()).mean() > 0.995
+    np.testing.assert_allclose(res.final_distances, rd.numpy(), rtol=1e-3, atol=1e-2)
+    assert len(res.gpu_results) == len(ibc.get_built_indices())
+    for r in res.gpu_results:
+        assert r.distances.shape == (50, 10) and r.k_returned == 10
+    ibc.cleanup_all_indices()
+    edm.cleanup_distribution()
+
+
+def test_inner_product_pipeline_descending(b2):
+    res, rd, ri, ibc, _ = pipeline(b2, "flat", {}, metric="inner_product")
+    assert (np.diff(res.final_distances, axis=1) <= 1e-6).all()
+    assert (res.final_indices == ri.numpy()).mean() > 0.995
+
+
+def test_ivf_flat_pipeline_default_nlists_and_probes(b2):
+    res, rd, ri, ibc, _ = pipeline(b2, "ivf_flat", {}, search_params={"n_probes": 31})
+    # default n_lists = min(256, N // 1000 + 1) = 31 per full corpus shard -> full probe = exact
+    hit = np.mean([len(set(a) & set(b)) / 10.0 for a, b in zip(res.final_indices.tolist(), ri.tolist())])
+    assert hit > 0.97, hit
+
+
+def test_ivf_pq_pipeline_runs(b2):
+    res, rd, ri, ibc, _ = pipeline(b2, "ivf_pq", {"n_lists": 16, "pq_dim": 32}, search_params={"nprobe": 16})
+    hit = np.mean([len(set(a) & set(b)) / 10.0 for a, b in zip(res.final_indices.tolist(), ri.tolist())])
+    assert hit > 0.5, hit
+
+
+def test_cagra_is_reported_not_faked(b2):
+    grm = b2.GPUResourceManager()
+    ibc = b2.IndexBuildingCoordinator(grm)
+    part = b2.EmbeddingPart(0, torch.randn(100, 16).cuda(), 0, 100)
+    dist = b2.DistributedEmbeddings([part], 100, 16)
+    out = ibc.build_indices_parallel(dist, b2.IndexBuildConfig("cagra", {}, max_retries=0))
+    assert not out.success and "out of scope" in out.build_results[0].error_message
+
+
+def test_simulated_index_is_rejected_on_a_gpu_box(b2):
+    grm = b2.GPUResourceManager()
+    sra = b2.SearchResultAggregator(grm)
+    with pytest.raises(TypeError, match="not a native index"):
+        sra.perform_distributed_search(torch.randn(2, 8), {0: {"type": "ivf_flat", "size": 1, "dim": 8}},
+                                       b2.SearchConfig(k=1, parallel_search=False))
