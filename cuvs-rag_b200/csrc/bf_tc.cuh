@@ -56,13 +56,89 @@ struct BfTcParams {
   int n_qblocks;        // ceil(nq / (128*G))
   int q_pad;            // n_qblocks * 128 * G
   int n_items;          // n_qblocks * n_splits
-  int tiles_total;      // ceil(n_db / 256)
+  int tiles_total;      // tiles visited by this launch: ceil(ceil(n_db / 256) / tile_stride)
   int tiles_per_split;
+  int tile_stride;      // visit db tiles 0, stride, 2*stride, ... (threshold-seeding passes sample)
+  const float* tau_init;  // [q_pad] starting threshold per query row (NULL = +inf)
   int k_blocks;         // ceil(K / 64)
   int k;                // 1..kMaxFusedK
   float alpha;          // -2 (L2) or -1 (inner product)
   uint32_t idesc;
 };
+
+
+// Scores one 32-column chunk of one query row held in registers: score = alpha*acc + beta.
+// Fast path (almost always taken once the threshold has warmed up): a min-reduction and ONE
+// compare, no per-element branches.  Slow path: append every score below the threshold to the
+// row's candidate buffer (or track the arg-min when k == 1).
+template <bool kArgmin>
+__device__ __forceinline__ void score_chunk(const uint32_t (&r)[32], const float4* __restrict__ nrm4,
+                                            float alpha, uint32_t col, float& tau, int& cnt,
+                                            u64& best, u64* __restrict__ my_cand) {
+  float sc[32];
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 nb = nrm4[j4];
+    sc[4 * j4 + 0] = fmaf(alpha, __uint_as_float(r[4 * j4 + 0]), nb.x);
+    sc[4 * j4 + 1] = fmaf(alpha, __uint_as_float(r[4 * j4 + 1]), nb.y);
+    sc[4 * j4 + 2] = fmaf(alpha, __uint_as_float(r[4 * j4 + 2]), nb.z);
+    sc[4 * j4 + 3] = fmaf(alpha, __uint_as_float(r[4 * j4 + 3]), nb.w);
+  }
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    m[i] = fminf(fminf(sc[4 * i], sc[4 * i + 1]), fminf(sc[4 * i + 2], sc[4 * i + 3]));
+  const float mn = fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])),
+                         fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
+  if (mn < tau) {
+    if (kArgmin) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (sc[j] < tau) {
+          tau = sc[j];
+          best = pack_key(sc[j], col + j);
+        }
+      }
+    } else {
+      // Hits are rare per row but common per warp (32 rows x 32 columns), so the cost here must
+      // scale with the number of hits: build the hit mask without branches, then visit set bits,
+      // pulling the score out of the register array with a 5-level select tree.
+      uint32_t mask = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mask |= (sc[j] < tau) ? (1u << j) : 0u;
+      while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        float v16[16], v8[8], v4[4], v2[2];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v16[i] = (j & 1) ? sc[2 * i + 1] : sc[2 * i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v8[i] = (j & 2) ? v16[2 * i + 1] : v16[2 * i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v4[i] = (j & 4) ? v8[2 * i + 1] : v8[2 * i];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) v2[i] = (j & 8) ? v4[2 * i + 1] : v4[2 * i];
+        const float v = (j & 16) ? v2[1] : v2[0];
+        __stcg(my_cand + cnt, pack_key(v, col + j));
+        ++cnt;
+      }
+    }
+  }
+}
+
+// A chunk appends at most 32 keys per row: compact (warp-cooperatively) the rows that could
+// overflow on the next chunk, which also tightens their thresholds.
+__device__ __forceinline__ void compact_if_needed(int& cnt, float& tau, u64* cand_warp, int k, int lane) {
+  uint32_t need = __ballot_sync(0xffffffffu, cnt > kCap - 32);
+  while (need) {
+    const int rr = __ffs(need) - 1;
+    need &= need - 1;
+    const int n_r = __shfl_sync(0xffffffffu, cnt, rr);
+    u64* rb = cand_warp + static_cast<size_t>(rr) * kCap;
+    const float nt = compact_row(rb, rb, n_r, k, lane);
+    if (lane == rr) { cnt = min(n_r, k); tau = nt; }
+  }
+}
 
 template <int G>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -136,7 +212,8 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         const int t0 = s * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
         const int q_row0 = qb * (kBM * G) + static_cast<int>(cta_rank) * kBM;
-        for (int t = t0; t < t1; ++t, ++tcount) {
+        for (int ti = t0; ti < t1; ++ti, ++tcount) {
+          const int t = ti * p.tile_stride;
           const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
           ptx::mbar_wait(bar_norm_empty + 8 * as, aph ^ 1u);
           ptx::mbar_arrive_expect_tx(bar_norm_full + 8 * as, kNormBytes);
@@ -213,74 +290,48 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       const int t0 = s * p.tiles_per_split;
       const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
       float tau = inf;
+      if (p.tau_init != nullptr)
+        tau = p.tau_init[static_cast<size_t>(qb) * (kBM * G) + cta_rank * kBM + ew * 32 + lane];
       int cnt = 0;
       u64 best = kKeyInf;  // k == 1 fast path keeps the running arg-min in a register
-      for (int t = t0; t < t1; ++t, ++tcount) {
+      for (int ti = t0; ti < t1; ++ti, ++tcount) {
+        const int t = ti * p.tile_stride;
         const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
         ptx::mbar_wait(bar_acc_full + 8 * as, aph);
         ptx::mbar_wait(bar_norm_full + 8 * as, aph);
         ptx::tc_fence_after();
         const float4* nrm4 = reinterpret_cast<const float4*>(norm_ptr + as * kBN);
         const uint32_t col0 = static_cast<uint32_t>(t) * kBN;
+        // Two register buffers: the TMEM load of chunk c+1 is in flight while chunk c is scored.
+        uint32_t ra[32], rb[32];
+        const uint32_t tile_taddr = lane_taddr + as * kBN;
+        ptx::tmem_ld_32x32b_x32(tile_taddr, ra);
 #pragma unroll 1
-        for (int c = 0; c < kBN / 32; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(lane_taddr + as * kBN + c * 32, r);
+        for (int c2 = 0; c2 < kBN / 64; ++c2) {
           ptx::tmem_ld_wait();
-          if (p.k == 1) {
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 nb = nrm4[c * 8 + j4];
-              const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int j = j4 * 4 + jj;
-                const float sc = fmaf(p.alpha, __uint_as_float(r[j]), nbv[jj]);
-                if (sc < tau) {
-                  tau = sc;
-                  best = pack_key(sc, col0 + c * 32 + j);
-                }
-              }
-            }
+          ptx::tmem_ld_32x32b_x32(tile_taddr + c2 * 64 + 32, rb);
+          if (p.k == 1) score_chunk<true>(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, cnt, best, my_cand);
+          else score_chunk<false>(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, cnt, best, my_cand);
+          if (p.k != 1) compact_if_needed(cnt, tau, cand_warp, p.k, lane);
+          ptx::tmem_ld_wait();
+          if (c2 + 1 < kBN / 64) {
+            ptx::tmem_ld_32x32b_x32(tile_taddr + c2 * 64 + 64, ra);
           } else {
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 nb = nrm4[c * 8 + j4];
-              const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int j = j4 * 4 + jj;
-                const float sc = fmaf(p.alpha, __uint_as_float(r[j]), nbv[jj]);
-                if (sc < tau) {
-                  __stcg(my_cand + cnt, pack_key(sc, col0 + c * 32 + j));
-                  ++cnt;
-                }
-              }
-            }
-          }
-          if (c == kBN / 32 - 1) {
-            // all TMEM / beta reads of this tile are done: hand both buffers back
+            // every TMEM read of this tile has landed in registers: hand the accumulator back
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
               if (G == 2) ptx::mbar_arrive_cluster(acc_empty_leader + 8 * as);
               else ptx::mbar_arrive(bar_acc_empty + 8 * as);
-              ptx::mbar_arrive(bar_norm_empty + 8 * as);
             }
           }
-          if (p.k != 1) {
-            // a chunk appends at most 32 keys per row: compact rows that could overflow next
-            uint32_t need = __ballot_sync(0xffffffffu, cnt > kCap - 32);
-            while (need) {
-              const int rr = __ffs(need) - 1;
-              need &= need - 1;
-              const int n_r = __shfl_sync(0xffffffffu, cnt, rr);
-              int kept;
-              u64* rb = cand_warp + static_cast<size_t>(rr) * kCap;
-              const float nt = compact_row(rb, rb, n_r, p.k, lane, &kept);
-              if (lane == rr) { cnt = kept; tau = nt; }
-            }
+          if (p.k == 1) score_chunk<true>(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, cnt, best, my_cand);
+          else score_chunk<false>(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, cnt, best, my_cand);
+          if (c2 + 1 == kBN / 64) {
+            __syncwarp();   // all lanes are done with this tile's beta values
+            if (lane == 0) ptx::mbar_arrive(bar_norm_empty + 8 * as);
           }
+          if (p.k != 1) compact_if_needed(cnt, tau, cand_warp, p.k, lane);
         }
       }
       // ---- item done: emit this (split, query block)'s sorted top-k keys
@@ -292,10 +343,9 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         __syncwarp();
         for (int rr = 0; rr < 32; ++rr) {
           const int n_r = __shfl_sync(0xffffffffu, cnt, rr);
-          int kept;
           u64* dst = out_blk + static_cast<size_t>(rr) * p.k;
-          compact_row(cand_warp + static_cast<size_t>(rr) * kCap, dst, n_r, p.k, lane, &kept);
-          for (int i = kept + lane; i < p.k; i += 32) dst[i] = kKeyInf;
+          compact_row(cand_warp + static_cast<size_t>(rr) * kCap, dst, n_r, p.k, lane);
+          for (int i = min(n_r, p.k) + lane; i < p.k; i += 32) dst[i] = kKeyInf;
         }
         __syncwarp();
       }

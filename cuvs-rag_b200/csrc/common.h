@@ -107,7 +107,7 @@ struct FlatEngine {
   CUtensorMap tm_x;       // db map, box = 256 rows (single-CTA kernel)
   CUtensorMap tm_x_half;  // db map, box = 128 rows (CTA-pair kernel: each CTA stages half a tile)
   // workspaces (grow-only)
-  DevBuf ws_cand, ws_keys, ws_q, ws_qnorm;
+  DevBuf ws_cand, ws_keys, ws_q, ws_qnorm, ws_tau;
   b2vs_search_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // optional timing of the dominant kernel
   bool timing_pending = false;
@@ -133,7 +133,8 @@ int encode_tmap_2d(CUtensorMap* tm, const void* base, int ab_format, int64_t row
 // `remap` (optional) translates key ids (list slots) to shard-local row ids before id_offset.
 int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k, int metric,
                         const float* qnorm, int64_t id_offset, float* out_d, int64_t* out_i,
-                        int32_t* out_label, cudaStream_t st, const uint32_t* remap = nullptr);
+                        int32_t* out_label, cudaStream_t st, const uint32_t* remap = nullptr,
+                        float* out_tau = nullptr);
 
 }  // namespace b2vs
 

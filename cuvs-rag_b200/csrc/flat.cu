@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 
@@ -220,6 +221,7 @@ void FlatEngine::destroy() {
   ws_keys.release();
   ws_q.release();
   ws_qnorm.release();
+  ws_tau.release();
 }
 
 __global__ void fill_missing_kernel(float* out_d, int64_t* out_i, int32_t* out_label, int64_t total,
@@ -243,9 +245,39 @@ static int tc_group_override() {
   return cached;
 }
 
+// Tile strides of the passes of one search (see FlatEngine::search).  B2VS_PASSES="16,1" etc.
+// overrides the heuristic for A/B measurements.
+static int pass_strides(int64_t tiles, int k, int* strides) {
+  static int env_n = -1, env_s[3];
+  if (env_n < 0) {
+    env_n = 0;
+    const char* e = std::getenv("B2VS_PASSES");
+    if (e) {
+      int a = 0, b = 0, c = 0;
+      const int got = std::sscanf(e, "%d,%d,%d", &a, &b, &c);
+      const int v[3] = {a, b, c};
+      for (int i = 0; i < got && i < 3; ++i)
+        if (v[i] >= 1) env_s[env_n++] = v[i];
+      if (env_n > 0 && env_s[env_n - 1] != 1) env_n = 0;  // the last pass must be the full one
+    }
+  }
+  if (k == 1) { strides[0] = 1; return 1; }        // arg-min keeps its state in registers
+  if (env_n > 0) {
+    int m = 0;
+    for (int i = 0; i < env_n; ++i)
+      if (env_s[i] == 1 || tiles / env_s[i] >= 8) strides[m++] = env_s[i];
+    return m;
+  }
+  int m = 0;
+  if (tiles >= 8192) strides[m++] = 256;
+  if (tiles >= 256) strides[m++] = 16;
+  strides[m++] = 1;
+  return m;
+}
+
 // Number of db splits: minimise waves * (tiles per split + fixed per-item cost in tile units).
-static int choose_splits(int n_qblocks, int64_t tiles, int sms, int k) {
-  const int64_t overhead = (k == 1) ? 1 : 40;
+static int choose_splits(int n_qblocks, int64_t tiles, int sms, int k, bool seeded = false) {
+  const int64_t overhead = (k == 1) ? 1 : (seeded ? 16 : 40);
   int64_t best_cost = INT64_MAX;
   int best = 1;
   const int64_t smax = std::min<int64_t>(tiles, 512);
@@ -307,29 +339,22 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   CUtensorMap tm_q;
   B2VS_TRY(encode_tmap_2d(&tm_q, q_mat, ab_format, nq, kdim, kBM));
 
-  // ---- decomposition
+  // ---- passes.  A pass visits every `stride`-th db tile.  The last pass (stride 1) produces the
+  // answer; earlier, sparser passes only seed each query's threshold with the k-th best score of
+  // a 1/stride sample (a valid upper bound of the final k-th score), so the full pass starts with
+  // a tight threshold: ~k*stride candidates per query in total instead of k*ln(N/k) per split,
+  // and practically no buffer compactions.
   const int sms = sm_count(dev);
   const int units = std::max(1, sms / group);  // CTAs (G=1) or CTA pairs (G=2) that run at once
   const int64_t tiles = ceil_div(n, kBN);
-  int n_splits = force_splits > 0 ? static_cast<int>(std::min<int64_t>(force_splits, tiles))
-                                  : choose_splits(n_qblocks, tiles, units, k);
-  const int tps = static_cast<int>(ceil_div(tiles, n_splits));
-  n_splits = static_cast<int>(ceil_div(tiles, tps));
-  const int n_items = n_qblocks * n_splits;
-  const int grid = std::min(n_items, units) * group;
-
-  B2VS_TRY(ws_cand.reserve(static_cast<size_t>(grid) * kBM * kCap * sizeof(u64)));
-  B2VS_TRY(ws_keys.reserve(static_cast<size_t>(n_splits) * q_pad * k * sizeof(u64)));
+  int strides[3];
+  int n_pass = pass_strides(tiles, k, strides);
+  B2VS_TRY(ws_tau.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
 
   BfTcParams p;
   p.beta = beta.as<float>();
-  p.cand = ws_cand.as<u64>();
-  p.out_keys = ws_keys.as<u64>();
   p.n_qblocks = n_qblocks;
   p.q_pad = q_pad;
-  p.n_items = n_items;
-  p.tiles_total = static_cast<int>(tiles);
-  p.tiles_per_split = tps;
   p.k_blocks = static_cast<int>(ceil_div(kdim, kBK));
   p.k = k;
   p.alpha = (metric == B2VS_METRIC_L2) ? -2.f : -1.f;
@@ -343,35 +368,62 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
     }
     B2VS_CUDA(cudaEventRecord(ev0, st));
   }
-  if (group == 1) {
-    B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   TcCfg<1>::kSmemBytes));
-    bf_tc_kernel<1><<<grid, kTcThreads, TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_x, p);
-  } else {
-    B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   TcCfg<2>::kSmemBytes));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kTcThreads);
-    cfg.dynamicSmemBytes = TcCfg<2>::kSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    B2VS_CUDA(cudaLaunchKernelEx(&cfg, bf_tc_kernel<2>, tm_q, tm_x_half, p));
+  int n_splits = 1, grid = 1;
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const int stride = strides[pass];
+    const bool last = (pass == n_pass - 1);
+    const int64_t ptiles = ceil_div(tiles, stride);
+    n_splits = (force_splits > 0 && last)
+                   ? static_cast<int>(std::min<int64_t>(force_splits, ptiles))
+                   : choose_splits(n_qblocks, ptiles, units, k, /*seeded=*/pass > 0);
+    const int tps = static_cast<int>(ceil_div(ptiles, n_splits));
+    n_splits = static_cast<int>(ceil_div(ptiles, tps));
+    const int n_items = n_qblocks * n_splits;
+    grid = std::min(n_items, units) * group;
+    B2VS_TRY(ws_cand.reserve(static_cast<size_t>(grid) * kBM * kCap * sizeof(u64)));
+    B2VS_TRY(ws_keys.reserve(static_cast<size_t>(n_splits) * q_pad * k * sizeof(u64)));
+    p.cand = ws_cand.as<u64>();
+    p.out_keys = ws_keys.as<u64>();
+    p.n_items = n_items;
+    p.tiles_total = static_cast<int>(ptiles);
+    p.tiles_per_split = tps;
+    p.tile_stride = stride;
+    p.tau_init = (pass > 0) ? ws_tau.as<float>() : nullptr;
+    if (group == 1) {
+      B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TcCfg<1>::kSmemBytes));
+      bf_tc_kernel<1><<<grid, kTcThreads, TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_x, p);
+    } else {
+      B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TcCfg<2>::kSmemBytes));
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(kTcThreads);
+      cfg.dynamicSmemBytes = TcCfg<2>::kSmemBytes;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      B2VS_CUDA(cudaLaunchKernelEx(&cfg, bf_tc_kernel<2>, tm_q, tm_x_half, p));
+    }
+    B2VS_CUDA(cudaGetLastError());
+    ++launches;
+    if (last && timed) B2VS_CUDA(cudaEventRecord(ev1, st));
+    if (last) {
+      B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits, q_pad, nq, k, metric,
+                                   ws_qnorm.as<float>(), id_offset, out_d, out_i, out_label, st));
+    } else {
+      // sampled pass: only the k-th best raw score per query is kept, as the next pass's threshold
+      B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits, q_pad, q_pad, k, metric, nullptr, 0,
+                                   nullptr, nullptr, nullptr, st, nullptr, ws_tau.as<float>()));
+    }
+    ++launches;
   }
-  B2VS_CUDA(cudaGetLastError());
-  if (timed) B2VS_CUDA(cudaEventRecord(ev1, st));
   timing_pending = timed;
-  ++launches;
-
-  B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits, q_pad, nq, k, metric,
-                               ws_qnorm.as<float>(), id_offset, out_d, out_i, out_label, st));
-  ++launches;
 
   stats.launches = launches;
   stats.n_splits = n_splits;

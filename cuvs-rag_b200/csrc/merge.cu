@@ -21,7 +21,8 @@ __global__ void merge_splits_kernel(const u64* __restrict__ keys, int n_splits, 
                                     int k, int metric, const float* __restrict__ qnorm,
                                     long long id_offset, float* __restrict__ out_d,
                                     long long* __restrict__ out_i, int* __restrict__ out_label,
-                                    const uint32_t* __restrict__ remap) {
+                                    const uint32_t* __restrict__ remap,
+                                    float* __restrict__ out_tau) {
   const int lane = threadIdx.x & 31;
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= nq) return;
@@ -37,6 +38,16 @@ __global__ void merge_splits_kernel(const u64* __restrict__ keys, int n_splits, 
       acc[e] = acc[e] < b ? acc[e] : b;
     }
     warp_bitonic_merge<kMergeE>(acc, lane);
+  }
+  if (out_tau) {
+    // threshold-seeding pass: publish one ulp above the k-th best raw score (inclusive bound)
+    u64 kth = kKeyInf;
+#pragma unroll
+    for (int e = 0; e < kMergeE; ++e)
+      if (lane * kMergeE + e == k - 1) kth = acc[e];
+    if (lane == (k - 1) / kMergeE)
+      out_tau[q] = (kth == kKeyInf) ? INFINITY : nextafterf(key_score(kth), INFINITY);
+    return;
   }
   const float qn = (metric == B2VS_METRIC_L2 && qnorm) ? qnorm[q] : 0.f;
 #pragma unroll
@@ -60,13 +71,13 @@ __global__ void merge_splits_kernel(const u64* __restrict__ keys, int n_splits, 
 
 int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k, int metric,
                         const float* qnorm, int64_t id_offset, float* out_d, int64_t* out_i,
-                        int32_t* out_label, cudaStream_t st, const uint32_t* remap) {
+                        int32_t* out_label, cudaStream_t st, const uint32_t* remap, float* out_tau) {
   const int threads = 128;
   const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(nq) * 32, threads));
   merge_splits_kernel<<<blocks, threads, 0, st>>>(keys, n_splits, q_pad, nq, k, metric, qnorm,
                                                   id_offset, out_d,
                                                   reinterpret_cast<long long*>(out_i), out_label,
-                                                  remap);
+                                                  remap, out_tau);
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }

@@ -117,9 +117,10 @@ __device__ __forceinline__ void warp_bitonic_merge(u64 (&key)[E], int lane) {
 
 // Warp-cooperative compaction of one row buffer: sort the first n keys, write the best
 // min(n, k) back in ascending order (to `dst`, which may be the buffer itself) and return the
-// new threshold (+inf while fewer than k candidates exist).  All 32 lanes must call it.
-__device__ __forceinline__ float compact_row(const u64* buf, u64* dst, int n, int k, int lane,
-                                             int* kept) {
+// new threshold (+inf while fewer than k candidates exist); min(n, k) keys are kept.  All 32
+// lanes must call it.  Deliberately not inlined: one copy of the sort network keeps the fused
+// kernel's hot loop inside the instruction cache.
+static __device__ __noinline__ float compact_row(const u64* buf, u64* dst, int n, int k, int lane) {
   u64 key[kSortE];
   const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(buf + lane * kSortE);
 #pragma unroll
@@ -142,7 +143,6 @@ __device__ __forceinline__ float compact_row(const u64* buf, u64* dst, int n, in
   for (int e = 0; e < kSortE; ++e)
     if (lane * kSortE + e == k - 1) kth = key[e];
   kth = shfl_u64(kth, (k - 1) / kSortE);
-  *kept = m;
   return (n >= k) ? key_score(kth) : __int_as_float(0x7f800000);
 }
 
