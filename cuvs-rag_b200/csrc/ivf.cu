@@ -125,22 +125,65 @@ __global__ void accumulate_kernel(const T* __restrict__ x, const int* __restrict
   }
 }
 
+// K2 update, second half: mean of each cluster.  Balancing (the role cuVS's balanced k-means
+// "adjust centers" step plays): `donor_of[c] >= 0` tells cluster c - empty, or far below the
+// average size - to restart on a data row of the over-full cluster donor_of[c] (the pairing is
+// computed on the host from the cluster sizes, see balance_pairs), so Lloyd does not leave a few
+// giant lists next to starved ones.  Empty clusters without a donor restart on a random row.
 template <typename T>
-__global__ void finalize_centroids_kernel(const T* __restrict__ x, int64_t n, int dim,
-                                          const float* __restrict__ sums,
-                                          const int* __restrict__ counts, uint64_t seed,
+__global__ void finalize_centroids_kernel(const T* __restrict__ x, const int* __restrict__ labels,
+                                          int64_t n, int dim, const float* __restrict__ sums,
+                                          const int* __restrict__ counts,
+                                          const int* __restrict__ donor_of, uint64_t seed,
                                           float* __restrict__ cent) {
   const int c = blockIdx.x;
   const int cnt = counts[c];
-  if (cnt > 0) {
+  const int want = donor_of ? donor_of[c] : -1;
+  if (cnt > 0 && want < 0) {
     const float inv = 1.f / static_cast<float>(cnt);
     for (int j = threadIdx.x; j < dim; j += blockDim.x)
       cent[static_cast<size_t>(c) * dim + j] = sums[static_cast<size_t>(c) * dim + j] * inv;
-  } else {
-    // empty cluster: restart it on a pseudo-random data row
-    const int64_t row = static_cast<int64_t>(mix64(seed ^ (0xA5ull * (c + 1))) % static_cast<uint64_t>(n));
-    for (int j = threadIdx.x; j < dim; j += blockDim.x)
-      cent[static_cast<size_t>(c) * dim + j] = ld_f32<T>(x + row * dim + j);
+    return;
+  }
+  __shared__ long long donor_row;
+  if (threadIdx.x == 0) {
+    long long row = 0;
+    // rejection-sample a row of the donor cluster (it is over-full, so this ends quickly)
+    for (int attempt = 0; attempt < 8192; ++attempt) {
+      row = static_cast<long long>(mix64(seed ^ (0xA5ull * (c + 1)) ^ (0x9E3779B9ull * attempt)) %
+                                   static_cast<uint64_t>(n));
+      if (want < 0 || labels[row] == want) break;
+    }
+    donor_row = row;
+  }
+  __syncthreads();
+  const long long row = donor_row;
+  for (int j = threadIdx.x; j < dim; j += blockDim.x)
+    cent[static_cast<size_t>(c) * dim + j] = ld_f32<T>(x + row * dim + j);
+}
+
+// Host side of the balancing step: clusters above 1.5x the average size want floor(size/avg) - 1
+// extra centroids; they are taken from the smallest clusters below 0.5x the average.
+static void balance_pairs(const std::vector<int>& counts, int64_t n, std::vector<int>* donor_of) {
+  const int ncl = static_cast<int>(counts.size());
+  donor_of->assign(ncl, -1);
+  const double avg = static_cast<double>(n) / ncl;
+  std::vector<int> order(ncl);
+  for (int i = 0; i < ncl; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return counts[a] < counts[b]; });
+  int lo = 0, hi = ncl - 1;
+  while (lo < hi) {
+    const int big = order[hi];
+    if (counts[big] <= 1.5 * avg) break;
+    int quota = static_cast<int>(counts[big] / avg) - 1;
+    if (quota < 1) quota = 1;
+    while (quota > 0 && lo < hi && counts[order[lo]] < 0.5 * avg) {
+      (*donor_of)[order[lo]] = big;
+      ++lo;
+      --quota;
+    }
+    if (quota > 0) break;  // no small clusters left to move
+    --hi;
   }
 }
 
@@ -150,14 +193,16 @@ static int kmeans_fit_impl(int dev, int dtype, int dim, const void* x, int64_t n
              "k-means needs 1 <= n_clusters <= n (n_clusters=%d, n=%lld)", ncl,
              static_cast<long long>(n));
   B2VS_CHECK(n < (1ll << 31), B2VS_EINVAL, "k-means input too large (n=%lld)", static_cast<long long>(n));
-  DevBuf sums, counts, labels;
+  DevBuf sums, counts, labels, donors;
+  std::vector<int> h_counts, h_donor;
   FlatEngine eng;
   int rc = B2VS_OK;
-  auto cleanup = [&]() { sums.release(); counts.release(); labels.release(); eng.destroy(); };
+  auto cleanup = [&]() { sums.release(); counts.release(); labels.release(); donors.release(); eng.destroy(); };
 #define KM_TRY(expr) do { rc = (expr); if (rc != B2VS_OK) { cleanup(); return rc; } } while (0)
 #define KM_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); cleanup(); return B2VS_ECUDA; } } while (0)
   KM_TRY(sums.reserve(static_cast<size_t>(ncl) * dim * sizeof(float)));
   KM_TRY(counts.reserve(static_cast<size_t>(ncl) * sizeof(int)));
+  KM_TRY(donors.reserve(static_cast<size_t>(ncl) * sizeof(int)));
   int32_t* lab = labels_out;
   if (!lab) {
     KM_TRY(labels.reserve(static_cast<size_t>(n) * sizeof(int32_t)));
@@ -178,9 +223,20 @@ static int kmeans_fit_impl(int dev, int dtype, int dim, const void* x, int64_t n
                                  static_cast<const T*>(x), lab, n, dim, sums.as<float>(),
                                  counts.as<int>())));
     KM_CUDA(cudaGetLastError());
+    const int* donor_ptr = nullptr;
+    if (it + 2 < iters && ncl > 1) {  // the last two iterations are plain Lloyd
+      h_counts.resize(ncl);
+      KM_CUDA(cudaMemcpyAsync(h_counts.data(), counts.ptr, static_cast<size_t>(ncl) * sizeof(int),
+                              cudaMemcpyDeviceToHost, st));
+      KM_CUDA(cudaStreamSynchronize(st));
+      balance_pairs(h_counts, n, &h_donor);
+      KM_CUDA(cudaMemcpyAsync(donors.ptr, h_donor.data(), static_cast<size_t>(ncl) * sizeof(int),
+                              cudaMemcpyHostToDevice, st));
+      donor_ptr = donors.as<int>();
+    }
     DISPATCH_DTYPE(dtype, T, (finalize_centroids_kernel<T><<<ncl, 128, 0, st>>>(
-                                 static_cast<const T*>(x), n, dim, sums.as<float>(), counts.as<int>(),
-                                 seed + 977ull * (it + 1), cent)));
+                                 static_cast<const T*>(x), lab, n, dim, sums.as<float>(),
+                                 counts.as<int>(), donor_ptr, seed + 977ull * (it + 1), cent)));
     KM_CUDA(cudaGetLastError());
   }
   if (labels_out) {

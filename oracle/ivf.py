@@ -25,7 +25,34 @@ from typing import Tuple
 import torch
 
 
-def kmeans(x: torch.Tensor, n_clusters: int, iters: int = 20, seed: int = 0) -> torch.Tensor:
+def balance_pairs(counts, n):
+    """Clusters above 1.5x the average size want floor(size/avg) - 1 extra centroids, taken from
+    the smallest clusters below 0.5x the average. Returns donor_of[c] (-1 = keep)."""
+    ncl = len(counts)
+    donor = [-1] * ncl
+    avg = n / float(ncl)
+    order = sorted(range(ncl), key=lambda c: counts[c])
+    lo, hi = 0, ncl - 1
+    while lo < hi:
+        big = order[hi]
+        if counts[big] <= 1.5 * avg:
+            break
+        quota = max(1, int(counts[big] / avg) - 1)
+        while quota > 0 and lo < hi and counts[order[lo]] < 0.5 * avg:
+            donor[order[lo]] = big
+            lo += 1
+            quota -= 1
+        if quota > 0:
+            break
+        hi -= 1
+    return donor
+
+
+def kmeans(x: torch.Tensor, n_clusters: int, iters: int = 20, seed: int = 0,
+           balance: bool = True) -> torch.Tensor:
+    """Lloyd iterations with the balancing step of cuVS's balanced k-means restated simply: except
+    in the last two iterations, under-full clusters restart on a data row of an over-full cluster
+    (pairing in ``balance_pairs``); empty clusters always restart on a data row."""
     x = x.to(torch.float32)
     n = x.shape[0]
     g = torch.Generator().manual_seed(seed)
@@ -33,12 +60,16 @@ def kmeans(x: torch.Tensor, n_clusters: int, iters: int = 20, seed: int = 0) -> 
     for it in range(iters):
         lab = assign(x, cent)
         sums = torch.zeros_like(cent).index_add_(0, lab, x)
-        cnt = torch.bincount(lab, minlength=n_clusters).to(torch.float32)
-        empty = cnt == 0
-        cent = sums / cnt.clamp_min(1.0)[:, None]
-        if empty.any():
-            repl = torch.randint(0, n, (int(empty.sum()),), generator=g)
-            cent[empty] = x[repl]
+        cnt = torch.bincount(lab, minlength=n_clusters)
+        cent = sums / cnt.clamp_min(1).to(torch.float32)[:, None]
+        donor = balance_pairs(cnt.tolist(), n) if (balance and it + 2 < iters and n_clusters > 1) \
+            else [-1] * n_clusters
+        for c in range(n_clusters):
+            if donor[c] >= 0:
+                rows = torch.nonzero(lab == donor[c])[:, 0]
+                cent[c] = x[rows[torch.randint(0, rows.numel(), (1,), generator=g)]]
+            elif cnt[c] == 0:
+                cent[c] = x[torch.randint(0, n, (1,), generator=g)]
     return cent
 
 
