@@ -61,6 +61,26 @@ def load_peaks():
         return {"tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic(world, args):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r1_c2_bf_tc_fullpass.csv); only valid for the exact configuration it was taken on."""
+    if world != 1 or (args.n_db, args.dim, args.queries, args.k) != (N_DB, DIM, N_QUERIES, K):
+        return None
+    try:
+        import csv
+        with open(os.path.join(ROOT, "profiles", "r1_c2_bf_tc_fullpass.csv")) as f:
+            rows = list(csv.reader(f))
+        h, units, v = rows[0], rows[1], rows[2]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = h.index(name)
+            tot += float(v[i]) * scale.get(units[i], 1.0)
+        return tot
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -288,7 +308,7 @@ def main():
     if rank == 0 and world == 1:
         try:
             from oracle.exact import topk_parity_report
-            nchk = min(n_local, 20000)
+            nchk = min(n_local, 300000)   # 1172 tiles: exercises the seeded multi-pass path
             sub = b2.NativeIndex.flat(shard[:nchk], metric="sqeuclidean")
             dd, ii = sub.search(q_dev[:64], args.k)
             rep = topk_parity_report(dd.cpu(), ii.cpu(), shard[:nchk].float().cpu(),
@@ -316,7 +336,7 @@ def main():
                        "n_splits": stats.n_splits, "grid": stats.grid},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
                          "unit": "TFLOP/s", "frac": (achieved / peaks["tflops"]) if achieved else None,
-                         "traffic": None, "kernel": "bf_tc_kernel", "kernel_ms": kms,
+                         "traffic": ncu_traffic(world, args), "kernel": "bf_tc_kernel", "kernel_ms": kms,
                          "algorithmic_flops_per_launch": flops_per_launch,
                          "peak_source": peaks["source"]},
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d,

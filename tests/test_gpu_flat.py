@@ -173,3 +173,40 @@ def test_sharded_search_equals_single_shard(b2):
     # split invariance: forcing a different db decomposition must not change the answer
     d3, i3 = b2.NativeIndex.flat(db).search(qs, 100, n_splits=3)
     assert (i3 == i1).float().mean().item() > 0.9995
+
+
+def test_three_pass_threshold_seeding_at_large_n(b2):
+    """N >= 8192 tiles triggers the stride-256 / stride-16 / full pass chain; ids must still match
+    an exact fp32 search (checked with the blocked CPU oracle on a query subset)."""
+    from oracle.exact import exact_knn
+    g = torch.Generator(device="cuda").manual_seed(17)
+    n, d = 2_200_000, 64
+    db = torch.randn(n, d, generator=g, device="cuda").to(torch.bfloat16)
+    qs = torch.randn(384, d, generator=g, device="cuda").to(torch.bfloat16)
+    ix = b2.NativeIndex.flat(db)
+    for k in (10, 100):
+        dd, ii = ix.search(qs, k)
+        torch.cuda.synchronize()
+        rd, ri = exact_knn(db.float().cpu(), qs[:48].float().cpu(), k)
+        same = (ii[:48].cpu() == ri).float().mean().item()
+        assert same > 0.999, (k, same)
+        assert torch.allclose(dd[:48].cpu(), rd, rtol=1e-3, atol=1e-2)
+        assert (dd[:, 1:] >= dd[:, :-1]).all()
+        assert ix.last_stats().launches >= 6      # 3 fused launches + 3 merges (+ query norms)
+
+
+def test_adversarial_order_sorted_database(b2):
+    """Rows sorted by distance to the query direction (best rows LAST) defeat the sampled
+    thresholds; the compaction fallback must keep the result exact."""
+    from oracle.exact import topk_parity_report
+    g = torch.Generator().manual_seed(23)
+    n, d = 70000, 32
+    db = torch.randn(n, d, generator=g)
+    q = torch.randn(4, d, generator=g)
+    order = torch.argsort(((db - q[0]) ** 2).sum(1), descending=True)
+    db = db[order].to(torch.bfloat16)
+    qs = q.to(torch.bfloat16)
+    ix = b2.NativeIndex.flat(db.cuda())
+    dd, ii = ix.search(qs.cuda(), 100)
+    torch.cuda.synchronize()
+    assert topk_parity_report(dd.cpu(), ii.cpu(), db.float(), qs.float(), 100, rtol=RTOL)["ok"]
