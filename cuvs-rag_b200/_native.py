@@ -224,7 +224,8 @@ class NativeIndex:
         _check(getattr(L, fn)(db.device.index, m, dtype_code(db.dtype), db.shape[1], db.data_ptr(),
                               db.shape[0], int(id_offset), ctypes.byref(p),
                               _stream_ptr(db.device, stream), ctypes.byref(out)), fn)
-        return cls(out.value, db.device, m, keepalive=None)
+        # IVF-PQ borrows the source rows for refine; IVF-Flat owns a copy of everything it needs
+        return cls(out.value, db.device, m, keepalive=db if pq_dim else None)
 
     # ------------------------------------------------------------------ search
     def search(self, queries: torch.Tensor, k: int, n_probes: int = 0, refine_ratio: int = 0,

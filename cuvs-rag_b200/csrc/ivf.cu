@@ -40,7 +40,8 @@ struct IvfData {
   DevBuf slot_norm;   // IVF-Flat: f32 [n_slots] ||x||^2
   DevBuf codebooks;   // IVF-PQ: f32 [pq_dim, 256, dsub]
   DevBuf codes;       // IVF-PQ: u8, 32-row groups interleaved by 16-byte chunks
-  DevBuf ws_probe_d, ws_probe_i, ws_keys, ws_qf, ws_qnorm, ws_counter;
+  DevBuf ws_probe_d, ws_probe_i, ws_keys, ws_qf, ws_qnorm, ws_counter, ws_ref_d, ws_ref_i;
+  const void* src_rows = nullptr;  // IVF-PQ: the caller's [n, dim] rows, BORROWED for refine
   std::vector<int32_t> h_sizes;
   b2vs_search_stats stats{};
   bool counter_pending = false;
@@ -56,7 +57,8 @@ struct IvfData {
     if (ev1) cudaEventDestroy(ev1);
     ev0 = ev1 = nullptr;
     for (DevBuf* b : {&centroids, &offsets, &sizes, &row_ids, &data, &slot_norm, &codebooks, &codes,
-                      &ws_probe_d, &ws_probe_i, &ws_keys, &ws_qf, &ws_qnorm, &ws_counter})
+                      &ws_probe_d, &ws_probe_i, &ws_keys, &ws_qf, &ws_qnorm, &ws_counter,
+                      &ws_ref_d, &ws_ref_i})
       b->release();
   }
 };
@@ -625,6 +627,58 @@ ivf_pq_scan_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict
                         out_keys + (static_cast<size_t>(p) * q_pad + q) * k);
 }
 
+// Refine (cuVS `refine` / FAISS IndexRefineFlat semantics): exact re-rank of the k' ADC candidates
+// of each query against the original rows.  One warp per query: lanes split the dimensions,
+// candidate j's exact score lands in lane j % 32, a 128-key warp sort orders them.
+template <typename T>
+__global__ void refine_kernel(const T* __restrict__ rows, int dim, const float* __restrict__ qf,
+                              int dp, const long long* __restrict__ cand, int nq, int k_in, int k_out,
+                              int metric, long long id_offset, float* __restrict__ out_d,
+                              long long* __restrict__ out_i) {
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  u64 key[kListE];
+#pragma unroll
+  for (int e = 0; e < kListE; ++e) key[e] = kKeyInf;
+  const float* qv = qf + static_cast<size_t>(q) * dp;
+  for (int j = 0; j < k_in; ++j) {
+    const long long row = cand[static_cast<size_t>(q) * k_in + j];  // shard-local row, -1 = none
+    float acc = 0.f;
+    if (row >= 0) {
+      const T* x = rows + static_cast<size_t>(row) * dim;
+      for (int t = lane; t < dim; t += 32) {
+        const float xv = ld_f32<T>(x + t);
+        if (metric == B2VS_METRIC_L2) { const float df = qv[t] - xv; acc = fmaf(df, df, acc); }
+        else acc = fmaf(-qv[t], xv, acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    // blocked layout of the warp sort: element j lives in lane j / kListE, register j % kListE
+    if (row >= 0 && lane == j / kListE) {
+#pragma unroll
+      for (int e = 0; e < kListE; ++e)
+        if (e == j % kListE) key[e] = pack_key(acc, static_cast<uint32_t>(row));
+    }
+  }
+  warp_bitonic_sort<kListE>(key, lane);
+#pragma unroll
+  for (int e = 0; e < kListE; ++e) {
+    const int i = lane * kListE + e;
+    if (i >= k_out) continue;
+    const size_t o = static_cast<size_t>(q) * k_out + i;
+    if (key[e] == kKeyInf) {
+      out_d[o] = metric == B2VS_METRIC_L2 ? INFINITY : -INFINITY;
+      out_i[o] = -1;
+    } else {
+      const float sc = key_score(key[e]);
+      out_d[o] = metric == B2VS_METRIC_L2 ? sc : -sc;
+      out_i[o] = static_cast<long long>(key_id(key[e])) + id_offset;
+    }
+  }
+}
+
 // queries -> fp32 [nq, dp] (+ ||q||^2)
 template <typename T>
 __global__ void queries_to_f32_kernel(const T* __restrict__ q, int nq, int dim, int dp, int fmt,
@@ -672,6 +726,10 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
   B2VS_CHECK(k >= 1 && k <= kMaxFusedK, B2VS_EUNSUP, "k=%d outside [1, %d]", k, kMaxFusedK);
   int n_probes = sp.n_probes > 0 ? sp.n_probes : 20;  // cuVS SearchParams default
   n_probes = std::min(n_probes, std::min(d->n_lists, kMaxFusedK));
+  // IVF-PQ refine: scan for k' = refine_ratio * k ADC candidates, then re-rank them exactly
+  const bool refine = index->kind == B2VS_KIND_IVF_PQ && sp.refine_ratio > 1 && d->src_rows != nullptr;
+  const int k_final = k;
+  if (refine) k = std::min(kMaxFusedK, k * sp.refine_ratio);
   const int q_pad = static_cast<int>(round_up(nq, 128));
   B2VS_TRY(d->ws_probe_d.reserve(static_cast<size_t>(nq) * n_probes * sizeof(float)));
   B2VS_TRY(d->ws_probe_i.reserve(static_cast<size_t>(nq) * n_probes * sizeof(int64_t)));
@@ -725,10 +783,26 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
   }
   if (timed) B2VS_CUDA(cudaEventRecord(d->ev1, st));
   ++launches;
-  B2VS_TRY(launch_merge_splits(d->ws_keys.as<u64>(), n_probes, q_pad, nq, k, index->metric,
-                               qnorm_for_merge, index->id_offset, out_d, out_i, nullptr, st,
-                               d->row_ids.as<uint32_t>()));
-  ++launches;
+  if (!refine) {
+    B2VS_TRY(launch_merge_splits(d->ws_keys.as<u64>(), n_probes, q_pad, nq, k, index->metric,
+                                 qnorm_for_merge, index->id_offset, out_d, out_i, nullptr, st,
+                                 d->row_ids.as<uint32_t>()));
+    ++launches;
+  } else {
+    B2VS_TRY(d->ws_ref_d.reserve(static_cast<size_t>(nq) * k * sizeof(float)));
+    B2VS_TRY(d->ws_ref_i.reserve(static_cast<size_t>(nq) * k * sizeof(int64_t)));
+    B2VS_TRY(launch_merge_splits(d->ws_keys.as<u64>(), n_probes, q_pad, nq, k, index->metric,
+                                 qnorm_for_merge, 0, d->ws_ref_d.as<float>(),
+                                 d->ws_ref_i.as<int64_t>(), nullptr, st, d->row_ids.as<uint32_t>()));
+    DISPATCH_DTYPE(index->dtype, T, (refine_kernel<T><<<static_cast<unsigned>(ceil_div(nq, 4)), 128, 0, st>>>(
+                                        static_cast<const T*>(d->src_rows), index->dim,
+                                        d->ws_qf.as<float>(), d->dp,
+                                        reinterpret_cast<const long long*>(d->ws_ref_i.ptr), nq, k,
+                                        k_final, index->metric, index->id_offset, out_d,
+                                        reinterpret_cast<long long*>(out_i))));
+    B2VS_CUDA(cudaGetLastError());
+    launches += 2;
+  }
   d->stats = b2vs_search_stats{};
   d->stats.launches = launches;
   d->stats.n_splits = n_probes;
@@ -821,6 +895,7 @@ static int ivf_build(int kind, int dev, int metric, int dtype, int dim, const vo
   d->dp = static_cast<int>(round_up(dim, 8));
   d->fmt = (dtype == B2VS_F16) ? 0 : 1;
   d->row_bytes = (kind == B2VS_KIND_IVF_FLAT) ? d->dp * 2 : pq_dim;
+  if (kind == B2VS_KIND_IVF_PQ) d->src_rows = db;  // borrowed: only dereferenced by refine
 
   DevBuf train, labels, cursor, slot_of_row, slices;
   FlatEngine assign_eng;

@@ -67,7 +67,7 @@ typedef struct b2vs_ivf_params {
 
 typedef struct b2vs_search_params {
   int32_t n_probes;       /* IVF: lists scanned per query (cuVS SearchParams.n_probes, default 20) */
-  int32_t refine_ratio;   /* IVF-PQ: exact re-rank of refine_ratio*k candidates (0/1 = off) */
+  int32_t refine_ratio;   /* IVF-PQ: exact re-rank of min(128, refine_ratio*k) ADC candidates (0/1 = off) */
   int32_t n_splits;       /* flat: force the number of db splits (0 = heuristic) */
   int32_t flags;          /* bit 0: time the dominant kernel with CUDA events (see stats.kernel_ms) */
 } b2vs_search_params;
@@ -110,7 +110,9 @@ int b2vs_ivfflat_build(int dev, int metric, int dtype, int dim, const void* db, 
                        int64_t id_offset, const b2vs_ivf_params* params, void* stream,
                        b2vs_index** out);
 
-/* IVF-PQ: coarse quantizer + per-subspace 256-entry codebooks on residuals, 8-bit codes. */
+/* IVF-PQ: coarse quantizer + per-subspace 256-entry codebooks on residuals, 8-bit codes.
+ * `db` is additionally BORROWED for searches with refine_ratio > 1 (exact re-rank against the
+ * original rows); callers that never refine may free it after the build. */
 int b2vs_ivfpq_build(int dev, int metric, int dtype, int dim, const void* db, int64_t n,
                      int64_t id_offset, const b2vs_ivf_params* params, void* stream,
                      b2vs_index** out);

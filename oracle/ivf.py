@@ -150,7 +150,12 @@ class IvfPqOracle(IvfFlatOracle):
             codes[:, m] = assign(res[:, m * self.dsub:(m + 1) * self.dsub], self.codebooks[m])
         self.codes = codes
 
-    def search(self, q: torch.Tensor, k: int, n_probes: int = 20):
+    def search(self, q: torch.Tensor, k: int, n_probes: int = 20, refine_ratio: int = 1):
+        """ADC search; ``refine_ratio > 1`` re-ranks the best refine_ratio*k ADC candidates with
+        exact distances to the original rows (cuVS ``refine`` semantics)."""
+        if refine_ratio > 1:
+            _, cand = self.search(q, min(128, k * refine_ratio), n_probes, 1)
+            return self._refine(q.to(torch.float32), cand, k)
         q = q.to(torch.float32)
         pr = self.probes(q, n_probes)
         out_d = torch.full((q.shape[0], k), float("inf"))
@@ -177,6 +182,22 @@ class IvfPqOracle(IvfFlatOracle):
                 continue
             sc = torch.cat(cand_s)
             rows = torch.cat(cand_r)
+            kk = min(k, rows.numel())
+            d, pos = torch.topk(sc, kk, largest=False, sorted=True)
+            out_d[qi, :kk] = d if l2 else -d
+            out_i[qi, :kk] = rows[pos]
+        return out_d, out_i
+
+    def _refine(self, q, cand, k):
+        l2 = self.metric in ("sqeuclidean", "l2", "L2")
+        out_d = torch.full((q.shape[0], k), float("inf") if l2 else float("-inf"))
+        out_i = torch.full((q.shape[0], k), -1, dtype=torch.int64)
+        for qi in range(q.shape[0]):
+            rows = cand[qi][cand[qi] >= 0]
+            if rows.numel() == 0:
+                continue
+            xs = self.db[rows]
+            sc = ((xs - q[qi][None, :]) ** 2).sum(1) if l2 else -(xs @ q[qi])
             kk = min(k, rows.numel())
             d, pos = torch.topk(sc, kk, largest=False, sorted=True)
             out_d[qi, :kk] = d if l2 else -d

@@ -96,3 +96,24 @@ def test_ivf_build_argument_errors(b2):
         b2.NativeIndex.ivf_flat(x, 5000)
     with pytest.raises(RuntimeError, match="must divide dim"):
         b2.NativeIndex.ivf_pq(x, 8, 5)
+
+
+def test_ivf_pq_refine_lifts_recall_like_the_oracle(b2):
+    from oracle.exact import exact_knn
+    from oracle.ivf import IvfPqOracle, recall
+    n, d, nlist, nprobe, k, m = 40000, 64, 64, 16, 10, 16     # dsub = 4: coarse codes
+    x = clustered(n, d, 100, 8).to(torch.float16)
+    q = queries_from(x.float(), 200, 9).to(torch.float16)
+    ix = b2.NativeIndex.ivf_pq(x.cuda(), nlist, m, kmeans_iters=10, id_offset=3)
+    _, ti = exact_knn(x.float(), q.float(), k)
+    _, g0 = ix.search(q.cuda(), k, n_probes=nprobe)
+    d1, g1 = ix.search(q.cuda(), k, n_probes=nprobe, refine_ratio=8)
+    r0, r1 = recall(g0.cpu() - 3, ti), recall(g1.cpu() - 3, ti)
+    oracle = IvfPqOracle(x.float(), nlist, m, iters=10, pq_iters=10)
+    _, o1 = oracle.search(q.float(), k, n_probes=nprobe, refine_ratio=8)
+    ro = recall(o1, ti)
+    assert r1 > r0 + 0.05 and abs(r1 - ro) < 0.06, (r0, r1, ro)
+    # refined distances are exact for the returned ids
+    d1, g1 = d1.cpu(), g1.cpu() - 3
+    true = ((x.float()[g1.clamp_min(0)] - q.float()[:, None, :]) ** 2).sum(2)
+    assert torch.allclose(d1, true, rtol=2e-3, atol=2e-3)

@@ -35,12 +35,12 @@ else:
 torch.cuda.synchronize()
 build_s = time.time() - t0
 sizes = ix.list_sizes()
-out = {"kind": kind, "n": n, "dim": d, "n_lists": nlist, "n_probes": nprobe, "nq": nq, "build_s": round(build_s, 2),
+out = {"refine": int(os.environ.get("REFINE", 0)), "kind": kind, "n": n, "dim": d, "n_lists": nlist, "n_probes": nprobe, "nq": nq, "build_s": round(build_s, 2),
        "list_min": int(sizes.min()), "list_max": int(sizes.max()), "list_mean": float(sizes.float().mean())}
 for rep in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    dd, ii = ix.search(q, k, n_probes=nprobe, time_kernel=True)
+    dd, ii = ix.search(q, k, n_probes=nprobe, time_kernel=True, refine_ratio=int(os.environ.get('REFINE', 0)))
     e1.record(); torch.cuda.synchronize()
     st = ix.last_stats()
     out[f"search_ms_{rep}"] = round(e0.elapsed_time(e1), 3)
