@@ -226,11 +226,13 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             if (G == 2) {
               const uint32_t fb = full_leader + 8 * stage;
               ptx::mbar_arrive_expect_tx_cluster(fb, kStageBytes);
-              ptx::tma_load_2d_2sm(a_dst, &tm_q, fb, kb * kBK, q_row0);
+              ptx::tma_load_2d_2sm_hint(a_dst, &tm_q, fb, kb * kBK, q_row0, ptx::kEvictLast);
               ptx::tma_load_2d_2sm(a_dst + Cfg::kABytes, &tm_x, fb, kb * kBK, x_row0);
             } else {
               ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
-              ptx::tma_load_2d(a_dst, &tm_q, bar_full + 8 * stage, kb * kBK, q_row0);
+              // the query block is re-read for every db tile: ask L2 to keep it (evict-last)
+              ptx::tma_load_2d_hint(a_dst, &tm_q, bar_full + 8 * stage, kb * kBK, q_row0,
+                                    ptx::kEvictLast);
               ptx::tma_load_2d(a_dst + Cfg::kABytes, &tm_x, bar_full + 8 * stage, kb * kBK, x_row0);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }

@@ -627,6 +627,212 @@ ivf_pq_scan_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict
                         out_keys + (static_cast<size_t>(p) * q_pad + q) * k);
 }
 
+// Query-major persistent variant of the PQ scan for indexes whose codebooks fit in shared memory
+// (pq_dim * 256 * dsub floats <= 128 KB, e.g. C4: M = 64, dsub = 2).  One CTA per SM keeps the
+// codebooks resident and owns whole queries: it walks the query's probes, rebuilding the LUT from
+// smem for each list, while every warp's sorted top-k list and threshold persist ACROSS the
+// probes.  Compared with one CTA per (query, probe) this removes the 128 KB L2 read per LUT, the
+// threshold warm-up of every list and all but one block-level merge per query.
+constexpr int kPqPersistThreads = 512;
+constexpr int kPqPersistWarps = kPqPersistThreads / 32;
+
+template <int NCH, int DSUB>  // code chunks per row (mp / 16) and sub-vector length; 0 = runtime
+__global__ void __launch_bounds__(kPqPersistThreads, 1)
+ivf_pq_scan_query_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ row_ids,
+                         const uint32_t* __restrict__ offsets, const long long* __restrict__ probe_ids,
+                         const float* __restrict__ qf, const float* __restrict__ cent,
+                         const float* __restrict__ codebooks, int dim, int dp, int pq_dim, int mp,
+                         int dsub, int n_probes, int nq, int k, int metric, u64* __restrict__ out_keys,
+                         unsigned long long* __restrict__ scanned_rows) {
+  extern __shared__ float smem_f[];
+  float* cb = smem_f;                                // [pq_dim * 256 * dsub]
+  float* lut = cb + pq_dim * 256 * dsub;             // [mp * 256]
+  float* rq = lut + mp * 256;                        // [dim] residual query of the current probe
+  float* sq = rq + dim;                              // [dim] the query
+  __shared__ u64 lists[kPqPersistWarps][32 * kListE];
+  __shared__ float bias_part[kPqPersistWarps];
+  __shared__ int s_list[kMaxFusedK];
+  __shared__ uint32_t s_begin[kMaxFusedK], s_end[kMaxFusedK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < pq_dim * 256 * dsub; i += blockDim.x) cb[i] = codebooks[i];
+  for (int i = pq_dim * 256 + threadIdx.x; i < mp * 256; i += blockDim.x) lut[i] = 0.f;  // padding rows
+  unsigned long long rows_seen = 0;
+  constexpr int kV = NCH > 0 ? NCH : 1;
+  const int n_chunks = NCH > 0 ? NCH : (mp >> 4);
+  const uint4* codes4 = reinterpret_cast<const uint4*>(codes);
+  for (int q = blockIdx.x; q < nq; q += gridDim.x) {
+    __syncthreads();  // previous query fully retired (lists, s_*, sq)
+    // the query's probe lists and their extents, fetched once in parallel
+    if (threadIdx.x < n_probes) {
+      const long long l = probe_ids[static_cast<size_t>(q) * n_probes + threadIdx.x];
+      s_list[threadIdx.x] = static_cast<int>(l);
+      s_begin[threadIdx.x] = l >= 0 ? offsets[l] : 0u;
+      s_end[threadIdx.x] = l >= 0 ? offsets[l + 1] : 0u;
+    }
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) sq[d] = qf[static_cast<size_t>(q) * dp + d];
+    __syncthreads();
+    WarpTopK tk;
+    tk.init();
+    // centroid values of the NEXT probe travel in registers while the current probe is scanned
+    float c_next[2] = {0.f, 0.f};
+    {
+      const int l0 = s_list[0];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int d = threadIdx.x + t * kPqPersistThreads;
+        if (d < dim && l0 >= 0) c_next[t] = cent[static_cast<size_t>(l0) * dim + d];
+      }
+    }
+    for (int p = 0; p < n_probes; ++p) {
+      const int list = s_list[p];
+      const uint32_t begin = s_begin[p], end = s_end[p];
+      rows_seen += (threadIdx.x == 0) ? (end - begin) : 0u;
+      // issue this warp's first code loads now: they complete during the rq / LUT phases
+      const uint32_t g_first = (begin >> 5) + warp;
+      uint4 v[kV];
+      uint32_t rid = kNoRow;
+      if (NCH > 0 && g_first < (end >> 5)) {
+#pragma unroll
+        for (int ch = 0; ch < kV; ++ch)
+          v[ch] = __ldg(codes4 + (static_cast<size_t>(g_first) * kV + ch) * 32 + lane);
+        rid = __ldg(row_ids + (g_first << 5) + lane);
+      }
+      float bpart = 0.f;
+      const float c_cur[2] = {c_next[0], c_next[1]};
+      if (p + 1 < n_probes) {
+        const int ln = s_list[p + 1];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int d = threadIdx.x + t * kPqPersistThreads;
+          if (d < dim && ln >= 0) c_next[t] = cent[static_cast<size_t>(ln) * dim + d];
+        }
+      }
+      __syncthreads();  // the previous probe's LUT / rq are no longer read
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int d = threadIdx.x + t * kPqPersistThreads;
+        if (d < dim) {
+          const float qv = sq[d];
+          if (metric == B2VS_METRIC_L2) rq[d] = qv - c_cur[t];
+          else { rq[d] = qv; bpart = fmaf(qv, c_cur[t], bpart); }
+        }
+      }
+      for (int d = threadIdx.x + 2 * kPqPersistThreads; d < dim; d += kPqPersistThreads) {  // dim > 1024
+        const float qv = sq[d];
+        const float cv = list >= 0 ? cent[static_cast<size_t>(list) * dim + d] : 0.f;
+        if (metric == B2VS_METRIC_L2) rq[d] = qv - cv;
+        else { rq[d] = qv; bpart = fmaf(qv, cv, bpart); }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) bpart += __shfl_xor_sync(0xffffffffu, bpart, o);
+      if (lane == 0) bias_part[warp] = bpart;
+      __syncthreads();
+      float bias = 0.f;
+#pragma unroll
+      for (int w = 0; w < kPqPersistWarps; ++w) bias += bias_part[w];
+      bias = -bias;
+      if (DSUB > 0) {
+        // specialised LUT build: sub-vector length known at compile time, metric hoisted
+        if (metric == B2VS_METRIC_L2) {
+          for (int idx = threadIdx.x; idx < pq_dim * 256; idx += kPqPersistThreads) {
+            const float* cbp = cb + idx * DSUB;
+            const float* rqm = rq + (idx >> 8) * DSUB;
+            float sacc = 0.f;
+#pragma unroll
+            for (int d = 0; d < DSUB; ++d) {
+              const float t = rqm[d] - cbp[d];
+              sacc = fmaf(t, t, sacc);
+            }
+            lut[idx] = sacc;
+          }
+        } else {
+          for (int idx = threadIdx.x; idx < pq_dim * 256; idx += kPqPersistThreads) {
+            const float* cbp = cb + idx * DSUB;
+            const float* rqm = rq + (idx >> 8) * DSUB;
+            float sacc = 0.f;
+#pragma unroll
+            for (int d = 0; d < DSUB; ++d) sacc = fmaf(-rqm[d], cbp[d], sacc);
+            lut[idx] = sacc;
+          }
+        }
+      } else {
+        for (int idx = threadIdx.x; idx < pq_dim * 256; idx += blockDim.x) {
+          const int m = idx >> 8;
+          const float* cbp = cb + static_cast<size_t>(idx) * dsub;
+          float sacc = 0.f;
+          for (int d = 0; d < dsub; ++d) {
+            if (metric == B2VS_METRIC_L2) {
+              const float t = rq[m * dsub + d] - cbp[d];
+              sacc = fmaf(t, t, sacc);
+            } else {
+              sacc = fmaf(-rq[m * dsub + d], cbp[d], sacc);
+            }
+          }
+          lut[idx] = sacc;
+        }
+      }
+      __syncthreads();
+      for (uint32_t g0 = g_first; g0 < (end >> 5); g0 += kPqPersistWarps) {
+        const uint32_t slot = (g0 << 5) + lane;
+        if (NCH == 0 || g0 != g_first) {
+          if (NCH > 0) {
+#pragma unroll
+            for (int ch = 0; ch < kV; ++ch)
+              v[ch] = __ldg(codes4 + (static_cast<size_t>(g0) * kV + ch) * 32 + lane);
+          }
+          rid = __ldg(row_ids + slot);
+        }
+        float sacc = bias;
+        for (int cc = 0; cc < n_chunks; ++cc) {
+          uint4 vv;
+          if (NCH > 0) {
+            vv = v[0];
+#pragma unroll
+            for (int ch = 1; ch < kV; ++ch)
+              if (ch == cc) vv = v[ch];
+          } else {
+            vv = __ldg(codes4 + (static_cast<size_t>(g0) * n_chunks + cc) * 32 + lane);
+          }
+          const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const int m = cc * 16 + i * 4 + b;
+              sacc += lut[m * 256 + ((w[i] >> (8 * b)) & 0xFFu)];
+            }
+          }
+        }
+        u64 ck = kKeyInf;
+        if (rid != kNoRow && sacc < tk.tau) ck = pack_key(sacc, slot);
+        tk.offer(ck, k, lane);
+      }
+    }
+    // one fold of the warps' lists per query
+#pragma unroll
+    for (int e = 0; e < kListE; ++e) lists[warp][lane * kListE + e] = tk.acc[e];
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 1; w < kPqPersistWarps; ++w) {
+#pragma unroll
+        for (int e = 0; e < kListE; ++e) {
+          const int src = 32 * kListE - 1 - (lane * kListE + e);
+          const u64 b = lists[w][src];
+          tk.acc[e] = tk.acc[e] < b ? tk.acc[e] : b;
+        }
+        warp_bitonic_merge<kListE>(tk.acc, lane);
+      }
+      u64* out = out_keys + static_cast<size_t>(q) * k;
+#pragma unroll
+      for (int e = 0; e < kListE; ++e) {
+        const int i = lane * kListE + e;
+        if (i < k) out[i] = tk.acc[e];
+      }
+    }
+  }
+  if (threadIdx.x == 0 && scanned_rows) atomicAdd(scanned_rows, rows_seen);
+}
+
 // Refine (cuVS `refine` / FAISS IndexRefineFlat semantics): exact re-rank of the k' ADC candidates
 // of each query against the original rows.  One warp per query: lanes split the dimensions,
 // candidate j's exact score lands in lane j % 32, a 128-key warp sort orders them.
@@ -752,6 +958,7 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
   const long long* probe_ids = reinterpret_cast<const long long*>(d->ws_probe_i.ptr);
   unsigned long long* counter = d->ws_counter.as<unsigned long long>();
   const float* qnorm_for_merge = nullptr;
+  bool pq_query_major = false;  // the query-major PQ scan leaves ONE list per query
   const bool timed = (sp.flags & B2VS_FLAG_TIME_KERNEL) != 0;
   if (timed) {
     if (!d->ev0) {
@@ -772,27 +979,52 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
                                    k, alpha, use_norm, d->ws_keys.as<u64>(), counter));
     qnorm_for_merge = d->ws_qnorm.as<float>();
   } else {
-    const size_t smem = (static_cast<size_t>(d->mp) * 256 + index->dim) * sizeof(float);
-    B2VS_CUDA(cudaFuncSetAttribute(ivf_pq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem)));
-    ivf_pq_scan_kernel<<<items, kScanThreads, smem, st>>>(
-        d->codes.as<uint8_t>(), d->row_ids.as<uint32_t>(), d->offsets.as<uint32_t>(), probe_ids,
-        d->ws_qf.as<float>(), d->centroids.as<float>(), d->codebooks.as<float>(), index->dim, d->dp,
-        d->pq_dim, d->mp, d->dsub, n_probes, q_pad, k, index->metric, d->ws_keys.as<u64>(), counter);
+    const size_t cb_floats = static_cast<size_t>(d->pq_dim) * 256 * d->dsub;
+    const size_t smem_p = (cb_floats + static_cast<size_t>(d->mp) * 256 + 2 * index->dim) * sizeof(float);
+    if (smem_p + 20 * 1024 <= 227 * 1024) {
+      // codebooks fit next to the LUT: query-major persistent CTAs, one per SM
+      const int grid = std::min(nq, sm_count(index->dev));
+#define PQ_QUERY_LAUNCH(NCH, DSUB)                                                                      \
+  do {                                                                                            \
+    B2VS_CUDA(cudaFuncSetAttribute((ivf_pq_scan_query_kernel<NCH, DSUB>),                                 \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize,                   \
+                                   static_cast<int>(smem_p)));                                    \
+    ivf_pq_scan_query_kernel<NCH, DSUB><<<grid, kPqPersistThreads, smem_p, st>>>(                       \
+        d->codes.as<uint8_t>(), d->row_ids.as<uint32_t>(), d->offsets.as<uint32_t>(), probe_ids,   \
+        d->ws_qf.as<float>(), d->centroids.as<float>(), d->codebooks.as<float>(), index->dim,      \
+        d->dp, d->pq_dim, d->mp, d->dsub, n_probes, nq, k, index->metric, d->ws_keys.as<u64>(),    \
+        counter);                                                                                 \
+  } while (0)
+      const int nch = d->mp >> 4;
+      if (nch == 4 && d->dsub == 2) PQ_QUERY_LAUNCH(4, 2);
+      else if (nch == 2 && d->dsub == 4) PQ_QUERY_LAUNCH(2, 4);
+      else if (nch == 1 && d->dsub == 8) PQ_QUERY_LAUNCH(1, 8);
+      else PQ_QUERY_LAUNCH(0, 0);
+#undef PQ_QUERY_LAUNCH
+      pq_query_major = true;
+    } else {
+      const size_t smem = (static_cast<size_t>(d->mp) * 256 + index->dim) * sizeof(float);
+      B2VS_CUDA(cudaFuncSetAttribute(ivf_pq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+      ivf_pq_scan_kernel<<<items, kScanThreads, smem, st>>>(
+          d->codes.as<uint8_t>(), d->row_ids.as<uint32_t>(), d->offsets.as<uint32_t>(), probe_ids,
+          d->ws_qf.as<float>(), d->centroids.as<float>(), d->codebooks.as<float>(), index->dim, d->dp,
+          d->pq_dim, d->mp, d->dsub, n_probes, q_pad, k, index->metric, d->ws_keys.as<u64>(), counter);
+    }
     B2VS_CUDA(cudaGetLastError());
   }
   if (timed) B2VS_CUDA(cudaEventRecord(d->ev1, st));
   ++launches;
   if (!refine) {
-    B2VS_TRY(launch_merge_splits(d->ws_keys.as<u64>(), n_probes, q_pad, nq, k, index->metric,
-                                 qnorm_for_merge, index->id_offset, out_d, out_i, nullptr, st,
-                                 d->row_ids.as<uint32_t>()));
+    B2VS_TRY(launch_merge_splits(d->ws_keys.as<u64>(), pq_query_major ? 1 : n_probes, q_pad, nq, k,
+                                 index->metric, qnorm_for_merge, index->id_offset, out_d, out_i,
+                                 nullptr, st, d->row_ids.as<uint32_t>()));
     ++launches;
   } else {
     B2VS_TRY(d->ws_ref_d.reserve(static_cast<size_t>(nq) * k * sizeof(float)));
     B2VS_TRY(d->ws_ref_i.reserve(static_cast<size_t>(nq) * k * sizeof(int64_t)));
-    B2VS_TRY(launch_merge_splits(d->ws_keys.as<u64>(), n_probes, q_pad, nq, k, index->metric,
-                                 qnorm_for_merge, 0, d->ws_ref_d.as<float>(),
+    B2VS_TRY(launch_merge_splits(d->ws_keys.as<u64>(), pq_query_major ? 1 : n_probes, q_pad, nq, k,
+                                 index->metric, qnorm_for_merge, 0, d->ws_ref_d.as<float>(),
                                  d->ws_ref_i.as<int64_t>(), nullptr, st, d->row_ids.as<uint32_t>()));
     DISPATCH_DTYPE(index->dtype, T, (refine_kernel<T><<<static_cast<unsigned>(ceil_div(nq, 4)), 128, 0, st>>>(
                                         static_cast<const T*>(d->src_rows), index->dim,
