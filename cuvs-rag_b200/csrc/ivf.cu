@@ -782,27 +782,32 @@ ivf_pq_scan_query_kernel(const uint8_t* __restrict__ codes, const uint32_t* __re
           }
           rid = __ldg(row_ids + slot);
         }
-        float sacc = bias;
-        for (int cc = 0; cc < n_chunks; ++cc) {
-          uint4 vv;
-          if (NCH > 0) {
-            vv = v[0];
+        // four independent partial sums keep the LDS -> FADD chains short
+        float part[4] = {bias, 0.f, 0.f, 0.f};
+        if (NCH > 0) {
 #pragma unroll
-            for (int ch = 1; ch < kV; ++ch)
-              if (ch == cc) vv = v[ch];
-          } else {
-            vv = __ldg(codes4 + (static_cast<size_t>(g0) * n_chunks + cc) * 32 + lane);
+          for (int cc = 0; cc < kV; ++cc) {
+            const uint32_t w[4] = {v[cc].x, v[cc].y, v[cc].z, v[cc].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+              for (int b = 0; b < 4; ++b)
+                part[b] += lut[(cc * 16 + i * 4 + b) * 256 + ((w[i] >> (8 * b)) & 0xFFu)];
+            }
           }
-          const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
+        } else {
+          for (int cc = 0; cc < n_chunks; ++cc) {
+            const uint4 vv = __ldg(codes4 + (static_cast<size_t>(g0) * n_chunks + cc) * 32 + lane);
+            const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 4; ++i) {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              const int m = cc * 16 + i * 4 + b;
-              sacc += lut[m * 256 + ((w[i] >> (8 * b)) & 0xFFu)];
+              for (int b = 0; b < 4; ++b)
+                part[b] += lut[(cc * 16 + i * 4 + b) * 256 + ((w[i] >> (8 * b)) & 0xFFu)];
             }
           }
         }
+        const float sacc = (part[0] + part[1]) + (part[2] + part[3]);
         u64 ck = kKeyInf;
         if (rid != kNoRow && sacc < tk.tau) ck = pack_key(sacc, slot);
         tk.offer(ck, k, lane);

@@ -117,3 +117,20 @@ def test_ivf_pq_refine_lifts_recall_like_the_oracle(b2):
     d1, g1 = d1.cpu(), g1.cpu() - 3
     true = ((x.float()[g1.clamp_min(0)] - q.float()[:, None, :]) ** 2).sum(2)
     assert torch.allclose(d1, true, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("d,m,label", [(128, 64, "specialised query-major scan (M=64, dsub=2)"),
+                                       (768, 96, "per-(query, probe) scan: codebooks exceed smem")])
+def test_ivf_pq_kernel_variants_match_oracle(b2, d, m, label):
+    from oracle.exact import exact_knn
+    from oracle.ivf import IvfPqOracle, recall
+    n, nlist, nprobe, k = 20000, 32, 8, 10
+    x = clustered(n, d, 60, 12).to(torch.float16)
+    q = queries_from(x.float(), 100, 13).to(torch.float16)
+    ix = b2.NativeIndex.ivf_pq(x.cuda(), nlist, m, kmeans_iters=8)
+    _, ti = exact_knn(x.float(), q.float(), k)
+    _, gi = ix.search(q.cuda(), k, n_probes=nprobe, refine_ratio=4)
+    oracle = IvfPqOracle(x.float(), nlist, m, iters=8, pq_iters=8)
+    _, oi = oracle.search(q.float(), k, n_probes=nprobe, refine_ratio=4)
+    r_gpu, r_ref = recall(gi.cpu(), ti), recall(oi, ti)
+    assert abs(r_gpu - r_ref) < 0.07, (label, r_gpu, r_ref)
