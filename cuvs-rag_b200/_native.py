@@ -19,12 +19,13 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libb2vs.so")
-SOURCES = ["api.cu", "flat.cu", "merge.cu", "ivf.cu"]
+SOURCES = ["api.cu", "flat.cu", "merge.cu", "ivf.cu", "bigk.cu"]
 
 METRIC_L2, METRIC_IP = 0, 1
 F32, F16, BF16 = 0, 1, 2
 KIND_FLAT, KIND_IVF_FLAT, KIND_IVF_PQ = 0, 1, 2
 MAX_FUSED_K = 128
+MAX_K = 2048   # flat indexes and merges; IVF searches stay at MAX_FUSED_K
 
 _DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 _METRIC_CODE = {

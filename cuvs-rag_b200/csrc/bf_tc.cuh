@@ -64,17 +64,27 @@ struct BfTcParams {
   int k;                // 1..kMaxFusedK
   float alpha;          // -2 (L2) or -1 (inner product)
   uint32_t idesc;
+  // large-k mode (k > kMaxFusedK): every score below the row's (fixed) threshold is appended to a
+  // per-query global buffer shared by all splits; selection happens in bigk.cu
+  u64* big_cand;        // [q_pad][big_cap] or NULL
+  int* big_count;       // [q_pad] atomic append cursors
+  int big_cap;
 };
+
+constexpr int kModeBuffer = 0;   // per-(CTA,row) candidate buffer + warp compaction (k <= 128)
+constexpr int kModeArgmin = 1;   // k == 1: running arg-min in a register
+constexpr int kModeAppend = 2;   // large k: atomic append to the query's global buffer
 
 
 // Scores one 32-column chunk of one query row held in registers: score = alpha*acc + beta.
 // Fast path (almost always taken once the threshold has warmed up): a min-reduction and ONE
 // compare, no per-element branches.  Slow path: append every score below the threshold to the
 // row's candidate buffer (or track the arg-min when k == 1).
-template <bool kArgmin>
+template <int kMode>
 __device__ __forceinline__ void score_chunk(const uint32_t (&r)[32], const float4* __restrict__ nrm4,
                                             float alpha, uint32_t col, float& tau, int& cnt,
-                                            u64& best, u64* __restrict__ my_cand) {
+                                            u64& best, u64* __restrict__ my_cand,
+                                            int* __restrict__ g_cnt = nullptr, int g_cap = 0) {
   float sc[32];
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
@@ -91,7 +101,7 @@ __device__ __forceinline__ void score_chunk(const uint32_t (&r)[32], const float
   const float mn = fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])),
                          fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
   if (mn < tau) {
-    if (kArgmin) {
+    if (kMode == kModeArgmin) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         if (sc[j] < tau) {
@@ -119,8 +129,13 @@ __device__ __forceinline__ void score_chunk(const uint32_t (&r)[32], const float
 #pragma unroll
         for (int i = 0; i < 2; ++i) v2[i] = (j & 8) ? v4[2 * i + 1] : v4[2 * i];
         const float v = (j & 16) ? v2[1] : v2[0];
-        __stcg(my_cand + cnt, pack_key(v, col + j));
-        ++cnt;
+        if (kMode == kModeAppend) {
+          const int pos = atomicAdd(g_cnt, 1);
+          if (pos < g_cap) __stcg(my_cand + pos, pack_key(v, col + j));
+        } else {
+          __stcg(my_cand + cnt, pack_key(v, col + j));
+          ++cnt;
+        }
       }
     }
   }
@@ -291,9 +306,12 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       const int s = item / p.n_qblocks;
       const int t0 = s * p.tiles_per_split;
       const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
+      const size_t q_row = static_cast<size_t>(qb) * (kBM * G) + cta_rank * kBM + ew * 32 + lane;
       float tau = inf;
-      if (p.tau_init != nullptr)
-        tau = p.tau_init[static_cast<size_t>(qb) * (kBM * G) + cta_rank * kBM + ew * 32 + lane];
+      if (p.tau_init != nullptr) tau = p.tau_init[q_row];
+      const int mode = p.big_cand ? kModeAppend : (p.k == 1 ? kModeArgmin : kModeBuffer);
+      u64* const row_buf = p.big_cand ? p.big_cand + q_row * p.big_cap : my_cand;
+      int* const row_cnt = p.big_cand ? p.big_count + q_row : nullptr;
       int cnt = 0;
       u64 best = kKeyInf;  // k == 1 fast path keeps the running arg-min in a register
       for (int ti = t0; ti < t1; ++ti, ++tcount) {
@@ -312,9 +330,14 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         for (int c2 = 0; c2 < kBN / 64; ++c2) {
           ptx::tmem_ld_wait();
           ptx::tmem_ld_32x32b_x32(tile_taddr + c2 * 64 + 32, rb);
-          if (p.k == 1) score_chunk<true>(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, cnt, best, my_cand);
-          else score_chunk<false>(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, cnt, best, my_cand);
-          if (p.k != 1) compact_if_needed(cnt, tau, cand_warp, p.k, lane);
+          if (mode == kModeArgmin)
+            score_chunk<kModeArgmin>(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, cnt, best, row_buf);
+          else if (mode == kModeAppend)
+            score_chunk<kModeAppend>(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, cnt, best, row_buf,
+                                     row_cnt, p.big_cap);
+          else
+            score_chunk<kModeBuffer>(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, cnt, best, row_buf);
+          if (mode == kModeBuffer) compact_if_needed(cnt, tau, cand_warp, p.k, lane);
           ptx::tmem_ld_wait();
           if (c2 + 1 < kBN / 64) {
             ptx::tmem_ld_32x32b_x32(tile_taddr + c2 * 64 + 64, ra);
@@ -327,19 +350,25 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
               else ptx::mbar_arrive(bar_acc_empty + 8 * as);
             }
           }
-          if (p.k == 1) score_chunk<true>(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, cnt, best, my_cand);
-          else score_chunk<false>(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, cnt, best, my_cand);
+          if (mode == kModeArgmin)
+            score_chunk<kModeArgmin>(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, cnt, best, row_buf);
+          else if (mode == kModeAppend)
+            score_chunk<kModeAppend>(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, cnt, best,
+                                     row_buf, row_cnt, p.big_cap);
+          else
+            score_chunk<kModeBuffer>(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, cnt, best, row_buf);
           if (c2 + 1 == kBN / 64) {
             __syncwarp();   // all lanes are done with this tile's beta values
             if (lane == 0) ptx::mbar_arrive(bar_norm_empty + 8 * as);
           }
-          if (p.k != 1) compact_if_needed(cnt, tau, cand_warp, p.k, lane);
+          if (mode == kModeBuffer) compact_if_needed(cnt, tau, cand_warp, p.k, lane);
         }
       }
+      if (mode == kModeAppend) continue;  // candidates already sit in the query's global buffer
       // ---- item done: emit this (split, query block)'s sorted top-k keys
       const size_t q_row0 = static_cast<size_t>(qb) * (kBM * G) + cta_rank * kBM + ew * 32;
       u64* out_blk = p.out_keys + (static_cast<size_t>(s) * p.q_pad + q_row0) * p.k;
-      if (p.k == 1) {
+      if (mode == kModeArgmin) {
         out_blk[lane] = best;
       } else {
         __syncwarp();

@@ -107,7 +107,7 @@ struct FlatEngine {
   CUtensorMap tm_x;       // db map, box = 256 rows (single-CTA kernel)
   CUtensorMap tm_x_half;  // db map, box = 128 rows (CTA-pair kernel: each CTA stages half a tile)
   // workspaces (grow-only)
-  DevBuf ws_cand, ws_keys, ws_q, ws_qnorm, ws_tau;
+  DevBuf ws_cand, ws_keys, ws_q, ws_qnorm, ws_tau, ws_big, ws_bigcnt;
   b2vs_search_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // optional timing of the dominant kernel
   bool timing_pending = false;
@@ -122,6 +122,9 @@ struct FlatEngine {
   int search(const void* q, int q_dtype, int nq, int k, int force_splits, int64_t id_offset,
              float* out_d, int64_t* out_i, int32_t* out_label, cudaStream_t st, int flags = 0);
   void resolve_timing();  // fills stats.kernel_ms once the timed launch has finished
+  // 128 < k <= 2048 (bigk.cu): append-mode passes + per-query radix select
+  int search_bigk(const void* q_mat, int nq, int q_pad, int group, int k, int64_t id_offset,
+                  float* out_d, int64_t* out_i, cudaStream_t st, int* launches);
   size_t owned_bytes() const { return owned.bytes + beta.bytes; }
   void destroy();
 };
@@ -135,6 +138,14 @@ int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k,
                         const float* qnorm, int64_t id_offset, float* out_d, int64_t* out_i,
                         int32_t* out_label, cudaStream_t st, const uint32_t* remap = nullptr,
                         float* out_tau = nullptr);
+
+// bigk.cu
+constexpr int kMaxBigK = 2048;
+int launch_bigk_select(const u64* cand, const int* counts, int cap, int nq, int k, int final_pass,
+                       int metric, const float* qnorm, int64_t id_offset, float* out_tau,
+                       float* out_d, int64_t* out_i, int* overflow, cudaStream_t st);
+int launch_merge_parts_big(const float* d_all, const int64_t* i_all, int n_parts, int nq, int k_in,
+                           int k_out, int descending, float* out_d, int64_t* out_i, cudaStream_t st);
 
 }  // namespace b2vs
 

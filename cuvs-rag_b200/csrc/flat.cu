@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "bf_tc.cuh"
 #include "common.h"
@@ -222,6 +223,8 @@ void FlatEngine::destroy() {
   ws_q.release();
   ws_qnorm.release();
   ws_tau.release();
+  ws_big.release();
+  ws_bigcnt.release();
 }
 
 __global__ void fill_missing_kernel(float* out_d, int64_t* out_i, int32_t* out_label, int64_t total,
@@ -295,8 +298,10 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
                        int64_t id_offset, float* out_d, int64_t* out_i, int32_t* out_label,
                        cudaStream_t st, int flags) {
   B2VS_CHECK(nq > 0, B2VS_EINVAL, "nq must be positive (got %d)", nq);
-  B2VS_CHECK(k >= 1 && k <= kMaxFusedK, B2VS_EUNSUP,
-             "k=%d outside the fused top-k range [1, %d]", k, kMaxFusedK);
+  B2VS_CHECK(k >= 1 && k <= kMaxBigK, B2VS_EUNSUP, "k=%d outside the supported range [1, %d]", k,
+             kMaxBigK);
+  B2VS_CHECK(k <= kMaxFusedK || out_label == nullptr, B2VS_EUNSUP, "labels need k <= %d",
+             kMaxFusedK);
   stats = b2vs_search_stats{};
   const float missing = (metric == B2VS_METRIC_IP) ? -INFINITY : INFINITY;
   if (n == 0) {
@@ -347,6 +352,13 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   CUtensorMap tm_q;
   B2VS_TRY(encode_tmap_2d(&tm_q, q_mat, ab_format, borrow_q ? nq : q_pad, kdim, kBM));
 
+  if (k > kMaxFusedK) {
+    B2VS_TRY(search_bigk(q_mat, nq, q_pad, group, k, id_offset, out_d, out_i, st, &launches));
+    stats.launches = launches;
+    stats.algo_flops = 2.0 * nq * static_cast<double>(n) * dim;
+    return B2VS_OK;
+  }
+
   // ---- passes.  A pass visits every `stride`-th db tile.  The last pass (stride 1) produces the
   // answer; earlier, sparser passes only seed each query's threshold with the k-th best score of
   // a 1/stride sample (a valid upper bound of the final k-th score), so the full pass starts with
@@ -359,7 +371,7 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   int n_pass = pass_strides(tiles, k, strides);
   B2VS_TRY(ws_tau.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
 
-  BfTcParams p;
+  BfTcParams p{};
   p.beta = beta.as<float>();
   p.n_qblocks = n_qblocks;
   p.q_pad = q_pad;
@@ -438,6 +450,115 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   stats.grid = grid;
   stats.algo_flops = 2.0 * nq * static_cast<double>(n) * dim;
   stats.algo_bytes = 0;
+  return B2VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Large k (128 < k <= 2048).  Passes are sparse-to-dense like the fused path, but the kernel only
+// APPENDS every score below the query's threshold to a per-query global buffer (no in-kernel
+// top-k); bigk_select_kernel then radix-selects the k-th key - the next pass's threshold, or,
+// after the full pass, the answer.  Strides are chosen so a pass is expected to leave at most a
+// quarter of the buffer per query; a buffer that overflows anyway (adversarial row order) is
+// cut to a valid tighter threshold and the pass is repeated.
+int FlatEngine::search_bigk(const void* q_mat, int nq, int q_pad, int group, int k,
+                            int64_t id_offset, float* out_d, int64_t* out_i, cudaStream_t st,
+                            int* launches) {
+  constexpr int kCapBig = 65536;
+  const int qrows = kBM * group;
+  const int sms = sm_count(dev);
+  const int units = std::max(1, sms / group);
+  const int64_t tiles = ceil_div(n, kBN);
+  const int chunk_rows = std::min(q_pad, 4096 / qrows * qrows);
+  B2VS_TRY(ws_big.reserve(static_cast<size_t>(chunk_rows) * kCapBig * sizeof(u64)));
+  B2VS_TRY(ws_bigcnt.reserve((static_cast<size_t>(chunk_rows) + 1) * sizeof(int)));
+  B2VS_TRY(ws_tau.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
+  int* counts = ws_bigcnt.as<int>();
+  int* overflow = counts + chunk_rows;
+  // stride schedule: first pass sees <= cap/2 rows, later passes expect <= cap/4 candidates
+  std::vector<int> strides;
+  strides.push_back(static_cast<int>(std::max<int64_t>(1, ceil_div(tiles * kBN, kCapBig / 2))));
+  while (strides.back() > 1) {
+    const int64_t nxt = std::max<int64_t>(1, ceil_div(4ll * k * strides.back(), kCapBig));
+    strides.push_back(static_cast<int>(std::min<int64_t>(nxt, strides.back() - 1)));
+  }
+  for (int q0 = 0; q0 < nq; q0 += chunk_rows) {
+    const int rows_c = std::min(chunk_rows, q_pad - q0);
+    const int valid_c = std::min(rows_c, nq - q0);
+    CUtensorMap tm_qc;
+    B2VS_TRY(encode_tmap_2d(&tm_qc,
+                            static_cast<const uint16_t*>(q_mat) + static_cast<size_t>(q0) * kdim,
+                            ab_format, rows_c, kdim, kBM));
+    BfTcParams p{};
+    p.beta = beta.as<float>();
+    p.n_qblocks = rows_c / qrows;
+    p.q_pad = rows_c;
+    p.k_blocks = static_cast<int>(ceil_div(kdim, kBK));
+    p.k = k;
+    p.alpha = (metric == B2VS_METRIC_L2) ? -2.f : -1.f;
+    p.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(ab_format), qrows, kBN);
+    p.big_cand = ws_big.as<u64>();
+    p.big_count = counts;
+    p.big_cap = kCapBig;
+    for (size_t pi = 0; pi < strides.size(); ++pi) {
+      const int stride = strides[pi];
+      const bool last = (pi + 1 == strides.size());
+      const int64_t ptiles = ceil_div(tiles, stride);
+      bool seeded = pi > 0;
+      for (int attempt = 0; attempt < 8; ++attempt) {
+        int n_splits = choose_splits(p.n_qblocks, ptiles, units, 1);
+        const int tps = static_cast<int>(ceil_div(ptiles, n_splits));
+        n_splits = static_cast<int>(ceil_div(ptiles, tps));
+        p.n_items = p.n_qblocks * n_splits;
+        p.tiles_total = static_cast<int>(ptiles);
+        p.tiles_per_split = tps;
+        p.tile_stride = stride;
+        p.tau_init = seeded ? ws_tau.as<float>() : nullptr;
+        const int grid = std::min(p.n_items, units) * group;
+        B2VS_CUDA(cudaMemsetAsync(counts, 0, (static_cast<size_t>(chunk_rows) + 1) * sizeof(int), st));
+        if (group == 1) {
+          B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TcCfg<1>::kSmemBytes));
+          bf_tc_kernel<1><<<grid, kTcThreads, TcCfg<1>::kSmemBytes, st>>>(tm_qc, tm_x, p);
+        } else {
+          B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TcCfg<2>::kSmemBytes));
+          cudaLaunchConfig_t cfg{};
+          cfg.gridDim = dim3(grid);
+          cfg.blockDim = dim3(kTcThreads);
+          cfg.dynamicSmemBytes = TcCfg<2>::kSmemBytes;
+          cfg.stream = st;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = 2;
+          attr[0].val.clusterDim.y = 1;
+          attr[0].val.clusterDim.z = 1;
+          cfg.attrs = attr;
+          cfg.numAttrs = 1;
+          B2VS_CUDA(cudaLaunchKernelEx(&cfg, bf_tc_kernel<2>, tm_qc, tm_x_half, p));
+        }
+        B2VS_CUDA(cudaGetLastError());
+        // k-th key per query: the next pass's threshold, or (last pass) the sorted answer
+        B2VS_TRY(launch_bigk_select(ws_big.as<u64>(), counts, kCapBig, last ? valid_c : rows_c, k,
+                                    last ? 1 : 0, metric, ws_qnorm.as<float>() + q0, id_offset,
+                                    ws_tau.as<float>(),
+                                    last ? out_d + static_cast<size_t>(q0) * k : nullptr,
+                                    last ? out_i + static_cast<size_t>(q0) * k : nullptr, overflow, st));
+        *launches += 2;
+        int h_over = 0;
+        B2VS_CUDA(cudaMemcpyAsync(&h_over, overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+        B2VS_CUDA(cudaStreamSynchronize(st));
+        if (h_over <= kCapBig) break;
+        // a buffer overflowed: the retained keys still give a valid, tighter bound; publish it as
+        // the threshold of every query of the chunk and repeat this pass
+        B2VS_CHECK(attempt < 7, B2VS_ECUDA, "large-k candidate buffers keep overflowing (%d keys)",
+                   h_over);
+        B2VS_TRY(launch_bigk_select(ws_big.as<u64>(), counts, kCapBig, rows_c, k, 0, metric, nullptr,
+                                    0, ws_tau.as<float>(), nullptr, nullptr, nullptr, st));
+        *launches += 1;
+        seeded = true;
+      }
+    }
+  }
   return B2VS_OK;
 }
 

@@ -145,11 +145,13 @@ extern "C" int b2vs_merge_topk(int dev, const float* d_all, const int64_t* i_all
   B2VS_CHECK(d_all && i_all && out_d && out_i, B2VS_EINVAL, "null pointer passed to b2vs_merge_topk");
   B2VS_CHECK(n_parts >= 1 && nq >= 1 && k_in >= 1, B2VS_EINVAL,
              "merge shape must be positive (n_parts=%d nq=%d k_in=%d)", n_parts, nq, k_in);
-  B2VS_CHECK(k_out >= 1 && k_out <= kMaxFusedK, B2VS_EUNSUP, "k_out=%d outside [1, %d]", k_out,
-             kMaxFusedK);
+  B2VS_CHECK(k_out >= 1 && k_out <= kMaxBigK, B2VS_EUNSUP, "k_out=%d outside [1, %d]", k_out,
+             kMaxBigK);
   DeviceGuard guard(dev);
   B2VS_CHECK(guard.ok, B2VS_ECUDA, "cannot select device %d", dev);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (k_out > kMaxFusedK)
+    return launch_merge_parts_big(d_all, i_all, n_parts, nq, k_in, k_out, descending, out_d, out_i, st);
   const int threads = 128;
   const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(nq) * 32, threads));
   merge_parts_kernel<<<blocks, threads, 0, st>>>(d_all, reinterpret_cast<const long long*>(i_all),

@@ -116,7 +116,7 @@ def _merge_arrays(dist_list: List[np.ndarray], idx_list: List[np.ndarray], k: in
     """Global top-k of per-shard host arrays: runs b2vs_merge_topk on a GPU when one exists."""
     k_total = sum(d.shape[1] for d in dist_list)
     k = min(k, k_total)
-    if torch.cuda.is_available() and k <= _native.MAX_FUSED_K:
+    if torch.cuda.is_available() and k <= _native.MAX_K:
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         k_in = max(d.shape[1] for d in dist_list)
         nq = dist_list[0].shape[0]

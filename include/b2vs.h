@@ -118,6 +118,8 @@ int b2vs_ivfpq_build(int dev, int metric, int dtype, int dim, const void* db, in
                      b2vs_index** out);
 
 /* k nearest rows for each of the nq queries ([nq, dim], `q_dtype`, device memory).
+ * k <= 128 on every index kind (fused in-kernel top-k); flat indexes also serve 128 < k <= 2048
+ * (append + radix-select path, synchronises `stream` once per pass).
  * out_d [nq, k] float32 and out_i [nq, k] int64 are caller-owned DEVICE buffers; missing
  * results are (inf | -inf, -1).  Asynchronous on `stream`.  `params` may be NULL. */
 int b2vs_search(b2vs_index* index, const void* queries, int q_dtype, int nq, int k,
@@ -132,7 +134,8 @@ int b2vs_search_host(b2vs_index* index, const void* queries_host, int q_dtype, i
 
 /* Global top-k over per-shard results: d_all / i_all are [n_parts, nq, k_in] (each part sorted
  * best-first, ids already global); writes the best k_out per query.  Ties keep the lower part
- * first (stable), matching the reference's concatenate + argsort merge. */
+ * first (stable), matching the reference's concatenate + argsort merge.  k_out <= 2048; for
+ * k_out > 128 at most 16384 candidates per query (n_parts * k_in). */
 int b2vs_merge_topk(int dev, const float* d_all, const int64_t* i_all, int n_parts, int nq,
                     int k_in, int k_out, int descending, float* out_d, int64_t* out_i,
                     void* stream);

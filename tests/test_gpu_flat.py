@@ -118,8 +118,8 @@ def test_search_host_matches_device_search(b2):
 def test_error_paths_return_codes_not_crashes(b2):
     db, qs = make(1000, 64, 4, "bf16", "sqeuclidean")
     ix = b2.NativeIndex.flat(db.cuda())
-    with pytest.raises(RuntimeError, match="outside the fused top-k range"):
-        ix.search(qs.cuda(), 129)
+    with pytest.raises(RuntimeError, match="outside the supported range"):
+        ix.search(qs.cuda(), 2049)
     with pytest.raises(ValueError, match="must live on a CUDA device"):
         ix.search(qs, 5)
     inf = ix.info()
@@ -210,3 +210,52 @@ def test_adversarial_order_sorted_database(b2):
     dd, ii = ix.search(qs.cuda(), 100)
     torch.cuda.synchronize()
     assert topk_parity_report(dd.cpu(), ii.cpu(), db.float(), qs.float(), 100, rtol=RTOL)["ok"]
+
+
+# ---- large k (the reference's top-2000 retrieval mode)
+@pytest.mark.parametrize("k,metric", [(1000, "sqeuclidean"), (2000, "sqeuclidean"), (500, "inner_product")])
+def test_large_k_exact(b2, k, metric):
+    from oracle.exact import exact_knn
+    db, qs = make(120_000, 64, 150, "bf16", metric)
+    ix = b2.NativeIndex.flat(db.cuda(), metric=metric, id_offset=9)
+    d, i = ix.search(qs.cuda(), k)
+    torch.cuda.synchronize()
+    from oracle.exact import topk_parity_report
+    rep = topk_parity_report(d.cpu(), i.cpu() - 9, db.float(), qs.float(), k, metric, rtol=RTOL)
+    assert rep["ok"], rep                       # ids exact up to ties within 1e-3 relative
+    rd, ri = exact_knn(db.float(), qs.float(), k, metric)
+    same_set = np.mean([len(set(a) & set(b)) / float(k) for a, b in zip((i.cpu() - 9).tolist(), ri.tolist())])
+    assert same_set > 0.9995, same_set          # the neighbour SETS agree; only tie order may differ
+    assert torch.allclose(d.cpu(), rd, rtol=1e-3, atol=1e-2)
+
+
+def test_large_k_overflow_recovery(b2):
+    """Sampled tiles hold only far rows, so the seeded threshold lets >65536 candidates through:
+    the append buffers overflow and the pass must be repeated with the tightened threshold."""
+    from oracle.exact import exact_knn
+    g = torch.Generator().manual_seed(31)
+    n, d, k = 400_000, 32, 1000
+    db = torch.randn(n, d, generator=g)
+    tile = torch.arange(n) // 256
+    stride = -(-((n + 255) // 256 * 256) // 32768)           # first-pass tile stride used by the engine
+    db[tile % stride == 0] += 40.0                           # the sample sees only far rows
+    db = db.to(torch.bfloat16)
+    qs = torch.randn(40, d, generator=g).to(torch.bfloat16)
+    ix = b2.NativeIndex.flat(db.cuda())
+    dd, ii = ix.search(qs.cuda(), k)
+    torch.cuda.synchronize()
+    rd, ri = exact_knn(db.float(), qs.float(), k)
+    same_set = np.mean([len(set(a) & set(b)) / float(k) for a, b in zip(ii.cpu().tolist(), ri.tolist())])
+    assert same_set > 0.9995, same_set
+    assert torch.allclose(dd.cpu(), rd, rtol=1e-3, atol=1e-2)
+
+
+def test_merge_topk_large_k(b2):
+    from oracle.merge import merge_topk
+    g = torch.Generator().manual_seed(6)
+    d = torch.sort(torch.rand(4, 50, 2000, generator=g), dim=2).values
+    i = torch.randint(0, 10**9, (4, 50, 2000), generator=g)
+    md, mi = b2.merge_topk(d.cuda(), i.cuda(), 2000)
+    od, oi = merge_topk(list(d.numpy()), list(i.numpy()), 2000)
+    np.testing.assert_array_equal(mi.cpu().numpy(), oi)
+    np.testing.assert_array_equal(md.cpu().numpy(), od)
