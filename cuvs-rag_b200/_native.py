@@ -66,6 +66,7 @@ EXPORTS = [
     "b2vs_ivfflat_build", "b2vs_ivfpq_build", "b2vs_search", "b2vs_search_host",
     "b2vs_merge_topk", "b2vs_kmeans_fit", "b2vs_index_info_get", "b2vs_index_last_stats",
     "b2vs_ivf_list_sizes_host", "b2vs_ivf_centroids_host", "b2vs_index_destroy",
+    "b2vs_index_save", "b2vs_index_load",
 ]
 
 _lib = None
@@ -132,6 +133,8 @@ def lib() -> ctypes.CDLL:
         L.b2vs_ivf_list_sizes_host.argtypes = [vp, vp]
         L.b2vs_ivf_centroids_host.argtypes = [vp, vp]
         L.b2vs_index_destroy.argtypes = [vp]
+        L.b2vs_index_save.argtypes = [vp, ctypes.c_char_p]
+        L.b2vs_index_load.argtypes = [i32, ctypes.c_char_p, vp, i64, vp, ctypes.POINTER(vp)]
         for name in EXPORTS:
             if name != "b2vs_last_error":
                 getattr(L, name).restype = i32
@@ -227,6 +230,27 @@ class NativeIndex:
                               _stream_ptr(db.device, stream), ctypes.byref(out)), fn)
         # IVF-PQ borrows the source rows for refine; IVF-Flat owns a copy of everything it needs
         return cls(out.value, db.device, m, keepalive=db if pq_dim else None)
+
+    # ------------------------------------------------------------------ persistence
+    def save(self, path: str) -> None:
+        """Write a trained IVF index to ``path`` (flat indexes hold no trained state)."""
+        _check(lib().b2vs_index_save(self._h, os.fsencode(path)), "b2vs_index_save")
+
+    @classmethod
+    def load(cls, path: str, device, rows: Optional[torch.Tensor] = None, id_offset: int = -1,
+             stream: Optional[torch.cuda.Stream] = None) -> "NativeIndex":
+        """Load an IVF index saved by ``save`` onto ``device``; ``rows`` (the shard's original
+        matrix on that device) is only needed for IVF-PQ searches with refine."""
+        device = torch.device(device)
+        if rows is not None:
+            _require_cuda_matrix(rows, "rows")
+        out = ctypes.c_void_p()
+        _check(lib().b2vs_index_load(device.index or 0, os.fsencode(path),
+                                     rows.data_ptr() if rows is not None else None, int(id_offset),
+                                     _stream_ptr(device, stream), ctypes.byref(out)), "b2vs_index_load")
+        inf = IndexInfo()
+        _check(lib().b2vs_index_info_get(out, ctypes.byref(inf)), "b2vs_index_info_get")
+        return cls(out.value, torch.device("cuda", inf.device), inf.metric, keepalive=rows)
 
     # ------------------------------------------------------------------ search
     def search(self, queries: torch.Tensor, k: int, n_probes: int = 0, refine_ratio: int = 0,

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <new>
 #include <vector>
 
@@ -1304,5 +1305,140 @@ extern "C" int b2vs_ivf_centroids_host(const b2vs_index* index, float* centroids
   B2VS_CUDA(cudaMemcpy(centroids_host, d->centroids.ptr,
                        static_cast<size_t>(d->n_lists) * index->dim * sizeof(float),
                        cudaMemcpyDeviceToHost));
+  return B2VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Index persistence: the reference rebuilds every index on every run (it only
+// saves raw embeddings as .pt files, cuvs-2gpu-main.ipynb cells 10/12).  An IVF index is written
+// as one little-endian file: header + raw device arrays; loading re-creates the coarse engine.
+namespace b2vs {
+
+struct IndexFileHeader {
+  char magic[8];       // "B2VSIDX1"
+  int32_t kind, metric, dtype, dim, n_lists, pq_dim, pq_bits, dsub, mp, dp, fmt, row_bytes;
+  int64_t n, id_offset, n_slots;
+  uint64_t bytes_centroids, bytes_offsets, bytes_sizes, bytes_row_ids, bytes_data, bytes_slot_norm,
+      bytes_codebooks, bytes_codes;
+};
+
+static int write_section(FILE* f, const DevBuf& b, uint64_t bytes) {
+  if (bytes == 0) return B2VS_OK;
+  std::vector<char> host(std::min<uint64_t>(bytes, 64ull << 20));
+  for (uint64_t off = 0; off < bytes; off += host.size()) {
+    const uint64_t len = std::min<uint64_t>(host.size(), bytes - off);
+    B2VS_CUDA(cudaMemcpy(host.data(), static_cast<const char*>(b.ptr) + off, len, cudaMemcpyDeviceToHost));
+    B2VS_CHECK(fwrite(host.data(), 1, len, f) == len, B2VS_EINVAL, "short write while saving index");
+  }
+  return B2VS_OK;
+}
+
+static int read_section(FILE* f, DevBuf* b, uint64_t bytes) {
+  if (bytes == 0) return B2VS_OK;
+  B2VS_TRY(b->reserve(bytes));
+  std::vector<char> host(std::min<uint64_t>(bytes, 64ull << 20));
+  for (uint64_t off = 0; off < bytes; off += host.size()) {
+    const uint64_t len = std::min<uint64_t>(host.size(), bytes - off);
+    B2VS_CHECK(fread(host.data(), 1, len, f) == len, B2VS_EINVAL, "index file is truncated");
+    B2VS_CUDA(cudaMemcpy(static_cast<char*>(b->ptr) + off, host.data(), len, cudaMemcpyHostToDevice));
+  }
+  return B2VS_OK;
+}
+
+}  // namespace b2vs
+
+extern "C" int b2vs_index_save(const b2vs_index* index, const char* path) {
+  B2VS_CHECK(index && path, B2VS_EINVAL, "NULL argument");
+  B2VS_CHECK(index->kind != B2VS_KIND_FLAT, B2VS_EUNSUP,
+             "flat indexes borrow their rows and hold no trained state: re-create them instead");
+  const IvfData* d = static_cast<const IvfData*>(index->ivf);
+  B2VS_CHECK(d != nullptr, B2VS_EINVAL, "index has no list data");
+  DeviceGuard guard(index->dev);
+  B2VS_CUDA(cudaDeviceSynchronize());
+  IndexFileHeader h{};
+  std::memcpy(h.magic, "B2VSIDX1", 8);
+  h.kind = index->kind; h.metric = index->metric; h.dtype = index->dtype; h.dim = index->dim;
+  h.n_lists = d->n_lists; h.pq_dim = d->pq_dim; h.pq_bits = d->pq_bits; h.dsub = d->dsub; h.mp = d->mp;
+  h.dp = d->dp; h.fmt = d->fmt; h.row_bytes = d->row_bytes;
+  h.n = index->n; h.id_offset = index->id_offset; h.n_slots = d->n_slots;
+  const uint64_t slots = std::max<int64_t>(d->n_slots, 1);
+  h.bytes_centroids = static_cast<uint64_t>(d->n_lists) * index->dim * sizeof(float);
+  h.bytes_offsets = static_cast<uint64_t>(d->n_lists + 1) * sizeof(uint32_t);
+  h.bytes_sizes = static_cast<uint64_t>(d->n_lists) * sizeof(int);
+  h.bytes_row_ids = slots * sizeof(uint32_t);
+  if (index->kind == B2VS_KIND_IVF_FLAT) {
+    h.bytes_data = slots * d->dp * 2;
+    h.bytes_slot_norm = slots * sizeof(float);
+  } else {
+    h.bytes_codebooks = static_cast<uint64_t>(d->pq_dim) * 256 * d->dsub * sizeof(float);
+    h.bytes_codes = std::max<uint64_t>(d->n_slots, 32) * d->mp;
+  }
+  FILE* f = fopen(path, "wb");
+  B2VS_CHECK(f != nullptr, B2VS_EINVAL, "cannot open %s for writing", path);
+  int rc = fwrite(&h, sizeof(h), 1, f) == 1 ? B2VS_OK : B2VS_EINVAL;
+  if (rc == B2VS_OK) rc = write_section(f, d->centroids, h.bytes_centroids);
+  if (rc == B2VS_OK) rc = write_section(f, d->offsets, h.bytes_offsets);
+  if (rc == B2VS_OK) rc = write_section(f, d->sizes, h.bytes_sizes);
+  if (rc == B2VS_OK) rc = write_section(f, d->row_ids, h.bytes_row_ids);
+  if (rc == B2VS_OK) rc = write_section(f, d->data, h.bytes_data);
+  if (rc == B2VS_OK) rc = write_section(f, d->slot_norm, h.bytes_slot_norm);
+  if (rc == B2VS_OK) rc = write_section(f, d->codebooks, h.bytes_codebooks);
+  if (rc == B2VS_OK) rc = write_section(f, d->codes, h.bytes_codes);
+  fclose(f);
+  if (rc != B2VS_OK && b2vs_last_error()[0] == 0) set_error("write to %s failed", path);
+  return rc;
+}
+
+extern "C" int b2vs_index_load(int dev, const char* path, const void* rows_for_refine, int64_t id_offset,
+                               void* stream, b2vs_index** out) {
+  B2VS_CHECK(path && out, B2VS_EINVAL, "NULL argument");
+  *out = nullptr;
+  int count = 0;
+  B2VS_CUDA(cudaGetDeviceCount(&count));
+  B2VS_CHECK(dev >= 0 && dev < count, B2VS_EINVAL, "device %d not in [0, %d)", dev, count);
+  FILE* f = fopen(path, "rb");
+  B2VS_CHECK(f != nullptr, B2VS_EINVAL, "cannot open %s", path);
+  IndexFileHeader h{};
+  if (fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "B2VSIDX1", 8) != 0) {
+    fclose(f);
+    set_error("%s is not a b2vs index file", path);
+    return B2VS_EINVAL;
+  }
+  DeviceGuard guard(dev);
+  b2vs_index* ix = new (std::nothrow) b2vs_index();
+  IvfData* d = new (std::nothrow) IvfData();
+  if (!ix || !d) { fclose(f); set_error("host allocation failed"); return B2VS_ENOMEM; }
+  ix->kind = h.kind; ix->dev = dev; ix->metric = h.metric; ix->dtype = h.dtype; ix->dim = h.dim;
+  ix->n = h.n; ix->id_offset = id_offset >= 0 ? id_offset : h.id_offset; ix->ivf = d;
+  d->n_lists = h.n_lists; d->pq_dim = h.pq_dim; d->pq_bits = h.pq_bits; d->dsub = h.dsub; d->mp = h.mp;
+  d->dp = h.dp; d->fmt = h.fmt; d->row_bytes = h.row_bytes; d->n = h.n; d->n_slots = h.n_slots;
+  d->src_rows = rows_for_refine;
+  int rc = read_section(f, &d->centroids, h.bytes_centroids);
+  if (rc == B2VS_OK) rc = read_section(f, &d->offsets, h.bytes_offsets);
+  if (rc == B2VS_OK) rc = read_section(f, &d->sizes, h.bytes_sizes);
+  if (rc == B2VS_OK) rc = read_section(f, &d->row_ids, h.bytes_row_ids);
+  if (rc == B2VS_OK) rc = read_section(f, &d->data, h.bytes_data);
+  if (rc == B2VS_OK) rc = read_section(f, &d->slot_norm, h.bytes_slot_norm);
+  if (rc == B2VS_OK) rc = read_section(f, &d->codebooks, h.bytes_codebooks);
+  if (rc == B2VS_OK) rc = read_section(f, &d->codes, h.bytes_codes);
+  fclose(f);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rc == B2VS_OK) {
+    d->h_sizes.resize(h.n_lists);
+    if (cudaMemcpy(d->h_sizes.data(), d->sizes.ptr, h.bytes_sizes, cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = B2VS_ECUDA;
+  }
+  if (rc == B2VS_OK) {
+    const int force = (h.dtype == B2VS_F32) ? -1 : h.fmt;
+    rc = ix->flat.init(dev, h.metric, B2VS_F32, h.dim, d->centroids.ptr, h.n_lists, st, force);
+  }
+  if (rc == B2VS_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = B2VS_ECUDA;
+  if (rc != B2VS_OK) {
+    ivf_destroy(ix);
+    ix->flat.destroy();
+    delete ix;
+    return rc;
+  }
+  *out = ix;
   return B2VS_OK;
 }

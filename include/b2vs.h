@@ -153,6 +153,14 @@ int b2vs_ivf_list_sizes_host(const b2vs_index* index, int32_t* sizes_host);
 int b2vs_ivf_centroids_host(const b2vs_index* index, float* centroids_host);
 int b2vs_index_destroy(b2vs_index* index);
 
+/* Persistence of trained IVF-Flat / IVF-PQ indexes (the reference re-trains on every run and only
+ * stores raw embeddings: cuvs-2gpu-main.ipynb cells 10/12).  One little-endian file per shard.
+ * b2vs_index_load: `rows_for_refine` (may be NULL) is the shard's original [n, dim] device matrix,
+ * borrowed for IVF-PQ refine; `id_offset` < 0 keeps the offset stored in the file. */
+int b2vs_index_save(const b2vs_index* index, const char* path);
+int b2vs_index_load(int dev, const char* path, const void* rows_for_refine, int64_t id_offset,
+                    void* stream, b2vs_index** out);
+
 #ifdef __cplusplus
 }
 #endif

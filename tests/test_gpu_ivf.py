@@ -134,3 +134,38 @@ def test_ivf_pq_kernel_variants_match_oracle(b2, d, m, label):
     _, oi = oracle.search(q.float(), k, n_probes=nprobe, refine_ratio=4)
     r_gpu, r_ref = recall(gi.cpu(), ti), recall(oi, ti)
     assert abs(r_gpu - r_ref) < 0.07, (label, r_gpu, r_ref)
+
+
+@pytest.mark.parametrize("kind", ["ivf_flat", "ivf_pq"])
+def test_index_save_load_roundtrip(b2, tmp_path, kind):
+    x = clustered(30000, 64, 60, 14).to(torch.float16).cuda()
+    q = queries_from(x.float().cpu(), 64, 15).to(torch.float16).cuda()
+    if kind == "ivf_flat":
+        ix = b2.NativeIndex.ivf_flat(x, 48, id_offset=100, kmeans_iters=6)
+        kw = dict(n_probes=8)
+    else:
+        ix = b2.NativeIndex.ivf_pq(x, 48, 32, id_offset=100, kmeans_iters=6)
+        kw = dict(n_probes=8, refine_ratio=4)
+    d0, i0 = ix.search(q, 10, **kw)
+    path = str(tmp_path / f"{kind}.b2vs")
+    ix.save(path)
+    ix.destroy()
+    ix2 = b2.NativeIndex.load(path, "cuda:0", rows=x if kind == "ivf_pq" else None)
+    inf = ix2.info()
+    assert (inf.n_rows, inf.dim, inf.n_lists, inf.id_offset) == (30000, 64, 48, 100)
+    d1, i1 = ix2.search(q, 10, **kw)
+    assert torch.equal(i0, i1) and torch.allclose(d0, d1)        # bit-identical after reload
+    assert int(ix2.list_sizes().sum()) == 30000
+    ix3 = b2.NativeIndex.load(path, "cuda:0", rows=x if kind == "ivf_pq" else None, id_offset=0)
+    _, i3 = ix3.search(q, 10, **kw)
+    assert torch.equal(i3, torch.where(i0 >= 0, i0 - 100, i0))
+
+
+def test_flat_index_save_is_refused(b2, tmp_path):
+    ix = b2.NativeIndex.flat(torch.randn(100, 16).half().cuda())
+    with pytest.raises(RuntimeError, match="re-create"):
+        ix.save(str(tmp_path / "flat.b2vs"))
+    with pytest.raises(RuntimeError, match="not a b2vs index file"):
+        p = tmp_path / "junk.b2vs"
+        p.write_bytes(b"x" * 4096)
+        b2.NativeIndex.load(str(p), "cuda:0")
