@@ -317,6 +317,24 @@ def main():
             sub.destroy()
         except Exception as exc:  # the bench number stands; parity is reported, not assumed
             parity = {"ok": False, "error": str(exc)[:200]}
+    if world > 1:
+        # sharded run: size-independent properties of the merged answer (all ranks hold it).
+        #  * the best merged hit of every query is the best hit of some shard (all-reduce MIN),
+        #  * rows are sorted, ids unique and inside [0, N), every rank computed the same result.
+        md, mi = step_device()
+        torch.cuda.synchronize()
+        best_local = out_d[:, 0].clone()
+        dist.all_reduce(best_local, op=dist.ReduceOp.MIN)
+        chk = torch.stack([(mi.double().sum()), md.double().sum()])
+        chk_max, chk_min = chk.clone(), chk.clone()
+        dist.all_reduce(chk_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(chk_min, op=dist.ReduceOp.MIN)
+        srt = bool((md[:, 1:] >= md[:, :-1]).all())
+        in_range = bool(((mi >= 0) & (mi < args.n_db)).all())
+        uniq = all(len(set(r)) == args.k for r in mi[:64].cpu().tolist())
+        parity = {"ok": bool(torch.equal(md[:, 0], best_local)) and srt and in_range and uniq and
+                  bool(torch.equal(chk_max, chk_min)),
+                  "check": "merged best == min over shards, sorted, unique in-range ids, identical on all ranks"}
 
     if rank == 0:
         peaks = load_peaks()

@@ -161,6 +161,40 @@ class EmbeddingDistributionManager:
         self.current_distribution = dist
         return dist
 
+    def load_embedding_parts(self, paths: List[str], dtype: Optional[torch.dtype] = None,
+                             target_gpus: Optional[List[int]] = None) -> DistributedEmbeddings:
+        """Load the reference's on-disk embedding format (``cuvs-2gpu-main.ipynb`` cells 10/12):
+        torch-saved ``[n, D]`` tensors, either one file per GPU (``embeddings_{size}_part{i}.pt``)
+        or a single ``embeddings_{size}.pt`` that is split like ``torch.chunk`` over the GPUs.
+        Part i goes to the i-th GPU; ``start_index`` is the running row count, so global ids are
+        right for uneven parts (380 000 + 370 000 in the reference's 750 k run)."""
+        if not paths:
+            raise ValueError("paths cannot be empty")
+        if len(paths) == 1:
+            full = torch.load(paths[0], map_location="cpu")
+            return self.distribute_embeddings(full, target_gpus=target_gpus, dtype=dtype)
+        gpus = list(target_gpus) if target_gpus is not None else self.gpu_manager.get_available_gpu_ids()
+        if len(gpus) < len(paths):
+            raise RuntimeError(f"{len(paths)} embedding parts but only {len(gpus)} GPUs available")
+        parts: List[EmbeddingPart] = []
+        start, dim = 0, None
+        for gpu_id, path in zip(gpus, paths):
+            if not self.gpu_manager.validate_gpu_index(gpu_id):
+                raise ValueError(f"Target GPU {gpu_id} is not available")
+            t = torch.load(path, map_location="cpu")
+            if not isinstance(t, torch.Tensor) or t.dim() != 2:
+                raise ValueError(f"{path} does not hold a 2D embedding tensor")
+            if dim is None:
+                dim = int(t.shape[1])
+            shard = t.contiguous().to(self.gpu_manager.get_safe_device_string(gpu_id))
+            if dtype is not None and shard.dtype != dtype:
+                shard = shard.to(dtype)
+            parts.append(EmbeddingPart(gpu_id, shard, start, start + int(t.shape[0])))
+            start += int(t.shape[0])
+        dist = DistributedEmbeddings(parts, start, dim)
+        self.current_distribution = dist
+        return dist
+
     # ------------------------------------------------------------------ validate
     def validate_distribution(self, distributed_embeddings: DistributedEmbeddings,
                               _available: Optional[List[int]] = None) -> bool:

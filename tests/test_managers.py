@@ -261,3 +261,22 @@ def test_recall_formula(b2):
     assert b2.RecallEvaluator.calculate_recall_at_k([1, 2], [], 2) == 0.0
     truth = np.array([[1, 2], [3, 4]])
     assert b2.RecallEvaluator.batch_recall(np.array([[2, 9], [4, 3]]), truth, 2) == 0.75
+
+
+def test_load_embedding_parts_reference_disk_format(b2, tmp_path):
+    """embeddings_{size}_part{i}.pt files (cuvs-2gpu-main.ipynb cells 10/12), uneven parts."""
+    a, b_ = torch.randn(38, 6), torch.randn(37, 6)
+    pa, pb = tmp_path / "embeddings_75_part0.pt", tmp_path / "embeddings_75_part1.pt"
+    torch.save(a, pa); torch.save(b_, pb)
+    edm = b2.EmbeddingDistributionManager(mock_grm(b2))
+    with patch.object(torch.Tensor, "to", lambda self, *a, **k: self):
+        dist = edm.load_embedding_parts([str(pa), str(pb)])
+    assert [(p.gpu_id, p.start_index, p.end_index) for p in dist.parts] == [(0, 0, 38), (1, 38, 75)]
+    assert torch.equal(dist.parts[1].tensor, b_) and dist.total_size == 75
+    full = tmp_path / "embeddings_75.pt"
+    torch.save(torch.cat([a, b_]), full)
+    with patch.object(torch.Tensor, "to", lambda self, *a, **k: self):
+        dist = edm.load_embedding_parts([str(full)])
+    assert [(p.start_index, p.end_index) for p in dist.parts] == [(0, 38), (38, 75)]
+    with pytest.raises(ValueError, match="paths cannot be empty"):
+        edm.load_embedding_parts([])
