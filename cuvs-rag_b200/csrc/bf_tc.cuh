@@ -36,7 +36,13 @@ namespace b2vs {
 
 constexpr int kBM = 128;   // query rows per CTA (TMEM lanes)
 constexpr int kBN = 256;   // db rows per tile (TMEM columns)
-constexpr int kBK = 64;    // K elements per smem stage (one 128-byte swizzle atom)
+#ifndef B2VS_BK
+#define B2VS_BK 64
+#endif
+// K elements per smem stage: 64 = one 128-byte swizzle atom (default); 32 = 64-byte swizzle, half
+// the stage size and more than twice the stage count (finer-grained operand prefetch)
+constexpr int kBK = B2VS_BK;
+static_assert(kBK == 64 || kBK == 32, "kBK must be 64 or 32");
 constexpr int kNormBytes = kBN * 4;
 constexpr int kTcThreads = 256;
 
@@ -45,7 +51,7 @@ template <int G> struct TcCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (G == 1) ? 4 : 6;
+  static constexpr int kStages = (kBK == 64) ? ((G == 1) ? 4 : 6) : ((G == 1) ? 9 : 13);
   static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kNormBytes + 256 + 1024;
 };
 
@@ -275,8 +281,8 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
             for (int kk = 0; kk < kBK / 16; ++kk) {
-              const uint64_t adesc = ptx::make_kmajor_sw128_desc(a_addr + kk * 32);
-              const uint64_t bdesc = ptx::make_kmajor_sw128_desc(b_addr + kk * 32);
+              const uint64_t adesc = ptx::make_kmajor_desc<kBK * 2>(a_addr + kk * 32);
+              const uint64_t bdesc = ptx::make_kmajor_desc<kBK * 2>(b_addr + kk * 32);
               if (G == 2) ptx::umma_f16_2sm(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
               else ptx::umma_f16(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
             }

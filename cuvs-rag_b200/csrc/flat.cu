@@ -148,7 +148,8 @@ int encode_tmap_2d(CUtensorMap* tm, const void* base, int ab_format, int64_t row
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, ab_format == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                   2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  kBK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B2VS_CHECK(r == CUDA_SUCCESS, B2VS_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d",
              static_cast<int>(r));

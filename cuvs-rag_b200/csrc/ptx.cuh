@@ -242,6 +242,19 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B   [61,64)
   return d;
 }
+// Same for a row pitch of kRowBytes = 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B): 8-row groups are
+// 8 * kRowBytes apart.
+template <int kRowBytes>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+  static_assert(kRowBytes == 128 || kRowBytes == 64, "unsupported swizzle span");
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((8 * kRowBytes) >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(kRowBytes == 128 ? 2 : 4) << 61;   // SWIZZLE_128B = 2, SWIZZLE_64B = 4
+  return d;
+}
 // Instruction descriptor for kind::f16: fp32 accumulate, A/B both K-major, dense.
 // ab_format: 0 = fp16, 1 = bf16.
 __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t ab_format, uint32_t m, uint32_t n) {
