@@ -111,21 +111,35 @@ __global__ void seed_centroids_kernel(const T* __restrict__ x, int64_t n, int di
     cent[static_cast<size_t>(c) * dim + j] = ld_f32<T>(x + row * dim + j);
 }
 
-// K2 update, accumulation half: one warp per row adds the row into its cluster's running sum.
+// K2 update, first half: SEGMENTED reduction.  Rows are grouped by label with the same
+// histogram -> scan -> scatter kernels that build the IVF lists (K3); then one CTA column per
+// cluster sums its segment, thread j owning dimension j (coalesced row reads, no atomics).
+__global__ void histogram_kernel(const int* __restrict__ labels, int64_t n, int* __restrict__ sizes);
+__global__ void scan_sizes_kernel(const int* __restrict__ sizes, int n_lists, int pad,
+                                  uint32_t* __restrict__ offsets);
+__global__ void scatter_rows_kernel(const int* __restrict__ labels, int64_t n,
+                                    const uint32_t* __restrict__ offsets, int* __restrict__ cursor,
+                                    uint32_t* __restrict__ row_ids, uint32_t* __restrict__ slot_of_row);
+
 template <typename T>
-__global__ void accumulate_kernel(const T* __restrict__ x, const int* __restrict__ labels, int64_t n,
-                                  int dim, float* __restrict__ sums, int* __restrict__ counts) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t r = warp0; r < n; r += nwarps) {
-    const int c = labels[r];
-    if (c < 0) continue;
-    float* s = sums + static_cast<size_t>(c) * dim;
-    const T* row = x + r * dim;
-    for (int j = lane; j < dim; j += 32) atomicAdd(s + j, ld_f32<T>(row + j));
-    if (lane == 0) atomicAdd(counts + c, 1);
+__global__ void segment_sum_kernel(const T* __restrict__ x, const uint32_t* __restrict__ offsets,
+                                   const uint32_t* __restrict__ row_ids, int dim,
+                                   float* __restrict__ sums) {
+  const int c = blockIdx.x;
+  const int j = blockIdx.y * blockDim.x + threadIdx.x;
+  if (j >= dim) return;
+  const uint32_t begin = offsets[c], end = offsets[c + 1];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  uint32_t i = begin;
+  for (; i + 4 <= end; i += 4) {
+    const uint32_t r0 = row_ids[i], r1 = row_ids[i + 1], r2 = row_ids[i + 2], r3 = row_ids[i + 3];
+    a0 += ld_f32<T>(x + static_cast<size_t>(r0) * dim + j);
+    a1 += ld_f32<T>(x + static_cast<size_t>(r1) * dim + j);
+    a2 += ld_f32<T>(x + static_cast<size_t>(r2) * dim + j);
+    a3 += ld_f32<T>(x + static_cast<size_t>(r3) * dim + j);
   }
+  for (; i < end; ++i) a0 += ld_f32<T>(x + static_cast<size_t>(row_ids[i]) * dim + j);
+  sums[static_cast<size_t>(c) * dim + j] = (a0 + a1) + (a2 + a3);
 }
 
 // K2 update, second half: mean of each cluster.  Balancing (the role cuVS's balanced k-means
@@ -196,16 +210,23 @@ static int kmeans_fit_impl(int dev, int dtype, int dim, const void* x, int64_t n
              "k-means needs 1 <= n_clusters <= n (n_clusters=%d, n=%lld)", ncl,
              static_cast<long long>(n));
   B2VS_CHECK(n < (1ll << 31), B2VS_EINVAL, "k-means input too large (n=%lld)", static_cast<long long>(n));
-  DevBuf sums, counts, labels, donors;
+  DevBuf sums, counts, labels, donors, seg_off, seg_cur, seg_rows, seg_slot;
   std::vector<int> h_counts, h_donor;
   FlatEngine eng;
   int rc = B2VS_OK;
-  auto cleanup = [&]() { sums.release(); counts.release(); labels.release(); donors.release(); eng.destroy(); };
+  auto cleanup = [&]() {
+    for (DevBuf* b : {&sums, &counts, &labels, &donors, &seg_off, &seg_cur, &seg_rows, &seg_slot}) b->release();
+    eng.destroy();
+  };
 #define KM_TRY(expr) do { rc = (expr); if (rc != B2VS_OK) { cleanup(); return rc; } } while (0)
 #define KM_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); cleanup(); return B2VS_ECUDA; } } while (0)
   KM_TRY(sums.reserve(static_cast<size_t>(ncl) * dim * sizeof(float)));
   KM_TRY(counts.reserve(static_cast<size_t>(ncl) * sizeof(int)));
   KM_TRY(donors.reserve(static_cast<size_t>(ncl) * sizeof(int)));
+  KM_TRY(seg_off.reserve(static_cast<size_t>(ncl + 1) * sizeof(uint32_t)));
+  KM_TRY(seg_cur.reserve(static_cast<size_t>(ncl) * sizeof(int)));
+  KM_TRY(seg_rows.reserve(static_cast<size_t>(n) * sizeof(uint32_t)));
+  KM_TRY(seg_slot.reserve(static_cast<size_t>(n) * sizeof(uint32_t)));
   int32_t* lab = labels_out;
   if (!lab) {
     KM_TRY(labels.reserve(static_cast<size_t>(n) * sizeof(int32_t)));
@@ -220,11 +241,20 @@ static int kmeans_fit_impl(int dev, int dtype, int dim, const void* x, int64_t n
   for (int it = 0; it < iters; ++it) {
     KM_TRY(eng.init(dev, B2VS_METRIC_L2, B2VS_F32, dim, cent, ncl, st, force));
     KM_TRY(eng.search(x, dtype, static_cast<int>(n), 1, 0, 0, nullptr, nullptr, lab, st));
-    KM_CUDA(cudaMemsetAsync(sums.ptr, 0, static_cast<size_t>(ncl) * dim * sizeof(float), st));
     KM_CUDA(cudaMemsetAsync(counts.ptr, 0, static_cast<size_t>(ncl) * sizeof(int), st));
-    DISPATCH_DTYPE(dtype, T, (accumulate_kernel<T><<<acc_blocks, 256, 0, st>>>(
-                                 static_cast<const T*>(x), lab, n, dim, sums.as<float>(),
-                                 counts.as<int>())));
+    KM_CUDA(cudaMemsetAsync(seg_cur.ptr, 0, static_cast<size_t>(ncl) * sizeof(int), st));
+    histogram_kernel<<<acc_blocks, 256, 0, st>>>(lab, n, counts.as<int>());
+    scan_sizes_kernel<<<1, 1024, 0, st>>>(counts.as<int>(), ncl, 1, seg_off.as<uint32_t>());
+    scatter_rows_kernel<<<acc_blocks, 256, 0, st>>>(lab, n, seg_off.as<uint32_t>(), seg_cur.as<int>(),
+                                                    seg_rows.as<uint32_t>(), seg_slot.as<uint32_t>());
+    KM_CUDA(cudaGetLastError());
+    {
+      const int tpb = dim >= 256 ? 256 : ((dim + 31) / 32) * 32;
+      const dim3 grid(ncl, static_cast<unsigned>(ceil_div(dim, tpb)));
+      DISPATCH_DTYPE(dtype, T, (segment_sum_kernel<T><<<grid, tpb, 0, st>>>(
+                                   static_cast<const T*>(x), seg_off.as<uint32_t>(),
+                                   seg_rows.as<uint32_t>(), dim, sums.as<float>())));
+    }
     KM_CUDA(cudaGetLastError());
     const int* donor_ptr = nullptr;
     if (it + 2 < iters && ncl > 1) {  // the last two iterations are plain Lloyd
