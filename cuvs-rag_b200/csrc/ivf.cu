@@ -42,6 +42,7 @@ struct IvfData {
   DevBuf codebooks;   // IVF-PQ: f32 [pq_dim, 256, dsub]
   DevBuf codes;       // IVF-PQ: u8, 32-row groups interleaved by 16-byte chunks
   DevBuf ws_probe_d, ws_probe_i, ws_keys, ws_qf, ws_qnorm, ws_counter, ws_ref_d, ws_ref_i;
+  DevBuf ws_item_lab, ws_item_cnt, ws_item_off, ws_item_perm, ws_item_slot;  // list-ordered scan items
   const void* src_rows = nullptr;  // IVF-PQ: the caller's [n, dim] rows, BORROWED for refine
   std::vector<int32_t> h_sizes;
   b2vs_search_stats stats{};
@@ -59,7 +60,8 @@ struct IvfData {
     ev0 = ev1 = nullptr;
     for (DevBuf* b : {&centroids, &offsets, &sizes, &row_ids, &data, &slot_norm, &codebooks, &codes,
                       &ws_probe_d, &ws_probe_i, &ws_keys, &ws_qf, &ws_qnorm, &ws_counter,
-                      &ws_ref_d, &ws_ref_i})
+                      &ws_ref_d, &ws_ref_i, &ws_item_lab, &ws_item_cnt, &ws_item_off, &ws_item_perm,
+                      &ws_item_slot})
       b->release();
   }
 };
@@ -448,10 +450,13 @@ ivf_flat_scan_kernel(const uint16_t* __restrict__ data, const float* __restrict_
                      const uint32_t* __restrict__ offsets, const long long* __restrict__ probe_ids,
                      const float* __restrict__ qf, int dp, int n_probes, int q_pad, int k,
                      float alpha, int use_norm, u64* __restrict__ out_keys,
-                     unsigned long long* __restrict__ scanned_rows) {
+                     unsigned long long* __restrict__ scanned_rows,
+                     const uint32_t* __restrict__ item_perm) {
   __shared__ u64 lists[kScanWarps][32 * kListE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x;
+  // item_perm (optional) orders the items by list, so the CTAs resident at one time read the
+  // same few lists and all but the first touch of a row is served by L2
+  const int item = item_perm ? static_cast<int>(item_perm[blockIdx.x]) : blockIdx.x;
   const int q = item / n_probes, p = item - q * n_probes;
   const long long list = probe_ids[item];
   uint32_t begin = 0, end = 0;
@@ -941,15 +946,21 @@ __global__ void queries_to_f32_kernel(const T* __restrict__ q, int nq, int dim, 
 }
 
 // ------------------------------------------------------------------------------------------
+__global__ void probe_labels_kernel(const long long* __restrict__ probe_ids, int items,
+                                    int* __restrict__ labels) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += gridDim.x * blockDim.x)
+    labels[i] = probe_ids[i] < 0 ? 0 : static_cast<int>(probe_ids[i]);  // empty items still run
+}
+
 template <int FMT>
 static int launch_flat_scan(int j, int items, cudaStream_t st, const IvfData* d,
                             const long long* probe_ids, const float* qf, int n_probes, int q_pad,
                             int k, float alpha, int use_norm, u64* out_keys,
-                            unsigned long long* counter) {
+                            unsigned long long* counter, const uint32_t* item_perm) {
 #define SCAN_CASE(JJ)                                                                          \
   ivf_flat_scan_kernel<FMT, JJ><<<items, kScanThreads, 0, st>>>(                               \
       d->data.as<uint16_t>(), d->slot_norm.as<float>(), d->offsets.as<uint32_t>(), probe_ids,  \
-      qf, d->dp, n_probes, q_pad, k, alpha, use_norm, out_keys, counter)
+      qf, d->dp, n_probes, q_pad, k, alpha, use_norm, out_keys, counter, item_perm)
   if (j <= 1) SCAN_CASE(1);
   else if (j == 2) SCAN_CASE(2);
   else if (j == 3) SCAN_CASE(3);
@@ -1004,15 +1015,40 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
     B2VS_CUDA(cudaEventRecord(d->ev0, st));
   }
   if (index->kind == B2VS_KIND_IVF_FLAT) {
+    // Counting sort of the (query, probe) items by list id (same three kernels as K3).  Pays
+    // once several queries share a list: the batch then reads each probed list from HBM about
+    // once instead of once per query that probes it.
+    const uint32_t* item_perm = nullptr;
+    static const bool no_sort = getenv("B2VS_NO_ITEM_SORT") != nullptr;
+    if (!no_sort && items >= 4 * d->n_lists) {
+      B2VS_TRY(d->ws_item_lab.reserve(static_cast<size_t>(items) * sizeof(int)));
+      B2VS_TRY(d->ws_item_cnt.reserve(static_cast<size_t>(d->n_lists) * 2 * sizeof(int)));
+      B2VS_TRY(d->ws_item_off.reserve((static_cast<size_t>(d->n_lists) + 1) * sizeof(uint32_t)));
+      B2VS_TRY(d->ws_item_perm.reserve(static_cast<size_t>(items) * sizeof(uint32_t)));
+      B2VS_TRY(d->ws_item_slot.reserve(static_cast<size_t>(items) * sizeof(uint32_t)));
+      const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(items, 256), 2048));
+      int* cnt = d->ws_item_cnt.as<int>();
+      B2VS_CUDA(cudaMemsetAsync(cnt, 0, static_cast<size_t>(d->n_lists) * 2 * sizeof(int), st));
+      probe_labels_kernel<<<blocks, 256, 0, st>>>(probe_ids, items, d->ws_item_lab.as<int>());
+      histogram_kernel<<<blocks, 256, 0, st>>>(d->ws_item_lab.as<int>(), items, cnt);
+      scan_sizes_kernel<<<1, 1024, 0, st>>>(cnt, d->n_lists, 1, d->ws_item_off.as<uint32_t>());
+      scatter_rows_kernel<<<blocks, 256, 0, st>>>(d->ws_item_lab.as<int>(), items,
+                                                  d->ws_item_off.as<uint32_t>(), cnt + d->n_lists,
+                                                  d->ws_item_perm.as<uint32_t>(),
+                                                  d->ws_item_slot.as<uint32_t>());
+      B2VS_CUDA(cudaGetLastError());
+      item_perm = d->ws_item_perm.as<uint32_t>();
+      launches += 5;
+    }
     const int j = static_cast<int>(ceil_div(d->dp / 8, 32));
     const float alpha = index->metric == B2VS_METRIC_L2 ? -2.f : -1.f;
     const int use_norm = index->metric == B2VS_METRIC_L2 ? 1 : 0;
     if (d->fmt == 0)
       B2VS_TRY(launch_flat_scan<0>(j, items, st, d, probe_ids, d->ws_qf.as<float>(), n_probes, q_pad,
-                                   k, alpha, use_norm, d->ws_keys.as<u64>(), counter));
+                                   k, alpha, use_norm, d->ws_keys.as<u64>(), counter, item_perm));
     else
       B2VS_TRY(launch_flat_scan<1>(j, items, st, d, probe_ids, d->ws_qf.as<float>(), n_probes, q_pad,
-                                   k, alpha, use_norm, d->ws_keys.as<u64>(), counter));
+                                   k, alpha, use_norm, d->ws_keys.as<u64>(), counter, item_perm));
     qnorm_for_merge = d->ws_qnorm.as<float>();
   } else {
     const size_t cb_floats = static_cast<size_t>(d->pq_dim) * 256 * d->dsub;
