@@ -75,6 +75,13 @@ struct BfTcParams {
   u64* big_cand;        // [q_pad][big_cap] or NULL
   int* big_count;       // [q_pad] atomic append cursors
   int big_cap;
+  // work-table mode (kWork kernels: the grouped IVF-Flat list scan, ivf.cu).  Item i is
+  // work[i] = {query block, first db row, end db row, -}: the rows are one inverted list, the
+  // query block holds (a slice of) the queries that probe it.  Always append mode; query row r
+  // appends to the buffer of query row_query[r] (< 0: padding row) with threshold tau_init[query].
+  const int4* work;
+  const int* n_work;    // device scalar: number of work items
+  const int* row_query; // [query rows]
 };
 
 constexpr int kModeBuffer = 0;   // per-(CTA,row) candidate buffer + warp compaction (k <= 128)
@@ -161,10 +168,11 @@ __device__ __forceinline__ void compact_if_needed(int& cnt, float& tau, u64* can
   }
 }
 
-template <int G>
+template <int G, bool kWork = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
              const BfTcParams p) {
+  static_assert(!kWork || G == 1, "work-table mode is single-CTA");
   using Cfg = TcCfg<G>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kStageBytes = Cfg::kStageBytes;
@@ -227,20 +235,29 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, tcount = 0;
       const uint32_t full_leader = (G == 2) ? ptx::mapa_cluster(bar_full, 0) : bar_full;
-      for (int item = unit; item < p.n_items; item += n_units) {
-        const int qb = item % p.n_qblocks;
-        const int s = item / p.n_qblocks;
-        const int t0 = s * p.tiles_per_split;
-        const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
+      const int n_items = kWork ? *p.n_work : p.n_items;
+      for (int item = unit; item < n_items; item += n_units) {
+        int qb, t0, t1, row_begin = 0;
+        if (kWork) {
+          const int4 w = __ldg(p.work + item);
+          qb = w.x; row_begin = w.y; t0 = 0; t1 = (w.z - w.y + kBN - 1) / kBN;
+        } else {
+          qb = item % p.n_qblocks;
+          t0 = (item / p.n_qblocks) * p.tiles_per_split;
+          t1 = min(t0 + p.tiles_per_split, p.tiles_total);
+        }
         const int q_row0 = qb * (kBM * G) + static_cast<int>(cta_rank) * kBM;
         for (int ti = t0; ti < t1; ++ti, ++tcount) {
           const int t = ti * p.tile_stride;
           const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
+          // first db row of the tile: tile-aligned, or (work mode) relative to the list start
+          const int x_row0 = kWork ? row_begin + ti * kBN
+                                   : t * kBN + static_cast<int>(cta_rank) * Cfg::kBRows;
           ptx::mbar_wait(bar_norm_empty + 8 * as, aph ^ 1u);
           ptx::mbar_arrive_expect_tx(bar_norm_full + 8 * as, kNormBytes);
-          ptx::bulk_load_1d(norm_base + as * kNormBytes, p.beta + static_cast<size_t>(t) * kBN,
+          ptx::bulk_load_1d(norm_base + as * kNormBytes,
+                            p.beta + (kWork ? static_cast<size_t>(x_row0) : static_cast<size_t>(t) * kBN),
                             kNormBytes, bar_norm_full + 8 * as);
-          const int x_row0 = t * kBN + static_cast<int>(cta_rank) * Cfg::kBRows;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
             const uint32_t a_dst = smem_base + stage * kStageBytes;
@@ -265,10 +282,16 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     // ------------------------------------------------------------------ MMA issuer (leader CTA)
     if (lane == 0 && cta_rank == 0) {
       uint32_t stage = 0, phase = 0, tcount = 0;
-      for (int item = unit; item < p.n_items; item += n_units) {
-        const int s = item / p.n_qblocks;
-        const int t0 = s * p.tiles_per_split;
-        const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
+      const int n_items = kWork ? *p.n_work : p.n_items;
+      for (int item = unit; item < n_items; item += n_units) {
+        int t0, t1;
+        if (kWork) {
+          const int4 w = __ldg(p.work + item);
+          t0 = 0; t1 = (w.z - w.y + kBN - 1) / kBN;
+        } else {
+          t0 = (item / p.n_qblocks) * p.tiles_per_split;
+          t1 = min(t0 + p.tiles_per_split, p.tiles_total);
+        }
         for (int t = t0; t < t1; ++t, ++tcount) {
           const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
           ptx::mbar_wait(bar_acc_empty + 8 * as, aph ^ 1u);
@@ -307,17 +330,30 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         (G == 2) ? ptx::mapa_cluster(bar_acc_empty, 0) : bar_acc_empty;
     const float inf = __int_as_float(0x7f800000);
     uint32_t tcount = 0;
-    for (int item = unit; item < p.n_items; item += n_units) {
-      const int qb = item % p.n_qblocks;
-      const int s = item / p.n_qblocks;
-      const int t0 = s * p.tiles_per_split;
-      const int t1 = min(t0 + p.tiles_per_split, p.tiles_total);
-      const size_t q_row = static_cast<size_t>(qb) * (kBM * G) + cta_rank * kBM + ew * 32 + lane;
+    const int n_items = kWork ? *p.n_work : p.n_items;
+    for (int item = unit; item < n_items; item += n_units) {
+      int qb, s = 0, t0, t1, row_begin = 0, row_end = 0;
+      if (kWork) {
+        const int4 w = __ldg(p.work + item);
+        qb = w.x; row_begin = w.y; row_end = w.z; t0 = 0; t1 = (w.z - w.y + kBN - 1) / kBN;
+      } else {
+        qb = item % p.n_qblocks;
+        s = item / p.n_qblocks;
+        t0 = s * p.tiles_per_split;
+        t1 = min(t0 + p.tiles_per_split, p.tiles_total);
+      }
+      size_t q_row = static_cast<size_t>(qb) * (kBM * G) + cta_rank * kBM + ew * 32 + lane;
       float tau = inf;
-      if (p.tau_init != nullptr) tau = p.tau_init[q_row];
-      const int mode = p.big_cand ? kModeAppend : (p.k == 1 ? kModeArgmin : kModeBuffer);
-      u64* const row_buf = p.big_cand ? p.big_cand + q_row * p.big_cap : my_cand;
-      int* const row_cnt = p.big_cand ? p.big_count + q_row : nullptr;
+      if (kWork) {
+        const int query = __ldg(p.row_query + q_row);
+        tau = query >= 0 ? p.tau_init[query] : -inf;   // padding rows never qualify
+        q_row = static_cast<size_t>(max(query, 0));
+      } else if (p.tau_init != nullptr) {
+        tau = p.tau_init[q_row];
+      }
+      const int mode = (kWork || p.big_cand) ? kModeAppend : (p.k == 1 ? kModeArgmin : kModeBuffer);
+      u64* const row_buf = (kWork || p.big_cand) ? p.big_cand + q_row * p.big_cap : my_cand;
+      int* const row_cnt = (kWork || p.big_cand) ? p.big_count + q_row : nullptr;
       int cnt = 0;
       u64 best = kKeyInf;  // k == 1 fast path keeps the running arg-min in a register
       for (int ti = t0; ti < t1; ++ti, ++tcount) {
@@ -327,7 +363,11 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         ptx::mbar_wait(bar_norm_full + 8 * as, aph);
         ptx::tc_fence_after();
         const float4* nrm4 = reinterpret_cast<const float4*>(norm_ptr + as * kBN);
-        const uint32_t col0 = static_cast<uint32_t>(t) * kBN;
+        const uint32_t col0 = kWork ? static_cast<uint32_t>(row_begin + ti * kBN)
+                                    : static_cast<uint32_t>(t) * kBN;
+        // work mode: columns past the end of the list belong to the next list (lists are padded
+        // to 32 rows, so validity is per 32-column chunk)
+        const int nv = kWork ? row_end - static_cast<int>(col0) : kBN;
         // Two register buffers: the TMEM load of chunk c+1 is in flight while chunk c is scored.
         uint32_t ra[32], rb[32];
         const uint32_t tile_taddr = lane_taddr + as * kBN;
@@ -336,7 +376,11 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         for (int c2 = 0; c2 < kBN / 64; ++c2) {
           ptx::tmem_ld_wait();
           ptx::tmem_ld_32x32b_x32(tile_taddr + c2 * 64 + 32, rb);
-          if (mode == kModeArgmin)
+          if (kWork) {
+            if (c2 * 64 < nv)
+              score_chunk<kModeAppend>(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, cnt, best,
+                                       row_buf, row_cnt, p.big_cap);
+          } else if (mode == kModeArgmin)
             score_chunk<kModeArgmin>(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, cnt, best, row_buf);
           else if (mode == kModeAppend)
             score_chunk<kModeAppend>(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, cnt, best, row_buf,
@@ -356,7 +400,11 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
               else ptx::mbar_arrive(bar_acc_empty + 8 * as);
             }
           }
-          if (mode == kModeArgmin)
+          if (kWork) {
+            if (c2 * 64 + 32 < nv)
+              score_chunk<kModeAppend>(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, cnt,
+                                       best, row_buf, row_cnt, p.big_cap);
+          } else if (mode == kModeArgmin)
             score_chunk<kModeArgmin>(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, cnt, best, row_buf);
           else if (mode == kModeAppend)
             score_chunk<kModeAppend>(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, cnt, best,

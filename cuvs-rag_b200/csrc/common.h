@@ -132,6 +132,27 @@ struct FlatEngine {
 int encode_tmap_2d(CUtensorMap* tm, const void* base, int ab_format, int64_t rows, int64_t cols,
                    int box_rows);
 
+// Grouped list scan on the tensor cores (flat.cu; used by the IVF-Flat batch search): work
+// item = (block of 128 gathered query rows, row range of one inverted list), append mode.
+struct GroupedScanArgs {
+  const void* q_mat;      // gathered query operand [q_rows, kdim] 16-bit, q_rows % 128 == 0
+  int64_t q_rows;
+  const void* x_mat;      // list rows [x_rows, kdim] 16-bit
+  int64_t x_rows;
+  int kdim, ab_format;
+  const float* beta;      // [x_rows + 256] additive term per list row (+inf on padding slots)
+  float alpha;
+  const void* work;       // int4 [max_work] {query block, first row, end row, -}
+  const int* n_work;      // device scalar
+  int max_work;
+  const int* row_query;   // [q_rows] query of each gathered row, -1 on padding
+  const float* tau;       // [nq] per-query threshold
+  u64* cand;              // [nq][cap]
+  int* count;             // [nq]
+  int cap;
+};
+int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st);
+
 // merge.cu
 // `remap` (optional) translates key ids (list slots) to shard-local row ids before id_offset.
 int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k, int metric,

@@ -455,6 +455,33 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
 }
 
 // ------------------------------------------------------------------------------------------
+int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st) {
+  CUtensorMap tm_q, tm_xl;
+  B2VS_TRY(encode_tmap_2d(&tm_q, a.q_mat, a.ab_format, a.q_rows, a.kdim, kBM));
+  B2VS_TRY(encode_tmap_2d(&tm_xl, a.x_mat, a.ab_format, a.x_rows, a.kdim, kBN));
+  BfTcParams p{};
+  p.beta = a.beta;
+  p.k_blocks = static_cast<int>(ceil_div(a.kdim, kBK));
+  p.k = 1;
+  p.tile_stride = 1;
+  p.alpha = a.alpha;
+  p.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(a.ab_format), kBM, kBN);
+  p.tau_init = a.tau;
+  p.big_cand = a.cand;
+  p.big_count = a.count;
+  p.big_cap = a.cap;
+  p.work = static_cast<const int4*>(a.work);
+  p.n_work = a.n_work;
+  p.row_query = a.row_query;
+  const int grid = std::max(1, std::min(a.max_work, sm_count(dev)));
+  B2VS_CUDA(cudaFuncSetAttribute((bf_tc_kernel<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 TcCfg<1>::kSmemBytes));
+  bf_tc_kernel<1, true><<<grid, kTcThreads, TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_xl, p);
+  B2VS_CUDA(cudaGetLastError());
+  return B2VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // Large k (128 < k <= 2048).  Passes are sparse-to-dense like the fused path, but the kernel only
 // APPENDS every score below the query's threshold to a per-query global buffer (no in-kernel
 // top-k); bigk_select_kernel then radix-selects the k-th key - the next pass's threshold, or,

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -26,10 +27,13 @@ constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kListE = 4;  // warp-resident sorted list: 32 * 4 = 128 keys
+constexpr int kGroupRows = 128;  // query rows per grouped-scan work item (= the UMMA M extent)
+constexpr int kNormSlack = 256;  // slot_norm floats past the last slot (whole-tile beta loads)
 
 struct IvfData {
   int n_lists = 0, pq_dim = 0, pq_bits = 0, dsub = 0, mp = 0;  // mp = pq_dim padded to 16
   int dp = 0;       // dim padded to 8 (16-bit storage pitch)
+  float max_norm2 = 0.f;  // IVF-Flat: largest ||x||^2 over the rows (rounding cushion of the seed threshold)
   int fmt = 1;      // storage format of list vectors: 0 fp16, 1 bf16
   int64_t n = 0;
   int64_t n_slots = 0;
@@ -38,11 +42,12 @@ struct IvfData {
   DevBuf sizes;       // i32 [n_lists]
   DevBuf row_ids;     // u32 [n_slots] shard-local row of each slot (kNoRow on padding)
   DevBuf data;        // IVF-Flat: u16 [n_slots, dp]
-  DevBuf slot_norm;   // IVF-Flat: f32 [n_slots] ||x||^2
+  DevBuf slot_norm;   // IVF-Flat: f32 [n_slots + kNormSlack] ||x||^2 (L2) or 0 (IP); +inf on padding
   DevBuf codebooks;   // IVF-PQ: f32 [pq_dim, 256, dsub]
   DevBuf codes;       // IVF-PQ: u8, 32-row groups interleaved by 16-byte chunks
   DevBuf ws_probe_d, ws_probe_i, ws_keys, ws_qf, ws_qnorm, ws_counter, ws_ref_d, ws_ref_i;
   DevBuf ws_item_lab, ws_item_cnt, ws_item_off, ws_item_perm, ws_item_slot;  // list-ordered scan items
+  DevBuf ws_g_work, ws_g_q, ws_g_rowq, ws_g_tau, ws_g_cand, ws_g_cnt;         // grouped scan
   const void* src_rows = nullptr;  // IVF-PQ: the caller's [n, dim] rows, BORROWED for refine
   std::vector<int32_t> h_sizes;
   b2vs_search_stats stats{};
@@ -61,7 +66,7 @@ struct IvfData {
     for (DevBuf* b : {&centroids, &offsets, &sizes, &row_ids, &data, &slot_norm, &codebooks, &codes,
                       &ws_probe_d, &ws_probe_i, &ws_keys, &ws_qf, &ws_qnorm, &ws_counter,
                       &ws_ref_d, &ws_ref_i, &ws_item_lab, &ws_item_cnt, &ws_item_off, &ws_item_perm,
-                      &ws_item_slot})
+                      &ws_item_slot, &ws_g_work, &ws_g_q, &ws_g_rowq, &ws_g_tau, &ws_g_cand, &ws_g_cnt})
       b->release();
   }
 };
@@ -343,11 +348,18 @@ __device__ __forceinline__ uint16_t to_op16(float v, int fmt, float* back) {
 }
 
 // one warp per row: copy the row into its list slot (16-bit storage) and record ||x||^2
+__global__ void fill_f32_kernel(float* __restrict__ p, size_t n, float v) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
 template <typename T>
 __global__ void fill_flat_lists_kernel(const T* __restrict__ x, int64_t n, int dim, int dp, int fmt,
                                        const uint32_t* __restrict__ slot_of_row,
-                                       uint16_t* __restrict__ data, float* __restrict__ slot_norm) {
+                                       uint16_t* __restrict__ data, float* __restrict__ slot_norm,
+                                       int want_norm, unsigned int* __restrict__ max_norm_bits) {
   const int lane = threadIdx.x & 31;
+  float warp_max = 0.f;
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   for (int64_t r = warp0; r < n; r += nwarps) {
@@ -364,8 +376,11 @@ __global__ void fill_flat_lists_kernel(const T* __restrict__ x, int64_t n, int d
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) slot_norm[slot] = acc;
+    if (lane == 0) slot_norm[slot] = want_norm ? acc : 0.f;  // inner product: no additive term
+    warp_max = fmaxf(warp_max, acc);
   }
+  // largest ||x||^2 of the index (non-negative floats order like their bit patterns)
+  if (lane == 0 && warp_max > 0.f) atomicMax(max_norm_bits, __float_as_uint(warp_max));
 }
 
 // ---- warp-resident sorted top-k list -------------------------------------------------------
@@ -444,37 +459,26 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   }
 }
 
-template <int FMT, int J>
-__global__ void __launch_bounds__(kScanThreads, 2)
-ivf_flat_scan_kernel(const uint16_t* __restrict__ data, const float* __restrict__ slot_norm,
-                     const uint32_t* __restrict__ offsets, const long long* __restrict__ probe_ids,
-                     const float* __restrict__ qf, int dp, int n_probes, int q_pad, int k,
-                     float alpha, int use_norm, u64* __restrict__ out_keys,
-                     unsigned long long* __restrict__ scanned_rows,
-                     const uint32_t* __restrict__ item_perm) {
-  __shared__ u64 lists[kScanWarps][32 * kListE];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // item_perm (optional) orders the items by list, so the CTAs resident at one time read the
-  // same few lists and all but the first touch of a row is served by L2
-  const int item = item_perm ? static_cast<int>(item_perm[blockIdx.x]) : blockIdx.x;
-  const int q = item / n_probes, p = item - q * n_probes;
-  const long long list = probe_ids[item];
-  uint32_t begin = 0, end = 0;
-  if (list >= 0) { begin = offsets[list]; end = offsets[list + 1]; }
-  if (threadIdx.x == 0 && scanned_rows) atomicAdd(scanned_rows, static_cast<unsigned long long>(end - begin));
-
-  const int n_chunks = dp >> 3;  // 16-byte chunks per row
-  float qr[J][8];
+// Loads lane's slice of query q into registers (J chunks of 8 elements).
+template <int J>
+__device__ __forceinline__ void load_query_regs(const float* __restrict__ qf, int q, int dp, int lane,
+                                                float (&qr)[J][8]) {
+  const int n_chunks = dp >> 3;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int c = lane + 32 * j;
 #pragma unroll
     for (int e = 0; e < 8; ++e) qr[j][e] = (c < n_chunks) ? qf[static_cast<size_t>(q) * dp + c * 8 + e] : 0.f;
   }
+}
 
-  WarpTopK tk;
-  tk.init();
-  const uint4* data4 = reinterpret_cast<const uint4*>(data);
+// Streams list rows [begin, end) through the CTA's warps and offers score = alpha*dot + slot_norm
+// to each warp's top-k list.  Padding slots carry slot_norm = +inf and never qualify.
+template <int FMT, int J>
+__device__ __forceinline__ void scan_list_rows(const uint4* __restrict__ data4,
+                                               const float* __restrict__ slot_norm, uint32_t begin,
+                                               uint32_t end, const float (&qr)[J][8], int n_chunks,
+                                               float alpha, WarpTopK& tk, int k, int warp, int lane) {
   for (uint32_t b0 = begin + warp * 32; b0 < end; b0 += kScanWarps * 32) {
     u64 ck = kKeyInf;
 #pragma unroll 1
@@ -514,16 +518,184 @@ ivf_flat_scan_kernel(const uint16_t* __restrict__ data, const float* __restrict_
       for (int r = 0; r < 4; ++r) {
         const uint32_t row = r0 + r;
         if (lane == it * 4 + r && row < end) {
-          const float base = use_norm ? slot_norm[row] : 0.f;
-          const float sc = fmaf(alpha, dot[r], base);
+          const float sc = fmaf(alpha, dot[r], slot_norm[row]);
           if (sc < tk.tau) ck = pack_key(sc, row);
         }
       }
     }
     tk.offer(ck, k, lane);
   }
+}
+
+template <int FMT, int J>
+__global__ void __launch_bounds__(kScanThreads, 2)
+ivf_flat_scan_kernel(const uint16_t* __restrict__ data, const float* __restrict__ slot_norm,
+                     const uint32_t* __restrict__ offsets, const long long* __restrict__ probe_ids,
+                     const float* __restrict__ qf, int dp, int n_probes, int q_pad, int k,
+                     float alpha, u64* __restrict__ out_keys,
+                     unsigned long long* __restrict__ scanned_rows,
+                     const uint32_t* __restrict__ item_perm) {
+  __shared__ u64 lists[kScanWarps][32 * kListE];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // item_perm (optional) orders the items by list, so the CTAs resident at one time read the
+  // same few lists and all but the first touch of a row is served by L2
+  const int item = item_perm ? static_cast<int>(item_perm[blockIdx.x]) : blockIdx.x;
+  const int q = item / n_probes, p = item - q * n_probes;
+  const long long list = probe_ids[item];
+  uint32_t begin = 0, end = 0;
+  if (list >= 0) { begin = offsets[list]; end = offsets[list + 1]; }
+  if (threadIdx.x == 0 && scanned_rows) atomicAdd(scanned_rows, static_cast<unsigned long long>(end - begin));
+  float qr[J][8];
+  load_query_regs<J>(qf, q, dp, lane, qr);
+  WarpTopK tk;
+  tk.init();
+  scan_list_rows<FMT, J>(reinterpret_cast<const uint4*>(data), slot_norm, begin, end, qr, dp >> 3,
+                         alpha, tk, k, warp, lane);
   block_merge_and_store(tk, lists, k, warp, lane,
                         out_keys + (static_cast<size_t>(p) * q_pad + q) * k);
+}
+
+// ---- K5b grouped IVF-Flat scan (large batches) ----------------------------------------------
+// When a batch holds many queries per list, the (query, probe) items are grouped by list and each
+// list is multiplied against the block of queries that probe it on the tensor cores
+// (bf_tc_kernel<1, true>, work-table mode).  The pieces around that kernel:
+//   seed    per query: k-th best score of the first rows of its NEAREST list = a valid upper
+//           bound of its final k-th score; every candidate below it is appended to the query's
+//           buffer by the tensor-core kernel
+//   work    one item per (list, 128-row slice of its query group)
+//   gather  the 16-bit query operand, rows in group order
+//   select  per query: sort the appended candidates, keep k
+//   rescue  queries whose buffer overflowed (threshold too loose) are rescanned exactly
+template <int FMT, int J>
+__global__ void __launch_bounds__(kScanThreads, 2)
+ivf_seed_tau_kernel(const uint16_t* __restrict__ data, const float* __restrict__ slot_norm,
+                    const uint32_t* __restrict__ offsets, const long long* __restrict__ probe_ids,
+                    const float* __restrict__ qf, int dp, int n_probes, int k, float alpha,
+                    uint32_t row_limit, float max_norm2, int l2, float* __restrict__ tau) {
+  __shared__ u64 lists[kScanWarps][32 * kListE];
+  __shared__ u64 top[kMaxFusedK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x;
+  const long long list = probe_ids[static_cast<size_t>(q) * n_probes];
+  uint32_t begin = 0, end = 0;
+  if (list >= 0) { begin = offsets[list]; end = min(offsets[list + 1], begin + row_limit); }
+  float qr[J][8];
+  load_query_regs<J>(qf, q, dp, lane, qr);
+  WarpTopK tk;
+  tk.init();
+  scan_list_rows<FMT, J>(reinterpret_cast<const uint4*>(data), slot_norm, begin, end, qr, dp >> 3,
+                         alpha, tk, k, warp, lane);
+  block_merge_and_store(tk, lists, k, warp, lane, top);
+  float qn = 0.f;
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qn = fmaf(qr[j][e], qr[j][e], qn);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // The tensor-core kernel recomputes these scores with a different summation order: the
+    // threshold gets a cushion that bounds the fp32 rounding difference of two length-dp dot
+    // products (|q.x| <= ||q|| ||x||_max), so no row of the true top-k can fall outside it.
+    const u64 kth = top[k - 1];
+    float t = INFINITY;
+    if (kth != kKeyInf) {
+      const float sc = key_score(kth);
+      const float eps = static_cast<float>(dp) * 1.2e-7f + 1e-6f;
+      t = sc + fabsf(alpha) * eps * sqrtf(qn * max_norm2) + 4e-7f * (fabsf(sc) + (l2 ? max_norm2 : 0.f));
+    }
+    tau[q] = t;
+  }
+}
+
+// One thread per list: emits the list's work items.  group_off = exclusive scan of the per-list
+// query counts rounded up to 128 (in gathered-row units).
+__global__ void build_group_work_kernel(const uint32_t* __restrict__ group_off,
+                                        const uint32_t* __restrict__ offsets,
+                                        const int* __restrict__ group_cnt, int n_lists,
+                                        int4* __restrict__ work, int* __restrict__ n_work,
+                                        unsigned long long* __restrict__ scanned_rows) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l == 0) *n_work = static_cast<int>(group_off[n_lists] >> 7);
+  if (l >= n_lists) return;
+  const int b0 = static_cast<int>(group_off[l] >> 7), b1 = static_cast<int>(group_off[l + 1] >> 7);
+  const int begin = static_cast<int>(offsets[l]), end = static_cast<int>(offsets[l + 1]);
+  for (int b = b0; b < b1; ++b) work[b] = make_int4(b, begin, end, 0);
+  if (scanned_rows && group_cnt[l] > 0)   // algorithmic work: every probing query sees every row
+    atomicAdd(scanned_rows, static_cast<unsigned long long>(group_cnt[l]) * static_cast<unsigned>(end - begin));
+}
+
+// One warp per gathered row: row_item[v] = (query, probe) item or kNoRow on group padding.
+__global__ void gather_group_queries_kernel(const uint32_t* __restrict__ row_item,
+                                            const uint32_t* __restrict__ group_off, int n_lists,
+                                            const float* __restrict__ qf, int dp, int n_probes,
+                                            int fmt, uint16_t* __restrict__ out,
+                                            int* __restrict__ row_query) {
+  const int lane = threadIdx.x & 31;
+  const int64_t v = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (v >= static_cast<int64_t>(group_off[n_lists])) return;
+  const uint32_t item = row_item[v];
+  const int q = item == kNoRow ? -1 : static_cast<int>(item / static_cast<uint32_t>(n_probes));
+  if (lane == 0) row_query[v] = q;
+  uint16_t* orow = out + static_cast<size_t>(v) * dp;
+  for (int j = lane; j < dp; j += 32) {
+    float back;
+    orow[j] = q < 0 ? uint16_t(0) : to_op16(qf[static_cast<size_t>(q) * dp + j], fmt, &back);
+  }
+}
+
+// One CTA per query: bitonic sort of the appended candidates in shared memory, first k kept.
+constexpr int kSelectThreads = 256;
+__global__ void __launch_bounds__(kSelectThreads)
+ivf_group_select_kernel(const u64* __restrict__ cand, const int* __restrict__ count, int cap, int k,
+                        u64* __restrict__ out_keys) {
+  extern __shared__ u64 sk[];
+  const int q = blockIdx.x;
+  const int n = count[q];
+  if (n > cap) return;  // overflow: left to the rescue kernel
+  int P = 32;
+  while (P < n) P <<= 1;
+  const u64* src = cand + static_cast<size_t>(q) * cap;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) sk[i] = i < n ? __ldcg(src + i) : kKeyInf;
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const u64 a = sk[lo], b = sk[hi];
+        if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < k; i += blockDim.x) out_keys[static_cast<size_t>(q) * k + i] = i < P ? sk[i] : kKeyInf;
+}
+
+// One CTA per query whose candidate buffer overflowed: exact scan of all its probes.
+template <int FMT, int J>
+__global__ void __launch_bounds__(kScanThreads, 2)
+ivf_flat_rescue_kernel(const uint16_t* __restrict__ data, const float* __restrict__ slot_norm,
+                       const uint32_t* __restrict__ offsets, const long long* __restrict__ probe_ids,
+                       const float* __restrict__ qf, int dp, int n_probes, int k, float alpha,
+                       const int* __restrict__ count, int cap, u64* __restrict__ out_keys) {
+  __shared__ u64 lists[kScanWarps][32 * kListE];
+  const int q = blockIdx.x;
+  if (count[q] <= cap) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float qr[J][8];
+  load_query_regs<J>(qf, q, dp, lane, qr);
+  WarpTopK tk;
+  tk.init();
+  for (int p = 0; p < n_probes; ++p) {
+    const long long list = probe_ids[static_cast<size_t>(q) * n_probes + p];
+    if (list < 0) continue;
+    scan_list_rows<FMT, J>(reinterpret_cast<const uint4*>(data), slot_norm, offsets[list],
+                           offsets[list + 1], qr, dp >> 3, alpha, tk, k, warp, lane);
+  }
+  block_merge_and_store(tk, lists, k, warp, lane, out_keys + static_cast<size_t>(q) * k);
 }
 
 // ---- K6 / K7 IVF-PQ -----------------------------------------------------------------------
@@ -952,24 +1124,71 @@ __global__ void probe_labels_kernel(const long long* __restrict__ probe_ids, int
     labels[i] = probe_ids[i] < 0 ? 0 : static_cast<int>(probe_ids[i]);  // empty items still run
 }
 
-template <int FMT>
-static int launch_flat_scan(int j, int items, cudaStream_t st, const IvfData* d,
-                            const long long* probe_ids, const float* qf, int n_probes, int q_pad,
-                            int k, float alpha, int use_norm, u64* out_keys,
-                            unsigned long long* counter, const uint32_t* item_perm) {
-#define SCAN_CASE(JJ)                                                                          \
-  ivf_flat_scan_kernel<FMT, JJ><<<items, kScanThreads, 0, st>>>(                               \
-      d->data.as<uint16_t>(), d->slot_norm.as<float>(), d->offsets.as<uint32_t>(), probe_ids,  \
-      qf, d->dp, n_probes, q_pad, k, alpha, use_norm, out_keys, counter, item_perm)
-  if (j <= 1) SCAN_CASE(1);
-  else if (j == 2) SCAN_CASE(2);
-  else if (j == 3) SCAN_CASE(3);
-  else if (j == 4) SCAN_CASE(4);
-  else if (j <= 6) SCAN_CASE(6);
-  else SCAN_CASE(8);
-#undef SCAN_CASE
+// Instantiation table of the <FMT, J> scan kernels: J = 16-byte chunks of a row owned by a lane.
+#define FLAT_SCAN_DISPATCH(KERNEL, fmt, j, grid, st, ...)                                    \
+  do {                                                                                       \
+    if ((fmt) == 0) {                                                                        \
+      if ((j) <= 1) KERNEL<0, 1><<<(grid), kScanThreads, 0, (st)>>>(__VA_ARGS__);            \
+      else if ((j) == 2) KERNEL<0, 2><<<(grid), kScanThreads, 0, (st)>>>(__VA_ARGS__);       \
+      else if ((j) == 3) KERNEL<0, 3><<<(grid), kScanThreads, 0, (st)>>>(__VA_ARGS__);       \
+      else if ((j) == 4) KERNEL<0, 4><<<(grid), kScanThreads, 0, (st)>>>(__VA_ARGS__);       \
+      else if ((j) <= 6) KERNEL<0, 6><<<(grid), kScanThreads, 0, (st)>>>(__VA_ARGS__);       \
+      else KERNEL<0, 8><<<(grid), kScanThreads, 0, (st)>>>(__VA_ARGS__);                     \
+    } else {                                                                                 \
+      if ((j) <= 1) KERNEL<1, 1><<<(grid), kScanThreads, 0, (st)>>>(__VA_ARGS__);            \
+      else if ((j) == 2) KERNEL<1, 2><<<(grid), kScanThreads, 0, (st)>>>(__VA_ARGS__);       \
+      else if ((j) == 3) KERNEL<1, 3><<<(grid), kScanThreads, 0, (st)>>>(__VA_ARGS__);       \
+      else if ((j) == 4) KERNEL<1, 4><<<(grid), kScanThreads, 0, (st)>>>(__VA_ARGS__);       \
+      else if ((j) <= 6) KERNEL<1, 6><<<(grid), kScanThreads, 0, (st)>>>(__VA_ARGS__);       \
+      else KERNEL<1, 8><<<(grid), kScanThreads, 0, (st)>>>(__VA_ARGS__);                     \
+    }                                                                                        \
+  } while (0)
+
+// Counting sort of the (query, probe) items by list id (the same three kernels that build the
+// lists).  group_pad = 1: dense permutation (row_item[i] = i-th item in list order);
+// group_pad = 128: every list's group starts on a 128-row boundary, holes hold kNoRow.
+static int sort_items_by_list(IvfData* d, const long long* probe_ids, int items, int group_pad,
+                              cudaStream_t st) {
+  const size_t rows_cap = group_pad == 1
+                              ? static_cast<size_t>(items)
+                              : static_cast<size_t>(items) +
+                                    static_cast<size_t>(group_pad) * std::min(d->n_lists, items);
+  B2VS_TRY(d->ws_item_lab.reserve(static_cast<size_t>(items) * sizeof(int)));
+  B2VS_TRY(d->ws_item_cnt.reserve(static_cast<size_t>(d->n_lists) * 2 * sizeof(int)));
+  B2VS_TRY(d->ws_item_off.reserve((static_cast<size_t>(d->n_lists) + 1) * sizeof(uint32_t)));
+  B2VS_TRY(d->ws_item_perm.reserve(rows_cap * sizeof(uint32_t)));
+  B2VS_TRY(d->ws_item_slot.reserve(static_cast<size_t>(items) * sizeof(uint32_t)));
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(items, 256), 2048));
+  int* cnt = d->ws_item_cnt.as<int>();
+  B2VS_CUDA(cudaMemsetAsync(cnt, 0, static_cast<size_t>(d->n_lists) * 2 * sizeof(int), st));
+  if (group_pad > 1) B2VS_CUDA(cudaMemsetAsync(d->ws_item_perm.ptr, 0xFF, rows_cap * sizeof(uint32_t), st));
+  probe_labels_kernel<<<blocks, 256, 0, st>>>(probe_ids, items, d->ws_item_lab.as<int>());
+  histogram_kernel<<<blocks, 256, 0, st>>>(d->ws_item_lab.as<int>(), items, cnt);
+  scan_sizes_kernel<<<1, 1024, 0, st>>>(cnt, d->n_lists, group_pad, d->ws_item_off.as<uint32_t>());
+  scatter_rows_kernel<<<blocks, 256, 0, st>>>(d->ws_item_lab.as<int>(), items,
+                                              d->ws_item_off.as<uint32_t>(), cnt + d->n_lists,
+                                              d->ws_item_perm.as<uint32_t>(),
+                                              d->ws_item_slot.as<uint32_t>());
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
+}
+
+// Candidate-buffer capacity (a power of two) and seed-sample length of the grouped scan, by k.
+// B2VS_IVF_GROUPED_CAP shrinks the buffers so tests can drive the overflow-rescue path.
+static int grouped_cap(int k) {
+  const char* e = std::getenv("B2VS_IVF_GROUPED_CAP");
+  if (e) {
+    const int v = std::atoi(e);
+    if (v >= 32 && v <= 4096 && (v & (v - 1)) == 0) return v;
+  }
+  return k <= 32 ? 2048 : 4096;
+}
+static uint32_t grouped_seed_rows(int k) { return static_cast<uint32_t>(std::max(512, 16 * k)); }
+
+// B2VS_IVF_GROUPED=0|1 forces the per-item / grouped IVF-Flat scan (A/B measurements, tests).
+static int grouped_override() {
+  const char* e = std::getenv("B2VS_IVF_GROUPED");
+  return (e && (e[0] == '0' || e[0] == '1')) ? (e[0] - '0') : -1;
 }
 
 int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
@@ -1005,7 +1224,6 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
   const long long* probe_ids = reinterpret_cast<const long long*>(d->ws_probe_i.ptr);
   unsigned long long* counter = d->ws_counter.as<unsigned long long>();
   const float* qnorm_for_merge = nullptr;
-  bool pq_query_major = false;  // the query-major PQ scan leaves ONE list per query
   const bool timed = (sp.flags & B2VS_FLAG_TIME_KERNEL) != 0;
   if (timed) {
     if (!d->ev0) {
@@ -1014,41 +1232,72 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
     }
     B2VS_CUDA(cudaEventRecord(d->ev0, st));
   }
+  bool single_list = false;  // the scan left ONE sorted list per query (not one per probe)
   if (index->kind == B2VS_KIND_IVF_FLAT) {
-    // Counting sort of the (query, probe) items by list id (same three kernels as K3).  Pays
-    // once several queries share a list: the batch then reads each probed list from HBM about
-    // once instead of once per query that probes it.
-    const uint32_t* item_perm = nullptr;
-    static const bool no_sort = getenv("B2VS_NO_ITEM_SORT") != nullptr;
-    if (!no_sort && items >= 4 * d->n_lists) {
-      B2VS_TRY(d->ws_item_lab.reserve(static_cast<size_t>(items) * sizeof(int)));
-      B2VS_TRY(d->ws_item_cnt.reserve(static_cast<size_t>(d->n_lists) * 2 * sizeof(int)));
-      B2VS_TRY(d->ws_item_off.reserve((static_cast<size_t>(d->n_lists) + 1) * sizeof(uint32_t)));
-      B2VS_TRY(d->ws_item_perm.reserve(static_cast<size_t>(items) * sizeof(uint32_t)));
-      B2VS_TRY(d->ws_item_slot.reserve(static_cast<size_t>(items) * sizeof(uint32_t)));
-      const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(items, 256), 2048));
-      int* cnt = d->ws_item_cnt.as<int>();
-      B2VS_CUDA(cudaMemsetAsync(cnt, 0, static_cast<size_t>(d->n_lists) * 2 * sizeof(int), st));
-      probe_labels_kernel<<<blocks, 256, 0, st>>>(probe_ids, items, d->ws_item_lab.as<int>());
-      histogram_kernel<<<blocks, 256, 0, st>>>(d->ws_item_lab.as<int>(), items, cnt);
-      scan_sizes_kernel<<<1, 1024, 0, st>>>(cnt, d->n_lists, 1, d->ws_item_off.as<uint32_t>());
-      scatter_rows_kernel<<<blocks, 256, 0, st>>>(d->ws_item_lab.as<int>(), items,
-                                                  d->ws_item_off.as<uint32_t>(), cnt + d->n_lists,
-                                                  d->ws_item_perm.as<uint32_t>(),
-                                                  d->ws_item_slot.as<uint32_t>());
-      B2VS_CUDA(cudaGetLastError());
-      item_perm = d->ws_item_perm.as<uint32_t>();
-      launches += 5;
-    }
     const int j = static_cast<int>(ceil_div(d->dp / 8, 32));
     const float alpha = index->metric == B2VS_METRIC_L2 ? -2.f : -1.f;
-    const int use_norm = index->metric == B2VS_METRIC_L2 ? 1 : 0;
-    if (d->fmt == 0)
-      B2VS_TRY(launch_flat_scan<0>(j, items, st, d, probe_ids, d->ws_qf.as<float>(), n_probes, q_pad,
-                                   k, alpha, use_norm, d->ws_keys.as<u64>(), counter, item_perm));
-    else
-      B2VS_TRY(launch_flat_scan<1>(j, items, st, d, probe_ids, d->ws_qf.as<float>(), n_probes, q_pad,
-                                   k, alpha, use_norm, d->ws_keys.as<u64>(), counter, item_perm));
+    const uint16_t* data = d->data.as<uint16_t>();
+    const float* snorm = d->slot_norm.as<float>();
+    const uint32_t* offs = d->offsets.as<uint32_t>();
+    const float* qf = d->ws_qf.as<float>();
+    const int ov = grouped_override();
+    // grouped tensor-core scan once the batch averages a few queries per list
+    // (fp32-source indexes keep fp32 queries against the 16-bit rows: per-item scan only)
+    const bool grouped = index->dtype != B2VS_F32 &&
+                         (ov >= 0 ? ov == 1 : (nq >= 64 && items >= 2 * d->n_lists));
+    if (grouped) {
+      const int cap = grouped_cap(k);
+      B2VS_TRY(sort_items_by_list(d, probe_ids, items, kGroupRows, st));
+      const int max_work = items / kGroupRows + std::min(d->n_lists, items) + 1;
+      const int64_t rows_cap = static_cast<int64_t>(items) + static_cast<int64_t>(kGroupRows) * std::min(d->n_lists, items);
+      B2VS_TRY(d->ws_g_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16));
+      B2VS_TRY(d->ws_g_q.reserve(static_cast<size_t>(rows_cap) * d->dp * 2));
+      B2VS_TRY(d->ws_g_rowq.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
+      B2VS_TRY(d->ws_g_tau.reserve(static_cast<size_t>(nq) * sizeof(float)));
+      B2VS_TRY(d->ws_g_cand.reserve(static_cast<size_t>(nq) * cap * sizeof(u64)));
+      B2VS_TRY(d->ws_g_cnt.reserve(static_cast<size_t>(nq) * sizeof(int)));
+      int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
+      B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
+      FLAT_SCAN_DISPATCH(ivf_seed_tau_kernel, d->fmt, j, nq, st, data, snorm, offs, probe_ids, qf, d->dp,
+                         n_probes, k, alpha, grouped_seed_rows(k), d->max_norm2,
+                         index->metric == B2VS_METRIC_L2 ? 1 : 0, d->ws_g_tau.as<float>());
+      build_group_work_kernel<<<static_cast<unsigned>(ceil_div(d->n_lists, 256)), 256, 0, st>>>(
+          d->ws_item_off.as<uint32_t>(), offs, d->ws_item_cnt.as<int>(), d->n_lists,
+          d->ws_g_work.as<int4>(), n_work, counter);
+      gather_group_queries_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
+          d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists, qf, d->dp,
+          n_probes, d->fmt, d->ws_g_q.as<uint16_t>(), d->ws_g_rowq.as<int>());
+      B2VS_CUDA(cudaGetLastError());
+      GroupedScanArgs ga{};
+      ga.q_mat = d->ws_g_q.ptr; ga.q_rows = rows_cap;
+      ga.x_mat = d->data.ptr; ga.x_rows = d->n_slots;
+      ga.kdim = d->dp; ga.ab_format = d->fmt;
+      ga.beta = snorm; ga.alpha = alpha;
+      ga.work = d->ws_g_work.ptr; ga.n_work = n_work; ga.max_work = max_work;
+      ga.row_query = d->ws_g_rowq.as<int>(); ga.tau = d->ws_g_tau.as<float>();
+      ga.cand = d->ws_g_cand.as<u64>(); ga.count = d->ws_g_cnt.as<int>(); ga.cap = cap;
+      B2VS_TRY(launch_grouped_scan(index->dev, ga, st));
+      ivf_group_select_kernel<<<nq, kSelectThreads, static_cast<size_t>(cap) * sizeof(u64), st>>>(
+          ga.cand, ga.count, cap, k, d->ws_keys.as<u64>());
+      FLAT_SCAN_DISPATCH(ivf_flat_rescue_kernel, d->fmt, j, nq, st, data, snorm, offs, probe_ids, qf,
+                         d->dp, n_probes, k, alpha, ga.count, cap, d->ws_keys.as<u64>());
+      B2VS_CUDA(cudaGetLastError());
+      launches += 11;
+      single_list = true;
+    } else {
+      // Per-item scan.  Ordering the items by list pays once several queries share a list: the
+      // batch then reads each probed list from HBM about once instead of once per probing query.
+      const uint32_t* item_perm = nullptr;
+      static const bool no_sort = getenv("B2VS_NO_ITEM_SORT") != nullptr;
+      if (!no_sort && items >= 4 * d->n_lists) {
+        B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, st));
+        item_perm = d->ws_item_perm.as<uint32_t>();
+        launches += 5;
+      }
+      FLAT_SCAN_DISPATCH(ivf_flat_scan_kernel, d->fmt, j, items, st, data, snorm, offs, probe_ids, qf,
+                         d->dp, n_probes, q_pad, k, alpha, d->ws_keys.as<u64>(), counter, item_perm);
+      B2VS_CUDA(cudaGetLastError());
+    }
     qnorm_for_merge = d->ws_qnorm.as<float>();
   } else {
     const size_t cb_floats = static_cast<size_t>(d->pq_dim) * 256 * d->dsub;
@@ -1073,7 +1322,7 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
       else if (nch == 1 && d->dsub == 8) PQ_QUERY_LAUNCH(1, 8);
       else PQ_QUERY_LAUNCH(0, 0);
 #undef PQ_QUERY_LAUNCH
-      pq_query_major = true;
+      single_list = true;
     } else {
       const size_t smem = (static_cast<size_t>(d->mp) * 256 + index->dim) * sizeof(float);
       B2VS_CUDA(cudaFuncSetAttribute(ivf_pq_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1088,14 +1337,14 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
   if (timed) B2VS_CUDA(cudaEventRecord(d->ev1, st));
   ++launches;
   if (!refine) {
-    B2VS_TRY(launch_merge_splits(d->ws_keys.as<u64>(), pq_query_major ? 1 : n_probes, q_pad, nq, k,
+    B2VS_TRY(launch_merge_splits(d->ws_keys.as<u64>(), single_list ? 1 : n_probes, q_pad, nq, k,
                                  index->metric, qnorm_for_merge, index->id_offset, out_d, out_i,
                                  nullptr, st, d->row_ids.as<uint32_t>()));
     ++launches;
   } else {
     B2VS_TRY(d->ws_ref_d.reserve(static_cast<size_t>(nq) * k * sizeof(float)));
     B2VS_TRY(d->ws_ref_i.reserve(static_cast<size_t>(nq) * k * sizeof(int64_t)));
-    B2VS_TRY(launch_merge_splits(d->ws_keys.as<u64>(), pq_query_major ? 1 : n_probes, q_pad, nq, k,
+    B2VS_TRY(launch_merge_splits(d->ws_keys.as<u64>(), single_list ? 1 : n_probes, q_pad, nq, k,
                                  index->metric, qnorm_for_merge, 0, d->ws_ref_d.as<float>(),
                                  d->ws_ref_i.as<int64_t>(), nullptr, st, d->row_ids.as<uint32_t>()));
     DISPATCH_DTYPE(index->dtype, T, (refine_kernel<T><<<static_cast<unsigned>(ceil_div(nq, 4)), 128, 0, st>>>(
@@ -1243,7 +1492,7 @@ static int ivf_build(int kind, int dev, int metric, int dtype, int dim, const vo
   IB_TRY(assign_eng.search(db, dtype, static_cast<int>(n), 1, 0, 0, nullptr, nullptr,
                            labels.as<int32_t>(), st));
   // ---- 4. lists: histogram -> scan -> scatter -> fill
-  const int pad = (kind == B2VS_KIND_IVF_PQ) ? 32 : 1;
+  const int pad = 32;  // lists start on 32-slot boundaries (interleaved PQ groups; grouped flat scan)
   IB_TRY(d->sizes.reserve(static_cast<size_t>(n_lists) * sizeof(int)));
   IB_TRY(d->offsets.reserve(static_cast<size_t>(n_lists + 1) * sizeof(uint32_t)));
   IB_TRY(cursor.reserve(static_cast<size_t>(n_lists) * sizeof(int)));
@@ -1272,12 +1521,20 @@ static int ivf_build(int kind, int dev, int metric, int dtype, int dim, const vo
   const int wblocks = static_cast<int>(std::min<int64_t>(ceil_div(n, 8), 148 * 16));
   if (kind == B2VS_KIND_IVF_FLAT) {
     IB_TRY(d->data.reserve(std::max<size_t>(total_slots, 1) * d->dp * 2));
-    IB_TRY(d->slot_norm.reserve(std::max<size_t>(total_slots, 1) * sizeof(float)));
+    IB_CUDA(cudaMemsetAsync(cursor.ptr, 0, sizeof(unsigned int), st));  // re-used as the max-norm cell
+    const size_t norm_floats = std::max<size_t>(total_slots, 1) + kNormSlack;
+    IB_TRY(d->slot_norm.reserve(norm_floats * sizeof(float)));
+    IB_CUDA(cudaMemsetAsync(d->data.ptr, 0, std::max<size_t>(total_slots, 1) * d->dp * 2, st));
+    fill_f32_kernel<<<static_cast<unsigned>(ceil_div(norm_floats, 256)), 256, 0, st>>>(
+        d->slot_norm.as<float>(), norm_floats, INFINITY);
     DISPATCH_DTYPE(dtype, T, (fill_flat_lists_kernel<T><<<wblocks, 256, 0, st>>>(
                                  static_cast<const T*>(db), n, dim, d->dp, d->fmt,
                                  slot_of_row.as<uint32_t>(), d->data.as<uint16_t>(),
-                                 d->slot_norm.as<float>())));
+                                 d->slot_norm.as<float>(), metric == B2VS_METRIC_L2 ? 1 : 0,
+                                 cursor.as<unsigned int>())));
     IB_CUDA(cudaGetLastError());
+    IB_CUDA(cudaMemcpyAsync(&d->max_norm2, cursor.ptr, sizeof(float), cudaMemcpyDeviceToHost, st));
+    IB_CUDA(cudaStreamSynchronize(st));
   } else {
     // ---- 5. PQ codebooks on residual sub-vectors of a training subset, then encode all rows
     int64_t pstride = std::max<int64_t>(1, n / 131072);
@@ -1381,9 +1638,11 @@ extern "C" int b2vs_ivf_centroids_host(const b2vs_index* index, float* centroids
 namespace b2vs {
 
 struct IndexFileHeader {
-  char magic[8];       // "B2VSIDX1"
+  char magic[8];       // "B2VSIDX2"
   int32_t kind, metric, dtype, dim, n_lists, pq_dim, pq_bits, dsub, mp, dp, fmt, row_bytes;
   int64_t n, id_offset, n_slots;
+  float max_norm2;
+  int32_t reserved;
   uint64_t bytes_centroids, bytes_offsets, bytes_sizes, bytes_row_ids, bytes_data, bytes_slot_norm,
       bytes_codebooks, bytes_codes;
 };
@@ -1422,11 +1681,12 @@ extern "C" int b2vs_index_save(const b2vs_index* index, const char* path) {
   DeviceGuard guard(index->dev);
   B2VS_CUDA(cudaDeviceSynchronize());
   IndexFileHeader h{};
-  std::memcpy(h.magic, "B2VSIDX1", 8);
+  std::memcpy(h.magic, "B2VSIDX2", 8);
   h.kind = index->kind; h.metric = index->metric; h.dtype = index->dtype; h.dim = index->dim;
   h.n_lists = d->n_lists; h.pq_dim = d->pq_dim; h.pq_bits = d->pq_bits; h.dsub = d->dsub; h.mp = d->mp;
   h.dp = d->dp; h.fmt = d->fmt; h.row_bytes = d->row_bytes;
   h.n = index->n; h.id_offset = index->id_offset; h.n_slots = d->n_slots;
+  h.max_norm2 = d->max_norm2;
   const uint64_t slots = std::max<int64_t>(d->n_slots, 1);
   h.bytes_centroids = static_cast<uint64_t>(d->n_lists) * index->dim * sizeof(float);
   h.bytes_offsets = static_cast<uint64_t>(d->n_lists + 1) * sizeof(uint32_t);
@@ -1434,7 +1694,7 @@ extern "C" int b2vs_index_save(const b2vs_index* index, const char* path) {
   h.bytes_row_ids = slots * sizeof(uint32_t);
   if (index->kind == B2VS_KIND_IVF_FLAT) {
     h.bytes_data = slots * d->dp * 2;
-    h.bytes_slot_norm = slots * sizeof(float);
+    h.bytes_slot_norm = (slots + kNormSlack) * sizeof(float);
   } else {
     h.bytes_codebooks = static_cast<uint64_t>(d->pq_dim) * 256 * d->dsub * sizeof(float);
     h.bytes_codes = std::max<uint64_t>(d->n_slots, 32) * d->mp;
@@ -1465,7 +1725,7 @@ extern "C" int b2vs_index_load(int dev, const char* path, const void* rows_for_r
   FILE* f = fopen(path, "rb");
   B2VS_CHECK(f != nullptr, B2VS_EINVAL, "cannot open %s", path);
   IndexFileHeader h{};
-  if (fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "B2VSIDX1", 8) != 0) {
+  if (fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "B2VSIDX2", 8) != 0) {
     fclose(f);
     set_error("%s is not a b2vs index file", path);
     return B2VS_EINVAL;
@@ -1478,6 +1738,7 @@ extern "C" int b2vs_index_load(int dev, const char* path, const void* rows_for_r
   ix->n = h.n; ix->id_offset = id_offset >= 0 ? id_offset : h.id_offset; ix->ivf = d;
   d->n_lists = h.n_lists; d->pq_dim = h.pq_dim; d->pq_bits = h.pq_bits; d->dsub = h.dsub; d->mp = h.mp;
   d->dp = h.dp; d->fmt = h.fmt; d->row_bytes = h.row_bytes; d->n = h.n; d->n_slots = h.n_slots;
+  d->max_norm2 = h.max_norm2;
   d->src_rows = rows_for_refine;
   int rc = read_section(f, &d->centroids, h.bytes_centroids);
   if (rc == B2VS_OK) rc = read_section(f, &d->offsets, h.bytes_offsets);

@@ -169,3 +169,49 @@ def test_flat_index_save_is_refused(b2, tmp_path):
         p = tmp_path / "junk.b2vs"
         p.write_bytes(b"x" * 4096)
         b2.NativeIndex.load(str(p), "cuda:0")
+
+
+@pytest.mark.parametrize("dtype,metric,d,k", [(torch.bfloat16, "sqeuclidean", 128, 10),
+                                               (torch.float16, "inner_product", 72, 10),
+                                               (torch.bfloat16, "sqeuclidean", 200, 100)])
+def test_ivf_flat_grouped_scan_equals_per_item_scan(b2, monkeypatch, dtype, metric, d, k):
+    """Large batches take the grouped tensor-core list scan; it must return what the per-(query,
+    probe) scan returns on the same index (ties aside), including when every candidate buffer
+    overflows and the rescue kernel answers instead."""
+    from oracle.exact import topk_parity_report
+    n, nlist, nprobe, nq = 40000, 64, 12, 700
+    x = clustered(n, d, 80, 21).to(dtype)
+    q = queries_from(x.float(), nq, 22).to(dtype)
+    ix = b2.NativeIndex.ivf_flat(x.cuda(), nlist, metric=metric, id_offset=5, kmeans_iters=8)
+    monkeypatch.setenv("B2VS_IVF_GROUPED", "0")
+    d0, i0 = ix.search(q.cuda(), k, n_probes=nprobe)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("B2VS_IVF_GROUPED", "1")
+    d1, i1 = ix.search(q.cuda(), k, n_probes=nprobe)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("B2VS_IVF_GROUPED_CAP", "32")     # forces overflow -> rescue path
+    d2, i2 = ix.search(q.cuda(), k, n_probes=nprobe)
+    torch.cuda.synchronize()
+    for dd, ii in ((d1, i1), (d2, i2)):
+        scale = float(d0.abs().max())
+        assert float((dd - d0).abs().max()) <= 2e-3 * scale + 1e-3
+        same = (ii == i0).float().mean().item()
+        assert same > 0.995, same
+        # rows that differ are ties / fp-order swaps: same id sets almost everywhere
+        inter = [len(set(a.tolist()) & set(b.tolist())) for a, b in zip(ii.cpu(), i0.cpu())]
+        assert sum(inter) >= 0.999 * nq * k
+
+
+def test_ivf_flat_grouped_scan_ragged_batch(b2, monkeypatch):
+    """Batch sizes that are not multiples of the 128-row query block and lists nobody probes."""
+    from oracle.exact import exact_knn
+    from oracle.ivf import recall
+    x = clustered(20000, 64, 40, 31).to(torch.bfloat16)
+    ix = b2.NativeIndex.ivf_flat(x.cuda(), 32, metric="sqeuclidean", kmeans_iters=8)
+    monkeypatch.setenv("B2VS_IVF_GROUPED", "1")
+    for nq in (1, 65, 129):
+        q = queries_from(x.float(), nq, 40 + nq).to(torch.bfloat16)
+        _, ti = exact_knn(x.float(), q.float(), 5, "sqeuclidean")
+        dd, ii = ix.search(q.cuda(), 5, n_probes=32)
+        assert recall(ii.cpu(), ti) > 0.99
+        assert bool((dd[:, 1:] >= dd[:, :-1]).all())
