@@ -55,7 +55,7 @@ class IndexInfo(ctypes.Structure):
 
 class SearchStats(ctypes.Structure):
     _fields_ = [("launches", ctypes.c_int32), ("n_splits", ctypes.c_int32),
-                ("grid", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("grid", ctypes.c_int32), ("mean_candidates", ctypes.c_int32),
                 ("algo_flops", ctypes.c_double), ("algo_bytes", ctypes.c_double),
                 ("kernel_ms", ctypes.c_double)]
 

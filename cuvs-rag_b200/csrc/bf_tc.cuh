@@ -129,6 +129,9 @@ __device__ __forceinline__ void score_chunk(const uint32_t (&r)[32], const float
       uint32_t mask = 0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) mask |= (sc[j] < tau) ? (1u << j) : 0u;
+      // append mode: ONE atomic reserves the slots of all of this chunk's hits
+      int pos = 0;
+      if (kMode == kModeAppend) pos = atomicAdd(g_cnt, __popc(mask));
       while (mask) {
         const int j = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -143,8 +146,8 @@ __device__ __forceinline__ void score_chunk(const uint32_t (&r)[32], const float
         for (int i = 0; i < 2; ++i) v2[i] = (j & 8) ? v4[2 * i + 1] : v4[2 * i];
         const float v = (j & 16) ? v2[1] : v2[0];
         if (kMode == kModeAppend) {
-          const int pos = atomicAdd(g_cnt, 1);
           if (pos < g_cap) __stcg(my_cand + pos, pack_key(v, col + j));
+          ++pos;
         } else {
           __stcg(my_cand + cnt, pack_key(v, col + j));
           ++cnt;

@@ -50,8 +50,10 @@ struct IvfData {
   DevBuf ws_g_work, ws_g_q, ws_g_rowq, ws_g_tau, ws_g_cand, ws_g_cnt;         // grouped scan
   const void* src_rows = nullptr;  // IVF-PQ: the caller's [n, dim] rows, BORROWED for refine
   std::vector<int32_t> h_sizes;
+  DevBuf rank_of_list, list_of_rank;  // int [n_lists]: lists in descending-size order (scan scheduling)
   b2vs_search_stats stats{};
   bool counter_pending = false;
+  int last_nq = 0;
   int row_bytes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timing_pending = false;
@@ -64,6 +66,7 @@ struct IvfData {
     if (ev1) cudaEventDestroy(ev1);
     ev0 = ev1 = nullptr;
     for (DevBuf* b : {&centroids, &offsets, &sizes, &row_ids, &data, &slot_norm, &codebooks, &codes,
+                      &rank_of_list, &list_of_rank,
                       &ws_probe_d, &ws_probe_i, &ws_keys, &ws_qf, &ws_qnorm, &ws_counter,
                       &ws_ref_d, &ws_ref_i, &ws_item_lab, &ws_item_cnt, &ws_item_off, &ws_item_perm,
                       &ws_item_slot, &ws_g_work, &ws_g_q, &ws_g_rowq, &ws_g_tau, &ws_g_cand, &ws_g_cnt})
@@ -571,11 +574,12 @@ __global__ void __launch_bounds__(kScanThreads, 2)
 ivf_seed_tau_kernel(const uint16_t* __restrict__ data, const float* __restrict__ slot_norm,
                     const uint32_t* __restrict__ offsets, const long long* __restrict__ probe_ids,
                     const float* __restrict__ qf, int dp, int n_probes, int k, float alpha,
-                    uint32_t row_limit, float max_norm2, int l2, float* __restrict__ tau) {
+                    uint32_t row_limit, float max_norm2, int l2,
+                    const uint32_t* __restrict__ q_perm, float* __restrict__ tau) {
   __shared__ u64 lists[kScanWarps][32 * kListE];
   __shared__ u64 top[kMaxFusedK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x;
+  const int q = static_cast<int>(q_perm[blockIdx.x]);  // queries ordered by nearest list (L2 reuse)
   const long long list = probe_ids[static_cast<size_t>(q) * n_probes];
   uint32_t begin = 0, end = 0;
   if (list >= 0) { begin = offsets[list]; end = min(offsets[list + 1], begin + row_limit); }
@@ -609,21 +613,23 @@ ivf_seed_tau_kernel(const uint16_t* __restrict__ data, const float* __restrict__
   }
 }
 
-// One thread per list: emits the list's work items.  group_off = exclusive scan of the per-list
-// query counts rounded up to 128 (in gathered-row units).
+// One thread per list: emits the list's work items.  group_off = exclusive scan (in size-rank
+// order) of the per-list query counts rounded up to 128, in gathered-row units.
 __global__ void build_group_work_kernel(const uint32_t* __restrict__ group_off,
                                         const uint32_t* __restrict__ offsets,
-                                        const int* __restrict__ group_cnt, int n_lists,
+                                        const int* __restrict__ group_cnt,
+                                        const int* __restrict__ list_of_rank, int n_lists,
                                         int4* __restrict__ work, int* __restrict__ n_work,
                                         unsigned long long* __restrict__ scanned_rows) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l == 0) *n_work = static_cast<int>(group_off[n_lists] >> 7);
-  if (l >= n_lists) return;
-  const int b0 = static_cast<int>(group_off[l] >> 7), b1 = static_cast<int>(group_off[l + 1] >> 7);
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;   // size rank: items come out longest first
+  if (r == 0) *n_work = static_cast<int>(group_off[n_lists] >> 7);
+  if (r >= n_lists) return;
+  const int l = list_of_rank[r];
+  const int b0 = static_cast<int>(group_off[r] >> 7), b1 = static_cast<int>(group_off[r + 1] >> 7);
   const int begin = static_cast<int>(offsets[l]), end = static_cast<int>(offsets[l + 1]);
   for (int b = b0; b < b1; ++b) work[b] = make_int4(b, begin, end, 0);
-  if (scanned_rows && group_cnt[l] > 0)   // algorithmic work: every probing query sees every row
-    atomicAdd(scanned_rows, static_cast<unsigned long long>(group_cnt[l]) * static_cast<unsigned>(end - begin));
+  if (scanned_rows && group_cnt[r] > 0)   // algorithmic work: every probing query sees every row
+    atomicAdd(scanned_rows, static_cast<unsigned long long>(group_cnt[r]) * static_cast<unsigned>(end - begin));
 }
 
 // One warp per gathered row: row_item[v] = (query, probe) item or kNoRow on group padding.
@@ -649,10 +655,11 @@ __global__ void gather_group_queries_kernel(const uint32_t* __restrict__ row_ite
 constexpr int kSelectThreads = 256;
 __global__ void __launch_bounds__(kSelectThreads)
 ivf_group_select_kernel(const u64* __restrict__ cand, const int* __restrict__ count, int cap, int k,
-                        u64* __restrict__ out_keys) {
+                        u64* __restrict__ out_keys, unsigned long long* __restrict__ total_cand) {
   extern __shared__ u64 sk[];
   const int q = blockIdx.x;
   const int n = count[q];
+  if (threadIdx.x == 0 && total_cand) atomicAdd(total_cand, static_cast<unsigned long long>(n));
   if (n > cap) return;  // overflow: left to the rescue kernel
   int P = 32;
   while (P < n) P <<= 1;
@@ -1118,10 +1125,30 @@ __global__ void queries_to_f32_kernel(const T* __restrict__ q, int nq, int dim, 
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void probe_labels_kernel(const long long* __restrict__ probe_ids, int items,
-                                    int* __restrict__ labels) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += gridDim.x * blockDim.x)
-    labels[i] = probe_ids[i] < 0 ? 0 : static_cast<int>(probe_ids[i]);  // empty items still run
+// Sort label of item i = size rank of the list it probes (rank 0 = longest list), so that work
+// derived from the sorted order starts with the longest lists.
+__global__ void probe_labels_kernel(const long long* __restrict__ probe_ids, int items, int stride,
+                                    const int* __restrict__ rank_of_list, int* __restrict__ labels) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += gridDim.x * blockDim.x) {
+    const long long l = probe_ids[static_cast<size_t>(i) * stride];
+    labels[i] = rank_of_list[l < 0 ? 0 : l];  // empty items still run
+  }
+}
+
+// Lists in descending-size order (host; sizes are known after the build / load).
+static int build_list_ranks(IvfData* d) {
+  std::vector<int> order(d->n_lists), rank(d->n_lists);
+  for (int i = 0; i < d->n_lists; ++i) order[i] = i;
+  if (std::getenv("B2VS_IVF_NO_RANK") == nullptr)  // A/B knob: keep list-id order
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return d->h_sizes[a] > d->h_sizes[b]; });
+  for (int r = 0; r < d->n_lists; ++r) rank[order[r]] = r;
+  const size_t bytes = static_cast<size_t>(d->n_lists) * sizeof(int);
+  B2VS_TRY(d->rank_of_list.reserve(bytes));
+  B2VS_TRY(d->list_of_rank.reserve(bytes));
+  B2VS_CUDA(cudaMemcpy(d->rank_of_list.ptr, rank.data(), bytes, cudaMemcpyHostToDevice));
+  B2VS_CUDA(cudaMemcpy(d->list_of_rank.ptr, order.data(), bytes, cudaMemcpyHostToDevice));
+  return B2VS_OK;
 }
 
 // Instantiation table of the <FMT, J> scan kernels: J = 16-byte chunks of a row owned by a lane.
@@ -1144,25 +1171,34 @@ __global__ void probe_labels_kernel(const long long* __restrict__ probe_ids, int
     }                                                                                        \
   } while (0)
 
-// Counting sort of the (query, probe) items by list id (the same three kernels that build the
-// lists).  group_pad = 1: dense permutation (row_item[i] = i-th item in list order);
+// Counting sort of items by the size rank of their list (the same three kernels that build the
+// lists).  Item i probes list probe_ids[i * stride].  group_pad = 1: dense permutation (row_item[i] = i-th item in list order);
 // group_pad = 128: every list's group starts on a 128-row boundary, holes hold kNoRow.
-static int sort_items_by_list(IvfData* d, const long long* probe_ids, int items, int group_pad,
-                              cudaStream_t st) {
-  const size_t rows_cap = group_pad == 1
-                              ? static_cast<size_t>(items)
-                              : static_cast<size_t>(items) +
-                                    static_cast<size_t>(group_pad) * std::min(d->n_lists, items);
+static size_t sorted_rows_cap(const IvfData* d, int items, int group_pad) {
+  return group_pad == 1 ? static_cast<size_t>(items)
+                        : static_cast<size_t>(items) +
+                              static_cast<size_t>(group_pad) * std::min(d->n_lists, items);
+}
+
+static int reserve_item_sort(IvfData* d, int items, int group_pad) {
   B2VS_TRY(d->ws_item_lab.reserve(static_cast<size_t>(items) * sizeof(int)));
   B2VS_TRY(d->ws_item_cnt.reserve(static_cast<size_t>(d->n_lists) * 2 * sizeof(int)));
   B2VS_TRY(d->ws_item_off.reserve((static_cast<size_t>(d->n_lists) + 1) * sizeof(uint32_t)));
-  B2VS_TRY(d->ws_item_perm.reserve(rows_cap * sizeof(uint32_t)));
+  B2VS_TRY(d->ws_item_perm.reserve(sorted_rows_cap(d, items, group_pad) * sizeof(uint32_t)));
   B2VS_TRY(d->ws_item_slot.reserve(static_cast<size_t>(items) * sizeof(uint32_t)));
+  return B2VS_OK;
+}
+
+static int sort_items_by_list(IvfData* d, const long long* probe_ids, int items, int stride,
+                              int group_pad, cudaStream_t st) {
+  const size_t rows_cap = sorted_rows_cap(d, items, group_pad);
+  B2VS_TRY(reserve_item_sort(d, items, group_pad));
   const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(items, 256), 2048));
   int* cnt = d->ws_item_cnt.as<int>();
   B2VS_CUDA(cudaMemsetAsync(cnt, 0, static_cast<size_t>(d->n_lists) * 2 * sizeof(int), st));
   if (group_pad > 1) B2VS_CUDA(cudaMemsetAsync(d->ws_item_perm.ptr, 0xFF, rows_cap * sizeof(uint32_t), st));
-  probe_labels_kernel<<<blocks, 256, 0, st>>>(probe_ids, items, d->ws_item_lab.as<int>());
+  probe_labels_kernel<<<blocks, 256, 0, st>>>(probe_ids, items, stride, d->rank_of_list.as<int>(),
+                                              d->ws_item_lab.as<int>());
   histogram_kernel<<<blocks, 256, 0, st>>>(d->ws_item_lab.as<int>(), items, cnt);
   scan_sizes_kernel<<<1, 1024, 0, st>>>(cnt, d->n_lists, group_pad, d->ws_item_off.as<uint32_t>());
   scatter_rows_kernel<<<blocks, 256, 0, st>>>(d->ws_item_lab.as<int>(), items,
@@ -1183,7 +1219,11 @@ static int grouped_cap(int k) {
   }
   return k <= 32 ? 2048 : 4096;
 }
-static uint32_t grouped_seed_rows(int k) { return static_cast<uint32_t>(std::max(512, 16 * k)); }
+static uint32_t grouped_seed_rows(int k) {
+  const char* e = std::getenv("B2VS_IVF_SEED_ROWS");  // A/B knob
+  if (e && std::atoi(e) >= 32) return static_cast<uint32_t>(std::atoi(e));
+  return static_cast<uint32_t>(std::max(256, 16 * k));
+}
 
 // B2VS_IVF_GROUPED=0|1 forces the per-item / grouped IVF-Flat scan (A/B measurements, tests).
 static int grouped_override() {
@@ -1208,7 +1248,7 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
   B2VS_TRY(d->ws_keys.reserve(static_cast<size_t>(n_probes) * q_pad * k * sizeof(u64)));
   B2VS_TRY(d->ws_qf.reserve(static_cast<size_t>(nq) * d->dp * sizeof(float)));
   B2VS_TRY(d->ws_qnorm.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
-  B2VS_TRY(d->ws_counter.reserve(sizeof(unsigned long long)));
+  B2VS_TRY(d->ws_counter.reserve(2 * sizeof(unsigned long long)));  // scanned rows, candidates
   // K4 coarse probe: top-n_probes centroids on the tensor cores
   B2VS_TRY(index->flat.search(q, q_dtype, nq, n_probes, 0, 0, d->ws_probe_d.as<float>(),
                               d->ws_probe_i.as<int64_t>(), nullptr, st));
@@ -1218,7 +1258,7 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
                                  static_cast<const T*>(q), nq, index->dim, d->dp, d->fmt, round16,
                                  d->ws_qf.as<float>(), d->ws_qnorm.as<float>())));
   B2VS_CUDA(cudaGetLastError());
-  B2VS_CUDA(cudaMemsetAsync(d->ws_counter.ptr, 0, sizeof(unsigned long long), st));
+  B2VS_CUDA(cudaMemsetAsync(d->ws_counter.ptr, 0, 2 * sizeof(unsigned long long), st));
   launches += 2;
   const int items = nq * n_probes;
   const long long* probe_ids = reinterpret_cast<const long long*>(d->ws_probe_i.ptr);
@@ -1247,7 +1287,9 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
                          (ov >= 0 ? ov == 1 : (nq >= 64 && items >= 2 * d->n_lists));
     if (grouped) {
       const int cap = grouped_cap(k);
-      B2VS_TRY(sort_items_by_list(d, probe_ids, items, kGroupRows, st));
+      // seed thresholds first (queries ordered by their nearest list), then group all the items
+      B2VS_TRY(reserve_item_sort(d, items, kGroupRows));  // both sorts share these buffers
+      B2VS_TRY(sort_items_by_list(d, probe_ids, nq, n_probes, 1, st));
       const int max_work = items / kGroupRows + std::min(d->n_lists, items) + 1;
       const int64_t rows_cap = static_cast<int64_t>(items) + static_cast<int64_t>(kGroupRows) * std::min(d->n_lists, items);
       B2VS_TRY(d->ws_g_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16));
@@ -1260,9 +1302,12 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
       B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
       FLAT_SCAN_DISPATCH(ivf_seed_tau_kernel, d->fmt, j, nq, st, data, snorm, offs, probe_ids, qf, d->dp,
                          n_probes, k, alpha, grouped_seed_rows(k), d->max_norm2,
-                         index->metric == B2VS_METRIC_L2 ? 1 : 0, d->ws_g_tau.as<float>());
+                         index->metric == B2VS_METRIC_L2 ? 1 : 0, d->ws_item_perm.as<uint32_t>(),
+                         d->ws_g_tau.as<float>());
+      B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, kGroupRows, st));
       build_group_work_kernel<<<static_cast<unsigned>(ceil_div(d->n_lists, 256)), 256, 0, st>>>(
-          d->ws_item_off.as<uint32_t>(), offs, d->ws_item_cnt.as<int>(), d->n_lists,
+          d->ws_item_off.as<uint32_t>(), offs, d->ws_item_cnt.as<int>(), d->list_of_rank.as<int>(),
+          d->n_lists,
           d->ws_g_work.as<int4>(), n_work, counter);
       gather_group_queries_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
           d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists, qf, d->dp,
@@ -1278,11 +1323,11 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
       ga.cand = d->ws_g_cand.as<u64>(); ga.count = d->ws_g_cnt.as<int>(); ga.cap = cap;
       B2VS_TRY(launch_grouped_scan(index->dev, ga, st));
       ivf_group_select_kernel<<<nq, kSelectThreads, static_cast<size_t>(cap) * sizeof(u64), st>>>(
-          ga.cand, ga.count, cap, k, d->ws_keys.as<u64>());
+          ga.cand, ga.count, cap, k, d->ws_keys.as<u64>(), counter + 1);
       FLAT_SCAN_DISPATCH(ivf_flat_rescue_kernel, d->fmt, j, nq, st, data, snorm, offs, probe_ids, qf,
                          d->dp, n_probes, k, alpha, ga.count, cap, d->ws_keys.as<u64>());
       B2VS_CUDA(cudaGetLastError());
-      launches += 11;
+      launches += 16;
       single_list = true;
     } else {
       // Per-item scan.  Ordering the items by list pays once several queries share a list: the
@@ -1290,7 +1335,7 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
       const uint32_t* item_perm = nullptr;
       static const bool no_sort = getenv("B2VS_NO_ITEM_SORT") != nullptr;
       if (!no_sort && items >= 4 * d->n_lists) {
-        B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, st));
+        B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, 1, st));
         item_perm = d->ws_item_perm.as<uint32_t>();
         launches += 5;
       }
@@ -1362,6 +1407,7 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
   d->stats.grid = items;
   d->stats.algo_flops = 2.0 * nq * static_cast<double>(d->n_lists) * index->dim;
   d->counter_pending = true;
+  d->last_nq = nq;
   d->timing_pending = timed;
   return B2VS_OK;
 }
@@ -1380,10 +1426,12 @@ void ivf_last_stats(const b2vs_index* index, b2vs_search_stats* stats) {
   *stats = b2vs_search_stats{};
   if (!d) return;
   if (d->counter_pending && d->ws_counter.ptr) {
-    unsigned long long rows = 0;
+    unsigned long long cnt[2] = {0, 0};
     DeviceGuard guard(index->dev);
-    if (cudaMemcpy(&rows, d->ws_counter.ptr, sizeof(rows), cudaMemcpyDeviceToHost) == cudaSuccess)
-      d->stats.algo_bytes = static_cast<double>(rows) * d->row_bytes;
+    if (cudaMemcpy(cnt, d->ws_counter.ptr, sizeof(cnt), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      d->stats.algo_bytes = static_cast<double>(cnt[0]) * d->row_bytes;
+      d->stats.mean_candidates = static_cast<int32_t>(cnt[1] / static_cast<unsigned long long>(std::max(d->last_nq, 1)));
+    }
     d->counter_pending = false;
   }
   if (d->timing_pending && d->ev1) {
@@ -1512,6 +1560,7 @@ static int ivf_build(int kind, int dev, int metric, int dtype, int dim, const vo
   d->h_sizes.resize(n_lists);
   IB_CUDA(cudaMemcpy(d->h_sizes.data(), d->sizes.ptr, static_cast<size_t>(n_lists) * sizeof(int),
                      cudaMemcpyDeviceToHost));
+  IB_TRY(build_list_ranks(d));
   IB_TRY(d->row_ids.reserve(std::max<size_t>(total_slots, 1) * sizeof(uint32_t)));
   IB_CUDA(cudaMemsetAsync(d->row_ids.ptr, 0xFF, std::max<size_t>(total_slots, 1) * sizeof(uint32_t), st));
   scatter_rows_kernel<<<eblocks, 256, 0, st>>>(labels.as<int>(), n, d->offsets.as<uint32_t>(),
@@ -1754,6 +1803,7 @@ extern "C" int b2vs_index_load(int dev, const char* path, const void* rows_for_r
     d->h_sizes.resize(h.n_lists);
     if (cudaMemcpy(d->h_sizes.data(), d->sizes.ptr, h.bytes_sizes, cudaMemcpyDeviceToHost) != cudaSuccess)
       rc = B2VS_ECUDA;
+    if (rc == B2VS_OK) rc = build_list_ranks(d);
   }
   if (rc == B2VS_OK) {
     const int force = (h.dtype == B2VS_F32) ? -1 : h.fmt;

@@ -86,7 +86,7 @@ typedef struct b2vs_search_stats {
   int32_t launches;        /* kernels launched by the call */
   int32_t n_splits;        /* flat: db splits used */
   int32_t grid;            /* CTAs of the dominant kernel */
-  int32_t reserved;
+  int32_t mean_candidates; /* IVF-Flat grouped scan: appended candidates per query (mean), else 0 */
   double algo_flops;       /* 2*Q*N*D for the distance contraction (flat / coarse) */
   double algo_bytes;       /* IVF: sum of probed list bytes actually scanned */
   double kernel_ms;        /* device time of the dominant kernel (fused distance / list scan) when

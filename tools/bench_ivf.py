@@ -48,6 +48,7 @@ for rep in range(3):
 out["qps"] = round(nq / (out["search_ms_2"] * 1e-3), 1)
 out["scan_GBs"] = round(st.algo_bytes / (st.kernel_ms * 1e-3) / 1e9, 1)
 out["algo_bytes"] = st.algo_bytes
+out["mean_candidates"] = st.mean_candidates
 # recall@10 against the exact index on a query subset
 nchk = min(nq, 1000)
 flat = b2.NativeIndex.flat(x)
