@@ -19,7 +19,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("B2VS_LIB_PATH") or os.path.join(_HERE, "libb2vs.so")
-SOURCES = ["api.cu", "flat.cu", "merge.cu", "ivf.cu", "bigk.cu"]
+SOURCES = ["api.cu", "flat.cu", "merge.cu", "ivf.cu", "bigk.cu", "pq_tc.cu"]
 
 METRIC_L2, METRIC_IP = 0, 1
 F32, F16, BF16 = 0, 1, 2

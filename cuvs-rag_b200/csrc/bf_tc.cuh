@@ -97,7 +97,8 @@ template <int kMode>
 __device__ __forceinline__ void score_chunk(const uint32_t (&r)[32], const float4* __restrict__ nrm4,
                                             float alpha, uint32_t col, float& tau, int& cnt,
                                             u64& best, u64* __restrict__ my_cand,
-                                            int* __restrict__ g_cnt = nullptr, int g_cap = 0) {
+                                            int* __restrict__ g_cnt = nullptr, int g_cap = 0,
+                                            float bias = 0.f) {
   float sc[32];
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
@@ -146,7 +147,7 @@ __device__ __forceinline__ void score_chunk(const uint32_t (&r)[32], const float
         for (int i = 0; i < 2; ++i) v2[i] = (j & 8) ? v4[2 * i + 1] : v4[2 * i];
         const float v = (j & 16) ? v2[1] : v2[0];
         if (kMode == kModeAppend) {
-          if (pos < g_cap) __stcg(my_cand + pos, pack_key(v, col + j));
+          if (pos < g_cap) __stcg(my_cand + pos, pack_key(v + bias, col + j));  // bias: pq_tc.cuh
           ++pos;
         } else {
           __stcg(my_cand + cnt, pack_key(v, col + j));

@@ -153,6 +153,29 @@ struct GroupedScanArgs {
 };
 int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st);
 
+// Grouped IVF-PQ scan (pq_tc.cu): lists decoded once per batch into bf16 tiles for the tensor cores.
+struct PqGroupedScanArgs {
+  const void* q_mat;      // gathered residual queries [q_rows, dim] bf16
+  int64_t q_rows;
+  int dim, pq_dim, dsub;
+  const void* codes;      // interleaved PQ codes
+  uint32_t n_groups;      // 32-row groups in `codes`
+  const void* cb16;       // bf16 codebooks [pq_dim][256][dsub]
+  const float* beta;      // [n_slots + 256] ||r^||^2 (L2) / 0 (IP), +inf on padding slots
+  float alpha;
+  const void* work;       // int4 [max_work]
+  const int* n_work;
+  int max_work;
+  const int* row_query;   // [q_rows]
+  const float* row_bias;  // [q_rows]
+  const float* tau;       // [nq]
+  u64* cand;
+  int* count;
+  int cap;
+};
+bool pq_grouped_supported(int dim, int dsub);
+int launch_pq_grouped_scan(int dev, const PqGroupedScanArgs& a, cudaStream_t st);
+
 // merge.cu
 // `remap` (optional) translates key ids (list slots) to shard-local row ids before id_offset.
 int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k, int metric,

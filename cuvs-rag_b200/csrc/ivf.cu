@@ -45,9 +45,15 @@ struct IvfData {
   DevBuf slot_norm;   // IVF-Flat: f32 [n_slots + kNormSlack] ||x||^2 (L2) or 0 (IP); +inf on padding
   DevBuf codebooks;   // IVF-PQ: f32 [pq_dim, 256, dsub]
   DevBuf codes;       // IVF-PQ: u8, 32-row groups interleaved by 16-byte chunks
+  // IVF-PQ grouped tensor-core scan (derived from codebooks + codes at build / load time)
+  DevBuf cb16;        // bf16 [pq_dim, 256, dsub]: the codebooks as the MMA sees them
+  DevBuf cbn;         // f32 [pq_dim, 256] squared norm of each (rounded) codebook entry
+  DevBuf pq_norm;     // f32 [n_slots + kNormSlack] ||decoded residual||^2 (L2) / 0 (IP); +inf on padding
+  float max_rhat2 = 0.f;
+  bool pq_tc_ready = false;
   DevBuf ws_probe_d, ws_probe_i, ws_keys, ws_qf, ws_qnorm, ws_counter, ws_ref_d, ws_ref_i;
   DevBuf ws_item_lab, ws_item_cnt, ws_item_off, ws_item_perm, ws_item_slot;  // list-ordered scan items
-  DevBuf ws_g_work, ws_g_q, ws_g_rowq, ws_g_tau, ws_g_cand, ws_g_cnt;         // grouped scan
+  DevBuf ws_g_work, ws_g_q, ws_g_rowq, ws_g_tau, ws_g_cand, ws_g_cnt, ws_g_bias;  // grouped scan
   const void* src_rows = nullptr;  // IVF-PQ: the caller's [n, dim] rows, BORROWED for refine
   std::vector<int32_t> h_sizes;
   DevBuf rank_of_list, list_of_rank;  // int [n_lists]: lists in descending-size order (scan scheduling)
@@ -69,7 +75,8 @@ struct IvfData {
                       &rank_of_list, &list_of_rank,
                       &ws_probe_d, &ws_probe_i, &ws_keys, &ws_qf, &ws_qnorm, &ws_counter,
                       &ws_ref_d, &ws_ref_i, &ws_item_lab, &ws_item_cnt, &ws_item_off, &ws_item_perm,
-                      &ws_item_slot, &ws_g_work, &ws_g_q, &ws_g_rowq, &ws_g_tau, &ws_g_cand, &ws_g_cnt})
+                      &ws_item_slot, &ws_g_work, &ws_g_q, &ws_g_rowq, &ws_g_tau, &ws_g_cand, &ws_g_cnt,
+                      &ws_g_bias, &cb16, &cbn, &pq_norm})
       b->release();
   }
 };
@@ -1151,6 +1158,209 @@ static int build_list_ranks(IvfData* d) {
   return B2VS_OK;
 }
 
+// ---- K7b grouped IVF-PQ scan: pieces around pq_tc_kernel (pq_tc.cuh) ------------------------
+// bf16 copy of the codebooks + squared norm of every rounded entry
+__global__ void pq_cb16_kernel(const float* __restrict__ codebooks, int entries, int dsub,
+                               uint16_t* __restrict__ cb16, float* __restrict__ cbn) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= entries) return;
+  float n2 = 0.f;
+  for (int d = 0; d < dsub; ++d) {
+    float back;
+    cb16[static_cast<size_t>(e) * dsub + d] = to_op16(codebooks[static_cast<size_t>(e) * dsub + d], 1, &back);
+    n2 = fmaf(back, back, n2);
+  }
+  cbn[e] = n2;
+}
+
+// ||decoded residual||^2 of every slot (thread = slot); +inf on padding slots and in the slack
+__global__ void pq_slot_norms_kernel(const uint4* __restrict__ codes4, const uint32_t* __restrict__ row_ids,
+                                     uint32_t n_slots, size_t n_out, int n_chunks,
+                                     const float* __restrict__ cbn, int l2, float* __restrict__ out,
+                                     unsigned int* __restrict__ max_bits) {
+  const size_t slot = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float n2 = 0.f;
+  const bool real = slot < n_slots && row_ids[slot] != kNoRow;
+  if (real) {
+    const size_t g = slot >> 5;
+    const int r = static_cast<int>(slot & 31);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const uint4 v = __ldg(codes4 + (g * n_chunks + ch) * 32 + r);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        n2 += __ldg(cbn + (ch * 16 + i) * 256 + ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu));
+    }
+  }
+  if (slot < n_out) out[slot] = real ? (l2 ? n2 : 0.f) : INFINITY;
+  const unsigned int wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(n2));
+  if ((threadIdx.x & 31) == 0 && wmax != 0u) atomicMax(max_bits, wmax);
+}
+
+// LUT scan with the grouped path's operands (bf16-rounded residual query and codebooks), used
+// for its two scalar-side jobs.  mode 0 = SEED: query q_perm[blockIdx.x], nearest list only,
+// first row_limit rows -> tau[q] (k-th best + rounding cushion).  mode 1 = RESCUE: queries whose
+// candidate buffer overflowed are rescanned over all their probes -> out_keys[q][k].
+//   L2 score = ||rq||^2 + sum_m (||cb||^2 - 2 rq_m.cb)      IP score = -q.c - sum_m q_m.cb
+__global__ void __launch_bounds__(kScanThreads)
+ivf_pq_lut_scan_kernel(int mode, const uint8_t* __restrict__ codes, const uint32_t* __restrict__ row_ids,
+                       const uint32_t* __restrict__ offsets, const long long* __restrict__ probe_ids,
+                       const float* __restrict__ qf, const float* __restrict__ cent,
+                       const uint16_t* __restrict__ cb16, const float* __restrict__ cbn, int dim,
+                       int dp, int pq_dim, int dsub, int n_probes, int k, int metric,
+                       uint32_t row_limit, float max_rhat2, const uint32_t* __restrict__ q_perm,
+                       const int* __restrict__ count, int cap, float* __restrict__ tau,
+                       u64* __restrict__ out_keys) {
+  extern __shared__ float smem_f[];
+  float* lut = smem_f;                 // [pq_dim * 256]
+  float* rq = smem_f + pq_dim * 256;   // [dim]
+  __shared__ u64 lists[kScanWarps][32 * kListE];
+  __shared__ u64 top[kMaxFusedK];
+  __shared__ float red[kScanWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = mode == 0 ? static_cast<int>(q_perm[blockIdx.x]) : blockIdx.x;
+  if (mode == 1 && count[q] <= cap) return;
+  const int l2 = metric == B2VS_METRIC_L2;
+  WarpTopK tk;
+  tk.init();
+  float bias_first = 0.f;
+  const int np = mode == 0 ? 1 : n_probes;
+  const int n_chunks = pq_dim >> 4;
+  const uint4* codes4 = reinterpret_cast<const uint4*>(codes);
+  for (int p = 0; p < np; ++p) {
+    const long long list = probe_ids[static_cast<size_t>(q) * n_probes + p];
+    if (list < 0) continue;
+    __syncthreads();   // previous probe's LUT no longer in use
+    const float* c = cent + static_cast<size_t>(list) * dim;
+    float part_b = 0.f, part_n = 0.f;
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+      const float qv = qf[static_cast<size_t>(q) * dp + d];
+      float back;
+      to_op16(l2 ? qv - c[d] : qv, 1, &back);
+      rq[d] = back;
+      part_n = fmaf(back, back, part_n);
+      if (!l2) part_b = fmaf(qv, c[d], part_b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      part_b += __shfl_xor_sync(0xffffffffu, part_b, o);
+      part_n += __shfl_xor_sync(0xffffffffu, part_n, o);
+    }
+    if (lane == 0) red[warp] = l2 ? part_n : part_b;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < kScanWarps; ++w) tot += red[w];
+    const float bias = l2 ? tot : -tot;
+    if (p == 0) bias_first = bias;
+    for (int idx = threadIdx.x; idx < pq_dim * 256; idx += blockDim.x) {
+      const int m = idx >> 8;
+      float dot = 0.f;
+      for (int d = 0; d < dsub; ++d)
+        dot = fmaf(rq[m * dsub + d], __uint_as_float(static_cast<uint32_t>(cb16[static_cast<size_t>(idx) * dsub + d]) << 16), dot);
+      lut[idx] = l2 ? fmaf(-2.f, dot, cbn[idx]) : -dot;
+    }
+    __syncthreads();
+    const uint32_t begin = offsets[list];
+    const uint32_t end = mode == 0 ? min(offsets[list + 1], begin + row_limit) : offsets[list + 1];
+    for (uint32_t g0 = (begin >> 5) + warp; g0 < (end >> 5); g0 += kScanWarps) {
+      const uint32_t slot = (g0 << 5) + lane;
+      float sc = bias;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        const uint4 v = __ldg(codes4 + (static_cast<size_t>(g0) * n_chunks + ch) * 32 + lane);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          sc += lut[(ch * 16 + i) * 256 + ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu)];
+      }
+      u64 ck = kKeyInf;
+      if (row_ids[slot] != kNoRow && sc < tk.tau) ck = pack_key(sc, slot);
+      tk.offer(ck, k, lane);
+    }
+  }
+  if (mode == 1) {
+    block_merge_and_store(tk, lists, k, warp, lane, out_keys + static_cast<size_t>(q) * k);
+    return;
+  }
+  block_merge_and_store(tk, lists, k, warp, lane, top);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // cushion for the different summation order of the tensor-core kernel (same products)
+    const u64 kth = top[k - 1];
+    float t = INFINITY;
+    if (kth != kKeyInf) {
+      const float sc = key_score(kth);
+      float rqn = 0.f;
+      for (int d = 0; d < dim; ++d) rqn = fmaf(rq[d], rq[d], rqn);
+      const float eps = static_cast<float>(dim) * 1.2e-7f + 1e-6f;
+      t = sc + (l2 ? 2.f : 1.f) * eps * sqrtf(rqn * max_rhat2) +
+          4e-7f * (fabsf(sc) + fabsf(bias_first) + rqn + max_rhat2);
+    }
+    tau[q] = t;
+  }
+}
+
+// One warp per gathered row: residual query (bf16) of item row_item[v] = (query, probe), its
+// additive constant (||rq||^2 or -q.c) and its query id.
+__global__ void gather_group_residuals_kernel(const uint32_t* __restrict__ row_item,
+                                              const uint32_t* __restrict__ group_off, int n_lists,
+                                              const long long* __restrict__ probe_ids,
+                                              const float* __restrict__ qf, const float* __restrict__ cent,
+                                              int dim, int dp, int n_probes, int l2,
+                                              uint16_t* __restrict__ out, int* __restrict__ row_query,
+                                              float* __restrict__ row_bias) {
+  const int lane = threadIdx.x & 31;
+  const int64_t v = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (v >= static_cast<int64_t>(group_off[n_lists])) return;
+  const uint32_t item = row_item[v];
+  uint16_t* orow = out + static_cast<size_t>(v) * dim;
+  if (item == kNoRow) {
+    for (int j = lane; j < dim; j += 32) orow[j] = 0;
+    if (lane == 0) { row_query[v] = -1; row_bias[v] = 0.f; }
+    return;
+  }
+  const int q = static_cast<int>(item / static_cast<uint32_t>(n_probes));
+  const long long list = probe_ids[item];
+  const float* c = cent + static_cast<size_t>(list < 0 ? 0 : list) * dim;
+  float acc = 0.f;
+  for (int j = lane; j < dim; j += 32) {
+    const float qv = qf[static_cast<size_t>(q) * dp + j];
+    float back;
+    orow[j] = to_op16(l2 ? qv - c[j] : qv, 1, &back);
+    acc = l2 ? fmaf(back, back, acc) : fmaf(qv, c[j], acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) { row_query[v] = q; row_bias[v] = l2 ? acc : -acc; }
+}
+
+// Derives the grouped scan's operands from codebooks + codes (after a build or a load).
+static int pq_prepare_grouped(b2vs_index* index, IvfData* d, cudaStream_t st) {
+  d->pq_tc_ready = false;
+  if (!pq_grouped_supported(index->dim, d->dsub) || d->mp != d->pq_dim) return B2VS_OK;
+  const int entries = d->pq_dim * 256;
+  const size_t n_out = static_cast<size_t>(std::max<int64_t>(d->n_slots, 1)) + kNormSlack;
+  B2VS_TRY(d->cb16.reserve(static_cast<size_t>(entries) * d->dsub * 2));
+  B2VS_TRY(d->cbn.reserve(static_cast<size_t>(entries) * sizeof(float)));
+  B2VS_TRY(d->pq_norm.reserve(n_out * sizeof(float)));
+  DevBuf cell;
+  B2VS_TRY(cell.reserve(sizeof(unsigned int)));
+  B2VS_CUDA(cudaMemsetAsync(cell.ptr, 0, sizeof(unsigned int), st));
+  pq_cb16_kernel<<<static_cast<unsigned>(ceil_div(entries, 256)), 256, 0, st>>>(
+      d->codebooks.as<float>(), entries, d->dsub, d->cb16.as<uint16_t>(), d->cbn.as<float>());
+  pq_slot_norms_kernel<<<static_cast<unsigned>(ceil_div(n_out, 256)), 256, 0, st>>>(
+      d->codes.as<uint4>(), d->row_ids.as<uint32_t>(), static_cast<uint32_t>(d->n_slots), n_out,
+      d->mp >> 4, d->cbn.as<float>(), index->metric == B2VS_METRIC_L2 ? 1 : 0,
+      d->pq_norm.as<float>(), cell.as<unsigned int>());
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&d->max_rhat2, cell.ptr, sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cell.release();
+  B2VS_CHECK(e == cudaSuccess, B2VS_ECUDA, "preparing the grouped PQ scan failed: %s", cudaGetErrorString(e));
+  d->pq_tc_ready = true;
+  return B2VS_OK;
+}
+
 // Instantiation table of the <FMT, J> scan kernels: J = 16-byte chunks of a row owned by a lane.
 #define FLAT_SCAN_DISPATCH(KERNEL, fmt, j, grid, st, ...)                                    \
   do {                                                                                       \
@@ -1344,6 +1554,68 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
       B2VS_CUDA(cudaGetLastError());
     }
     qnorm_for_merge = d->ws_qnorm.as<float>();
+  } else if (d->pq_tc_ready &&
+             (grouped_override() >= 0 ? grouped_override() == 1
+                                      : (nq >= 64 && items >= 2 * d->n_lists))) {
+    // Grouped tensor-core scan (pq_tc.cuh): same pipeline as the IVF-Flat one, the list tiles are
+    // decoded from the PQ codes instead of loaded.
+    const int l2 = index->metric == B2VS_METRIC_L2 ? 1 : 0;
+    const float alpha = l2 ? -2.f : -1.f;
+    const int cap = grouped_cap(k);
+    const uint32_t* offs = d->offsets.as<uint32_t>();
+    const float* qf = d->ws_qf.as<float>();
+    B2VS_TRY(reserve_item_sort(d, items, kGroupRows));
+    B2VS_TRY(sort_items_by_list(d, probe_ids, nq, n_probes, 1, st));
+    const int max_work = items / kGroupRows + std::min(d->n_lists, items) + 1;
+    const int64_t rows_cap = static_cast<int64_t>(sorted_rows_cap(d, items, kGroupRows));
+    B2VS_TRY(d->ws_g_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16));
+    B2VS_TRY(d->ws_g_q.reserve(static_cast<size_t>(rows_cap) * index->dim * 2));
+    B2VS_TRY(d->ws_g_rowq.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
+    B2VS_TRY(d->ws_g_bias.reserve(static_cast<size_t>(rows_cap) * sizeof(float)));
+    B2VS_TRY(d->ws_g_tau.reserve(static_cast<size_t>(nq) * sizeof(float)));
+    B2VS_TRY(d->ws_g_cand.reserve(static_cast<size_t>(nq) * cap * sizeof(u64)));
+    B2VS_TRY(d->ws_g_cnt.reserve(static_cast<size_t>(nq) * sizeof(int)));
+    int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
+    B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
+    const size_t lut_smem = (static_cast<size_t>(d->pq_dim) * 256 + index->dim) * sizeof(float);
+    B2VS_CUDA(cudaFuncSetAttribute(ivf_pq_lut_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(lut_smem)));
+    ivf_pq_lut_scan_kernel<<<nq, kScanThreads, lut_smem, st>>>(
+        0, d->codes.as<uint8_t>(), d->row_ids.as<uint32_t>(), offs, probe_ids, qf,
+        d->centroids.as<float>(), d->cb16.as<uint16_t>(), d->cbn.as<float>(), index->dim, d->dp,
+        d->pq_dim, d->dsub, n_probes, k, index->metric, grouped_seed_rows(k), d->max_rhat2,
+        d->ws_item_perm.as<uint32_t>(), nullptr, cap, d->ws_g_tau.as<float>(), nullptr);
+    B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, kGroupRows, st));
+    build_group_work_kernel<<<static_cast<unsigned>(ceil_div(d->n_lists, 256)), 256, 0, st>>>(
+        d->ws_item_off.as<uint32_t>(), offs, d->ws_item_cnt.as<int>(), d->list_of_rank.as<int>(),
+        d->n_lists, d->ws_g_work.as<int4>(), n_work, counter);
+    gather_group_residuals_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
+        d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists, probe_ids, qf,
+        d->centroids.as<float>(), index->dim, d->dp, n_probes, l2, d->ws_g_q.as<uint16_t>(),
+        d->ws_g_rowq.as<int>(), d->ws_g_bias.as<float>());
+    B2VS_CUDA(cudaGetLastError());
+    PqGroupedScanArgs ga{};
+    ga.q_mat = d->ws_g_q.ptr; ga.q_rows = rows_cap;
+    ga.dim = index->dim; ga.pq_dim = d->pq_dim; ga.dsub = d->dsub;
+    ga.codes = d->codes.ptr;
+    ga.n_groups = static_cast<uint32_t>(std::max<int64_t>(d->n_slots, 32) >> 5);
+    ga.cb16 = d->cb16.ptr;
+    ga.beta = d->pq_norm.as<float>(); ga.alpha = alpha;
+    ga.work = d->ws_g_work.ptr; ga.n_work = n_work; ga.max_work = max_work;
+    ga.row_query = d->ws_g_rowq.as<int>(); ga.row_bias = d->ws_g_bias.as<float>();
+    ga.tau = d->ws_g_tau.as<float>();
+    ga.cand = d->ws_g_cand.as<u64>(); ga.count = d->ws_g_cnt.as<int>(); ga.cap = cap;
+    B2VS_TRY(launch_pq_grouped_scan(index->dev, ga, st));
+    ivf_group_select_kernel<<<nq, kSelectThreads, static_cast<size_t>(cap) * sizeof(u64), st>>>(
+        ga.cand, ga.count, cap, k, d->ws_keys.as<u64>(), counter + 1);
+    ivf_pq_lut_scan_kernel<<<nq, kScanThreads, lut_smem, st>>>(
+        1, d->codes.as<uint8_t>(), d->row_ids.as<uint32_t>(), offs, probe_ids, qf,
+        d->centroids.as<float>(), d->cb16.as<uint16_t>(), d->cbn.as<float>(), index->dim, d->dp,
+        d->pq_dim, d->dsub, n_probes, k, index->metric, 0u, d->max_rhat2, nullptr, ga.count, cap,
+        nullptr, d->ws_keys.as<u64>());
+    B2VS_CUDA(cudaGetLastError());
+    launches += 16;
+    single_list = true;
   } else {
     const size_t cb_floats = static_cast<size_t>(d->pq_dim) * 256 * d->dsub;
     const size_t smem_p = (cb_floats + static_cast<size_t>(d->mp) * 256 + 2 * index->dim) * sizeof(float);
@@ -1612,6 +1884,7 @@ static int ivf_build(int kind, int dev, int metric, int dtype, int dim, const vo
                                  d->codebooks.as<float>(), slot_of_row.as<uint32_t>(), n, dim, dsub,
                                  d->mp, d->codes.as<uint8_t>())));
     IB_CUDA(cudaGetLastError());
+    IB_TRY(pq_prepare_grouped(ix, d, st));
   }
   // ---- 6. coarse quantizer used at search time (index metric)
   if (metric == B2VS_METRIC_L2) {
@@ -1809,6 +2082,7 @@ extern "C" int b2vs_index_load(int dev, const char* path, const void* rows_for_r
     const int force = (h.dtype == B2VS_F32) ? -1 : h.fmt;
     rc = ix->flat.init(dev, h.metric, B2VS_F32, h.dim, d->centroids.ptr, h.n_lists, st, force);
   }
+  if (rc == B2VS_OK && h.kind == B2VS_KIND_IVF_PQ) rc = pq_prepare_grouped(ix, d, st);
   if (rc == B2VS_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = B2VS_ECUDA;
   if (rc != B2VS_OK) {
     ivf_destroy(ix);

@@ -1,0 +1,51 @@
+// Host launcher of the grouped IVF-PQ tensor-core scan (pq_tc.cuh); called from ivf.cu.
+#include <algorithm>
+
+#include "common.h"
+#include "pq_tc.cuh"
+
+namespace b2vs {
+
+bool pq_grouped_supported(int dim, int dsub) {
+  return (dsub == 2 || dsub == 4) && dim % kBK == 0 && dim * 512 <= kPqTcMaxCbBytes;
+}
+
+int launch_pq_grouped_scan(int dev, const PqGroupedScanArgs& a, cudaStream_t st) {
+  CUtensorMap tm_q;
+  B2VS_TRY(encode_tmap_2d(&tm_q, a.q_mat, 1, a.q_rows, a.dim, kBM));
+  PqTcParams pp{};
+  BfTcParams& p = pp.tc;
+  p.beta = a.beta;
+  p.k_blocks = a.dim / kBK;
+  p.k = 1;
+  p.tile_stride = 1;
+  p.alpha = a.alpha;
+  p.idesc = ptx::make_idesc_f16(1u, kBM, kBN);
+  p.tau_init = a.tau;
+  p.big_cand = a.cand;
+  p.big_count = a.count;
+  p.big_cap = a.cap;
+  p.work = static_cast<const int4*>(a.work);
+  p.n_work = a.n_work;
+  p.row_query = a.row_query;
+  pp.codes4 = static_cast<const uint4*>(a.codes);
+  pp.cb16 = static_cast<const uint32_t*>(a.cb16);
+  pp.row_bias = a.row_bias;
+  pp.n_code_chunks = a.pq_dim / 16;
+  pp.n_groups = a.n_groups;
+  pp.cb_words = a.pq_dim * 256 * a.dsub / 2;
+  const int grid = std::max(1, std::min(a.max_work, sm_count(dev)));
+  if (a.dsub == 2) {
+    B2VS_CUDA(cudaFuncSetAttribute(pq_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kPqTcSmemBytes));
+    pq_tc_kernel<2><<<grid, kPqTcThreads, kPqTcSmemBytes, st>>>(tm_q, pp);
+  } else {
+    B2VS_CUDA(cudaFuncSetAttribute(pq_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kPqTcSmemBytes));
+    pq_tc_kernel<4><<<grid, kPqTcThreads, kPqTcSmemBytes, st>>>(tm_q, pp);
+  }
+  B2VS_CUDA(cudaGetLastError());
+  return B2VS_OK;
+}
+
+}  // namespace b2vs

@@ -121,9 +121,10 @@ def test_ivf_pq_refine_lifts_recall_like_the_oracle(b2):
 
 @pytest.mark.parametrize("d,m,label", [(128, 64, "specialised query-major scan (M=64, dsub=2)"),
                                        (768, 96, "per-(query, probe) scan: codebooks exceed smem")])
-def test_ivf_pq_kernel_variants_match_oracle(b2, d, m, label):
+def test_ivf_pq_kernel_variants_match_oracle(b2, monkeypatch, d, m, label):
     from oracle.exact import exact_knn
     from oracle.ivf import IvfPqOracle, recall
+    monkeypatch.setenv("B2VS_IVF_GROUPED", "0")      # the look-up-table kernels, not the grouped scan
     n, nlist, nprobe, k = 20000, 32, 8, 10
     x = clustered(n, d, 60, 12).to(torch.float16)
     q = queries_from(x.float(), 100, 13).to(torch.float16)
@@ -215,3 +216,40 @@ def test_ivf_flat_grouped_scan_ragged_batch(b2, monkeypatch):
         dd, ii = ix.search(q.cuda(), 5, n_probes=32)
         assert recall(ii.cpu(), ti) > 0.99
         assert bool((dd[:, 1:] >= dd[:, :-1]).all())
+
+
+@pytest.mark.parametrize("metric,d,m", [("sqeuclidean", 128, 64), ("inner_product", 128, 64),
+                                         ("sqeuclidean", 64, 16)])
+def test_ivf_pq_grouped_scan_equals_lut_scan(b2, monkeypatch, metric, d, m):
+    """Large batches decode each probed list once into bf16 tiles for the tensor cores.  Its ADC
+    scores use bf16-rounded residual queries / codebooks, so against the fp32 look-up-table scan
+    of the same index: near-identical candidate sets and distances, same recall; after the exact
+    refine step the answers coincide.  Also drives the overflow-rescue kernel."""
+    from oracle.exact import exact_knn
+    from oracle.ivf import recall
+    n, nlist, nprobe, nq, k = 40000, 64, 12, 600, 10
+    x = clustered(n, d, 80, 51).to(torch.float16)
+    q = queries_from(x.float(), nq, 52).to(torch.float16)
+    ix = b2.NativeIndex.ivf_pq(x.cuda(), nlist, m, metric=metric, kmeans_iters=8, id_offset=7)
+    _, ti = exact_knn(x.float(), q.float(), k, metric)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B2VS_IVF_GROUPED", mode)
+        out[mode] = ix.search(q.cuda(), k, n_probes=nprobe)
+        out[mode + "r"] = ix.search(q.cuda(), k, n_probes=nprobe, refine_ratio=4)
+        torch.cuda.synchronize()
+    monkeypatch.setenv("B2VS_IVF_GROUPED_CAP", "32")
+    out["1c"] = ix.search(q.cuda(), k, n_probes=nprobe)
+    torch.cuda.synchronize()
+    (d0, i0), (d1, i1), (d2, i2) = out["0"], out["1"], out["1c"]
+    for dd, ii in ((d1, i1), (d2, i2)):
+        inter = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(ii.cpu(), i0.cpu()))
+        assert inter >= 0.93 * nq * k, inter / (nq * k)
+        scale = float(d0[torch.isfinite(d0)].abs().max())
+        assert float((dd - d0).abs().median()) <= 5e-3 * scale
+        assert abs(recall(ii.cpu() - 7, ti) - recall(i0.cpu() - 7, ti)) < 0.02
+    # the rescue kernel uses the same operands as the tensor-core path: same answer as uncapped
+    assert (i2 == i1).float().mean().item() > 0.97
+    (dr0, ir0), (dr1, ir1) = out["0r"], out["1r"]
+    assert abs(recall(ir1.cpu() - 7, ti) - recall(ir0.cpu() - 7, ti)) < 0.01
+    assert (ir1 == ir0).float().mean().item() > 0.97
