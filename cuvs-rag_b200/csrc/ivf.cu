@@ -1253,12 +1253,26 @@ ivf_pq_lut_scan_kernel(int mode, const uint8_t* __restrict__ codes, const uint32
     for (int w = 0; w < kScanWarps; ++w) tot += red[w];
     const float bias = l2 ? tot : -tot;
     if (p == 0) bias_first = bias;
-    for (int idx = threadIdx.x; idx < pq_dim * 256; idx += blockDim.x) {
-      const int m = idx >> 8;
-      float dot = 0.f;
-      for (int d = 0; d < dsub; ++d)
-        dot = fmaf(rq[m * dsub + d], __uint_as_float(static_cast<uint32_t>(cb16[static_cast<size_t>(idx) * dsub + d]) << 16), dot);
-      lut[idx] = l2 ? fmaf(-2.f, dot, cbn[idx]) : -dot;
+    // one entry per thread per step; unrolled so several L2 loads are in flight per thread
+    if (dsub == 2) {
+      const uint32_t* cbw = reinterpret_cast<const uint32_t*>(cb16);
+#pragma unroll 8
+      for (int idx = threadIdx.x; idx < pq_dim * 256; idx += kScanThreads) {
+        const int m = idx >> 8;
+        const uint32_t w = __ldg(cbw + idx);
+        const float dot = fmaf(rq[2 * m + 1], __uint_as_float(w & 0xFFFF0000u),
+                               rq[2 * m] * __uint_as_float(w << 16));
+        lut[idx] = l2 ? fmaf(-2.f, dot, __ldg(cbn + idx)) : -dot;
+      }
+    } else {
+#pragma unroll 4
+      for (int idx = threadIdx.x; idx < pq_dim * 256; idx += kScanThreads) {
+        const int m = idx >> 8;
+        float dot = 0.f;
+        for (int d = 0; d < dsub; ++d)
+          dot = fmaf(rq[m * dsub + d], __uint_as_float(static_cast<uint32_t>(cb16[static_cast<size_t>(idx) * dsub + d]) << 16), dot);
+        lut[idx] = l2 ? fmaf(-2.f, dot, __ldg(cbn + idx)) : -dot;
+      }
     }
     __syncthreads();
     const uint32_t begin = offsets[list];
