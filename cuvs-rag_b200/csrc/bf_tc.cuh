@@ -82,6 +82,8 @@ struct BfTcParams {
   const int4* work;
   const int* n_work;    // device scalar: number of work items
   const int* row_query; // [query rows]
+  int x_kblocks;        // > 0: the query operand is [hi | lo] (2*x_kblocks k-blocks) against the SAME
+                        // x_kblocks db k-blocks (fp32 queries split into two bf16 halves)
 };
 
 constexpr int kModeBuffer = 0;   // per-(CTA,row) candidate buffer + warp compaction (k <= 128)
@@ -275,7 +277,8 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
               // the query block is re-read for every db tile: ask L2 to keep it (evict-last)
               ptx::tma_load_2d_hint(a_dst, &tm_q, bar_full + 8 * stage, kb * kBK, q_row0,
                                     ptx::kEvictLast);
-              ptx::tma_load_2d(a_dst + Cfg::kABytes, &tm_x, bar_full + 8 * stage, kb * kBK, x_row0);
+              const int xkb = (kWork && p.x_kblocks > 0 && kb >= p.x_kblocks) ? kb - p.x_kblocks : kb;
+              ptx::tma_load_2d(a_dst + Cfg::kABytes, &tm_x, bar_full + 8 * stage, xkb * kBK, x_row0);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }

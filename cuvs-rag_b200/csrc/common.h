@@ -140,6 +140,7 @@ struct GroupedScanArgs {
   const void* x_mat;      // list rows [x_rows, kdim] 16-bit
   int64_t x_rows;
   int kdim, ab_format;
+  int q_split;            // 1: q_mat is [hi | lo], each half padded to a multiple of 64 columns
   const float* beta;      // [x_rows + 256] additive term per list row (+inf on padding slots)
   float alpha;
   const void* work;       // int4 [max_work] {query block, first row, end row, -}

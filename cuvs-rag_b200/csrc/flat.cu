@@ -457,11 +457,13 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
 // ------------------------------------------------------------------------------------------
 int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st) {
   CUtensorMap tm_q, tm_xl;
-  B2VS_TRY(encode_tmap_2d(&tm_q, a.q_mat, a.ab_format, a.q_rows, a.kdim, kBM));
+  const int xkb = static_cast<int>(ceil_div(a.kdim, kBK));
+  B2VS_TRY(encode_tmap_2d(&tm_q, a.q_mat, a.ab_format, a.q_rows, a.q_split ? 2 * xkb * kBK : a.kdim, kBM));
   B2VS_TRY(encode_tmap_2d(&tm_xl, a.x_mat, a.ab_format, a.x_rows, a.kdim, kBN));
   BfTcParams p{};
   p.beta = a.beta;
-  p.k_blocks = static_cast<int>(ceil_div(a.kdim, kBK));
+  p.k_blocks = a.q_split ? 2 * xkb : xkb;
+  p.x_kblocks = a.q_split ? xkb : 0;
   p.k = 1;
   p.tile_stride = 1;
   p.alpha = a.alpha;

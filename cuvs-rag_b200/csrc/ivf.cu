@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(kScanThreads, 2)
 ivf_seed_tau_kernel(const uint16_t* __restrict__ data, const float* __restrict__ slot_norm,
                     const uint32_t* __restrict__ offsets, const long long* __restrict__ probe_ids,
                     const float* __restrict__ qf, int dp, int n_probes, int k, float alpha,
-                    uint32_t row_limit, float max_norm2, int l2,
+                    uint32_t row_limit, float max_norm2, int l2, float extra_eps,
                     const uint32_t* __restrict__ q_perm, float* __restrict__ tau) {
   __shared__ u64 lists[kScanWarps][32 * kListE];
   __shared__ u64 top[kMaxFusedK];
@@ -613,7 +613,7 @@ ivf_seed_tau_kernel(const uint16_t* __restrict__ data, const float* __restrict__
     float t = INFINITY;
     if (kth != kKeyInf) {
       const float sc = key_score(kth);
-      const float eps = static_cast<float>(dp) * 1.2e-7f + 1e-6f;
+      const float eps = static_cast<float>(dp) * 1.2e-7f + 1e-6f + extra_eps;
       t = sc + fabsf(alpha) * eps * sqrtf(qn * max_norm2) + 4e-7f * (fabsf(sc) + (l2 ? max_norm2 : 0.f));
     }
     tau[q] = t;
@@ -643,7 +643,7 @@ __global__ void build_group_work_kernel(const uint32_t* __restrict__ group_off,
 __global__ void gather_group_queries_kernel(const uint32_t* __restrict__ row_item,
                                             const uint32_t* __restrict__ group_off, int n_lists,
                                             const float* __restrict__ qf, int dp, int n_probes,
-                                            int fmt, uint16_t* __restrict__ out,
+                                            int fmt, int split, uint16_t* __restrict__ out,
                                             int* __restrict__ row_query) {
   const int lane = threadIdx.x & 31;
   const int64_t v = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -651,10 +651,27 @@ __global__ void gather_group_queries_kernel(const uint32_t* __restrict__ row_ite
   const uint32_t item = row_item[v];
   const int q = item == kNoRow ? -1 : static_cast<int>(item / static_cast<uint32_t>(n_probes));
   if (lane == 0) row_query[v] = q;
-  uint16_t* orow = out + static_cast<size_t>(v) * dp;
-  for (int j = lane; j < dp; j += 32) {
-    float back;
-    orow[j] = q < 0 ? uint16_t(0) : to_op16(qf[static_cast<size_t>(q) * dp + j], fmt, &back);
+  if (!split) {
+    uint16_t* orow = out + static_cast<size_t>(v) * dp;
+    for (int j = lane; j < dp; j += 32) {
+      float back;
+      orow[j] = q < 0 ? uint16_t(0) : to_op16(qf[static_cast<size_t>(q) * dp + j], fmt, &back);
+    }
+    return;
+  }
+  // fp32 queries: [hi | lo] bf16 halves, each padded to a multiple of 64 columns
+  const int half = (dp + 63) & ~63;
+  uint16_t* orow = out + static_cast<size_t>(v) * 2 * half;
+  for (int j = lane; j < half; j += 32) {
+    uint16_t hi = 0, lo = 0;
+    if (q >= 0 && j < dp) {
+      const float x = qf[static_cast<size_t>(q) * dp + j];
+      float hb, lb;
+      hi = to_op16(x, 1, &hb);
+      lo = to_op16(x - hb, 1, &lb);
+    }
+    orow[j] = hi;
+    orow[half + j] = lo;
   }
 }
 
@@ -1506,9 +1523,11 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
     const float* qf = d->ws_qf.as<float>();
     const int ov = grouped_override();
     // grouped tensor-core scan once the batch averages a few queries per list
-    // (fp32-source indexes keep fp32 queries against the 16-bit rows: per-item scan only)
-    const bool grouped = index->dtype != B2VS_F32 &&
-                         (ov >= 0 ? ov == 1 : (nq >= 64 && items >= 2 * d->n_lists));
+    const bool grouped = ov >= 0 ? ov == 1 : (nq >= 64 && items >= 2 * d->n_lists);
+    // fp32-source indexes keep fp32 queries against their bf16 rows: the query operand is split
+    // into bf16 [hi | lo] halves multiplied against the same list tiles (2x the MMA work)
+    const int q_split = index->dtype == B2VS_F32 ? 1 : 0;
+    const int q_pitch = q_split ? 2 * static_cast<int>(round_up(d->dp, 64)) : d->dp;
     if (grouped) {
       const int cap = grouped_cap(k);
       // seed thresholds first (queries ordered by their nearest list), then group all the items
@@ -1517,7 +1536,7 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
       const int max_work = items / kGroupRows + std::min(d->n_lists, items) + 1;
       const int64_t rows_cap = static_cast<int64_t>(items) + static_cast<int64_t>(kGroupRows) * std::min(d->n_lists, items);
       B2VS_TRY(d->ws_g_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16));
-      B2VS_TRY(d->ws_g_q.reserve(static_cast<size_t>(rows_cap) * d->dp * 2));
+      B2VS_TRY(d->ws_g_q.reserve(static_cast<size_t>(rows_cap) * q_pitch * 2));
       B2VS_TRY(d->ws_g_rowq.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
       B2VS_TRY(d->ws_g_tau.reserve(static_cast<size_t>(nq) * sizeof(float)));
       B2VS_TRY(d->ws_g_cand.reserve(static_cast<size_t>(nq) * cap * sizeof(u64)));
@@ -1526,8 +1545,8 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
       B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
       FLAT_SCAN_DISPATCH(ivf_seed_tau_kernel, d->fmt, j, nq, st, data, snorm, offs, probe_ids, qf, d->dp,
                          n_probes, k, alpha, grouped_seed_rows(k), d->max_norm2,
-                         index->metric == B2VS_METRIC_L2 ? 1 : 0, d->ws_item_perm.as<uint32_t>(),
-                         d->ws_g_tau.as<float>());
+                         index->metric == B2VS_METRIC_L2 ? 1 : 0, q_split ? 1e-5f : 0.f,
+                         d->ws_item_perm.as<uint32_t>(), d->ws_g_tau.as<float>());
       B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, kGroupRows, st));
       build_group_work_kernel<<<static_cast<unsigned>(ceil_div(d->n_lists, 256)), 256, 0, st>>>(
           d->ws_item_off.as<uint32_t>(), offs, d->ws_item_cnt.as<int>(), d->list_of_rank.as<int>(),
@@ -1535,12 +1554,12 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
           d->ws_g_work.as<int4>(), n_work, counter);
       gather_group_queries_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
           d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists, qf, d->dp,
-          n_probes, d->fmt, d->ws_g_q.as<uint16_t>(), d->ws_g_rowq.as<int>());
+          n_probes, d->fmt, q_split, d->ws_g_q.as<uint16_t>(), d->ws_g_rowq.as<int>());
       B2VS_CUDA(cudaGetLastError());
       GroupedScanArgs ga{};
       ga.q_mat = d->ws_g_q.ptr; ga.q_rows = rows_cap;
       ga.x_mat = d->data.ptr; ga.x_rows = d->n_slots;
-      ga.kdim = d->dp; ga.ab_format = d->fmt;
+      ga.kdim = d->dp; ga.ab_format = d->fmt; ga.q_split = q_split;
       ga.beta = snorm; ga.alpha = alpha;
       ga.work = d->ws_g_work.ptr; ga.n_work = n_work; ga.max_work = max_work;
       ga.row_query = d->ws_g_rowq.as<int>(); ga.tau = d->ws_g_tau.as<float>();

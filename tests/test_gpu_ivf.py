@@ -174,7 +174,9 @@ def test_flat_index_save_is_refused(b2, tmp_path):
 
 @pytest.mark.parametrize("dtype,metric,d,k", [(torch.bfloat16, "sqeuclidean", 128, 10),
                                                (torch.float16, "inner_product", 72, 10),
-                                               (torch.bfloat16, "sqeuclidean", 200, 100)])
+                                               (torch.bfloat16, "sqeuclidean", 200, 100),
+                                               (torch.float32, "sqeuclidean", 200, 100),
+                                               (torch.float32, "inner_product", 96, 10)])
 def test_ivf_flat_grouped_scan_equals_per_item_scan(b2, monkeypatch, dtype, metric, d, k):
     """Large batches take the grouped tensor-core list scan; it must return what the per-(query,
     probe) scan returns on the same index (ties aside), including when every candidate buffer
