@@ -1472,10 +1472,39 @@ static int grouped_override() {
   return (e && (e[0] == '0' || e[0] == '1')) ? (e[0] - '0') : -1;
 }
 
+static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
+                            const b2vs_search_params& sp, float* out_d, int64_t* out_i,
+                            cudaStream_t st);
+
+// Workspaces scale with nq * n_probes (grouped query operand: up to ~2x that many rows of the
+// index dimension), so very large batches run as consecutive sub-batches.
+constexpr int64_t kMaxItemsPerBatch = 4 << 20;
+
 int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
                const b2vs_search_params& sp, float* out_d, int64_t* out_i, cudaStream_t st) {
   IvfData* d = static_cast<IvfData*>(index->ivf);
   B2VS_CHECK(d != nullptr, B2VS_EINVAL, "IVF index has no list data");
+  int n_probes = sp.n_probes > 0 ? sp.n_probes : 20;
+  n_probes = std::max(1, std::min(n_probes, std::min(d->n_lists, kMaxFusedK)));
+  const int chunk = static_cast<int>(std::max<int64_t>(1024, kMaxItemsPerBatch / n_probes));
+  if (nq <= chunk) return ivf_search_batch(index, q, q_dtype, nq, k, sp, out_d, out_i, st);
+  const size_t q_pitch = static_cast<size_t>(index->dim) * elem_bytes(q_dtype);
+  int launches = 0;
+  for (int q0 = 0; q0 < nq; q0 += chunk) {
+    const int nc = std::min(chunk, nq - q0);
+    B2VS_TRY(ivf_search_batch(index, static_cast<const char*>(q) + static_cast<size_t>(q0) * q_pitch,
+                              q_dtype, nc, k, sp, out_d + static_cast<size_t>(q0) * k,
+                              out_i + static_cast<size_t>(q0) * k, st));
+    launches += d->stats.launches;
+  }
+  d->stats.launches = launches;   // the other fields describe the last sub-batch
+  return B2VS_OK;
+}
+
+static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
+                            const b2vs_search_params& sp, float* out_d, int64_t* out_i,
+                            cudaStream_t st) {
+  IvfData* d = static_cast<IvfData*>(index->ivf);
   B2VS_CHECK(k >= 1 && k <= kMaxFusedK, B2VS_EUNSUP, "k=%d outside [1, %d]", k, kMaxFusedK);
   int n_probes = sp.n_probes > 0 ? sp.n_probes : 20;  // cuVS SearchParams default
   n_probes = std::min(n_probes, std::min(d->n_lists, kMaxFusedK));

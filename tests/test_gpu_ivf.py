@@ -255,3 +255,18 @@ def test_ivf_pq_grouped_scan_equals_lut_scan(b2, monkeypatch, metric, d, m):
     (dr0, ir0), (dr1, ir1) = out["0r"], out["1r"]
     assert abs(recall(ir1.cpu() - 7, ti) - recall(ir0.cpu() - 7, ti)) < 0.01
     assert (ir1 == ir0).float().mean().item() > 0.97
+
+
+def test_ivf_search_runs_huge_batches_in_sub_batches(b2):
+    """nq * n_probes beyond the workspace budget is processed as consecutive sub-batches."""
+    from oracle.ivf import recall
+    x = clustered(20000, 32, 50, 61).to(torch.bfloat16).cuda()
+    ix = b2.NativeIndex.ivf_flat(x, 128, metric="sqeuclidean", kmeans_iters=5)
+    nq = 40000                                   # 128 probes -> sub-batches of 32768 queries
+    q = x[torch.arange(nq, device="cuda") % x.shape[0]].clone()
+    dd, ii = ix.search(q, 3, n_probes=128)
+    flat = b2.NativeIndex.flat(x, metric="sqeuclidean")
+    fd, fi = flat.search(q, 3)
+    assert recall(ii.cpu(), fi.cpu()) > 0.999
+    assert torch.allclose(dd, fd, rtol=1e-3, atol=1e-2)
+    assert float(dd[:, 0].max()) < 1e-2          # every query is a database row
