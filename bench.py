@@ -239,13 +239,26 @@ def main():
         g_d = torch.empty((world, args.queries, args.k), dtype=torch.float32, device=dev)
         g_i = torch.empty((world, args.queries, args.k), dtype=torch.int64, device=dev)
 
-    def step_device(time_kernel=False):
+    phase_ev = []   # (start, after search, after all-gather, after merge) event tuples, N > 1
+
+    def step_device(time_kernel=False, phases=False):
         """One batch with inputs resident in HBM: local search -> all-gather -> merge."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if phases and world > 1 else None
+        if ev:
+            ev[0].record()
         index.search(q_dev, args.k, out=(out_d, out_i), time_kernel=time_kernel)
         if world > 1:
+            if ev:
+                ev[1].record()
             dist.all_gather_into_tensor(g_d, out_d)
             dist.all_gather_into_tensor(g_i, out_i)
-            return b2.merge_topk(g_d, g_i, args.k, descending=False)
+            if ev:
+                ev[2].record()
+            res = b2.merge_topk(g_d, g_i, args.k, descending=False)
+            if ev:
+                ev[3].record()
+                phase_ev.append(ev)
+            return res
         return out_d, out_i
 
     def sync_all():
@@ -268,7 +281,7 @@ def main():
     sync_all()
     e0.record()
     for _ in range(args.steps):
-        step_device(time_kernel=True)
+        step_device(time_kernel=True, phases=True)
         st = index.last_stats()   # resolves the event pair of this step's fused kernel
         kernel_ms.append(st.kernel_ms)
         launches += st.launches + (1 if world > 1 else 0)
@@ -364,6 +377,13 @@ def main():
             "clocks": clocks,
             "parity": parity,
         }
+        if phase_ev:
+            # rank 0's device time per phase (mean over the timed steps)
+            n = len(phase_ev)
+            line["phases_ms"] = {
+                "search": sum(e[0].elapsed_time(e[1]) for e in phase_ev) / n,
+                "all_gather": sum(e[1].elapsed_time(e[2]) for e in phase_ev) / n,
+                "merge": sum(e[2].elapsed_time(e[3]) for e in phase_ev) / n}
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             rows = min(args.cpu_sample_rows, args.n_db)
