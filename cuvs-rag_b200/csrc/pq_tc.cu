@@ -7,7 +7,16 @@
 namespace b2vs {
 
 bool pq_grouped_supported(int dim, int dsub) {
-  return (dsub == 2 || dsub == 4) && dim % kBK == 0 && dim * 512 <= kPqTcMaxCbBytes;
+  return (dsub == 2 || dsub == 4 || dsub == 8) && dim % kBK == 0 && dim <= 4096;
+}
+
+template <int DSUB, bool kCbSmem>
+static int launch_one(int grid, const CUtensorMap& tm_q, const PqTcParams& pp, cudaStream_t st) {
+  B2VS_CUDA(cudaFuncSetAttribute((pq_tc_kernel<DSUB, kCbSmem>),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kPqTcSmemBytes));
+  pq_tc_kernel<DSUB, kCbSmem><<<grid, kPqTcThreads, kPqTcSmemBytes, st>>>(tm_q, pp);
+  B2VS_CUDA(cudaGetLastError());
+  return B2VS_OK;
 }
 
 int launch_pq_grouped_scan(int dev, const PqGroupedScanArgs& a, cudaStream_t st) {
@@ -35,17 +44,10 @@ int launch_pq_grouped_scan(int dev, const PqGroupedScanArgs& a, cudaStream_t st)
   pp.n_groups = a.n_groups;
   pp.cb_words = a.pq_dim * 256 * a.dsub / 2;
   const int grid = std::max(1, std::min(a.max_work, sm_count(dev)));
-  if (a.dsub == 2) {
-    B2VS_CUDA(cudaFuncSetAttribute(pq_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kPqTcSmemBytes));
-    pq_tc_kernel<2><<<grid, kPqTcThreads, kPqTcSmemBytes, st>>>(tm_q, pp);
-  } else {
-    B2VS_CUDA(cudaFuncSetAttribute(pq_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kPqTcSmemBytes));
-    pq_tc_kernel<4><<<grid, kPqTcThreads, kPqTcSmemBytes, st>>>(tm_q, pp);
-  }
-  B2VS_CUDA(cudaGetLastError());
-  return B2VS_OK;
+  const bool cb_smem = pp.cb_words * 4 <= kPqTcMaxCbBytes;
+  if (a.dsub == 2) return cb_smem ? launch_one<2, true>(grid, tm_q, pp, st) : launch_one<2, false>(grid, tm_q, pp, st);
+  if (a.dsub == 4) return cb_smem ? launch_one<4, true>(grid, tm_q, pp, st) : launch_one<4, false>(grid, tm_q, pp, st);
+  return cb_smem ? launch_one<8, true>(grid, tm_q, pp, st) : launch_one<8, false>(grid, tm_q, pp, st);
 }
 
 }  // namespace b2vs

@@ -16,7 +16,8 @@
 // k-blocks + the tile's ||r^||^2 vector), warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4-7 = epilogue, warps 8-11 = decoders.  A smem stage = 16 KB query k-block (TMA) + 32 KB
 // decoded list k-block (256 rows x 64 dims); its "full" barrier takes the TMA transaction plus
-// one arrival per decoder warp.  The bf16 codebooks (<= 64 KB) stay resident in shared memory.
+// one arrival per decoder warp.  bf16 codebooks of at most 64 KB stay resident in shared memory;
+// larger ones (e.g. 768-d) are looked up in global memory, i.e. L2.
 #pragma once
 #include "bf_tc.cuh"
 
@@ -40,10 +41,13 @@ struct PqTcParams {
   int cb_words;             // pq_dim * 256 * DSUB / 2
 };
 
-template <int DSUB>   // sub-vector length: 2 or 4 (a code decodes to 4 or 8 bytes of bf16)
+// DSUB = sub-vector length (2, 4 or 8: a code decodes to 4, 8 or 16 bytes of bf16).
+// kCbSmem: the bf16 codebooks (dim * 512 bytes) fit in 64 KB and stay resident in shared memory;
+// otherwise (e.g. 768-d) the decoders look entries up in global memory, where L2 holds them.
+template <int DSUB, bool kCbSmem>
 __global__ void __launch_bounds__(kPqTcThreads, 1)
 pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
-  static_assert(DSUB == 2 || DSUB == 4, "DSUB");
+  static_assert(DSUB == 2 || DSUB == 4 || DSUB == 8, "DSUB");
   const BfTcParams& p = pp.tc;
   constexpr int kStages = kPqTcStages;
   constexpr int kStageBytes = kPqTcStageBytes;
@@ -90,7 +94,9 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < pp.cb_words; i += kPqTcThreads) cb_s[i] = __ldg(pp.cb16 + i);
+  if (kCbSmem)
+    for (int i = threadIdx.x; i < pp.cb_words; i += kPqTcThreads) cb_s[i] = __ldg(pp.cb16 + i);
+  const uint32_t* cb_w = kCbSmem ? cb_s : pp.cb16;   // codebook words the decoders read
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -158,7 +164,9 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
     // -> 16 codebook look-ups -> 16 * DSUB bf16 values = (DSUB * 2) 16-byte stores into the
     // row's 128-byte swizzled line: chunk c of row r lives at (r/8)*1024 + (r%8)*128 + ((c^(r%8))*16).
     const int dw = warp - 8;
-    constexpr int kChunksPerKb = (kBK / DSUB) / 16 > 0 ? (kBK / DSUB) / 16 : 1;  // code chunks per k-block: 2 | 1
+    // code chunks per k-block: 2 (DSUB 2) | 1 (DSUB 4) | half a chunk (DSUB 8: k-block kb uses
+    // bytes [8*(kb&1), +8) of chunk kb/2)
+    constexpr int kChunksPerKb = (DSUB == 2) ? 2 : 1;
     constexpr int kPairs = 8 * kChunksPerKb;                                     // (group, chunk) pairs per stage
     uint32_t stage = 0, phase = 0;
     for (int item = unit; item < n_items; item += n_units) {
@@ -173,7 +181,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
           for (int u = 0; u < kPairs / 4; ++u) {
             const int pi = dw * (kPairs / 4) + u;
             const uint32_t g = g_tile0 + static_cast<uint32_t>(pi / kChunksPerKb);
-            const int ch = kb * kChunksPerKb + (pi % kChunksPerKb);
+            const int ch = (DSUB == 8) ? (kb >> 1) : kb * kChunksPerKb + (pi % kChunksPerKb);
             cv[u] = make_uint4(0, 0, 0, 0);
             if (g < pp.n_groups)
               cv[u] = __ldg(pp.codes4 + (static_cast<size_t>(g) * pp.n_code_chunks + ch) * 32 + lane);
@@ -185,7 +193,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
             const int pi = dw * (kPairs / 4) + u;
             const int gl = pi / kChunksPerKb;
             const int chl = pi % kChunksPerKb;                  // chunk within the k-block
-            const int ch = kb * kChunksPerKb + chl;
+            const int ch = (DSUB == 8) ? (kb >> 1) : kb * kChunksPerKb + chl;
             const uint32_t r = static_cast<uint32_t>(gl) * 32u + lane;
             const uint32_t line = b_base + (r >> 3) * 1024u + (r & 7u) * 128u;
             const uint32_t wv[4] = {cv[u].x, cv[u].y, cv[u].z, cv[u].w};
@@ -197,15 +205,31 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                   const int m = ch * 16 + oc * 4 + b;
-                  o[b] = cb_s[m * 256 + ((wv[oc] >> (8 * b)) & 0xFFu)];
+                  o[b] = cb_w[m * 256 + ((wv[oc] >> (8 * b)) & 0xFFu)];
                 }
                 const uint32_t c = static_cast<uint32_t>(chl * 4 + oc);
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(line + ((c ^ (r & 7u)) << 4)),
                              "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
               }
+            } else if (DSUB == 8) {
+              // this k-block's 8 codes (half of the chunk) -> 64 dims -> the row's 8 output chunks
+              const uint4* cb4 = reinterpret_cast<const uint4*>(cb_w);
+              const int h = kb & 1;
+              uint4 e[8];
+#pragma unroll
+              for (int oc = 0; oc < 8; ++oc) {
+                const int m = ch * 16 + h * 8 + oc;
+                e[oc] = cb4[m * 256 + ((wv[2 * h + (oc >> 2)] >> (8 * (oc & 3))) & 0xFFu)];
+              }
+#pragma unroll
+              for (int oc = 0; oc < 8; ++oc) {
+                const uint32_t c = static_cast<uint32_t>(oc);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(line + ((c ^ (r & 7u)) << 4)),
+                             "r"(e[oc].x), "r"(e[oc].y), "r"(e[oc].z), "r"(e[oc].w) : "memory");
+              }
             } else {
               // 16 codes -> 64 dims -> the row's 8 output chunks
-              const uint2* cb2 = reinterpret_cast<const uint2*>(cb_s);
+              const uint2* cb2 = reinterpret_cast<const uint2*>(cb_w);
 #pragma unroll
               for (int oc = 0; oc < 8; ++oc) {
                 const int i0 = oc * 2;

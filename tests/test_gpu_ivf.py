@@ -221,7 +221,10 @@ def test_ivf_flat_grouped_scan_ragged_batch(b2, monkeypatch):
 
 
 @pytest.mark.parametrize("metric,d,m", [("sqeuclidean", 128, 64), ("inner_product", 128, 64),
-                                         ("sqeuclidean", 64, 16)])
+                                         ("sqeuclidean", 64, 16),      # dsub 4, codebooks in smem
+                                         ("sqeuclidean", 128, 16),     # dsub 8, codebooks in smem
+                                         ("sqeuclidean", 256, 32),     # dsub 8, codebooks via L2
+                                         ("inner_product", 256, 128)]) # dsub 2, codebooks via L2
 def test_ivf_pq_grouped_scan_equals_lut_scan(b2, monkeypatch, metric, d, m):
     """Large batches decode each probed list once into bf16 tiles for the tensor cores.  Its ADC
     scores use bf16-rounded residual queries / codebooks, so against the fp32 look-up-table scan
