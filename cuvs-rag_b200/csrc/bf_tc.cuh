@@ -86,6 +86,7 @@ struct BfTcParams {
                         // x_kblocks db k-blocks (fp32 queries split into two bf16 halves)
 };
 
+constexpr bool kWorkNoHint = false;   // A/B switch for the evict-first hint of work-mode list tiles
 constexpr int kModeBuffer = 0;   // per-(CTA,row) candidate buffer + warp compaction (k <= 128)
 constexpr int kModeArgmin = 1;   // k == 1: running arg-min in a register
 constexpr int kModeAppend = 2;   // large k: atomic append to the query's global buffer
@@ -278,7 +279,12 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
               ptx::tma_load_2d_hint(a_dst, &tm_q, bar_full + 8 * stage, kb * kBK, q_row0,
                                     ptx::kEvictLast);
               const int xkb = (kWork && p.x_kblocks > 0 && kb >= p.x_kblocks) ? kb - p.x_kblocks : kb;
-              ptx::tma_load_2d(a_dst + Cfg::kABytes, &tm_x, bar_full + 8 * stage, xkb * kBK, x_row0);
+              // work mode streams every list once: keep it from evicting the query blocks in L2
+              if (kWork && !kWorkNoHint)
+                ptx::tma_load_2d_hint(a_dst + Cfg::kABytes, &tm_x, bar_full + 8 * stage, xkb * kBK,
+                                      x_row0, ptx::kEvictFirst);
+              else
+                ptx::tma_load_2d(a_dst + Cfg::kABytes, &tm_x, bar_full + 8 * stage, xkb * kBK, x_row0);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
