@@ -28,6 +28,7 @@ constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kListE = 4;  // warp-resident sorted list: 32 * 4 = 128 keys
 constexpr int kGroupRows = 128;  // query rows per grouped-scan work item (= the UMMA M extent)
+constexpr int kMaxProbes = 2048;  // coarse probe = exact top-n_probes (large-k path above 128)
 constexpr int kNormSlack = 256;  // slot_norm floats past the last slot (whole-tile beta loads)
 
 struct IvfData {
@@ -1485,7 +1486,7 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
   IvfData* d = static_cast<IvfData*>(index->ivf);
   B2VS_CHECK(d != nullptr, B2VS_EINVAL, "IVF index has no list data");
   int n_probes = sp.n_probes > 0 ? sp.n_probes : 20;
-  n_probes = std::max(1, std::min(n_probes, std::min(d->n_lists, kMaxFusedK)));
+  n_probes = std::max(1, std::min(n_probes, std::min(d->n_lists, kMaxProbes)));
   const int chunk = static_cast<int>(std::max<int64_t>(1024, kMaxItemsPerBatch / n_probes));
   if (nq <= chunk) return ivf_search_batch(index, q, q_dtype, nq, k, sp, out_d, out_i, st);
   const size_t q_pitch = static_cast<size_t>(index->dim) * elem_bytes(q_dtype);
@@ -1507,7 +1508,7 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
   IvfData* d = static_cast<IvfData*>(index->ivf);
   B2VS_CHECK(k >= 1 && k <= kMaxFusedK, B2VS_EUNSUP, "k=%d outside [1, %d]", k, kMaxFusedK);
   int n_probes = sp.n_probes > 0 ? sp.n_probes : 20;  // cuVS SearchParams default
-  n_probes = std::min(n_probes, std::min(d->n_lists, kMaxFusedK));
+  n_probes = std::min(n_probes, std::min(d->n_lists, kMaxProbes));
   // IVF-PQ refine: scan for k' = refine_ratio * k ADC candidates, then re-rank them exactly
   const bool refine = index->kind == B2VS_KIND_IVF_PQ && sp.refine_ratio > 1 && d->src_rows != nullptr;
   const int k_final = k;
@@ -1681,7 +1682,7 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
   } else {
     const size_t cb_floats = static_cast<size_t>(d->pq_dim) * 256 * d->dsub;
     const size_t smem_p = (cb_floats + static_cast<size_t>(d->mp) * 256 + 2 * index->dim) * sizeof(float);
-    if (smem_p + 20 * 1024 <= 227 * 1024) {
+    if (smem_p + 20 * 1024 <= 227 * 1024 && n_probes <= kMaxFusedK) {
       // codebooks fit next to the LUT: query-major persistent CTAs, one per SM
       const int grid = std::min(nq, sm_count(index->dev));
 #define PQ_QUERY_LAUNCH(NCH, DSUB)                                                                      \

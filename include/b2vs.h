@@ -66,7 +66,8 @@ typedef struct b2vs_ivf_params {
 } b2vs_ivf_params;
 
 typedef struct b2vs_search_params {
-  int32_t n_probes;       /* IVF: lists scanned per query (cuVS SearchParams.n_probes, default 20) */
+  int32_t n_probes;       /* IVF: lists scanned per query (cuVS SearchParams.n_probes, default 20);
+                             clamped to min(n_lists, 2048) */
   int32_t refine_ratio;   /* IVF-PQ: exact re-rank of min(128, refine_ratio*k) ADC candidates (0/1 = off) */
   int32_t n_splits;       /* flat: force the number of db splits (0 = heuristic) */
   int32_t flags;          /* bit 0: time the dominant kernel with CUDA events (see stats.kernel_ms) */

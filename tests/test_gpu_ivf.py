@@ -273,3 +273,23 @@ def test_ivf_search_runs_huge_batches_in_sub_batches(b2):
     assert recall(ii.cpu(), fi.cpu()) > 0.999
     assert torch.allclose(dd, fd, rtol=1e-3, atol=1e-2)
     assert float(dd[:, 0].max()) < 1e-2          # every query is a database row
+
+
+@pytest.mark.parametrize("nq", [40, 300])
+def test_ivf_more_than_128_probes(b2, nq):
+    """n_probes above the fused top-k limit (128) goes through the large-k coarse probe; probing
+    every one of 256 lists must reproduce the exact search (both scan paths, Flat and PQ run)."""
+    from oracle.ivf import recall
+    x = clustered(30000, 64, 70, 71).to(torch.float16).cuda()
+    q = queries_from(x.float().cpu(), nq, 72).to(torch.float16).cuda()
+    flat = b2.NativeIndex.flat(x, metric="sqeuclidean")
+    fd, fi = flat.search(q, 10)
+    ix = b2.NativeIndex.ivf_flat(x, 256, metric="sqeuclidean", kmeans_iters=6)
+    dd, ii = ix.search(q, 10, n_probes=256)
+    assert recall(ii.cpu(), fi.cpu()) > 0.999
+    assert torch.allclose(dd, fd, rtol=1e-3, atol=1e-2)
+    d2, i2 = ix.search(q, 10, n_probes=200)
+    assert recall(i2.cpu(), fi.cpu()) > 0.99
+    pq = b2.NativeIndex.ivf_pq(x, 256, 32, metric="sqeuclidean", kmeans_iters=6)
+    _, ip = pq.search(q, 10, n_probes=256, refine_ratio=8)
+    assert recall(ip.cpu(), fi.cpu()) > 0.9
