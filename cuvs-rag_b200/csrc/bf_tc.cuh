@@ -239,7 +239,8 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // Whole warp walks the loops and waits; one elected lane issues the copies.
+    {
       uint32_t stage = 0, phase = 0, tcount = 0;
       const uint32_t full_leader = (G == 2) ? ptx::mapa_cluster(bar_full, 0) : bar_full;
       const int n_items = kWork ? *p.n_work : p.n_items;
@@ -261,31 +262,37 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
           const int x_row0 = kWork ? row_begin + ti * kBN
                                    : t * kBN + static_cast<int>(cta_rank) * Cfg::kBRows;
           ptx::mbar_wait(bar_norm_empty + 8 * as, aph ^ 1u);
-          ptx::mbar_arrive_expect_tx(bar_norm_full + 8 * as, kNormBytes);
-          ptx::bulk_load_1d(norm_base + as * kNormBytes,
-                            p.beta + (kWork ? static_cast<size_t>(x_row0) : static_cast<size_t>(t) * kBN),
-                            kNormBytes, bar_norm_full + 8 * as);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar_norm_full + 8 * as, kNormBytes);
+            ptx::bulk_load_1d(norm_base + as * kNormBytes,
+                              p.beta + (kWork ? static_cast<size_t>(x_row0) : static_cast<size_t>(t) * kBN),
+                              kNormBytes, bar_norm_full + 8 * as);
+          }
+          __syncwarp();
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
             const uint32_t a_dst = smem_base + stage * kStageBytes;
-            if (G == 2) {
-              const uint32_t fb = full_leader + 8 * stage;
-              ptx::mbar_arrive_expect_tx_cluster(fb, kStageBytes);
-              ptx::tma_load_2d_2sm_hint(a_dst, &tm_q, fb, kb * kBK, q_row0, ptx::kEvictLast);
-              ptx::tma_load_2d_2sm(a_dst + Cfg::kABytes, &tm_x, fb, kb * kBK, x_row0);
-            } else {
-              ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
-              // the query block is re-read for every db tile: ask L2 to keep it (evict-last)
-              ptx::tma_load_2d_hint(a_dst, &tm_q, bar_full + 8 * stage, kb * kBK, q_row0,
-                                    ptx::kEvictLast);
-              const int xkb = (kWork && p.x_kblocks > 0 && kb >= p.x_kblocks) ? kb - p.x_kblocks : kb;
-              // work mode streams every list once: keep it from evicting the query blocks in L2
-              if (kWork && !kWorkNoHint)
-                ptx::tma_load_2d_hint(a_dst + Cfg::kABytes, &tm_x, bar_full + 8 * stage, xkb * kBK,
-                                      x_row0, ptx::kEvictFirst);
-              else
-                ptx::tma_load_2d(a_dst + Cfg::kABytes, &tm_x, bar_full + 8 * stage, xkb * kBK, x_row0);
+            if (ptx::elect_one()) {
+              if (G == 2) {
+                const uint32_t fb = full_leader + 8 * stage;
+                ptx::mbar_arrive_expect_tx_cluster(fb, kStageBytes);
+                ptx::tma_load_2d_2sm_hint(a_dst, &tm_q, fb, kb * kBK, q_row0, ptx::kEvictLast);
+                ptx::tma_load_2d_2sm(a_dst + Cfg::kABytes, &tm_x, fb, kb * kBK, x_row0);
+              } else {
+                ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
+                // the query block is re-read for every db tile: ask L2 to keep it (evict-last)
+                ptx::tma_load_2d_hint(a_dst, &tm_q, bar_full + 8 * stage, kb * kBK, q_row0,
+                                      ptx::kEvictLast);
+                const int xkb = (kWork && p.x_kblocks > 0 && kb >= p.x_kblocks) ? kb - p.x_kblocks : kb;
+                // work mode streams every list once: keep it from evicting the query blocks in L2
+                if (kWork && !kWorkNoHint)
+                  ptx::tma_load_2d_hint(a_dst + Cfg::kABytes, &tm_x, bar_full + 8 * stage, xkb * kBK,
+                                        x_row0, ptx::kEvictFirst);
+                else
+                  ptx::tma_load_2d(a_dst + Cfg::kABytes, &tm_x, bar_full + 8 * stage, xkb * kBK, x_row0);
+              }
             }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -293,7 +300,8 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA)
-    if (lane == 0 && cta_rank == 0) {
+    // The whole warp walks the loops and waits on the barriers; one elected lane issues.
+    if (cta_rank == 0) {
       uint32_t stage = 0, phase = 0, tcount = 0;
       const int n_items = kWork ? *p.n_work : p.n_items;
       for (int item = unit; item < n_items; item += n_units) {
@@ -315,21 +323,28 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             ptx::tc_fence_after();
             const uint32_t a_addr = smem_base + stage * kStageBytes;
             const uint32_t b_addr = a_addr + Cfg::kABytes;
+            // descriptors of the stage's first 16-wide K slice; +32 bytes per slice = +2 in the
+            // (address >> 4) field (smem addresses stay below 2^18, no carry out of the field)
+            const uint64_t adesc0 = ptx::make_kmajor_desc<kBK * 2>(a_addr);
+            const uint64_t bdesc0 = ptx::make_kmajor_desc<kBK * 2>(b_addr);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < kBK / 16; ++kk) {
-              const uint64_t adesc = ptx::make_kmajor_desc<kBK * 2>(a_addr + kk * 32);
-              const uint64_t bdesc = ptx::make_kmajor_desc<kBK * 2>(b_addr + kk * 32);
-              if (G == 2) ptx::umma_f16_2sm(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
-              else ptx::umma_f16(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < kBK / 16; ++kk) {
+                if (G == 2) ptx::umma_f16_2sm(d_tmem, adesc0 + 2u * kk, bdesc0 + 2u * kk, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+                else ptx::umma_f16(d_tmem, adesc0 + 2u * kk, bdesc0 + 2u * kk, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+              }
+              // smem slot reusable (in both CTAs) once these MMAs retire
+              if (G == 2) ptx::umma_commit_2sm(bar_empty + 8 * stage, 0x3);
+              else ptx::umma_commit(bar_empty + 8 * stage);
+              // last k-block: accumulator ready for the epilogue warps (of both CTAs)
+              if (kb + 1 == p.k_blocks) {
+                if (G == 2) ptx::umma_commit_2sm(bar_acc_full + 8 * as, 0x3);
+                else ptx::umma_commit(bar_acc_full + 8 * as);
+              }
             }
-            // smem slot reusable (in both CTAs) once these MMAs retire
-            if (G == 2) ptx::umma_commit_2sm(bar_empty + 8 * stage, 0x3);
-            else ptx::umma_commit(bar_empty + 8 * stage);
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          // accumulator ready for the epilogue warps (of both CTAs)
-          if (G == 2) ptx::umma_commit_2sm(bar_acc_full + 8 * as, 0x3);
-          else ptx::umma_commit(bar_acc_full + 8 * as);
         }
       }
     }

@@ -105,7 +105,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0, tcount = 0;
       for (int item = unit; item < n_items; item += n_units) {
         const int4 w = __ldg(p.work + item);
@@ -114,14 +114,20 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
         for (int ti = 0; ti < t1; ++ti, ++tcount) {
           const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
           ptx::mbar_wait(bar_norm_empty + 8 * as, aph ^ 1u);
-          ptx::mbar_arrive_expect_tx(bar_norm_full + 8 * as, kNormBytes);
-          ptx::bulk_load_1d(norm_base + as * kNormBytes, p.beta + static_cast<size_t>(w.y + ti * kBN),
-                            kNormBytes, bar_norm_full + 8 * as);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(bar_norm_full + 8 * as, kNormBytes);
+            ptx::bulk_load_1d(norm_base + as * kNormBytes, p.beta + static_cast<size_t>(w.y + ti * kBN),
+                              kNormBytes, bar_norm_full + 8 * as);
+          }
+          __syncwarp();
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-            ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kABytes);
-            ptx::tma_load_2d_hint(smem_base + stage * kStageBytes, &tm_q, bar_full + 8 * stage,
-                                  kb * kBK, q_row0, ptx::kEvictLast);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kABytes);
+              ptx::tma_load_2d_hint(smem_base + stage * kStageBytes, &tm_q, bar_full + 8 * stage,
+                                    kb * kBK, q_row0, ptx::kEvictLast);
+            }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -129,7 +135,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0, tcount = 0;
       for (int item = unit; item < n_items; item += n_units) {
         const int4 w = __ldg(p.work + item);
@@ -143,17 +149,18 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
             ptx::mbar_wait(bar_full + 8 * stage, phase);
             ptx::tc_fence_after();
             const uint32_t a_addr = smem_base + stage * kStageBytes;
-            const uint32_t b_addr = a_addr + kABytes;
+            const uint64_t adesc0 = ptx::make_kmajor_desc<kBK * 2>(a_addr);
+            const uint64_t bdesc0 = ptx::make_kmajor_desc<kBK * 2>(a_addr + kABytes);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < kBK / 16; ++kk) {
-              const uint64_t adesc = ptx::make_kmajor_desc<kBK * 2>(a_addr + kk * 32);
-              const uint64_t bdesc = ptx::make_kmajor_desc<kBK * 2>(b_addr + kk * 32);
-              ptx::umma_f16(d_tmem, adesc, bdesc, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+              for (int kk = 0; kk < kBK / 16; ++kk)
+                ptx::umma_f16(d_tmem, adesc0 + 2u * kk, bdesc0 + 2u * kk, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+              ptx::umma_commit(bar_empty + 8 * stage);
+              if (kb + 1 == p.k_blocks) ptx::umma_commit(bar_acc_full + 8 * as);
             }
-            ptx::umma_commit(bar_empty + 8 * stage);
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          ptx::umma_commit(bar_acc_full + 8 * as);
         }
       }
     }
