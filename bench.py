@@ -63,12 +63,12 @@ def load_peaks():
 
 def ncu_traffic(world, args):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/r1_c2_bf_tc_fullpass.csv); only valid for the exact configuration it was taken on."""
+    (profiles/r1_c2_bf_tc_fullpass_v2.csv); only valid for the exact configuration it was taken on."""
     if world != 1 or (args.n_db, args.dim, args.queries, args.k) != (N_DB, DIM, N_QUERIES, K):
         return None
     try:
         import csv
-        with open(os.path.join(ROOT, "profiles", "r1_c2_bf_tc_fullpass.csv")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_c2_bf_tc_fullpass_v2.csv")) as f:
             rows = list(csv.reader(f))
         h, units, v = rows[0], rows[1], rows[2]
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
