@@ -164,7 +164,7 @@ __device__ __forceinline__ void score_chunk(const uint32_t (&r)[32], const float
 // A chunk appends at most 32 keys per row: compact (warp-cooperatively) the rows that could
 // overflow on the next chunk, which also tightens their thresholds.
 __device__ __forceinline__ void compact_if_needed(int& cnt, float& tau, u64* cand_warp, int k, int lane) {
-  uint32_t need = __ballot_sync(0xffffffffu, cnt > kCap - 32);
+  uint32_t need = __ballot_sync(0xffffffffu, cnt > compact_trigger(k));
   while (need) {
     const int rr = __ffs(need) - 1;
     need &= need - 1;

@@ -118,32 +118,57 @@ __device__ __forceinline__ void warp_bitonic_merge(u64 (&key)[E], int lane) {
 // Warp-cooperative compaction of one row buffer: sort the first n keys, write the best
 // min(n, k) back in ascending order (to `dst`, which may be the buffer itself) and return the
 // new threshold (+inf while fewer than k candidates exist); min(n, k) keys are kept.  All 32
-// lanes must call it.  Deliberately not inlined: one copy of the sort network keeps the fused
-// kernel's hot loop inside the instruction cache.
-static __device__ __noinline__ float compact_row(const u64* buf, u64* dst, int n, int k, int lane) {
-  u64 key[kSortE];
-  const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(buf + lane * kSortE);
+// lanes must call it.  The sort network is sized to n (64 / 128 / 256 keys): short buffers -
+// small k, whose buffers are compacted early, and most final flushes - cost a fraction of the
+// full network.  Deliberately not inlined: one copy of each network keeps the fused kernel's
+// hot loop inside the instruction cache.
+template <int E>
+__device__ __forceinline__ float compact_row_impl(const u64* buf, u64* dst, int n, int k, int lane) {
+  u64 key[E];
+  const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(buf + lane * E);
 #pragma unroll
-  for (int e = 0; e < kSortE; e += 2) {
-    const int idx = lane * kSortE + e;
+  for (int e = 0; e < E; e += 2) {
+    const int idx = lane * E + e;
     ulonglong2 v = make_ulonglong2(kKeyInf, kKeyInf);
     if (idx < n) v = __ldcg(b2 + e / 2);
     key[e] = v.x;
     key[e + 1] = (idx + 1 < n) ? v.y : kKeyInf;
   }
-  warp_bitonic_sort<kSortE>(key, lane);
+  warp_bitonic_sort<E>(key, lane);
   const int m = n < k ? n : k;
 #pragma unroll
-  for (int e = 0; e < kSortE; ++e) {
-    const int idx = lane * kSortE + e;
+  for (int e = 0; e < E; ++e) {
+    const int idx = lane * E + e;
     if (idx < m) __stcg(dst + idx, key[e]);
   }
   u64 kth = kKeyInf;
 #pragma unroll
-  for (int e = 0; e < kSortE; ++e)
-    if (lane * kSortE + e == k - 1) kth = key[e];
-  kth = shfl_u64(kth, (k - 1) / kSortE);
+  for (int e = 0; e < E; ++e)
+    if (lane * E + e == k - 1) kth = key[e];
+  kth = shfl_u64(kth, (k - 1) / E);
   return (n >= k) ? key_score(kth) : __int_as_float(0x7f800000);
+}
+static __device__ __noinline__ float compact_row_256(const u64* buf, u64* dst, int n, int k, int lane) {
+  return compact_row_impl<8>(buf, dst, n, k, lane);
+}
+static __device__ __noinline__ float compact_row_128(const u64* buf, u64* dst, int n, int k, int lane) {
+  return compact_row_impl<4>(buf, dst, n, k, lane);
+}
+static __device__ __noinline__ float compact_row_64(const u64* buf, u64* dst, int n, int k, int lane) {
+  return compact_row_impl<2>(buf, dst, n, k, lane);
+}
+// n and k are warp-uniform.  The chosen network must hold both the n keys and position k - 1.
+__device__ __forceinline__ float compact_row(const u64* buf, u64* dst, int n, int k, int lane) {
+  const int need = n > k ? n : k;
+  if (need <= 64) return compact_row_64(buf, dst, n, k, lane);
+  if (need <= 128) return compact_row_128(buf, dst, n, k, lane);
+  return compact_row_256(buf, dst, n, k, lane);
+}
+
+// Fill level at which a row buffer is compacted.  Small k compacts early: the threshold tightens
+// sooner (fewer candidates overall) and the sorts run on the 64- / 128-key networks.
+__host__ __device__ inline int compact_trigger(int k) {
+  return (k <= 16 ? 64 : (k <= 48 ? 128 : kCap)) - 32;
 }
 
 }  // namespace b2vs
