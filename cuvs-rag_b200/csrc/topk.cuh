@@ -57,16 +57,15 @@ __device__ __forceinline__ void warp_bitonic_sort(u64 (&key)[E], int lane) {
 #pragma unroll
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       if (stride >= E) {
+        // partner in another lane: keep own key iff (own < other) == (this position keeps the min)
         const int lm = stride / E;
         const bool lower = (lane & lm) == 0;
+        const bool up = size >= N ? true : (((lane * E) & size) == 0);   // size >= E here: lane-only
+        const bool keep_min = (lower == up);
 #pragma unroll
         for (int e = 0; e < E; ++e) {
           const u64 other = shfl_xor_u64(key[e], lm);
-          const bool up = (((lane * E + e) & size) == 0);
-          const bool keep_min = (lower == up);
-          const u64 mn = key[e] < other ? key[e] : other;
-          const u64 mx = key[e] < other ? other : key[e];
-          key[e] = keep_min ? mn : mx;
+          key[e] = ((key[e] < other) == keep_min) ? key[e] : other;
         }
       } else {
 #pragma unroll
@@ -74,10 +73,9 @@ __device__ __forceinline__ void warp_bitonic_sort(u64 (&key)[E], int lane) {
           if ((e & stride) == 0) {
             const bool up = (((lane * E + e) & size) == 0);
             const u64 a = key[e], b = key[e + stride];
-            const u64 mn = a < b ? a : b;
-            const u64 mx = a < b ? b : a;
-            key[e] = up ? mn : mx;
-            key[e + stride] = up ? mx : mn;
+            const bool swap = (a < b) != up;
+            key[e] = swap ? b : a;
+            key[e + stride] = swap ? a : b;
           }
         }
       }
@@ -98,17 +96,16 @@ __device__ __forceinline__ void warp_bitonic_merge(u64 (&key)[E], int lane) {
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const u64 other = shfl_xor_u64(key[e], lm);
-        const u64 mn = key[e] < other ? key[e] : other;
-        const u64 mx = key[e] < other ? other : key[e];
-        key[e] = lower ? mn : mx;
+        key[e] = ((key[e] < other) == lower) ? key[e] : other;
       }
     } else {
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         if ((e & stride) == 0) {
           const u64 a = key[e], b = key[e + stride];
-          key[e] = a < b ? a : b;
-          key[e + stride] = a < b ? b : a;
+          const bool swap = !(a < b);
+          key[e] = swap ? b : a;
+          key[e + stride] = swap ? a : b;
         }
       }
     }
