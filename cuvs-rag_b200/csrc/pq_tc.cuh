@@ -14,7 +14,7 @@
 //
 // Same skeleton as bf_tc_kernel<1, true> (work-table + append mode): warp 0 = TMA producer (query
 // k-blocks + the tile's ||r^||^2 vector), warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = epilogue, warps 8-11 = decoders.  A smem stage = 16 KB query k-block (TMA) + 32 KB
+// warps 4-7 and 12-15 = epilogue (column halves), warps 8-11 = decoders.  A smem stage = 16 KB query k-block (TMA) + 32 KB
 // decoded list k-block (256 rows x 64 dims); its "full" barrier takes the TMA transaction plus
 // one arrival per decoder warp.  bf16 codebooks of at most 64 KB stay resident in shared memory;
 // larger ones (e.g. 768-d) are looked up in global memory, i.e. L2.
@@ -23,7 +23,7 @@
 
 namespace b2vs {
 
-constexpr int kPqTcThreads = 384;
+constexpr int kPqTcThreads = 512;
 constexpr int kPqTcStages = 3;
 constexpr int kPqTcStageBytes = kBM * kBK * 2 + kBN * kBK * 2;   // 48 KB
 constexpr int kPqTcMaxCbBytes = 64 * 1024;
@@ -83,9 +83,9 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(bar_acc_full + 8 * i, 1);
-      ptx::mbar_init(bar_acc_empty + 8 * i, 4);
+      ptx::mbar_init(bar_acc_empty + 8 * i, 8);    // eight epilogue warps
       ptx::mbar_init(bar_norm_full + 8 * i, 1);
-      ptx::mbar_init(bar_norm_empty + 8 * i, 4);
+      ptx::mbar_init(bar_norm_empty + 8 * i, 8);
     }
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tm_q);
@@ -164,7 +164,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // ------------------------------------------------------------------ decoders
     // A stage's list k-block = 256 rows x 64 dims = 64 / DSUB codes per row.  Work unit of a lane:
     // one 16-byte code chunk of one row (coalesced across the warp by the interleaved layout)
@@ -259,7 +259,12 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (append mode)
-    const int ew = warp - 4;
+    // Eight warps: warps 4-7 take columns 0-127 of a tile, warps 12-15 columns 128-255 (warp w may
+    // only read TMEM lanes 32*(w%4)..+31, so both groups cover all four lane quarters).  With K as
+    // short as 128 the MMA of a tile is over in ~1 us and this loop sets the pace; append mode
+    // keeps no per-row state besides the threshold, so splitting a row's columns is free.
+    const int ew = warp & 3;
+    const int half = warp >= 12 ? 1 : 0;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
     const float inf = __int_as_float(0x7f800000);
     uint32_t tcount = 0;
@@ -285,32 +290,25 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
         const float4* nrm4 = reinterpret_cast<const float4*>(norm_ptr + as * kBN);
         const uint32_t col0 = static_cast<uint32_t>(row_begin + ti * kBN);
         const int nv = row_end - static_cast<int>(col0);
-        uint32_t ra[32], rb[32];
         const uint32_t tile_taddr = lane_taddr + as * kBN;
-        ptx::tmem_ld_32x32b_x32(tile_taddr, ra);
+        uint32_t ra[32];
 #pragma unroll 1
-        for (int c2 = 0; c2 < kBN / 64; ++c2) {
+        for (int c = 0; c < 4; ++c) {
+          const int col = half * (kBN / 2) + c * 32;
+          ptx::tmem_ld_32x32b_x32(tile_taddr + col, ra);
           ptx::tmem_ld_wait();
-          ptx::tmem_ld_32x32b_x32(tile_taddr + c2 * 64 + 32, rb);
-          if (c2 * 64 < nv)
-            score_chunk<kModeAppend>(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, cnt, best,
-                                     row_buf, row_cnt, p.big_cap, bias);
-          ptx::tmem_ld_wait();
-          if (c2 + 1 < kBN / 64) {
-            ptx::tmem_ld_32x32b_x32(tile_taddr + c2 * 64 + 64, ra);
-          } else {
+          if (c == 3) {
+            // this warp's last TMEM read of the tile has landed: hand the accumulator back
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar_acc_empty + 8 * as);
           }
-          if (c2 * 64 + 32 < nv)
-            score_chunk<kModeAppend>(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, cnt,
-                                     best, row_buf, row_cnt, p.big_cap, bias);
-          if (c2 + 1 == kBN / 64) {
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(bar_norm_empty + 8 * as);
-          }
+          if (col < nv)
+            score_chunk<kModeAppend>(ra, nrm4 + col / 4, p.alpha, col0 + col, tau, cnt, best, row_buf,
+                                     row_cnt, p.big_cap, bias);
         }
+        __syncwarp();   // all lanes are done with this tile's ||r^||^2 values
+        if (lane == 0) ptx::mbar_arrive(bar_norm_empty + 8 * as);
       }
     }
   }
