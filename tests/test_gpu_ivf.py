@@ -293,3 +293,25 @@ def test_ivf_more_than_128_probes(b2, nq):
     pq = b2.NativeIndex.ivf_pq(x, 256, 32, metric="sqeuclidean", kmeans_iters=6)
     _, ip = pq.search(q, 10, n_probes=256, refine_ratio=8)
     assert recall(ip.cpu(), fi.cpu()) > 0.9
+
+
+@pytest.mark.parametrize("kind", ["flat", "pq"])
+def test_ivf_grouped_scan_with_every_query_on_the_same_lists(b2, monkeypatch, kind):
+    """Worst-case skew: 700 near-identical queries probe the same few lists, so those lists get
+    several 128-row query blocks each and every other list none."""
+    x = clustered(30000, 64, 60, 81).to(torch.bfloat16)
+    q = (x[123].float()[None, :] + 0.01 * torch.randn(700, 64)).to(torch.bfloat16)
+    if kind == "flat":
+        ix = b2.NativeIndex.ivf_flat(x.cuda(), 64, metric="sqeuclidean", kmeans_iters=6)
+    else:
+        ix = b2.NativeIndex.ivf_pq(x.cuda(), 64, 32, metric="sqeuclidean", kmeans_iters=6)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B2VS_IVF_GROUPED", mode)
+        res[mode] = ix.search(q.cuda(), 10, n_probes=6)
+        torch.cuda.synchronize()
+    (d0, i0), (d1, i1) = res["0"], res["1"]
+    inter = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(i1.cpu(), i0.cpu()))
+    assert inter >= (0.999 if kind == "flat" else 0.93) * 700 * 10
+    assert bool((i1[:, 0] == 123).float().mean() > 0.95)          # the perturbed row itself
+    assert bool((d1[:, 1:] >= d1[:, :-1]).all())
