@@ -1552,8 +1552,9 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
     const uint32_t* offs = d->offsets.as<uint32_t>();
     const float* qf = d->ws_qf.as<float>();
     const int ov = grouped_override();
-    // grouped tensor-core scan once the batch averages a few queries per list
-    const bool grouped = ov >= 0 ? ov == 1 : (nq >= 64 && items >= 2 * d->n_lists);
+    // The grouped tensor-core scan is the default at every batch size (measured faster than the
+    // per-item scan from Q = 1 up); B2VS_IVF_GROUPED=0 selects the per-item kernels.
+    const bool grouped = ov >= 0 ? ov == 1 : true;
     // fp32-source indexes keep fp32 queries against their bf16 rows: the query operand is split
     // into bf16 [hi | lo] halves multiplied against the same list tiles (2x the MMA work)
     const int q_split = index->dtype == B2VS_F32 ? 1 : 0;
@@ -1617,9 +1618,7 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
       B2VS_CUDA(cudaGetLastError());
     }
     qnorm_for_merge = d->ws_qnorm.as<float>();
-  } else if (d->pq_tc_ready &&
-             (grouped_override() >= 0 ? grouped_override() == 1
-                                      : (nq >= 64 && items >= 2 * d->n_lists))) {
+  } else if (d->pq_tc_ready && grouped_override() != 0) {
     // Grouped tensor-core scan (pq_tc.cuh): same pipeline as the IVF-Flat one, the list tiles are
     // decoded from the PQ codes instead of loaded.
     const int l2 = index->metric == B2VS_METRIC_L2 ? 1 : 0;
