@@ -20,7 +20,8 @@ __global__ void __launch_bounds__(kBigThreads)
 bigk_select_kernel(const u64* __restrict__ cand, const int* __restrict__ counts, int cap, int k,
                    int final_pass, int metric, const float* __restrict__ qnorm, long long id_offset,
                    float* __restrict__ out_tau, float* __restrict__ out_d,
-                   long long* __restrict__ out_i, int* __restrict__ overflow) {
+                   long long* __restrict__ out_i, int* __restrict__ overflow,
+                   const uint32_t* __restrict__ remap) {
   __shared__ int hist[256];
   __shared__ u64 s_prefix;
   __shared__ int s_rank;
@@ -101,18 +102,20 @@ bigk_select_kernel(const u64* __restrict__ cand, const int* __restrict__ counts,
     } else {
       const float sc = key_score(key);
       out_d[o] = metric == B2VS_METRIC_L2 ? fmaxf(sc + qn, 0.f) : -sc;
-      out_i[o] = static_cast<long long>(key_id(key)) + id_offset;
+      const uint32_t id = key_id(key);
+      out_i[o] = static_cast<long long>(remap ? remap[id] : id) + id_offset;   // remap: list slot -> row
     }
   }
 }
 
 int launch_bigk_select(const u64* cand, const int* counts, int cap, int nq, int k, int final_pass,
                        int metric, const float* qnorm, int64_t id_offset, float* out_tau,
-                       float* out_d, int64_t* out_i, int* overflow, cudaStream_t st) {
+                       float* out_d, int64_t* out_i, int* overflow, cudaStream_t st,
+                       const uint32_t* remap) {
   B2VS_CHECK(k <= kBigSortMax, B2VS_EUNSUP, "k=%d exceeds the large-k limit %d", k, kBigSortMax);
   bigk_select_kernel<<<nq, kBigThreads, 0, st>>>(cand, counts, cap, k, final_pass, metric, qnorm,
                                                  id_offset, out_tau, out_d,
-                                                 reinterpret_cast<long long*>(out_i), overflow);
+                                                 reinterpret_cast<long long*>(out_i), overflow, remap);
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }

@@ -188,7 +188,8 @@ int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k,
 constexpr int kMaxBigK = 2048;
 int launch_bigk_select(const u64* cand, const int* counts, int cap, int nq, int k, int final_pass,
                        int metric, const float* qnorm, int64_t id_offset, float* out_tau,
-                       float* out_d, int64_t* out_i, int* overflow, cudaStream_t st);
+                       float* out_d, int64_t* out_i, int* overflow, cudaStream_t st,
+                       const uint32_t* remap = nullptr);
 int launch_merge_parts_big(const float* d_all, const int64_t* i_all, int n_parts, int nq, int k_in,
                            int k_out, int descending, float* out_d, int64_t* out_i, cudaStream_t st);
 

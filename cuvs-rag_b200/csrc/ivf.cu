@@ -1477,6 +1477,120 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
                             const b2vs_search_params& sp, float* out_d, int64_t* out_i,
                             cudaStream_t st);
 
+// Groups the nq * n_probes (query, probe) items by list and runs the tensor-core list scan in
+// append mode against the thresholds in ws_g_tau; candidates land in ws_g_cand / ws_g_cnt (the
+// caller sizes, zeroes and later selects from them).  probe_ids is [nq, n_probes] dense.
+static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long* probe_ids,
+                                 int n_probes, int nq, int cap, unsigned long long* counter,
+                                 cudaStream_t st) {
+  const int items = nq * n_probes;
+  const int q_split = index->dtype == B2VS_F32 ? 1 : 0;
+  const int q_pitch = q_split ? 2 * static_cast<int>(round_up(d->dp, 64)) : d->dp;
+  const int max_work = items / kGroupRows + std::min(d->n_lists, items) + 1;
+  const int64_t rows_cap = static_cast<int64_t>(sorted_rows_cap(d, items, kGroupRows));
+  B2VS_TRY(d->ws_g_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16));
+  B2VS_TRY(d->ws_g_q.reserve(static_cast<size_t>(rows_cap) * q_pitch * 2));
+  B2VS_TRY(d->ws_g_rowq.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
+  int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
+  B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, kGroupRows, st));
+  build_group_work_kernel<<<static_cast<unsigned>(ceil_div(d->n_lists, 256)), 256, 0, st>>>(
+      d->ws_item_off.as<uint32_t>(), d->offsets.as<uint32_t>(), d->ws_item_cnt.as<int>(),
+      d->list_of_rank.as<int>(), d->n_lists, d->ws_g_work.as<int4>(), n_work, counter);
+  gather_group_queries_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
+      d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists,
+      d->ws_qf.as<float>(), d->dp, n_probes, d->fmt, q_split, d->ws_g_q.as<uint16_t>(),
+      d->ws_g_rowq.as<int>());
+  B2VS_CUDA(cudaGetLastError());
+  GroupedScanArgs ga{};
+  ga.q_mat = d->ws_g_q.ptr; ga.q_rows = rows_cap;
+  ga.x_mat = d->data.ptr; ga.x_rows = d->n_slots;
+  ga.kdim = d->dp; ga.ab_format = d->fmt; ga.q_split = q_split;
+  ga.beta = d->slot_norm.as<float>();
+  ga.alpha = index->metric == B2VS_METRIC_L2 ? -2.f : -1.f;
+  ga.work = d->ws_g_work.ptr; ga.n_work = n_work; ga.max_work = max_work;
+  ga.row_query = d->ws_g_rowq.as<int>(); ga.tau = d->ws_g_tau.as<float>();
+  ga.cand = d->ws_g_cand.as<u64>(); ga.count = d->ws_g_cnt.as<int>(); ga.cap = cap;
+  return launch_grouped_scan(index->dev, ga, st);
+}
+
+// IVF-Flat with 128 < k <= 2048 (the reference's top-2000 retrieval mode on an IVF index,
+// improved_multi_gpu_rag.py:37-48 + :247).  Two grouped scans into 64 K-key per-query buffers:
+//   1. the m nearest lists of every query with no threshold (m lists hold ~3k rows) -> radix
+//      select of the k-th key = a valid threshold computed with the scan's own arithmetic;
+//   2. all n_probes lists below that threshold -> radix select + sort of the k best.
+static int ivf_flat_search_bigk(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
+                                const b2vs_search_params& sp, float* out_d, int64_t* out_i,
+                                cudaStream_t st) {
+  IvfData* d = static_cast<IvfData*>(index->ivf);
+  constexpr int kCapBig = 65536;
+  int n_probes = sp.n_probes > 0 ? sp.n_probes : 20;
+  n_probes = std::min(n_probes, std::min(d->n_lists, kMaxProbes));
+  int max_size = 1;
+  for (int v : d->h_sizes) max_size = std::max(max_size, static_cast<int>(round_up(v, 32)));
+  const double mean_size = std::max(1.0, static_cast<double>(d->n) / d->n_lists);
+  int m = std::min(n_probes, static_cast<int>(std::ceil(3.0 * k / mean_size)) + 1);
+  m = std::max(1, std::min(m, kCapBig / max_size));
+  B2VS_CHECK(max_size <= kCapBig, B2VS_EUNSUP, "a list of %d rows exceeds the large-k buffer", max_size);
+  const int q_pad = static_cast<int>(round_up(nq, 128));
+  B2VS_TRY(d->ws_probe_d.reserve(static_cast<size_t>(nq) * n_probes * sizeof(float)));
+  B2VS_TRY(d->ws_probe_i.reserve(static_cast<size_t>(nq) * n_probes * sizeof(int64_t)));
+  B2VS_TRY(d->ws_ref_i.reserve(static_cast<size_t>(nq) * m * sizeof(int64_t)));   // first m probes
+  B2VS_TRY(d->ws_qf.reserve(static_cast<size_t>(nq) * d->dp * sizeof(float)));
+  B2VS_TRY(d->ws_qnorm.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
+  B2VS_TRY(d->ws_counter.reserve(2 * sizeof(unsigned long long) + sizeof(int)));
+  B2VS_TRY(d->ws_g_tau.reserve(static_cast<size_t>(nq) * sizeof(float)));
+  B2VS_TRY(d->ws_g_cand.reserve(static_cast<size_t>(nq) * kCapBig * sizeof(u64)));
+  B2VS_TRY(d->ws_g_cnt.reserve(static_cast<size_t>(nq) * sizeof(int)));
+  B2VS_TRY(reserve_item_sort(d, nq * n_probes, kGroupRows));
+  B2VS_TRY(index->flat.search(q, q_dtype, nq, n_probes, 0, 0, d->ws_probe_d.as<float>(),
+                              d->ws_probe_i.as<int64_t>(), nullptr, st));
+  int launches = index->flat.stats.launches;
+  const int round16 = index->dtype != B2VS_F32 ? 1 : 0;
+  DISPATCH_DTYPE(q_dtype, T, (queries_to_f32_kernel<T><<<static_cast<unsigned>(ceil_div(nq, 4)), 128, 0, st>>>(
+                                 static_cast<const T*>(q), nq, index->dim, d->dp, d->fmt, round16,
+                                 d->ws_qf.as<float>(), d->ws_qnorm.as<float>())));
+  B2VS_CUDA(cudaGetLastError());
+  unsigned long long* counter = d->ws_counter.as<unsigned long long>();
+  int* overflow = reinterpret_cast<int*>(counter + 2);
+  B2VS_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned long long) + sizeof(int), st));
+  const long long* probe_ids = reinterpret_cast<const long long*>(d->ws_probe_i.ptr);
+  // ---- pass 1: nearest m lists, no threshold
+  B2VS_CUDA(cudaMemcpy2DAsync(d->ws_ref_i.ptr, static_cast<size_t>(m) * sizeof(int64_t), probe_ids,
+                              static_cast<size_t>(n_probes) * sizeof(int64_t),
+                              static_cast<size_t>(m) * sizeof(int64_t), nq, cudaMemcpyDeviceToDevice, st));
+  fill_f32_kernel<<<static_cast<unsigned>(ceil_div(nq, 256)), 256, 0, st>>>(d->ws_g_tau.as<float>(), nq, INFINITY);
+  B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
+  B2VS_TRY(run_grouped_flat_scan(index, d, reinterpret_cast<const long long*>(d->ws_ref_i.ptr), m, nq,
+                                 kCapBig, nullptr, st));
+  B2VS_TRY(launch_bigk_select(d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), kCapBig, nq, k, 0,
+                              index->metric, nullptr, 0, d->ws_g_tau.as<float>(), nullptr, nullptr,
+                              nullptr, st));
+  // ---- pass 2: every probed list below the threshold
+  B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
+  B2VS_TRY(run_grouped_flat_scan(index, d, probe_ids, n_probes, nq, kCapBig, counter, st));
+  B2VS_TRY(launch_bigk_select(d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), kCapBig, nq, k, 1,
+                              index->metric, d->ws_qnorm.as<float>(), index->id_offset, nullptr,
+                              out_d, out_i, overflow, st, d->row_ids.as<uint32_t>()));
+  int h_over = 0;
+  B2VS_CUDA(cudaMemcpyAsync(&h_over, overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B2VS_CUDA(cudaStreamSynchronize(st));
+  B2VS_CHECK(h_over <= kCapBig, B2VS_EUNSUP,
+             "large-k IVF search: %d candidates under the seed threshold exceed the %d-key buffer "
+             "(fewer than k rows in the nearest lists); use more lists per query or a flat index",
+             h_over, kCapBig);
+  launches += 22;
+  d->stats = b2vs_search_stats{};
+  d->stats.launches = launches;
+  d->stats.n_splits = n_probes;
+  d->stats.grid = nq * n_probes;
+  d->stats.algo_flops = 2.0 * nq * static_cast<double>(d->n_lists) * index->dim;
+  d->counter_pending = true;
+  d->last_nq = nq;
+  d->timing_pending = false;
+  return B2VS_OK;
+}
+
+
 // Workspaces scale with nq * n_probes (grouped query operand: up to ~2x that many rows of the
 // index dimension), so very large batches run as consecutive sub-batches.
 constexpr int64_t kMaxItemsPerBatch = 4 << 20;
@@ -1487,15 +1601,24 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
   B2VS_CHECK(d != nullptr, B2VS_EINVAL, "IVF index has no list data");
   int n_probes = sp.n_probes > 0 ? sp.n_probes : 20;
   n_probes = std::max(1, std::min(n_probes, std::min(d->n_lists, kMaxProbes)));
-  const int chunk = static_cast<int>(std::max<int64_t>(1024, kMaxItemsPerBatch / n_probes));
-  if (nq <= chunk) return ivf_search_batch(index, q, q_dtype, nq, k, sp, out_d, out_i, st);
+  int chunk = static_cast<int>(std::max<int64_t>(1024, kMaxItemsPerBatch / n_probes));
+  const bool bigk = k > kMaxFusedK;
+  if (bigk) {
+    B2VS_CHECK(index->kind == B2VS_KIND_IVF_FLAT && k <= kMaxBigK, B2VS_EUNSUP,
+               "k=%d: IVF-Flat serves k <= %d, IVF-PQ k <= %d", k, kMaxBigK, kMaxFusedK);
+    chunk = std::min(chunk, 4096);   // 64 K-key candidate buffer per query
+  }
+  auto run = [&](const void* qq, int n, float* od, int64_t* oi) {
+    return bigk ? ivf_flat_search_bigk(index, qq, q_dtype, n, k, sp, od, oi, st)
+                : ivf_search_batch(index, qq, q_dtype, n, k, sp, od, oi, st);
+  };
+  if (nq <= chunk) return run(q, nq, out_d, out_i);
   const size_t q_pitch = static_cast<size_t>(index->dim) * elem_bytes(q_dtype);
   int launches = 0;
   for (int q0 = 0; q0 < nq; q0 += chunk) {
     const int nc = std::min(chunk, nq - q0);
-    B2VS_TRY(ivf_search_batch(index, static_cast<const char*>(q) + static_cast<size_t>(q0) * q_pitch,
-                              q_dtype, nc, k, sp, out_d + static_cast<size_t>(q0) * k,
-                              out_i + static_cast<size_t>(q0) * k, st));
+    B2VS_TRY(run(static_cast<const char*>(q) + static_cast<size_t>(q0) * q_pitch, nc,
+                 out_d + static_cast<size_t>(q0) * k, out_i + static_cast<size_t>(q0) * k));
     launches += d->stats.launches;
   }
   d->stats.launches = launches;   // the other fields describe the last sub-batch
@@ -1558,48 +1681,24 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
     // fp32-source indexes keep fp32 queries against their bf16 rows: the query operand is split
     // into bf16 [hi | lo] halves multiplied against the same list tiles (2x the MMA work)
     const int q_split = index->dtype == B2VS_F32 ? 1 : 0;
-    const int q_pitch = q_split ? 2 * static_cast<int>(round_up(d->dp, 64)) : d->dp;
     if (grouped) {
       const int cap = grouped_cap(k);
       // seed thresholds first (queries ordered by their nearest list), then group all the items
       B2VS_TRY(reserve_item_sort(d, items, kGroupRows));  // both sorts share these buffers
       B2VS_TRY(sort_items_by_list(d, probe_ids, nq, n_probes, 1, st));
-      const int max_work = items / kGroupRows + std::min(d->n_lists, items) + 1;
-      const int64_t rows_cap = static_cast<int64_t>(items) + static_cast<int64_t>(kGroupRows) * std::min(d->n_lists, items);
-      B2VS_TRY(d->ws_g_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16));
-      B2VS_TRY(d->ws_g_q.reserve(static_cast<size_t>(rows_cap) * q_pitch * 2));
-      B2VS_TRY(d->ws_g_rowq.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
       B2VS_TRY(d->ws_g_tau.reserve(static_cast<size_t>(nq) * sizeof(float)));
       B2VS_TRY(d->ws_g_cand.reserve(static_cast<size_t>(nq) * cap * sizeof(u64)));
       B2VS_TRY(d->ws_g_cnt.reserve(static_cast<size_t>(nq) * sizeof(int)));
-      int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
       B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
       FLAT_SCAN_DISPATCH(ivf_seed_tau_kernel, d->fmt, j, nq, st, data, snorm, offs, probe_ids, qf, d->dp,
                          n_probes, k, alpha, grouped_seed_rows(k), d->max_norm2,
                          index->metric == B2VS_METRIC_L2 ? 1 : 0, q_split ? 1e-5f : 0.f,
                          d->ws_item_perm.as<uint32_t>(), d->ws_g_tau.as<float>());
-      B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, kGroupRows, st));
-      build_group_work_kernel<<<static_cast<unsigned>(ceil_div(d->n_lists, 256)), 256, 0, st>>>(
-          d->ws_item_off.as<uint32_t>(), offs, d->ws_item_cnt.as<int>(), d->list_of_rank.as<int>(),
-          d->n_lists,
-          d->ws_g_work.as<int4>(), n_work, counter);
-      gather_group_queries_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
-          d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists, qf, d->dp,
-          n_probes, d->fmt, q_split, d->ws_g_q.as<uint16_t>(), d->ws_g_rowq.as<int>());
-      B2VS_CUDA(cudaGetLastError());
-      GroupedScanArgs ga{};
-      ga.q_mat = d->ws_g_q.ptr; ga.q_rows = rows_cap;
-      ga.x_mat = d->data.ptr; ga.x_rows = d->n_slots;
-      ga.kdim = d->dp; ga.ab_format = d->fmt; ga.q_split = q_split;
-      ga.beta = snorm; ga.alpha = alpha;
-      ga.work = d->ws_g_work.ptr; ga.n_work = n_work; ga.max_work = max_work;
-      ga.row_query = d->ws_g_rowq.as<int>(); ga.tau = d->ws_g_tau.as<float>();
-      ga.cand = d->ws_g_cand.as<u64>(); ga.count = d->ws_g_cnt.as<int>(); ga.cap = cap;
-      B2VS_TRY(launch_grouped_scan(index->dev, ga, st));
+      B2VS_TRY(run_grouped_flat_scan(index, d, probe_ids, n_probes, nq, cap, counter, st));
       ivf_group_select_kernel<<<nq, kSelectThreads, static_cast<size_t>(cap) * sizeof(u64), st>>>(
-          ga.cand, ga.count, cap, k, d->ws_keys.as<u64>(), counter + 1);
+          d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), cap, k, d->ws_keys.as<u64>(), counter + 1);
       FLAT_SCAN_DISPATCH(ivf_flat_rescue_kernel, d->fmt, j, nq, st, data, snorm, offs, probe_ids, qf,
-                         d->dp, n_probes, k, alpha, ga.count, cap, d->ws_keys.as<u64>());
+                         d->dp, n_probes, k, alpha, d->ws_g_cnt.as<int>(), cap, d->ws_keys.as<u64>());
       B2VS_CUDA(cudaGetLastError());
       launches += 16;
       single_list = true;

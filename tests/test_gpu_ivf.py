@@ -315,3 +315,35 @@ def test_ivf_grouped_scan_with_every_query_on_the_same_lists(b2, monkeypatch, ki
     assert inter >= (0.999 if kind == "flat" else 0.93) * 700 * 10
     assert bool((i1[:, 0] == 123).float().mean() > 0.95)          # the perturbed row itself
     assert bool((d1[:, 1:] >= d1[:, :-1]).all())
+
+
+@pytest.mark.parametrize("dtype,metric,k", [(torch.bfloat16, "sqeuclidean", 500),
+                                             (torch.float32, "inner_product", 2000)])
+def test_ivf_flat_large_k(b2, dtype, metric, k):
+    """128 < k <= 2048 on an IVF-Flat index (the reference's top-2000 mode): probing every list
+    must reproduce the flat index's large-k answer; a partial probe is a subset search."""
+    from oracle.ivf import recall
+    x = clustered(40000, 96, 50, 91).to(dtype).cuda()
+    q = queries_from(x.float().cpu(), 130, 92).to(dtype).cuda()
+    ix = b2.NativeIndex.ivf_flat(x, 32, metric=metric, id_offset=9, kmeans_iters=6)
+    dd, ii = ix.search(q, k, n_probes=32)
+    torch.cuda.synchronize()
+    assert ii.shape == (130, k) and int(ii.min()) >= 9
+    # exact ground truth over the index's own representation (bf16 rows, fp32 accumulate)
+    xf = x.to(torch.bfloat16).float() if dtype == torch.float32 else x.float()
+    qf = q.float()
+    if metric == "sqeuclidean":
+        full = (xf * xf).sum(1)[None, :] - 2.0 * qf @ xf.T + (qf * qf).sum(1)[:, None]
+        td, ti = torch.topk(full, k, dim=1, largest=False)
+    else:
+        full = qf @ xf.T
+        td, ti = torch.topk(full, k, dim=1, largest=True)
+    assert recall((ii - 9).cpu(), ti.cpu()) > 0.998
+    assert torch.allclose(dd, td, rtol=2e-3, atol=2e-2)
+    srt = dd[:, 1:] >= dd[:, :-1] if metric == "sqeuclidean" else dd[:, 1:] <= dd[:, :-1]
+    assert bool(srt.all())
+    d2, i2 = ix.search(q, k, n_probes=8)          # subset of the lists: still k results, sorted
+    assert int((i2 >= 0).sum()) > 0.9 * i2.numel()
+    pq = b2.NativeIndex.ivf_pq(x, 32, 24, metric=metric)
+    with pytest.raises(RuntimeError, match="IVF-PQ k <="):
+        pq.search(q, k)
