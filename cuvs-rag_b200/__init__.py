@@ -4,7 +4,7 @@ The package directory is named ``cuvs-rag_b200`` (not importable by name), so it
 either through the repo-root shim ``cuvs_rag_b200.py`` (``import cuvs_rag_b200``) or by putting
 this directory on ``sys.path`` and importing the reference's flat module names
 (``gpu_resource_manager``, ``embedding_distribution_manager``, ``index_building_coordinator``,
-``search_result_aggregator``) exactly as the reference's scripts and tests do.  Both spellings
+``search_result_aggregator``, ``improved_multi_gpu_rag``) exactly as the reference's scripts and tests do.  Both spellings
 resolve to ONE module object each (registered in ``sys.modules`` under both names), so classes
 compare equal whichever way they were imported.
 """
@@ -30,6 +30,7 @@ embedding_distribution_manager = _load("embedding_distribution_manager")
 index_building_coordinator = _load("index_building_coordinator")
 search_result_aggregator = _load("search_result_aggregator")
 evaluation = _load("evaluation")
+improved_multi_gpu_rag = _load("improved_multi_gpu_rag")
 
 from _native import NativeIndex, merge_topk, kmeans_fit, build as build_native  # noqa: E402
 from gpu_resource_manager import GPUResourceManager, GPUConfig, MultiGPUConfig, partition_even  # noqa: E402
@@ -41,6 +42,8 @@ from search_result_aggregator import (  # noqa: E402
     SearchResultAggregator, SearchResult, AggregatedSearchResult, SearchConfig,
     combine_search_results, filter_search_results_by_distance)
 from evaluation import RecallEvaluator, recall_at_k  # noqa: E402
+from improved_multi_gpu_rag import (  # noqa: E402
+    IndexType, ParallelIndexBuilder, ParallelSearchEngine, CUDAMemoryManager)
 
 __all__ = [
     "NativeIndex", "merge_topk", "kmeans_fit", "build_native",
@@ -50,4 +53,5 @@ __all__ = [
     "SearchResultAggregator", "SearchResult", "AggregatedSearchResult", "SearchConfig",
     "combine_search_results", "filter_search_results_by_distance",
     "RecallEvaluator", "recall_at_k",
+    "IndexType", "ParallelIndexBuilder", "ParallelSearchEngine", "CUDAMemoryManager",
 ]
