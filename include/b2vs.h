@@ -119,8 +119,8 @@ int b2vs_ivfpq_build(int dev, int metric, int dtype, int dim, const void* db, in
                      b2vs_index** out);
 
 /* k nearest rows for each of the nq queries ([nq, dim], `q_dtype`, device memory).
- * k <= 128 on every index kind (fused in-kernel top-k); flat indexes also serve 128 < k <= 2048
- * (append + radix-select path, synchronises `stream` once per pass).
+ * k <= 128 on every index kind (fused in-kernel top-k); flat and IVF-Flat indexes also serve
+ * 128 < k <= 2048 (append + radix-select paths, which synchronise `stream`).
  * out_d [nq, k] float32 and out_i [nq, k] int64 are caller-owned DEVICE buffers; missing
  * results are (inf | -inf, -1).  Asynchronous on `stream`.  `params` may be NULL. */
 int b2vs_search(b2vs_index* index, const void* queries, int q_dtype, int nq, int k,
