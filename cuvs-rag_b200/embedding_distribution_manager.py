@@ -233,9 +233,58 @@ class EmbeddingDistributionManager:
         if all(g in available for g in used) and self.validate_distribution(distributed_embeddings):
             return distributed_embeddings
         logger.warning("re-sharding: GPUs %s no longer all usable (available %s)", used, available)
+        peer = self._reshard_device_to_device(distributed_embeddings, list(available))
+        if peer is not None:
+            return peer
         full = self._gather_embeddings_to_cpu(distributed_embeddings)
         self._release_parts(distributed_embeddings.parts)
         return self.distribute_embeddings(full)
+
+    def _reshard_device_to_device(self, dist: DistributedEmbeddings,
+                                  target_gpus: List[int]) -> Optional[DistributedEmbeddings]:
+        """Elastic re-shard without the host round trip (the reference gathers
+        everything on the CPU, ``embedding_distribution_manager.py:274-334``): the new shards are
+        allocated on the surviving GPUs and filled by direct device-to-device copies of the
+        overlapping row ranges of the old shards (NVLink peer copies between GPUs).  Returns None
+        when the shards are not CUDA tensors or a copy fails (source GPU really gone) — the caller
+        then falls back to the host route."""
+        parts = sorted(dist.parts, key=lambda p: p.start_index)
+        if not target_gpus or not parts or not all(
+                isinstance(p.tensor, torch.Tensor) and p.tensor.is_cuda for p in parts):
+            return None
+        try:
+            ranges = self.gpu_manager.distribute_workload(dist.total_size, "even", gpu_ids=list(target_gpus))
+        except TypeError:          # a manager without the gpu_ids extension
+            return None
+        new_parts: List[EmbeddingPart] = []
+        try:
+            for gpu_id, start, end in ranges:
+                if end <= start:
+                    continue
+                keep = next((p for p in parts if p.gpu_id == gpu_id and p.start_index == start
+                             and p.end_index == end), None)
+                if keep is not None:                       # shard already where it belongs
+                    new_parts.append(keep)
+                    continue
+                dev = torch.device(self.gpu_manager.get_safe_device_string(gpu_id))
+                shard = torch.empty((end - start, dist.embedding_dim), dtype=parts[0].tensor.dtype, device=dev)
+                for p in parts:
+                    lo, hi = max(start, p.start_index), min(end, p.end_index)
+                    if lo < hi:
+                        shard[lo - start:hi - start].copy_(
+                            p.tensor[lo - p.start_index:hi - p.start_index], non_blocking=True)
+                new_parts.append(EmbeddingPart(gpu_id, shard, start, end))
+            for g in {p.gpu_id for p in new_parts} | {p.gpu_id for p in parts}:
+                torch.cuda.synchronize(g)
+        except Exception as exc:
+            logger.warning("device-to-device re-shard failed (%s): falling back to the host route", exc)
+            self._release_parts([p for p in new_parts if p not in parts])
+            return None
+        kept = {id(p) for p in new_parts}
+        self._release_parts([p for p in parts if id(p) not in kept])
+        out = DistributedEmbeddings(new_parts, dist.total_size, dist.embedding_dim)
+        self.current_distribution = out
+        return out
 
     def _gather_embeddings_to_cpu(self, distributed_embeddings: DistributedEmbeddings) -> torch.Tensor:
         ordered = sorted(distributed_embeddings.parts, key=lambda p: p.start_index)

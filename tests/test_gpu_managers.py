@@ -73,3 +73,37 @@ def test_simulated_index_is_rejected_on_a_gpu_box(b2):
     with pytest.raises(TypeError, match="not a native index"):
         sra.perform_distributed_search(torch.randn(2, 8), {0: {"type": "ivf_flat", "size": 1, "dim": 8}},
                                        b2.SearchConfig(k=1, parallel_search=False))
+
+
+def test_device_to_device_reshard_reassembles_rows(b2):
+    """Elastic re-shard without the host round trip: new shards are filled from the overlapping
+    row ranges of the old ones by device-to-device copies."""
+    grm = b2.GPUResourceManager()
+    edm = b2.EmbeddingDistributionManager(grm)
+    x = torch.randn(1000, 48)
+    parts = [b2.EmbeddingPart(0, x[:600].cuda(), 0, 600), b2.EmbeddingPart(0, x[600:].cuda(), 600, 1000)]
+    dist = b2.DistributedEmbeddings(parts, 1000, 48)
+    out = edm._reshard_device_to_device(dist, [0])
+    assert out is not None and len(out.parts) == 1
+    p = out.parts[0]
+    assert (p.gpu_id, p.start_index, p.end_index) == (0, 0, 1000) and p.tensor.is_cuda
+    assert torch.equal(p.tensor.cpu(), x)
+    assert parts[0].tensor is None and parts[1].tensor is None      # old shards were released
+    assert edm.current_distribution is out
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NVLink peer copies)")
+def test_redistribute_moves_shards_over_nvlink_when_a_gpu_drops_out(b2):
+    grm = b2.GPUResourceManager()
+    edm = b2.EmbeddingDistributionManager(grm)
+    x = torch.randn(5001, 64)
+    dist = edm.distribute_embeddings(x, target_gpus=[0, 1], dtype=torch.bfloat16)
+    assert [p.gpu_id for p in dist.parts] == [0, 1]
+    grm.available_gpus = [1]                                         # GPU 0 is taken away
+    out = edm.redistribute_if_needed(dist)
+    assert [(p.gpu_id, p.start_index, p.end_index) for p in out.parts] == [(1, 0, 5001)]
+    assert torch.equal(out.parts[0].tensor.cpu(), x.to(torch.bfloat16))
+    # and the index built on the re-sharded data answers with global ids
+    ix = b2.NativeIndex.flat(out.parts[0].tensor, metric="sqeuclidean")
+    _, ids = ix.search(out.parts[0].tensor[[7, 4999]], 1)
+    assert ids[:, 0].tolist() == [7, 4999]
