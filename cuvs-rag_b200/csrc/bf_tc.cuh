@@ -44,7 +44,18 @@ constexpr int kBN = 256;   // db rows per tile (TMEM columns)
 constexpr int kBK = B2VS_BK;
 static_assert(kBK == 64 || kBK == 32, "kBK must be 64 or 32");
 constexpr int kNormBytes = kBN * 4;
-constexpr int kTcThreads = 256;
+// Epilogue warp groups (compile-time A/B switch, default 1).  With 2 groups (warps 4-7 and 8-11)
+// each group owns one of the two TMEM accumulator buffers, i.e. every other tile, with its own
+// per-row candidate state; an item then leaves one sorted list per group and the split merge
+// folds them.  Measured at C2 on the same box, 15 sustained steps: 2 groups 72.0 K QPS at
+// ~1.2 GHz, 1 group 73.6-74.3 K QPS at ~1.33 GHz - the kernel is power-capped, and the extra
+// warps cost more clock than the shorter accumulator hand-off wins back.
+#ifndef B2VS_EPI_GROUPS
+#define B2VS_EPI_GROUPS 1
+#endif
+constexpr int kEpiGroups = B2VS_EPI_GROUPS;
+static_assert(kEpiGroups == 1 || kEpiGroups == 2, "kEpiGroups");
+constexpr int kTcThreads = 128 + 128 * kEpiGroups;
 
 template <int G> struct TcCfg {
   static constexpr int kBRows = kBN / G;                     // db rows staged by one CTA
@@ -57,8 +68,8 @@ template <int G> struct TcCfg {
 
 struct BfTcParams {
   const float* beta;    // [tiles_total*256] per db row additive term (||x||^2, 0, +inf on padding)
-  u64* cand;            // [grid][128][kCap] candidate buffers
-  u64* out_keys;        // [n_splits][q_pad][k] sorted ascending, kKeyInf padded
+  u64* cand;            // [grid][kEpiGroups][128][kCap] candidate buffers
+  u64* out_keys;        // [n_splits * kEpiGroups][q_pad][k] sorted ascending, kKeyInf padded
   int n_qblocks;        // ceil(nq / (128*G))
   int q_pad;            // n_qblocks * 128 * G
   int n_items;          // n_qblocks * n_splits
@@ -350,9 +361,11 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 4;                // TMEM lane quarter == warp % 4
+    const int ew = warp & 3;                // TMEM lane quarter == warp % 4
+    const uint32_t eg = static_cast<uint32_t>(warp - 4) >> 2;   // epilogue group = accumulator buffer
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-    u64* const cand_warp = p.cand + (static_cast<size_t>(blockIdx.x) * kBM + ew * 32) * kCap;
+    u64* const cand_warp =
+        p.cand + ((static_cast<size_t>(blockIdx.x) * kEpiGroups + eg) * kBM + ew * 32) * kCap;
     u64* const my_cand = cand_warp + static_cast<size_t>(lane) * kCap;
     const uint32_t acc_empty_leader =
         (G == 2) ? ptx::mapa_cluster(bar_acc_empty, 0) : bar_acc_empty;
@@ -387,6 +400,7 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       for (int ti = t0; ti < t1; ++ti, ++tcount) {
         const int t = ti * p.tile_stride;
         const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
+        if (kEpiGroups == 2 && as != eg) continue;   // the other group's accumulator buffer
         ptx::mbar_wait(bar_acc_full + 8 * as, aph);
         ptx::mbar_wait(bar_norm_full + 8 * as, aph);
         ptx::tc_fence_after();
@@ -449,7 +463,7 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       if (mode == kModeAppend) continue;  // candidates already sit in the query's global buffer
       // ---- item done: emit this (split, query block)'s sorted top-k keys
       const size_t q_row0 = static_cast<size_t>(qb) * (kBM * G) + cta_rank * kBM + ew * 32;
-      u64* out_blk = p.out_keys + (static_cast<size_t>(s) * p.q_pad + q_row0) * p.k;
+      u64* out_blk = p.out_keys + ((static_cast<size_t>(s) * kEpiGroups + eg) * p.q_pad + q_row0) * p.k;
       if (mode == kModeArgmin) {
         out_blk[lane] = best;
       } else {

@@ -401,8 +401,8 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
     n_splits = static_cast<int>(ceil_div(ptiles, tps));
     const int n_items = n_qblocks * n_splits;
     grid = std::min(n_items, units) * group;
-    B2VS_TRY(ws_cand.reserve(static_cast<size_t>(grid) * kBM * kCap * sizeof(u64)));
-    B2VS_TRY(ws_keys.reserve(static_cast<size_t>(n_splits) * q_pad * k * sizeof(u64)));
+    B2VS_TRY(ws_cand.reserve(static_cast<size_t>(grid) * kEpiGroups * kBM * kCap * sizeof(u64)));
+    B2VS_TRY(ws_keys.reserve(static_cast<size_t>(n_splits) * kEpiGroups * q_pad * k * sizeof(u64)));
     p.cand = ws_cand.as<u64>();
     p.out_keys = ws_keys.as<u64>();
     p.n_items = n_items;
@@ -435,12 +435,12 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
     ++launches;
     if (last && timed) B2VS_CUDA(cudaEventRecord(ev1, st));
     if (last) {
-      B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits, q_pad, nq, k, metric,
+      B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits * kEpiGroups, q_pad, nq, k, metric,
                                    ws_qnorm.as<float>(), id_offset, out_d, out_i, out_label, st));
     } else {
       // sampled pass: only the k-th best raw score per query is kept, as the next pass's threshold
-      B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits, q_pad, q_pad, k, metric, nullptr, 0,
-                                   nullptr, nullptr, nullptr, st, nullptr, ws_tau.as<float>()));
+      B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits * kEpiGroups, q_pad, q_pad, k, metric,
+                                   nullptr, 0, nullptr, nullptr, nullptr, st, nullptr, ws_tau.as<float>()));
     }
     ++launches;
   }
