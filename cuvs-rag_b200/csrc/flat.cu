@@ -238,6 +238,7 @@ __global__ void fill_missing_kernel(float* out_d, int64_t* out_i, int32_t* out_l
 }
 
 constexpr int kDefaultTcGroup = 1;
+constexpr int kPairMaxK = 32;   // largest k served by the CTA-pair kernel by default
 
 // B2VS_TC_GROUP=1|2 forces the single-CTA / CTA-pair kernel (bring-up and A/B measurements).
 static int tc_group_override() {
@@ -315,9 +316,12 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   }
   const int dp = static_cast<int>(round_up(dim, 8));
   const int want_norm = (metric == B2VS_METRIC_L2) ? 1 : 0;
-  // CTA-pair (cta_group::2) kernel for batches that fill a 256-row query block, else single CTA
+  // kernel variant: CTA pair (cta_group::2, 256-row query blocks) or single CTA (128-row blocks)
   int group = tc_group_override();
-  if (group == 0) group = (nq > kBM) ? kDefaultTcGroup : 1;
+  // Default: the CTA-pair kernel for small k (sustained C2-size runs: k=1 +5.4 %, k=10 +3.2 % over
+  // the single-CTA kernel), the single-CTA kernel otherwise (k=100: pair -3.5 %: both sit at the
+  // power cap and the pair's 98 %-busy tensor pipe loses more clock than it gains).
+  if (group == 0) group = (nq > kBM && k <= kPairMaxK) ? 2 : kDefaultTcGroup;
   if (flags & B2VS_FLAG_TC_SINGLE) group = 1;
   if (flags & B2VS_FLAG_TC_PAIR) group = 2;
   const int qrows = kBM * group;
