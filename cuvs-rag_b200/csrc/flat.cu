@@ -321,7 +321,10 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   // Default: the CTA-pair kernel for small k (sustained C2-size runs: k=1 +5.4 %, k=10 +3.2 % over
   // the single-CTA kernel), the single-CTA kernel otherwise (k=100: pair -3.5 %: both sit at the
   // power cap and the pair's 98 %-busy tensor pipe loses more clock than it gains).
-  if (group == 0) group = (nq > kBM && k <= kPairMaxK) ? 2 : kDefaultTcGroup;
+  // (C5, 50M x 1024, k=10: the pair wins at Q = 256 (one 256-row block) and from Q = 4096 up,
+  // the single-CTA kernel at Q = 1024 by 11 %.)
+  if (group == 0)
+    group = (k <= kPairMaxK && (nq >= 4096 || (nq > kBM && nq <= 2 * kBM))) ? 2 : kDefaultTcGroup;
   if (flags & B2VS_FLAG_TC_SINGLE) group = 1;
   if (flags & B2VS_FLAG_TC_PAIR) group = 2;
   const int qrows = kBM * group;
