@@ -222,19 +222,34 @@ static void balance_pairs(const std::vector<int>& counts, int64_t n, std::vector
   }
 }
 
+// Temporaries of one k-means fit.  A caller that fits many small problems in a row (the 64+ PQ
+// sub-codebooks) passes the same workspace to every fit, so device memory is allocated once
+// instead of being malloc'ed and freed (= device-synchronised) per fit.
+struct KmWorkspace {
+  DevBuf sums, counts, labels, donors, seg_off, seg_cur, seg_rows, seg_slot;
+  FlatEngine eng;
+  void release() {
+    for (DevBuf* b : {&sums, &counts, &labels, &donors, &seg_off, &seg_cur, &seg_rows, &seg_slot}) b->release();
+    eng.destroy();
+  }
+};
+
 static int kmeans_fit_impl(int dev, int dtype, int dim, const void* x, int64_t n, int ncl, int iters,
-                           uint64_t seed, float* cent, int32_t* labels_out, cudaStream_t st) {
+                           uint64_t seed, float* cent, int32_t* labels_out, cudaStream_t st,
+                           KmWorkspace* shared_ws = nullptr) {
   B2VS_CHECK(n >= 1 && ncl >= 1 && ncl <= n, B2VS_EINVAL,
              "k-means needs 1 <= n_clusters <= n (n_clusters=%d, n=%lld)", ncl,
              static_cast<long long>(n));
   B2VS_CHECK(n < (1ll << 31), B2VS_EINVAL, "k-means input too large (n=%lld)", static_cast<long long>(n));
-  DevBuf sums, counts, labels, donors, seg_off, seg_cur, seg_rows, seg_slot;
+  KmWorkspace local_ws;
+  KmWorkspace& w = shared_ws ? *shared_ws : local_ws;
+  DevBuf &sums = w.sums, &counts = w.counts, &labels = w.labels, &donors = w.donors,
+         &seg_off = w.seg_off, &seg_cur = w.seg_cur, &seg_rows = w.seg_rows, &seg_slot = w.seg_slot;
+  FlatEngine& eng = w.eng;
   std::vector<int> h_counts, h_donor;
-  FlatEngine eng;
   int rc = B2VS_OK;
   auto cleanup = [&]() {
-    for (DevBuf* b : {&sums, &counts, &labels, &donors, &seg_off, &seg_cur, &seg_rows, &seg_slot}) b->release();
-    eng.destroy();
+    if (!shared_ws) local_ws.release();   // a shared workspace is released by its owner
   };
 #define KM_TRY(expr) do { rc = (expr); if (rc != B2VS_OK) { cleanup(); return rc; } } while (0)
 #define KM_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); cleanup(); return B2VS_ECUDA; } } while (0)
@@ -2030,11 +2045,16 @@ static int ivf_build(int kind, int dev, int metric, int dtype, int dim, const vo
     IB_CUDA(cudaGetLastError());
     IB_TRY(d->codebooks.reserve(static_cast<size_t>(pq_dim) * 256 * dsub * sizeof(float)));
     const int pq_iters = std::min(iters, 10);
+    KmWorkspace km_ws;   // one set of temporaries for all sub-codebooks
     for (int m = 0; m < pq_dim; ++m) {
-      IB_TRY(kmeans_fit_impl(dev, B2VS_F32, dsub, slices.as<float>() + static_cast<size_t>(m) * p_train * dsub,
-                             p_train, 256, pq_iters, params->seed + 31ull * (m + 1),
-                             d->codebooks.as<float>() + static_cast<size_t>(m) * 256 * dsub, nullptr, st));
+      rc = kmeans_fit_impl(dev, B2VS_F32, dsub, slices.as<float>() + static_cast<size_t>(m) * p_train * dsub,
+                           p_train, 256, pq_iters, params->seed + 31ull * (m + 1),
+                           d->codebooks.as<float>() + static_cast<size_t>(m) * 256 * dsub, nullptr, st,
+                           &km_ws);
+      if (rc != B2VS_OK) break;
     }
+    km_ws.release();
+    if (rc != B2VS_OK) return fail(rc);
     slices.release();
     const size_t code_bytes = static_cast<size_t>(std::max<uint32_t>(total_slots, 32)) * d->mp;
     IB_TRY(d->codes.reserve(code_bytes));
