@@ -72,6 +72,7 @@ struct BfTcParams {
   u64* out_keys;        // [n_splits * kEpiGroups][q_pad][k] sorted ascending, kKeyInf padded
   int n_qblocks;        // ceil(nq / (128*G))
   int q_pad;            // n_qblocks * 128 * G
+  int nq;               // real query rows; rows >= nq are padding and never collect candidates
   int n_items;          // n_qblocks * n_splits
   int tiles_total;      // tiles visited by this launch: ceil(ceil(n_db / 256) / tile_stride)
   int tiles_per_split;
@@ -389,6 +390,8 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         const int query = __ldg(p.row_query + q_row);
         tau = query >= 0 ? p.tau_init[query] : -inf;   // padding rows never qualify
         q_row = static_cast<size_t>(max(query, 0));
+      } else if (q_row >= static_cast<size_t>(p.nq)) {
+        tau = -inf;            // padding row of the last query block: stays empty, costs nothing
       } else if (p.tau_init != nullptr) {
         tau = p.tau_init[q_row];
       }
@@ -471,7 +474,7 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         for (int rr = 0; rr < 32; ++rr) {
           const int n_r = __shfl_sync(0xffffffffu, cnt, rr);
           u64* dst = out_blk + static_cast<size_t>(rr) * p.k;
-          compact_row(cand_warp + static_cast<size_t>(rr) * kCap, dst, n_r, p.k, lane);
+          if (n_r > 0) compact_row(cand_warp + static_cast<size_t>(rr) * kCap, dst, n_r, p.k, lane);
           for (int i = min(n_r, p.k) + lane; i < p.k; i += 32) dst[i] = kKeyInf;
         }
         __syncwarp();

@@ -383,6 +383,7 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   p.beta = beta.as<float>();
   p.n_qblocks = n_qblocks;
   p.q_pad = q_pad;
+  p.nq = nq;
   p.k_blocks = static_cast<int>(ceil_div(kdim, kBK));
   p.k = k;
   p.alpha = (metric == B2VS_METRIC_L2) ? -2.f : -1.f;
@@ -529,6 +530,7 @@ int FlatEngine::search_bigk(const void* q_mat, int nq, int q_pad, int group, int
     p.beta = beta.as<float>();
     p.n_qblocks = rows_c / qrows;
     p.q_pad = rows_c;
+    p.nq = valid_c;
     p.k_blocks = static_cast<int>(ceil_div(kdim, kBK));
     p.k = k;
     p.alpha = (metric == B2VS_METRIC_L2) ? -2.f : -1.f;

@@ -58,6 +58,7 @@ struct IvfData {
   const void* src_rows = nullptr;  // IVF-PQ: the caller's [n, dim] rows, BORROWED for refine
   std::vector<int32_t> h_sizes;
   DevBuf rank_of_list, list_of_rank;  // int [n_lists]: lists in descending-size order (scan scheduling)
+  int max_list_rows = 0;              // longest list, padded to 32 slots
   b2vs_search_stats stats{};
   bool counter_pending = false;
   int last_nq = 0;
@@ -642,15 +643,24 @@ __global__ void build_group_work_kernel(const uint32_t* __restrict__ group_off,
                                         const uint32_t* __restrict__ offsets,
                                         const int* __restrict__ group_cnt,
                                         const int* __restrict__ list_of_rank, int n_lists,
+                                        int chunk_rows, int slots,
                                         int4* __restrict__ work, int* __restrict__ n_work,
                                         unsigned long long* __restrict__ scanned_rows) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;   // size rank: items come out longest first
-  if (r == 0) *n_work = static_cast<int>(group_off[n_lists] >> 7);
+  if (r == 0) *n_work = static_cast<int>(group_off[n_lists] >> 7) * slots;
   if (r >= n_lists) return;
   const int l = list_of_rank[r];
   const int b0 = static_cast<int>(group_off[r] >> 7), b1 = static_cast<int>(group_off[r + 1] >> 7);
   const int begin = static_cast<int>(offsets[l]), end = static_cast<int>(offsets[l + 1]);
-  for (int b = b0; b < b1; ++b) work[b] = make_int4(b, begin, end, 0);
+  // Small batches have fewer (list, query block) pairs than SMs: a list is then cut into `slots`
+  // row ranges of chunk_rows (a multiple of the 256-row tile), one work item each - append mode
+  // keeps no per-item state, so the pieces are independent.  Ranges past the list end are empty.
+  for (int b = b0; b < b1; ++b)
+    for (int c = 0; c < slots; ++c) {
+      const int rb = min(end, begin + c * chunk_rows);
+      const int re = c + 1 == slots ? end : min(end, rb + chunk_rows);
+      work[b * slots + c] = make_int4(b, rb, re, 0);
+    }
   if (scanned_rows && group_cnt[r] > 0)   // algorithmic work: every probing query sees every row
     atomicAdd(scanned_rows, static_cast<unsigned long long>(group_cnt[r]) * static_cast<unsigned>(end - begin));
 }
@@ -1183,6 +1193,8 @@ static int build_list_ranks(IvfData* d) {
     std::stable_sort(order.begin(), order.end(),
                      [&](int a, int b) { return d->h_sizes[a] > d->h_sizes[b]; });
   for (int r = 0; r < d->n_lists; ++r) rank[order[r]] = r;
+  d->max_list_rows = 0;
+  for (int v : d->h_sizes) d->max_list_rows = std::max(d->max_list_rows, static_cast<int>(round_up(v, 32)));
   const size_t bytes = static_cast<size_t>(d->n_lists) * sizeof(int);
   B2VS_TRY(d->rank_of_list.reserve(bytes));
   B2VS_TRY(d->list_of_rank.reserve(bytes));
@@ -1492,6 +1504,20 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
                             const b2vs_search_params& sp, float* out_d, int64_t* out_i,
                             cudaStream_t st);
 
+// Row-range split of the grouped scan's work items (see build_group_work_kernel): aim at two
+// items per SM when the batch alone does not provide them.
+static void choose_work_split(const b2vs_index* index, const IvfData* d, int items, int* chunk_rows,
+                              int* slots) {
+  const int sms = sm_count(index->dev);
+  const double mean_rows = std::max(1.0, static_cast<double>(d->n) / std::max(d->n_lists, 1));
+  const double est_tiles = static_cast<double>(items) * (mean_rows / 256.0 + 0.5);
+  const int max_tiles = std::max(1, static_cast<int>(ceil_div(std::max(d->max_list_rows, 1), 256)));
+  int chunk_tiles = static_cast<int>(std::ceil(est_tiles / (2.0 * sms)));
+  chunk_tiles = std::max(1, std::min(chunk_tiles, max_tiles));
+  *slots = static_cast<int>(ceil_div(max_tiles, chunk_tiles));
+  *chunk_rows = chunk_tiles * 256;
+}
+
 // Groups the nq * n_probes (query, probe) items by list and runs the tensor-core list scan in
 // append mode against the thresholds in ws_g_tau; candidates land in ws_g_cand / ws_g_cnt (the
 // caller sizes, zeroes and later selects from them).  probe_ids is [nq, n_probes] dense.
@@ -1501,7 +1527,9 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
   const int items = nq * n_probes;
   const int q_split = index->dtype == B2VS_F32 ? 1 : 0;
   const int q_pitch = q_split ? 2 * static_cast<int>(round_up(d->dp, 64)) : d->dp;
-  const int max_work = items / kGroupRows + std::min(d->n_lists, items) + 1;
+  int chunk_rows = 0, slots = 1;
+  choose_work_split(index, d, items, &chunk_rows, &slots);
+  const int max_work = (items / kGroupRows + std::min(d->n_lists, items) + 1) * slots;
   const int64_t rows_cap = static_cast<int64_t>(sorted_rows_cap(d, items, kGroupRows));
   B2VS_TRY(d->ws_g_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16));
   B2VS_TRY(d->ws_g_q.reserve(static_cast<size_t>(rows_cap) * q_pitch * 2));
@@ -1510,7 +1538,7 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
   B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, kGroupRows, st));
   build_group_work_kernel<<<static_cast<unsigned>(ceil_div(d->n_lists, 256)), 256, 0, st>>>(
       d->ws_item_off.as<uint32_t>(), d->offsets.as<uint32_t>(), d->ws_item_cnt.as<int>(),
-      d->list_of_rank.as<int>(), d->n_lists, d->ws_g_work.as<int4>(), n_work, counter);
+      d->list_of_rank.as<int>(), d->n_lists, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work, counter);
   gather_group_queries_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
       d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists,
       d->ws_qf.as<float>(), d->dp, n_probes, d->fmt, q_split, d->ws_g_q.as<uint16_t>(),
@@ -1742,7 +1770,9 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
     const float* qf = d->ws_qf.as<float>();
     B2VS_TRY(reserve_item_sort(d, items, kGroupRows));
     B2VS_TRY(sort_items_by_list(d, probe_ids, nq, n_probes, 1, st));
-    const int max_work = items / kGroupRows + std::min(d->n_lists, items) + 1;
+    int chunk_rows = 0, slots = 1;
+    choose_work_split(index, d, items, &chunk_rows, &slots);
+    const int max_work = (items / kGroupRows + std::min(d->n_lists, items) + 1) * slots;
     const int64_t rows_cap = static_cast<int64_t>(sorted_rows_cap(d, items, kGroupRows));
     B2VS_TRY(d->ws_g_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16));
     B2VS_TRY(d->ws_g_q.reserve(static_cast<size_t>(rows_cap) * index->dim * 2));
@@ -1764,7 +1794,7 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
     B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, kGroupRows, st));
     build_group_work_kernel<<<static_cast<unsigned>(ceil_div(d->n_lists, 256)), 256, 0, st>>>(
         d->ws_item_off.as<uint32_t>(), offs, d->ws_item_cnt.as<int>(), d->list_of_rank.as<int>(),
-        d->n_lists, d->ws_g_work.as<int4>(), n_work, counter);
+        d->n_lists, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work, counter);
     gather_group_residuals_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
         d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists, probe_ids, qf,
         d->centroids.as<float>(), index->dim, d->dp, n_probes, l2, d->ws_g_q.as<uint16_t>(),
