@@ -28,6 +28,7 @@ constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kListE = 4;  // warp-resident sorted list: 32 * 4 = 128 keys
 constexpr int kGroupRows = 128;  // query rows per grouped-scan work item (= the UMMA M extent)
+constexpr int kSeedSortMinQueries = 2048;  // below this the seed pass skips its ordering sort
 constexpr int kMaxProbes = 2048;  // coarse probe = exact top-n_probes (large-k path above 128)
 constexpr int kNormSlack = 256;  // slot_norm floats past the last slot (whole-tile beta loads)
 
@@ -603,7 +604,8 @@ ivf_seed_tau_kernel(const uint16_t* __restrict__ data, const float* __restrict__
   __shared__ u64 lists[kScanWarps][32 * kListE];
   __shared__ u64 top[kMaxFusedK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = static_cast<int>(q_perm[blockIdx.x]);  // queries ordered by nearest list (L2 reuse)
+  // large batches: queries ordered by nearest list (L2 reuse); small ones skip the sort
+  const int q = q_perm ? static_cast<int>(q_perm[blockIdx.x]) : static_cast<int>(blockIdx.x);
   const long long list = probe_ids[static_cast<size_t>(q) * n_probes];
   uint32_t begin = 0, end = 0;
   if (list >= 0) { begin = offsets[list]; end = min(offsets[list + 1], begin + row_limit); }
@@ -1263,7 +1265,7 @@ ivf_pq_lut_scan_kernel(int mode, const uint8_t* __restrict__ codes, const uint32
   __shared__ u64 top[kMaxFusedK];
   __shared__ float red[kScanWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = mode == 0 ? static_cast<int>(q_perm[blockIdx.x]) : blockIdx.x;
+  const int q = (mode == 0 && q_perm) ? static_cast<int>(q_perm[blockIdx.x]) : blockIdx.x;
   if (mode == 1 && count[q] <= cap) return;
   const int l2 = metric == B2VS_METRIC_L2;
   WarpTopK tk;
@@ -1728,7 +1730,8 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
       const int cap = grouped_cap(k);
       // seed thresholds first (queries ordered by their nearest list), then group all the items
       B2VS_TRY(reserve_item_sort(d, items, kGroupRows));  // both sorts share these buffers
-      B2VS_TRY(sort_items_by_list(d, probe_ids, nq, n_probes, 1, st));
+      const bool order_seeds = nq >= kSeedSortMinQueries;
+      if (order_seeds) B2VS_TRY(sort_items_by_list(d, probe_ids, nq, n_probes, 1, st));
       B2VS_TRY(d->ws_g_tau.reserve(static_cast<size_t>(nq) * sizeof(float)));
       B2VS_TRY(d->ws_g_cand.reserve(static_cast<size_t>(nq) * cap * sizeof(u64)));
       B2VS_TRY(d->ws_g_cnt.reserve(static_cast<size_t>(nq) * sizeof(int)));
@@ -1736,7 +1739,7 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
       FLAT_SCAN_DISPATCH(ivf_seed_tau_kernel, d->fmt, j, nq, st, data, snorm, offs, probe_ids, qf, d->dp,
                          n_probes, k, alpha, grouped_seed_rows(k), d->max_norm2,
                          index->metric == B2VS_METRIC_L2 ? 1 : 0, q_split ? 1e-5f : 0.f,
-                         d->ws_item_perm.as<uint32_t>(), d->ws_g_tau.as<float>());
+                         order_seeds ? d->ws_item_perm.as<uint32_t>() : nullptr, d->ws_g_tau.as<float>());
       B2VS_TRY(run_grouped_flat_scan(index, d, probe_ids, n_probes, nq, cap, counter, st));
       ivf_group_select_kernel<<<nq, kSelectThreads, static_cast<size_t>(cap) * sizeof(u64), st>>>(
           d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), cap, k, d->ws_keys.as<u64>(), counter + 1);
@@ -1769,7 +1772,8 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
     const uint32_t* offs = d->offsets.as<uint32_t>();
     const float* qf = d->ws_qf.as<float>();
     B2VS_TRY(reserve_item_sort(d, items, kGroupRows));
-    B2VS_TRY(sort_items_by_list(d, probe_ids, nq, n_probes, 1, st));
+    const bool order_seeds = nq >= kSeedSortMinQueries;
+    if (order_seeds) B2VS_TRY(sort_items_by_list(d, probe_ids, nq, n_probes, 1, st));
     int chunk_rows = 0, slots = 1;
     choose_work_split(index, d, items, &chunk_rows, &slots);
     const int max_work = (items / kGroupRows + std::min(d->n_lists, items) + 1) * slots;
@@ -1790,7 +1794,8 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
         0, d->codes.as<uint8_t>(), d->row_ids.as<uint32_t>(), offs, probe_ids, qf,
         d->centroids.as<float>(), d->cb16.as<uint16_t>(), d->cbn.as<float>(), index->dim, d->dp,
         d->pq_dim, d->dsub, n_probes, k, index->metric, grouped_seed_rows(k), d->max_rhat2,
-        d->ws_item_perm.as<uint32_t>(), nullptr, cap, d->ws_g_tau.as<float>(), nullptr);
+        order_seeds ? d->ws_item_perm.as<uint32_t>() : nullptr, nullptr, cap, d->ws_g_tau.as<float>(),
+        nullptr);
     B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, kGroupRows, st));
     build_group_work_kernel<<<static_cast<unsigned>(ceil_div(d->n_lists, 256)), 256, 0, st>>>(
         d->ws_item_off.as<uint32_t>(), offs, d->ws_item_cnt.as<int>(), d->list_of_rank.as<int>(),
