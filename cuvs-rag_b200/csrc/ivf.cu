@@ -1506,6 +1506,105 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
                             const b2vs_search_params& sp, float* out_d, int64_t* out_i,
                             cudaStream_t st);
 
+// Small batches are launch-bound (a Q = 1 search is ~20 tiny kernels), so when the item count is
+// small one CTA does the whole planning step: rank labels, shared-memory histogram, scan of the
+// 128-padded group sizes, scatter of the items into group order and the work table - the job of
+// probe_labels / histogram / scan_sizes / scatter_rows / build_group_work (+ two memsets).
+constexpr int kPlanThreads = 1024;
+constexpr int kPlanMaxItems = 16384;
+constexpr int kPlanMaxLists = 16384;
+__global__ void __launch_bounds__(kPlanThreads)
+ivf_plan_small_kernel(const long long* __restrict__ probe_ids, int items,
+                      const int* __restrict__ rank_of_list, const int* __restrict__ list_of_rank,
+                      const uint32_t* __restrict__ offsets, int n_lists, int chunk_rows, int slots,
+                      uint32_t* __restrict__ row_item, uint32_t* __restrict__ group_off,
+                      int4* __restrict__ work, int* __restrict__ n_work,
+                      unsigned long long* __restrict__ scanned_rows) {
+  extern __shared__ int plan_sm[];
+  int* cnt = plan_sm;                                             // [n_lists] by size rank
+  uint32_t* off = reinterpret_cast<uint32_t*>(plan_sm + n_lists); // [n_lists + 1]
+  __shared__ uint32_t part[kPlanThreads];
+  const int t = threadIdx.x;
+  for (int i = t; i < n_lists; i += kPlanThreads) cnt[i] = 0;
+  __syncthreads();
+  for (int i = t; i < items; i += kPlanThreads) {
+    const long long l = probe_ids[i];
+    atomicAdd(&cnt[rank_of_list[l < 0 ? 0 : l]], 1);
+  }
+  __syncthreads();
+  const int per = (n_lists + kPlanThreads - 1) / kPlanThreads;
+  const int lo = min(n_lists, t * per), hi = min(n_lists, lo + per);
+  uint32_t sum = 0;
+  for (int i = lo; i < hi; ++i) sum += static_cast<uint32_t>((cnt[i] + kGroupRows - 1) / kGroupRows * kGroupRows);
+  part[t] = sum;
+  __syncthreads();
+  if (t == 0) {
+    uint32_t run = 0;
+    for (int i = 0; i < kPlanThreads; ++i) { const uint32_t v = part[i]; part[i] = run; run += v; }
+    off[n_lists] = run;
+    group_off[n_lists] = run;
+    *n_work = static_cast<int>(run >> 7) * slots;
+  }
+  __syncthreads();
+  uint32_t run = part[t];
+  for (int i = lo; i < hi; ++i) {
+    off[i] = run;
+    group_off[i] = run;
+    run += static_cast<uint32_t>((cnt[i] + kGroupRows - 1) / kGroupRows * kGroupRows);
+  }
+  __syncthreads();
+  unsigned long long rows_scanned = 0;
+  for (int r = t; r < n_lists; r += kPlanThreads) {
+    if (cnt[r] == 0) continue;
+    const int l = list_of_rank[r];
+    const int b0 = static_cast<int>(off[r] >> 7), b1 = static_cast<int>(off[r + 1] >> 7);
+    const int begin = static_cast<int>(offsets[l]), end = static_cast<int>(offsets[l + 1]);
+    for (int b = b0; b < b1; ++b)
+      for (int c = 0; c < slots; ++c) {
+        const int rb = min(end, begin + c * chunk_rows);
+        const int re = c + 1 == slots ? end : min(end, rb + chunk_rows);
+        work[b * slots + c] = make_int4(b, rb, re, 0);
+      }
+    rows_scanned += static_cast<unsigned long long>(cnt[r]) * static_cast<unsigned>(end - begin);
+  }
+  if (scanned_rows && rows_scanned) atomicAdd(scanned_rows, rows_scanned);
+  __syncthreads();
+  for (int i = t; i < n_lists; i += kPlanThreads) cnt[i] = 0;   // now the scatter cursors
+  __syncthreads();
+  for (int i = t; i < items; i += kPlanThreads) {
+    const long long l = probe_ids[i];
+    const int r = rank_of_list[l < 0 ? 0 : l];
+    row_item[off[r] + static_cast<uint32_t>(atomicAdd(&cnt[r], 1))] = static_cast<uint32_t>(i);
+  }
+}
+
+// Sort + work table of the grouped scans: the one-CTA plan for small batches, else the
+// counting-sort kernels + build_group_work_kernel.
+static int plan_grouped_work(IvfData* d, const long long* probe_ids, int items, int chunk_rows,
+                             int slots, int4* work, int* n_work, unsigned long long* counter,
+                             cudaStream_t st) {
+  if (items <= kPlanMaxItems && d->n_lists <= kPlanMaxLists) {
+    B2VS_TRY(reserve_item_sort(d, items, kGroupRows));
+    B2VS_CUDA(cudaMemsetAsync(d->ws_item_perm.ptr, 0xFF,
+                              sorted_rows_cap(d, items, kGroupRows) * sizeof(uint32_t), st));
+    const size_t smem = (2 * static_cast<size_t>(d->n_lists) + 1) * sizeof(int);
+    B2VS_CUDA(cudaFuncSetAttribute(ivf_plan_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+    ivf_plan_small_kernel<<<1, kPlanThreads, smem, st>>>(
+        probe_ids, items, d->rank_of_list.as<int>(), d->list_of_rank.as<int>(),
+        d->offsets.as<uint32_t>(), d->n_lists, chunk_rows, slots, d->ws_item_perm.as<uint32_t>(),
+        d->ws_item_off.as<uint32_t>(), work, n_work, counter);
+    B2VS_CUDA(cudaGetLastError());
+    return B2VS_OK;
+  }
+  B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, kGroupRows, st));
+  build_group_work_kernel<<<static_cast<unsigned>(ceil_div(d->n_lists, 256)), 256, 0, st>>>(
+      d->ws_item_off.as<uint32_t>(), d->offsets.as<uint32_t>(), d->ws_item_cnt.as<int>(),
+      d->list_of_rank.as<int>(), d->n_lists, chunk_rows, slots, work, n_work, counter);
+  B2VS_CUDA(cudaGetLastError());
+  return B2VS_OK;
+}
+
 // Row-range split of the grouped scan's work items (see build_group_work_kernel): aim at two
 // items per SM when the batch alone does not provide them.
 static void choose_work_split(const b2vs_index* index, const IvfData* d, int items, int* chunk_rows,
@@ -1537,10 +1636,8 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
   B2VS_TRY(d->ws_g_q.reserve(static_cast<size_t>(rows_cap) * q_pitch * 2));
   B2VS_TRY(d->ws_g_rowq.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
   int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
-  B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, kGroupRows, st));
-  build_group_work_kernel<<<static_cast<unsigned>(ceil_div(d->n_lists, 256)), 256, 0, st>>>(
-      d->ws_item_off.as<uint32_t>(), d->offsets.as<uint32_t>(), d->ws_item_cnt.as<int>(),
-      d->list_of_rank.as<int>(), d->n_lists, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work, counter);
+  B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
+                             counter, st));
   gather_group_queries_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
       d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists,
       d->ws_qf.as<float>(), d->dp, n_probes, d->fmt, q_split, d->ws_g_q.as<uint16_t>(),
@@ -1796,10 +1893,8 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
         d->pq_dim, d->dsub, n_probes, k, index->metric, grouped_seed_rows(k), d->max_rhat2,
         order_seeds ? d->ws_item_perm.as<uint32_t>() : nullptr, nullptr, cap, d->ws_g_tau.as<float>(),
         nullptr);
-    B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, kGroupRows, st));
-    build_group_work_kernel<<<static_cast<unsigned>(ceil_div(d->n_lists, 256)), 256, 0, st>>>(
-        d->ws_item_off.as<uint32_t>(), offs, d->ws_item_cnt.as<int>(), d->list_of_rank.as<int>(),
-        d->n_lists, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work, counter);
+    B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
+                               counter, st));
     gather_group_residuals_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
         d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists, probe_ids, qf,
         d->centroids.as<float>(), index->dim, d->dp, n_probes, l2, d->ws_g_q.as<uint16_t>(),
