@@ -1,0 +1,104 @@
+"""BASELINE.json configs at FULL size through size-independent properties (the oracle cannot run
+10M x 768 in seconds): known-answer queries (a perturbed database row must come back first),
+linearity of the split (the sharded search merged == the unsharded search), sortedness, unique
+in-range ids, and — for IVF — recall against the exact index of the same corpus."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _needs(gb):
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < gb * (1 << 30):
+        pytest.skip(f"needs {gb} GB of free device memory")
+
+
+def _corpus(n, d, dtype, n_comp=0, seed=1234):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.empty((n, d), dtype=dtype, device=dev)
+    cent = torch.randn(n_comp, d, generator=g, device=dev) if n_comp else None
+    for s in range(0, n, 1 << 20):
+        e = min(n, s + (1 << 20))
+        noise = torch.randn((e - s, d), generator=g, device=dev)
+        if cent is not None:
+            noise = cent[torch.randint(0, n_comp, (e - s,), generator=g, device=dev)] + 0.42 * noise
+        x[s:e] = noise.to(dtype)
+    return x, g
+
+
+def test_config_c2_full_size_properties(b2):
+    """C2: exact L2, k = 100, 10M x 768 bf16 (the bench workload), 256 known-answer queries."""
+    _needs(30)
+    n, d, k, nq = 10_000_000, 768, 100, 256
+    x, g = _corpus(n, d, torch.bfloat16)
+    rows = torch.randint(0, n, (nq,), generator=g, device=x.device)
+    q = (x[rows].float() + 0.05 * torch.randn((nq, d), generator=g, device=x.device)).to(torch.bfloat16)
+    ix = b2.NativeIndex.flat(x)
+    dd, ii = ix.search(q, k)
+    torch.cuda.synchronize()
+    assert bool((ii[:, 0] == rows).all())                         # the perturbed row itself
+    assert bool((dd[:, 1:] >= dd[:, :-1]).all())
+    assert int(ii.min()) >= 0 and int(ii.max()) < n
+    assert all(len(set(r.tolist())) == k for r in ii[:32].cpu())
+    # distances are what an fp32 evaluation of the returned pairs gives
+    chk = ((x[ii[:8].reshape(-1)].float() - q[:8].float().repeat_interleave(k, 0)) ** 2).sum(1).reshape(8, k)
+    assert torch.allclose(dd[:8], chk, rtol=1e-3, atol=1e-2)
+    # linearity of the row split: two shards searched separately and merged == the whole
+    half = n // 2
+    a = b2.NativeIndex.flat(x[:half])
+    b = b2.NativeIndex.flat(x[half:], id_offset=half)
+    da, ia = a.search(q, k)
+    db_, ib = b.search(q, k)
+    md, mi = b2.merge_topk(torch.stack([da, db_]), torch.stack([ia, ib]), k)
+    assert float((mi == ii).float().mean()) > 0.999
+    assert torch.allclose(md, dd, rtol=1e-4, atol=1e-3)
+
+
+def test_config_c3_full_size_properties(b2):
+    """C3: IVF-Flat, 4096 lists, 32 probes, 10M x 768 fp16 clustered mixture, k = 10."""
+    _needs(40)
+    from oracle.ivf import recall
+    n, d, nq = 10_000_000, 768, 512
+    x, g = _corpus(n, d, torch.float16, n_comp=4096, seed=7)
+    rows = torch.randint(0, n, (nq,), generator=g, device=x.device)
+    q = (x[rows].float() + 0.1 * torch.randn((nq, d), generator=g, device=x.device)).to(torch.float16)
+    ix = b2.NativeIndex.ivf_flat(x, 4096, kmeans_iters=10)
+    sizes = ix.list_sizes()
+    assert int(sizes.sum()) == n and int(sizes.max()) < 12 * n // 4096     # balanced lists
+    dd, ii = ix.search(q, 10, n_probes=32)
+    torch.cuda.synchronize()
+    assert float((ii[:, 0] == rows).float().mean()) > 0.99
+    assert bool((dd[:, 1:] >= dd[:, :-1]).all())
+    flat = b2.NativeIndex.flat(x)
+    _, ti = flat.search(q, 10)
+    assert recall(ii.cpu(), ti.cpu()) > 0.98
+    # half of the lists probed (n_probes is capped at 2048): practically the exact search
+    d_all, i_all = ix.search(q[:64], 10, n_probes=2048)
+    _, t64 = flat.search(q[:64], 10)
+    assert recall(i_all.cpu(), t64.cpu()) > 0.995
+
+
+def test_config_c4_shard_full_size_recall(b2):
+    """C4, one of the 8 shards: IVF-PQ, 16384 lists, M = 64 x 8 bit, 12.5M x 128 fp16, k = 10,
+    64 probes + refine 4.  North-star criterion: recall@10 >= 0.95 against the exact search."""
+    _needs(20)
+    from oracle.ivf import recall
+    n, d, nq = 12_500_000, 128, 1000
+    x, g = _corpus(n, d, torch.float16, n_comp=16384, seed=99)
+    lab = torch.randint(0, n, (nq,), generator=g, device=x.device)
+    q = (x[lab].float() + 0.3 * torch.randn((nq, d), generator=g, device=x.device)).to(torch.float16)
+    ix = b2.NativeIndex.ivf_pq(x, 16384, 64, kmeans_iters=10, id_offset=1000)
+    info = ix.info()
+    assert (info.n_lists, info.pq_dim, info.pq_bits) == (16384, 64, 8)
+    dd, ii = ix.search(q, 10, n_probes=64, refine_ratio=4)
+    torch.cuda.synchronize()
+    flat = b2.NativeIndex.flat(x, id_offset=1000)
+    td, ti = flat.search(q, 10)
+    r = recall(ii.cpu(), ti.cpu())
+    assert r >= 0.95, r
+    assert bool((dd[:, 1:] >= dd[:, :-1]).all()) and int(ii.min()) >= 1000
+    # refined distances are exact for the ids they come with
+    same = ii == ti
+    assert torch.allclose(dd[same], td[same], rtol=2e-3, atol=2e-2)
