@@ -28,6 +28,10 @@ constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kListE = 4;  // warp-resident sorted list: 32 * 4 = 128 keys
 constexpr int kGroupRows = 128;  // query rows per grouped-scan work item (= the UMMA M extent)
+#ifndef B2VS_SKIP_PAD_ROWS
+#define B2VS_SKIP_PAD_ROWS 1
+#endif
+constexpr bool kSkipPaddingRows = B2VS_SKIP_PAD_ROWS != 0;   // gather kernels leave group-padding rows unwritten
 constexpr int kSeedSortMinQueries = 2048;  // below this the seed pass skips its ordering sort
 constexpr int kMaxProbes = 2048;  // coarse probe = exact top-n_probes (large-k path above 128)
 constexpr int kNormSlack = 256;  // slot_norm floats past the last slot (whole-tile beta loads)
@@ -679,6 +683,7 @@ __global__ void gather_group_queries_kernel(const uint32_t* __restrict__ row_ite
   const uint32_t item = row_item[v];
   const int q = item == kNoRow ? -1 : static_cast<int>(item / static_cast<uint32_t>(n_probes));
   if (lane == 0) row_query[v] = q;
+  if (kSkipPaddingRows && q < 0) return;   // never qualifies (threshold -inf): bytes are don't-care
   if (!split) {
     uint16_t* orow = out + static_cast<size_t>(v) * dp;
     for (int j = lane; j < dp; j += 32) {
@@ -1376,7 +1381,9 @@ __global__ void gather_group_residuals_kernel(const uint32_t* __restrict__ row_i
   const uint32_t item = row_item[v];
   uint16_t* orow = out + static_cast<size_t>(v) * dim;
   if (item == kNoRow) {
-    for (int j = lane; j < dim; j += 32) orow[j] = 0;
+    // group padding: the row never qualifies (threshold -inf); its operand bytes are don't-care
+    if (!kSkipPaddingRows)
+      for (int j = lane; j < dim; j += 32) orow[j] = 0;
     if (lane == 0) { row_query[v] = -1; row_bias[v] = 0.f; }
     return;
   }
