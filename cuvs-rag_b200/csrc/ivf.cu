@@ -72,7 +72,8 @@ struct IvfData {
   bool timing_pending = false;
   size_t owned_bytes() const {
     return centroids.bytes + offsets.bytes + sizes.bytes + row_ids.bytes + data.bytes +
-           slot_norm.bytes + codebooks.bytes + codes.bytes;
+           slot_norm.bytes + codebooks.bytes + codes.bytes + cb16.bytes + cbn.bytes + pq_norm.bytes +
+           rank_of_list.bytes + list_of_rank.bytes;
   }
   void destroy() {
     if (ev0) cudaEventDestroy(ev0);
