@@ -25,7 +25,7 @@ METRIC_L2, METRIC_IP = 0, 1
 F32, F16, BF16 = 0, 1, 2
 KIND_FLAT, KIND_IVF_FLAT, KIND_IVF_PQ = 0, 1, 2
 MAX_FUSED_K = 128
-MAX_K = 2048   # flat and IVF-Flat indexes, merges; IVF-PQ searches stay at MAX_FUSED_K
+MAX_K = 2048   # flat, IVF-Flat and (grouped-scan shapes) IVF-PQ indexes, merges
 
 _DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 _METRIC_CODE = {

@@ -1513,6 +1513,9 @@ static int grouped_override() {
 static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
                             const b2vs_search_params& sp, float* out_d, int64_t* out_i,
                             cudaStream_t st);
+static int ivf_pq_search_bigk(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
+                              const b2vs_search_params& sp, float* out_d, int64_t* out_i,
+                              cudaStream_t st);
 
 // Small batches are launch-bound (a Q = 1 search is ~20 tiny kernels), so when the item count is
 // small one CTA does the whole planning step: rank labels, shared-memory histogram, scan of the
@@ -1752,15 +1755,19 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
   int n_probes = sp.n_probes > 0 ? sp.n_probes : 20;
   n_probes = std::max(1, std::min(n_probes, std::min(d->n_lists, kMaxProbes)));
   int chunk = static_cast<int>(std::max<int64_t>(1024, kMaxItemsPerBatch / n_probes));
-  const bool bigk = k > kMaxFusedK;
+  // large k: k itself, or (IVF-PQ) the number of ADC candidates kept for the exact re-rank
+  const bool pq = index->kind == B2VS_KIND_IVF_PQ;
+  const bool pq_refine = pq && sp.refine_ratio > 1 && d->src_rows != nullptr;
+  const bool bigk = k > kMaxFusedK ||
+                    (pq_refine && d->pq_tc_ready && static_cast<int64_t>(k) * sp.refine_ratio > kMaxFusedK);
   if (bigk) {
-    B2VS_CHECK(index->kind == B2VS_KIND_IVF_FLAT && k <= kMaxBigK, B2VS_EUNSUP,
-               "k=%d: IVF-Flat serves k <= %d, IVF-PQ k <= %d", k, kMaxBigK, kMaxFusedK);
+    B2VS_CHECK(k <= kMaxBigK, B2VS_EUNSUP, "k=%d exceeds the large-k limit %d", k, kMaxBigK);
     chunk = std::min(chunk, 4096);   // 64 K-key candidate buffer per query
   }
   auto run = [&](const void* qq, int n, float* od, int64_t* oi) {
-    return bigk ? ivf_flat_search_bigk(index, qq, q_dtype, n, k, sp, od, oi, st)
-                : ivf_search_batch(index, qq, q_dtype, n, k, sp, od, oi, st);
+    if (!bigk) return ivf_search_batch(index, qq, q_dtype, n, k, sp, od, oi, st);
+    return pq ? ivf_pq_search_bigk(index, qq, q_dtype, n, k, sp, od, oi, st)
+              : ivf_flat_search_bigk(index, qq, q_dtype, n, k, sp, od, oi, st);
   };
   if (nq <= chunk) return run(q, nq, out_d, out_i);
   const size_t q_pitch = static_cast<size_t>(index->dim) * elem_bytes(q_dtype);
@@ -1772,6 +1779,185 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
     launches += d->stats.launches;
   }
   d->stats.launches = launches;   // the other fields describe the last sub-batch
+  return B2VS_OK;
+}
+
+// PQ counterpart of run_grouped_flat_scan: plan, gather the residual queries, decode + scan on
+// the tensor cores.  Thresholds / candidate buffers (ws_g_tau, ws_g_cand, ws_g_cnt) are the caller's.
+static int run_grouped_pq_scan(b2vs_index* index, IvfData* d, const long long* probe_ids, int n_probes,
+                               int nq, int cap, unsigned long long* counter, cudaStream_t st) {
+  const int items = nq * n_probes;
+  const int l2 = index->metric == B2VS_METRIC_L2 ? 1 : 0;
+  int chunk_rows = 0, slots = 1;
+  choose_work_split(index, d, items, &chunk_rows, &slots);
+  const int max_work = (items / kGroupRows + std::min(d->n_lists, items) + 1) * slots;
+  const int64_t rows_cap = static_cast<int64_t>(sorted_rows_cap(d, items, kGroupRows));
+  B2VS_TRY(d->ws_g_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16));
+  B2VS_TRY(d->ws_g_q.reserve(static_cast<size_t>(rows_cap) * index->dim * 2));
+  B2VS_TRY(d->ws_g_rowq.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
+  B2VS_TRY(d->ws_g_bias.reserve(static_cast<size_t>(rows_cap) * sizeof(float)));
+  int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
+  B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
+                             counter, st));
+  gather_group_residuals_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
+      d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists, probe_ids,
+      d->ws_qf.as<float>(), d->centroids.as<float>(), index->dim, d->dp, n_probes, l2,
+      d->ws_g_q.as<uint16_t>(), d->ws_g_rowq.as<int>(), d->ws_g_bias.as<float>());
+  B2VS_CUDA(cudaGetLastError());
+  PqGroupedScanArgs ga{};
+  ga.q_mat = d->ws_g_q.ptr; ga.q_rows = rows_cap;
+  ga.dim = index->dim; ga.pq_dim = d->pq_dim; ga.dsub = d->dsub;
+  ga.codes = d->codes.ptr;
+  ga.n_groups = static_cast<uint32_t>(std::max<int64_t>(d->n_slots, 32) >> 5);
+  ga.cb16 = d->cb16.ptr;
+  ga.beta = d->pq_norm.as<float>(); ga.alpha = l2 ? -2.f : -1.f;
+  ga.work = d->ws_g_work.ptr; ga.n_work = n_work; ga.max_work = max_work;
+  ga.row_query = d->ws_g_rowq.as<int>(); ga.row_bias = d->ws_g_bias.as<float>();
+  ga.tau = d->ws_g_tau.as<float>();
+  ga.cand = d->ws_g_cand.as<u64>(); ga.count = d->ws_g_cnt.as<int>(); ga.cap = cap;
+  return launch_pq_grouped_scan(index->dev, ga, st);
+}
+
+// Exact re-rank of up to 2048 candidates per query (one CTA per query): every warp scores
+// candidates against the caller's original rows, the CTA sorts them in shared memory.
+constexpr int kRefineBigThreads = 256;
+template <typename T>
+__global__ void __launch_bounds__(kRefineBigThreads)
+refine_big_kernel(const T* __restrict__ rows, int dim, const float* __restrict__ qf, int dp,
+                  const long long* __restrict__ cand, int k_in, int k_out, int metric,
+                  long long id_offset, float* __restrict__ out_d, long long* __restrict__ out_i) {
+  __shared__ u64 keys[2048];
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int P = 32;
+  while (P < k_in) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) keys[i] = kKeyInf;
+  __syncthreads();
+  const float* qv = qf + static_cast<size_t>(q) * dp;
+  for (int j = warp; j < k_in; j += kRefineBigThreads / 32) {
+    const long long row = cand[static_cast<size_t>(q) * k_in + j];
+    if (row < 0) continue;
+    const T* x = rows + static_cast<size_t>(row) * dim;
+    float acc = 0.f;
+    for (int t = lane; t < dim; t += 32) {
+      const float xv = ld_f32<T>(x + t);
+      if (metric == B2VS_METRIC_L2) { const float df = qv[t] - xv; acc = fmaf(df, df, acc); }
+      else acc = fmaf(-qv[t], xv, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) keys[j] = pack_key(acc, static_cast<uint32_t>(row));
+  }
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const u64 a = keys[lo], b = keys[hi];
+        if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < k_out; i += blockDim.x) {
+    const size_t o = static_cast<size_t>(q) * k_out + i;
+    const u64 key = i < P ? keys[i] : kKeyInf;
+    if (key == kKeyInf) {
+      out_d[o] = metric == B2VS_METRIC_L2 ? INFINITY : -INFINITY;
+      out_i[o] = -1;
+    } else {
+      const float sc = key_score(key);
+      out_d[o] = metric == B2VS_METRIC_L2 ? sc : -sc;
+      out_i[o] = static_cast<long long>(key_id(key)) + id_offset;
+    }
+  }
+}
+
+// IVF-PQ with k (or k * refine_ratio) above 128, up to 2048: the two-pass scheme of
+// ivf_flat_search_bigk on the decoded-tile scan, then (optionally) the exact re-rank.
+static int ivf_pq_search_bigk(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
+                              const b2vs_search_params& sp, float* out_d, int64_t* out_i,
+                              cudaStream_t st) {
+  IvfData* d = static_cast<IvfData*>(index->ivf);
+  B2VS_CHECK(d->pq_tc_ready, B2VS_EUNSUP,
+             "k > %d on this IVF-PQ shape needs the grouped scan (dsub 2/4/8, dim %% 64 == 0)", kMaxFusedK);
+  constexpr int kCapBig = 65536;
+  const bool refine = sp.refine_ratio > 1 && d->src_rows != nullptr;
+  const int k_scan = refine ? std::min(kMaxBigK, k * sp.refine_ratio) : k;
+  int n_probes = sp.n_probes > 0 ? sp.n_probes : 20;
+  n_probes = std::min(n_probes, std::min(d->n_lists, kMaxProbes));
+  const int max_size = std::max(32, d->max_list_rows);
+  B2VS_CHECK(max_size <= kCapBig, B2VS_EUNSUP, "a list of %d rows exceeds the large-k buffer", max_size);
+  const double mean_size = std::max(1.0, static_cast<double>(d->n) / d->n_lists);
+  int m = std::min(n_probes, static_cast<int>(std::ceil(3.0 * k_scan / mean_size)) + 1);
+  m = std::max(1, std::min(m, kCapBig / max_size));
+  const int q_pad = static_cast<int>(round_up(nq, 128));
+  B2VS_TRY(d->ws_probe_d.reserve(static_cast<size_t>(nq) * n_probes * sizeof(float)));
+  B2VS_TRY(d->ws_probe_i.reserve(static_cast<size_t>(nq) * n_probes * sizeof(int64_t)));
+  B2VS_TRY(d->ws_keys.reserve(static_cast<size_t>(nq) * m * sizeof(int64_t)));        // first m probes
+  B2VS_TRY(d->ws_qf.reserve(static_cast<size_t>(nq) * d->dp * sizeof(float)));
+  B2VS_TRY(d->ws_qnorm.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
+  B2VS_TRY(d->ws_counter.reserve(2 * sizeof(unsigned long long) + sizeof(int)));
+  B2VS_TRY(d->ws_g_tau.reserve(static_cast<size_t>(nq) * sizeof(float)));
+  B2VS_TRY(d->ws_g_cand.reserve(static_cast<size_t>(nq) * kCapBig * sizeof(u64)));
+  B2VS_TRY(d->ws_g_cnt.reserve(static_cast<size_t>(nq) * sizeof(int)));
+  B2VS_TRY(reserve_item_sort(d, nq * n_probes, kGroupRows));
+  B2VS_TRY(index->flat.search(q, q_dtype, nq, n_probes, 0, 0, d->ws_probe_d.as<float>(),
+                              d->ws_probe_i.as<int64_t>(), nullptr, st));
+  int launches = index->flat.stats.launches;
+  DISPATCH_DTYPE(q_dtype, T, (queries_to_f32_kernel<T><<<static_cast<unsigned>(ceil_div(nq, 4)), 128, 0, st>>>(
+                                 static_cast<const T*>(q), nq, index->dim, d->dp, d->fmt, 0,
+                                 d->ws_qf.as<float>(), d->ws_qnorm.as<float>())));
+  B2VS_CUDA(cudaGetLastError());
+  unsigned long long* counter = d->ws_counter.as<unsigned long long>();
+  int* overflow = reinterpret_cast<int*>(counter + 2);
+  B2VS_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned long long) + sizeof(int), st));
+  const long long* probe_ids = reinterpret_cast<const long long*>(d->ws_probe_i.ptr);
+  B2VS_CUDA(cudaMemcpy2DAsync(d->ws_keys.ptr, static_cast<size_t>(m) * sizeof(int64_t), probe_ids,
+                              static_cast<size_t>(n_probes) * sizeof(int64_t),
+                              static_cast<size_t>(m) * sizeof(int64_t), nq, cudaMemcpyDeviceToDevice, st));
+  fill_f32_kernel<<<static_cast<unsigned>(ceil_div(nq, 256)), 256, 0, st>>>(d->ws_g_tau.as<float>(), nq, INFINITY);
+  B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
+  B2VS_TRY(run_grouped_pq_scan(index, d, reinterpret_cast<const long long*>(d->ws_keys.ptr), m, nq,
+                               kCapBig, nullptr, st));
+  B2VS_TRY(launch_bigk_select(d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), kCapBig, nq, k_scan, 0,
+                              index->metric, nullptr, 0, d->ws_g_tau.as<float>(), nullptr, nullptr,
+                              nullptr, st));
+  B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
+  B2VS_TRY(run_grouped_pq_scan(index, d, probe_ids, n_probes, nq, kCapBig, counter, st));
+  if (!refine) {
+    B2VS_TRY(launch_bigk_select(d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), kCapBig, nq, k, 1,
+                                index->metric, nullptr, index->id_offset, nullptr, out_d, out_i,
+                                overflow, st, d->row_ids.as<uint32_t>()));
+  } else {
+    B2VS_TRY(d->ws_ref_d.reserve(static_cast<size_t>(nq) * k_scan * sizeof(float)));
+    B2VS_TRY(d->ws_ref_i.reserve(static_cast<size_t>(nq) * k_scan * sizeof(int64_t)));
+    B2VS_TRY(launch_bigk_select(d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), kCapBig, nq, k_scan, 1,
+                                index->metric, nullptr, 0, nullptr, d->ws_ref_d.as<float>(),
+                                d->ws_ref_i.as<int64_t>(), overflow, st, d->row_ids.as<uint32_t>()));
+    DISPATCH_DTYPE(index->dtype, T, (refine_big_kernel<T><<<nq, kRefineBigThreads, 0, st>>>(
+                                        static_cast<const T*>(d->src_rows), index->dim,
+                                        d->ws_qf.as<float>(), d->dp,
+                                        reinterpret_cast<const long long*>(d->ws_ref_i.ptr), k_scan, k,
+                                        index->metric, index->id_offset, out_d,
+                                        reinterpret_cast<long long*>(out_i))));
+    B2VS_CUDA(cudaGetLastError());
+  }
+  int h_over = 0;
+  B2VS_CUDA(cudaMemcpyAsync(&h_over, overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B2VS_CUDA(cudaStreamSynchronize(st));
+  B2VS_CHECK(h_over <= kCapBig, B2VS_EUNSUP,
+             "large-k IVF-PQ search: %d candidates under the seed threshold exceed the %d-key buffer",
+             h_over, kCapBig);
+  launches += 24;
+  d->stats = b2vs_search_stats{};
+  d->stats.launches = launches;
+  d->stats.n_splits = n_probes;
+  d->stats.grid = nq * n_probes;
+  d->stats.algo_flops = 2.0 * nq * static_cast<double>(d->n_lists) * index->dim;
+  d->counter_pending = true;
+  d->last_nq = nq;
+  d->timing_pending = false;
   return B2VS_OK;
 }
 
@@ -1879,18 +2065,9 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
     B2VS_TRY(reserve_item_sort(d, items, kGroupRows));
     const bool order_seeds = nq >= kSeedSortMinQueries;
     if (order_seeds) B2VS_TRY(sort_items_by_list(d, probe_ids, nq, n_probes, 1, st));
-    int chunk_rows = 0, slots = 1;
-    choose_work_split(index, d, items, &chunk_rows, &slots);
-    const int max_work = (items / kGroupRows + std::min(d->n_lists, items) + 1) * slots;
-    const int64_t rows_cap = static_cast<int64_t>(sorted_rows_cap(d, items, kGroupRows));
-    B2VS_TRY(d->ws_g_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16));
-    B2VS_TRY(d->ws_g_q.reserve(static_cast<size_t>(rows_cap) * index->dim * 2));
-    B2VS_TRY(d->ws_g_rowq.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
-    B2VS_TRY(d->ws_g_bias.reserve(static_cast<size_t>(rows_cap) * sizeof(float)));
     B2VS_TRY(d->ws_g_tau.reserve(static_cast<size_t>(nq) * sizeof(float)));
     B2VS_TRY(d->ws_g_cand.reserve(static_cast<size_t>(nq) * cap * sizeof(u64)));
     B2VS_TRY(d->ws_g_cnt.reserve(static_cast<size_t>(nq) * sizeof(int)));
-    int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
     B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
     const size_t lut_smem = (static_cast<size_t>(d->pq_dim) * 256 + index->dim) * sizeof(float);
     B2VS_CUDA(cudaFuncSetAttribute(ivf_pq_lut_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1901,32 +2078,14 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
         d->pq_dim, d->dsub, n_probes, k, index->metric, grouped_seed_rows(k), d->max_rhat2,
         order_seeds ? d->ws_item_perm.as<uint32_t>() : nullptr, nullptr, cap, d->ws_g_tau.as<float>(),
         nullptr);
-    B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
-                               counter, st));
-    gather_group_residuals_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
-        d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists, probe_ids, qf,
-        d->centroids.as<float>(), index->dim, d->dp, n_probes, l2, d->ws_g_q.as<uint16_t>(),
-        d->ws_g_rowq.as<int>(), d->ws_g_bias.as<float>());
-    B2VS_CUDA(cudaGetLastError());
-    PqGroupedScanArgs ga{};
-    ga.q_mat = d->ws_g_q.ptr; ga.q_rows = rows_cap;
-    ga.dim = index->dim; ga.pq_dim = d->pq_dim; ga.dsub = d->dsub;
-    ga.codes = d->codes.ptr;
-    ga.n_groups = static_cast<uint32_t>(std::max<int64_t>(d->n_slots, 32) >> 5);
-    ga.cb16 = d->cb16.ptr;
-    ga.beta = d->pq_norm.as<float>(); ga.alpha = alpha;
-    ga.work = d->ws_g_work.ptr; ga.n_work = n_work; ga.max_work = max_work;
-    ga.row_query = d->ws_g_rowq.as<int>(); ga.row_bias = d->ws_g_bias.as<float>();
-    ga.tau = d->ws_g_tau.as<float>();
-    ga.cand = d->ws_g_cand.as<u64>(); ga.count = d->ws_g_cnt.as<int>(); ga.cap = cap;
-    B2VS_TRY(launch_pq_grouped_scan(index->dev, ga, st));
+    B2VS_TRY(run_grouped_pq_scan(index, d, probe_ids, n_probes, nq, cap, counter, st));
     ivf_group_select_kernel<<<nq, kSelectThreads, static_cast<size_t>(cap) * sizeof(u64), st>>>(
-        ga.cand, ga.count, cap, k, d->ws_keys.as<u64>(), counter + 1);
+        d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), cap, k, d->ws_keys.as<u64>(), counter + 1);
     ivf_pq_lut_scan_kernel<<<nq, kScanThreads, lut_smem, st>>>(
         1, d->codes.as<uint8_t>(), d->row_ids.as<uint32_t>(), offs, probe_ids, qf,
         d->centroids.as<float>(), d->cb16.as<uint16_t>(), d->cbn.as<float>(), index->dim, d->dp,
-        d->pq_dim, d->dsub, n_probes, k, index->metric, 0u, d->max_rhat2, nullptr, ga.count, cap,
-        nullptr, d->ws_keys.as<u64>());
+        d->pq_dim, d->dsub, n_probes, k, index->metric, 0u, d->max_rhat2, nullptr, d->ws_g_cnt.as<int>(),
+        cap, nullptr, d->ws_keys.as<u64>());
     B2VS_CUDA(cudaGetLastError());
     launches += 16;
     single_list = true;

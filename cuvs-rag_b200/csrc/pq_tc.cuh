@@ -275,8 +275,15 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
       const size_t v_row = static_cast<size_t>(w.x) * kBM + ew * 32 + lane;
       const int query = __ldg(p.row_query + v_row);
       const float bias = query >= 0 ? __ldg(pp.row_bias + v_row) : 0.f;
-      // the threshold is on the full score (bias + alpha*acc + beta): compare the tile part
-      float tau = query >= 0 ? p.tau_init[query] - bias : -inf;
+      // The threshold is on the full score (bias + alpha*acc + beta); the tile part is compared
+      // against tau - bias, widened by a few ulps of the larger magnitude so that a key whose
+      // rounded sum (v + bias) lies at the threshold is never lost to the rounding of (tau - bias).
+      // A slightly larger candidate set is harmless: the select step is exact.
+      float tau = -inf;
+      if (query >= 0) {
+        const float tq = p.tau_init[query];
+        tau = (tq - bias) + 4.f * 1.1920929e-7f * fmaxf(fabsf(tq), fabsf(bias));
+      }
       const size_t qslot = static_cast<size_t>(max(query, 0));
       u64* const row_buf = p.big_cand + qslot * p.big_cap;
       int* const row_cnt = p.big_count + qslot;

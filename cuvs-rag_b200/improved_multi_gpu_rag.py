@@ -16,6 +16,8 @@ What changes for a caller, all of it deliberate:
     already contains the shard's part of the global top-k;
   * ``batch_search`` runs the whole list of queries as ONE batch per GPU instead of one thread
     per query (``:279-303``); the return value is still a list of per-query tuples;
+  * ``top_k = 2000`` (the default) is served by the large-k paths of the flat, IVF-Flat and IVF-PQ
+    indexes (IVF-PQ: sub-vector length 2/4/8 and dim % 64 == 0, else k <= 128);
   * ``FAISS_FLAT`` / ``FAISS_IVF`` map to the exact and IVF-Flat indexes; ``CAGRA`` is out of
     scope and raises; there is no CPU or simulated path here — without CUDA every build raises.
 """

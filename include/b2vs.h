@@ -68,7 +68,8 @@ typedef struct b2vs_ivf_params {
 typedef struct b2vs_search_params {
   int32_t n_probes;       /* IVF: lists scanned per query (cuVS SearchParams.n_probes, default 20);
                              clamped to min(n_lists, 2048) */
-  int32_t refine_ratio;   /* IVF-PQ: exact re-rank of min(128, refine_ratio*k) ADC candidates (0/1 = off) */
+  int32_t refine_ratio;   /* IVF-PQ: exact re-rank of min(2048, refine_ratio*k) ADC candidates (0/1 = off;
+                             min(128, ..) on shapes without the grouped scan) */
   int32_t n_splits;       /* flat: force the number of db splits (0 = heuristic) */
   int32_t flags;          /* bit 0: time the dominant kernel with CUDA events (see stats.kernel_ms) */
 } b2vs_search_params;
@@ -119,8 +120,9 @@ int b2vs_ivfpq_build(int dev, int metric, int dtype, int dim, const void* db, in
                      b2vs_index** out);
 
 /* k nearest rows for each of the nq queries ([nq, dim], `q_dtype`, device memory).
- * k <= 128 on every index kind (fused in-kernel top-k); flat and IVF-Flat indexes also serve
- * 128 < k <= 2048 (append + radix-select paths, which synchronise `stream`).
+ * k <= 128 on every index kind (fused in-kernel top-k); flat, IVF-Flat and (grouped-scan shapes:
+ * dsub 2/4/8, dim % 64 == 0) IVF-PQ indexes also serve 128 < k <= 2048 (append + radix-select
+ * paths, which synchronise `stream`).
  * out_d [nq, k] float32 and out_i [nq, k] int64 are caller-owned DEVICE buffers; missing
  * results are (inf | -inf, -1).  Asynchronous on `stream`.  `params` may be NULL. */
 int b2vs_search(b2vs_index* index, const void* queries, int q_dtype, int nq, int k,

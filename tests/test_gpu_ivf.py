@@ -345,5 +345,32 @@ def test_ivf_flat_large_k(b2, dtype, metric, k):
     d2, i2 = ix.search(q, k, n_probes=8)          # subset of the lists: still k results, sorted
     assert int((i2 >= 0).sum()) > 0.9 * i2.numel()
     pq = b2.NativeIndex.ivf_pq(x, 32, 24, metric=metric)
-    with pytest.raises(RuntimeError, match="IVF-PQ k <="):
-        pq.search(q, k)
+    with pytest.raises(RuntimeError, match="needs the grouped scan"):
+        pq.search(q, k)                               # dim 96 is not a multiple of 64
+
+
+@pytest.mark.parametrize("metric", ["sqeuclidean", "inner_product"])
+def test_ivf_pq_large_k_and_deep_refine(b2, metric):
+    """IVF-PQ beyond the fused limit: k = 500 ADC results, and k = 100 refined from 400 candidates
+    (k * refine_ratio > 128 takes the large-k path instead of being clamped to 128)."""
+    from oracle.exact import exact_knn
+    from oracle.ivf import recall
+    x = clustered(40000, 128, 50, 93).to(torch.float16)
+    q = queries_from(x.float(), 150, 94).to(torch.float16)
+    ix = b2.NativeIndex.ivf_pq(x.cuda(), 32, 64, metric=metric, id_offset=4, kmeans_iters=8)
+    _, t500 = exact_knn(x.float(), q.float(), 500, metric)
+    dd, ii = ix.search(q.cuda(), 500, n_probes=32)
+    torch.cuda.synchronize()
+    assert ii.shape == (150, 500) and int(ii.min()) >= 4
+    srt = dd[:, 1:] >= dd[:, :-1] if metric == "sqeuclidean" else dd[:, 1:] <= dd[:, :-1]
+    assert bool(srt.all())
+    assert recall((ii - 4).cpu(), t500) > 0.8             # ADC ordering of the true top-500
+    d1, i1 = ix.search(q.cuda(), 100, n_probes=32, refine_ratio=4)    # 400 candidates re-ranked
+    d0, i0 = ix.search(q.cuda(), 100, n_probes=32, refine_ratio=1)
+    _, t100 = exact_knn(x.float(), q.float(), 100, metric)
+    r1, r0 = recall((i1 - 4).cpu(), t100), recall((i0 - 4).cpu(), t100)
+    assert r1 > 0.97 and r1 > r0 + 0.02, (r0, r1)
+    xs, qs = x.float(), q.float()
+    g = (i1 - 4).cpu().clamp_min(0)
+    true = ((xs[g] - qs[:, None, :]) ** 2).sum(2) if metric == "sqeuclidean" else (xs[g] * qs[:, None, :]).sum(2)
+    assert torch.allclose(d1.cpu(), true, rtol=2e-3, atol=2e-2)
