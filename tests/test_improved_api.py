@@ -74,7 +74,7 @@ def test_golden_host_merge_through_the_gpu_merge_kernel(gold):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("itype,k", [("FAISS_FLAT", 2000), ("IVF_FLAT", 2000), ("IVF_FLAT", 10),
-                                     ("IVF_PQ", 10)])
+                                     ("IVF_PQ", 10), ("IVF_PQ", 2000)])
 def test_builder_and_engine_end_to_end(itype, k):
     from oracle.exact import exact_knn
     g = torch.Generator().manual_seed(3)
