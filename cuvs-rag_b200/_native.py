@@ -25,6 +25,7 @@ METRIC_L2, METRIC_IP = 0, 1
 F32, F16, BF16 = 0, 1, 2
 KIND_FLAT, KIND_IVF_FLAT, KIND_IVF_PQ = 0, 1, 2
 MAX_FUSED_K = 128
+FLAG_TIME_KERNEL, FLAG_TC_SINGLE, FLAG_TC_PAIR, FLAG_GRAPH = 1, 2, 4, 8   # b2vs_search_params.flags
 MAX_K = 2048   # flat, IVF-Flat and (grouped-scan shapes) IVF-PQ indexes, merges
 
 _DTYPE_CODE = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
@@ -255,9 +256,12 @@ class NativeIndex:
     # ------------------------------------------------------------------ search
     def search(self, queries: torch.Tensor, k: int, n_probes: int = 0, refine_ratio: int = 0,
                n_splits: int = 0, stream: Optional[torch.cuda.Stream] = None,
-               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, time_kernel: bool = False
-               ) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Device-resident search: returns (distances f32 [Q,k], ids i64 [Q,k]) on this GPU."""
+               out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, time_kernel: bool = False,
+               graph: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Device-resident search: returns (distances f32 [Q,k], ids i64 [Q,k]) on this GPU.
+        ``graph=True`` (IVF indexes, Q <= 64, k <= 128) replays the call as one CUDA graph from
+        the second call of a (Q, k, dtype, n_probes, refine_ratio) signature on
+        (``B2VS_FLAG_GRAPH``): the interactive single-query case is launch-bound."""
         if self._h.value is None:
             raise RuntimeError("index has been destroyed")
         _require_cuda_matrix(queries, "queries")
@@ -269,7 +273,8 @@ class NativeIndex:
             i = torch.empty((nq, k), dtype=torch.int64, device=self.device)
         else:
             d, i = out
-        sp = SearchParams(int(n_probes), int(refine_ratio), int(n_splits), 1 if time_kernel else 0)
+        sp = SearchParams(int(n_probes), int(refine_ratio), int(n_splits),
+                          (FLAG_TIME_KERNEL if time_kernel else 0) | (FLAG_GRAPH if graph else 0))
         _check(lib().b2vs_search(self._h, queries.data_ptr(), dtype_code(queries.dtype), nq, int(k),
                                  ctypes.byref(sp), d.data_ptr(), i.data_ptr(),
                                  _stream_ptr(self.device, stream)), "b2vs_search")

@@ -1,4 +1,5 @@
 // C ABI entry points (include/b2vs.h): error state, flat index, dispatch, host-buffer search.
+#include <atomic>
 #include <cstring>
 #include <new>
 
@@ -15,6 +16,10 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<uint64_t> g_realloc_generation{1};
+uint64_t realloc_generation() { return g_realloc_generation.load(std::memory_order_acquire); }
+void note_realloc() { g_realloc_generation.fetch_add(1, std::memory_order_acq_rel); }
 
 static bool valid_dtype(int d) { return d == B2VS_F32 || d == B2VS_F16 || d == B2VS_BF16; }
 static bool valid_metric(int m) { return m == B2VS_METRIC_L2 || m == B2VS_METRIC_IP; }

@@ -52,12 +52,18 @@ struct DeviceGuard {
   }
 };
 
+// Bumped whenever a DevBuf frees or replaces its allocation: a captured CUDA graph of a search
+// holds workspace pointers and is only replayed while this value is the one it was captured at.
+uint64_t realloc_generation();
+void note_realloc();
+
 // Growable device buffer (grow-only; steady-state searches allocate nothing).
 struct DevBuf {
   void* ptr = nullptr;
   size_t bytes = 0;
   int reserve(size_t need) {
     if (need <= bytes) return B2VS_OK;
+    note_realloc();
     if (ptr) { cudaFree(ptr); ptr = nullptr; bytes = 0; }
     size_t want = need + need / 8;
     cudaError_t e = cudaMalloc(&ptr, want);
@@ -76,7 +82,7 @@ struct DevBuf {
     return B2VS_OK;
   }
   void release() {
-    if (ptr) cudaFree(ptr);
+    if (ptr) { note_realloc(); cudaFree(ptr); }
     ptr = nullptr;
     bytes = 0;
   }

@@ -36,6 +36,29 @@ constexpr int kSeedSortMinQueries = 2048;  // below this the seed pass skips its
 constexpr int kMaxProbes = 2048;  // coarse probe = exact top-n_probes (large-k path above 128)
 constexpr int kNormSlack = 256;  // slot_norm floats past the last slot (whole-tile beta loads)
 
+// A small-batch search replayed as one CUDA graph (the Q <= 64 path is ~15-20 tiny kernels and
+// launch-bound).  The graph is captured against library-owned staging buffers, so a replay is
+// copy-in, graph launch, two copies out, whatever pointers the caller passes.
+struct SearchGraph {
+  int nq = 0, k = 0, q_dtype = 0, n_probes = 0, refine_ratio = 0, flags = 0;
+  int seen = 0;              // direct (un-captured) calls with this signature so far
+  bool failed = false;       // capture was refused once: stay on the direct path
+  uint64_t generation = 0;   // realloc_generation() at capture time
+  uint64_t last_use = 0;
+  cudaGraphExec_t exec = nullptr;
+  char* io = nullptr;        // staging: queries | distances | ids
+  size_t q_bytes = 0, d_off = 0, i_off = 0;
+  b2vs_search_stats stats{};
+  void destroy() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (io) cudaFree(io);
+    exec = nullptr;
+    io = nullptr;
+  }
+};
+constexpr int kGraphMaxQueries = 64;   // larger batches are no longer launch-bound
+constexpr int kGraphMaxEntries = 16;
+
 struct IvfData {
   int n_lists = 0, pq_dim = 0, pq_bits = 0, dsub = 0, mp = 0;  // mp = pq_dim padded to 16
   int dp = 0;       // dim padded to 8 (16-bit storage pitch)
@@ -70,6 +93,9 @@ struct IvfData {
   int row_bytes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timing_pending = false;
+  std::vector<SearchGraph> graphs;      // captured small-batch searches (see ivf_search)
+  cudaStream_t cap_stream = nullptr;    // capture happens here: the caller's stream may be the legacy one
+  uint64_t graph_clock = 0;
   size_t owned_bytes() const {
     return centroids.bytes + offsets.bytes + sizes.bytes + row_ids.bytes + data.bytes +
            slot_norm.bytes + codebooks.bytes + codes.bytes + cb16.bytes + cbn.bytes + pq_norm.bytes +
@@ -79,6 +105,10 @@ struct IvfData {
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     ev0 = ev1 = nullptr;
+    for (SearchGraph& g : graphs) g.destroy();
+    graphs.clear();
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+    cap_stream = nullptr;
     for (DevBuf* b : {&centroids, &offsets, &sizes, &row_ids, &data, &slot_norm, &codebooks, &codes,
                       &rank_of_list, &list_of_rank,
                       &ws_probe_d, &ws_probe_i, &ws_keys, &ws_qf, &ws_qnorm, &ws_counter,
@@ -1748,18 +1778,24 @@ static int ivf_flat_search_bigk(b2vs_index* index, const void* q, int q_dtype, i
 // index dimension), so very large batches run as consecutive sub-batches.
 constexpr int64_t kMaxItemsPerBatch = 4 << 20;
 
-int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
-               const b2vs_search_params& sp, float* out_d, int64_t* out_i, cudaStream_t st) {
+// large k: k itself, or (IVF-PQ) the number of ADC candidates kept for the exact re-rank
+static bool uses_bigk_path(const b2vs_index* index, const IvfData* d, int k, const b2vs_search_params& sp) {
+  const bool pq = index->kind == B2VS_KIND_IVF_PQ;
+  const bool pq_refine = pq && sp.refine_ratio > 1 && d->src_rows != nullptr;
+  return k > kMaxFusedK ||
+         (pq_refine && d->pq_tc_ready && static_cast<int64_t>(k) * sp.refine_ratio > kMaxFusedK);
+}
+
+static int ivf_search_direct(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
+                             const b2vs_search_params& sp, float* out_d, int64_t* out_i,
+                             cudaStream_t st) {
   IvfData* d = static_cast<IvfData*>(index->ivf);
   B2VS_CHECK(d != nullptr, B2VS_EINVAL, "IVF index has no list data");
   int n_probes = sp.n_probes > 0 ? sp.n_probes : 20;
   n_probes = std::max(1, std::min(n_probes, std::min(d->n_lists, kMaxProbes)));
   int chunk = static_cast<int>(std::max<int64_t>(1024, kMaxItemsPerBatch / n_probes));
-  // large k: k itself, or (IVF-PQ) the number of ADC candidates kept for the exact re-rank
   const bool pq = index->kind == B2VS_KIND_IVF_PQ;
-  const bool pq_refine = pq && sp.refine_ratio > 1 && d->src_rows != nullptr;
-  const bool bigk = k > kMaxFusedK ||
-                    (pq_refine && d->pq_tc_ready && static_cast<int64_t>(k) * sp.refine_ratio > kMaxFusedK);
+  const bool bigk = uses_bigk_path(index, d, k, sp);
   if (bigk) {
     B2VS_CHECK(k <= kMaxBigK, B2VS_EUNSUP, "k=%d exceeds the large-k limit %d", k, kMaxBigK);
     chunk = std::min(chunk, 4096);   // 64 K-key candidate buffer per query
@@ -2155,6 +2191,134 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
   d->last_nq = nq;
   d->timing_pending = timed;
   return B2VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Small batches as one CUDA graph.  B2VS_GRAPH=1 enables it for every eligible call, =0 disables
+// it even when a call asks with B2VS_FLAG_GRAPH; unset = only calls that set the flag.
+static int graph_override() {
+  static const int v = [] {
+    const char* e = std::getenv("B2VS_GRAPH");
+    return e ? (e[0] == '0' ? 0 : 1) : -1;
+  }();
+  return v;
+}
+
+static void drop_graph_error() { cudaGetLastError(); }
+
+// Replays (capturing first if needed) the search of this signature.  *handled = false means the
+// caller must run the direct path (first sighting of the signature, or capture was refused).
+static int ivf_search_graphed(b2vs_index* index, IvfData* d, const void* q, int q_dtype, int nq, int k,
+                              const b2vs_search_params& sp, float* out_d, int64_t* out_i,
+                              cudaStream_t st, bool* handled) {
+  *handled = false;
+  const int flags = sp.flags & ~B2VS_FLAG_GRAPH;
+  SearchGraph* g = nullptr;
+  for (SearchGraph& e : d->graphs)
+    if (e.nq == nq && e.k == k && e.q_dtype == q_dtype && e.n_probes == sp.n_probes &&
+        e.refine_ratio == sp.refine_ratio && e.flags == flags) { g = &e; break; }
+  if (!g) {
+    if (static_cast<int>(d->graphs.size()) >= kGraphMaxEntries) {
+      size_t victim = 0;
+      for (size_t i = 1; i < d->graphs.size(); ++i)
+        if (d->graphs[i].last_use < d->graphs[victim].last_use) victim = i;
+      // the victim's graph may still be running on the caller's stream
+      if (d->graphs[victim].exec) cudaStreamSynchronize(st);
+      d->graphs[victim].destroy();
+      d->graphs.erase(d->graphs.begin() + static_cast<long>(victim));
+    }
+    d->graphs.emplace_back();
+    g = &d->graphs.back();
+    g->nq = nq; g->k = k; g->q_dtype = q_dtype; g->n_probes = sp.n_probes;
+    g->refine_ratio = sp.refine_ratio; g->flags = flags;
+  }
+  g->last_use = ++d->graph_clock;
+  if (g->failed) return B2VS_OK;
+  if (g->exec && g->generation != realloc_generation()) {
+    // some workspace moved since the capture: the graph's pointers may be stale
+    cudaStreamSynchronize(st);
+    cudaGraphExecDestroy(g->exec);
+    g->exec = nullptr;
+  }
+  if (!g->exec) {
+    // the first call of a signature runs directly and sizes every workspace, so that the
+    // capture below allocates nothing
+    if (g->seen++ == 0) return B2VS_OK;
+    if (!d->cap_stream)
+      B2VS_CUDA(cudaStreamCreateWithFlags(&d->cap_stream, cudaStreamNonBlocking));
+    if (!g->io) {
+      g->q_bytes = static_cast<size_t>(nq) * index->dim * elem_bytes(q_dtype);
+      g->d_off = static_cast<size_t>(round_up(static_cast<int64_t>(g->q_bytes), 256));
+      g->i_off = g->d_off + static_cast<size_t>(round_up(static_cast<int64_t>(nq) * k * sizeof(float), 256));
+      void* p = nullptr;
+      if (cudaMalloc(&p, g->i_off + static_cast<size_t>(nq) * k * sizeof(int64_t)) != cudaSuccess) {
+        drop_graph_error();
+        g->failed = true;
+        return B2VS_OK;
+      }
+      g->io = static_cast<char*>(p);
+    }
+    b2vs_search_params spd = sp;
+    spd.flags = flags;
+    const uint64_t gen0 = realloc_generation();
+    if (cudaStreamBeginCapture(d->cap_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+      drop_graph_error();
+      g->failed = true;
+      return B2VS_OK;
+    }
+    const int rc = ivf_search_direct(index, g->io, q_dtype, nq, k, spd,
+                                     reinterpret_cast<float*>(g->io + g->d_off),
+                                     reinterpret_cast<int64_t*>(g->io + g->i_off), d->cap_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e_end = cudaStreamEndCapture(d->cap_stream, &graph);
+    size_t n_nodes = 0;
+    bool ok = rc == B2VS_OK && e_end == cudaSuccess && graph != nullptr &&
+              gen0 == realloc_generation() &&
+              cudaGraphGetNodes(graph, nullptr, &n_nodes) == cudaSuccess &&
+              cudaGraphInstantiate(&g->exec, graph, 0ull) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      drop_graph_error();
+      if (g->exec) cudaGraphExecDestroy(g->exec);
+      g->exec = nullptr;
+      // a workspace grew under the capture (another signature's sizes): try again next call;
+      // anything else is a refusal
+      if (gen0 == realloc_generation()) g->failed = true;
+      return B2VS_OK;
+    }
+    g->generation = gen0;
+    g->stats = d->stats;
+    g->stats.launches = static_cast<int32_t>(n_nodes);
+  }
+  B2VS_CUDA(cudaMemcpyAsync(g->io, q, g->q_bytes, cudaMemcpyDeviceToDevice, st));
+  B2VS_CUDA(cudaGraphLaunch(g->exec, st));
+  B2VS_CUDA(cudaMemcpyAsync(out_d, g->io + g->d_off, static_cast<size_t>(nq) * k * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
+  B2VS_CUDA(cudaMemcpyAsync(out_i, g->io + g->i_off, static_cast<size_t>(nq) * k * sizeof(int64_t),
+                            cudaMemcpyDeviceToDevice, st));
+  d->stats = g->stats;
+  d->counter_pending = true;
+  d->last_nq = nq;
+  d->timing_pending = false;
+  *handled = true;
+  return B2VS_OK;
+}
+
+int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
+               const b2vs_search_params& sp, float* out_d, int64_t* out_i, cudaStream_t st) {
+  IvfData* d = static_cast<IvfData*>(index->ivf);
+  B2VS_CHECK(d != nullptr, B2VS_EINVAL, "IVF index has no list data");
+  const int ov = graph_override();
+  const bool want_graph = ov == 1 || (ov < 0 && (sp.flags & B2VS_FLAG_GRAPH) != 0);
+  if (want_graph && nq <= kGraphMaxQueries && k >= 1 && (sp.flags & B2VS_FLAG_TIME_KERNEL) == 0 &&
+      !uses_bigk_path(index, d, k, sp)) {
+    bool handled = false;
+    B2VS_TRY(ivf_search_graphed(index, d, q, q_dtype, nq, k, sp, out_d, out_i, st, &handled));
+    if (handled) return B2VS_OK;
+  }
+  b2vs_search_params spd = sp;
+  spd.flags &= ~B2VS_FLAG_GRAPH;
+  return ivf_search_direct(index, q, q_dtype, nq, k, spd, out_d, out_i, st);
 }
 
 void ivf_fill_info(const b2vs_index* index, b2vs_index_info* info) {

@@ -221,7 +221,8 @@ class SearchResultAggregator:
                     q = q.contiguous()
                 d, i = index.search(q, k_local,
                                     n_probes=int(params.get("n_probes", params.get("nprobe", 0)) or 0),
-                                    refine_ratio=int(params.get("refine_ratio", 0) or 0))
+                                    refine_ratio=int(params.get("refine_ratio", 0) or 0),
+                                    graph=bool(params.get("graph", False)))
                 return d, i, time.time() - t0, True
             if CUVS_AVAILABLE and torch.cuda.is_available():
                 raise TypeError(f"index for GPU {gpu_id} is {type(index).__name__}, not a native "

@@ -374,3 +374,44 @@ def test_ivf_pq_large_k_and_deep_refine(b2, metric):
     g = (i1 - 4).cpu().clamp_min(0)
     true = ((xs[g] - qs[:, None, :]) ** 2).sum(2) if metric == "sqeuclidean" else (xs[g] * qs[:, None, :]).sum(2)
     assert torch.allclose(d1.cpu(), true, rtol=2e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("kind", ["flat", "pq"])
+def test_small_batch_cuda_graph_replay_equals_direct_search(b2, kind):
+    """B2VS_FLAG_GRAPH: from the second call of a signature on the search is one captured CUDA
+    graph replayed against staging buffers; answers must be those of the direct launches, for
+    fresh query / output tensors on every call, and must survive a workspace re-allocation
+    caused by a larger batch in between (stale-pointer guard)."""
+    n, d, nlist = 40000, 64, 64
+    x = clustered(n, d, 100, 21).to(torch.float16).cuda()
+    if kind == "flat":
+        ix = b2.NativeIndex.ivf_flat(x, nlist, kmeans_iters=5, id_offset=5)
+        kw = dict(n_probes=8)
+    else:
+        ix = b2.NativeIndex.ivf_pq(x, nlist, 32, kmeans_iters=5, id_offset=5)
+        kw = dict(n_probes=8, refine_ratio=4)
+    for nq in (1, 3, 64):
+        qs = [queries_from(x.float().cpu(), nq, 30 + t).to(torch.float16).cuda() for t in range(4)]
+        want = [tuple(t.clone() for t in ix.search(q, 10, **kw)) for q in qs]
+        got = [tuple(t.clone() for t in ix.search(q, 10, graph=True, **kw)) for q in qs]
+        torch.cuda.synchronize()
+        for (wd, wi), (gd, gi) in zip(want, got):
+            assert torch.equal(wi, gi)
+            assert torch.allclose(wd, gd, rtol=1e-6, atol=0)
+        assert ix.last_stats().launches > 0   # nodes of the captured graph
+    # a larger batch grows the workspaces; the cached graphs must notice and re-capture
+    q1 = queries_from(x.float().cpu(), 1, 77).to(torch.float16).cuda()
+    wd, wi = (t.clone() for t in ix.search(q1, 10, **kw))
+    big = queries_from(x.float().cpu(), 3000, 78).to(torch.float16).cuda()
+    ix.search(big, 10, **kw)
+    for _ in range(3):
+        gd, gi = ix.search(q1, 10, graph=True, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(wi, gi) and torch.allclose(wd, gd, rtol=1e-6, atol=0)
+    # searches on a side stream replay the same graph
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        sd, si = ix.search(q1, 10, graph=True, stream=s, **kw)
+    s.synchronize()
+    assert torch.equal(wi, si) and torch.allclose(wd, sd, rtol=1e-6, atol=0)

@@ -5,6 +5,7 @@ import torch
 import cuvs_rag_b200 as b2
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "flat"
+use_graph = len(sys.argv) > 2 and sys.argv[2] == "graph"   # also time B2VS_FLAG_GRAPH on Q <= 64
 n, d, nlist, nprobe = 10_000_000, 768, 4096, 32
 if kind == "pq":
     n, d, nlist, nprobe = 12_500_000, 128, 16384, 64
@@ -18,16 +19,22 @@ for s in range(0, n, 1 << 19):
     x[s:e] = (cent[lab] + 0.42 * torch.randn((e - s, d), generator=g, device=dev)).to(torch.float16)
 ix = (b2.NativeIndex.ivf_flat(x, nlist, kmeans_iters=10) if kind == "flat"
       else b2.NativeIndex.ivf_pq(x, nlist, 64, kmeans_iters=10))
-for nq in [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024]:
+sizes = [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024]
+if len(sys.argv) > 3:
+    sizes = [int(v) for v in sys.argv[3].split(",")]
+rr = 4 if kind == "pq" else 0
+for nq in sizes:
     qi = torch.randint(0, n, (nq,), generator=g, device=dev)
     q = (x[qi].float() + 0.1 * torch.randn((nq, d), generator=g, device=dev)).to(torch.float16)
-    for _ in range(3):
-        ix.search(q, 20, n_probes=nprobe, refine_ratio=4 if kind == "pq" else 0)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(20):
-        ix.search(q, 20, n_probes=nprobe, refine_ratio=4 if kind == "pq" else 0)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 20
-    print(json.dumps({"kind": kind, "Q": nq, "ms": round(ms, 4), "qps": round(nq / ms * 1e3)}), flush=True)
+    for graph in ([False, True] if use_graph and nq <= 64 else [False]):
+        for _ in range(3):
+            ix.search(q, 20, n_probes=nprobe, refine_ratio=rr, graph=graph)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            ix.search(q, 20, n_probes=nprobe, refine_ratio=rr, graph=graph)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 50
+        print(json.dumps({"kind": kind, "graph": graph, "Q": nq, "ms": round(ms, 4),
+                          "qps": round(nq / ms * 1e3), "nodes": ix.last_stats().launches}), flush=True)
