@@ -31,8 +31,10 @@ index_building_coordinator = _load("index_building_coordinator")
 search_result_aggregator = _load("search_result_aggregator")
 evaluation = _load("evaluation")
 improved_multi_gpu_rag = _load("improved_multi_gpu_rag")
+encoder_handoff = _load("encoder_handoff")
 
-from _native import NativeIndex, merge_topk, kmeans_fit, build as build_native  # noqa: E402
+from _native import NativeIndex, merge_topk, kmeans_fit, pool_normalize, build as build_native  # noqa: E402
+from encoder_handoff import QueryEncoderHandoff, embed_queries, last_token_pool  # noqa: E402
 from gpu_resource_manager import GPUResourceManager, GPUConfig, MultiGPUConfig, partition_even  # noqa: E402
 from embedding_distribution_manager import (  # noqa: E402
     EmbeddingDistributionManager, EmbeddingPart, DistributedEmbeddings)
@@ -54,4 +56,5 @@ __all__ = [
     "combine_search_results", "filter_search_results_by_distance",
     "RecallEvaluator", "recall_at_k",
     "IndexType", "ParallelIndexBuilder", "ParallelSearchEngine", "CUDAMemoryManager",
+    "pool_normalize", "QueryEncoderHandoff", "embed_queries", "last_token_pool",
 ]

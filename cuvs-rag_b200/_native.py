@@ -19,7 +19,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("B2VS_LIB_PATH") or os.path.join(_HERE, "libb2vs.so")
-SOURCES = ["api.cu", "flat.cu", "merge.cu", "ivf.cu", "bigk.cu", "pq_tc.cu"]
+SOURCES = ["api.cu", "flat.cu", "merge.cu", "ivf.cu", "bigk.cu", "pq_tc.cu", "encode.cu"]
 
 METRIC_L2, METRIC_IP = 0, 1
 F32, F16, BF16 = 0, 1, 2
@@ -67,7 +67,7 @@ EXPORTS = [
     "b2vs_ivfflat_build", "b2vs_ivfpq_build", "b2vs_search", "b2vs_search_host",
     "b2vs_merge_topk", "b2vs_kmeans_fit", "b2vs_index_info_get", "b2vs_index_last_stats",
     "b2vs_ivf_list_sizes_host", "b2vs_ivf_centroids_host", "b2vs_index_destroy",
-    "b2vs_index_save", "b2vs_index_load",
+    "b2vs_index_save", "b2vs_index_load", "b2vs_pool_normalize",
 ]
 
 _lib = None
@@ -136,6 +136,7 @@ def lib() -> ctypes.CDLL:
         L.b2vs_index_destroy.argtypes = [vp]
         L.b2vs_index_save.argtypes = [vp, ctypes.c_char_p]
         L.b2vs_index_load.argtypes = [i32, ctypes.c_char_p, vp, i64, vp, ctypes.POINTER(vp)]
+        L.b2vs_pool_normalize.argtypes = [i32, i32, vp, i32, i32, i32, vp, i32, i32, i32, vp, vp]
         for name in EXPORTS:
             if name != "b2vs_last_error":
                 getattr(L, name).restype = i32
@@ -369,6 +370,44 @@ def kmeans_fit(x: torch.Tensor, n_clusters: int, iters: int = 20, seed: int = 0,
                                  cent.data_ptr(), labels.data_ptr(), _stream_ptr(x.device, stream)),
            "b2vs_kmeans_fit")
     return cent, labels
+
+
+POOL_LAST_TOKEN, POOL_MEAN = 0, 1
+_POOLING_CODE = {"last_token": POOL_LAST_TOKEN, "last": POOL_LAST_TOKEN, "mean": POOL_MEAN}
+
+
+def pool_normalize(hidden: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                   pooling: str = "last_token", normalize: bool = True,
+                   out_dtype: Optional[torch.dtype] = None,
+                   stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+    """Encoder hand-off (``b2vs_pool_normalize``): hidden states [B, T, D] on a GPU -> pooled,
+    L2-normalised query rows [B, D] on the same GPU in ``out_dtype`` (default: the hidden states'
+    dtype).  ``pooling="last_token"`` follows the reference's ``last_token_pool``
+    (generate_embeddings.py:11-21), ``"mean"`` is the sentence-transformers masked mean."""
+    if not isinstance(hidden, torch.Tensor) or hidden.dim() != 3:
+        raise ValueError("hidden must be a 3D tensor [batch, seq_len, dim]")
+    if not hidden.is_cuda:
+        raise ValueError("pool_normalize runs on the GPU; hidden states must be CUDA tensors")
+    try:
+        mode = _POOLING_CODE[pooling]
+    except KeyError:
+        raise ValueError(f"unknown pooling {pooling!r}; expected 'last_token' or 'mean'")
+    hidden = hidden.contiguous()
+    b, t, d = hidden.shape
+    if b == 0 or t == 0 or d == 0:
+        raise ValueError(f"hidden has an empty dimension: {tuple(hidden.shape)}")
+    mask_ptr = None
+    if attention_mask is not None:
+        if tuple(attention_mask.shape) != (b, t):
+            raise ValueError(f"attention_mask shape {tuple(attention_mask.shape)} != ({b}, {t})")
+        attention_mask = attention_mask.to(device=hidden.device, dtype=torch.int64).contiguous()
+        mask_ptr = attention_mask.data_ptr()
+    out = torch.empty((b, d), dtype=out_dtype or hidden.dtype, device=hidden.device)
+    _check(lib().b2vs_pool_normalize(hidden.device.index, dtype_code(hidden.dtype), hidden.data_ptr(),
+                                     b, t, d, mask_ptr, mode, 1 if normalize else 0,
+                                     dtype_code(out.dtype), out.data_ptr(),
+                                     _stream_ptr(hidden.device, stream)), "b2vs_pool_normalize")
+    return out
 
 
 def device_count() -> int:

@@ -168,6 +168,22 @@ int b2vs_index_save(const b2vs_index* index, const char* path);
 int b2vs_index_load(int dev, const char* path, const void* rows_for_refine, int64_t id_offset,
                     void* stream, b2vs_index** out);
 
+/* Encoder hand-off: pooled (and L2-normalised) query rows from a bi-encoder's hidden states,
+ * on the device, in the dtype the index wants -- replaces last_token_pool + F.normalize +
+ * `.cpu().numpy()` of Latest/cuVS-2-gpu/old/generate_embeddings.py:11-21, :100-105 (and the
+ * `.to(device)` before the search in cuvs-2gpu-main.ipynb cell 16).
+ * hidden [batch, seq_len, dim] `dtype` row-major device; attention_mask [batch, seq_len] int64 device
+ * or NULL (= all ones); out [batch, dim] `out_dtype` device.  pooling: LAST_TOKEN follows the
+ * reference (left-padding test on the mask's last column, else row sum - 1 with python's negative
+ * index wrap); MEAN is the sentence-transformers masked mean (prepare_dataset.py:149).
+ * normalize != 0: x / max(||x||_2, 1e-12).  Arithmetic in fp32.  Asynchronous on `stream`; the
+ * scratch is per calling thread, so one call at a time per thread. */
+#define B2VS_POOL_LAST_TOKEN 0
+#define B2VS_POOL_MEAN 1
+int b2vs_pool_normalize(int dev, int dtype, const void* hidden, int batch, int seq_len, int dim,
+                        const int64_t* attention_mask, int pooling, int normalize, int out_dtype,
+                        void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

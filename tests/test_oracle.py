@@ -134,3 +134,28 @@ def test_ivf_pq_oracle_recall_reasonable():
     td, ti = exact.exact_knn(x, q, 10)
     d, i = o.search(q, 10, n_probes=8)
     assert recall(i, ti) > 0.7
+
+
+# ---- encoder hand-off: the reference's own last_token_pool + F.normalize outputs
+#      (tests/golden/encode.npz, generated by importing generate_embeddings.py:11-21)
+ENCODE_CASES = ["left_padded", "right_padded", "zero_row", "all_ones", "single", "zero_vector"]
+
+
+@pytest.mark.parametrize("case", ENCODE_CASES)
+def test_encode_oracle_matches_reference_golden(case, golden_dir):
+    from oracle import encode
+    g = np.load(os.path.join(golden_dir, "encode.npz"))
+    h, m = g[case + "_hidden"], g[case + "_mask"]
+    np.testing.assert_array_equal(encode.last_token_pool(h, m), g[case + "_pooled"])   # a gather: bit-exact
+    np.testing.assert_allclose(encode.pool_normalize(h, m), g[case + "_normalized"], rtol=2e-6, atol=1e-12)
+    assert encode.pool_normalize(h, m, normalize=False).dtype == np.float32
+
+
+def test_encode_oracle_mean_pool_definition():
+    from oracle import encode
+    h = np.arange(2 * 3 * 2, dtype=np.float32).reshape(2, 3, 2)
+    m = np.array([[1, 1, 0], [0, 0, 0]], np.int64)
+    out = encode.mean_pool(h, m)
+    np.testing.assert_allclose(out[0], (h[0, 0] + h[0, 1]) / 2)
+    np.testing.assert_array_equal(out[1], [0.0, 0.0])          # 0 / clamp(0, 1e-9)
+    np.testing.assert_allclose(encode.mean_pool(h, None), h.mean(axis=1))
