@@ -1144,6 +1144,7 @@ ivf_pq_scan_query_kernel(const uint8_t* __restrict__ codes, const uint32_t* __re
 // Refine (cuVS `refine` / FAISS IndexRefineFlat semantics): exact re-rank of the k' ADC candidates
 // of each query against the original rows.  One warp per query: lanes split the dimensions,
 // candidate j's exact score lands in lane j % 32, a 128-key warp sort orders them.
+constexpr int kRefineAhead = 8;   // candidate rows in flight per warp (divides 32)
 template <typename T>
 __global__ void refine_kernel(const T* __restrict__ rows, int dim, const float* __restrict__ qf,
                               int dp, const long long* __restrict__ cand, int nq, int k_in, int k_out,
@@ -1156,24 +1157,53 @@ __global__ void refine_kernel(const T* __restrict__ rows, int dim, const float* 
 #pragma unroll
   for (int e = 0; e < kListE; ++e) key[e] = kKeyInf;
   const float* qv = qf + static_cast<size_t>(q) * dp;
-  for (int j = 0; j < k_in; ++j) {
-    const long long row = cand[static_cast<size_t>(q) * k_in + j];  // shard-local row, -1 = none
-    float acc = 0.f;
-    if (row >= 0) {
-      const T* x = rows + static_cast<size_t>(row) * dim;
-      for (int t = lane; t < dim; t += 32) {
-        const float xv = ld_f32<T>(x + t);
-        if (metric == B2VS_METRIC_L2) { const float df = qv[t] - xv; acc = fmaf(df, df, acc); }
-        else acc = fmaf(-qv[t], xv, acc);
+  // candidate ids: lane l holds candidates l, l + 32, ... (k_in <= 128), broadcast by shuffle, so
+  // the row reads do not wait for a dependent id load; kRefineAhead rows are in flight at a time
+  // (a single query used to be a chain of k_in dependent HBM round trips: 92 us at k_in = 80)
+  long long my_cand[kListE];
+#pragma unroll
+  for (int e = 0; e < kListE; ++e) {
+    const int j = lane + 32 * e;
+    my_cand[e] = j < k_in ? cand[static_cast<size_t>(q) * k_in + j] : -1ll;  // shard-local row, -1 = none
+  }
+  for (int j0 = 0; j0 < k_in; j0 += kRefineAhead) {
+    long long row[kRefineAhead];
+    float acc[kRefineAhead];
+#pragma unroll
+    for (int b = 0; b < kRefineAhead; ++b) {
+      const int j = j0 + b;   // j0 is a multiple of kRefineAhead (which divides 32): same register for all b
+      long long r = -1ll;
+#pragma unroll
+      for (int e = 0; e < kListE; ++e)
+        if (e == (j0 >> 5)) r = __shfl_sync(0xffffffffu, my_cand[e], j & 31);
+      row[b] = j < k_in ? r : -1ll;
+      acc[b] = 0.f;
+    }
+    for (int t = lane; t < dim; t += 32) {
+      const float qt = qv[t];
+      float xv[kRefineAhead];
+#pragma unroll
+      for (int b = 0; b < kRefineAhead; ++b)
+        xv[b] = row[b] >= 0 ? ld_f32<T>(rows + static_cast<size_t>(row[b]) * dim + t) : 0.f;
+#pragma unroll
+      for (int b = 0; b < kRefineAhead; ++b) {
+        if (row[b] < 0) continue;
+        if (metric == B2VS_METRIC_L2) { const float df = qt - xv[b]; acc[b] = fmaf(df, df, acc[b]); }
+        else acc[b] = fmaf(-qt, xv[b], acc[b]);
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    // blocked layout of the warp sort: element j lives in lane j / kListE, register j % kListE
-    if (row >= 0 && lane == j / kListE) {
+    for (int b = 0; b < kRefineAhead; ++b) {
+      const int j = j0 + b;
+      float a = acc[b];
 #pragma unroll
-      for (int e = 0; e < kListE; ++e)
-        if (e == j % kListE) key[e] = pack_key(acc, static_cast<uint32_t>(row));
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      // blocked layout of the warp sort: element j lives in lane j / kListE, register j % kListE
+      if (row[b] >= 0 && lane == j / kListE) {
+#pragma unroll
+        for (int e = 0; e < kListE; ++e)
+          if (e == j % kListE) key[e] = pack_key(a, static_cast<uint32_t>(row[b]));
+      }
     }
   }
   warp_bitonic_sort<kListE>(key, lane);
@@ -1564,7 +1594,8 @@ ivf_plan_small_kernel(const long long* __restrict__ probe_ids, int items,
   extern __shared__ int plan_sm[];
   int* cnt = plan_sm;                                             // [n_lists] by size rank
   uint32_t* off = reinterpret_cast<uint32_t*>(plan_sm + n_lists); // [n_lists + 1]
-  __shared__ uint32_t part[kPlanThreads];
+  __shared__ uint32_t part[kPlanThreads / 32];
+  static_assert(kPlanThreads == 1024, "the block scan assumes 32 full warps");
   const int t = threadIdx.x;
   for (int i = t; i < n_lists; i += kPlanThreads) cnt[i] = 0;
   __syncthreads();
@@ -1577,17 +1608,34 @@ ivf_plan_small_kernel(const long long* __restrict__ probe_ids, int items,
   const int lo = min(n_lists, t * per), hi = min(n_lists, lo + per);
   uint32_t sum = 0;
   for (int i = lo; i < hi; ++i) sum += static_cast<uint32_t>((cnt[i] + kGroupRows - 1) / kGroupRows * kGroupRows);
-  part[t] = sum;
+  // exclusive scan of the per-thread sums: shuffle scan inside each warp, then across the 32
+  // warp totals (a one-thread loop over the 1024 partials cost ~10 us of a 160 us Q = 1 search)
+  const int lane = t & 31, warp = t >> 5;
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) part[warp] = inc;
   __syncthreads();
-  if (t == 0) {
-    uint32_t run = 0;
-    for (int i = 0; i < kPlanThreads; ++i) { const uint32_t v = part[i]; part[i] = run; run += v; }
-    off[n_lists] = run;
-    group_off[n_lists] = run;
-    *n_work = static_cast<int>(run >> 7) * slots;
+  if (warp == 0) {
+    const uint32_t w = part[lane];
+    uint32_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += v;
+    }
+    part[lane] = winc - w;   // rows before this warp
+    if (lane == 31) {
+      off[n_lists] = winc;
+      group_off[n_lists] = winc;
+      *n_work = static_cast<int>(winc >> 7) * slots;
+    }
   }
   __syncthreads();
-  uint32_t run = part[t];
+  uint32_t run = part[warp] + inc - sum;
   for (int i = lo; i < hi; ++i) {
     off[i] = run;
     group_off[i] = run;

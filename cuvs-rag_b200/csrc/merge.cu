@@ -16,6 +16,7 @@
 namespace b2vs {
 
 constexpr int kMergeE = 4;  // 32 * 4 = 128 = kMaxFusedK
+constexpr int kMergeAhead = 4;  // split lists in flight per warp in merge_splits_kernel
 
 __global__ void merge_splits_kernel(const u64* __restrict__ keys, int n_splits, int q_pad, int nq,
                                     int k, int metric, const float* __restrict__ qnorm,
@@ -29,15 +30,29 @@ __global__ void merge_splits_kernel(const u64* __restrict__ keys, int n_splits, 
   u64 acc[kMergeE];
 #pragma unroll
   for (int e = 0; e < kMergeE; ++e) acc[e] = kKeyInf;
-  for (int s = 0; s < n_splits; ++s) {
-    const u64* list = keys + (static_cast<size_t>(s) * q_pad + q) * k;
+  // The lists of kMergeAhead splits are loaded before any of them is folded in: with one warp
+  // per query a small batch is a chain of dependent global loads otherwise (Q = 1 IVF-PQ coarse
+  // probe, 64 splits: 65 us of a 236 us search).
+  for (int s0 = 0; s0 < n_splits; s0 += kMergeAhead) {
+    u64 ahead[kMergeAhead][kMergeE];
 #pragma unroll
-    for (int e = 0; e < kMergeE; ++e) {
-      const int src = 32 * kMergeE - 1 - (lane * kMergeE + e);  // reversed run
-      const u64 b = (src < k) ? __ldcg(list + src) : kKeyInf;
-      acc[e] = acc[e] < b ? acc[e] : b;
+    for (int p = 0; p < kMergeAhead; ++p) {
+      const bool live = s0 + p < n_splits;
+      const u64* list = keys + (static_cast<size_t>(live ? s0 + p : s0) * q_pad + q) * k;
+#pragma unroll
+      for (int e = 0; e < kMergeE; ++e) {
+        const int src = 32 * kMergeE - 1 - (lane * kMergeE + e);  // reversed run
+        ahead[p][e] = (live && src < k) ? __ldcg(list + src) : kKeyInf;
+      }
     }
-    warp_bitonic_merge<kMergeE>(acc, lane);
+#pragma unroll
+    for (int p = 0; p < kMergeAhead; ++p) {
+      if (s0 + p < n_splits) {   // warp-uniform
+#pragma unroll
+        for (int e = 0; e < kMergeE; ++e) acc[e] = acc[e] < ahead[p][e] ? acc[e] : ahead[p][e];
+        warp_bitonic_merge<kMergeE>(acc, lane);
+      }
+    }
   }
   if (out_tau) {
     // threshold-seeding pass: publish one ulp above the k-th best raw score (inclusive bound)

@@ -103,6 +103,52 @@ class DistributedEmbeddings:
             raise ValueError(f"Parts cover {expect} rows but total_size is {self.total_size}")
 
 
+STAGE_MIN_BYTES = 64 << 20     # host shards below this go up in one plain copy
+STAGE_CHUNK_BYTES = 256 << 20   # size of each of the two pinned staging buffers
+
+
+def staged_host_to_device(src: torch.Tensor, device: torch.device, dtype: Optional[torch.dtype] = None,
+                          chunk_bytes: int = STAGE_CHUNK_BYTES) -> torch.Tensor:
+    """Pageable host rows ``[n, D]`` -> one resident ``[n, D]`` device tensor in ``dtype``.
+
+    The reference does ``embeddings[start:end].clone().to('cuda:i')``
+    (``embedding_distribution_manager.py:161-166``): an extra host copy, a pageable (slow,
+    synchronous) H2D of the whole shard, and — when the shard is to live in 16 bits — the full
+    fp32 shard on the device next to its converted copy (C5: 205 GB of fp32 for a 102 GB bf16
+    corpus, more than one B200 holds).  Here the shard goes up in chunks through two pinned
+    staging buffers on a copy stream: the host memcpy of chunk i+1 overlaps the H2D + on-device
+    conversion of chunk i, and the transient device footprint is one chunk.
+    """
+    n, d = int(src.shape[0]), int(src.shape[1])
+    out = torch.empty((n, d), dtype=dtype or src.dtype, device=device)
+    rows = max(1, int(chunk_bytes) // max(1, d * src.element_size()))
+    copy_stream = torch.cuda.Stream(device)
+    copy_stream.wait_stream(torch.cuda.current_stream(device))
+    pinned_src = src.is_pinned()
+    stage = [] if pinned_src else [torch.empty((min(rows, n), d), dtype=src.dtype, pin_memory=True)
+                                   for _ in range(2)]
+    done = [None, None]
+    for ci, s0 in enumerate(range(0, n, rows)):
+        e0 = min(n, s0 + rows)
+        if pinned_src:
+            host = src[s0:e0]
+        else:
+            b = ci & 1
+            if done[b] is not None:
+                done[b].synchronize()          # the H2D that was reading this staging buffer
+            host = stage[b][: e0 - s0]
+            host.copy_(src[s0:e0])
+        with torch.cuda.stream(copy_stream):
+            out[s0:e0].copy_(host, non_blocking=True)      # H2D (+ conversion on the device)
+            if not pinned_src:
+                done[b] = torch.cuda.Event()
+                done[b].record(copy_stream)
+    torch.cuda.current_stream(device).wait_stream(copy_stream)
+    if not pinned_src:
+        copy_stream.synchronize()              # the staging buffers are freed on return
+    return out
+
+
 class EmbeddingDistributionManager:
     def __init__(self, gpu_manager: GPUResourceManager):
         # duck-typed on purpose: the reference tests pass Mock(spec=GPUResourceManager)
@@ -118,8 +164,9 @@ class EmbeddingDistributionManager:
                               strategy: str = "even") -> DistributedEmbeddings:
         """Shard ``embeddings`` [N, D] over ``target_gpus`` (default: all available GPUs).
 
-        Each shard is one sliced H2D copy (no intermediate clone); ``dtype`` optionally converts
-        the shard ON the device (fp32 host data -> bf16/fp16 resident shards, config C2/C3).
+        No intermediate host clone; ``dtype`` optionally converts the shard ON the device (fp32
+        host data -> bf16/fp16 resident shards, config C2/C3).  Host shards of 64 MB and more go
+        up in pinned, double-buffered chunks (``staged_host_to_device``), smaller ones in one copy.
         """
         if not isinstance(embeddings, torch.Tensor):
             raise TypeError("embeddings must be a torch.Tensor")
@@ -146,9 +193,7 @@ class EmbeddingDistributionManager:
                 if end <= start:
                     continue  # more GPUs than rows
                 device_string = self.gpu_manager.get_safe_device_string(gpu_id)
-                shard = embeddings[start:end].to(device_string)
-                if dtype is not None and shard.dtype != dtype:
-                    shard = shard.to(dtype)
+                shard = self._upload(embeddings[start:end], device_string, dtype)
                 if isinstance(shard, torch.Tensor) and not shard.is_contiguous():
                     shard = shard.contiguous()
                 parts.append(EmbeddingPart(gpu_id, shard, start, end))
@@ -160,6 +205,23 @@ class EmbeddingDistributionManager:
             logger.warning("distribution failed device validation (expected only in mocked tests)")
         self.current_distribution = dist
         return dist
+
+    @staticmethod
+    def _upload(rows: torch.Tensor, device_string: str, dtype: Optional[torch.dtype]) -> torch.Tensor:
+        """One shard onto its device: staged for large host tensors, a plain copy otherwise
+        (device-resident input, small shards, and the mocked / CPU-only unit-test mode)."""
+        try:
+            device = torch.device(device_string)
+        except (TypeError, RuntimeError):
+            device = None
+        if (device is not None and device.type == "cuda" and isinstance(rows, torch.Tensor)
+                and not rows.is_cuda and rows.dim() == 2 and torch.cuda.is_available()
+                and rows.numel() * rows.element_size() >= STAGE_MIN_BYTES):
+            return staged_host_to_device(rows, device, dtype, STAGE_CHUNK_BYTES)
+        shard = rows.to(device_string)
+        if dtype is not None and shard.dtype != dtype:
+            shard = shard.to(dtype)
+        return shard
 
     def load_embedding_parts(self, paths: List[str], dtype: Optional[torch.dtype] = None,
                              target_gpus: Optional[List[int]] = None) -> DistributedEmbeddings:
@@ -186,9 +248,7 @@ class EmbeddingDistributionManager:
                 raise ValueError(f"{path} does not hold a 2D embedding tensor")
             if dim is None:
                 dim = int(t.shape[1])
-            shard = t.contiguous().to(self.gpu_manager.get_safe_device_string(gpu_id))
-            if dtype is not None and shard.dtype != dtype:
-                shard = shard.to(dtype)
+            shard = self._upload(t.contiguous(), self.gpu_manager.get_safe_device_string(gpu_id), dtype)
             parts.append(EmbeddingPart(gpu_id, shard, start, start + int(t.shape[0])))
             start += int(t.shape[0])
         dist = DistributedEmbeddings(parts, start, dim)
