@@ -1704,6 +1704,19 @@ static void choose_work_split(const b2vs_index* index, const IvfData* d, int ite
   const int max_tiles = std::max(1, static_cast<int>(ceil_div(std::max(d->max_list_rows, 1), 256)));
   int chunk_tiles = static_cast<int>(std::ceil(est_tiles / (2.0 * sms)));
   chunk_tiles = std::max(1, std::min(chunk_tiles, max_tiles));
+  if (chunk_tiles < max_tiles) {
+    // Few items (small batches): the grid runs ceil(n_items / SMs) waves and the slowest CTA sets
+    // the time, so pick the chunk that minimises waves x (tiles per item + a fixed per-item cost
+    // of about half a tile).  Q = 1, 32 probes of ~10-tile lists: 3-tile chunks = 128 items in one
+    // wave, instead of 2-tile chunks = 160 items whose last 12 make a second wave.
+    const int list_tiles = std::max(1, static_cast<int>(std::ceil(mean_rows / 256.0)));
+    double best = 1e300;
+    for (int c = 1; c <= max_tiles; ++c) {
+      const int64_t n_items = static_cast<int64_t>(items) * ceil_div(list_tiles, c);
+      const double cost = static_cast<double>(ceil_div(n_items, sms)) * (std::min(c, list_tiles) + 0.5);
+      if (cost <= best) { best = cost; chunk_tiles = c; }   // ties: the larger chunk (fewer items)
+    }
+  }
   *slots = static_cast<int>(ceil_div(max_tiles, chunk_tiles));
   *chunk_rows = chunk_tiles * 256;
 }
