@@ -159,10 +159,13 @@ def run_reference(args):
     rows = min(args.cpu_sample_rows, args.n_db)
     nq = min(args.cpu_sample_queries, args.queries)
     # each "step" = one bounded sample; extrapolate linearly in rows to the full database
-    for _ in range(max(0, min(args.warmup, 1))):
+    # W warm-up steps on a tenth of the sample (thread pool, page faults), then K timed steps
+    # (capped at 50: a step is ~3 s of all host cores)
+    n_warm = max(0, min(args.warmup, 5))
+    for _ in range(n_warm):
         cpu_exact_qps(min(rows, 100_000), args.dim, min(nq, 128), args.k, cores)
     times = []
-    for _ in range(max(1, min(args.steps, 3))):
+    for _ in range(max(1, min(args.steps, 50))):
         qps_s, dt = cpu_exact_qps(rows, args.dim, nq, args.k, cores)
         times.append(dt)
     dt = sum(times) / len(times)
@@ -172,7 +175,7 @@ def run_reference(args):
               f"(oracle.exact.exact_knn), QPS scaled by {rows}/{args.n_db} to the full database")
     line = {
         "impl": "reference", "metric": METRIC_NAME, "value": qps_full, "unit": "queries/s",
-        "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1),
+        "n_gpus": args.gpus, "steps": len(times), "warmup": n_warm,
         "ms_per_step": dt * 1e3 * (args.n_db / rows) * (args.queries / nq),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",

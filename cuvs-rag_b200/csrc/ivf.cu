@@ -1704,11 +1704,15 @@ static void choose_work_split(const b2vs_index* index, const IvfData* d, int ite
   const int max_tiles = std::max(1, static_cast<int>(ceil_div(std::max(d->max_list_rows, 1), 256)));
   int chunk_tiles = static_cast<int>(std::ceil(est_tiles / (2.0 * sms)));
   chunk_tiles = std::max(1, std::min(chunk_tiles, max_tiles));
-  if (chunk_tiles < max_tiles) {
-    // Few items (small batches): the grid runs ceil(n_items / SMs) waves and the slowest CTA sets
-    // the time, so pick the chunk that minimises waves x (tiles per item + a fixed per-item cost
-    // of about half a tile).  Q = 1, 32 probes of ~10-tile lists: 3-tile chunks = 128 items in one
-    // wave, instead of 2-tile chunks = 160 items whose last 12 make a second wave.
+  // Experimental (B2VS_WORK_SPLIT_WAVE=1; off: the first B200 run with it lost 30 % at Q = 1 on
+  // IVF-Flat while Q >= 8 and IVF-PQ gained a few %): with few items the grid runs
+  // ceil(n_items / SMs) waves, so pick the chunk that minimises waves x (tiles per item + a
+  // fixed per-item cost of about half a tile).
+  static const bool wave_split = [] {
+    const char* e = std::getenv("B2VS_WORK_SPLIT_WAVE");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (wave_split && chunk_tiles < max_tiles) {
     const int list_tiles = std::max(1, static_cast<int>(std::ceil(mean_rows / 256.0)));
     double best = 1e300;
     for (int c = 1; c <= max_tiles; ++c) {
@@ -1717,8 +1721,16 @@ static void choose_work_split(const b2vs_index* index, const IvfData* d, int ite
       if (cost <= best) { best = cost; chunk_tiles = c; }   // ties: the larger chunk (fewer items)
     }
   }
+  // A/B switches (read per call): B2VS_WORK_CHUNK_TILES=n forces the chunk, B2VS_DEBUG_SPLIT prints it
+  if (const char* e = std::getenv("B2VS_WORK_CHUNK_TILES")) {
+    const int v = std::atoi(e);
+    if (v > 0) chunk_tiles = std::min(v, max_tiles);
+  }
   *slots = static_cast<int>(ceil_div(max_tiles, chunk_tiles));
   *chunk_rows = chunk_tiles * 256;
+  if (std::getenv("B2VS_DEBUG_SPLIT"))
+    std::fprintf(stderr, "[b2vs] work split: items=%d mean_rows=%.0f max_tiles=%d chunk_tiles=%d slots=%d\n",
+                 items, mean_rows, max_tiles, chunk_tiles, *slots);
 }
 
 // Groups the nq * n_probes (query, probe) items by list and runs the tensor-core list scan in
