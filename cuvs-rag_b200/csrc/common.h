@@ -98,6 +98,8 @@ int sm_count(int dev);
 // ------------------------------------------------------------------------------------------
 // The exact-search engine: a [n, kdim] 16-bit K-major matrix + per-row additive term.
 // Used directly by flat indexes and re-used for the coarse quantizer / k-means assignment.
+struct BfTcParams;  // kernel parameters (bf_tc.cuh)
+
 struct FlatEngine {
   int dev = 0;
   int metric = B2VS_METRIC_L2;
@@ -127,6 +129,8 @@ struct FlatEngine {
   // (k == 1) when out_label is given.
   int search(const void* q, int q_dtype, int nq, int k, int force_splits, int64_t id_offset,
              float* out_d, int64_t* out_i, int32_t* out_label, cudaStream_t st, int flags = 0);
+  int launch_fused(int group, int grid, const CUtensorMap& tm_q, const BfTcParams& p,
+                   cudaStream_t st) const;
   void resolve_timing();  // fills stats.kernel_ms once the timed launch has finished
   // 128 < k <= 2048 (bigk.cu): append-mode passes + per-query radix select
   int search_bigk(const void* q_mat, int nq, int q_pad, int group, int k, int64_t id_offset,

@@ -296,6 +296,35 @@ static int choose_splits(int n_qblocks, int64_t tiles, int sms, int k, bool seed
   return best;
 }
 
+// One launch of the fused distance + top-k kernel over this engine's matrix: the single-CTA
+// variant, or CTA pairs (cluster of 2, each CTA staging half of every db tile).
+int FlatEngine::launch_fused(int group, int grid, const CUtensorMap& tm_q, const BfTcParams& p,
+                             cudaStream_t st) const {
+  if (group == 1) {
+    B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TcCfg<1>::kSmemBytes));
+    bf_tc_kernel<1><<<grid, kTcThreads, TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_x, p);
+  } else {
+    B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TcCfg<2>::kSmemBytes));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = TcCfg<2>::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2VS_CUDA(cudaLaunchKernelEx(&cfg, bf_tc_kernel<2>, tm_q, tm_x_half, p));
+  }
+  B2VS_CUDA(cudaGetLastError());
+  return B2VS_OK;
+}
+
 int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_splits,
                        int64_t id_offset, float* out_d, int64_t* out_i, int32_t* out_label,
                        cudaStream_t st, int flags) {
@@ -418,28 +447,7 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
     p.tiles_per_split = tps;
     p.tile_stride = stride;
     p.tau_init = (pass > 0) ? ws_tau.as<float>() : nullptr;
-    if (group == 1) {
-      B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     TcCfg<1>::kSmemBytes));
-      bf_tc_kernel<1><<<grid, kTcThreads, TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_x, p);
-    } else {
-      B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     TcCfg<2>::kSmemBytes));
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(grid);
-      cfg.blockDim = dim3(kTcThreads);
-      cfg.dynamicSmemBytes = TcCfg<2>::kSmemBytes;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      B2VS_CUDA(cudaLaunchKernelEx(&cfg, bf_tc_kernel<2>, tm_q, tm_x_half, p));
-    }
-    B2VS_CUDA(cudaGetLastError());
+    B2VS_TRY(launch_fused(group, grid, tm_q, p, st));
     ++launches;
     if (last && timed) B2VS_CUDA(cudaEventRecord(ev1, st));
     if (last) {
@@ -554,28 +562,7 @@ int FlatEngine::search_bigk(const void* q_mat, int nq, int q_pad, int group, int
         p.tau_init = seeded ? ws_tau.as<float>() : nullptr;
         const int grid = std::min(p.n_items, units) * group;
         B2VS_CUDA(cudaMemsetAsync(counts, 0, (static_cast<size_t>(chunk_rows) + 1) * sizeof(int), st));
-        if (group == 1) {
-          B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TcCfg<1>::kSmemBytes));
-          bf_tc_kernel<1><<<grid, kTcThreads, TcCfg<1>::kSmemBytes, st>>>(tm_qc, tm_x, p);
-        } else {
-          B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TcCfg<2>::kSmemBytes));
-          cudaLaunchConfig_t cfg{};
-          cfg.gridDim = dim3(grid);
-          cfg.blockDim = dim3(kTcThreads);
-          cfg.dynamicSmemBytes = TcCfg<2>::kSmemBytes;
-          cfg.stream = st;
-          cudaLaunchAttribute attr[1];
-          attr[0].id = cudaLaunchAttributeClusterDimension;
-          attr[0].val.clusterDim.x = 2;
-          attr[0].val.clusterDim.y = 1;
-          attr[0].val.clusterDim.z = 1;
-          cfg.attrs = attr;
-          cfg.numAttrs = 1;
-          B2VS_CUDA(cudaLaunchKernelEx(&cfg, bf_tc_kernel<2>, tm_qc, tm_x_half, p));
-        }
-        B2VS_CUDA(cudaGetLastError());
+        B2VS_TRY(launch_fused(group, grid, tm_qc, p, st));
         // k-th key per query: the next pass's threshold, or (last pass) the sorted answer
         B2VS_TRY(launch_bigk_select(ws_big.as<u64>(), counts, kCapBig, last ? valid_c : rows_c, k,
                                     last ? 1 : 0, metric, ws_qnorm.as<float>() + q0, id_offset,
