@@ -1594,7 +1594,7 @@ ivf_plan_small_kernel(const long long* __restrict__ probe_ids, int items,
   extern __shared__ int plan_sm[];
   int* cnt = plan_sm;                                             // [n_lists] by size rank
   uint32_t* off = reinterpret_cast<uint32_t*>(plan_sm + n_lists); // [n_lists + 1]
-  __shared__ uint32_t part[kPlanThreads / 32];
+  __shared__ u64 part[kPlanThreads / 32];
   static_assert(kPlanThreads == 1024, "the block scan assumes 32 full warps");
   const int t = threadIdx.x;
   for (int i = t; i < n_lists; i += kPlanThreads) cnt[i] = 0;
@@ -1606,55 +1606,64 @@ ivf_plan_small_kernel(const long long* __restrict__ probe_ids, int items,
   __syncthreads();
   const int per = (n_lists + kPlanThreads - 1) / kPlanThreads;
   const int lo = min(n_lists, t * per), hi = min(n_lists, lo + per);
-  uint32_t sum = 0;
-  for (int i = lo; i < hi; ++i) sum += static_cast<uint32_t>((cnt[i] + kGroupRows - 1) / kGroupRows * kGroupRows);
+  // per thread: padded group rows (high half) and work items (low half) of its lists; a list
+  // probed by c queries gives ceil(c / 128) query blocks x ceil(rows / chunk_rows) row ranges.
+  // Only non-empty ranges become work items, packed densely in rank order (longest list first):
+  // the scan kernel strides over them statically, so holes would unbalance its CTAs.
+  u64 sum = 0;
+  for (int i = lo; i < hi; ++i) {
+    const int c = cnt[i];
+    if (c == 0) continue;
+    const int l = list_of_rank[i];
+    const int rows = static_cast<int>(offsets[l + 1] - offsets[l]);
+    const u64 blocks = static_cast<u64>((c + kGroupRows - 1) / kGroupRows);
+    sum += ((blocks * kGroupRows) << 32) | (blocks * static_cast<u64>((rows + chunk_rows - 1) / chunk_rows));
+  }
   // exclusive scan of the per-thread sums: shuffle scan inside each warp, then across the 32
   // warp totals (a one-thread loop over the 1024 partials cost ~10 us of a 160 us Q = 1 search)
   const int lane = t & 31, warp = t >> 5;
-  uint32_t inc = sum;
+  u64 inc = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    const u64 v = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += v;
   }
   if (lane == 31) part[warp] = inc;
   __syncthreads();
   if (warp == 0) {
-    const uint32_t w = part[lane];
-    uint32_t winc = w;
+    const u64 w = part[lane];
+    u64 winc = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
+      const u64 v = __shfl_up_sync(0xffffffffu, winc, o);
       if (lane >= o) winc += v;
     }
-    part[lane] = winc - w;   // rows before this warp
+    part[lane] = winc - w;   // totals before this warp
     if (lane == 31) {
-      off[n_lists] = winc;
-      group_off[n_lists] = winc;
-      *n_work = static_cast<int>(winc >> 7) * slots;
+      off[n_lists] = static_cast<uint32_t>(winc >> 32);
+      group_off[n_lists] = static_cast<uint32_t>(winc >> 32);
+      *n_work = static_cast<int>(winc & 0xffffffffu);
     }
   }
   __syncthreads();
-  uint32_t run = part[warp] + inc - sum;
+  const u64 before = part[warp] + inc - sum;
+  uint32_t run = static_cast<uint32_t>(before >> 32);
+  uint32_t wrun = static_cast<uint32_t>(before & 0xffffffffu);
+  unsigned long long rows_scanned = 0;
   for (int i = lo; i < hi; ++i) {
     off[i] = run;
     group_off[i] = run;
-    run += static_cast<uint32_t>((cnt[i] + kGroupRows - 1) / kGroupRows * kGroupRows);
-  }
-  __syncthreads();
-  unsigned long long rows_scanned = 0;
-  for (int r = t; r < n_lists; r += kPlanThreads) {
-    if (cnt[r] == 0) continue;
-    const int l = list_of_rank[r];
-    const int b0 = static_cast<int>(off[r] >> 7), b1 = static_cast<int>(off[r + 1] >> 7);
+    const int c = cnt[i];
+    if (c == 0) continue;
+    const int l = list_of_rank[i];
     const int begin = static_cast<int>(offsets[l]), end = static_cast<int>(offsets[l + 1]);
-    for (int b = b0; b < b1; ++b)
-      for (int c = 0; c < slots; ++c) {
-        const int rb = min(end, begin + c * chunk_rows);
-        const int re = c + 1 == slots ? end : min(end, rb + chunk_rows);
-        work[b * slots + c] = make_int4(b, rb, re, 0);
-      }
-    rows_scanned += static_cast<unsigned long long>(cnt[r]) * static_cast<unsigned>(end - begin);
+    const int blocks = (c + kGroupRows - 1) / kGroupRows;
+    const int b0 = static_cast<int>(run >> 7);
+    for (int b = 0; b < blocks; ++b)
+      for (int rb = begin; rb < end; rb += chunk_rows)
+        work[wrun++] = make_int4(b0 + b, rb, min(end, rb + chunk_rows), 0);
+    rows_scanned += static_cast<unsigned long long>(c) * static_cast<unsigned>(end - begin);
+    run += static_cast<uint32_t>(blocks * kGroupRows);
   }
   if (scanned_rows && rows_scanned) atomicAdd(scanned_rows, rows_scanned);
   __syncthreads();
@@ -1694,8 +1703,8 @@ static int plan_grouped_work(IvfData* d, const long long* probe_ids, int items, 
   return B2VS_OK;
 }
 
-// Row-range split of the grouped scan's work items (see build_group_work_kernel): aim at two
-// items per SM when the batch alone does not provide them.
+// Row-range split of the grouped scan's work items (see build_group_work_kernel): large batches
+// aim at two items per SM when the batch alone does not provide them.
 static void choose_work_split(const b2vs_index* index, const IvfData* d, int items, int* chunk_rows,
                               int* slots) {
   const int sms = sm_count(index->dev);
@@ -1704,22 +1713,14 @@ static void choose_work_split(const b2vs_index* index, const IvfData* d, int ite
   const int max_tiles = std::max(1, static_cast<int>(ceil_div(std::max(d->max_list_rows, 1), 256)));
   int chunk_tiles = static_cast<int>(std::ceil(est_tiles / (2.0 * sms)));
   chunk_tiles = std::max(1, std::min(chunk_tiles, max_tiles));
-  // Experimental (B2VS_WORK_SPLIT_WAVE=1; off: the first B200 run with it lost 30 % at Q = 1 on
-  // IVF-Flat while Q >= 8 and IVF-PQ gained a few %): with few items the grid runs
-  // ceil(n_items / SMs) waves, so pick the chunk that minimises waves x (tiles per item + a
-  // fixed per-item cost of about half a tile).
-  static const bool wave_split = [] {
-    const char* e = std::getenv("B2VS_WORK_SPLIT_WAVE");
-    return e != nullptr && e[0] == '1';
-  }();
-  if (wave_split && chunk_tiles < max_tiles) {
-    const int list_tiles = std::max(1, static_cast<int>(std::ceil(mean_rows / 256.0)));
-    double best = 1e300;
-    for (int c = 1; c <= max_tiles; ++c) {
-      const int64_t n_items = static_cast<int64_t>(items) * ceil_div(list_tiles, c);
-      const double cost = static_cast<double>(ceil_div(n_items, sms)) * (std::min(c, list_tiles) + 0.5);
-      if (cost <= best) { best = cost; chunk_tiles = c; }   // ties: the larger chunk (fewer items)
-    }
+  // Small batches (the one-CTA planner, which packs the non-empty row ranges densely): measured
+  // on B200 (profiles/r1_work_split_sweep_*.jsonl, tools/sweep_work_split.py) one-tile items win
+  // up to Q = 8 (IVF-Flat -7..-12 %), four-tile items from Q = 16 to 64 (-4..-19 %), and the
+  // per-item cost (query block re-staged per item) only shows from Q = 128 on: aim at ~16 items
+  // per SM with at most four tiles each.
+  if (items <= kPlanMaxItems && d->n_lists <= kPlanMaxLists) {
+    chunk_tiles = static_cast<int>(est_tiles / (16.0 * sms));
+    chunk_tiles = std::max(1, std::min(chunk_tiles, std::min(4, max_tiles)));
   }
   // A/B switches (read per call): B2VS_WORK_CHUNK_TILES=n forces the chunk, B2VS_DEBUG_SPLIT prints it
   if (const char* e = std::getenv("B2VS_WORK_CHUNK_TILES")) {

@@ -1,5 +1,5 @@
 """Q = 1..8 IVF latency against the row-range chunk of the grouped scan's work items
-(B2VS_WORK_CHUNK_TILES; 0 = the heuristic).  usage: sweep_work_split.py flat|pq"""
+(B2VS_WORK_CHUNK_TILES; 0 = the heuristic).  usage: sweep_work_split.py flat|pq [Q,Q,...] [chunk,chunk,...]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -22,14 +22,16 @@ ix = (b2.NativeIndex.ivf_flat(x, nlist, kmeans_iters=10) if kind == "flat"
 rr = 4 if kind == "pq" else 0
 sizes = ix.list_sizes()
 print(json.dumps({"kind": kind, "mean_list": float(sizes.float().mean()), "max_list": int(sizes.max())}), flush=True)
-for nq in (1, 2, 4, 8):
+q_list = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2, 4, 8]
+c_list = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2, 3, 4, 5, 6, 8, 10, 16]
+for nq in q_list:
     qi = torch.randint(0, n, (nq,), generator=g, device=dev)
     q = (x[qi].float() + 0.1 * torch.randn((nq, d), generator=g, device=dev)).to(torch.float16)
     os.environ["B2VS_DEBUG_SPLIT"] = "1"
     os.environ.pop("B2VS_WORK_CHUNK_TILES", None)
     ix.search(q, 20, n_probes=nprobe, refine_ratio=rr)
     os.environ.pop("B2VS_DEBUG_SPLIT")
-    for c in (0, 1, 2, 3, 4, 5, 6, 8, 10, 16):
+    for c in c_list:
         if c:
             os.environ["B2VS_WORK_CHUNK_TILES"] = str(c)
         else:
