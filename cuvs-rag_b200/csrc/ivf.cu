@@ -93,6 +93,10 @@ struct IvfData {
   int row_bytes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timing_pending = false;
+  // coarse probe of very small batches on the CUDA cores (coarse_probe_scan): the centroid table
+  // seen as 256-row pseudo-lists
+  DevBuf cq_offsets, cq_probe, ws_cq_keys;
+  bool cq_ready = false;
   std::vector<SearchGraph> graphs;      // captured small-batch searches (see ivf_search)
   cudaStream_t cap_stream = nullptr;    // capture happens here: the caller's stream may be the legacy one
   uint64_t graph_clock = 0;
@@ -114,7 +118,7 @@ struct IvfData {
                       &ws_probe_d, &ws_probe_i, &ws_keys, &ws_qf, &ws_qnorm, &ws_counter,
                       &ws_ref_d, &ws_ref_i, &ws_item_lab, &ws_item_cnt, &ws_item_off, &ws_item_perm,
                       &ws_item_slot, &ws_g_work, &ws_g_q, &ws_g_rowq, &ws_g_tau, &ws_g_cand, &ws_g_cnt,
-                      &ws_g_bias, &cb16, &cbn, &pq_norm})
+                      &ws_g_bias, &cb16, &cbn, &pq_norm, &cq_offsets, &cq_probe, &ws_cq_keys})
       b->release();
   }
 };
@@ -2071,6 +2075,55 @@ static int ivf_pq_search_bigk(b2vs_index* index, const void* q, int q_dtype, int
   return B2VS_OK;
 }
 
+// ---- K4b coarse probe of very small batches ---------------------------------------------------
+// The tensor-core probe works on 128-query blocks: for a handful of queries it is one 256-centroid
+// tile per CTA on 16 (4096 lists) to 64 CTAs and takes 30-43 us of a 140-170 us search.  Here the
+// centroid operand matrix of the flat engine is read as 256-row pseudo-lists by the per-item list
+// scan (K5: one CTA per (query, pseudo-list), query slice in registers, warp-resident top-k), and
+// the per-chunk lists are folded by merge_splits_kernel - the same two kernels, the same score
+// (alpha * q.c + ||c||^2 over the rounded operands) as the tensor-core path.
+constexpr int kCoarseScanMaxQueries = 8;
+constexpr int kCoarseScanRows = 256;
+
+// Number of pseudo-lists, or 0 when the tensor-core probe should run (B2VS_COARSE_SCAN=0 forces that).
+static int coarse_scan_chunks(const b2vs_index* index, const IvfData* d, int nq, int n_probes) {
+  const char* e = std::getenv("B2VS_COARSE_SCAN");
+  if (e && e[0] == '0') return 0;
+  if (nq > kCoarseScanMaxQueries || n_probes > kMaxFusedK) return 0;
+  if (index->flat.split3 || index->flat.kdim != d->dp || (d->dp >> 3) > 32 * 8) return 0;
+  const int chunks = static_cast<int>(ceil_div(d->n_lists, kCoarseScanRows));
+  if (chunks < 1 || static_cast<int64_t>(nq) * chunks > 2ll * sm_count(index->dev)) return 0;
+  return chunks;
+}
+
+static int coarse_probe_scan(b2vs_index* index, IvfData* d, int nq, int n_probes, int chunks,
+                             cudaStream_t st) {
+  if (!d->cq_ready) {
+    std::vector<uint32_t> offs(static_cast<size_t>(chunks) + 1);
+    for (int c = 0; c <= chunks; ++c)
+      offs[c] = static_cast<uint32_t>(std::min<int64_t>(d->n_lists, static_cast<int64_t>(c) * kCoarseScanRows));
+    std::vector<long long> probes(static_cast<size_t>(kCoarseScanMaxQueries) * chunks);
+    for (int qi = 0; qi < kCoarseScanMaxQueries; ++qi)
+      for (int c = 0; c < chunks; ++c) probes[static_cast<size_t>(qi) * chunks + c] = c;
+    B2VS_TRY(d->cq_offsets.reserve(offs.size() * sizeof(uint32_t)));
+    B2VS_TRY(d->cq_probe.reserve(probes.size() * sizeof(long long)));
+    B2VS_CUDA(cudaMemcpy(d->cq_offsets.ptr, offs.data(), offs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    B2VS_CUDA(cudaMemcpy(d->cq_probe.ptr, probes.data(), probes.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    d->cq_ready = true;
+  }
+  B2VS_TRY(d->ws_cq_keys.reserve(static_cast<size_t>(chunks) * nq * n_probes * sizeof(u64)));
+  const int j = static_cast<int>(ceil_div(d->dp / 8, 32));
+  const float alpha = index->flat.metric == B2VS_METRIC_L2 ? -2.f : -1.f;
+  FLAT_SCAN_DISPATCH(ivf_flat_scan_kernel, index->flat.ab_format, j, nq * chunks, st,
+                     static_cast<const uint16_t*>(index->flat.mat), index->flat.beta.as<float>(),
+                     d->cq_offsets.as<uint32_t>(), d->cq_probe.as<long long>(), d->ws_qf.as<float>(),
+                     d->dp, chunks, nq, n_probes, alpha, d->ws_cq_keys.as<u64>(), nullptr, nullptr);
+  B2VS_CUDA(cudaGetLastError());
+  return launch_merge_splits(d->ws_cq_keys.as<u64>(), chunks, nq, nq, n_probes, index->flat.metric,
+                             d->ws_qnorm.as<float>(), 0, d->ws_probe_d.as<float>(),
+                             d->ws_probe_i.as<int64_t>(), nullptr, st);
+}
+
 static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
                             const b2vs_search_params& sp, float* out_d, int64_t* out_i,
                             cudaStream_t st) {
@@ -2089,15 +2142,21 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
   B2VS_TRY(d->ws_qf.reserve(static_cast<size_t>(nq) * d->dp * sizeof(float)));
   B2VS_TRY(d->ws_qnorm.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
   B2VS_TRY(d->ws_counter.reserve(2 * sizeof(unsigned long long)));  // scanned rows, candidates
-  // K4 coarse probe: top-n_probes centroids on the tensor cores
-  B2VS_TRY(index->flat.search(q, q_dtype, nq, n_probes, 0, 0, d->ws_probe_d.as<float>(),
-                              d->ws_probe_i.as<int64_t>(), nullptr, st));
-  int launches = index->flat.stats.launches;
   const int round16 = (index->kind == B2VS_KIND_IVF_FLAT && index->dtype != B2VS_F32) ? 1 : 0;
   DISPATCH_DTYPE(q_dtype, T, (queries_to_f32_kernel<T><<<static_cast<unsigned>(ceil_div(nq, 4)), 128, 0, st>>>(
                                  static_cast<const T*>(q), nq, index->dim, d->dp, d->fmt, round16,
                                  d->ws_qf.as<float>(), d->ws_qnorm.as<float>())));
   B2VS_CUDA(cudaGetLastError());
+  // K4 coarse probe: top-n_probes centroids - on the tensor cores, or (a handful of queries) K4b
+  int launches = 2;
+  const int coarse_chunks = coarse_scan_chunks(index, d, nq, n_probes);
+  if (coarse_chunks > 0) {
+    B2VS_TRY(coarse_probe_scan(index, d, nq, n_probes, coarse_chunks, st));
+  } else {
+    B2VS_TRY(index->flat.search(q, q_dtype, nq, n_probes, 0, 0, d->ws_probe_d.as<float>(),
+                                d->ws_probe_i.as<int64_t>(), nullptr, st));
+    launches = index->flat.stats.launches;
+  }
   B2VS_CUDA(cudaMemsetAsync(d->ws_counter.ptr, 0, 2 * sizeof(unsigned long long), st));
   launches += 2;
   const int items = nq * n_probes;

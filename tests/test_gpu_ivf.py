@@ -415,3 +415,44 @@ def test_small_batch_cuda_graph_replay_equals_direct_search(b2, kind):
         sd, si = ix.search(q1, 10, graph=True, stream=s, **kw)
     s.synchronize()
     assert torch.equal(wi, si) and torch.allclose(wd, sd, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("kind,dtype,metric,d", [("flat", torch.float16, "sqeuclidean", 128),
+                                                  ("flat", torch.bfloat16, "inner_product", 72),
+                                                  ("flat", torch.float32, "sqeuclidean", 200),
+                                                  ("pq", torch.float16, "sqeuclidean", 64)])
+def test_tiny_batch_coarse_probe_scan_equals_tensor_core_probe(b2, monkeypatch, kind, dtype, metric, d):
+    """Batches of up to 8 queries pick their probe lists with the CUDA-core scan over the centroid
+    operand matrix (K4b) instead of the tensor-core probe; both must lead to the same answers
+    (B2VS_COARSE_SCAN=0 forces the tensor-core probe), including with fewer centroids than one
+    256-row chunk and with a ragged last chunk."""
+    for nlist in (40, 300):
+        x = clustered(30000, d, 120, 41).to(dtype)
+        if kind == "flat":
+            ix = b2.NativeIndex.ivf_flat(x.cuda(), nlist, metric=metric, id_offset=3, kmeans_iters=6)
+            kw = dict(n_probes=min(nlist, 24))
+        else:
+            ix = b2.NativeIndex.ivf_pq(x.cuda(), nlist, 32, metric=metric, id_offset=3, kmeans_iters=6)
+            kw = dict(n_probes=min(nlist, 24), refine_ratio=4)
+        for nq in (1, 5, 8):
+            q = queries_from(x.float(), nq, 50 + nq).to(dtype).cuda()
+            monkeypatch.setenv("B2VS_COARSE_SCAN", "0")
+            d0, i0 = (t.clone() for t in ix.search(q, 10, **kw))
+            monkeypatch.delenv("B2VS_COARSE_SCAN")
+            d1, i1 = (t.clone() for t in ix.search(q, 10, **kw))
+            torch.cuda.synchronize()
+            # same probe lists -> same candidates; a near-tie between two centroids may swap the
+            # last probed list, which can only change an answer's tail
+            same = (i0 == i1).float().mean().item()
+            assert same >= 0.9, (nlist, nq, same)
+            assert torch.equal(i0[:, 0], i1[:, 0])
+            scale = float(d0.abs().max())
+            assert float((d0[:, 0] - d1[:, 0]).abs().max()) <= 1e-3 * scale + 1e-4
+        # a full probe is exact whichever way the lists were ranked
+        if kind == "flat" and nlist == 40:
+            qf = queries_from(x.float(), 4, 77).to(dtype).cuda()
+            monkeypatch.setenv("B2VS_COARSE_SCAN", "0")
+            _, j0 = ix.search(qf, 10, n_probes=nlist)
+            monkeypatch.delenv("B2VS_COARSE_SCAN")
+            _, j1 = ix.search(qf, 10, n_probes=nlist)
+            assert torch.equal(j0, j1)
