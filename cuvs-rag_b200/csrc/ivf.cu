@@ -2082,17 +2082,30 @@ static int ivf_pq_search_bigk(b2vs_index* index, const void* q, int q_dtype, int
 // scan (K5: one CTA per (query, pseudo-list), query slice in registers, warp-resident top-k), and
 // the per-chunk lists are folded by merge_splits_kernel - the same two kernels, the same score
 // (alpha * q.c + ||c||^2 over the rounded operands) as the tensor-core path.
-constexpr int kCoarseScanMaxQueries = 8;
+constexpr int kCoarseScanMaxQueries = 8;    // default batch limit (B2VS_COARSE_SCAN_MAXQ overrides, <= 32)
+constexpr int kCoarseScanCtasPerSm = 2;     // default limit on (queries x pseudo-lists) / SMs (B2VS_COARSE_SCAN_CTAS)
+constexpr int kCoarseScanProbeRows = 32;    // rows of the constant pseudo-probe table
 constexpr int kCoarseScanRows = 256;
+
+static int env_int(const char* name, int fallback, int lo, int hi) {
+  const char* e = std::getenv(name);
+  if (!e) return fallback;
+  const int v = std::atoi(e);
+  return v < lo ? lo : (v > hi ? hi : v);
+}
 
 // Number of pseudo-lists, or 0 when the tensor-core probe should run (B2VS_COARSE_SCAN=0 forces that).
 static int coarse_scan_chunks(const b2vs_index* index, const IvfData* d, int nq, int n_probes) {
   const char* e = std::getenv("B2VS_COARSE_SCAN");
   if (e && e[0] == '0') return 0;
-  if (nq > kCoarseScanMaxQueries || n_probes > kMaxFusedK) return 0;
+  if (nq > env_int("B2VS_COARSE_SCAN_MAXQ", kCoarseScanMaxQueries, 1, kCoarseScanProbeRows) ||
+      n_probes > kMaxFusedK)
+    return 0;
   if (index->flat.split3 || index->flat.kdim != d->dp || (d->dp >> 3) > 32 * 8) return 0;
   const int chunks = static_cast<int>(ceil_div(d->n_lists, kCoarseScanRows));
-  if (chunks < 1 || static_cast<int64_t>(nq) * chunks > 2ll * sm_count(index->dev)) return 0;
+  const int64_t max_ctas = static_cast<int64_t>(env_int("B2VS_COARSE_SCAN_CTAS", kCoarseScanCtasPerSm, 1, 64)) *
+                           sm_count(index->dev);
+  if (chunks < 1 || static_cast<int64_t>(nq) * chunks > max_ctas) return 0;
   return chunks;
 }
 
@@ -2102,8 +2115,8 @@ static int coarse_probe_scan(b2vs_index* index, IvfData* d, int nq, int n_probes
     std::vector<uint32_t> offs(static_cast<size_t>(chunks) + 1);
     for (int c = 0; c <= chunks; ++c)
       offs[c] = static_cast<uint32_t>(std::min<int64_t>(d->n_lists, static_cast<int64_t>(c) * kCoarseScanRows));
-    std::vector<long long> probes(static_cast<size_t>(kCoarseScanMaxQueries) * chunks);
-    for (int qi = 0; qi < kCoarseScanMaxQueries; ++qi)
+    std::vector<long long> probes(static_cast<size_t>(kCoarseScanProbeRows) * chunks);
+    for (int qi = 0; qi < kCoarseScanProbeRows; ++qi)
       for (int c = 0; c < chunks; ++c) probes[static_cast<size_t>(qi) * chunks + c] = c;
     B2VS_TRY(d->cq_offsets.reserve(offs.size() * sizeof(uint32_t)));
     B2VS_TRY(d->cq_probe.reserve(probes.size() * sizeof(long long)));
