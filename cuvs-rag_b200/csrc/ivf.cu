@@ -2077,13 +2077,16 @@ static int ivf_pq_search_bigk(b2vs_index* index, const void* q, int q_dtype, int
 
 // ---- K4b coarse probe of very small batches ---------------------------------------------------
 // The tensor-core probe works on 128-query blocks: for a handful of queries it is one 256-centroid
-// tile per CTA on 16 (4096 lists) to 64 CTAs and takes 30-43 us of a 140-170 us search.  Here the
+// tile per CTA on 16 (4096 lists) to 64 CTAs and takes 30-43 us of a 140-170 us search.  Here (K4b) the
 // centroid operand matrix of the flat engine is read as 256-row pseudo-lists by the per-item list
 // scan (K5: one CTA per (query, pseudo-list), query slice in registers, warp-resident top-k), and
 // the per-chunk lists are folded by merge_splits_kernel - the same two kernels, the same score
 // (alpha * q.c + ||c||^2 over the rounded operands) as the tensor-core path.
-constexpr int kCoarseScanMaxQueries = 8;    // default batch limit (B2VS_COARSE_SCAN_MAXQ overrides, <= 32)
-constexpr int kCoarseScanCtasPerSm = 2;     // default limit on (queries x pseudo-lists) / SMs (B2VS_COARSE_SCAN_CTAS)
+// Limits measured on B200 (profiles/r1_coarse_scan_ab.txt): against the tensor-core probe the scan
+// saves 16-20 % of the whole search from Q = 1 to Q = 32 (IVF-Flat, 4096 lists) / Q = 16 (IVF-PQ,
+// 16384 lists = 1024 CTAs); larger batches were not measured and keep the tensor cores.
+constexpr int kCoarseScanMaxQueries = 32;   // batch limit (B2VS_COARSE_SCAN_MAXQ overrides, <= 32)
+constexpr int kCoarseScanCtasPerSm = 8;     // limit on (queries x pseudo-lists) / SMs (B2VS_COARSE_SCAN_CTAS)
 constexpr int kCoarseScanProbeRows = 32;    // rows of the constant pseudo-probe table
 constexpr int kCoarseScanRows = 256;
 
