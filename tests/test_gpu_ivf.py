@@ -422,7 +422,7 @@ def test_small_batch_cuda_graph_replay_equals_direct_search(b2, kind):
                                                   ("flat", torch.float32, "sqeuclidean", 200),
                                                   ("pq", torch.float16, "sqeuclidean", 64)])
 def test_tiny_batch_coarse_probe_scan_equals_tensor_core_probe(b2, monkeypatch, kind, dtype, metric, d):
-    """Batches of up to 8 queries pick their probe lists with the CUDA-core scan over the centroid
+    """Batches of up to 32 queries pick their probe lists with the CUDA-core scan over the centroid
     operand matrix (K4b) instead of the tensor-core probe; both must lead to the same answers
     (B2VS_COARSE_SCAN=0 forces the tensor-core probe), including with fewer centroids than one
     256-row chunk and with a ragged last chunk."""
@@ -434,7 +434,7 @@ def test_tiny_batch_coarse_probe_scan_equals_tensor_core_probe(b2, monkeypatch, 
         else:
             ix = b2.NativeIndex.ivf_pq(x.cuda(), nlist, 32, metric=metric, id_offset=3, kmeans_iters=6)
             kw = dict(n_probes=min(nlist, 24), refine_ratio=4)
-        for nq in (1, 5, 8):
+        for nq in (1, 5, 8, 32):
             q = queries_from(x.float(), nq, 50 + nq).to(dtype).cuda()
             monkeypatch.setenv("B2VS_COARSE_SCAN", "0")
             d0, i0 = (t.clone() for t in ix.search(q, 10, **kw))
