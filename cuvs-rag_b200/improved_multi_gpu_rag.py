@@ -194,6 +194,7 @@ class ParallelSearchEngine:
     """Sharded search: every GPU answers for its rows, one GPU merges (b2vs_merge_topk)."""
 
     def __init__(self, gpu_indexes: Dict[int, Any], index_type: IndexType, search_config: SearchConfig):
+        self.last_missing_shards: List[Tuple[int, str]] = []   # (gpu, error) of the last search
         self.gpu_indexes = gpu_indexes
         self.index_type = index_type
         self.search_config = search_config
@@ -216,10 +217,22 @@ class ParallelSearchEngine:
     def _search_merged(self, queries: torch.Tensor, k: int, params: Optional[Dict] = None):
         """[Q, D] -> merged (dist [Q, k'], ids [Q, k']) on the first index's GPU."""
         gpus = sorted(self.gpu_indexes)
+        # A shard that fails is skipped, as in the reference (:261-263 logs and carries on), but
+        # not silently: ``last_missing_shards`` lists (gpu, error) of the call, and a search with
+        # no answering shard raises.
+        self.last_missing_shards = []
+        raw = []
         if len(gpus) > 1:
             futs = [self.executor.submit(self._search_device, g, self.gpu_indexes[g], queries, k, params)
                     for g in gpus]
-            raw = [f.result(timeout=60) for f in futs]
+            for g, f in zip(gpus, futs):
+                try:
+                    raw.append(f.result(timeout=60))
+                except Exception as exc:  # noqa: BLE001 - reported per shard
+                    self.last_missing_shards.append((g, f"{type(exc).__name__}: {exc}"))
+                    logger.error("search on GPU %d failed, its shard is missing from the result: %s", g, exc)
+            if not raw:
+                raise RuntimeError(f"search failed on every shard: {self.last_missing_shards}")
         else:
             raw = [self._search_device(gpus[0], self.gpu_indexes[gpus[0]], queries, k, params)]
         primary = raw[0][0].device

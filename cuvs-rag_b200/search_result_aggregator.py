@@ -71,6 +71,15 @@ class AggregatedSearchResult:
     k_requested: int
     k_returned: int
     num_queries: int
+    # degraded searches (SearchConfig.search_params["allow_partial"]): the GPUs whose shard did not
+    # answer and why - the rows of those shards are absent from final_* (the reference drops
+    # failed shards with a log line only, improved_multi_gpu_rag.py:261-263)
+    missing_gpus: List[int] = field(default_factory=list)
+    shard_errors: Dict[int, str] = field(default_factory=dict)
+
+    @property
+    def complete(self) -> bool:
+        return not self.missing_gpus
 
     def __post_init__(self):
         if self.k_requested <= 0:
@@ -85,7 +94,10 @@ class AggregatedSearchResult:
 class SearchConfig:
     """``search_params`` keys understood by the native path: ``n_probes`` (alias ``nprobe``),
     ``refine_ratio``, ``k_local`` (per-shard k, default k), ``collect_gpu_results`` (default
-    True: per-shard results are copied to the host into ``gpu_results`` as the reference does)."""
+    True: per-shard results are copied to the host into ``gpu_results`` as the reference does),
+    ``graph`` (replay small IVF batches as a CUDA graph), ``allow_partial`` (default False: a shard
+    that fails fails the search; True: answer from the shards that did respond and list the others
+    in ``AggregatedSearchResult.missing_gpus`` / ``shard_errors``)."""
     k: int
     search_params: Optional[Dict[str, Any]] = None
     parallel_search: bool = True
@@ -255,13 +267,38 @@ class SearchResultAggregator:
         nq = query.shape[0]
         gpus = sorted(indices)
 
+        allow_partial = bool(params.get("allow_partial", False))
+        shard_errors: Dict[int, str] = {}
+
+        def shard_failed(g: int, exc: BaseException) -> None:
+            if not allow_partial:
+                raise exc          # unchanged type and message: the default is to fail loudly
+            shard_errors[g] = f"{type(exc).__name__}: {exc}"
+            logger.error("search on GPU %d failed, its shard is missing from the result: %s", g, exc)
+
+        answered: List[int] = []
+        raw = []
         if config.parallel_search and len(gpus) > 1:
             with ThreadPoolExecutor(max_workers=len(gpus)) as pool:
                 futs = [pool.submit(self._search_single_gpu, g, indices[g], query, k_local, params)
                         for g in gpus]
-                raw = [f.result(timeout=config.timeout_seconds) for f in futs]
+                for g, f in zip(gpus, futs):
+                    try:
+                        raw.append(f.result(timeout=config.timeout_seconds))
+                        answered.append(g)
+                    except Exception as exc:  # noqa: BLE001 - reported per shard
+                        shard_failed(g, exc)
         else:
-            raw = [self._search_single_gpu(g, indices[g], query, k_local, params) for g in gpus]
+            for g in gpus:
+                try:
+                    raw.append(self._search_single_gpu(g, indices[g], query, k_local, params))
+                    answered.append(g)
+                except Exception as exc:  # noqa: BLE001
+                    shard_failed(g, exc)
+        if not raw:
+            raise RuntimeError(f"search failed on every shard: {shard_errors}")
+        missing = [g for g in gpus if g not in answered]
+        gpus = answered
 
         on_device = all(r[3] for r in raw)
         descending = any(getattr(indices[g], "descending", False) is True for g in gpus)
@@ -280,7 +317,7 @@ class SearchResultAggregator:
             if final_d.shape != final_i.shape or final_d.shape[0] != nq:
                 raise ValueError(f"merged result has shape {final_d.shape}, expected ({nq}, {k})")
         result = AggregatedSearchResult(final_d, final_i, time.time() - t0, gpu_results, k,
-                                        int(final_d.shape[1]), nq)
+                                        int(final_d.shape[1]), nq, missing, shard_errors)
         self.search_history.append(result)
         return result
 

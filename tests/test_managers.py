@@ -280,3 +280,36 @@ def test_load_embedding_parts_reference_disk_format(b2, tmp_path):
     assert [(p.start_index, p.end_index) for p in dist.parts] == [(0, 38), (38, 75)]
     with pytest.raises(ValueError, match="paths cannot be empty"):
         edm.load_embedding_parts([])
+
+
+def test_degraded_search_reports_the_missing_shard(b2):
+    """A shard that fails: by default the search fails with the shard's own exception; with
+    search_params['allow_partial'] the other shards answer and the result names the missing GPUs
+    (the reference drops failed shards with a log line only, improved_multi_gpu_rag.py:261-263)."""
+    agg, g = sra_fixture(b2)
+    real = agg._search_single_gpu
+
+    def flaky(gpu_id, index, query, k_local, params):
+        if gpu_id == 1:
+            raise RuntimeError("Xid 79: GPU has fallen off the bus")
+        return real(gpu_id, index, query, k_local, params)
+
+    with patch("search_result_aggregator.CUVS_AVAILABLE", False), patch.object(agg, "_search_single_gpu", flaky):
+        for parallel in (False, True):
+            with pytest.raises(RuntimeError, match="fallen off the bus"):
+                agg.perform_distributed_search(torch.randn(2, 4), {0: Mock(), 1: Mock(), 2: Mock()},
+                                               b2.SearchConfig(k=3, parallel_search=parallel))
+            res = agg.perform_distributed_search(
+                torch.randn(2, 4), {0: Mock(), 1: Mock(), 2: Mock()},
+                b2.SearchConfig(k=3, parallel_search=parallel, search_params={"allow_partial": True}))
+            assert res.missing_gpus == [1] and not res.complete
+            assert "fallen off the bus" in res.shard_errors[1]
+            assert [r.gpu_id for r in res.gpu_results] == [0, 2]
+            assert res.final_distances.shape == (2, 3)
+        with pytest.raises(RuntimeError, match="failed on every shard"):
+            agg.perform_distributed_search(torch.randn(2, 4), {1: Mock()},
+                                           b2.SearchConfig(k=3, search_params={"allow_partial": True}))
+    # a healthy search is complete and lists nothing
+    with patch("search_result_aggregator.CUVS_AVAILABLE", False):
+        res = agg.perform_distributed_search(torch.randn(2, 4), {0: Mock()}, b2.SearchConfig(k=3))
+    assert res.complete and res.missing_gpus == [] and res.shard_errors == {}
