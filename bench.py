@@ -151,6 +151,40 @@ def cpu_exact_qps(n_rows, dim, n_queries, k, threads, seconds_budget=30.0):
     return n_queries / dt, dt
 
 
+def cpu_sklearn_qps(n_rows, dim, n_queries, k):
+    """The reference's own CPU path (Attempt_1/VectorSearch_QuestionRetrieval.ipynb:L878):
+    scikit-learn NearestNeighbors(algorithm='brute', n_jobs=-1) on a bounded sample.  Returns
+    (QPS on the sample, seconds) or None when scikit-learn is unavailable."""
+    try:
+        from sklearn.neighbors import NearestNeighbors
+    except Exception:
+        return None
+    g = torch.Generator().manual_seed(98)
+    db = torch.randn(n_rows, dim, generator=g).numpy()
+    q = torch.randn(n_queries, dim, generator=g).numpy()
+    t0 = time.time()
+    nn = NearestNeighbors(n_neighbors=min(k, n_rows), algorithm="brute", n_jobs=-1).fit(db)
+    nn.kneighbors(q)
+    dt = time.time() - t0
+    return n_queries / dt, dt
+
+
+def sklearn_baseline(args, cores):
+    """cpu_baseline-shaped entry for the reference's scikit-learn path (None if unavailable)."""
+    rows, nq = min(200_000, args.n_db), min(200, args.queries)
+    try:
+        r = cpu_sklearn_qps(rows, args.dim, nq, args.k)
+    except Exception:
+        r = None
+    if r is None:
+        return None
+    qps_s, dt = r
+    return {"value": qps_s * rows / args.n_db, "unit": "queries/s", "cores": cores, "kind": "reference",
+            "sample": f"scikit-learn NearestNeighbors(brute, n_jobs=-1), the reference's CPU baseline "
+                      f"(VectorSearch_QuestionRetrieval.ipynb:L878): {rows} x {args.dim} fp32 rows x {nq} "
+                      f"queries in {dt:.1f} s, QPS scaled by {rows}/{args.n_db} to the full database"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -187,6 +221,9 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    sk = sklearn_baseline(args, cores)
+    if sk is not None:
+        line["cpu_baseline_sklearn"] = sk
     print(json.dumps(line), flush=True)
 
 
@@ -397,6 +434,9 @@ def main():
                 "sample": f"{rows} x {args.dim} fp32 rows x {nq} queries in {dt:.1f} s "
                           f"(oracle.exact.exact_knn = FAISS IndexFlatL2 restatement), QPS scaled by "
                           f"{rows}/{args.n_db} to the full database"}
+            sk = sklearn_baseline(args, cores)
+            if sk is not None:
+                line["cpu_baseline_sklearn"] = sk
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

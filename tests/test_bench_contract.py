@@ -35,6 +35,9 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"] and "model" not in line["config"]
+    # the reference's own CPU path (scikit-learn brute force) is reported beside the port
+    sk = line["cpu_baseline_sklearn"]
+    assert sk["kind"] == "reference" and sk["value"] > 0 and "NearestNeighbors" in sk["sample"]
 
 
 def test_reference_arm_other_ranks_print_nothing():
