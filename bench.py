@@ -37,7 +37,7 @@ METRIC_NAME = "QPS at k=100 exact L2 (10M x 768 bf16, 10K-query batches, global 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)   # >= 20 back-to-back batches, >= 2 s (clocks settle)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b2vs", choices=["b2vs", "reference"])
     ap.add_argument("--n-db", type=int, default=N_DB)
