@@ -50,3 +50,20 @@ def test_gpu_arm_has_no_cpu_fallback():
         return
     r = run_bench("--steps", "1", "--warmup", "0", "--n-db", "1000", "--queries", "8", "--k", "4")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """The driver launches N > 1 through torch.distributed.run: rank 0 alone works and prints,
+    the other ranks exit 0 without work."""
+    e = dict(os.environ)
+    r = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+         "--master-addr", "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "bench.py"),
+         "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--n-db", "20000",
+         "--queries", "32", "--k", "10", "--cpu-sample-rows", "20000", "--cpu-sample-queries", "32"],
+        capture_output=True, text=True, timeout=600, env=e)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
