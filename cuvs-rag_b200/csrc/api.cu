@@ -1,6 +1,9 @@
 // C ABI entry points (include/b2vs.h): error state, flat index, dispatch, host-buffer search.
+#include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "common.h"
@@ -21,8 +24,56 @@ static std::atomic<uint64_t> g_realloc_generation{1};
 uint64_t realloc_generation() { return g_realloc_generation.load(std::memory_order_acquire); }
 void note_realloc() { g_realloc_generation.fetch_add(1, std::memory_order_acq_rel); }
 
+static int env_int_or(const char* name, int fallback) {
+  const char* e = std::getenv(name);
+  return (e && *e) ? std::atoi(e) : fallback;
+}
+static EnvConfig read_env() {
+  EnvConfig c;
+  if (const char* e = std::getenv("B2VS_TC_GROUP")) c.tc_group = (e[0] == '1' || e[0] == '2') ? e[0] - '0' : 0;
+  if (const char* e = std::getenv("B2VS_PASSES")) {
+    int v[3] = {0, 0, 0};
+    const int got = std::sscanf(e, "%d,%d,%d", &v[0], &v[1], &v[2]);
+    for (int i = 0; i < got && i < 3; ++i)
+      if (v[i] >= 1) c.pass_s[c.pass_n++] = v[i];
+    if (c.pass_n > 0 && c.pass_s[c.pass_n - 1] != 1) c.pass_n = 0;  // the last pass must be the full one
+  }
+  c.no_qpad = std::getenv("B2VS_NO_QPAD") != nullptr;
+  c.ivf_no_rank = std::getenv("B2VS_IVF_NO_RANK") != nullptr;
+  {
+    const int v = env_int_or("B2VS_IVF_GROUPED_CAP", 0);
+    if (v >= 32 && v <= 4096 && (v & (v - 1)) == 0) c.grouped_cap = v;
+  }
+  {
+    const int v = env_int_or("B2VS_IVF_SEED_ROWS", 0);
+    if (v >= 32) c.seed_rows = v;
+  }
+  if (const char* e = std::getenv("B2VS_IVF_GROUPED")) c.ivf_grouped = (e[0] == '0' || e[0] == '1') ? e[0] - '0' : -1;
+  {
+    const int v = env_int_or("B2VS_WORK_CHUNK_TILES", 0);
+    if (v > 0) c.work_chunk_tiles = v;
+  }
+  c.debug_split = std::getenv("B2VS_DEBUG_SPLIT") != nullptr;
+  if (const char* e = std::getenv("B2VS_COARSE_SCAN")) c.coarse_scan = e[0] == '0' ? 0 : 1;
+  c.coarse_scan_maxq = env_int_or("B2VS_COARSE_SCAN_MAXQ", -1);
+  c.coarse_scan_ctas = env_int_or("B2VS_COARSE_SCAN_CTAS", -1);
+  c.no_item_sort = std::getenv("B2VS_NO_ITEM_SORT") != nullptr;
+  if (const char* e = std::getenv("B2VS_GRAPH")) c.graph = e[0] == '0' ? 0 : 1;
+  if (const char* e = std::getenv("B2VS_IVF_SEED")) c.seed_mode = e[0] == '0' ? 0 : 1;
+  return c;
+}
+static EnvConfig g_env;
+static std::once_flag g_env_once;
+static std::mutex g_env_mutex;
+const EnvConfig& env() {
+  std::call_once(g_env_once, [] { g_env = read_env(); });
+  return g_env;
+}
+
 static bool valid_dtype(int d) { return d == B2VS_F32 || d == B2VS_F16 || d == B2VS_BF16; }
-static bool valid_metric(int m) { return m == B2VS_METRIC_L2 || m == B2VS_METRIC_IP; }
+static bool valid_metric(int m) {
+  return m == B2VS_METRIC_L2 || m == B2VS_METRIC_IP || m == B2VS_METRIC_COSINE;
+}
 
 int check_matrix_args(int dev, int metric, int dtype, int dim, const void* db, int64_t n,
                       b2vs_index** out) {
@@ -40,12 +91,25 @@ int check_matrix_args(int dev, int metric, int dtype, int dim, const void* db, i
   return B2VS_OK;
 }
 
+// B2VS_METRIC_COSINE build step: unit-norm copy of the rows (owned by `buf`).
+int cosine_rows(int dtype, int dim, const void* db, int64_t n, cudaStream_t st, DevBuf* buf) {
+  B2VS_TRY(buf->reserve(static_cast<size_t>(std::max<int64_t>(n, 1)) * dim * elem_bytes(dtype)));
+  return launch_unit_rows(db, buf->ptr, dtype, n, dim, st);
+}
+
 }  // namespace b2vs
 
 using namespace b2vs;
 
 extern "C" const char* b2vs_last_error(void) { return g_err; }
 extern "C" int b2vs_version(void) { return B2VS_VERSION; }
+
+extern "C" int b2vs_reload_env(void) {
+  env();  // make sure the once-flag is spent before overwriting
+  std::lock_guard<std::mutex> lock(g_env_mutex);
+  g_env = read_env();
+  return B2VS_OK;
+}
 
 extern "C" int b2vs_device_count(int* count) {
   B2VS_CHECK(count != nullptr, B2VS_EINVAL, "count pointer is NULL");
@@ -68,14 +132,22 @@ extern "C" int b2vs_bf_create(int dev, int metric, int dtype, int dim, const voi
   B2VS_CHECK(ix != nullptr, B2VS_ENOMEM, "host allocation failed");
   ix->kind = B2VS_KIND_FLAT;
   ix->dev = dev;
-  ix->metric = metric;
+  ix->cosine = metric == B2VS_METRIC_COSINE;
+  ix->metric = ix->cosine ? B2VS_METRIC_IP : metric;
   ix->dtype = dtype;
   ix->dim = dim;
   ix->n = n;
   ix->id_offset = id_offset;
-  int rc = ix->flat.init(dev, metric, dtype, dim, db, n, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = B2VS_OK;
+  if (ix->cosine) {
+    rc = cosine_rows(dtype, dim, db, n, st, &ix->cos_rows);
+    db = ix->cos_rows.ptr;
+  }
+  if (rc == B2VS_OK) rc = ix->flat.init(dev, ix->metric, dtype, dim, db, n, st);
   if (rc != B2VS_OK) {
     ix->flat.destroy();
+    ix->cos_rows.release();
     delete ix;
     return rc;
   }
@@ -83,7 +155,7 @@ extern "C" int b2vs_bf_create(int dev, int metric, int dtype, int dim, const voi
   return B2VS_OK;
 }
 
-extern "C" int b2vs_search(b2vs_index* index, const void* queries, int q_dtype, int nq, int k,
+extern "C" int b2vs_search(b2vs_index* index, const void* queries, int q_dtype, int nq, int dim, int k,
                            const b2vs_search_params* params, float* out_d, int64_t* out_i,
                            void* stream) {
   B2VS_CHECK(index != nullptr, B2VS_EINVAL, "index is NULL");
@@ -92,32 +164,46 @@ extern "C" int b2vs_search(b2vs_index* index, const void* queries, int q_dtype, 
   B2VS_CHECK(valid_dtype(q_dtype), B2VS_EINVAL, "unknown query dtype %d", q_dtype);
   B2VS_CHECK(nq >= 1, B2VS_EINVAL, "nq must be positive (got %d)", nq);
   B2VS_CHECK(k >= 1, B2VS_EINVAL, "k must be positive (got %d)", k);
+  B2VS_CHECK(dim == index->dim, B2VS_EINVAL, "queries have dim %d, the index has dim %d", dim, index->dim);
   DeviceGuard guard(index->dev);
   B2VS_CHECK(guard.ok, B2VS_ECUDA, "cannot select device %d", index->dev);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   b2vs_search_params sp{};
   if (params) sp = *params;
+  if (index->cosine) {
+    // unit-norm copy of the batch (same dtype), then the IP engine; 1 - similarity at the end
+    B2VS_TRY(index->cos_q.reserve(static_cast<size_t>(nq) * dim * elem_bytes(q_dtype)));
+    B2VS_TRY(launch_unit_rows(queries, index->cos_q.ptr, q_dtype, nq, dim, st));
+    queries = index->cos_q.ptr;
+  }
+  int rc;
   switch (index->kind) {
     case B2VS_KIND_FLAT:
-      return index->flat.search(queries, q_dtype, nq, k, sp.n_splits, index->id_offset, out_d,
-                                out_i, nullptr, st, sp.flags);
+      rc = index->flat.search(queries, q_dtype, nq, k, sp.n_splits, index->id_offset, out_d, out_i,
+                              nullptr, st, sp.flags);
+      break;
     case B2VS_KIND_IVF_FLAT:
     case B2VS_KIND_IVF_PQ:
-      return ivf_search(index, queries, q_dtype, nq, k, sp, out_d, out_i, st);
+      rc = ivf_search(index, queries, q_dtype, nq, k, sp, out_d, out_i, st);
+      break;
     default:
       set_error("unknown index kind %d", index->kind);
       return B2VS_EINVAL;
   }
+  B2VS_TRY(rc);
+  if (index->cosine) B2VS_TRY(launch_cosine_fixup(out_d, static_cast<int64_t>(nq) * k, st));
+  return B2VS_OK;
 }
 
 extern "C" int b2vs_search_host(b2vs_index* index, const void* queries_host, int q_dtype, int nq,
-                                int k, const b2vs_search_params* params, float* out_d_host,
+                                int dim, int k, const b2vs_search_params* params, float* out_d_host,
                                 int64_t* out_i_host, void* stream) {
   B2VS_CHECK(index != nullptr, B2VS_EINVAL, "index is NULL");
   B2VS_CHECK(queries_host && out_d_host && out_i_host, B2VS_EINVAL,
              "queries / output pointer is NULL");
   B2VS_CHECK(valid_dtype(q_dtype), B2VS_EINVAL, "unknown query dtype %d", q_dtype);
   B2VS_CHECK(nq >= 1 && k >= 1, B2VS_EINVAL, "nq and k must be positive (nq=%d k=%d)", nq, k);
+  B2VS_CHECK(dim == index->dim, B2VS_EINVAL, "queries have dim %d, the index has dim %d", dim, index->dim);
   DeviceGuard guard(index->dev);
   B2VS_CHECK(guard.ok, B2VS_ECUDA, "cannot select device %d", index->dev);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -138,7 +224,7 @@ extern "C" int b2vs_search_host(b2vs_index* index, const void* queries_host, int
   B2VS_CUDA(cudaMemcpyAsync(base, queries_host, qb, cudaMemcpyHostToDevice, st));
   float* d_dev = reinterpret_cast<float*>(base + qb_al);
   int64_t* i_dev = reinterpret_cast<int64_t*>(base + qb_al + db_al);
-  B2VS_TRY(b2vs_search(index, base, q_dtype, nq, k, params, d_dev, i_dev, stream));
+  B2VS_TRY(b2vs_search(index, base, q_dtype, nq, dim, k, params, d_dev, i_dev, stream));
   B2VS_CUDA(cudaMemcpyAsync(out_d_host, d_dev, db, cudaMemcpyDeviceToHost, st));
   B2VS_CUDA(cudaMemcpyAsync(out_i_host, i_dev, ib, cudaMemcpyDeviceToHost, st));
   B2VS_CUDA(cudaStreamSynchronize(st));
@@ -150,12 +236,12 @@ extern "C" int b2vs_index_info_get(const b2vs_index* index, b2vs_index_info* inf
   std::memset(info, 0, sizeof(*info));
   info->kind = index->kind;
   info->device = index->dev;
-  info->metric = index->metric;
+  info->metric = index->cosine ? B2VS_METRIC_COSINE : index->metric;
   info->dtype = index->dtype;
   info->dim = index->dim;
   info->n_rows = index->n;
   info->id_offset = index->id_offset;
-  info->device_bytes = static_cast<int64_t>(index->flat.owned_bytes());
+  info->device_bytes = static_cast<int64_t>(index->flat.owned_bytes() + index->cos_rows.bytes);
   if (index->kind != B2VS_KIND_FLAT) ivf_fill_info(index, info);
   return B2VS_OK;
 }
@@ -177,6 +263,8 @@ extern "C" int b2vs_index_destroy(b2vs_index* index) {
   DeviceGuard guard(index->dev);
   if (index->kind != B2VS_KIND_FLAT) ivf_destroy(index);
   index->flat.destroy();
+  index->cos_rows.release();
+  index->cos_q.release();
   delete index;
   return B2VS_OK;
 }

@@ -95,10 +95,43 @@ inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 int sm_count(int dev);
 
+// Every B2VS_* environment switch (A/B knobs for measurements and tests), read ONCE into this
+// struct at first use: nothing on the search path calls getenv.  b2vs_reload_env() re-reads them
+// (tests flip switches inside one process).
+struct EnvConfig {
+  int tc_group = 0;            // B2VS_TC_GROUP=1|2: force the single-CTA / CTA-pair flat kernel
+  int pass_n = 0;              // B2VS_PASSES="256,16,1": tile strides of the flat passes
+  int pass_s[3] = {0, 0, 0};
+  bool no_qpad = false;        // B2VS_NO_QPAD: stage ragged query blocks through TMA's OOB fill
+  bool ivf_no_rank = false;    // B2VS_IVF_NO_RANK: keep lists in id order (no size ranking)
+  int grouped_cap = 0;         // B2VS_IVF_GROUPED_CAP: candidate-buffer capacity (power of two, 32..4096)
+  int seed_rows = 0;           // B2VS_IVF_SEED_ROWS: seed-sample length (>= 32)
+  int ivf_grouped = -1;        // B2VS_IVF_GROUPED=0|1: force per-item / grouped scans
+  int work_chunk_tiles = 0;    // B2VS_WORK_CHUNK_TILES: row-range size of grouped work items
+  bool debug_split = false;    // B2VS_DEBUG_SPLIT: print the work split
+  int coarse_scan = -1;        // B2VS_COARSE_SCAN=0: always probe on the tensor cores
+  int coarse_scan_maxq = -1;   // B2VS_COARSE_SCAN_MAXQ
+  int coarse_scan_ctas = -1;   // B2VS_COARSE_SCAN_CTAS
+  bool no_item_sort = false;   // B2VS_NO_ITEM_SORT: per-item scan without the list ordering
+  int graph = -1;              // B2VS_GRAPH=0|1: never / always replay small IVF batches as a graph
+  int seed_mode = -1;          // B2VS_IVF_SEED=0|1: legacy seed kernels / seeds from the tensor-core pass
+};
+const EnvConfig& env();
+
 // ------------------------------------------------------------------------------------------
 // The exact-search engine: a [n, kdim] 16-bit K-major matrix + per-row additive term.
 // Used directly by flat indexes and re-used for the coarse quantizer / k-means assignment.
 struct BfTcParams;  // kernel parameters (bf_tc.cuh)
+
+// Hook called between the passes of a flat search with the per-query thresholds of the sampled
+// pass (device, n floats): the sharded search all-reduces them (MIN) across ranks (comm.cu).
+struct TauExchange {
+  int (*fn)(void* ctx, float* tau, int64_t n, cudaStream_t st);
+  void* ctx;
+};
+// True when a flat search over at least `min_rows` rows with this k runs a sampled pass before
+// the full one, i.e. has thresholds to exchange (must evaluate identically on every rank).
+bool flat_exchanges_tau(int64_t min_rows, int k);
 
 struct FlatEngine {
   int dev = 0;
@@ -128,7 +161,8 @@ struct FlatEngine {
   // (dist fp32, id int64 = row + id_offset) when out_d/out_i are given, or as int32 labels
   // (k == 1) when out_label is given.
   int search(const void* q, int q_dtype, int nq, int k, int force_splits, int64_t id_offset,
-             float* out_d, int64_t* out_i, int32_t* out_label, cudaStream_t st, int flags = 0);
+             float* out_d, int64_t* out_i, int32_t* out_label, cudaStream_t st, int flags = 0,
+             const TauExchange* tau_exchange = nullptr);
   int launch_fused(int group, int grid, const CUtensorMap& tm_q, const BfTcParams& p,
                    cudaStream_t st) const;
   void resolve_timing();  // fills stats.kernel_ms once the timed launch has finished
@@ -194,6 +228,10 @@ int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k,
                         int32_t* out_label, cudaStream_t st, const uint32_t* remap = nullptr,
                         float* out_tau = nullptr);
 
+// cosine.cu
+int launch_unit_rows(const void* src, void* dst, int dtype, int64_t n, int dim, cudaStream_t st);
+int launch_cosine_fixup(float* d, int64_t total, cudaStream_t st);
+
 // bigk.cu
 constexpr int kMaxBigK = 2048;
 int launch_bigk_select(const u64* cand, const int* counts, int cap, int nq, int k, int final_pass,
@@ -214,5 +252,9 @@ struct b2vs_index {
   int64_t n = 0;
   int64_t id_offset = 0;
   b2vs::FlatEngine flat;  // flat index, or the coarse quantizer of an IVF index
-  void* ivf = nullptr;    // b2vs::IvfData* (ivf.cu)
+  void* ivf = nullptr;    // b2vs::IvfData* (ivf_internal.cuh)
+  // B2VS_METRIC_COSINE: the index runs as IP (metric == B2VS_METRIC_IP) over an owned unit-norm
+  // copy of the rows; queries are normalised into cos_q and distances leave as 1 - similarity
+  bool cosine = false;
+  b2vs::DevBuf cos_rows, cos_q;
 };

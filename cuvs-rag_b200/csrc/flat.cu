@@ -241,31 +241,13 @@ constexpr int kDefaultTcGroup = 1;
 constexpr int kPairMaxK = 32;   // largest k served by the CTA-pair kernel by default
 
 // B2VS_TC_GROUP=1|2 forces the single-CTA / CTA-pair kernel (bring-up and A/B measurements).
-static int tc_group_override() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = std::getenv("B2VS_TC_GROUP");
-    cached = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
-  }
-  return cached;
-}
+static int tc_group_override() { return env().tc_group; }
 
 // Tile strides of the passes of one search (see FlatEngine::search).  B2VS_PASSES="16,1" etc.
 // overrides the heuristic for A/B measurements.
 static int pass_strides(int64_t tiles, int k, int* strides) {
-  static int env_n = -1, env_s[3];
-  if (env_n < 0) {
-    env_n = 0;
-    const char* e = std::getenv("B2VS_PASSES");
-    if (e) {
-      int a = 0, b = 0, c = 0;
-      const int got = std::sscanf(e, "%d,%d,%d", &a, &b, &c);
-      const int v[3] = {a, b, c};
-      for (int i = 0; i < got && i < 3; ++i)
-        if (v[i] >= 1) env_s[env_n++] = v[i];
-      if (env_n > 0 && env_s[env_n - 1] != 1) env_n = 0;  // the last pass must be the full one
-    }
-  }
+  const int env_n = env().pass_n;
+  const int* env_s = env().pass_s;
   if (k == 1) { strides[0] = 1; return 1; }        // arg-min keeps its state in registers
   if (env_n > 0) {
     int m = 0;
@@ -325,9 +307,15 @@ int FlatEngine::launch_fused(int group, int grid, const CUtensorMap& tm_q, const
   return B2VS_OK;
 }
 
+bool flat_exchanges_tau(int64_t min_rows, int k) {
+  if (k <= 1 || k > kMaxFusedK) return false;
+  int strides[3];
+  return pass_strides(ceil_div(std::max<int64_t>(min_rows, 1), kBN), k, strides) >= 2;
+}
+
 int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_splits,
                        int64_t id_offset, float* out_d, int64_t* out_i, int32_t* out_label,
-                       cudaStream_t st, int flags) {
+                       cudaStream_t st, int flags, const TauExchange* tau_exchange) {
   B2VS_CHECK(nq > 0, B2VS_EINVAL, "nq must be positive (got %d)", nq);
   B2VS_CHECK(k >= 1 && k <= kMaxBigK, B2VS_EUNSUP, "k=%d outside the supported range [1, %d]", k,
              kMaxBigK);
@@ -367,7 +355,7 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   // out-of-bounds fill, which measurably slows the load of that block (the HBM-bound small-batch
   // case loses ~30 %): unless the batch is an exact multiple of the block, queries are copied into
   // a zero-padded operand so every block is fully in bounds.
-  static const bool no_qpad = std::getenv("B2VS_NO_QPAD") != nullptr;  // A/B switch
+  const bool no_qpad = env().no_qpad;  // A/B switch
   const bool borrow_q = !split3 && q_dtype == op_dtype && dp == dim && (nq == q_pad || no_qpad) &&
                         (reinterpret_cast<uintptr_t>(q) & 15) == 0;
   B2VS_TRY(ws_qnorm.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
@@ -457,6 +445,9 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
       // sampled pass: only the k-th best raw score per query is kept, as the next pass's threshold
       B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits * kEpiGroups, q_pad, q_pad, k, metric,
                                    nullptr, 0, nullptr, nullptr, nullptr, st, nullptr, ws_tau.as<float>()));
+      // sharded search: every shard continues with the tightest bound any shard found (a shard's
+      // k-th best sampled score bounds the GLOBAL k-th score from above, so the minimum does too)
+      if (tau_exchange) B2VS_TRY(tau_exchange->fn(tau_exchange->ctx, ws_tau.as<float>(), q_pad, st));
     }
     ++launches;
   }

@@ -8,6 +8,7 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
 void ivf_fill_info(const b2vs_index* index, b2vs_index_info* info);
 void ivf_last_stats(const b2vs_index* index, b2vs_search_stats* stats);
 void ivf_destroy(b2vs_index* index);
+int cosine_rows(int dtype, int dim, const void* db, int64_t n, cudaStream_t st, DevBuf* buf);
 int check_matrix_args(int dev, int metric, int dtype, int dim, const void* db, int64_t n,
                       b2vs_index** out);
 }  // namespace b2vs

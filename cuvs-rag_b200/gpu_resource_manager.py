@@ -67,6 +67,7 @@ class GPUResourceManager:
         self.gpu_configs: List[GPUConfig] = []
         self._device_filter = None if devices is None else [int(d) for d in devices]
         self._streams: Dict[int, Any] = {}
+        self._exchange_comms: Dict[int, Any] = {}
         self._discover_gpus()
 
     # ------------------------------------------------------------------ discovery
@@ -223,6 +224,25 @@ class GPUResourceManager:
             dist.init_process_group(backend=backend, **kwargs)
             return dist.group.WORLD
         return None
+
+    def get_exchange_comm(self, gpu_id: Optional[int] = None):
+        """The library-level communicator of the cross-shard exchange (``_native.Comm`` =
+        ``b2vs_comm*``: NCCL inside the C ABI) for this process's GPU, created on first use from
+        the torch.distributed group (which only carries the 128-byte unique id).  None when the
+        job is not distributed or has no CUDA device."""
+        rank, world = self.get_rank_info()
+        if world <= 1 or not torch.cuda.is_available():
+            return None
+        gid = gpu_id if gpu_id is not None else (self.available_gpus[0] if self.available_gpus else 0)
+        comm = self._exchange_comms.get(gid)
+        if comm is None:
+            try:
+                import _native
+            except ImportError:  # pragma: no cover - package-style import
+                from . import _native
+            comm = _native.Comm.from_torch_distributed(torch.device("cuda", gid))
+            self._exchange_comms[gid] = comm
+        return comm
 
     def get_rank_info(self) -> Tuple[int, int]:
         """(rank, world_size) of this process in the sharded job; (0, 1) when not distributed."""

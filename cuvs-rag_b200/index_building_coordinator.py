@@ -250,7 +250,10 @@ class IndexBuildingCoordinator:
                 if config.index_type == "ivf_flat":
                     ix = _native.NativeIndex.ivf_flat(embeddings, n_lists, **common)
                 else:
-                    ix = _native.NativeIndex.ivf_pq(embeddings, n_lists, int(p.get("pq_dim", 0) or d // 2 or 1),
+                    # reference default: pq_dim = min(64, dim // 4) (index_building_coordinator.py:401),
+                    # snapped to a divisor of dim the engine supports
+                    pq_dim = int(p.get("pq_dim", 0) or _native.NativeIndex.default_pq_dim(d))
+                    ix = _native.NativeIndex.ivf_pq(embeddings, n_lists, pq_dim,
                                                     int(p.get("pq_bits", 8)), **common)
             if stream is not None:
                 stream.synchronize()

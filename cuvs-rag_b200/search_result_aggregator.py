@@ -95,7 +95,10 @@ class SearchConfig:
     """``search_params`` keys understood by the native path: ``n_probes`` (alias ``nprobe``),
     ``refine_ratio``, ``k_local`` (per-shard k, default k), ``collect_gpu_results`` (default
     True: per-shard results are copied to the host into ``gpu_results`` as the reference does),
-    ``graph`` (replay small IVF batches as a CUDA graph), ``allow_partial`` (default False: a shard
+    ``graph`` (replay small IVF batches as a CUDA graph), ``result_layout`` (``"sliced"``: one
+    process per GPU, each rank passes ITS slice of the batch and gets that slice's global answer -
+    see ``_search_sliced``; default: every rank passes and receives the whole batch),
+    ``allow_partial`` (default False: a shard
     that fails fails the search; True: answer from the shards that did respond and list the others
     in ``AggregatedSearchResult.missing_gpus`` / ``shard_errors``)."""
     k: int
@@ -125,10 +128,14 @@ def _host_merge(dist_list: List[np.ndarray], idx_list: List[np.ndarray], k: int,
 def _merge_arrays(dist_list: List[np.ndarray], idx_list: List[np.ndarray], k: int,
                   descending: bool = False, device: Optional[torch.device] = None
                   ) -> Tuple[np.ndarray, np.ndarray]:
-    """Global top-k of per-shard host arrays: runs b2vs_merge_topk on a GPU when one exists."""
+    """Global top-k of per-shard host arrays: runs b2vs_merge_topk on a GPU when one exists.
+    The host merge below is reached ONLY on a box without CUDA (host-side unit tests): on a GPU
+    box a k beyond the kernel's limit raises, like every other limit of the native path."""
     k_total = sum(d.shape[1] for d in dist_list)
     k = min(k, k_total)
-    if torch.cuda.is_available() and k <= _native.MAX_K:
+    if torch.cuda.is_available() and k > _native.MAX_K:
+        raise RuntimeError(f"b2vs_merge_topk failed (code -4): k_out={k} outside [1, {_native.MAX_K}]")
+    if torch.cuda.is_available():
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         k_in = max(d.shape[1] for d in dist_list)
         nq = dist_list[0].shape[0]
@@ -144,7 +151,7 @@ def _merge_arrays(dist_list: List[np.ndarray], idx_list: List[np.ndarray], k: in
 
 
 def allgather_and_merge(d_all: torch.Tensor, i_all: torch.Tensor, k: int, descending: bool = False,
-                        world_size: int = 1) -> Tuple[torch.Tensor, torch.Tensor]:
+                        world_size: int = 1, comm: Any = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Exchange step of the sharded search: ``d_all`` / ``i_all`` are this process's
     [n_local_shards, Q, k'] results (ids already global).  With ``world_size > 1`` (one process per
     GPU under torchrun) every rank all-gathers the other ranks' lists — NCCL over NVLink for CUDA
@@ -152,6 +159,18 @@ def allgather_and_merge(d_all: torch.Tensor, i_all: torch.Tensor, k: int, descen
     the gloo + host-merge route, which exists only so the N>1 host logic is testable without GPUs.
     """
     nq = d_all.shape[1]
+    if world_size > 1 and comm is not None and d_all.is_cuda:
+        # the exchange lives behind the C ABI: one grouped NCCL all-gather (+ K8b)
+        if d_all.shape[0] > 1:   # several local shards: fold them first, then exchange one list
+            k_loc = min(d_all.shape[2] * d_all.shape[0], max(k, d_all.shape[2]))
+            d_loc, i_loc = _native.merge_topk(d_all, i_all, min(k_loc, _native.MAX_K), descending)
+        else:
+            d_loc, i_loc = d_all[0].contiguous(), i_all[0].contiguous()
+        k_eff = min(k, world_size * d_loc.shape[1])
+        if k_eff <= _native.MAX_FUSED_K:
+            return comm.allgather_merge_topk(d_loc, i_loc, k_eff, descending)
+        g_d, g_i = comm.allgather_topk(d_loc, i_loc)
+        return _native.merge_topk(g_d, g_i, k_eff, descending)
     if world_size > 1:
         import torch.distributed as dist
         g_d = torch.empty((world_size,) + tuple(d_all.shape), dtype=d_all.dtype, device=d_all.device)
@@ -261,6 +280,8 @@ class SearchResultAggregator:
                 raise ValueError(f"GPU {g} in indices is not available")
         t0 = time.time()
         params = dict(config.search_params or {})
+        if params.get("result_layout") == "sliced":
+            return self._search_sliced(query, indices, config, params, t0)
         k = config.k
         k_local = int(params.get("k_local", k))
         collect = bool(params.get("collect_gpu_results", True))
@@ -332,7 +353,8 @@ class SearchResultAggregator:
                 torch.cuda.current_stream(primary).wait_stream(torch.cuda.current_stream(r[0].device))
         d_all = torch.stack(d_parts) if len(d_parts) > 1 else d_parts[0].unsqueeze(0)
         i_all = torch.stack(i_parts) if len(i_parts) > 1 else i_parts[0].unsqueeze(0)
-        out_d, out_i = allgather_and_merge(d_all, i_all, k, descending, self._world_size())
+        out_d, out_i = allgather_and_merge(d_all, i_all, k, descending, self._world_size(),
+                                           self._exchange_comm(primary))
         final_d = out_d.cpu().numpy()
         final_i = out_i.cpu().numpy()
         gpu_results = []
@@ -344,6 +366,51 @@ class SearchResultAggregator:
                 gpu_results.append(SearchResult(np.empty((nq, 0), np.float32),
                                                 np.empty((nq, 0), np.int64), g, secs, k_local, 0))
         return final_d, final_i, gpu_results
+
+    def _exchange_comm(self, device):
+        try:
+            return self.gpu_manager.get_exchange_comm(device.index)
+        except Exception as exc:  # noqa: BLE001 - fall back to torch.distributed's collectives
+            logger.warning("library-level exchange communicator unavailable (%s)", exc)
+            return None
+
+    def _search_sliced(self, query: torch.Tensor, indices: Dict[int, Any], config: SearchConfig,
+                       params: Dict[str, Any], t0: float) -> AggregatedSearchResult:
+        """``search_params["result_layout"] == "sliced"`` under torchrun (one process per GPU):
+        ``query`` is THIS rank's slice of the batch (rows ``partition_even(Q, world)[rank]``, host
+        or device).  One ``b2vs_search_sharded`` call does the rest behind the C ABI: the slices
+        are all-gathered over NVLink, every rank searches its shard for all Q queries, the lists
+        are exchanged all-to-all and rank r merges (and downloads) only its own Q/G answers.
+        ``search_params["num_queries_total"]`` gives Q (default: slice rows x world, equal slices)."""
+        if len(indices) != 1:
+            raise ValueError("sliced results need exactly one shard (one process per GPU)")
+        (gpu, index), = indices.items()
+        if not (CUVS_AVAILABLE and isinstance(index, _native.NativeIndex)):
+            raise TypeError("sliced results need a native index on a CUDA device")
+        comm = self.gpu_manager.get_exchange_comm(gpu)
+        if comm is None:
+            raise RuntimeError("sliced results need a distributed job (torchrun, WORLD_SIZE > 1)")
+        nq_total = int(params.get("num_queries_total", query.shape[0] * comm.n_ranks))
+        k = config.k
+        self._active_searches[gpu] = True
+        try:
+            q = query if query.is_contiguous() else query.contiguous()
+            d, i = comm.search_sharded(index, q, nq_total, k,
+                                       n_probes=int(params.get("n_probes", params.get("nprobe", 0)) or 0),
+                                       refine_ratio=int(params.get("refine_ratio", 0) or 0))
+        finally:
+            self._active_searches[gpu] = False
+        final_d = d.cpu().numpy() if d.is_cuda else d.numpy()
+        final_i = i.cpu().numpy() if i.is_cuda else i.numpy()
+        nq = query.shape[0]
+        secs = time.time() - t0
+        gpu_results = [SearchResult(np.empty((nq, 0), np.float32), np.empty((nq, 0), np.int64), gpu, secs,
+                                    k, 0)]
+        if config.validate_results and np.isnan(final_d).any():
+            raise ValueError("merged result contains NaN distances")
+        result = AggregatedSearchResult(final_d, final_i, secs, gpu_results, k, int(final_d.shape[1]), nq)
+        self.search_history.append(result)
+        return result
 
     def _world_size(self) -> int:
         try:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B2VS_VERSION 100
+#define B2VS_VERSION 200
 
 /* status codes */
 #define B2VS_OK 0
@@ -40,9 +40,16 @@ extern "C" {
 #define B2VS_EUNSUP (-4)  /* unsupported combination (e.g. k too large for the fused path) */
 
 /* metric: scores are returned best-first. L2 = squared euclidean, ascending;
- * IP = inner product, descending (FAISS IndexFlatIP convention). */
+ * IP = inner product, descending (FAISS IndexFlatIP convention);
+ * COSINE = cosine DISTANCE 1 - cos(q, x), ascending - scikit-learn's metric='cosine', the
+ * reference's CPU baseline (Attempt_1/VectorSearch_QuestionRetrieval.ipynb:L878).  A cosine index
+ * owns an L2-normalised copy of the rows (x / max(||x||, 1e-12), rounded once into the row
+ * dtype) and normalises every query batch the same way: it is the IP engine on unit vectors.
+ * Callers whose rows are already unit-norm (the encoder hand-off) should ask for IP instead and
+ * keep their rows borrowed. */
 #define B2VS_METRIC_L2 0
 #define B2VS_METRIC_IP 1
+#define B2VS_METRIC_COSINE 2
 
 /* element type of a database / query matrix (row-major [n, dim]) */
 #define B2VS_F32 0
@@ -69,7 +76,8 @@ typedef struct b2vs_search_params {
   int32_t n_probes;       /* IVF: lists scanned per query (cuVS SearchParams.n_probes, default 20);
                              clamped to min(n_lists, 2048) */
   int32_t refine_ratio;   /* IVF-PQ: exact re-rank of min(2048, refine_ratio*k) ADC candidates (0/1 = off;
-                             min(128, ..) on shapes without the grouped scan) */
+                             min(128, ..) on shapes without the grouped scan).  Needs the borrowed source
+                             rows: B2VS_EINVAL when the index was loaded without rows_for_refine */
   int32_t n_splits;       /* flat: force the number of db splits (0 = heuristic) */
   int32_t flags;          /* bit 0: time the dominant kernel with CUDA events (see stats.kernel_ms) */
 } b2vs_search_params;
@@ -102,6 +110,9 @@ typedef struct b2vs_search_stats {
 const char* b2vs_last_error(void);
 int b2vs_version(void);
 int b2vs_device_count(int* count);
+/* Re-reads the B2VS_* environment switches (A/B knobs; they are otherwise read once, at first
+ * use, so nothing on the search path calls getenv).  For tests and measurement tools. */
+int b2vs_reload_env(void);
 
 /* Exact (brute-force) index over `db` ([n, dim], `dtype`) resident on device `dev`.
  * 16-bit databases with dim % 8 == 0 are BORROWED (the caller keeps them alive); fp32
@@ -123,21 +134,25 @@ int b2vs_ivfpq_build(int dev, int metric, int dtype, int dim, const void* db, in
                      int64_t id_offset, const b2vs_ivf_params* params, void* stream,
                      b2vs_index** out);
 
-/* k nearest rows for each of the nq queries ([nq, dim], `q_dtype`, device memory).
+/* k nearest rows for each of the nq queries ([nq, dim], `q_dtype`, device memory).  `dim` must
+ * equal the index dimension (B2VS_EINVAL otherwise: a narrower matrix would be read out of
+ * bounds, a wider one would silently give wrong neighbours).
+ * Searches on ONE index must be serialised by the caller: workspaces, captured graphs and the
+ * statistics live in the index (different indexes / devices may be searched concurrently).
  * k <= 128 on every index kind (fused in-kernel top-k); flat, IVF-Flat and (grouped-scan shapes:
  * dsub 2/4/8, dim % 64 == 0) IVF-PQ indexes also serve 128 < k <= 2048 (append + radix-select
  * paths, which synchronise `stream`).
  * out_d [nq, k] float32 and out_i [nq, k] int64 are caller-owned DEVICE buffers; missing
  * results are (inf | -inf, -1).  Asynchronous on `stream`.  `params` may be NULL. */
-int b2vs_search(b2vs_index* index, const void* queries, int q_dtype, int nq, int k,
+int b2vs_search(b2vs_index* index, const void* queries, int q_dtype, int nq, int dim, int k,
                 const b2vs_search_params* params, float* out_d, int64_t* out_i, void* stream);
 
 /* Same call with HOST buffers: copies queries H2D, searches, copies results D2H and
  * synchronises `stream` before returning (the reference's cuVS calls return host arrays
  * through pylibraft's copy_to_host hook, improved_multi_gpu_rag.py:114). */
-int b2vs_search_host(b2vs_index* index, const void* queries_host, int q_dtype, int nq, int k,
-                     const b2vs_search_params* params, float* out_d_host, int64_t* out_i_host,
-                     void* stream);
+int b2vs_search_host(b2vs_index* index, const void* queries_host, int q_dtype, int nq, int dim,
+                     int k, const b2vs_search_params* params, float* out_d_host,
+                     int64_t* out_i_host, void* stream);
 
 /* Global top-k over per-shard results: d_all / i_all are [n_parts, nq, k_in] (each part sorted
  * best-first, ids already global); writes the best k_out per query.  Ties keep the lower part
@@ -183,6 +198,71 @@ int b2vs_index_load(int dev, const char* path, const void* rows_for_refine, int6
 int b2vs_pool_normalize(int dev, int dtype, const void* hidden, int batch, int seq_len, int dim,
                         const int64_t* attention_mask, int pooling, int normalize, int out_dtype,
                         void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Cross-shard exchange: the NCCL communicator and the collectives of the
+ * sharded search live behind the C ABI, so a caller of this header gets the exchange step too
+ * (the reference concatenates per-GPU results on the host: improved_multi_gpu_rag.py:251-277,
+ * cuvs-2gpu-main.ipynb:L1806-1832).  NCCL is loaded at run time (dlopen "libnccl.so.2"; the copy
+ * already loaded by the host process - e.g. PyTorch's - is reused); B2VS_EUNSUP if it is absent.
+ *
+ * One b2vs_comm per rank (= per GPU).  All collective calls below must be made by every rank of
+ * the communicator in the same order; they are asynchronous on `stream`. */
+typedef struct b2vs_comm b2vs_comm;
+#define B2VS_UNIQUE_ID_BYTES 128
+/* rank 0: fill a 128-byte id and hand it to the other ranks out of band (torch.distributed
+ * broadcast, MPI, a file ...); then every rank calls b2vs_comm_init_rank with the same bytes. */
+int b2vs_comm_unique_id(void* id128);
+int b2vs_comm_init_rank(int dev, int n_ranks, int rank, const void* id128, b2vs_comm** out);
+/* single process driving n GPUs (the reference's thread-per-GPU mode): comms[i] is the
+ * communicator of rank i on device devs[i] */
+int b2vs_comm_init_all(int n, const int* devs, b2vs_comm** comms);
+int b2vs_comm_info(const b2vs_comm* comm, int* n_ranks, int* rank, int* dev);
+int b2vs_comm_destroy(b2vs_comm* comm);
+
+/* Row range [*begin, *end) of rank `rank` when `n` items are split into `n_parts` contiguous
+ * near-equal parts (remainder to the first parts): the reference's 'even' strategy
+ * (gpu_resource_manager.py:190-202), used for database rows AND for the query slices below. */
+int b2vs_partition_even(int64_t n, int n_parts, int rank, int64_t* begin, int64_t* end);
+
+/* Query all-gather: rank r holds its slice q_local = rows partition_even(nq_total, n_ranks)[r] of
+ * the batch; afterwards q_all [nq_total, dim] is complete on every rank (each rank uploads 1/G of
+ * the batch over PCIe and NVLink carries the rest). */
+int b2vs_allgather_queries(b2vs_comm* comm, const void* q_local, int q_dtype, int nq_total, int dim,
+                           void* q_all, void* stream);
+/* Per-shard top-k all-gather: d_local / i_local [nq, k] -> d_all / i_all [n_ranks, nq, k] on every
+ * rank, both buffers in ONE NCCL group (one collective launch). */
+int b2vs_allgather_topk(b2vs_comm* comm, const float* d_local, const int64_t* i_local, int nq, int k,
+                        float* d_all, int64_t* i_all, void* stream);
+/* All-gather + b2vs_merge_topk: every rank ends with the global top-k_out of all nq queries
+ * (out_d / out_i [nq, k_out]).  k <= 128. */
+int b2vs_allgather_merge_topk(b2vs_comm* comm, const float* d_local, const int64_t* i_local, int nq,
+                              int k, int k_out, int descending, float* out_d, int64_t* out_i,
+                              void* stream);
+/* All-to-all + merge: rank r receives from every rank the lists of ITS query slice
+ * partition_even(nq, n_ranks)[r] and merges only those: out_d / out_i [slice rows, k_out].  Per
+ * rank this moves and merges 1/G of what the all-gather variant does; the batch's answer is then
+ * distributed like its queries were (rank r answers the queries rank r uploaded). */
+int b2vs_exchange_merge_topk(b2vs_comm* comm, const float* d_local, const int64_t* i_local, int nq,
+                             int k, int k_out, int descending, float* out_d, int64_t* out_i,
+                             void* stream);
+/* In-place element-wise MIN all-reduce of a float vector (per-query threshold exchange). */
+int b2vs_allreduce_min_f32(b2vs_comm* comm, float* values, int64_t n, void* stream);
+
+/* The whole sharded step behind one call: all-gather of the query slices, local search of this
+ * rank's shard - flat indexes exchange their per-query thresholds after the sampled pass, so
+ * every shard runs its full pass against the GLOBAL k-th bound - then all-to-all + merge.
+ * q_local: this rank's query slice (device); out_d / out_i [slice rows, k] device.
+ * The local per-shard result is NOT the shard's full top-k in this mode (rows that cannot be in
+ * the global top-k are skipped), which is why it is not returned. */
+int b2vs_search_sharded(b2vs_comm* comm, b2vs_index* index, const void* q_local, int q_dtype,
+                        int nq_total, int dim, int k, const b2vs_search_params* params, float* out_d,
+                        int64_t* out_i, void* stream);
+/* Same with HOST buffers: H2D of the slice, the step above, D2H of the slice's answer, stream
+ * synchronised before returning. */
+int b2vs_search_sharded_host(b2vs_comm* comm, b2vs_index* index, const void* q_local_host, int q_dtype,
+                             int nq_total, int dim, int k, const b2vs_search_params* params,
+                             float* out_d_host, int64_t* out_i_host, void* stream);
 
 #ifdef __cplusplus
 }
