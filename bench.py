@@ -1,14 +1,26 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the retrieval hot path (contract: see DESIGN.md §Measurement).
+"""bench.py — benchmark of the retrieval hot path (contract: DESIGN.md §Measurement).
 
-Workload (BASELINE.json configs[1], "C2"): exact squared-L2 search, k=100, 10 M x 768 bf16
+Headline workload (BASELINE.json configs[1], "C2"): exact squared-L2 search, k=100, 10 M x 768 bf16
 database sharded by contiguous row ranges over N GPUs (10 M / N rows each: strong scaling),
-10 K-query batches; every rank searches its shard with the fused tcgen05 kernel, the per-shard
-top-k lists are all-gathered over NCCL/NVLink and merged on the GPU (K8).  A "step" = one
-10 K-query batch.  Metric = whole-job queries per second.
+10 K-query batches.  One process per GPU.  A "step" = one 10 K-query batch:
+  N = 1   index.search on the resident batch                                  (device-timed `value`)
+  N > 1   b2vs_search_sharded: every rank holds 1/N of the batch; the slices are all-gathered over
+          NVLink, every rank searches its shard (thresholds exchanged after the sampled pass), the
+          per-shard lists go all-to-all and rank r merges / returns the answers of its own slice.
+`e2e` is the same step through SearchResultAggregator.perform_distributed_search with HOST buffers
+(H2D of the queries + D2H of the answers inside the timed region).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]          # our arm
-  python bench.py --impl reference ...                          # CPU arm (FAISS-IndexFlat restatement)
+The same JSON line carries `configs`: sub-records for the other BASELINE configs, each with QPS at
+k=10, recall@10 against the exact index on the same corpus, ms_per_step, a CUDA-event kernel_ms of
+the dominant kernel and a roofline entry:
+  C1        exact IP k=10, 100K x 384 fp32 unit-norm rows, 1K queries (replicated, not sharded)
+  C3        IVF-Flat n_lists=4096 n_probes=32, 10M x 768 fp16 (row-sharded over N)
+  C4_shard  IVF-PQ n_lists=16384 M=64 8-bit, 12.5M x 128 fp16 PER GPU (N = 8: the 100M config)
+  C5        exact L2 k=10, 50M x 1024 bf16 (row-sharded over N), Q in {1, 64, 1024, 16384}
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--configs C1,C3,C4,C5|none]   # our arm
+  python bench.py --impl reference ...                     # CPU arm (FAISS-IndexFlat restatement)
 
 Prints ONE JSON line (rank 0).
 """
@@ -32,6 +44,7 @@ DIM = 768
 N_QUERIES = 10_000
 K = 100
 METRIC_NAME = "QPS at k=100 exact L2 (10M x 768 bf16, 10K-query batches, global top-k merge)"
+N_PLANTED = 64       # known-answer queries inside every timed batch (rows of the corpus itself)
 
 
 def parse_args():
@@ -47,6 +60,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-queries", type=int, default=1000)
+    ap.add_argument("--configs", default="C1,C3,C4,C5",
+                    help="sub-records to run after the headline (comma list of C1,C3,C4,C5; 'none')")
+    ap.add_argument("--scale", type=float, default=1.0,
+                    help="row-count multiplier of the sub-record corpora (bring-up; 1.0 = BASELINE sizes)")
+    ap.add_argument("--ivf-latent-dim", type=int, default=32,
+                    help="intrinsic dimension of the IVF corpora (see ivf_corpus)")
     return ap.parse_args()
 
 
@@ -56,14 +75,17 @@ def load_peaks():
         with open(path) as f:
             p = json.load(f)
         return {"tflops": float(p.get("bf16_tflops_sustained") or p["bf16_tflops"]),
-                "hbm_gbs": float(p["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json, sustained)"}
+                "tflops_burst": float(p["bf16_tflops"]),
+                "hbm_gbs": float(p["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
     except Exception:
-        return {"tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+        return {"tflops": 1400.0, "tflops_burst": 1650.0, "hbm_gbs": 6650.0,
+                "source": "fallback (B200_PROFILING.md)"}
 
 
 def ncu_traffic(world, args):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/r1_c2_bf_tc_fullpass_v2.csv); only valid for the exact configuration it was taken on."""
+    """DRAM bytes per launch of the dominant kernel from the COMMITTED ncu --set full capture
+    (profiles/r1_c2_bf_tc_fullpass_v2.csv); only valid for the exact configuration it was taken on.
+    Not measured in this run: the line tags it `traffic_source`."""
     if world != 1 or (args.n_db, args.dim, args.queries, args.k) != (N_DB, DIM, N_QUERIES, K):
         return None
     try:
@@ -77,6 +99,20 @@ def ncu_traffic(world, args):
             i = h.index(name)
             tot += float(v[i]) * scale.get(units[i], 1.0)
         return tot
+    except Exception:
+        return None
+
+
+def ncu_traffic_named(fname):
+    """Same for a sub-record kernel (profiles/<fname>), or None when no capture is committed."""
+    try:
+        import csv
+        with open(os.path.join(ROOT, "profiles", fname)) as f:
+            rows = list(csv.reader(f))
+        h, units, v = rows[0], rows[1], rows[2]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        return sum(float(v[h.index(n)]) * scale.get(units[h.index(n)], 1.0)
+                   for n in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     except Exception:
         return None
 
@@ -198,9 +234,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     rows = min(args.cpu_sample_rows, args.n_db)
     nq = min(args.cpu_sample_queries, args.queries)
-    # each "step" = one bounded sample; extrapolate linearly in rows to the full database
-    # W warm-up steps on a tenth of the sample (thread pool, page faults), then K timed steps
-    # (capped at 50: a step is ~3 s of all host cores)
+    # each "step" = one bounded sample; W warm-up steps on a tenth of the sample (thread pool, page
+    # faults), then K timed steps (capped at 50: a step is ~3 s of all host cores)
     n_warm = max(0, min(args.warmup, 5))
     for _ in range(n_warm):
         cpu_exact_qps(min(rows, 100_000), args.dim, min(nq, 128), args.k, cores)
@@ -219,11 +254,15 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC_NAME, "value": qps_full, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": n_warm,
-        "ms_per_step": dt * 1e3 * (args.n_db / rows) * (args.queries / nq),
+        # the MEASURED duration of one timed step (= one bounded sample); the extrapolation to the
+        # full database lives in `value` / `sample` only
+        "ms_per_step": dt * 1e3,
+        "ms_per_full_batch_extrapolated": dt * 1e3 * (args.n_db / rows) * (args.queries / nq),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "C2 exact L2 k=100 10Mx768, CPU host cores", "n_db": args.n_db,
-                   "dim": args.dim, "queries_per_batch": args.queries, "k": args.k},
+        "config": {"workload": workload_name(args), "n_db": args.n_db,
+                   "dim": args.dim, "queries_per_batch": args.queries, "k": args.k,
+                   "host": "CPU host cores, bounded sample per step"},
         "cpu_baseline": {"value": qps_full, "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": qps_full, "unit": "queries/s", "h2d_bytes_per_step": 0,
@@ -236,43 +275,352 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def workload_name(args):
+    return (f"C2: exact L2 k={args.k}, {args.n_db // 1_000_000}Mx{args.dim} bf16 row-sharded, "
+            f"{args.queries // 1000}K-query batches, global top-k merge")
+
+
+# =============================================================================================
+# helpers shared by the headline and the sub-records
+class Job:
+    """Per-process context: device, ranks, the library-level exchange communicator."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        import cuvs_rag_b200 as b2
+        self.b2, self.dist = b2, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group(backend="nccl", device_id=self.dev)
+        self.grm = b2.GPUResourceManager(devices=[self.local_rank])
+        self.comm = self.grm.get_exchange_comm(self.local_rank) if self.world > 1 else None
+        self.peaks = load_peaks()
+
+    def sync_all(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def query_slice(self, nq):
+        return self.b2.partition_even(nq, self.world)[self.rank]
+
+    def timed(self, fn, steps, warmup):
+        """W warm-ups, then K steps bracketed by barrier + synchronize; device-timed, max over ranks."""
+        for _ in range(warmup):
+            fn()
+        self.sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.sync_all()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps
+
+
+def planted_rows(job, shard, start, n_total, count, seed):
+    """`count` rows of the GLOBAL corpus at seeded global ids, identical on every rank (the owner of
+    a row contributes it, one all-reduce).  Returns (ids int64 [count], rows fp32 [count, D])."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randperm(n_total, generator=g)[:count].sort().values
+    rows = torch.zeros((count, shard.shape[1]), dtype=torch.float32, device=job.dev)
+    local = ids - start
+    own = (local >= 0) & (local < shard.shape[0])
+    if own.any():
+        rows[own.to(job.dev)] = shard[local[own].to(job.dev)].float()
+    if job.world > 1:
+        job.dist.all_reduce(rows, op=job.dist.ReduceOp.SUM)
+    return ids, rows
+
+
+def gen_randn_rows(n, d, dtype, dev, seed, chunk=1 << 20):
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    out = torch.empty((n, d), dtype=dtype, device=dev)
+    for s in range(0, n, chunk):
+        e = min(s + chunk, n)
+        out[s:e] = torch.randn((e - s, d), generator=gen, device=dev, dtype=torch.float32).to(dtype)
+    return out
+
+
+def ivf_corpus(n, d, latent, dtype, dev, seed, basis_seed=777, chunk=1 << 20):
+    """Synthetic embedding-like corpus with LOW INTRINSIC DIMENSION: x = z W + 0.05 eps with
+    z ~ N(0, I_latent), W a fixed [latent, d] Gaussian basis (shared by every shard and by the
+    queries), eps ~ N(0, I_d).  Unlike a mixture of well-separated blobs (round 1) an IVF index does
+    not get recall 1.0 for finding "the right cluster": neighbourhoods straddle list boundaries, so
+    recall genuinely depends on n_probes.  Queries are INDEPENDENT draws from the same law (seeded
+    differently), never perturbed database rows.  (iid N(0, I_d) data - SURVEY §8d's other corpus -
+    has no structure at all in 768-d: it is what tests/test_gpu_ivf_parity.py uses.)"""
+    gb = torch.Generator(device=dev).manual_seed(basis_seed)
+    w = torch.randn((latent, d), generator=gb, device=dev) / (latent ** 0.5)    # unit variance per dim
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    out = torch.empty((n, d), dtype=dtype, device=dev)
+    for s in range(0, n, chunk):
+        e = min(s + chunk, n)
+        z = torch.randn((e - s, latent), generator=gen, device=dev)
+        x = z @ w
+        x.add_(torch.randn((e - s, d), generator=gen, device=dev), alpha=0.05)
+        out[s:e] = x.to(dtype)
+    return out
+
+
+def recall_at_k(job, ids, truth):
+    """|ids ∩ truth| / |truth| over this rank's query slice, summed over ranks."""
+    a = ids.unsqueeze(2) == truth.unsqueeze(1)          # [q, k, k]
+    hits = float(a.any(dim=2).sum().item())
+    denom = float((truth >= 0).sum().item())
+    return job.sum_over_ranks(hits) / max(job.sum_over_ranks(denom), 1.0)
+
+
+def sharded_search(job, index, q_all, q_slice, k, **kw):
+    """The search of this job's layout: plain index.search on one GPU, b2vs_search_sharded (slice
+    in, slice answers out) on several."""
+    if job.world == 1:
+        return index.search(q_all, k, **kw)
+    return job.comm.search_sharded(index, q_slice, q_all.shape[0], k, **kw)
+
+
+# =============================================================================================
+# sub-records
+def roofline_entry(bound, achieved, peak, unit, kernel, kernel_ms, source, **extra):
+    e = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+         "frac": (achieved / peak) if (achieved and peak) else None, "kernel": kernel,
+         "kernel_ms": kernel_ms, "peak_source": source, "traffic": None,
+         "traffic_source": "not captured for this kernel"}
+    e.update(extra)
+    return e
+
+
+def run_c1(job, args):
+    """BASELINE configs[0]: exact inner product k=10, 100K x 384 fp32 unit-norm (MiniLM-shaped) rows,
+    1K queries - FAISS IndexFlatIP.  Too small to shard: every rank runs it whole (replica)."""
+    b2 = job.b2
+    n, d, nq, k = 100_000, 384, 1000, 10
+    g = torch.Generator().manual_seed(4321)
+    db = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1)
+    qs = torch.nn.functional.normalize(torch.randn(nq, d, generator=g), dim=1)
+    x, q = db.to(job.dev), qs.to(job.dev)
+    ix = b2.NativeIndex.flat(x, metric="inner_product")
+    out = (torch.empty((nq, k), dtype=torch.float32, device=job.dev),
+           torch.empty((nq, k), dtype=torch.int64, device=job.dev))
+    steps, warm = 200, 20
+    ms = job.timed(lambda: ix.search(q, k, out=out), steps, warm)
+    kms = []
+    for _ in range(20):
+        ix.search(q, k, out=out, time_kernel=True)
+        kms.append(ix.last_stats().kernel_ms)
+    kernel_ms = sum(kms) / len(kms)
+    st = ix.last_stats()
+    # parity against the CPU oracle (the whole config runs on CPU in < 1 s)
+    from oracle.exact import exact_knn, topk_parity_report
+    _, ti = exact_knn(db, qs, k, "inner_product")
+    rep = topk_parity_report(out[0].cpu(), out[1].cpu(), db, qs, k, metric="inner_product")
+    rec = recall_at_k(job, out[1], ti.to(job.dev)) if job.world == 1 else \
+        float((out[1].cpu().unsqueeze(2) == ti.unsqueeze(1)).any(2).sum()) / ti.numel()
+    flops = 2.0 * nq * n * d
+    rec_out = {
+        "workload": "C1: exact IP k=10, 100Kx384 fp32 unit-norm, 1K queries (replicated per GPU)",
+        "value": nq / (ms * 1e-3), "unit": "queries/s", "k": k, "ms_per_step": ms, "steps": steps,
+        "recall_at_10": rec, "parity": {"ok": rep["ok"], "exact_id_match": rep["exact_id_match"],
+                                        "against": "oracle.exact (fp32 CPU)"},
+        "gpu_launches_per_step": st.launches, "dtype": "f32 as bf16 [hi|hi|lo] x [hi|lo|hi] (3x MMA work)",
+        "roofline": roofline_entry("tensor", flops / (kernel_ms * 1e-3) / 1e12 if kernel_ms else None,
+                                   job.peaks["tflops_burst"], "TFLOP/s", "bf_tc_kernel", kernel_ms,
+                                   job.peaks["source"] + ", burst (sub-ms kernel timed alone)",
+                                   algorithmic_flops_per_launch=flops,
+                                   note="algorithmic 2*Q*N*D; the fp32 emulation issues 3x that on the tensor pipe"),
+    }
+    ix.destroy()
+    return rec_out
+
+
+def run_ivf(job, args, name):
+    """C3 (IVF-Flat) / C4_shard (IVF-PQ): build on this rank's shard, search the 10K-query batch
+    through the job's layout, recall@10 against the exact index over the SAME rows."""
+    b2 = job.b2
+    nq, k = 10_000, 10
+    if name == "C3":
+        n_total, d, n_lists, n_probes, refine, dtype = int(10_000_000 * args.scale), 768, 4096, 32, 0, torch.float16
+        start, end = b2.partition_even(n_total, job.world)[job.rank]
+        kind, layout = "ivf_flat", f"row-sharded over {job.world} GPU(s), {n_lists} lists per shard"
+    else:
+        n_shard, d, n_lists, n_probes, refine, dtype = int(12_500_000 * args.scale), 128, 16384, 64, 4, torch.float16
+        n_total = n_shard * job.world
+        start, end = job.rank * n_shard, (job.rank + 1) * n_shard
+        kind, layout = "ivf_pq", f"{job.world} shard(s) of 12.5M rows (8 = the 100M config), M=64 x 8 bit, refine 4"
+    n_lists = max(16, min(n_lists, (end - start) // 64))
+    x = ivf_corpus(end - start, d, args.ivf_latent_dim, dtype, job.dev, seed=5000 + job.rank)
+    q_all = ivf_corpus(nq, d, args.ivf_latent_dim, dtype, job.dev, seed=99)      # same on every rank
+    qb, qe = job.query_slice(nq)
+    q_slice = q_all[qb:qe].contiguous()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    if kind == "ivf_flat":
+        ix = b2.NativeIndex.ivf_flat(x, n_lists, id_offset=start, kmeans_iters=20)
+    else:
+        ix = b2.NativeIndex.ivf_pq(x, n_lists, 64, id_offset=start, kmeans_iters=20)
+    torch.cuda.synchronize()
+    build_s = job.max_over_ranks(time.perf_counter() - t0)
+    kw = dict(n_probes=n_probes, refine_ratio=refine)
+    # exact ground truth over the same rows, same layout
+    flat = b2.NativeIndex.flat(x, id_offset=start)
+    _, truth = sharded_search(job, flat, q_all, q_slice, k)
+    truth = truth.clone()
+    flat.destroy()
+    steps, warm = 20, 3
+    res = {}
+
+    def step():
+        res["out"] = sharded_search(job, ix, q_all, q_slice, k, **kw)
+    ms = job.timed(step, steps, warm)
+    rec = recall_at_k(job, res["out"][1], truth)
+    kms = []
+    for _ in range(5):
+        sharded_search(job, ix, q_all, q_slice, k, time_kernel=True, **kw)
+        kms.append(ix.last_stats().kernel_ms)
+    kernel_ms = sum(kms) / len(kms)
+    st = ix.last_stats()
+    distinct = st.distinct_bytes
+    hbm = job.peaks["hbm_gbs"]
+    kernel = "bf_tc_kernel<1,true> (grouped list scan)" if kind == "ivf_flat" else "pq_tc_kernel (grouped PQ scan)"
+    rl = roofline_entry("hbm", distinct / (kernel_ms * 1e-3) / 1e9 if kernel_ms else None, hbm, "GB/s", kernel,
+                        kernel_ms, job.peaks["source"],
+                        algorithmic_bytes=distinct,
+                        algorithmic_bytes_def="distinct probed list bytes of this rank's shard (b2vs_index_last_stats.distinct_bytes)",
+                        per_probe_bytes=st.algo_bytes,
+                        batch_frac=(distinct / (ms * 1e-3) / 1e9 / hbm) if ms else None,
+                        batch_frac_def="distinct bytes / whole-step time / HBM peak (seed, probe, gather, select, exchange included)")
+    cap = {"C3": "r2_c3_ivf_flat_grouped_tc.csv", "C4_shard": "r2_c4_pq_tc_kernel.csv"}[name]
+    tr = ncu_traffic_named(cap) if (job.world == 1 and args.scale == 1.0) else None
+    if tr is not None:
+        rl["traffic"], rl["traffic_source"] = tr, f"committed ncu capture profiles/{cap}"
+    out = {
+        "workload": f"{name}: {kind} n_lists={n_lists} n_probes={n_probes}, {n_total} x {d} fp16, "
+                    f"{nq}-query batches, k={k}; {layout}",
+        "value": nq / (ms * 1e-3), "unit": "queries/s", "k": k, "ms_per_step": ms, "steps": steps,
+        "recall_at_10": rec, "recall_against": "exact (flat) index over the same rows, same layout",
+        "build_s": build_s, "rows_per_gpu": end - start, "n_probes": n_probes, "refine_ratio": refine,
+        "mean_candidates_per_query": st.mean_candidates, "gpu_launches_per_step": st.launches,
+        "corpus": f"latent-{args.ivf_latent_dim} Gaussian factor model + 0.05 noise, independent queries",
+        "roofline": rl,
+    }
+    ix.destroy()
+    del x
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_c5(job, args):
+    """BASELINE configs[4]: exact L2 k=10 on 50M x 1024 bf16 (row-sharded over N), batch sweep."""
+    b2 = job.b2
+    n_total, d, k = int(50_000_000 * args.scale), 1024, 10
+    start, end = b2.partition_even(n_total, job.world)[job.rank]
+    free, _ = torch.cuda.mem_get_info(job.dev)
+    need = (end - start) * d * 2 + (8 << 30)
+    if free < need:
+        return {"workload": "C5", "skipped": f"needs {need >> 30} GiB free, device has {free >> 30} GiB"}
+    x = gen_randn_rows(end - start, d, torch.bfloat16, job.dev, seed=7000 + job.rank, chunk=1 << 19)
+    ix = b2.NativeIndex.flat(x, id_offset=start)
+    ids, rows = planted_rows(job, x, start, n_total, 16, seed=71)
+    sweep = {}
+    for nq in (1, 64, 1024, 16384):
+        if job.world > nq:      # fewer queries than ranks: slices would be empty
+            continue
+        gq = torch.Generator(device=job.dev).manual_seed(4242 + nq)
+        q_all = torch.randn((nq, d), generator=gq, device=job.dev).to(torch.bfloat16)
+        n_pl = min(nq, 16)
+        q_all[:n_pl] = rows[:n_pl].to(torch.bfloat16)
+        qb, qe = job.query_slice(nq)
+        q_slice = q_all[qb:qe].contiguous()
+        steps, warm = (10, 3) if nq <= 64 else ((5, 2) if nq <= 1024 else (3, 1))
+        res = {}
+
+        def step():
+            res["out"] = sharded_search(job, ix, q_all, q_slice, k)
+        ms = job.timed(step, steps, warm)
+        dd, ii = res["out"]
+        # known answers: the planted rows come back first, at distance ~0 (rank slices hold [qb, qe))
+        lo, hi = max(qb, 0), min(qe, n_pl)
+        ok = 1.0
+        if hi > lo:
+            ok = float(bool((ii[lo - qb:hi - qb, 0].cpu() == ids[lo:hi]).all()) and
+                       bool((dd[lo - qb:hi - qb, 0] < 1e-2 * d).all()))
+        ok = job.sum_over_ranks(ok) == job.world
+        kms = []
+        for _ in range(2):
+            sharded_search(job, ix, q_all, q_slice, k, time_kernel=True)
+            kms.append(ix.last_stats().kernel_ms)
+        kernel_ms = sum(kms) / len(kms)
+        n_local = end - start
+        flops = 2.0 * nq * n_local * d
+        byts = float(n_local) * d * 2
+        ridge = job.peaks["tflops"] * 1e12 / (job.peaks["hbm_gbs"] * 1e9)    # FLOP per byte
+        if 2.0 * nq / 2 < ridge:    # 2*Q FLOP per 2-byte element -> Q FLOP per byte
+            rl = roofline_entry("hbm", byts / (kernel_ms * 1e-3) / 1e9 if kernel_ms else None,
+                                job.peaks["hbm_gbs"], "GB/s", "bf_tc_kernel", kernel_ms, job.peaks["source"],
+                                algorithmic_bytes=byts)
+        else:
+            peak = job.peaks["tflops"] if kernel_ms > 100 else job.peaks["tflops_burst"]
+            rl = roofline_entry("tensor", flops / (kernel_ms * 1e-3) / 1e12 if kernel_ms else None, peak,
+                                "TFLOP/s", "bf_tc_kernel", kernel_ms,
+                                job.peaks["source"] + (", sustained" if kernel_ms > 100 else ", burst"),
+                                algorithmic_flops_per_launch=flops)
+        sweep[str(nq)] = {"value": nq / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "steps": steps,
+                          "known_answers_ok": ok, "roofline": rl}
+    out = {"workload": f"C5: exact L2 k={k}, {n_total} x {d} bf16 row-sharded over {job.world} GPU(s), batch sweep",
+           "k": k, "rows_per_gpu": end - start, "batch_sweep": sweep}
+    ix.destroy()
+    del x
+    torch.cuda.empty_cache()
+    return out
+
+
+# =============================================================================================
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
 
-    import torch.distributed as dist
-    import cuvs_rag_b200 as b2
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group(backend="nccl", device_id=dev)
-
-    # ---- the reference-facing objects (drop-in surface)
-    grm = b2.GPUResourceManager(devices=[local_rank])
-    edm = b2.EmbeddingDistributionManager(grm)
+    job = Job()
+    b2, dist = job.b2, job.dist
+    world, rank, local_rank, dev = job.world, job.rank, job.local_rank, job.dev
+    grm = job.grm
     ibc = b2.IndexBuildingCoordinator(grm)
     sra = b2.SearchResultAggregator(grm)
 
     # ---- synthetic shard, generated on the device (reference style: torch.randn, unseeded there)
     start, end = b2.partition_even(args.n_db, world)[rank]
     n_local = end - start
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    shard = torch.empty((n_local, args.dim), dtype=torch.bfloat16, device=dev)
-    chunk = 1 << 20
-    for s in range(0, n_local, chunk):
-        e = min(s + chunk, n_local)
-        shard[s:e] = torch.randn((e - s, args.dim), generator=gen, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    shard = gen_randn_rows(n_local, args.dim, torch.bfloat16, dev, seed=1234 + rank)
     qgen = torch.Generator(device="cpu").manual_seed(4321)
-    q_host = torch.randn((args.queries, args.dim), generator=qgen).to(torch.bfloat16).pin_memory()
-    q_dev = q_host.to(dev)
+    q_full = torch.randn((args.queries, args.dim), generator=qgen)
+    # known answers inside the timed batch: its first rows ARE rows of the (global) corpus
+    n_pl = min(N_PLANTED, args.queries)
+    pl_ids, pl_rows = planted_rows(job, shard, start, args.n_db, n_pl, seed=17)
+    q_full[:n_pl] = pl_rows.cpu()
+    q_host_all = q_full.to(torch.bfloat16)
+    qb, qe = job.query_slice(args.queries)
+    q_host = q_host_all[qb:qe].contiguous().pin_memory()      # this rank's slice of the batch
+    q_dev_all = q_host_all.to(dev)
+    q_dev = q_dev_all[qb:qe].contiguous()
 
     part = b2.EmbeddingPart(local_rank, shard, start, end)
     cfg = b2.IndexBuildConfig("brute_force", {"metric": "sqeuclidean"}, parallel_build=False, max_retries=0)
@@ -282,43 +630,20 @@ def main():
     index = res.index
     ibc.built_indices[local_rank] = index
 
-    out_d = torch.empty((args.queries, args.k), dtype=torch.float32, device=dev)
-    out_i = torch.empty((args.queries, args.k), dtype=torch.int64, device=dev)
-    if world > 1:
-        g_d = torch.empty((world, args.queries, args.k), dtype=torch.float32, device=dev)
-        g_i = torch.empty((world, args.queries, args.k), dtype=torch.int64, device=dev)
+    out_d = torch.empty((qe - qb, args.k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((qe - qb, args.k), dtype=torch.int64, device=dev)
 
-    phase_ev = []   # (start, after search, after all-gather, after merge) event tuples, N > 1
-
-    def step_device(time_kernel=False, phases=False):
-        """One batch with inputs resident in HBM: local search -> all-gather -> merge."""
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if phases and world > 1 else None
-        if ev:
-            ev[0].record()
-        index.search(q_dev, args.k, out=(out_d, out_i), time_kernel=time_kernel)
-        if world > 1:
-            if ev:
-                ev[1].record()
-            dist.all_gather_into_tensor(g_d, out_d)
-            dist.all_gather_into_tensor(g_i, out_i)
-            if ev:
-                ev[2].record()
-            res = b2.merge_topk(g_d, g_i, args.k, descending=False)
-            if ev:
-                ev[3].record()
-                phase_ev.append(ev)
-            return res
-        return out_d, out_i
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def step_device(time_kernel=False):
+        """One batch with inputs resident in HBM (each rank: its query slice)."""
+        if world == 1:
+            return index.search(q_dev, args.k, out=(out_d, out_i), time_kernel=time_kernel)
+        return job.comm.search_sharded(index, q_dev, args.queries, args.k, time_kernel=time_kernel,
+                                       out=(out_d, out_i))
 
     # ---- warm-up
     for _ in range(args.warmup):
         step_device()
-    sync_all()
+    job.sync_all()
 
     # ---- timed region (device timed, inputs resident; db shard >> L2 so no flush is needed)
     sampler = ClockSampler(local_rank)
@@ -327,46 +652,90 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
     launches = 0
-    sync_all()
+    job.sync_all()
     e0.record()
     for _ in range(args.steps):
-        step_device(time_kernel=True, phases=True)
+        step_device(time_kernel=True)
         st = index.last_stats()   # resolves the event pair of this step's fused kernel
         kernel_ms.append(st.kernel_ms)
-        launches += st.launches + (1 if world > 1 else 0)
+        launches += st.launches + (4 if world > 1 else 0)   # + query all-gather, tau all-reduce, exchange, merge
     e1.record()
-    sync_all()
-    ms_total = e0.elapsed_time(e1)
+    job.sync_all()
+    ms_total = job.max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
     qps = args.queries * args.steps / (ms_total * 1e-3)
     stats = index.last_stats()
 
-    # ---- e2e: the user-facing call with HOST buffers (H2D + search + merge + D2H every step)
-    scfg = b2.SearchConfig(k=args.k, search_params={"collect_gpu_results": False},
-                           parallel_search=False, validate_results=False)
+    # ---- known answers across real ranks: query j < n_pl is global row pl_ids[j] -> first hit
+    lo, hi = qb, min(qe, n_pl)
+    known_ok = 1.0
+    if hi > lo:
+        known_ok = float(bool((out_i[:hi - lo, 0].cpu() == pl_ids[lo:hi]).all()) and
+                         bool((out_d[:hi - lo, 0] < 1.0).all()))
+    known_ok = job.sum_over_ranks(known_ok) == world
+    srt = bool((out_d[:, 1:] >= out_d[:, :-1]).all())
+    in_range = bool(((out_i >= 0) & (out_i < args.n_db)).all())
+    uniq = all(len(set(r)) == args.k for r in out_i[:64].cpu().tolist())
+    props_ok = job.sum_over_ranks(float(srt and in_range and uniq)) == world
+
+    # ---- phases (N > 1), measured in separate un-timed steps: all-gather / search / exchange+merge
+    phases = None
+    if world > 1:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        acc = [0.0, 0.0, 0.0]
+        reps = 5
+        ld = torch.empty((args.queries, args.k), dtype=torch.float32, device=dev)
+        li = torch.empty((args.queries, args.k), dtype=torch.int64, device=dev)
+        for _ in range(reps):
+            job.sync_all()
+            ev[0].record()
+            qa = job.comm.allgather_queries(q_dev, args.queries)
+            ev[1].record()
+            index.search(qa, args.k, out=(ld, li))     # private thresholds here (no exchange hook)
+            ev[2].record()
+            job.comm.exchange_merge_topk(ld, li, args.k, out=(out_d, out_i))
+            ev[3].record()
+            torch.cuda.synchronize()
+            for j in range(3):
+                acc[j] += ev[j].elapsed_time(ev[j + 1]) / reps
+        phases = {"allgather_queries": acc[0], "search_private_tau": acc[1], "exchange_merge": acc[2],
+                  "note": "rank 0, separate un-timed steps; the timed step fuses them in b2vs_search_sharded "
+                          "and exchanges thresholds between the passes"}
+
+    # ---- e2e: the user-facing call with HOST buffers (H2D + search + exchange + merge + D2H every step)
+    if world == 1:
+        scfg = b2.SearchConfig(k=args.k, search_params={"collect_gpu_results": False},
+                               parallel_search=False, validate_results=False)
+        api = "SearchResultAggregator.perform_distributed_search (pinned host queries)"
+    else:
+        scfg = b2.SearchConfig(k=args.k, search_params={"result_layout": "sliced",
+                                                        "num_queries_total": args.queries},
+                               parallel_search=False, validate_results=False)
+        api = ("SearchResultAggregator.perform_distributed_search(result_layout='sliced') -> "
+               "b2vs_search_sharded_host: each rank uploads its 1/N of the batch and downloads its 1/N of the answers")
     for _ in range(max(1, args.warmup)):
         sra.perform_distributed_search(q_host, {local_rank: index}, scfg)
-    sync_all()
+    job.sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         r = sra.perform_distributed_search(q_host, {local_rank: index}, scfg)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_s = job.max_over_ranks(time.perf_counter() - t0)
     e2e_qps = args.queries * args.steps / e2e_s
-    h2d = q_host.numel() * q_host.element_size()
-    d2h = args.queries * args.k * (4 + 8)
+    e2e_known = True
+    if hi > lo:
+        e2e_known = bool((torch.from_numpy(r.final_indices[:hi - lo, 0]) == pl_ids[lo:hi]).all())
+    e2e_known = job.sum_over_ranks(float(e2e_known)) == world
+    # bytes over PCIe per step, whole job: every rank moves its own slice only
+    h2d = int(job.sum_over_ranks(q_host.numel() * q_host.element_size()))
+    d2h = int(job.sum_over_ranks((qe - qb) * args.k * (4 + 8)))
 
     # ---- parity spot-check against the oracle on a small slice (checker only, untimed)
-    parity = None
+    parity = {"known_answers_first_hit": known_ok, "sorted_unique_in_range": props_ok,
+              "e2e_known_answers_first_hit": e2e_known,
+              "check": f"{n_pl} queries of every timed batch are rows of the global corpus: first hit must be "
+                       "that global row id on whichever rank returns the query's slice"}
     if rank == 0 and world == 1:
         try:
             from oracle.exact import topk_parity_report
@@ -375,64 +744,49 @@ def main():
             dd, ii = sub.search(q_dev[:64], args.k)
             rep = topk_parity_report(dd.cpu(), ii.cpu(), shard[:nchk].float().cpu(),
                                      q_dev[:64].float().cpu(), args.k)
-            parity = {"ok": rep["ok"], "exact_id_match": rep["exact_id_match"]}
+            parity.update({"oracle_ok": rep["ok"], "exact_id_match": rep["exact_id_match"]})
             sub.destroy()
         except Exception as exc:  # the bench number stands; parity is reported, not assumed
-            parity = {"ok": False, "error": str(exc)[:200]}
-    if world > 1:
-        # sharded run: size-independent properties of the merged answer (all ranks hold it).
-        #  * the best merged hit of every query is the best hit of some shard (all-reduce MIN),
-        #  * rows are sorted, ids unique and inside [0, N), every rank computed the same result.
-        md, mi = step_device()
-        torch.cuda.synchronize()
-        best_local = out_d[:, 0].clone()
-        dist.all_reduce(best_local, op=dist.ReduceOp.MIN)
-        chk = torch.stack([(mi.double().sum()), md.double().sum()])
-        chk_max, chk_min = chk.clone(), chk.clone()
-        dist.all_reduce(chk_max, op=dist.ReduceOp.MAX)
-        dist.all_reduce(chk_min, op=dist.ReduceOp.MIN)
-        srt = bool((md[:, 1:] >= md[:, :-1]).all())
-        in_range = bool(((mi >= 0) & (mi < args.n_db)).all())
-        uniq = all(len(set(r)) == args.k for r in mi[:64].cpu().tolist())
-        parity = {"ok": bool(torch.equal(md[:, 0], best_local)) and srt and in_range and uniq and
-                  bool(torch.equal(chk_max, chk_min)),
-                  "check": "merged best == min over shards, sorted, unique in-range ids, identical on all ranks"}
+            parity.update({"oracle_ok": False, "error": str(exc)[:200]})
+    parity["ok"] = bool(known_ok and props_ok and e2e_known and parity.get("oracle_ok", True))
 
+    line = None
     if rank == 0:
-        peaks = load_peaks()
+        peaks = job.peaks
         kms = sum(kernel_ms) / max(1, len(kernel_ms))
         flops_per_launch = 2.0 * args.queries * n_local * args.dim
         achieved = flops_per_launch / (kms * 1e-3) / 1e12 if kms > 0 else None
+        tr = ncu_traffic(world, args)
         line = {
             "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": "C2: exact L2 k=100, 10Mx768 bf16 row-sharded, 10K-query batches, "
-                                   "NCCL all-gather + GPU merge",
+            "config": {"workload": workload_name(args),
                        "n_db": args.n_db, "dim": args.dim, "queries_per_batch": args.queries,
                        "k": args.k, "rows_per_gpu": n_local, "parallelism": f"shard{world}",
                        "l2_policy": "inputs larger than L2 (db shard >= 1.9 GB vs 126 MB L2), no flush",
+                       "exchange": ("none (one shard)" if world == 1 else
+                                    "b2vs_search_sharded: NCCL all-gather of query slices, MIN all-reduce of "
+                                    "thresholds between passes, all-to-all of per-shard lists + merge of each "
+                                    "rank's slice"),
                        "n_splits": stats.n_splits, "grid": stats.grid},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
                          "unit": "TFLOP/s", "frac": (achieved / peaks["tflops"]) if achieved else None,
-                         "traffic": ncu_traffic(world, args), "kernel": "bf_tc_kernel", "kernel_ms": kms,
+                         "traffic": tr,
+                         "traffic_source": ("committed ncu capture profiles/r1_c2_bf_tc_fullpass_v2.csv "
+                                            "(not measured in this run)" if tr is not None else "none for this configuration"),
+                         "kernel": "bf_tc_kernel (full pass)", "kernel_ms": kms,
                          "algorithmic_flops_per_launch": flops_per_launch,
-                         "peak_source": peaks["source"]},
+                         "peak_source": peaks["source"] + ", sustained"},
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h,
-                    "api": "SearchResultAggregator.perform_distributed_search (pinned host queries)"},
+                    "d2h_bytes_per_step": d2h, "api": api},
             "gpu_launches": launches,
             "clocks": clocks,
             "parity": parity,
         }
-        if phase_ev:
-            # rank 0's device time per phase (mean over the timed steps)
-            n = len(phase_ev)
-            line["phases_ms"] = {
-                "search": sum(e[0].elapsed_time(e[1]) for e in phase_ev) / n,
-                "all_gather": sum(e[1].elapsed_time(e[2]) for e in phase_ev) / n,
-                "merge": sum(e[2].elapsed_time(e[3]) for e in phase_ev) / n}
+        if phases:
+            line["phases_ms"] = phases
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             rows = min(args.cpu_sample_rows, args.n_db)
@@ -446,9 +800,44 @@ def main():
             sk = sklearn_baseline(args, cores)
             if sk is not None:
                 line["cpu_baseline_sklearn"] = sk
+
+    # ---- sub-records: the other BASELINE configs, on freed memory
+    wanted = [] if args.configs.strip().lower() in ("none", "") else [c.strip().upper() for c in args.configs.split(",")]
+    index.destroy()
+    ibc.built_indices.pop(local_rank, None)
+    del shard, part, res
+    torch.cuda.empty_cache()
+    subs = {}
+    for name in wanted:
+        job.sync_all()
+        t0 = time.perf_counter()
+        try:
+            if name == "C1":
+                subs["C1"] = run_c1(job, args)
+            elif name == "C3":
+                subs["C3"] = run_ivf(job, args, "C3")
+            elif name in ("C4", "C4_SHARD"):
+                subs["C4_shard"] = run_ivf(job, args, "C4_shard")
+            elif name == "C5":
+                subs["C5"] = run_c5(job, args)
+            else:
+                continue
+        except Exception as exc:   # a sub-record must not take the headline down with it
+            key = "C4_shard" if name.startswith("C4") else name
+            subs[key] = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+            if world > 1:
+                raise       # ranks would desynchronise: fail loudly instead
+        key = "C4_shard" if name.startswith("C4") else name
+        if key in subs:
+            subs[key]["wall_s"] = time.perf_counter() - t0
+        torch.cuda.empty_cache()
+    if rank == 0:
+        line["configs"] = subs
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        if job.comm is not None:
+            job.comm.destroy()
         dist.destroy_process_group()
 
 

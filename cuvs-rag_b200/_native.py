@@ -63,7 +63,7 @@ class SearchStats(ctypes.Structure):
     _fields_ = [("launches", ctypes.c_int32), ("n_splits", ctypes.c_int32),
                 ("grid", ctypes.c_int32), ("mean_candidates", ctypes.c_int32),
                 ("algo_flops", ctypes.c_double), ("algo_bytes", ctypes.c_double),
-                ("kernel_ms", ctypes.c_double)]
+                ("kernel_ms", ctypes.c_double), ("distinct_bytes", ctypes.c_double)]
 
 
 # Every symbol include/b2vs.h declares; tests assert the built library exports all of them.
@@ -76,7 +76,7 @@ EXPORTS = [
     "b2vs_comm_unique_id", "b2vs_comm_init_rank", "b2vs_comm_init_all", "b2vs_comm_info",
     "b2vs_comm_destroy", "b2vs_partition_even", "b2vs_allgather_queries", "b2vs_allgather_topk",
     "b2vs_allgather_merge_topk", "b2vs_exchange_merge_topk", "b2vs_allreduce_min_f32",
-    "b2vs_search_sharded", "b2vs_search_sharded_host",
+    "b2vs_search_sharded", "b2vs_search_sharded_host", "b2vs_comm_register_index",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -190,6 +190,7 @@ def lib() -> ctypes.CDLL:
         L.b2vs_search_sharded.argtypes = [vp, vp, vp, i32, i32, i32, i32, ctypes.POINTER(SearchParams),
                                           vp, vp, vp]
         L.b2vs_search_sharded_host.argtypes = L.b2vs_search_sharded.argtypes
+        L.b2vs_comm_register_index.argtypes = [vp, vp, vp]
         for name in EXPORTS:
             if name != "b2vs_last_error":
                 getattr(L, name).restype = i32
@@ -634,6 +635,17 @@ class Comm:
                                             _stream_ptr(self.device, stream)), "b2vs_allreduce_min_f32")
         return values
 
+    def register_index(self, index: "NativeIndex", stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Collective (every rank, same order): agree on the smallest shard so sharded flat searches
+        exchange thresholds between their passes.  Done once per index object; ranks create their
+        index objects in lockstep (SPMD), so the first sharded search of a new index registers it
+        on every rank at the same point."""
+        if getattr(index, "_sharded_comm", None) is self:
+            return
+        _check(lib().b2vs_comm_register_index(self._h, index._h, _stream_ptr(self.device, stream)),
+               "b2vs_comm_register_index")
+        index._sharded_comm = self
+
     def search_sharded(self, index: "NativeIndex", q_local: torch.Tensor, nq_total: int, k: int,
                        n_probes: int = 0, refine_ratio: int = 0, time_kernel: bool = False,
                        stream: Optional[torch.cuda.Stream] = None,
@@ -644,6 +656,7 @@ class Comm:
         b, e = self.query_slice(nq_total)
         if q_local.dim() != 2 or q_local.shape[0] != e - b or not q_local.is_contiguous():
             raise ValueError(f"rank {self.rank} must pass its contiguous [{e - b}, dim] query slice")
+        self.register_index(index, stream)
         index._check_queries(q_local)
         index._check_refine(refine_ratio)
         host = not q_local.is_cuda

@@ -103,9 +103,6 @@ struct b2vs_comm {
   int n_ranks = 1, rank = 0, dev = 0;
   // grow-only workspaces of the exchange calls
   b2vs::DevBuf recv_d, recv_i, q_all, loc_d, loc_i, io;
-  // rows of the smallest shard, agreed on the first sharded search of an index (see search_sharded)
-  const b2vs_index* agreed_index = nullptr;
-  int64_t agreed_min_rows = 0;
 };
 
 using namespace b2vs;
@@ -319,6 +316,27 @@ int tau_exchange_cb(void* ctx, float* tau, int64_t n, cudaStream_t st) {
 }  // namespace
 }  // namespace b2vs
 
+extern "C" int b2vs_comm_register_index(b2vs_comm* comm, b2vs_index* index, void* stream) {
+  B2VS_CHECK(comm && index, B2VS_EINVAL, "NULL argument");
+  B2VS_CHECK(index->dev == comm->dev, B2VS_EINVAL, "index on device %d, communicator on device %d",
+             index->dev, comm->dev);
+  DeviceGuard guard(comm->dev);
+  B2VS_CHECK(guard.ok, B2VS_ECUDA, "cannot select device %d", comm->dev);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  index->sharded_min_rows = 0;
+  if (comm->n_ranks == 1) { index->sharded_min_rows = index->n; return B2VS_OK; }
+  B2VS_TRY(comm->io.reserve(sizeof(float)));
+  // shard sizes are < 2^32 rows: exact in the float MIN after >> 8 (256-row tile units)
+  const float tiles = static_cast<float>(index->n >> 8);
+  B2VS_CUDA(cudaMemcpyAsync(comm->io.ptr, &tiles, sizeof(float), cudaMemcpyHostToDevice, st));
+  B2VS_TRY(b2vs_allreduce_min_f32(comm, comm->io.as<float>(), 1, stream));
+  float min_tiles = 0.f;
+  B2VS_CUDA(cudaMemcpyAsync(&min_tiles, comm->io.ptr, sizeof(float), cudaMemcpyDeviceToHost, st));
+  B2VS_CUDA(cudaStreamSynchronize(st));
+  index->sharded_min_rows = static_cast<int64_t>(min_tiles) << 8;
+  return B2VS_OK;
+}
+
 extern "C" int b2vs_search_sharded(b2vs_comm* comm, b2vs_index* index, const void* q_local, int q_dtype,
                                    int nq_total, int dim, int k, const b2vs_search_params* params,
                                    float* out_d, int64_t* out_i, void* stream) {
@@ -336,26 +354,15 @@ extern "C" int b2vs_search_sharded(b2vs_comm* comm, b2vs_index* index, const voi
   B2VS_TRY(comm->loc_d.reserve(cnt * sizeof(float)));
   B2VS_TRY(comm->loc_i.reserve(cnt * sizeof(int64_t)));
   B2VS_TRY(b2vs_allgather_queries(comm, q_local, q_dtype, nq_total, dim, comm->q_all.ptr, stream));
-  // Threshold exchange needs every rank to run the same pass schedule: agree once per index on
-  // the smallest shard (one 8-byte all-reduce + sync, first call only).
-  if (comm->agreed_index != index && comm->n_ranks > 1) {
-    B2VS_TRY(comm->io.reserve(sizeof(float)));
-    // shard sizes are < 2^32 rows: exact in the float MIN below after >> 8 (tile units)
-    const float tiles = static_cast<float>(index->n >> 8);
-    B2VS_CUDA(cudaMemcpyAsync(comm->io.ptr, &tiles, sizeof(float), cudaMemcpyHostToDevice, st));
-    B2VS_TRY(b2vs_allreduce_min_f32(comm, comm->io.as<float>(), 1, stream));
-    float min_tiles = 0.f;
-    B2VS_CUDA(cudaMemcpyAsync(&min_tiles, comm->io.ptr, sizeof(float), cudaMemcpyDeviceToHost, st));
-    B2VS_CUDA(cudaStreamSynchronize(st));
-    comm->agreed_min_rows = static_cast<int64_t>(min_tiles) << 8;
-    comm->agreed_index = index;
-  }
   b2vs_search_params sp{};
   if (params) sp = *params;
   int rc;
-  if (index->kind == B2VS_KIND_FLAT && comm->n_ranks > 1 && !index->cosine &&
-      flat_exchanges_tau(comm->agreed_min_rows, k)) {
-    TauExchange tx{tau_exchange_cb, comm};
+  // Threshold exchange needs every rank to run the same pass schedule: it is derived from the
+  // smallest shard's size, agreed once by b2vs_comm_register_index (unregistered indexes - and
+  // jobs with an empty shard - keep private thresholds: no collective inside the search).
+  if (index->kind == B2VS_KIND_FLAT && comm->n_ranks > 1 && index->n > 0 &&
+      flat_exchanges_tau(index->sharded_min_rows, k)) {
+    TauExchange tx{tau_exchange_cb, comm, index->sharded_min_rows};
     rc = index->flat.search(comm->q_all.ptr, q_dtype, nq_total, k, sp.n_splits, index->id_offset,
                             comm->loc_d.as<float>(), comm->loc_i.as<int64_t>(), nullptr, st, sp.flags, &tx);
   } else {

@@ -128,6 +128,8 @@ struct BfTcParams;  // kernel parameters (bf_tc.cuh)
 struct TauExchange {
   int (*fn)(void* ctx, float* tau, int64_t n, cudaStream_t st);
   void* ctx;
+  int64_t schedule_rows;   // rows of the SMALLEST shard: the pass schedule (= number of exchanges)
+                           // is derived from it, so every rank makes the same collective calls
 };
 // True when a flat search over at least `min_rows` rows with this k runs a sampled pass before
 // the full one, i.e. has thresholds to exchange (must evaluate identically on every rank).
@@ -257,4 +259,7 @@ struct b2vs_index {
   // copy of the rows; queries are normalised into cos_q and distances leave as 1 - similarity
   bool cosine = false;
   b2vs::DevBuf cos_rows, cos_q;
+  // rows of the smallest shard of the sharded job this index belongs to, agreed by
+  // b2vs_comm_register_index (0 = not registered: sharded searches keep private thresholds)
+  int64_t sharded_min_rows = 0;
 };

@@ -393,7 +393,10 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   const int units = std::max(1, sms / group);  // CTAs (G=1) or CTA pairs (G=2) that run at once
   const int64_t tiles = ceil_div(n, kBN);
   int strides[3];
-  int n_pass = pass_strides(tiles, k, strides);
+  // sharded search with threshold exchange: the schedule follows the smallest shard of the job,
+  // so that every rank runs the same number of passes (= collective calls)
+  const int64_t sched_tiles = tau_exchange ? ceil_div(std::max<int64_t>(tau_exchange->schedule_rows, 1), kBN) : tiles;
+  int n_pass = pass_strides(sched_tiles, k, strides);
   B2VS_TRY(ws_tau.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
 
   BfTcParams p{};

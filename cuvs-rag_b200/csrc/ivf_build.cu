@@ -196,10 +196,11 @@ void ivf_last_stats(const b2vs_index* index, b2vs_search_stats* stats) {
   *stats = b2vs_search_stats{};
   if (!d) return;
   if (d->counter_pending && d->ws_counter.ptr) {
-    unsigned long long cnt[2] = {0, 0};
+    unsigned long long cnt[3] = {0, 0, 0};
     DeviceGuard guard(index->dev);
     if (cudaMemcpy(cnt, d->ws_counter.ptr, sizeof(cnt), cudaMemcpyDeviceToHost) == cudaSuccess) {
       d->stats.algo_bytes = static_cast<double>(cnt[0]) * d->row_bytes;
+      d->stats.distinct_bytes = static_cast<double>(cnt[2]) * d->row_bytes;
       d->stats.mean_candidates = static_cast<int32_t>(cnt[1] / static_cast<unsigned long long>(std::max(d->last_nq, 1)));
     }
     d->counter_pending = false;

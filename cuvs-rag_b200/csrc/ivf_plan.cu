@@ -31,8 +31,10 @@ __global__ void build_group_work_kernel(const uint32_t* __restrict__ group_off,
       const int re = c + 1 == slots ? end : min(end, rb + chunk_rows);
       work[b * slots + c] = make_int4(b, rb, re, 0);
     }
-  if (scanned_rows && group_cnt[r] > 0)   // algorithmic work: every probing query sees every row
+  if (scanned_rows && group_cnt[r] > 0) {  // algorithmic work: every probing query sees every row
     atomicAdd(scanned_rows, static_cast<unsigned long long>(group_cnt[r]) * static_cast<unsigned>(end - begin));
+    atomicAdd(scanned_rows + 2, static_cast<unsigned long long>(end - begin));   // distinct list rows
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -154,7 +156,7 @@ ivf_plan_small_kernel(const long long* __restrict__ probe_ids, int items,
   const u64 before = part[warp] + inc - sum;
   uint32_t run = static_cast<uint32_t>(before >> 32);
   uint32_t wrun = static_cast<uint32_t>(before & 0xffffffffu);
-  unsigned long long rows_scanned = 0;
+  unsigned long long rows_scanned = 0, rows_distinct = 0;
   for (int i = lo; i < hi; ++i) {
     off[i] = run;
     group_off[i] = run;
@@ -168,9 +170,13 @@ ivf_plan_small_kernel(const long long* __restrict__ probe_ids, int items,
       for (int rb = begin; rb < end; rb += chunk_rows)
         work[wrun++] = make_int4(b0 + b, rb, min(end, rb + chunk_rows), 0);
     rows_scanned += static_cast<unsigned long long>(c) * static_cast<unsigned>(end - begin);
+    rows_distinct += static_cast<unsigned>(end - begin);
     run += static_cast<uint32_t>(blocks * kGroupRows);
   }
-  if (scanned_rows && rows_scanned) atomicAdd(scanned_rows, rows_scanned);
+  if (scanned_rows && rows_scanned) {
+    atomicAdd(scanned_rows, rows_scanned);
+    atomicAdd(scanned_rows + 2, rows_distinct);
+  }
   __syncthreads();
   for (int i = t; i < n_lists; i += kPlanThreads) cnt[i] = 0;   // now the scatter cursors
   __syncthreads();

@@ -8,6 +8,10 @@
 
 namespace b2vs {
 
+// ws_counter: [0] rows scanned counted per (query, probe), [1] appended candidates,
+// [2] DISTINCT probed list rows (grouped scans), [3] large-k overflow flag (int)
+constexpr size_t kCounterBytes = 4 * sizeof(unsigned long long);
+
 // Candidate-buffer capacity (a power of two) and seed-sample length of the grouped scan, by k.
 // B2VS_IVF_GROUPED_CAP shrinks the buffers so tests can drive the overflow-rescue path.
 static int grouped_cap(int k) {
@@ -34,7 +38,7 @@ static int ivf_pq_search_bigk(b2vs_index* index, const void* q, int q_dtype, int
 // caller sizes, zeroes and later selects from them).  probe_ids is [nq, n_probes] dense.
 static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long* probe_ids,
                                  int n_probes, int nq, int cap, unsigned long long* counter,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, bool timed = false) {
   const int items = nq * n_probes;
   const int q_split = index->dtype == B2VS_F32 ? 1 : 0;
   const int q_pitch = q_split ? 2 * static_cast<int>(round_up(d->dp, 64)) : d->dp;
@@ -58,7 +62,10 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
   ga.work = d->ws_g_work.ptr; ga.n_work = n_work; ga.max_work = max_work;
   ga.row_query = d->ws_g_rowq.as<int>(); ga.tau = d->ws_g_tau.as<float>();
   ga.cand = d->ws_g_cand.as<u64>(); ga.count = d->ws_g_cnt.as<int>(); ga.cap = cap;
-  return launch_grouped_scan(index->dev, ga, st);
+  if (timed) B2VS_CUDA(cudaEventRecord(d->ev0, st));
+  B2VS_TRY(launch_grouped_scan(index->dev, ga, st));
+  if (timed) B2VS_CUDA(cudaEventRecord(d->ev1, st));
+  return B2VS_OK;
 }
 
 // IVF-Flat with 128 < k <= 2048 (the reference's top-2000 retrieval mode on an IVF index,
@@ -85,7 +92,7 @@ static int ivf_flat_search_bigk(b2vs_index* index, const void* q, int q_dtype, i
   B2VS_TRY(d->ws_ref_i.reserve(static_cast<size_t>(nq) * m * sizeof(int64_t)));   // first m probes
   B2VS_TRY(d->ws_qf.reserve(static_cast<size_t>(nq) * d->dp * sizeof(float)));
   B2VS_TRY(d->ws_qnorm.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
-  B2VS_TRY(d->ws_counter.reserve(2 * sizeof(unsigned long long) + sizeof(int)));
+  B2VS_TRY(d->ws_counter.reserve(kCounterBytes));
   B2VS_TRY(d->ws_g_tau.reserve(static_cast<size_t>(nq) * sizeof(float)));
   B2VS_TRY(d->ws_g_cand.reserve(static_cast<size_t>(nq) * kCapBig * sizeof(u64)));
   B2VS_TRY(d->ws_g_cnt.reserve(static_cast<size_t>(nq) * sizeof(int)));
@@ -97,8 +104,8 @@ static int ivf_flat_search_bigk(b2vs_index* index, const void* q, int q_dtype, i
   B2VS_TRY(launch_queries_to_f32(q, q_dtype, nq, index->dim, d->dp, d->fmt, round16,
                                  d->ws_qf.as<float>(), d->ws_qnorm.as<float>(), st));
   unsigned long long* counter = d->ws_counter.as<unsigned long long>();
-  int* overflow = reinterpret_cast<int*>(counter + 2);
-  B2VS_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned long long) + sizeof(int), st));
+  int* overflow = reinterpret_cast<int*>(counter + 3);
+  B2VS_CUDA(cudaMemsetAsync(counter, 0, kCounterBytes, st));
   const long long* probe_ids = reinterpret_cast<const long long*>(d->ws_probe_i.ptr);
   // ---- pass 1: nearest m lists, no threshold
   B2VS_CUDA(cudaMemcpy2DAsync(d->ws_ref_i.ptr, static_cast<size_t>(m) * sizeof(int64_t), probe_ids,
@@ -202,7 +209,8 @@ int ivf_search_direct(b2vs_index* index, const void* q, int q_dtype, int nq, int
 // PQ counterpart of run_grouped_flat_scan: plan, gather the residual queries, decode + scan on
 // the tensor cores.  Thresholds / candidate buffers (ws_g_tau, ws_g_cand, ws_g_cnt) are the caller's.
 static int run_grouped_pq_scan(b2vs_index* index, IvfData* d, const long long* probe_ids, int n_probes,
-                               int nq, int cap, unsigned long long* counter, cudaStream_t st) {
+                               int nq, int cap, unsigned long long* counter, cudaStream_t st,
+                               bool timed = false) {
   const int items = nq * n_probes;
   const int l2 = index->metric == B2VS_METRIC_L2 ? 1 : 0;
   int chunk_rows = 0, slots = 1;
@@ -228,7 +236,10 @@ static int run_grouped_pq_scan(b2vs_index* index, IvfData* d, const long long* p
   ga.row_query = d->ws_g_rowq.as<int>(); ga.row_bias = d->ws_g_bias.as<float>();
   ga.tau = d->ws_g_tau.as<float>();
   ga.cand = d->ws_g_cand.as<u64>(); ga.count = d->ws_g_cnt.as<int>(); ga.cap = cap;
-  return launch_pq_grouped_scan(index->dev, ga, st);
+  if (timed) B2VS_CUDA(cudaEventRecord(d->ev0, st));
+  B2VS_TRY(launch_pq_grouped_scan(index->dev, ga, st));
+  if (timed) B2VS_CUDA(cudaEventRecord(d->ev1, st));
+  return B2VS_OK;
 }
 
 // IVF-PQ with k (or k * refine_ratio) above 128, up to 2048: the two-pass scheme of
@@ -255,7 +266,7 @@ static int ivf_pq_search_bigk(b2vs_index* index, const void* q, int q_dtype, int
   B2VS_TRY(d->ws_keys.reserve(static_cast<size_t>(nq) * m * sizeof(int64_t)));        // first m probes
   B2VS_TRY(d->ws_qf.reserve(static_cast<size_t>(nq) * d->dp * sizeof(float)));
   B2VS_TRY(d->ws_qnorm.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
-  B2VS_TRY(d->ws_counter.reserve(2 * sizeof(unsigned long long) + sizeof(int)));
+  B2VS_TRY(d->ws_counter.reserve(kCounterBytes));
   B2VS_TRY(d->ws_g_tau.reserve(static_cast<size_t>(nq) * sizeof(float)));
   B2VS_TRY(d->ws_g_cand.reserve(static_cast<size_t>(nq) * kCapBig * sizeof(u64)));
   B2VS_TRY(d->ws_g_cnt.reserve(static_cast<size_t>(nq) * sizeof(int)));
@@ -266,8 +277,8 @@ static int ivf_pq_search_bigk(b2vs_index* index, const void* q, int q_dtype, int
   B2VS_TRY(launch_queries_to_f32(q, q_dtype, nq, index->dim, d->dp, d->fmt, 0,
                                  d->ws_qf.as<float>(), d->ws_qnorm.as<float>(), st));
   unsigned long long* counter = d->ws_counter.as<unsigned long long>();
-  int* overflow = reinterpret_cast<int*>(counter + 2);
-  B2VS_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(unsigned long long) + sizeof(int), st));
+  int* overflow = reinterpret_cast<int*>(counter + 3);
+  B2VS_CUDA(cudaMemsetAsync(counter, 0, kCounterBytes, st));
   const long long* probe_ids = reinterpret_cast<const long long*>(d->ws_probe_i.ptr);
   B2VS_CUDA(cudaMemcpy2DAsync(d->ws_keys.ptr, static_cast<size_t>(m) * sizeof(int64_t), probe_ids,
                               static_cast<size_t>(n_probes) * sizeof(int64_t),
@@ -389,7 +400,7 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
   B2VS_TRY(d->ws_keys.reserve(static_cast<size_t>(will_group ? 1 : n_probes) * q_pad * k * sizeof(u64)));
   B2VS_TRY(d->ws_qf.reserve(static_cast<size_t>(nq) * d->dp * sizeof(float)));
   B2VS_TRY(d->ws_qnorm.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
-  B2VS_TRY(d->ws_counter.reserve(2 * sizeof(unsigned long long)));  // scanned rows, candidates
+  B2VS_TRY(d->ws_counter.reserve(kCounterBytes));
   const int round16 = (index->kind == B2VS_KIND_IVF_FLAT && index->dtype != B2VS_F32) ? 1 : 0;
   B2VS_TRY(launch_queries_to_f32(q, q_dtype, nq, index->dim, d->dp, d->fmt, round16,
                                  d->ws_qf.as<float>(), d->ws_qnorm.as<float>(), st));
@@ -403,7 +414,7 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
                                 d->ws_probe_i.as<int64_t>(), nullptr, st));
     launches = index->flat.stats.launches;
   }
-  B2VS_CUDA(cudaMemsetAsync(d->ws_counter.ptr, 0, 2 * sizeof(unsigned long long), st));
+  B2VS_CUDA(cudaMemsetAsync(d->ws_counter.ptr, 0, kCounterBytes, st));
   launches += 2;
   const int items = nq * n_probes;
   const long long* probe_ids = reinterpret_cast<const long long*>(d->ws_probe_i.ptr);
@@ -415,8 +426,8 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
       B2VS_CUDA(cudaEventCreate(&d->ev0));
       B2VS_CUDA(cudaEventCreate(&d->ev1));
     }
-    B2VS_CUDA(cudaEventRecord(d->ev0, st));
   }
+  bool scan_timed_inside = false;   // grouped paths time the tensor-core scan kernel alone
   bool single_list = false;  // the scan left ONE sorted list per query (not one per probe)
   if (index->kind == B2VS_KIND_IVF_FLAT) {
     const float alpha = index->metric == B2VS_METRIC_L2 ? -2.f : -1.f;
@@ -440,7 +451,8 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
       B2VS_TRY(launch_flat_seed_tau(index, d, probe_ids, n_probes, nq, k, grouped_seed_rows(k),
                                     q_split ? 1e-5f : 0.f,
                                     order_seeds ? d->ws_item_perm.as<uint32_t>() : nullptr, st));
-      B2VS_TRY(run_grouped_flat_scan(index, d, probe_ids, n_probes, nq, cap, counter, st));
+      B2VS_TRY(run_grouped_flat_scan(index, d, probe_ids, n_probes, nq, cap, counter, st, timed));
+      scan_timed_inside = true;
       B2VS_TRY(launch_group_select(d, nq, cap, k, counter + 1, st));
       B2VS_TRY(launch_flat_rescue(index, d, probe_ids, n_probes, nq, k, cap, st));
       launches += 16;
@@ -449,6 +461,7 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
       // Per-item scan.  Ordering the items by list pays once several queries share a list: the
       // batch then reads each probed list from HBM about once instead of once per probing query.
       const uint32_t* item_perm = nullptr;
+      if (timed) B2VS_CUDA(cudaEventRecord(d->ev0, st));
       if (!env().no_item_sort && items >= 4 * d->n_lists) {
         B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, 1, st));
         item_perm = d->ws_item_perm.as<uint32_t>();
@@ -473,15 +486,17 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
     B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
     B2VS_TRY(launch_pq_lut_scan(0, index, d, probe_ids, n_probes, nq, k, cap, grouped_seed_rows(k),
                                 order_seeds ? d->ws_item_perm.as<uint32_t>() : nullptr, st));
-    B2VS_TRY(run_grouped_pq_scan(index, d, probe_ids, n_probes, nq, cap, counter, st));
+    B2VS_TRY(run_grouped_pq_scan(index, d, probe_ids, n_probes, nq, cap, counter, st, timed));
+    scan_timed_inside = true;
     B2VS_TRY(launch_group_select(d, nq, cap, k, counter + 1, st));
     B2VS_TRY(launch_pq_lut_scan(1, index, d, probe_ids, n_probes, nq, k, cap, 0u, nullptr, st));
     launches += 16;
     single_list = true;
   } else {
+    if (timed) B2VS_CUDA(cudaEventRecord(d->ev0, st));
     B2VS_TRY(launch_pq_table_scan(index, d, probe_ids, n_probes, nq, q_pad, k, counter, &single_list, st));
   }
-  if (timed) B2VS_CUDA(cudaEventRecord(d->ev1, st));
+  if (timed && !scan_timed_inside) B2VS_CUDA(cudaEventRecord(d->ev1, st));
   ++launches;
   if (!refine) {
     B2VS_TRY(launch_merge_splits(d->ws_keys.as<u64>(), single_list ? 1 : n_probes, q_pad, nq, k,

@@ -103,8 +103,12 @@ typedef struct b2vs_search_stats {
   int32_t mean_candidates; /* IVF-Flat grouped scan: appended candidates per query (mean), else 0 */
   double algo_flops;       /* 2*Q*N*D for the distance contraction (flat / coarse) */
   double algo_bytes;       /* IVF: sum of probed list bytes actually scanned */
-  double kernel_ms;        /* device time of the dominant kernel (fused distance / list scan) when
-                              B2VS_FLAG_TIME_KERNEL was set, else 0 */
+  double kernel_ms;        /* device time of the dominant kernel (the fused distance kernel's full
+                              pass / the list-scan kernel alone) when B2VS_FLAG_TIME_KERNEL was set,
+                              else 0 */
+  double distinct_bytes;   /* IVF grouped scans: bytes of the DISTINCT probed lists - what the batch
+                              has to read from HBM once (algo_bytes counts a list once per probing
+                              query); 0 on the per-(query, probe) paths */
 } b2vs_search_stats;
 
 const char* b2vs_last_error(void);
@@ -248,6 +252,12 @@ int b2vs_exchange_merge_topk(b2vs_comm* comm, const float* d_local, const int64_
                              void* stream);
 /* In-place element-wise MIN all-reduce of a float vector (per-query threshold exchange). */
 int b2vs_allreduce_min_f32(b2vs_comm* comm, float* values, int64_t n, void* stream);
+
+/* Collective, once per (communicator, index) after the build: the ranks agree on the size of the
+ * smallest shard, from which sharded flat searches derive ONE pass schedule for every rank (the
+ * threshold exchange sits between the passes).  Synchronises `stream`.  Without it
+ * b2vs_search_sharded still works, with private per-shard thresholds. */
+int b2vs_comm_register_index(b2vs_comm* comm, b2vs_index* index, void* stream);
 
 /* The whole sharded step behind one call: all-gather of the query slices, local search of this
  * rank's shard - flat indexes exchange their per-query thresholds after the sampled pass, so

@@ -23,3 +23,31 @@ def b2():
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _reload_b2vs_env_switches(request, monkeypatch):
+    """The library reads its B2VS_* switches once; tests that flip them through ``setenv`` (below)
+    get a re-read, and the defaults are restored when the test ends."""
+    yield
+    if any(k.startswith("B2VS_") for k in os.environ) or getattr(request.node, "_b2vs_env_touched", False):
+        monkeypatch.undo()
+        try:
+            import cuvs_rag_b200
+            cuvs_rag_b200._native.reload_env()
+        except Exception:
+            pass
+
+
+@pytest.fixture
+def setenv(request, monkeypatch):
+    """setenv(name, value | None): set / delete a B2VS_* switch and make the library re-read them."""
+    def _set(name, value):
+        import cuvs_rag_b200
+        request.node._b2vs_env_touched = True
+        if value is None:
+            monkeypatch.delenv(name, raising=False)
+        else:
+            monkeypatch.setenv(name, value)
+        cuvs_rag_b200._native.reload_env()
+    return _set

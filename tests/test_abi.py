@@ -38,7 +38,7 @@ def test_struct_layouts_match_header(b2):
     assert ctypes.sizeof(n.IvfParams) == 32
     assert ctypes.sizeof(n.SearchParams) == 16
     assert ctypes.sizeof(n.IndexInfo) == 56
-    assert ctypes.sizeof(n.SearchStats) == 40
+    assert ctypes.sizeof(n.SearchStats) == 48
 
 
 def test_null_arguments_are_rejected_without_touching_a_gpu(b2):

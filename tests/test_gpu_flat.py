@@ -64,7 +64,7 @@ def test_both_kernel_variants_agree(b2, group_flag):
     d = torch.empty((700, 50), dtype=torch.float32, device="cuda")
     i = torch.empty((700, 50), dtype=torch.int64, device="cuda")
     sp = n.SearchParams(0, 0, 0, flag)
-    rc = n.lib().b2vs_search(ix._h, qs.cuda().data_ptr(), n.BF16, 700, 50, ctypes.byref(sp),
+    rc = n.lib().b2vs_search(ix._h, qs.cuda().data_ptr(), n.BF16, 700, 256, 50, ctypes.byref(sp),
                              d.data_ptr(), i.data_ptr(), torch.cuda.current_stream().cuda_stream)
     assert rc == 0, n.lib().b2vs_last_error()
     torch.cuda.synchronize()

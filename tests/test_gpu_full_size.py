@@ -102,3 +102,54 @@ def test_config_c4_shard_full_size_recall(b2):
     # refined distances are exact for the ids they come with
     same = ii == ti
     assert torch.allclose(dd[same], td[same], rtol=2e-3, atol=2e-2)
+
+
+def test_config_c5_full_size_batch_sweep(b2):
+    """BASELINE configs[4] at full size: exact L2 k=10 on 50M x 1024 bf16 (102 GB on ONE GPU), batch
+    sweep Q = 1 / 64 / 1024.  Size-independent properties: planted rows come back first with their
+    id at distance ~0, rows sorted, ids unique and in range; a small batch is a prefix of a larger
+    one (each query's answer does not depend on the batch it travels in); and the first 2 M rows
+    searched alone agree with the full search restricted to them."""
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 115 * (1 << 30):
+        pytest.skip(f"needs ~115 GiB free device memory, {free >> 30} GiB available")
+    n, d, k = 50_000_000, 1024, 10
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    x = torch.empty((n, d), dtype=torch.bfloat16, device="cuda")
+    chunk = 1 << 19
+    for s0 in range(0, n, chunk):
+        e0 = min(s0 + chunk, n)
+        x[s0:e0] = torch.randn((e0 - s0, d), generator=gen, device="cuda").to(torch.bfloat16)
+    ix = b2.NativeIndex.flat(x, id_offset=1_000_000_000)     # ids beyond 2^31: int64 end to end
+    planted = torch.tensor([0, 1, 255, 256, 24_999_999, 25_000_000, 49_999_744, 49_999_999])
+    qgen = torch.Generator(device="cuda").manual_seed(78)
+    q = torch.randn((1024, d), generator=qgen, device="cuda").to(torch.bfloat16)
+    q[:8] = x[planted.cuda()]
+    res = {}
+    for nq in (1, 64, 1024):
+        dd, ii = ix.search(q[:nq].contiguous(), k)
+        torch.cuda.synchronize()
+        res[nq] = (dd.cpu(), ii.cpu())
+        m = min(nq, 8)
+        assert (res[nq][1][:m, 0] == planted[:m] + 1_000_000_000).all()
+        assert (res[nq][0][:m, 0] < 1.0).all()
+        assert (res[nq][0][:, 1:] >= res[nq][0][:, :-1]).all()
+        ids = res[nq][1]
+        assert ((ids >= 1_000_000_000) & (ids < 1_000_000_000 + n)).all()
+        assert all(len(set(r)) == k for r in ids[:64].tolist())
+    assert torch.equal(res[1][1], res[64][1][:1]) and torch.equal(res[64][1], res[1024][1][:64])
+    assert torch.allclose(res[64][0], res[1024][0][:64], rtol=1e-5, atol=1e-3)
+    # a 2M-row prefix searched alone: its answers are the full answers that fall inside it
+    sub = b2.NativeIndex.flat(x[:2_000_000], id_offset=1_000_000_000)
+    ds, is_ = sub.search(q[:64].contiguous(), k)
+    full_in = res[64][1] < 1_000_000_000 + 2_000_000
+    for r in range(64):
+        want = set(res[64][1][r][full_in[r]].tolist())
+        assert want <= set(is_[r].cpu().tolist())
+    sub.destroy()
+    ix.destroy()
+    del x
+    torch.cuda.empty_cache()

@@ -121,10 +121,10 @@ def test_ivf_pq_refine_lifts_recall_like_the_oracle(b2):
 
 @pytest.mark.parametrize("d,m,label", [(128, 64, "specialised query-major scan (M=64, dsub=2)"),
                                        (768, 96, "per-(query, probe) scan: codebooks exceed smem")])
-def test_ivf_pq_kernel_variants_match_oracle(b2, monkeypatch, d, m, label):
+def test_ivf_pq_kernel_variants_match_oracle(b2, setenv, d, m, label):
     from oracle.exact import exact_knn
     from oracle.ivf import IvfPqOracle, recall
-    monkeypatch.setenv("B2VS_IVF_GROUPED", "0")      # the look-up-table kernels, not the grouped scan
+    setenv("B2VS_IVF_GROUPED", "0")      # the look-up-table kernels, not the grouped scan
     n, nlist, nprobe, k = 20000, 32, 8, 10
     x = clustered(n, d, 60, 12).to(torch.float16)
     q = queries_from(x.float(), 100, 13).to(torch.float16)
@@ -177,7 +177,7 @@ def test_flat_index_save_is_refused(b2, tmp_path):
                                                (torch.bfloat16, "sqeuclidean", 200, 100),
                                                (torch.float32, "sqeuclidean", 200, 100),
                                                (torch.float32, "inner_product", 96, 10)])
-def test_ivf_flat_grouped_scan_equals_per_item_scan(b2, monkeypatch, dtype, metric, d, k):
+def test_ivf_flat_grouped_scan_equals_per_item_scan(b2, setenv, dtype, metric, d, k):
     """Large batches take the grouped tensor-core list scan; it must return what the per-(query,
     probe) scan returns on the same index (ties aside), including when every candidate buffer
     overflows and the rescue kernel answers instead."""
@@ -186,13 +186,13 @@ def test_ivf_flat_grouped_scan_equals_per_item_scan(b2, monkeypatch, dtype, metr
     x = clustered(n, d, 80, 21).to(dtype)
     q = queries_from(x.float(), nq, 22).to(dtype)
     ix = b2.NativeIndex.ivf_flat(x.cuda(), nlist, metric=metric, id_offset=5, kmeans_iters=8)
-    monkeypatch.setenv("B2VS_IVF_GROUPED", "0")
+    setenv("B2VS_IVF_GROUPED", "0")
     d0, i0 = ix.search(q.cuda(), k, n_probes=nprobe)
     torch.cuda.synchronize()
-    monkeypatch.setenv("B2VS_IVF_GROUPED", "1")
+    setenv("B2VS_IVF_GROUPED", "1")
     d1, i1 = ix.search(q.cuda(), k, n_probes=nprobe)
     torch.cuda.synchronize()
-    monkeypatch.setenv("B2VS_IVF_GROUPED_CAP", "32")     # forces overflow -> rescue path
+    setenv("B2VS_IVF_GROUPED_CAP", "32")     # forces overflow -> rescue path
     d2, i2 = ix.search(q.cuda(), k, n_probes=nprobe)
     torch.cuda.synchronize()
     for dd, ii in ((d1, i1), (d2, i2)):
@@ -205,13 +205,13 @@ def test_ivf_flat_grouped_scan_equals_per_item_scan(b2, monkeypatch, dtype, metr
         assert sum(inter) >= 0.999 * nq * k
 
 
-def test_ivf_flat_grouped_scan_ragged_batch(b2, monkeypatch):
+def test_ivf_flat_grouped_scan_ragged_batch(b2, setenv):
     """Batch sizes that are not multiples of the 128-row query block and lists nobody probes."""
     from oracle.exact import exact_knn
     from oracle.ivf import recall
     x = clustered(20000, 64, 40, 31).to(torch.bfloat16)
     ix = b2.NativeIndex.ivf_flat(x.cuda(), 32, metric="sqeuclidean", kmeans_iters=8)
-    monkeypatch.setenv("B2VS_IVF_GROUPED", "1")
+    setenv("B2VS_IVF_GROUPED", "1")
     for nq in (1, 65, 129):
         q = queries_from(x.float(), nq, 40 + nq).to(torch.bfloat16)
         _, ti = exact_knn(x.float(), q.float(), 5, "sqeuclidean")
@@ -225,7 +225,7 @@ def test_ivf_flat_grouped_scan_ragged_batch(b2, monkeypatch):
                                          ("sqeuclidean", 128, 16),     # dsub 8, codebooks in smem
                                          ("sqeuclidean", 256, 32),     # dsub 8, codebooks via L2
                                          ("inner_product", 256, 128)]) # dsub 2, codebooks via L2
-def test_ivf_pq_grouped_scan_equals_lut_scan(b2, monkeypatch, metric, d, m):
+def test_ivf_pq_grouped_scan_equals_lut_scan(b2, setenv, metric, d, m):
     """Large batches decode each probed list once into bf16 tiles for the tensor cores.  Its ADC
     scores use bf16-rounded residual queries / codebooks, so against the fp32 look-up-table scan
     of the same index: near-identical candidate sets and distances, same recall; after the exact
@@ -239,11 +239,11 @@ def test_ivf_pq_grouped_scan_equals_lut_scan(b2, monkeypatch, metric, d, m):
     _, ti = exact_knn(x.float(), q.float(), k, metric)
     out = {}
     for mode in ("0", "1"):
-        monkeypatch.setenv("B2VS_IVF_GROUPED", mode)
+        setenv("B2VS_IVF_GROUPED", mode)
         out[mode] = ix.search(q.cuda(), k, n_probes=nprobe)
         out[mode + "r"] = ix.search(q.cuda(), k, n_probes=nprobe, refine_ratio=4)
         torch.cuda.synchronize()
-    monkeypatch.setenv("B2VS_IVF_GROUPED_CAP", "32")
+    setenv("B2VS_IVF_GROUPED_CAP", "32")
     out["1c"] = ix.search(q.cuda(), k, n_probes=nprobe)
     torch.cuda.synchronize()
     (d0, i0), (d1, i1), (d2, i2) = out["0"], out["1"], out["1c"]
@@ -296,7 +296,7 @@ def test_ivf_more_than_128_probes(b2, nq):
 
 
 @pytest.mark.parametrize("kind", ["flat", "pq"])
-def test_ivf_grouped_scan_with_every_query_on_the_same_lists(b2, monkeypatch, kind):
+def test_ivf_grouped_scan_with_every_query_on_the_same_lists(b2, setenv, kind):
     """Worst-case skew: 700 near-identical queries probe the same few lists, so those lists get
     several 128-row query blocks each and every other list none."""
     x = clustered(30000, 64, 60, 81).to(torch.bfloat16)
@@ -307,7 +307,7 @@ def test_ivf_grouped_scan_with_every_query_on_the_same_lists(b2, monkeypatch, ki
         ix = b2.NativeIndex.ivf_pq(x.cuda(), 64, 32, metric="sqeuclidean", kmeans_iters=6)
     res = {}
     for mode in ("0", "1"):
-        monkeypatch.setenv("B2VS_IVF_GROUPED", mode)
+        setenv("B2VS_IVF_GROUPED", mode)
         res[mode] = ix.search(q.cuda(), 10, n_probes=6)
         torch.cuda.synchronize()
     (d0, i0), (d1, i1) = res["0"], res["1"]
@@ -421,7 +421,7 @@ def test_small_batch_cuda_graph_replay_equals_direct_search(b2, kind):
                                                   ("flat", torch.bfloat16, "inner_product", 72),
                                                   ("flat", torch.float32, "sqeuclidean", 200),
                                                   ("pq", torch.float16, "sqeuclidean", 64)])
-def test_tiny_batch_coarse_probe_scan_equals_tensor_core_probe(b2, monkeypatch, kind, dtype, metric, d):
+def test_tiny_batch_coarse_probe_scan_equals_tensor_core_probe(b2, setenv, kind, dtype, metric, d):
     """Batches of up to 32 queries pick their probe lists with the CUDA-core scan over the centroid
     operand matrix (K4b) instead of the tensor-core probe; both must lead to the same answers
     (B2VS_COARSE_SCAN=0 forces the tensor-core probe), including with fewer centroids than one
@@ -436,9 +436,9 @@ def test_tiny_batch_coarse_probe_scan_equals_tensor_core_probe(b2, monkeypatch, 
             kw = dict(n_probes=min(nlist, 24), refine_ratio=4)
         for nq in (1, 5, 8, 32):
             q = queries_from(x.float(), nq, 50 + nq).to(dtype).cuda()
-            monkeypatch.setenv("B2VS_COARSE_SCAN", "0")
+            setenv("B2VS_COARSE_SCAN", "0")
             d0, i0 = (t.clone() for t in ix.search(q, 10, **kw))
-            monkeypatch.delenv("B2VS_COARSE_SCAN")
+            setenv("B2VS_COARSE_SCAN", None)
             d1, i1 = (t.clone() for t in ix.search(q, 10, **kw))
             torch.cuda.synchronize()
             # same probe lists -> same candidates; a near-tie between two centroids may swap the
@@ -451,8 +451,8 @@ def test_tiny_batch_coarse_probe_scan_equals_tensor_core_probe(b2, monkeypatch, 
         # a full probe is exact whichever way the lists were ranked
         if kind == "flat" and nlist == 40:
             qf = queries_from(x.float(), 4, 77).to(dtype).cuda()
-            monkeypatch.setenv("B2VS_COARSE_SCAN", "0")
+            setenv("B2VS_COARSE_SCAN", "0")
             _, j0 = ix.search(qf, 10, n_probes=nlist)
-            monkeypatch.delenv("B2VS_COARSE_SCAN")
+            setenv("B2VS_COARSE_SCAN", None)
             _, j1 = ix.search(qf, 10, n_probes=nlist)
             assert torch.equal(j0, j1)

@@ -159,3 +159,87 @@ def test_encode_oracle_mean_pool_definition():
     np.testing.assert_allclose(out[0], (h[0, 0] + h[0, 1]) / 2)
     np.testing.assert_array_equal(out[1], [0.0, 0.0])          # 0 / clamp(0, 1e-9)
     np.testing.assert_allclose(encode.mean_pool(h, None), h.mean(axis=1))
+
+
+# ---- IVF restatement anchored on scikit-learn (tests/golden/ivf.npz, make_golden_ivf.py) ----------
+@pytest.fixture(scope="module")
+def ivf_gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "ivf.npz"))
+
+
+def test_oracle_kmeans_equals_sklearn_lloyd_from_the_same_init(ivf_gold):
+    from oracle.ivf import assign, kmeans
+    g = ivf_gold
+    x = torch.from_numpy(g["x"])
+    cent = kmeans(x, len(g["init_rows"]), iters=int(g["iters"]), balance=False,
+                  init=x[torch.from_numpy(g["init_rows"])])
+    np.testing.assert_allclose(cent.numpy(), g["centroids"], rtol=2e-4, atol=2e-4)
+    # list assignment == KMeans.predict
+    lab = assign(x, torch.from_numpy(g["centroids"]))
+    assert (lab.numpy() == g["labels"]).mean() > 0.999   # fp32 vs fp64 near-ties only
+
+
+def test_oracle_probes_and_list_scan_equal_sklearn(ivf_gold):
+    g = ivf_gold
+    x, q = torch.from_numpy(g["x"]), torch.from_numpy(g["q"])
+    o = IvfFlatOracle(x, len(g["init_rows"]), iters=int(g["iters"]), train_fraction=1.0, balance=False,
+                      init=x[torch.from_numpy(g["init_rows"])])
+    pr = o.probes(q, int(g["n_probes"]))
+    assert np.array_equal(pr.numpy(), g["probes"])
+    d, i = o.search(q, int(g["k"]), n_probes=int(g["n_probes"]))
+    assert np.array_equal(i.numpy(), g["scan_i"])
+    np.testing.assert_allclose(d.numpy(), g["scan_d"], rtol=1e-4, atol=1e-4)
+
+
+def test_oracle_residual_pq_equals_sklearn_codebooks_and_adc(ivf_gold):
+    g = ivf_gold
+    x, q = torch.from_numpy(g["x"]), torch.from_numpy(g["q"])
+    o = IvfPqOracle(x, len(g["init_rows"]), int(g["pq_M"]), iters=int(g["iters"]), train_fraction=1.0,
+                    pq_iters=int(g["pq_iters"]), n_codes=int(g["pq_ncode"]), balance=False,
+                    init=x[torch.from_numpy(g["init_rows"])], pq_init_rows=torch.from_numpy(g["pq_init_rows"]))
+    np.testing.assert_allclose(o.codebooks.numpy(), g["pq_codebooks"], rtol=5e-4, atol=5e-4)
+    assert (o.codes.numpy() == g["pq_codes"]).mean() > 0.995
+    # ADC over the nearest list only == per-subspace squared distances to the chosen codebook rows
+    # (16 codes x 4 subspaces: many rows share a code word, so ids tie; the sorted distances do not)
+    d, i = o.search(q, int(g["k"]), n_probes=1)
+    np.testing.assert_allclose(d.numpy(), g["adc_d"], rtol=2e-3, atol=2e-3)
+    strict = np.ones_like(g["adc_d"], bool)                      # positions with a unique distance
+    strict[:, 1:] &= np.abs(np.diff(g["adc_d"], axis=1)) > 1e-3
+    strict[:, :-1] &= np.abs(np.diff(g["adc_d"], axis=1)) > 1e-3
+    assert (i.numpy()[strict] == g["adc_rows"][strict]).mean() > 0.97
+
+
+def test_oracle_refine_candidates_are_not_clamped():
+    """k * refine_ratio > 128 candidates are re-ranked (the GPU path does not clamp either)."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3000, 16, generator=g)
+    q = torch.randn(8, 16, generator=g)
+    o = IvfPqOracle(x, 8, 4, iters=4, pq_iters=3)
+    seen = {}
+    orig = o._refine
+    o._refine = lambda qq, cand, k: seen.setdefault("n", cand.shape[1]) and orig(qq, cand, k)
+    o.search(q, 40, n_probes=8, refine_ratio=5)
+    assert seen["n"] == 200
+
+
+def test_cosine_golden_is_one_minus_normalised_inner_product(ivf_gold):
+    """B2VS_METRIC_COSINE semantics = scikit-learn metric='cosine' (the reference's CPU baseline,
+    VectorSearch_QuestionRetrieval.ipynb:L878): checked against the exact oracle on unit rows."""
+    g = ivf_gold
+    x = torch.nn.functional.normalize(torch.from_numpy(g["x"]), dim=1)
+    q = torch.nn.functional.normalize(torch.from_numpy(g["q"]), dim=1)
+    d, i = exact.exact_knn(x, q, int(g["k"]), "inner_product")
+    assert (i.numpy() == g["cos_i"]).mean() > 0.99
+    np.testing.assert_allclose(1.0 - d.numpy(), g["cos_d"], atol=2e-5)
+
+
+def test_oracle_search_many_equals_search():
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(4000, 24, generator=g)
+    q = torch.randn(30, 24, generator=g)
+    for metric in ("sqeuclidean", "inner_product"):
+        o = IvfFlatOracle(x, 32, metric, iters=5)
+        many = o.search_many(q, 7, [1, 4, 32])
+        for p in (1, 4, 32):
+            _, i = o.search(q, 7, n_probes=p)
+            assert torch.equal(many[p], i), (metric, p)

@@ -25,8 +25,10 @@ for case in range(n_cases):
     q = torch.randn(nq, d, generator=g, device="cuda").to(dtype)
     if group:
         os.environ["B2VS_TC_GROUP"] = group
+        b2._native.reload_env()
     else:
         os.environ.pop("B2VS_TC_GROUP", None)
+        b2._native.reload_env()
     try:
         ix = b2.NativeIndex.flat(x, metric=metric, id_offset=11)
         dd, ii = ix.search(q, k)
@@ -50,5 +52,6 @@ for case in range(n_cases):
         print("EXC", tag, repr(e)[:300], flush=True)
         bad += 1
 os.environ.pop("B2VS_TC_GROUP", None)
+b2._native.reload_env()
 print("bad cases:", bad)
 sys.exit(1 if bad else 0)

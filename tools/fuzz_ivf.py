@@ -41,10 +41,12 @@ for case in range(n_cases):
                 assert "grouped scan" in str(e) or "exceed" in str(e), e
                 print("ok (unsupported, reported)", tag); continue
         os.environ["B2VS_IVF_GROUPED"] = "1"
+        b2._native.reload_env()
         d1, i1 = ix.search(q, k, n_probes=nprobe)
         torch.cuda.synchronize()
         if k <= 128:
             os.environ["B2VS_IVF_GROUPED"] = "0"
+            b2._native.reload_env()
             d0, i0 = ix.search(q, k, n_probes=nprobe)
             torch.cuda.synchronize()
             inter = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(i1.cpu(), i0.cpu()))
@@ -64,10 +66,12 @@ for case in range(n_cases):
             inter = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(i1[:, :kk].cpu(), fi.cpu()))
             ok = ok and inter >= 0.985 * nq * kk
         os.environ.pop("B2VS_IVF_GROUPED", None)
+        b2._native.reload_env()
         print("ok " if ok else "BAD", tag, flush=True)
         bad += 0 if ok else 1
     except Exception as e:
         os.environ.pop("B2VS_IVF_GROUPED", None)
+        b2._native.reload_env()
         print("EXC", tag, repr(e)[:300], flush=True)
         bad += 1
 print("bad cases:", bad)

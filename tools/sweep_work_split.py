@@ -28,14 +28,19 @@ for nq in q_list:
     qi = torch.randint(0, n, (nq,), generator=g, device=dev)
     q = (x[qi].float() + 0.1 * torch.randn((nq, d), generator=g, device=dev)).to(torch.float16)
     os.environ["B2VS_DEBUG_SPLIT"] = "1"
+    b2._native.reload_env()
     os.environ.pop("B2VS_WORK_CHUNK_TILES", None)
+    b2._native.reload_env()
     ix.search(q, 20, n_probes=nprobe, refine_ratio=rr)
     os.environ.pop("B2VS_DEBUG_SPLIT")
+    b2._native.reload_env()
     for c in c_list:
         if c:
             os.environ["B2VS_WORK_CHUNK_TILES"] = str(c)
+            b2._native.reload_env()
         else:
             os.environ.pop("B2VS_WORK_CHUNK_TILES", None)
+            b2._native.reload_env()
         for _ in range(5):
             ix.search(q, 20, n_probes=nprobe, refine_ratio=rr)
         torch.cuda.synchronize()
