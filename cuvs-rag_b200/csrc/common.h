@@ -205,9 +205,9 @@ struct PqGroupedScanArgs {
   const void* q_mat;      // gathered residual queries [q_rows, dim] bf16
   int64_t q_rows;
   int dim, pq_dim, dsub;
-  const void* codes;      // interleaved PQ codes
+  const void* codes;      // PQ codes [n_groups][pq_dim][32] (sub-space major inside 32-row groups)
   uint32_t n_groups;      // 32-row groups in `codes`
-  const void* cb16;       // bf16 codebooks [pq_dim][256][dsub]
+  const void* cb16t;      // bf16 codebooks, code-major [256][pq_dim][dsub]
   const float* beta;      // [n_slots + 256] ||r^||^2 (L2) / 0 (IP), +inf on padding slots
   float alpha;
   const void* work;       // int4 [max_work]

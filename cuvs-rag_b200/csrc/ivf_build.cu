@@ -73,7 +73,6 @@ pq_encode_kernel(const T* __restrict__ x, const int* __restrict__ labels,
   for (int i = threadIdx.x; i < 256 * dsub; i += blockDim.x)
     cb[i] = codebooks[static_cast<size_t>(m) * 256 * dsub + i];
   __syncthreads();
-  const int n_chunks = mp >> 4;
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < n;
        r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const uint32_t slot = slot_of_row[r];
@@ -92,9 +91,7 @@ pq_encode_kernel(const T* __restrict__ x, const int* __restrict__ labels,
       }
       if (s < best) { best = s; best_j = j; }
     }
-    const uint32_t g = slot >> 5, l = slot & 31;
-    codes[((static_cast<size_t>(g) * n_chunks + (m >> 4)) * 32 + l) * 16 + (m & 15)] =
-        static_cast<uint8_t>(best_j);
+    codes[pq_code_offset(slot, m, mp)] = static_cast<uint8_t>(best_j);
   }
 }
 
@@ -131,24 +128,27 @@ __global__ void pq_cb16_kernel(const float* __restrict__ codebooks, int entries,
   cbn[e] = n2;
 }
 
+// transposed bf16 codebooks [256][pq_dim][dsub]: what the grouped scan's decoder warps look up
+// (lanes = consecutive sub-spaces of one list row -> consecutive shared-memory banks)
+__global__ void pq_cb16t_kernel(const uint16_t* __restrict__ cb16, int pq_dim, int dsub,
+                                uint16_t* __restrict__ cb16t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [pq_dim][256][dsub]
+  if (i >= pq_dim * 256 * dsub) return;
+  const int d = i % dsub, j = (i / dsub) & 255, m = i / (dsub * 256);
+  cb16t[(static_cast<size_t>(j) * pq_dim + m) * dsub + d] = cb16[i];
+}
+
 // ||decoded residual||^2 of every slot (thread = slot); +inf on padding slots and in the slack
-__global__ void pq_slot_norms_kernel(const uint4* __restrict__ codes4, const uint32_t* __restrict__ row_ids,
-                                     uint32_t n_slots, size_t n_out, int n_chunks,
+__global__ void pq_slot_norms_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ row_ids,
+                                     uint32_t n_slots, size_t n_out, int pq_dim, int mp,
                                      const float* __restrict__ cbn, int l2, float* __restrict__ out,
                                      unsigned int* __restrict__ max_bits) {
   const size_t slot = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   float n2 = 0.f;
   const bool real = slot < n_slots && row_ids[slot] != kNoRow;
   if (real) {
-    const size_t g = slot >> 5;
-    const int r = static_cast<int>(slot & 31);
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      const uint4 v = __ldg(codes4 + (g * n_chunks + ch) * 32 + r);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        n2 += __ldg(cbn + (ch * 16 + i) * 256 + ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu));
-    }
+    for (int m = 0; m < pq_dim; ++m)
+      n2 += __ldg(cbn + m * 256 + __ldg(codes + pq_code_offset(slot, m, mp)));
   }
   if (slot < n_out) out[slot] = real ? (l2 ? n2 : 0.f) : INFINITY;
   const unsigned int wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(n2));
@@ -162,6 +162,7 @@ int pq_prepare_grouped(b2vs_index* index, IvfData* d, cudaStream_t st) {
   const int entries = d->pq_dim * 256;
   const size_t n_out = static_cast<size_t>(std::max<int64_t>(d->n_slots, 1)) + kNormSlack;
   B2VS_TRY(d->cb16.reserve(static_cast<size_t>(entries) * d->dsub * 2));
+  B2VS_TRY(d->cb16t.reserve(static_cast<size_t>(entries) * d->dsub * 2));
   B2VS_TRY(d->cbn.reserve(static_cast<size_t>(entries) * sizeof(float)));
   B2VS_TRY(d->pq_norm.reserve(n_out * sizeof(float)));
   DevBuf cell;
@@ -169,9 +170,11 @@ int pq_prepare_grouped(b2vs_index* index, IvfData* d, cudaStream_t st) {
   B2VS_CUDA(cudaMemsetAsync(cell.ptr, 0, sizeof(unsigned int), st));
   pq_cb16_kernel<<<static_cast<unsigned>(ceil_div(entries, 256)), 256, 0, st>>>(
       d->codebooks.as<float>(), entries, d->dsub, d->cb16.as<uint16_t>(), d->cbn.as<float>());
+  pq_cb16t_kernel<<<static_cast<unsigned>(ceil_div(entries * d->dsub, 256)), 256, 0, st>>>(
+      d->cb16.as<uint16_t>(), d->pq_dim, d->dsub, d->cb16t.as<uint16_t>());
   pq_slot_norms_kernel<<<static_cast<unsigned>(ceil_div(n_out, 256)), 256, 0, st>>>(
-      d->codes.as<uint4>(), d->row_ids.as<uint32_t>(), static_cast<uint32_t>(d->n_slots), n_out,
-      d->mp >> 4, d->cbn.as<float>(), index->metric == B2VS_METRIC_L2 ? 1 : 0,
+      d->codes.as<uint8_t>(), d->row_ids.as<uint32_t>(), static_cast<uint32_t>(d->n_slots), n_out,
+      d->pq_dim, d->mp, d->cbn.as<float>(), index->metric == B2VS_METRIC_L2 ? 1 : 0,
       d->pq_norm.as<float>(), cell.as<unsigned int>());
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(&d->max_rhat2, cell.ptr, sizeof(float), cudaMemcpyDeviceToHost, st);

@@ -40,6 +40,8 @@ constexpr int kGroupRows = 128;  // query rows per grouped-scan work item (= the
 #endif
 constexpr bool kSkipPaddingRows = B2VS_SKIP_PAD_ROWS != 0;   // gather kernels leave group-padding rows unwritten
 constexpr int kSeedSortMinQueries = 2048;  // below this the seed pass skips its ordering sort
+constexpr int kTcSeedMinQueries = 256;     // from here on thresholds come from a tensor-core seed pass
+constexpr int kSeedTileRows = 256;         // rows of every seed list that the seed pass scores
 constexpr int kMaxProbes = 2048;  // coarse probe = exact top-n_probes (large-k path above 128)
 constexpr int kNormSlack = 256;  // slot_norm floats past the last slot (whole-tile beta loads)
 
@@ -80,9 +82,12 @@ struct IvfData {
   DevBuf data;        // IVF-Flat: u16 [n_slots, dp]
   DevBuf slot_norm;   // IVF-Flat: f32 [n_slots + kNormSlack] ||x||^2 (L2) or 0 (IP); +inf on padding
   DevBuf codebooks;   // IVF-PQ: f32 [pq_dim, 256, dsub]
-  DevBuf codes;       // IVF-PQ: u8, 32-row groups interleaved by 16-byte chunks
+  DevBuf codes;       // IVF-PQ: u8 [n_slots / 32][mp][32]: 32-row groups, sub-space major inside a
+                      // group (see pq_code_offset): the decoder warps of the grouped scan read the
+                      // 32 codes of one (group, sub-space) as ONE 32-byte piece per lane
   // IVF-PQ grouped tensor-core scan (derived from codebooks + codes at build / load time)
   DevBuf cb16;        // bf16 [pq_dim, 256, dsub]: the codebooks as the MMA sees them
+  DevBuf cb16t;       // bf16 [256, pq_dim, dsub]: the same, code-major (decoder look-ups, bank = sub-space)
   DevBuf cbn;         // f32 [pq_dim, 256] squared norm of each (rounded) codebook entry
   DevBuf pq_norm;     // f32 [n_slots + kNormSlack] ||decoded residual||^2 (L2) / 0 (IP); +inf on padding
   float max_rhat2 = 0.f;
@@ -90,6 +95,7 @@ struct IvfData {
   DevBuf ws_probe_d, ws_probe_i, ws_keys, ws_qf, ws_qnorm, ws_counter, ws_ref_d, ws_ref_i;
   DevBuf ws_item_lab, ws_item_cnt, ws_item_off, ws_item_perm, ws_item_slot;  // list-ordered scan items
   DevBuf ws_g_work, ws_g_q, ws_g_rowq, ws_g_tau, ws_g_cand, ws_g_cnt, ws_g_bias;  // grouped scan
+  DevBuf ws_seed_ids;   // [nq, m] the nearest probes of every query (tensor-core seed pass)
   const void* src_rows = nullptr;  // IVF-PQ: the caller's [n, dim] rows, BORROWED for refine
   std::vector<int32_t> h_sizes;
   DevBuf rank_of_list, list_of_rank;  // int [n_lists]: lists in descending-size order (scan scheduling)
@@ -109,7 +115,7 @@ struct IvfData {
   uint64_t graph_clock = 0;
   size_t owned_bytes() const {
     return centroids.bytes + offsets.bytes + sizes.bytes + row_ids.bytes + data.bytes +
-           slot_norm.bytes + codebooks.bytes + codes.bytes + cb16.bytes + cbn.bytes + pq_norm.bytes +
+           slot_norm.bytes + codebooks.bytes + codes.bytes + cb16.bytes + cb16t.bytes + cbn.bytes + pq_norm.bytes +
            rank_of_list.bytes + list_of_rank.bytes;
   }
   void destroy() {
@@ -125,7 +131,7 @@ struct IvfData {
                       &ws_probe_d, &ws_probe_i, &ws_keys, &ws_qf, &ws_qnorm, &ws_counter,
                       &ws_ref_d, &ws_ref_i, &ws_item_lab, &ws_item_cnt, &ws_item_off, &ws_item_perm,
                       &ws_item_slot, &ws_g_work, &ws_g_q, &ws_g_rowq, &ws_g_tau, &ws_g_cand, &ws_g_cnt,
-                      &ws_g_bias, &cb16, &cbn, &pq_norm, &cq_offsets, &cq_probe, &ws_cq_keys})
+                      &ws_g_bias, &ws_seed_ids, &cb16, &cb16t, &cbn, &pq_norm, &cq_offsets, &cq_probe, &ws_cq_keys})
       b->release();
   }
 };
@@ -162,16 +168,20 @@ __device__ __forceinline__ uint16_t to_op16(float v, int fmt, float* back) {
   return __bfloat16_as_ushort(b);
 }
 
+// byte offset of the code of sub-space m of list slot `slot` (mp = pq_dim padded to 16)
+__host__ __device__ __forceinline__ size_t pq_code_offset(size_t slot, int m, int mp) {
+  return ((slot >> 5) * static_cast<size_t>(mp) + static_cast<size_t>(m)) * 32 + (slot & 31);
+}
+
 // ---- kmeans.cu ------------------------------------------------------------------------------
 // Temporaries of one k-means fit.  A caller that fits many small problems in a row (the 64+ PQ
 // sub-codebooks) passes the same workspace to every fit, so device memory is allocated once
 // instead of being malloc'ed and freed (= device-synchronised) per fit.
 struct KmWorkspace {
-  DevBuf sums, counts, labels, donors, seg_off, seg_cur, seg_rows, seg_slot, order, donor_scratch;
+  DevBuf sums, counts, labels, seg_off, seg_cur, seg_rows, seg_slot;
   FlatEngine eng;
   void release() {
-    for (DevBuf* b : {&sums, &counts, &labels, &donors, &seg_off, &seg_cur, &seg_rows, &seg_slot,
-                      &order, &donor_scratch})
+    for (DevBuf* b : {&sums, &counts, &labels, &seg_off, &seg_cur, &seg_rows, &seg_slot})
       b->release();
     eng.destroy();
   }
@@ -198,8 +208,10 @@ size_t sorted_rows_cap(const IvfData* d, int items, int group_pad);
 int reserve_item_sort(IvfData* d, int items, int group_pad);
 int sort_items_by_list(IvfData* d, const long long* probe_ids, int items, int stride, int group_pad,
                        cudaStream_t st);
+// row_limit > 0: only the first row_limit rows of every list become work (the seed pass)
 int plan_grouped_work(IvfData* d, const long long* probe_ids, int items, int chunk_rows, int slots,
-                      int4* work, int* n_work, unsigned long long* counter, cudaStream_t st);
+                      int4* work, int* n_work, unsigned long long* counter, cudaStream_t st,
+                      int row_limit = 0);
 void choose_work_split(const b2vs_index* index, const IvfData* d, int items, int* chunk_rows, int* slots);
 bool plan_is_small(const IvfData* d, int items);
 
@@ -217,6 +229,8 @@ int launch_flat_seed_tau(const b2vs_index* index, IvfData* d, const long long* p
 int launch_flat_rescue(const b2vs_index* index, IvfData* d, const long long* probe_ids, int n_probes,
                        int nq, int k, int cap, cudaStream_t st);
 int launch_group_select(IvfData* d, int nq, int cap, int k, unsigned long long* total_cand, cudaStream_t st);
+// thresholds of the full pass from the candidates the seed pass appended (k-th best per query)
+int launch_seed_select(IvfData* d, int nq, int cap, int k, cudaStream_t st);
 int launch_gather_group_queries(IvfData* d, int64_t rows_cap, int n_probes, int q_split, cudaStream_t st);
 int launch_gather_group_residuals(const b2vs_index* index, IvfData* d, int64_t rows_cap,
                                   const long long* probe_ids, int n_probes, cudaStream_t st);

@@ -13,7 +13,7 @@ __global__ void build_group_work_kernel(const uint32_t* __restrict__ group_off,
                                         const uint32_t* __restrict__ offsets,
                                         const int* __restrict__ group_cnt,
                                         const int* __restrict__ list_of_rank, int n_lists,
-                                        int chunk_rows, int slots,
+                                        int chunk_rows, int slots, int row_limit,
                                         int4* __restrict__ work, int* __restrict__ n_work,
                                         unsigned long long* __restrict__ scanned_rows) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;   // size rank: items come out longest first
@@ -21,7 +21,9 @@ __global__ void build_group_work_kernel(const uint32_t* __restrict__ group_off,
   if (r >= n_lists) return;
   const int l = list_of_rank[r];
   const int b0 = static_cast<int>(group_off[r] >> 7), b1 = static_cast<int>(group_off[r + 1] >> 7);
-  const int begin = static_cast<int>(offsets[l]), end = static_cast<int>(offsets[l + 1]);
+  const int begin = static_cast<int>(offsets[l]);
+  int end = static_cast<int>(offsets[l + 1]);
+  if (row_limit > 0) end = min(end, begin + row_limit);   // seed pass: the head of every list only
   // Small batches have fewer (list, query block) pairs than SMs: a list is then cut into `slots`
   // row ranges of chunk_rows (a multiple of the 256-row tile), one work item each - append mode
   // keeps no per-item state, so the pieces are independent.  Ranges past the list end are empty.
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(kPlanThreads)
 ivf_plan_small_kernel(const long long* __restrict__ probe_ids, int items,
                       const int* __restrict__ rank_of_list, const int* __restrict__ list_of_rank,
                       const uint32_t* __restrict__ offsets, int n_lists, int chunk_rows, int slots,
-                      uint32_t* __restrict__ row_item, uint32_t* __restrict__ group_off,
+                      int row_limit, uint32_t* __restrict__ row_item, uint32_t* __restrict__ group_off,
                       int4* __restrict__ work, int* __restrict__ n_work,
                       unsigned long long* __restrict__ scanned_rows) {
   extern __shared__ int plan_sm[];
@@ -122,7 +124,8 @@ ivf_plan_small_kernel(const long long* __restrict__ probe_ids, int items,
     const int c = cnt[i];
     if (c == 0) continue;
     const int l = list_of_rank[i];
-    const int rows = static_cast<int>(offsets[l + 1] - offsets[l]);
+    int rows = static_cast<int>(offsets[l + 1] - offsets[l]);
+    if (row_limit > 0) rows = min(rows, row_limit);
     const u64 blocks = static_cast<u64>((c + kGroupRows - 1) / kGroupRows);
     sum += ((blocks * kGroupRows) << 32) | (blocks * static_cast<u64>((rows + chunk_rows - 1) / chunk_rows));
   }
@@ -163,7 +166,9 @@ ivf_plan_small_kernel(const long long* __restrict__ probe_ids, int items,
     const int c = cnt[i];
     if (c == 0) continue;
     const int l = list_of_rank[i];
-    const int begin = static_cast<int>(offsets[l]), end = static_cast<int>(offsets[l + 1]);
+    const int begin = static_cast<int>(offsets[l]);
+    int end = static_cast<int>(offsets[l + 1]);
+    if (row_limit > 0) end = min(end, begin + row_limit);
     const int blocks = (c + kGroupRows - 1) / kGroupRows;
     const int b0 = static_cast<int>(run >> 7);
     for (int b = 0; b < blocks; ++b)
@@ -195,7 +200,7 @@ bool plan_is_small(const IvfData* d, int items) {
 // counting-sort kernels + build_group_work_kernel.
 int plan_grouped_work(IvfData* d, const long long* probe_ids, int items, int chunk_rows,
                              int slots, int4* work, int* n_work, unsigned long long* counter,
-                             cudaStream_t st) {
+                             cudaStream_t st, int row_limit) {
   if (plan_is_small(d, items)) {
     B2VS_TRY(reserve_item_sort(d, items, kGroupRows));
     B2VS_CUDA(cudaMemsetAsync(d->ws_item_perm.ptr, 0xFF,
@@ -205,7 +210,7 @@ int plan_grouped_work(IvfData* d, const long long* probe_ids, int items, int chu
                                    static_cast<int>(smem)));
     ivf_plan_small_kernel<<<1, kPlanThreads, smem, st>>>(
         probe_ids, items, d->rank_of_list.as<int>(), d->list_of_rank.as<int>(),
-        d->offsets.as<uint32_t>(), d->n_lists, chunk_rows, slots, d->ws_item_perm.as<uint32_t>(),
+        d->offsets.as<uint32_t>(), d->n_lists, chunk_rows, slots, row_limit, d->ws_item_perm.as<uint32_t>(),
         d->ws_item_off.as<uint32_t>(), work, n_work, counter);
     B2VS_CUDA(cudaGetLastError());
     return B2VS_OK;
@@ -213,7 +218,7 @@ int plan_grouped_work(IvfData* d, const long long* probe_ids, int items, int chu
   B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, kGroupRows, st));
   build_group_work_kernel<<<static_cast<unsigned>(ceil_div(d->n_lists, 256)), 256, 0, st>>>(
       d->ws_item_off.as<uint32_t>(), d->offsets.as<uint32_t>(), d->ws_item_cnt.as<int>(),
-      d->list_of_rank.as<int>(), d->n_lists, chunk_rows, slots, work, n_work, counter);
+      d->list_of_rank.as<int>(), d->n_lists, chunk_rows, slots, row_limit, work, n_work, counter);
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }

@@ -66,6 +66,22 @@ __device__ __forceinline__ void block_merge_and_store(WarpTopK& tk, u64 (*lists)
   }
 }
 
+// The 16 codes of sub-spaces [m0, m0 + 16) of list slot (g << 5) + lane, packed into one uint4 (code
+// of sub-space m0 + i in byte i).  Codes are stored sub-space major inside every 32-row group
+// (pq_code_offset), the layout the grouped tensor-core scan's decoders want; the look-up-table
+// scans below - lane = list row - collect their row's codes with 16 coalesced byte loads.
+__device__ __forceinline__ uint4 ld_code_chunk(const uint8_t* __restrict__ codes, size_t g, int mp, int m0,
+                                               int lane) {
+  const uint8_t* p = codes + (g * static_cast<size_t>(mp) + static_cast<size_t>(m0)) * 32 + lane;
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    w[i] = static_cast<uint32_t>(__ldg(p + (4 * i) * 32)) | (static_cast<uint32_t>(__ldg(p + (4 * i + 1) * 32)) << 8) |
+           (static_cast<uint32_t>(__ldg(p + (4 * i + 2) * 32)) << 16) |
+           (static_cast<uint32_t>(__ldg(p + (4 * i + 3) * 32)) << 24);
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // ---- K5 IVF-Flat list scan -----------------------------------------------------------------
 // One CTA per (query, probe).  A warp streams 32 consecutive list rows per batch, 4 rows at a
 // time; each lane owns the same 16-byte chunks of every row, so its slice of the query stays in
@@ -306,6 +322,35 @@ ivf_group_select_kernel(const u64* __restrict__ cand, const int* __restrict__ co
   for (int i = threadIdx.x; i < k; i += blockDim.x) out_keys[static_cast<size_t>(q) * k + i] = i < P ? sk[i] : kKeyInf;
 }
 
+// Seed pass -> thresholds.  The tensor-core kernel appended the scores of the first rows of each
+// query's nearest lists (no threshold) to the query's buffer; the k-th best of them is a valid
+// upper bound of the query's final k-th score, computed by the SAME arithmetic as the full pass
+// (identical MMA sequence over identical operands), so it needs no rounding cushion beyond the
+// inclusive ulp.  One warp per query: a 128-key sorted list in registers, candidates offered 32
+// at a time and filtered by the running k-th score.
+__global__ void __launch_bounds__(128)
+ivf_seed_select_kernel(const u64* __restrict__ cand, const int* __restrict__ count, int cap, int k,
+                       int nq, float* __restrict__ tau) {
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  const int n = min(count[q], cap);
+  const u64* src = cand + static_cast<size_t>(q) * cap;
+  WarpTopK tk;
+  tk.init();
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    u64 ck = kKeyInf;
+    if (i < n) {
+      const u64 v = __ldcg(src + i);
+      if (key_score(v) < tk.tau) ck = v;
+    }
+    tk.offer(ck, k, lane);
+  }
+  // tk.tau = k-th best score (+inf while fewer than k candidates): publish it inclusively
+  if (lane == 0) tau[q] = isinf(tk.tau) ? tk.tau : nextafterf(tk.tau, INFINITY);
+}
+
 // One CTA per query whose candidate buffer overflowed: exact scan of all its probes.
 template <int FMT, int J>
 __global__ void __launch_bounds__(kScanThreads, 2)
@@ -387,12 +432,11 @@ ivf_pq_scan_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict
   WarpTopK tk;
   tk.init();
   const int n_chunks = mp >> 4;
-  const uint4* codes4 = reinterpret_cast<const uint4*>(codes);
   for (uint32_t g0 = (begin >> 5) + warp; g0 < (end >> 5); g0 += kScanWarps) {
     const uint32_t slot = (g0 << 5) + lane;
     float s = bias;
     for (int ch = 0; ch < n_chunks; ++ch) {
-      const uint4 v = __ldg(codes4 + (static_cast<size_t>(g0) * n_chunks + ch) * 32 + lane);
+      const uint4 v = ld_code_chunk(codes, g0, mp, ch * 16, lane);
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -443,7 +487,6 @@ ivf_pq_scan_query_kernel(const uint8_t* __restrict__ codes, const uint32_t* __re
   unsigned long long rows_seen = 0;
   constexpr int kV = NCH > 0 ? NCH : 1;
   const int n_chunks = NCH > 0 ? NCH : (mp >> 4);
-  const uint4* codes4 = reinterpret_cast<const uint4*>(codes);
   for (int q = blockIdx.x; q < nq; q += gridDim.x) {
     __syncthreads();  // previous query fully retired (lists, s_*, sq)
     // the query's probe lists and their extents, fetched once in parallel
@@ -478,7 +521,7 @@ ivf_pq_scan_query_kernel(const uint8_t* __restrict__ codes, const uint32_t* __re
       if (NCH > 0 && g_first < (end >> 5)) {
 #pragma unroll
         for (int ch = 0; ch < kV; ++ch)
-          v[ch] = __ldg(codes4 + (static_cast<size_t>(g_first) * kV + ch) * 32 + lane);
+          v[ch] = ld_code_chunk(codes, g_first, mp, ch * 16, lane);
         rid = __ldg(row_ids + (g_first << 5) + lane);
       }
       float bpart = 0.f;
@@ -562,7 +605,7 @@ ivf_pq_scan_query_kernel(const uint8_t* __restrict__ codes, const uint32_t* __re
           if (NCH > 0) {
 #pragma unroll
             for (int ch = 0; ch < kV; ++ch)
-              v[ch] = __ldg(codes4 + (static_cast<size_t>(g0) * kV + ch) * 32 + lane);
+              v[ch] = ld_code_chunk(codes, g0, mp, ch * 16, lane);
           }
           rid = __ldg(row_ids + slot);
         }
@@ -581,7 +624,7 @@ ivf_pq_scan_query_kernel(const uint8_t* __restrict__ codes, const uint32_t* __re
           }
         } else {
           for (int cc = 0; cc < n_chunks; ++cc) {
-            const uint4 vv = __ldg(codes4 + (static_cast<size_t>(g0) * n_chunks + cc) * 32 + lane);
+            const uint4 vv = ld_code_chunk(codes, g0, mp, cc * 16, lane);
             const uint32_t w[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -752,7 +795,7 @@ ivf_pq_lut_scan_kernel(int mode, const uint8_t* __restrict__ codes, const uint32
   float bias_first = 0.f;
   const int np = mode == 0 ? 1 : n_probes;
   const int n_chunks = pq_dim >> 4;
-  const uint4* codes4 = reinterpret_cast<const uint4*>(codes);
+  const int mp = pq_dim;   // the grouped scan requires pq_dim % 16 == 0
   for (int p = 0; p < np; ++p) {
     const long long list = probe_ids[static_cast<size_t>(q) * n_probes + p];
     if (list < 0) continue;
@@ -807,7 +850,7 @@ ivf_pq_lut_scan_kernel(int mode, const uint8_t* __restrict__ codes, const uint32
       const uint32_t slot = (g0 << 5) + lane;
       float sc = bias;
       for (int ch = 0; ch < n_chunks; ++ch) {
-        const uint4 v = __ldg(codes4 + (static_cast<size_t>(g0) * n_chunks + ch) * 32 + lane);
+        const uint4 v = ld_code_chunk(codes, g0, mp, ch * 16, lane);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 16; ++i)
@@ -1001,6 +1044,13 @@ int launch_flat_rescue(const b2vs_index* index, IvfData* d, const long long* pro
 int launch_group_select(IvfData* d, int nq, int cap, int k, unsigned long long* total_cand, cudaStream_t st) {
   ivf_group_select_kernel<<<nq, kSelectThreads, static_cast<size_t>(cap) * sizeof(u64), st>>>(
       d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), cap, k, d->ws_keys.as<u64>(), total_cand);
+  B2VS_CUDA(cudaGetLastError());
+  return B2VS_OK;
+}
+
+int launch_seed_select(IvfData* d, int nq, int cap, int k, cudaStream_t st) {
+  ivf_seed_select_kernel<<<static_cast<unsigned>(ceil_div(nq, 4)), 128, 0, st>>>(
+      d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), cap, k, nq, d->ws_g_tau.as<float>());
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }

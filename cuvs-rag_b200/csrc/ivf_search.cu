@@ -38,12 +38,13 @@ static int ivf_pq_search_bigk(b2vs_index* index, const void* q, int q_dtype, int
 // caller sizes, zeroes and later selects from them).  probe_ids is [nq, n_probes] dense.
 static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long* probe_ids,
                                  int n_probes, int nq, int cap, unsigned long long* counter,
-                                 cudaStream_t st, bool timed = false) {
+                                 cudaStream_t st, bool timed = false, int row_limit = 0) {
   const int items = nq * n_probes;
   const int q_split = index->dtype == B2VS_F32 ? 1 : 0;
   const int q_pitch = q_split ? 2 * static_cast<int>(round_up(d->dp, 64)) : d->dp;
   int chunk_rows = 0, slots = 1;
   choose_work_split(index, d, items, &chunk_rows, &slots);
+  if (row_limit > 0) { chunk_rows = row_limit; slots = 1; }   // seed pass: one tile per list
   const int max_work = (items / kGroupRows + std::min(d->n_lists, items) + 1) * slots;
   const int64_t rows_cap = static_cast<int64_t>(sorted_rows_cap(d, items, kGroupRows));
   B2VS_TRY(d->ws_g_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16));
@@ -51,7 +52,7 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
   B2VS_TRY(d->ws_g_rowq.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
   int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
   B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
-                             counter, st));
+                             counter, st, row_limit));
   B2VS_TRY(launch_gather_group_queries(d, rows_cap, n_probes, q_split, st));
   GroupedScanArgs ga{};
   ga.q_mat = d->ws_g_q.ptr; ga.q_rows = rows_cap;
@@ -65,6 +66,36 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
   if (timed) B2VS_CUDA(cudaEventRecord(d->ev0, st));
   B2VS_TRY(launch_grouped_scan(index->dev, ga, st));
   if (timed) B2VS_CUDA(cudaEventRecord(d->ev1, st));
+  return B2VS_OK;
+}
+
+// Thresholds from a tensor-core SEED PASS (batches of kTcSeedMinQueries queries and more): the
+// first kSeedTileRows rows of each query's m nearest lists are scored by the same grouped kernel
+// with no threshold (m * 256 <= cap / 4 keys per query), and the k-th best of them becomes the
+// query's threshold for the full pass.  Against the CUDA-core seed kernels (one CTA per query over
+// the nearest list only) the sample is m times larger - on corpora without cluster structure the
+// nearest list's head alone leaves thousands of candidates per query, overflowing the buffers
+// into the exact rescue scan - it runs on the tensor cores, and it uses the full pass's own
+// arithmetic, so the threshold carries no rounding cushion.
+static int seed_lists(int n_probes, int cap) {
+  return std::max(1, std::min(n_probes, cap / 4 / kSeedTileRows));
+}
+static bool use_tc_seed(int nq) {
+  const int m = env().seed_mode;
+  return m >= 0 ? m == 1 : nq >= kTcSeedMinQueries;
+}
+template <typename ScanFn>
+static int run_tc_seed(IvfData* d, const long long* probe_ids, int n_probes, int nq, int k, int cap,
+                       cudaStream_t st, ScanFn scan) {
+  const int m = seed_lists(n_probes, cap);
+  B2VS_TRY(d->ws_seed_ids.reserve(static_cast<size_t>(nq) * m * sizeof(int64_t)));
+  B2VS_CUDA(cudaMemcpy2DAsync(d->ws_seed_ids.ptr, static_cast<size_t>(m) * sizeof(int64_t), probe_ids,
+                              static_cast<size_t>(n_probes) * sizeof(int64_t),
+                              static_cast<size_t>(m) * sizeof(int64_t), nq, cudaMemcpyDeviceToDevice, st));
+  B2VS_TRY(launch_fill_f32(d->ws_g_tau.as<float>(), static_cast<size_t>(nq), INFINITY, st));
+  B2VS_TRY(scan(reinterpret_cast<const long long*>(d->ws_seed_ids.ptr), m));
+  B2VS_TRY(launch_seed_select(d, nq, cap, k, st));
+  B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
   return B2VS_OK;
 }
 
@@ -210,11 +241,12 @@ int ivf_search_direct(b2vs_index* index, const void* q, int q_dtype, int nq, int
 // the tensor cores.  Thresholds / candidate buffers (ws_g_tau, ws_g_cand, ws_g_cnt) are the caller's.
 static int run_grouped_pq_scan(b2vs_index* index, IvfData* d, const long long* probe_ids, int n_probes,
                                int nq, int cap, unsigned long long* counter, cudaStream_t st,
-                               bool timed = false) {
+                               bool timed = false, int row_limit = 0) {
   const int items = nq * n_probes;
   const int l2 = index->metric == B2VS_METRIC_L2 ? 1 : 0;
   int chunk_rows = 0, slots = 1;
   choose_work_split(index, d, items, &chunk_rows, &slots);
+  if (row_limit > 0) { chunk_rows = row_limit; slots = 1; }   // seed pass: one tile per list
   const int max_work = (items / kGroupRows + std::min(d->n_lists, items) + 1) * slots;
   const int64_t rows_cap = static_cast<int64_t>(sorted_rows_cap(d, items, kGroupRows));
   B2VS_TRY(d->ws_g_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16));
@@ -223,14 +255,14 @@ static int run_grouped_pq_scan(b2vs_index* index, IvfData* d, const long long* p
   B2VS_TRY(d->ws_g_bias.reserve(static_cast<size_t>(rows_cap) * sizeof(float)));
   int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
   B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
-                             counter, st));
+                             counter, st, row_limit));
   B2VS_TRY(launch_gather_group_residuals(index, d, rows_cap, probe_ids, n_probes, st));
   PqGroupedScanArgs ga{};
   ga.q_mat = d->ws_g_q.ptr; ga.q_rows = rows_cap;
   ga.dim = index->dim; ga.pq_dim = d->pq_dim; ga.dsub = d->dsub;
   ga.codes = d->codes.ptr;
   ga.n_groups = static_cast<uint32_t>(std::max<int64_t>(d->n_slots, 32) >> 5);
-  ga.cb16 = d->cb16.ptr;
+  ga.cb16t = d->cb16t.ptr;
   ga.beta = d->pq_norm.as<float>(); ga.alpha = l2 ? -2.f : -1.f;
   ga.work = d->ws_g_work.ptr; ga.n_work = n_work; ga.max_work = max_work;
   ga.row_query = d->ws_g_rowq.as<int>(); ga.row_bias = d->ws_g_bias.as<float>();
@@ -442,15 +474,23 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
       const int cap = grouped_cap(k);
       // seed thresholds first (queries ordered by their nearest list), then group all the items
       B2VS_TRY(reserve_item_sort(d, items, kGroupRows));  // both sorts share these buffers
-      const bool order_seeds = nq >= kSeedSortMinQueries;
+      const bool tc_seed = use_tc_seed(nq);
+      const bool order_seeds = !tc_seed && nq >= kSeedSortMinQueries;
       if (order_seeds) B2VS_TRY(sort_items_by_list(d, probe_ids, nq, n_probes, 1, st));
       B2VS_TRY(d->ws_g_tau.reserve(static_cast<size_t>(nq) * sizeof(float)));
       B2VS_TRY(d->ws_g_cand.reserve(static_cast<size_t>(nq) * cap * sizeof(u64)));
       B2VS_TRY(d->ws_g_cnt.reserve(static_cast<size_t>(nq) * sizeof(int)));
       B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
-      B2VS_TRY(launch_flat_seed_tau(index, d, probe_ids, n_probes, nq, k, grouped_seed_rows(k),
-                                    q_split ? 1e-5f : 0.f,
-                                    order_seeds ? d->ws_item_perm.as<uint32_t>() : nullptr, st));
+      if (tc_seed) {
+        B2VS_TRY(run_tc_seed(d, probe_ids, n_probes, nq, k, cap, st, [&](const long long* ids, int m) {
+          return run_grouped_flat_scan(index, d, ids, m, nq, cap, nullptr, st, false, kSeedTileRows);
+        }));
+        launches += 8;
+      } else {
+        B2VS_TRY(launch_flat_seed_tau(index, d, probe_ids, n_probes, nq, k, grouped_seed_rows(k),
+                                      q_split ? 1e-5f : 0.f,
+                                      order_seeds ? d->ws_item_perm.as<uint32_t>() : nullptr, st));
+      }
       B2VS_TRY(run_grouped_flat_scan(index, d, probe_ids, n_probes, nq, cap, counter, st, timed));
       scan_timed_inside = true;
       B2VS_TRY(launch_group_select(d, nq, cap, k, counter + 1, st));
@@ -478,14 +518,22 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
     // decoded from the PQ codes instead of loaded.
     const int cap = grouped_cap(k);
     B2VS_TRY(reserve_item_sort(d, items, kGroupRows));
-    const bool order_seeds = nq >= kSeedSortMinQueries;
+    const bool tc_seed = use_tc_seed(nq);
+    const bool order_seeds = !tc_seed && nq >= kSeedSortMinQueries;
     if (order_seeds) B2VS_TRY(sort_items_by_list(d, probe_ids, nq, n_probes, 1, st));
     B2VS_TRY(d->ws_g_tau.reserve(static_cast<size_t>(nq) * sizeof(float)));
     B2VS_TRY(d->ws_g_cand.reserve(static_cast<size_t>(nq) * cap * sizeof(u64)));
     B2VS_TRY(d->ws_g_cnt.reserve(static_cast<size_t>(nq) * sizeof(int)));
     B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
-    B2VS_TRY(launch_pq_lut_scan(0, index, d, probe_ids, n_probes, nq, k, cap, grouped_seed_rows(k),
-                                order_seeds ? d->ws_item_perm.as<uint32_t>() : nullptr, st));
+    if (tc_seed) {
+      B2VS_TRY(run_tc_seed(d, probe_ids, n_probes, nq, k, cap, st, [&](const long long* ids, int m) {
+        return run_grouped_pq_scan(index, d, ids, m, nq, cap, nullptr, st, false, kSeedTileRows);
+      }));
+      launches += 8;
+    } else {
+      B2VS_TRY(launch_pq_lut_scan(0, index, d, probe_ids, n_probes, nq, k, cap, grouped_seed_rows(k),
+                                  order_seeds ? d->ws_item_perm.as<uint32_t>() : nullptr, st));
+    }
     B2VS_TRY(run_grouped_pq_scan(index, d, probe_ids, n_probes, nq, cap, counter, st, timed));
     scan_timed_inside = true;
     B2VS_TRY(launch_group_select(d, nq, cap, k, counter + 1, st));

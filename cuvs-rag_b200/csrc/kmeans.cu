@@ -2,7 +2,8 @@
 // reference call sites index_building_coordinator.py:392-404) and the label-grouping kernels.
 //   K1 assign  = the fused tensor-core engine with k = 1 (arg-min kept in a register, flat.cu)
 //   K2 update  = segmented reduction: rows grouped by label (histogram -> scan -> scatter), one CTA
-//                column per cluster sums its segment; balancing pairs computed ON THE DEVICE
+//                column per cluster sums its segment; cuVS-style balancing (adjust_centers) on
+//                the device, no host round trip per iteration
 //   K3 grouping kernels, shared with the IVF list construction and the (query, probe) item sort
 #include "ivf_internal.cuh"
 
@@ -55,43 +56,6 @@ __global__ void segment_sum_kernel(const T* __restrict__ x, const uint32_t* __re
   sums[static_cast<size_t>(c) * dim + j] = (a0 + a1) + (a2 + a3);
 }
 
-// K2 update, second half: mean of each cluster.  Balancing (the role cuVS's balanced k-means
-// "adjust centers" step plays): `donor_of[c] >= 0` tells cluster c - empty, or far below the
-// average size - to restart on a data row of the over-full cluster donor_of[c] (the pairing is
-// computed on the host from the cluster sizes, see balance_pairs), so Lloyd does not leave a few
-// giant lists next to starved ones.  Empty clusters without a donor restart on a random row.
-template <typename T>
-__global__ void finalize_centroids_kernel(const T* __restrict__ x, const int* __restrict__ labels,
-                                          int64_t n, int dim, const float* __restrict__ sums,
-                                          const int* __restrict__ counts,
-                                          const int* __restrict__ donor_of, uint64_t seed,
-                                          float* __restrict__ cent) {
-  const int c = blockIdx.x;
-  const int cnt = counts[c];
-  const int want = donor_of ? donor_of[c] : -1;
-  if (cnt > 0 && want < 0) {
-    const float inv = 1.f / static_cast<float>(cnt);
-    for (int j = threadIdx.x; j < dim; j += blockDim.x)
-      cent[static_cast<size_t>(c) * dim + j] = sums[static_cast<size_t>(c) * dim + j] * inv;
-    return;
-  }
-  __shared__ long long donor_row;
-  if (threadIdx.x == 0) {
-    long long row = 0;
-    // rejection-sample a row of the donor cluster (it is over-full, so this ends quickly)
-    for (int attempt = 0; attempt < 8192; ++attempt) {
-      row = static_cast<long long>(mix64(seed ^ (0xA5ull * (c + 1)) ^ (0x9E3779B9ull * attempt)) %
-                                   static_cast<uint64_t>(n));
-      if (want < 0 || labels[row] == want) break;
-    }
-    donor_row = row;
-  }
-  __syncthreads();
-  const long long row = donor_row;
-  for (int j = threadIdx.x; j < dim; j += blockDim.x)
-    cent[static_cast<size_t>(c) * dim + j] = ld_f32<T>(x + row * dim + j);
-}
-
 // ---- K3 list construction -----------------------------------------------------------------
 __global__ void histogram_kernel(const int* __restrict__ labels, int64_t n, int* __restrict__ sizes) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -139,113 +103,57 @@ __global__ void scatter_rows_kernel(const int* __restrict__ labels, int64_t n,
 }
 
 
-// Host side of the balancing step: clusters above 1.5x the average size want floor(size/avg) - 1
-// extra centroids; they are taken from the smallest clusters below 0.5x the average.
-static void balance_pairs(const std::vector<int>& counts, int64_t n, std::vector<int>* donor_of) {
-  const int ncl = static_cast<int>(counts.size());
-  donor_of->assign(ncl, -1);
-  const double avg = static_cast<double>(n) / ncl;
-  std::vector<int> order(ncl);
-  for (int i = 0; i < ncl; ++i) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](int a, int b) { return counts[a] < counts[b]; });
-  int lo = 0, hi = ncl - 1;
-  while (lo < hi) {
-    const int big = order[hi];
-    if (counts[big] <= 1.5 * avg) break;
-    int quota = static_cast<int>(counts[big] / avg) - 1;
-    if (quota < 1) quota = 1;
-    while (quota > 0 && lo < hi && counts[order[lo]] < 0.5 * avg) {
-      (*donor_of)[order[lo]] = big;
-      ++lo;
-      --quota;
-    }
-    if (quota > 0) break;  // no small clusters left to move
-    --hi;
-  }
+// K2 update, second half: mean of each cluster (a cluster left empty keeps its previous centre).
+__global__ void finalize_centroids_kernel(int dim, const float* __restrict__ sums,
+                                          const int* __restrict__ counts, float* __restrict__ cent) {
+  const int c = blockIdx.x;
+  const int cnt = counts[c];
+  if (cnt <= 0) return;
+  const float inv = 1.f / static_cast<float>(cnt);
+  for (int j = threadIdx.x; j < dim; j += blockDim.x)
+    cent[static_cast<size_t>(c) * dim + j] = sums[static_cast<size_t>(c) * dim + j] * inv;
 }
 
-
-// Device side of the same pairing (one CTA; the host version above is kept for cluster counts
-// beyond kBalanceMaxClusters).  Clusters are sorted by (size, id) ascending in global scratch;
-// big cluster j (j-th from the top, size > 1.5 avg) wants quota_j = max(1, floor(size / avg) - 1)
-// donors-in-reverse: the small clusters (size < 0.5 avg) at sorted positions
-// [sum_{i<j} quota_i, + quota_j) restart inside it, as long as position < #small and < ncl-1-j -
-// the closed form of the host loop's two-pointer walk.  No host round trip per Lloyd iteration.
-constexpr int kBalanceThreads = 1024;
-constexpr int kBalanceMaxClusters = 1 << 16;
-__global__ void __launch_bounds__(kBalanceThreads)
-balance_pairs_kernel(const int* __restrict__ counts, int ncl, long long n, u64* __restrict__ order,
-                     int* __restrict__ qprefix, int* __restrict__ donor_of) {
-  __shared__ int part[kBalanceThreads];
-  __shared__ int s_small, s_big;
-  const int t = threadIdx.x;
-  int P = 1;
-  while (P < ncl) P <<= 1;
-  for (int i = t; i < P; i += kBalanceThreads)
-    order[i] = i < ncl ? ((static_cast<u64>(static_cast<uint32_t>(counts[i])) << 32) | static_cast<uint32_t>(i))
-                       : kKeyInf;
-  for (int i = t; i < ncl; i += kBalanceThreads) donor_of[i] = -1;
-  if (t == 0) { s_small = 0; s_big = 0; }
-  __syncthreads();
-  for (int size = 2; size <= P; size <<= 1)
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = t; i < (P >> 1); i += kBalanceThreads) {
-        const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
-        const bool up = (lo & size) == 0;
-        const u64 a = order[lo], b = order[hi];
-        if ((a > b) == up) { order[lo] = b; order[hi] = a; }
-      }
-      __syncthreads();
+// Balancing step = cuVS / RAFT balanced k-means "adjust_centers" (raft/cluster/detail/
+// kmeans_balanced.cuh, restated - same rule as oracle/ivf.py::adjust_centers): a cluster of at
+// most kAdjustThreshold x the average size is re-seeded next to a LARGE cluster: pick a random data
+// row i whose own cluster l has at least the average size and set
+//     centre[small] = (wc * centre[l] + x[i]) / (wc + 1),    wc = min(size[l], kAdjustWeight).
+// Large clusters are never adjusted themselves, so reading centre[l] races with nothing.  Runs
+// entirely on the device: no host round trip per Lloyd iteration.
+constexpr float kAdjustThreshold = 0.25f;
+constexpr float kAdjustWeight = 7.0f;
+template <typename T>
+__global__ void adjust_centers_kernel(const T* __restrict__ x, const int* __restrict__ labels, int64_t n,
+                                      int dim, int ncl, const int* __restrict__ counts, uint64_t seed,
+                                      float* __restrict__ cent) {
+  const int c = blockIdx.x;
+  const float avg = static_cast<float>(n) / static_cast<float>(ncl);
+  if (static_cast<float>(counts[c]) > kAdjustThreshold * avg) return;
+  __shared__ long long s_row;
+  __shared__ int s_donor;
+  if (threadIdx.x == 0) {
+    long long row = -1;
+    int donor = -1;
+    // rejection-sample a row of a cluster with >= average size (such clusters hold most rows)
+    for (int attempt = 0; attempt < 4096; ++attempt) {
+      const long long r = static_cast<long long>(
+          mix64(seed ^ (0xA5ull * (c + 1)) ^ (0x9E3779B9ull * attempt)) % static_cast<uint64_t>(n));
+      const int l = labels[r];
+      if (l >= 0 && static_cast<float>(counts[l]) >= avg) { row = r; donor = l; break; }
     }
-  const double avg = static_cast<double>(n) / ncl;
-  // #small = clusters below 0.5 avg (a prefix of the order), #big = clusters above 1.5 avg (a suffix)
-  int my_small = 0, my_big = 0;
-  for (int i = t; i < ncl; i += kBalanceThreads) {
-    const int c = static_cast<int>(order[i] >> 32);
-    my_small += (c < 0.5 * avg) ? 1 : 0;
-    my_big += (c > 1.5 * avg) ? 1 : 0;
-  }
-  if (my_small) atomicAdd(&s_small, my_small);
-  if (my_big) atomicAdd(&s_big, my_big);
-  __syncthreads();
-  const int n_small = s_small, n_big = s_big;
-  if (n_small == 0 || n_big == 0) return;
-  // exclusive prefix of the quotas of big clusters j = 0 .. n_big-1 (j-th largest)
-  const int per = (n_big + kBalanceThreads - 1) / kBalanceThreads;
-  const int j0 = min(n_big, t * per), j1 = min(n_big, j0 + per);
-  int sum = 0;
-  for (int j = j0; j < j1; ++j) {
-    const int c = static_cast<int>(order[ncl - 1 - j] >> 32);
-    int quota = static_cast<int>(c / avg) - 1;
-    sum += quota < 1 ? 1 : quota;
-  }
-  part[t] = sum;
-  __syncthreads();
-  if (t == 0) {
-    int run = 0;
-    for (int i = 0; i < kBalanceThreads; ++i) { const int v = part[i]; part[i] = run; run += v; }
-    qprefix[n_big] = run;
+    s_row = row;
+    s_donor = donor;
   }
   __syncthreads();
-  int run = part[t];
-  for (int j = j0; j < j1; ++j) {
-    qprefix[j] = run;
-    const int c = static_cast<int>(order[ncl - 1 - j] >> 32);
-    int quota = static_cast<int>(c / avg) - 1;
-    run += quota < 1 ? 1 : quota;
-  }
-  __syncthreads();
-  for (int s = t; s < n_small; s += kBalanceThreads) {
-    // big cluster whose quota range holds sorted position s: last j with qprefix[j] <= s
-    int lo = 0, hi = n_big;   // qprefix[0] = 0 <= s
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (qprefix[mid] <= s) lo = mid; else hi = mid;
-    }
-    const int j = lo;
-    if (s < qprefix[j + 1] && s < ncl - 1 - j)
-      donor_of[static_cast<uint32_t>(order[s])] = static_cast<int>(static_cast<uint32_t>(order[ncl - 1 - j]));
-  }
+  const long long row = s_row;
+  const int l = s_donor;
+  if (row < 0 || l == c) return;
+  const float wc = fminf(static_cast<float>(counts[l]), kAdjustWeight);
+  const float inv = 1.f / (wc + 1.f);
+  for (int j = threadIdx.x; j < dim; j += blockDim.x)
+    cent[static_cast<size_t>(c) * dim + j] =
+        (wc * cent[static_cast<size_t>(l) * dim + j] + ld_f32<T>(x + row * dim + j)) * inv;
 }
 
 int kmeans_fit_impl(int dev, int dtype, int dim, const void* x, int64_t n, int ncl, int iters,
@@ -257,10 +165,9 @@ int kmeans_fit_impl(int dev, int dtype, int dim, const void* x, int64_t n, int n
   B2VS_CHECK(n < (1ll << 31), B2VS_EINVAL, "k-means input too large (n=%lld)", static_cast<long long>(n));
   KmWorkspace local_ws;
   KmWorkspace& w = shared_ws ? *shared_ws : local_ws;
-  DevBuf &sums = w.sums, &counts = w.counts, &labels = w.labels, &donors = w.donors,
+  DevBuf &sums = w.sums, &counts = w.counts, &labels = w.labels,
          &seg_off = w.seg_off, &seg_cur = w.seg_cur, &seg_rows = w.seg_rows, &seg_slot = w.seg_slot;
   FlatEngine& eng = w.eng;
-  std::vector<int> h_counts, h_donor;
   int rc = B2VS_OK;
   auto cleanup = [&]() {
     if (!shared_ws) local_ws.release();   // a shared workspace is released by its owner
@@ -269,17 +176,10 @@ int kmeans_fit_impl(int dev, int dtype, int dim, const void* x, int64_t n, int n
 #define KM_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); cleanup(); return B2VS_ECUDA; } } while (0)
   KM_TRY(sums.reserve(static_cast<size_t>(ncl) * dim * sizeof(float)));
   KM_TRY(counts.reserve(static_cast<size_t>(ncl) * sizeof(int)));
-  KM_TRY(donors.reserve(static_cast<size_t>(ncl) * sizeof(int)));
   KM_TRY(seg_off.reserve(static_cast<size_t>(ncl + 1) * sizeof(uint32_t)));
   KM_TRY(seg_cur.reserve(static_cast<size_t>(ncl) * sizeof(int)));
   KM_TRY(seg_rows.reserve(static_cast<size_t>(n) * sizeof(uint32_t)));
   KM_TRY(seg_slot.reserve(static_cast<size_t>(n) * sizeof(uint32_t)));
-  {
-    size_t p2 = 1;
-    while (p2 < static_cast<size_t>(ncl)) p2 <<= 1;
-    KM_TRY(w.order.reserve(p2 * sizeof(u64)));
-    KM_TRY(w.donor_scratch.reserve((static_cast<size_t>(ncl) + 1) * sizeof(int)));
-  }
   int32_t* lab = labels_out;
   if (!lab) {
     KM_TRY(labels.reserve(static_cast<size_t>(n) * sizeof(int32_t)));
@@ -309,28 +209,14 @@ int kmeans_fit_impl(int dev, int dtype, int dim, const void* x, int64_t n, int n
                                    seg_rows.as<uint32_t>(), dim, sums.as<float>())));
     }
     KM_CUDA(cudaGetLastError());
-    const int* donor_ptr = nullptr;
-    if (it + 2 < iters && ncl > 1) {  // the last two iterations are plain Lloyd
-      if (ncl <= kBalanceMaxClusters) {
-        balance_pairs_kernel<<<1, kBalanceThreads, 0, st>>>(counts.as<int>(), ncl, static_cast<long long>(n),
-                                                           w.order.as<u64>(), w.donor_scratch.as<int>(),
-                                                           donors.as<int>());
-        KM_CUDA(cudaGetLastError());
-      } else {
-        h_counts.resize(ncl);
-        KM_CUDA(cudaMemcpyAsync(h_counts.data(), counts.ptr, static_cast<size_t>(ncl) * sizeof(int),
-                                cudaMemcpyDeviceToHost, st));
-        KM_CUDA(cudaStreamSynchronize(st));
-        balance_pairs(h_counts, n, &h_donor);
-        KM_CUDA(cudaMemcpyAsync(donors.ptr, h_donor.data(), static_cast<size_t>(ncl) * sizeof(int),
-                                cudaMemcpyHostToDevice, st));
-      }
-      donor_ptr = donors.as<int>();
-    }
-    DISPATCH_DTYPE(dtype, T, (finalize_centroids_kernel<T><<<ncl, 128, 0, st>>>(
-                                 static_cast<const T*>(x), lab, n, dim, sums.as<float>(),
-                                 counts.as<int>(), donor_ptr, seed + 977ull * (it + 1), cent)));
+    finalize_centroids_kernel<<<ncl, 128, 0, st>>>(dim, sums.as<float>(), counts.as<int>(), cent);
     KM_CUDA(cudaGetLastError());
+    if (it + 1 < iters && ncl > 1) {   // every iteration but the last ends with an M step only
+      DISPATCH_DTYPE(dtype, T, (adjust_centers_kernel<T><<<ncl, 128, 0, st>>>(
+                                   static_cast<const T*>(x), lab, n, dim, ncl, counts.as<int>(),
+                                   seed + 977ull * (it + 1), cent)));
+      KM_CUDA(cudaGetLastError());
+    }
   }
   if (labels_out) {
     KM_TRY(eng.init(dev, B2VS_METRIC_L2, B2VS_F32, dim, cent, ncl, st, force));

@@ -37,10 +37,10 @@ int launch_pq_grouped_scan(int dev, const PqGroupedScanArgs& a, cudaStream_t st)
   p.work = static_cast<const int4*>(a.work);
   p.n_work = a.n_work;
   p.row_query = a.row_query;
-  pp.codes4 = static_cast<const uint4*>(a.codes);
-  pp.cb16 = static_cast<const uint32_t*>(a.cb16);
+  pp.codes = static_cast<const uint8_t*>(a.codes);
+  pp.cb16 = static_cast<const uint32_t*>(a.cb16t);
   pp.row_bias = a.row_bias;
-  pp.n_code_chunks = a.pq_dim / 16;
+  pp.mp = a.pq_dim;
   pp.n_groups = a.n_groups;
   pp.cb_words = a.pq_dim * 256 * a.dsub / 2;
   const int grid = std::max(1, std::min(a.max_work, sm_count(dev)));

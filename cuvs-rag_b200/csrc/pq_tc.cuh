@@ -10,7 +10,9 @@
 // are grouped by list (ivf.cu) and each list is DECODED ONCE per batch into a bf16 K-major tile
 // in shared memory — by four decoder warps, straight into the 128-byte-swizzled layout the UMMA
 // descriptors expect — and multiplied against the 128-row block of residual queries that probe
-// the list.  The smem look-ups per row drop from (queries probing the list) x pq_dim to pq_dim.
+// the list.  The smem look-ups per row drop from (queries probing the list) x pq_dim to pq_dim,
+// and with lanes walking the sub-spaces of a row over a code-major codebook copy every look-up
+// and every store instruction is bank-conflict free (see the decoder role below).
 //
 // Same skeleton as bf_tc_kernel<1, true> (work-table + append mode): warp 0 = TMA producer (query
 // k-blocks + the tile's ||r^||^2 vector), warp 1 = MMA issuer, warp 2 = TMEM allocator,
@@ -33,11 +35,11 @@ static_assert(kBK == 64, "the decoder writes 128-byte swizzled rows");
 
 struct PqTcParams {
   BfTcParams tc;            // work table, thresholds, append buffers (see bf_tc.cuh, work mode)
-  const uint4* codes4;      // PQ codes, 32-row groups interleaved by 16-byte chunks
-  const uint32_t* cb16;     // bf16 codebooks [pq_dim][256][DSUB] viewed as 32-bit words
+  const uint8_t* codes;     // PQ codes [n_groups][mp][32]: 32-row groups, sub-space major inside a group
+  const uint32_t* cb16;     // bf16 codebooks, CODE-major [256][pq_dim][DSUB], viewed as 32-bit words
   const float* row_bias;    // [query rows] ||rq||^2 (L2) or -q.c_l (IP) of each gathered row
-  int n_code_chunks;        // 16-byte code chunks per row (pq_dim / 16)
-  uint32_t n_groups;        // 32-row groups in `codes4`
+  int mp;                   // sub-spaces per row as stored (= pq_dim: the grouped scan needs pq_dim % 16 == 0)
+  uint32_t n_groups;        // 32-row groups in `codes`
   int cb_words;             // pq_dim * 256 * DSUB / 2
 };
 
@@ -166,96 +168,107 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
     }
   } else if (warp >= 8 && warp < 12) {
     // ------------------------------------------------------------------ decoders
-    // A stage's list k-block = 256 rows x 64 dims = 64 / DSUB codes per row.  Work unit of a lane:
-    // one 16-byte code chunk of one row (coalesced across the warp by the interleaved layout)
-    // -> 16 codebook look-ups -> 16 * DSUB bf16 values = (DSUB * 2) 16-byte stores into the
-    // row's 128-byte swizzled line: chunk c of row r lives at (r/8)*1024 + (r%8)*128 + ((c^(r%8))*16).
+    // A stage's list k-block = 256 rows x 64 dims = LPR = 64 / DSUB sub-spaces per row.  LANES WALK
+    // THE SUB-SPACES of one list row (DSUB 2: 32 lanes = one row per instruction; DSUB 4 / 8: two /
+    // four rows per instruction), so with the code-major codebook copy cb16t[code][sub-space]
+    //  * a look-up instruction touches 32 consecutive banks whatever the codes are (the row-per-lane
+    //    layout of round 1 hit ~3.5-way bank conflicts on its random 4-byte reads), and
+    //  * the decoded pieces of one instruction fill whole 128-byte swizzled row lines: the stores
+    //    are conflict-free too.
+    // Codes are stored sub-space major inside 32-row groups (pq_code_offset), so the 32 codes a
+    // lane needs for one (group, k-block) unit are ONE 32-byte piece; the pieces of the k-blocks two
+    // steps ahead are already in flight while a k-block is decoded (prefetch distance 2: the
+    // exposed global-load latency of the decoders was the kernel's top stall).
     const int dw = warp - 8;
-    // code chunks per k-block: 2 (DSUB 2) | 1 (DSUB 4) | half a chunk (DSUB 8: k-block kb uses
-    // bytes [8*(kb&1), +8) of chunk kb/2)
-    constexpr int kChunksPerKb = (DSUB == 2) ? 2 : 1;
-    constexpr int kPairs = 8 * kChunksPerKb;                                     // (group, chunk) pairs per stage
-    uint32_t stage = 0, phase = 0;
-    for (int item = unit; item < n_items; item += n_units) {
-      const int4 w = __ldg(p.work + item);
-      const int t1 = (w.z - w.y + kBN - 1) / kBN;
-      for (int ti = 0; ti < t1; ++ti) {
-        const uint32_t g_tile0 = (static_cast<uint32_t>(w.y) >> 5) + static_cast<uint32_t>(ti) * 8u;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          // issue this warp's code loads before waiting for the smem slot
-          uint4 cv[kPairs / 4];
+    constexpr int LPR = 64 / DSUB;     // lanes per list row
+    constexpr int RPI = 32 / LPR;      // list rows per warp instruction
+    constexpr int WPC = DSUB / 2;      // 32-bit words per codebook entry
+    const int sub = lane % LPR;
+    const int rph = lane / LPR;
+    const uint32_t wps = static_cast<uint32_t>(pp.mp) * WPC;        // words per code value in cb16t
+    const uint32_t piece = static_cast<uint32_t>(sub) * WPC * 4u;   // lane's byte offset in a row line
+    const uint32_t pc = piece >> 4, pw = piece & 15u;
+    struct KbIter { int item, ti, t1, kb; uint32_t g0; };
+    auto seek = [&](KbIter& it, int item) {   // first k-block of the first non-empty item >= item
+      it.ti = 0; it.kb = 0; it.t1 = 0; it.g0 = 0;
+      while (item < n_items) {
+        const int4 w = __ldg(p.work + item);
+        it.t1 = (w.z - w.y + kBN - 1) / kBN;
+        it.g0 = static_cast<uint32_t>(w.y) >> 5;
+        if (it.t1 > 0) break;
+        item += n_units;
+      }
+      it.item = item;
+    };
+    auto step = [&](KbIter& it) {
+      if (++it.kb == p.k_blocks) {
+        it.kb = 0;
+        if (++it.ti == it.t1) seek(it, it.item + n_units);
+      }
+    };
+    // the two 32-byte code pieces (units = groups 2*dw, 2*dw + 1 of the tile) of k-block `it`
+    auto fetch = [&](const KbIter& it, uint4 (&cv)[2][2]) {
 #pragma unroll
-          for (int u = 0; u < kPairs / 4; ++u) {
-            const int pi = dw * (kPairs / 4) + u;
-            const uint32_t g = g_tile0 + static_cast<uint32_t>(pi / kChunksPerKb);
-            const int ch = (DSUB == 8) ? (kb >> 1) : kb * kChunksPerKb + (pi % kChunksPerKb);
-            cv[u] = make_uint4(0, 0, 0, 0);
-            if (g < pp.n_groups)
-              cv[u] = __ldg(pp.codes4 + (static_cast<size_t>(g) * pp.n_code_chunks + ch) * 32 + lane);
-          }
-          ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-          const uint32_t b_base = smem_base + stage * kStageBytes + kABytes;
-#pragma unroll
-          for (int u = 0; u < kPairs / 4; ++u) {
-            const int pi = dw * (kPairs / 4) + u;
-            const int gl = pi / kChunksPerKb;
-            const int chl = pi % kChunksPerKb;                  // chunk within the k-block
-            const int ch = (DSUB == 8) ? (kb >> 1) : kb * kChunksPerKb + chl;
-            const uint32_t r = static_cast<uint32_t>(gl) * 32u + lane;
-            const uint32_t line = b_base + (r >> 3) * 1024u + (r & 7u) * 128u;
-            const uint32_t wv[4] = {cv[u].x, cv[u].y, cv[u].z, cv[u].w};
-            if (DSUB == 2) {
-              // 16 codes -> 32 dims -> 4 output chunks; output chunk index = chl*4 + oc
-#pragma unroll
-              for (int oc = 0; oc < 4; ++oc) {
-                uint32_t o[4];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                  const int m = ch * 16 + oc * 4 + b;
-                  o[b] = cb_w[m * 256 + ((wv[oc] >> (8 * b)) & 0xFFu)];
-                }
-                const uint32_t c = static_cast<uint32_t>(chl * 4 + oc);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(line + ((c ^ (r & 7u)) << 4)),
-                             "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-              }
-            } else if (DSUB == 8) {
-              // this k-block's 8 codes (half of the chunk) -> 64 dims -> the row's 8 output chunks
-              const uint4* cb4 = reinterpret_cast<const uint4*>(cb_w);
-              const int h = kb & 1;
-              uint4 e[8];
-#pragma unroll
-              for (int oc = 0; oc < 8; ++oc) {
-                const int m = ch * 16 + h * 8 + oc;
-                e[oc] = cb4[m * 256 + ((wv[2 * h + (oc >> 2)] >> (8 * (oc & 3))) & 0xFFu)];
-              }
-#pragma unroll
-              for (int oc = 0; oc < 8; ++oc) {
-                const uint32_t c = static_cast<uint32_t>(oc);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(line + ((c ^ (r & 7u)) << 4)),
-                             "r"(e[oc].x), "r"(e[oc].y), "r"(e[oc].z), "r"(e[oc].w) : "memory");
-              }
-            } else {
-              // 16 codes -> 64 dims -> the row's 8 output chunks
-              const uint2* cb2 = reinterpret_cast<const uint2*>(cb_w);
-#pragma unroll
-              for (int oc = 0; oc < 8; ++oc) {
-                const int i0 = oc * 2;
-                const int m0 = ch * 16 + i0;
-                const uint2 a = cb2[m0 * 256 + ((wv[i0 >> 2] >> (8 * (i0 & 3))) & 0xFFu)];
-                const uint2 b = cb2[(m0 + 1) * 256 + ((wv[(i0 + 1) >> 2] >> (8 * ((i0 + 1) & 3))) & 0xFFu)];
-                const uint32_t c = static_cast<uint32_t>(oc);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(line + ((c ^ (r & 7u)) << 4)),
-                             "r"(a.x), "r"(a.y), "r"(b.x), "r"(b.y) : "memory");
-              }
-            }
-          }
-          // generic-proxy writes -> visible to the tensor core's async-proxy reads
-          ptx::fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar_full + 8 * stage);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      for (int u = 0; u < 2; ++u) {
+        cv[u][0] = make_uint4(0, 0, 0, 0);
+        cv[u][1] = make_uint4(0, 0, 0, 0);
+        const uint32_t g = it.g0 + static_cast<uint32_t>(it.ti) * 8u + static_cast<uint32_t>(2 * dw + u);
+        if (it.item < n_items && g < pp.n_groups) {
+          const uint4* src = reinterpret_cast<const uint4*>(
+              pp.codes + (static_cast<size_t>(g) * pp.mp + static_cast<size_t>(it.kb * LPR + sub)) * 32);
+          cv[u][0] = __ldg(src);
+          cv[u][1] = __ldg(src + 1);
         }
       }
+    };
+    KbIter cur, pre;
+    seek(cur, unit);
+    pre = cur;
+    uint4 cv0[2][2], cv1[2][2], cv2[2][2];
+    fetch(pre, cv0); step(pre);
+    fetch(pre, cv1); step(pre);
+    uint32_t stage = 0, phase = 0;
+    while (cur.item < n_items) {
+      fetch(pre, cv2); step(pre);
+      ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+      const uint32_t b_base = smem_base + stage * kStageBytes + kABytes;
+      const uint32_t* cb_kb = cb_w + static_cast<uint32_t>(cur.kb * LPR + sub) * WPC;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const uint32_t w8[8] = {cv0[u][0].x, cv0[u][0].y, cv0[u][0].z, cv0[u][0].w,
+                                cv0[u][1].x, cv0[u][1].y, cv0[u][1].z, cv0[u][1].w};
+        const uint32_t unit_base = b_base + static_cast<uint32_t>(2 * dw + u) * 4096u;   // 32 rows x 128 B
+#pragma unroll
+        for (int r = 0; r < 32; r += RPI) {
+          const uint32_t rr = static_cast<uint32_t>(r) + static_cast<uint32_t>(rph);     // row in the group
+          const uint32_t code = (w8[r >> 2] >> (8u * ((r & 3) + rph))) & 0xFFu;
+          const uint32_t* src = cb_kb + code * wps;
+          const uint32_t swz = rr & 7u;
+          const uint32_t dst = unit_base + (rr >> 3) * 1024u + swz * 128u + (((pc ^ swz) << 4) | pw);
+          if (WPC == 1) {
+            const uint32_t v = src[0];
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(v) : "memory");
+          } else if (WPC == 2) {
+            const uint2 v = *reinterpret_cast<const uint2*>(src);
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(v.x), "r"(v.y) : "memory");
+          } else {
+            const uint4 v = *reinterpret_cast<const uint4*>(src);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z),
+                         "r"(v.w) : "memory");
+          }
+        }
+      }
+      // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_full + 8 * stage);
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        cv0[u][0] = cv1[u][0]; cv0[u][1] = cv1[u][1];
+        cv1[u][0] = cv2[u][0]; cv1[u][1] = cv2[u][1];
+      }
+      step(cur);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (append mode)

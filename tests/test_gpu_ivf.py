@@ -456,3 +456,34 @@ def test_tiny_batch_coarse_probe_scan_equals_tensor_core_probe(b2, setenv, kind,
             setenv("B2VS_COARSE_SCAN", None)
             _, j1 = ix.search(qf, 10, n_probes=nlist)
             assert torch.equal(j0, j1)
+
+
+@pytest.mark.parametrize("kind", ["ivf_flat", "ivf_pq"])
+def test_grouped_scan_seed_modes_agree_on_structureless_data(b2, setenv, kind):
+    """Thresholds of the grouped scans come from the CUDA-core seed kernels (B2VS_IVF_SEED=0, small
+    batches) or from a tensor-core seed pass over the heads of the nearest lists (=1, default from
+    256 queries): on iid Gaussian rows - where the nearest list's head is a weak bound - both must
+    give what the per-(query, probe) scan gives, the second without flooding the buffers."""
+    g = torch.Generator().manual_seed(61)
+    n, d, nlist, nprobe, nq, k = 60000, 128, 128, 32, 300, 10
+    x = torch.randn(n, d, generator=g).to(torch.float16)
+    q = torch.randn(nq, d, generator=g).to(torch.float16)
+    if kind == "ivf_flat":
+        ix = b2.NativeIndex.ivf_flat(x.cuda(), nlist, kmeans_iters=6)
+        kw = {}
+    else:
+        ix = b2.NativeIndex.ivf_pq(x.cuda(), nlist, 64, kmeans_iters=6)
+        kw = {"refine_ratio": 4}
+    setenv("B2VS_IVF_GROUPED", "0")
+    _, i_ref = ix.search(q.cuda(), k, n_probes=nprobe, **kw)
+    setenv("B2VS_IVF_GROUPED", "1")
+    cands = {}
+    for seed in ("0", "1"):
+        setenv("B2VS_IVF_SEED", seed)
+        _, ii = ix.search(q.cuda(), k, n_probes=nprobe, **kw)
+        torch.cuda.synchronize()
+        cands[seed] = ix.last_stats().mean_candidates
+        inter = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(ii.cpu(), i_ref.cpu()))
+        assert inter >= (0.999 if kind == "ivf_flat" else 0.97) * nq * k, (seed, inter / (nq * k))
+    # the larger, tensor-core sample gives the tighter threshold
+    assert 0 < cands["1"] < cands["0"], cands
