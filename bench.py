@@ -64,7 +64,7 @@ def parse_args():
                     help="sub-records to run after the headline (comma list of C1,C3,C4,C5; 'none')")
     ap.add_argument("--scale", type=float, default=1.0,
                     help="row-count multiplier of the sub-record corpora (bring-up; 1.0 = BASELINE sizes)")
-    ap.add_argument("--ivf-latent-dim", type=int, default=32,
+    ap.add_argument("--ivf-latent-dim", type=int, default=16,
                     help="intrinsic dimension of the IVF corpora (see ivf_corpus)")
     return ap.parse_args()
 
