@@ -57,13 +57,20 @@ constexpr int kEpiGroups = B2VS_EPI_GROUPS;
 static_assert(kEpiGroups == 1 || kEpiGroups == 2, "kEpiGroups");
 constexpr int kTcThreads = 128 + 128 * kEpiGroups;
 
+// Work-table (grouped scan) epilogue: hits are staged in a small per-warp shared-memory queue and
+// appended to the queries' global buffers in batches (one atomic round trip per batch instead of
+// one per 32-column chunk on the epilogue's critical path).
+constexpr int kQueueCap = 96;                                 // entries per epilogue warp
+constexpr int kQueueWarpBytes = kQueueCap * (8 + 4);          // keys (u64) + query slots (int)
+constexpr int kQueueBytes = 4 * kEpiGroups * kQueueWarpBytes;
+
 template <int G> struct TcCfg {
   static constexpr int kBRows = kBN / G;                     // db rows staged by one CTA
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kBK == 64) ? ((G == 1) ? 4 : 6) : ((G == 1) ? 9 : 13);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kNormBytes + 256 + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kNormBytes + 256 + kQueueBytes + 1024;
 };
 
 struct BfTcParams {
@@ -96,7 +103,13 @@ struct BfTcParams {
   const int* row_query; // [query rows]
   int x_kblocks;        // > 0: the query operand is [hi | lo] (2*x_kblocks k-blocks) against the SAME
                         // x_kblocks db k-blocks (fp32 queries split into two bf16 halves)
+  // seed pass of the grouped scans (work mode): every score of the item's (single) tile is stored
+  // at a FIXED place - big_cand[query][row_slot[row] * kSeedSlotRows + column] - no threshold, no
+  // atomics; the caller pre-fills the buffers with kKeyInf
+  int seed_all;
+  const int* row_slot;  // [query rows] which of the query's seed lists this gathered row probes
 };
+constexpr int kSeedSlotRows = 256;   // = one tile: the seed pass scores the first tile of a list
 
 constexpr bool kWorkNoHint = false;   // A/B switch for the evict-first hint of work-mode list tiles
 constexpr int kModeBuffer = 0;   // per-(CTA,row) candidate buffer + warp compaction (k <= 128)
@@ -187,6 +200,107 @@ __device__ __forceinline__ void compact_if_needed(int& cnt, float& tau, u64* can
   }
 }
 
+struct HitQueue {
+  u64* keys;    // [kQueueCap] shared memory, private to one epilogue warp
+  int* slots;   // [kQueueCap] query slot of each key
+  int n;        // fill level (warp-uniform register)
+};
+
+// Appends the queued hits to their queries' global buffers: every lane takes entries, so the
+// atomics of up to 32 entries are in flight together.  Warp-collective.
+__device__ __forceinline__ void queue_drain(HitQueue& hq, u64* __restrict__ cand, int* __restrict__ count,
+                                            int cap, int lane) {
+  __syncwarp();
+  for (int e = lane; e < hq.n; e += 32) {
+    const u64 key = hq.keys[e];
+    const int s = hq.slots[e];
+    const int pos = atomicAdd(count + s, 1);
+    if (pos < cap) __stcg(cand + static_cast<size_t>(s) * cap + pos, key);
+  }
+  __syncwarp();
+  hq.n = 0;
+}
+
+// Work-table epilogue: scores one 32-column chunk of the warp's 32 query rows and queues every
+// score below its row's threshold.  Warp-collective (all lanes call it for the same chunk): the
+// queue positions come from a warp prefix sum of the per-lane hit counts, no atomics.
+__device__ __forceinline__ void score_chunk_queue(const uint32_t (&r)[32], const float4* __restrict__ nrm4,
+                                                  float alpha, uint32_t col, float tau, float bias, int qslot,
+                                                  HitQueue& hq, u64* __restrict__ cand,
+                                                  int* __restrict__ count, int cap, int lane) {
+  float sc[32];
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 nb = nrm4[j4];
+    sc[4 * j4 + 0] = fmaf(alpha, __uint_as_float(r[4 * j4 + 0]), nb.x);
+    sc[4 * j4 + 1] = fmaf(alpha, __uint_as_float(r[4 * j4 + 1]), nb.y);
+    sc[4 * j4 + 2] = fmaf(alpha, __uint_as_float(r[4 * j4 + 2]), nb.z);
+    sc[4 * j4 + 3] = fmaf(alpha, __uint_as_float(r[4 * j4 + 3]), nb.w);
+  }
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    m[i] = fminf(fminf(sc[4 * i], sc[4 * i + 1]), fminf(sc[4 * i + 2], sc[4 * i + 3]));
+  const float mn = fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])),
+                         fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
+  if (!__any_sync(0xffffffffu, mn < tau)) return;      // the common case: nothing in this chunk
+  uint32_t mask = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) mask |= (sc[j] < tau) ? (1u << j) : 0u;
+  const int nh = __popc(mask);
+  int inc = nh;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, inc, 31);
+  const bool direct = total > kQueueCap;               // a flood (loose threshold): straight to global
+  if (!direct && hq.n + total > kQueueCap) queue_drain(hq, cand, count, cap, lane);
+  int pos = direct ? (nh ? atomicAdd(count + qslot, nh) : 0) : hq.n + inc - nh;
+  u64* const row_buf = cand + static_cast<size_t>(qslot) * cap;
+  while (mask) {
+    const int j = __ffs(mask) - 1;
+    mask &= mask - 1;
+    float v16[16], v8[8], v4[4], v2[2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v16[i] = (j & 1) ? sc[2 * i + 1] : sc[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v8[i] = (j & 2) ? v16[2 * i + 1] : v16[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v4[i] = (j & 4) ? v8[2 * i + 1] : v8[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) v2[i] = (j & 8) ? v4[2 * i + 1] : v4[2 * i];
+    const float v = (j & 16) ? v2[1] : v2[0];
+    const u64 key = pack_key(v + bias, col + j);
+    if (direct) {
+      if (pos < cap) __stcg(row_buf + pos, key);
+    } else {
+      hq.keys[pos] = key;
+      hq.slots[pos] = qslot;
+    }
+    ++pos;
+  }
+  if (!direct) hq.n += total;
+}
+
+// Seed pass: all 32 scores of the chunk go to their fixed places (dst = the row's slot + column).
+__device__ __forceinline__ void score_chunk_seed(const uint32_t (&r)[32], const float4* __restrict__ nrm4,
+                                                 float alpha, uint32_t col, float bias,
+                                                 u64* __restrict__ dst) {
+  ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst);
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 nb = nrm4[j4];
+    const u64 k0 = pack_key(fmaf(alpha, __uint_as_float(r[4 * j4 + 0]), nb.x) + bias, col + 4 * j4 + 0);
+    const u64 k1 = pack_key(fmaf(alpha, __uint_as_float(r[4 * j4 + 1]), nb.y) + bias, col + 4 * j4 + 1);
+    const u64 k2 = pack_key(fmaf(alpha, __uint_as_float(r[4 * j4 + 2]), nb.z) + bias, col + 4 * j4 + 2);
+    const u64 k3 = pack_key(fmaf(alpha, __uint_as_float(r[4 * j4 + 3]), nb.w) + bias, col + 4 * j4 + 3);
+    __stcg(d2 + 2 * j4, make_ulonglong2(k0, k1));
+    __stcg(d2 + 2 * j4 + 1, make_ulonglong2(k2, k3));
+  }
+}
+
 template <int G, bool kWork = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
@@ -213,6 +327,8 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
   const uint32_t tmem_slot = bar_acc_full + 64;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
       smem + kStages * kStageBytes + 2 * kNormBytes + 16 * kStages + 64);
+
+  uint8_t* const queue_mem = smem + kStages * kStageBytes + 2 * kNormBytes + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -373,6 +489,10 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     const float inf = __int_as_float(0x7f800000);
     uint32_t tcount = 0;
     const int n_items = kWork ? *p.n_work : p.n_items;
+    HitQueue hq;
+    hq.keys = reinterpret_cast<u64*>(queue_mem + (warp - 4) * kQueueWarpBytes);
+    hq.slots = reinterpret_cast<int*>(queue_mem + (warp - 4) * kQueueWarpBytes + kQueueCap * 8);
+    hq.n = 0;
     for (int item = unit; item < n_items; item += n_units) {
       int qb, s = 0, t0, t1, row_begin = 0, row_end = 0;
       if (kWork) {
@@ -386,9 +506,13 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       }
       size_t q_row = static_cast<size_t>(qb) * (kBM * G) + cta_rank * kBM + ew * 32 + lane;
       float tau = inf;
+      int seed_slot = 0;
+      bool real_row = true;
       if (kWork) {
         const int query = __ldg(p.row_query + q_row);
+        if (p.seed_all) seed_slot = __ldg(p.row_slot + q_row);
         tau = query >= 0 ? p.tau_init[query] : -inf;   // padding rows never qualify
+        real_row = query >= 0;
         q_row = static_cast<size_t>(max(query, 0));
       } else if (q_row >= static_cast<size_t>(p.nq)) {
         tau = -inf;            // padding row of the last query block: stays empty, costs nothing
@@ -422,9 +546,16 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
           ptx::tmem_ld_wait();
           ptx::tmem_ld_32x32b_x32(tile_taddr + c2 * 64 + 32, rb);
           if (kWork) {
-            if (c2 * 64 < nv)
-              score_chunk<kModeAppend>(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, cnt, best,
-                                       row_buf, row_cnt, p.big_cap);
+            if (c2 * 64 < nv) {
+              if (p.seed_all) {
+                if (real_row)
+                  score_chunk_seed(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, 0.f,
+                                   row_buf + seed_slot * kSeedSlotRows + (ti * kBN + c2 * 64));
+              } else {
+                score_chunk_queue(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, 0.f,
+                                  static_cast<int>(q_row), hq, p.big_cand, p.big_count, p.big_cap, lane);
+              }
+            }
           } else if (mode == kModeArgmin)
             score_chunk<kModeArgmin>(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, cnt, best, row_buf);
           else if (mode == kModeAppend)
@@ -446,9 +577,16 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
             }
           }
           if (kWork) {
-            if (c2 * 64 + 32 < nv)
-              score_chunk<kModeAppend>(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, cnt,
-                                       best, row_buf, row_cnt, p.big_cap);
+            if (c2 * 64 + 32 < nv) {
+              if (p.seed_all) {
+                if (real_row)
+                  score_chunk_seed(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, 0.f,
+                                   row_buf + seed_slot * kSeedSlotRows + (ti * kBN + c2 * 64 + 32));
+              } else {
+                score_chunk_queue(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, 0.f,
+                                  static_cast<int>(q_row), hq, p.big_cand, p.big_count, p.big_cap, lane);
+              }
+            }
           } else if (mode == kModeArgmin)
             score_chunk<kModeArgmin>(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, cnt, best, row_buf);
           else if (mode == kModeAppend)
@@ -463,7 +601,7 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
           if (mode == kModeBuffer) compact_if_needed(cnt, tau, cand_warp, p.k, lane);
         }
       }
-      if (mode == kModeAppend) continue;  // candidates already sit in the query's global buffer
+      if (mode == kModeAppend) continue;  // candidates sit in the query's global buffer / the warp's queue
       // ---- item done: emit this (split, query block)'s sorted top-k keys
       const size_t q_row0 = static_cast<size_t>(qb) * (kBM * G) + cta_rank * kBM + ew * 32;
       u64* out_blk = p.out_keys + ((static_cast<size_t>(s) * kEpiGroups + eg) * p.q_pad + q_row0) * p.k;
@@ -480,6 +618,7 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         __syncwarp();
       }
     }
+    if (kWork) queue_drain(hq, p.big_cand, p.big_count, p.big_cap, lane);
   }
 
   __syncwarp();  // role branches above are per-lane: reconverge before the aligned barrier

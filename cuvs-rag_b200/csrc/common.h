@@ -197,6 +197,8 @@ struct GroupedScanArgs {
   u64* cand;              // [nq][cap]
   int* count;             // [nq]
   int cap;
+  const int* row_slot;    // seed pass (seed_all): which seed list of its query a gathered row probes
+  int seed_all;           // 1: every score of the (single-tile) items goes to its fixed slot
 };
 int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st);
 
@@ -219,6 +221,8 @@ struct PqGroupedScanArgs {
   u64* cand;
   int* count;
   int cap;
+  const int* row_slot;    // seed pass, as in GroupedScanArgs
+  int seed_all;
 };
 bool pq_grouped_supported(int dim, int dsub);
 int launch_pq_grouped_scan(int dev, const PqGroupedScanArgs& a, cudaStream_t st);

@@ -485,6 +485,8 @@ int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st) {
   p.work = static_cast<const int4*>(a.work);
   p.n_work = a.n_work;
   p.row_query = a.row_query;
+  p.row_slot = a.row_slot;
+  p.seed_all = a.seed_all;
   const int grid = std::max(1, std::min(a.max_work, sm_count(dev)));
   B2VS_CUDA(cudaFuncSetAttribute((bf_tc_kernel<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  TcCfg<1>::kSmemBytes));

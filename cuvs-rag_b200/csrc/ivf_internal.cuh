@@ -95,6 +95,7 @@ struct IvfData {
   DevBuf ws_probe_d, ws_probe_i, ws_keys, ws_qf, ws_qnorm, ws_counter, ws_ref_d, ws_ref_i;
   DevBuf ws_item_lab, ws_item_cnt, ws_item_off, ws_item_perm, ws_item_slot;  // list-ordered scan items
   DevBuf ws_g_work, ws_g_q, ws_g_rowq, ws_g_tau, ws_g_cand, ws_g_cnt, ws_g_bias;  // grouped scan
+  DevBuf ws_g_rowslot;  // [gathered rows] probe rank of each row inside its query
   DevBuf ws_seed_ids;   // [nq, m] the nearest probes of every query (tensor-core seed pass)
   const void* src_rows = nullptr;  // IVF-PQ: the caller's [n, dim] rows, BORROWED for refine
   std::vector<int32_t> h_sizes;
@@ -131,7 +132,7 @@ struct IvfData {
                       &ws_probe_d, &ws_probe_i, &ws_keys, &ws_qf, &ws_qnorm, &ws_counter,
                       &ws_ref_d, &ws_ref_i, &ws_item_lab, &ws_item_cnt, &ws_item_off, &ws_item_perm,
                       &ws_item_slot, &ws_g_work, &ws_g_q, &ws_g_rowq, &ws_g_tau, &ws_g_cand, &ws_g_cnt,
-                      &ws_g_bias, &ws_seed_ids, &cb16, &cb16t, &cbn, &pq_norm, &cq_offsets, &cq_probe, &ws_cq_keys})
+                      &ws_g_bias, &ws_g_rowslot, &ws_seed_ids, &cb16, &cb16t, &cbn, &pq_norm, &cq_offsets, &cq_probe, &ws_cq_keys})
       b->release();
   }
 };
@@ -178,10 +179,11 @@ __host__ __device__ __forceinline__ size_t pq_code_offset(size_t slot, int m, in
 // sub-codebooks) passes the same workspace to every fit, so device memory is allocated once
 // instead of being malloc'ed and freed (= device-synchronised) per fit.
 struct KmWorkspace {
-  DevBuf sums, counts, labels, seg_off, seg_cur, seg_rows, seg_slot;
+  DevBuf sums, counts, labels, donors, seg_off, seg_cur, seg_rows, seg_slot, order, donor_scratch;
   FlatEngine eng;
   void release() {
-    for (DevBuf* b : {&sums, &counts, &labels, &seg_off, &seg_cur, &seg_rows, &seg_slot})
+    for (DevBuf* b : {&sums, &counts, &labels, &donors, &seg_off, &seg_cur, &seg_rows, &seg_slot,
+                      &order, &donor_scratch})
       b->release();
     eng.destroy();
   }
@@ -230,7 +232,7 @@ int launch_flat_rescue(const b2vs_index* index, IvfData* d, const long long* pro
                        int nq, int k, int cap, cudaStream_t st);
 int launch_group_select(IvfData* d, int nq, int cap, int k, unsigned long long* total_cand, cudaStream_t st);
 // thresholds of the full pass from the candidates the seed pass appended (k-th best per query)
-int launch_seed_select(IvfData* d, int nq, int cap, int k, cudaStream_t st);
+int launch_seed_select(IvfData* d, int nq, int n_keys, int cap, int k, cudaStream_t st);
 int launch_gather_group_queries(IvfData* d, int64_t rows_cap, int n_probes, int q_split, cudaStream_t st);
 int launch_gather_group_residuals(const b2vs_index* index, IvfData* d, int64_t rows_cap,
                                   const long long* probe_ids, int n_probes, cudaStream_t st);

@@ -260,13 +260,16 @@ __global__ void gather_group_queries_kernel(const uint32_t* __restrict__ row_ite
                                             const uint32_t* __restrict__ group_off, int n_lists,
                                             const float* __restrict__ qf, int dp, int n_probes,
                                             int fmt, int split, uint16_t* __restrict__ out,
-                                            int* __restrict__ row_query) {
+                                            int* __restrict__ row_query, int* __restrict__ row_slot) {
   const int lane = threadIdx.x & 31;
   const int64_t v = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (v >= static_cast<int64_t>(group_off[n_lists])) return;
   const uint32_t item = row_item[v];
   const int q = item == kNoRow ? -1 : static_cast<int>(item / static_cast<uint32_t>(n_probes));
-  if (lane == 0) row_query[v] = q;
+  if (lane == 0) {
+    row_query[v] = q;
+    row_slot[v] = item == kNoRow ? 0 : static_cast<int>(item % static_cast<uint32_t>(n_probes));
+  }
   if (kSkipPaddingRows && q < 0) return;   // never qualifies (threshold -inf): bytes are don't-care
   if (!split) {
     uint16_t* orow = out + static_cast<size_t>(v) * dp;
@@ -329,12 +332,12 @@ ivf_group_select_kernel(const u64* __restrict__ cand, const int* __restrict__ co
 // inclusive ulp.  One warp per query: a 128-key sorted list in registers, candidates offered 32
 // at a time and filtered by the running k-th score.
 __global__ void __launch_bounds__(128)
-ivf_seed_select_kernel(const u64* __restrict__ cand, const int* __restrict__ count, int cap, int k,
-                       int nq, float* __restrict__ tau) {
+ivf_seed_select_kernel(const u64* __restrict__ cand, int n_keys, int cap, int k, int nq,
+                       float* __restrict__ tau) {
   const int lane = threadIdx.x & 31;
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= nq) return;
-  const int n = min(count[q], cap);
+  const int n = min(n_keys, cap);   // the seed pass fills fixed slots (kKeyInf where a list is short)
   const u64* src = cand + static_cast<size_t>(q) * cap;
   WarpTopK tk;
   tk.init();
@@ -891,7 +894,7 @@ __global__ void gather_group_residuals_kernel(const uint32_t* __restrict__ row_i
                                               const float* __restrict__ qf, const float* __restrict__ cent,
                                               int dim, int dp, int n_probes, int l2,
                                               uint16_t* __restrict__ out, int* __restrict__ row_query,
-                                              float* __restrict__ row_bias) {
+                                              float* __restrict__ row_bias, int* __restrict__ row_slot) {
   const int lane = threadIdx.x & 31;
   const int64_t v = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (v >= static_cast<int64_t>(group_off[n_lists])) return;
@@ -901,10 +904,11 @@ __global__ void gather_group_residuals_kernel(const uint32_t* __restrict__ row_i
     // group padding: the row never qualifies (threshold -inf); its operand bytes are don't-care
     if (!kSkipPaddingRows)
       for (int j = lane; j < dim; j += 32) orow[j] = 0;
-    if (lane == 0) { row_query[v] = -1; row_bias[v] = 0.f; }
+    if (lane == 0) { row_query[v] = -1; row_bias[v] = 0.f; row_slot[v] = 0; }
     return;
   }
   const int q = static_cast<int>(item / static_cast<uint32_t>(n_probes));
+  if (lane == 0) row_slot[v] = static_cast<int>(item % static_cast<uint32_t>(n_probes));
   const long long list = probe_ids[item];
   const float* c = cent + static_cast<size_t>(list < 0 ? 0 : list) * dim;
   float acc = 0.f;
@@ -1048,9 +1052,9 @@ int launch_group_select(IvfData* d, int nq, int cap, int k, unsigned long long* 
   return B2VS_OK;
 }
 
-int launch_seed_select(IvfData* d, int nq, int cap, int k, cudaStream_t st) {
+int launch_seed_select(IvfData* d, int nq, int n_keys, int cap, int k, cudaStream_t st) {
   ivf_seed_select_kernel<<<static_cast<unsigned>(ceil_div(nq, 4)), 128, 0, st>>>(
-      d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), cap, k, nq, d->ws_g_tau.as<float>());
+      d->ws_g_cand.as<u64>(), n_keys, cap, k, nq, d->ws_g_tau.as<float>());
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }
@@ -1058,7 +1062,8 @@ int launch_seed_select(IvfData* d, int nq, int cap, int k, cudaStream_t st) {
 int launch_gather_group_queries(IvfData* d, int64_t rows_cap, int n_probes, int q_split, cudaStream_t st) {
   gather_group_queries_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
       d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists, d->ws_qf.as<float>(),
-      d->dp, n_probes, d->fmt, q_split, d->ws_g_q.as<uint16_t>(), d->ws_g_rowq.as<int>());
+      d->dp, n_probes, d->fmt, q_split, d->ws_g_q.as<uint16_t>(), d->ws_g_rowq.as<int>(),
+      d->ws_g_rowslot.as<int>());
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }
@@ -1069,7 +1074,7 @@ int launch_gather_group_residuals(const b2vs_index* index, IvfData* d, int64_t r
       d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists, probe_ids,
       d->ws_qf.as<float>(), d->centroids.as<float>(), index->dim, d->dp, n_probes,
       index->metric == B2VS_METRIC_L2 ? 1 : 0, d->ws_g_q.as<uint16_t>(), d->ws_g_rowq.as<int>(),
-      d->ws_g_bias.as<float>());
+      d->ws_g_bias.as<float>(), d->ws_g_rowslot.as<int>());
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }

@@ -50,6 +50,7 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
   B2VS_TRY(d->ws_g_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16));
   B2VS_TRY(d->ws_g_q.reserve(static_cast<size_t>(rows_cap) * q_pitch * 2));
   B2VS_TRY(d->ws_g_rowq.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
+  B2VS_TRY(d->ws_g_rowslot.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
   int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
   B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
                              counter, st, row_limit));
@@ -63,6 +64,7 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
   ga.work = d->ws_g_work.ptr; ga.n_work = n_work; ga.max_work = max_work;
   ga.row_query = d->ws_g_rowq.as<int>(); ga.tau = d->ws_g_tau.as<float>();
   ga.cand = d->ws_g_cand.as<u64>(); ga.count = d->ws_g_cnt.as<int>(); ga.cap = cap;
+  ga.row_slot = d->ws_g_rowslot.as<int>(); ga.seed_all = row_limit > 0 ? 1 : 0;
   if (timed) B2VS_CUDA(cudaEventRecord(d->ev0, st));
   B2VS_TRY(launch_grouped_scan(index->dev, ga, st));
   if (timed) B2VS_CUDA(cudaEventRecord(d->ev1, st));
@@ -71,8 +73,8 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
 
 // Thresholds from a tensor-core SEED PASS (batches of kTcSeedMinQueries queries and more): the
 // first kSeedTileRows rows of each query's m nearest lists are scored by the same grouped kernel
-// with no threshold (m * 256 <= cap / 4 keys per query), and the k-th best of them becomes the
-// query's threshold for the full pass.  Against the CUDA-core seed kernels (one CTA per query over
+// with no threshold - every score lands in a FIXED slot of the query's buffer (m * 256 <= cap / 4
+// keys, no atomics) - and the k-th best of them becomes the query's threshold for the full pass.  Against the CUDA-core seed kernels (one CTA per query over
 // the nearest list only) the sample is m times larger - on corpora without cluster structure the
 // nearest list's head alone leaves thousands of candidates per query, overflowing the buffers
 // into the exact rescue scan - it runs on the tensor cores, and it uses the full pass's own
@@ -80,7 +82,8 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
 static int seed_lists(int n_probes, int cap) {
   return std::max(1, std::min(n_probes, cap / 4 / kSeedTileRows));
 }
-static bool use_tc_seed(int nq) {
+static bool use_tc_seed(int nq, int cap) {
+  if (cap < 4 * kSeedTileRows) return false;   // shrunken test buffers cannot hold a seed tile
   const int m = env().seed_mode;
   return m >= 0 ? m == 1 : nq >= kTcSeedMinQueries;
 }
@@ -92,10 +95,11 @@ static int run_tc_seed(IvfData* d, const long long* probe_ids, int n_probes, int
   B2VS_CUDA(cudaMemcpy2DAsync(d->ws_seed_ids.ptr, static_cast<size_t>(m) * sizeof(int64_t), probe_ids,
                               static_cast<size_t>(n_probes) * sizeof(int64_t),
                               static_cast<size_t>(m) * sizeof(int64_t), nq, cudaMemcpyDeviceToDevice, st));
-  B2VS_TRY(launch_fill_f32(d->ws_g_tau.as<float>(), static_cast<size_t>(nq), INFINITY, st));
+  // fixed slots: [query][seed list j][row of the list's first tile]; short lists leave kKeyInf
+  B2VS_CUDA(cudaMemset2DAsync(d->ws_g_cand.ptr, static_cast<size_t>(cap) * sizeof(u64), 0xFF,
+                              static_cast<size_t>(m) * kSeedTileRows * sizeof(u64), nq, st));
   B2VS_TRY(scan(reinterpret_cast<const long long*>(d->ws_seed_ids.ptr), m));
-  B2VS_TRY(launch_seed_select(d, nq, cap, k, st));
-  B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
+  B2VS_TRY(launch_seed_select(d, nq, m * kSeedTileRows, cap, k, st));
   return B2VS_OK;
 }
 
@@ -252,6 +256,7 @@ static int run_grouped_pq_scan(b2vs_index* index, IvfData* d, const long long* p
   B2VS_TRY(d->ws_g_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16));
   B2VS_TRY(d->ws_g_q.reserve(static_cast<size_t>(rows_cap) * index->dim * 2));
   B2VS_TRY(d->ws_g_rowq.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
+  B2VS_TRY(d->ws_g_rowslot.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
   B2VS_TRY(d->ws_g_bias.reserve(static_cast<size_t>(rows_cap) * sizeof(float)));
   int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
   B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
@@ -268,6 +273,7 @@ static int run_grouped_pq_scan(b2vs_index* index, IvfData* d, const long long* p
   ga.row_query = d->ws_g_rowq.as<int>(); ga.row_bias = d->ws_g_bias.as<float>();
   ga.tau = d->ws_g_tau.as<float>();
   ga.cand = d->ws_g_cand.as<u64>(); ga.count = d->ws_g_cnt.as<int>(); ga.cap = cap;
+  ga.row_slot = d->ws_g_rowslot.as<int>(); ga.seed_all = row_limit > 0 ? 1 : 0;
   if (timed) B2VS_CUDA(cudaEventRecord(d->ev0, st));
   B2VS_TRY(launch_pq_grouped_scan(index->dev, ga, st));
   if (timed) B2VS_CUDA(cudaEventRecord(d->ev1, st));
@@ -474,7 +480,7 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
       const int cap = grouped_cap(k);
       // seed thresholds first (queries ordered by their nearest list), then group all the items
       B2VS_TRY(reserve_item_sort(d, items, kGroupRows));  // both sorts share these buffers
-      const bool tc_seed = use_tc_seed(nq);
+      const bool tc_seed = use_tc_seed(nq, cap);
       const bool order_seeds = !tc_seed && nq >= kSeedSortMinQueries;
       if (order_seeds) B2VS_TRY(sort_items_by_list(d, probe_ids, nq, n_probes, 1, st));
       B2VS_TRY(d->ws_g_tau.reserve(static_cast<size_t>(nq) * sizeof(float)));
@@ -518,7 +524,7 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
     // decoded from the PQ codes instead of loaded.
     const int cap = grouped_cap(k);
     B2VS_TRY(reserve_item_sort(d, items, kGroupRows));
-    const bool tc_seed = use_tc_seed(nq);
+    const bool tc_seed = use_tc_seed(nq, cap);
     const bool order_seeds = !tc_seed && nq >= kSeedSortMinQueries;
     if (order_seeds) B2VS_TRY(sort_items_by_list(d, probe_ids, nq, n_probes, 1, st));
     B2VS_TRY(d->ws_g_tau.reserve(static_cast<size_t>(nq) * sizeof(float)));

@@ -37,6 +37,8 @@ int launch_pq_grouped_scan(int dev, const PqGroupedScanArgs& a, cudaStream_t st)
   p.work = static_cast<const int4*>(a.work);
   p.n_work = a.n_work;
   p.row_query = a.row_query;
+  p.row_slot = a.row_slot;
+  p.seed_all = a.seed_all;
   pp.codes = static_cast<const uint8_t*>(a.codes);
   pp.cb16 = static_cast<const uint32_t*>(a.cb16t);
   pp.row_bias = a.row_bias;

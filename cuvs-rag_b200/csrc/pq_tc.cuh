@@ -29,8 +29,10 @@ constexpr int kPqTcThreads = 512;
 constexpr int kPqTcStages = 3;
 constexpr int kPqTcStageBytes = kBM * kBK * 2 + kBN * kBK * 2;   // 48 KB
 constexpr int kPqTcMaxCbBytes = 64 * 1024;
+constexpr int kPqTcQueueBytes = 8 * kQueueWarpBytes;   // one hit queue per epilogue warp (bf_tc.cuh)
 constexpr int kPqTcSmemBytes =
-    kPqTcStages * kPqTcStageBytes + 2 * kNormBytes + 256 + kPqTcMaxCbBytes + 1024;
+    kPqTcStages * kPqTcStageBytes + 2 * kNormBytes + 256 + kPqTcMaxCbBytes + kPqTcQueueBytes + 1024;
+static_assert(kPqTcSmemBytes <= 227 * 1024, "pq_tc_kernel shared memory");
 static_assert(kBK == 64, "the decoder writes 128-byte swizzled rows");
 
 struct PqTcParams {
@@ -72,6 +74,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
       smem + kStages * kStageBytes + 2 * kNormBytes + 16 * kStages + 64);
   uint32_t* cb_s = reinterpret_cast<uint32_t*>(smem + kStages * kStageBytes + 2 * kNormBytes + 256);
+  uint8_t* const queue_mem = smem + kStages * kStageBytes + 2 * kNormBytes + 256 + kPqTcMaxCbBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -281,6 +284,13 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
     const float inf = __int_as_float(0x7f800000);
     uint32_t tcount = 0;
+    HitQueue hq;
+    {
+      const int qi = ew + 4 * half;
+      hq.keys = reinterpret_cast<u64*>(queue_mem + qi * kQueueWarpBytes);
+      hq.slots = reinterpret_cast<int*>(queue_mem + qi * kQueueWarpBytes + kQueueCap * 8);
+      hq.n = 0;
+    }
     for (int item = unit; item < n_items; item += n_units) {
       const int4 w = __ldg(p.work + item);
       const int row_begin = w.y, row_end = w.z;
@@ -299,9 +309,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
       }
       const size_t qslot = static_cast<size_t>(max(query, 0));
       u64* const row_buf = p.big_cand + qslot * p.big_cap;
-      int* const row_cnt = p.big_count + qslot;
-      int cnt = 0;
-      u64 best = kKeyInf;
+      const int seed_slot = p.seed_all ? __ldg(p.row_slot + v_row) : 0;
       for (int ti = 0; ti < t1; ++ti, ++tcount) {
         const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
         ptx::mbar_wait(bar_acc_full + 8 * as, aph);
@@ -323,14 +331,22 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar_acc_empty + 8 * as);
           }
-          if (col < nv)
-            score_chunk<kModeAppend>(ra, nrm4 + col / 4, p.alpha, col0 + col, tau, cnt, best, row_buf,
-                                     row_cnt, p.big_cap, bias);
+          if (col < nv) {
+            if (p.seed_all) {
+              if (query >= 0)
+                score_chunk_seed(ra, nrm4 + col / 4, p.alpha, col0 + col, bias,
+                                 row_buf + seed_slot * kSeedSlotRows + (ti * kBN + col));
+            } else {
+              score_chunk_queue(ra, nrm4 + col / 4, p.alpha, col0 + col, tau, bias, static_cast<int>(qslot),
+                                hq, p.big_cand, p.big_count, p.big_cap, lane);
+            }
+          }
         }
         __syncwarp();   // all lanes are done with this tile's ||r^||^2 values
         if (lane == 0) ptx::mbar_arrive(bar_norm_empty + 8 * as);
       }
     }
+    queue_drain(hq, p.big_cand, p.big_count, p.big_cap, lane);
   }
 
   __syncwarp();

@@ -32,35 +32,54 @@ from typing import Tuple
 import torch
 
 
-ADJUST_THRESHOLD = 0.25   # a cluster is "small" when size <= 0.25 x the average size
-ADJUST_WEIGHT = 7.0       # weight of the donor cluster's centre against the picked data row
+ADJUST_WEIGHT = 7.0       # weight of the large cluster's centre against the picked data row
+
+
+def balance_pairs(counts, n):
+    """WHICH clusters move: clusters above 1.5x the average size want floor(size/avg) - 1 extra
+    centroids, taken from the smallest clusters below 0.5x the average (smallest first, largest
+    cluster served first).  Returns donor_of[c] (-1 = keep).  cuVS's adjust_centers picks the large
+    cluster through a random data row (probability ~ size) and only moves clusters below a quarter
+    of the average; ranking instead empties over-full "hub" lists first (measured: DESIGN.md §4)."""
+    ncl = len(counts)
+    donor = [-1] * ncl
+    avg = n / float(ncl)
+    order = sorted(range(ncl), key=lambda c: (counts[c], c))
+    lo, hi = 0, ncl - 1
+    while lo < hi:
+        big = order[hi]
+        if counts[big] <= 1.5 * avg:
+            break
+        quota = max(1, int(counts[big] / avg) - 1)
+        while quota > 0 and lo < hi and counts[order[lo]] < 0.5 * avg:
+            donor[order[lo]] = big
+            lo += 1
+            quota -= 1
+        if quota > 0:
+            break
+        hi -= 1
+    return donor
 
 
 def adjust_centers(cent: torch.Tensor, cnt: torch.Tensor, lab: torch.Tensor, x: torch.Tensor,
                    g: torch.Generator) -> torch.Tensor:
-    """The balancing step of cuVS / RAFT balanced k-means ("adjust_centers", published in
-    raft/cluster/detail/kmeans_balanced.cuh) restated: every cluster whose size is at most
-    ``ADJUST_THRESHOLD`` x average is re-seeded next to a LARGE cluster - pick a random data row
-    ``i`` whose own cluster ``l`` has at least the average size, and set
+    """WHERE they move: the re-seed position of cuVS / RAFT balanced k-means ("adjust_centers",
+    published in raft/cluster/detail/kmeans_balanced.cuh) restated - next to the large cluster l,
+    nudged towards one of its members i:
 
         centre[small] = (wc * centre[l] + x[i]) / (wc + 1),   wc = min(size[l], ADJUST_WEIGHT)
 
-    i.e. a point close to the large cluster's centre, nudged towards one of its members, so the
-    next assignment splits the large cluster.  (Restarting ON a data row - this file's round-1
-    reading - isolates the new centre in high dimensions: ||x||^2 dominates its score and only the
-    row itself joins, leaving singleton lists.)"""
-    n, ncl = x.shape[0], cent.shape[0]
-    avg = n / float(ncl)
+    so the next assignment splits the large cluster.  (Restarting ON a data row - this file's
+    round-1 reading - isolates the new centre in high dimensions: ||x||^2 dominates its score and
+    only the row itself joins, leaving singleton lists: 60 % of the lists on iid Gaussian rows.)"""
+    n = x.shape[0]
     out = cent.clone()
-    small = torch.nonzero(cnt.to(torch.float64) <= ADJUST_THRESHOLD * avg)[:, 0].tolist()
-    if not small or not bool((cnt.to(torch.float64) >= avg).any()):
-        return out
-    for c in small:
-        while True:
-            i = int(torch.randint(0, n, (1,), generator=g))
-            l = int(lab[i])
-            if float(cnt[l]) >= avg:
-                break
+    donor = balance_pairs(cnt.tolist(), n)
+    for c, l in enumerate(donor):
+        if l < 0 or l == c:
+            continue
+        rows = torch.nonzero(lab == l)[:, 0]
+        i = rows[int(torch.randint(0, rows.numel(), (1,), generator=g))]
         wc = min(float(cnt[l]), ADJUST_WEIGHT)
         out[c] = (wc * cent[l] + x[i]) / (wc + 1.0)
     return out
@@ -68,10 +87,11 @@ def adjust_centers(cent: torch.Tensor, cnt: torch.Tensor, lab: torch.Tensor, x: 
 
 def kmeans(x: torch.Tensor, n_clusters: int, iters: int = 20, seed: int = 0,
            balance: bool = True, init: "torch.Tensor | None" = None) -> torch.Tensor:
-    """Lloyd iterations (assign, mean) with cuVS's balancing step between them: after the update
-    of every iteration but the last, small clusters are re-seeded by ``adjust_centers`` (cuVS
-    adjusts before the E-step of every iteration after the first - the same schedule).  A cluster
-    that is empty when no balancing follows keeps its previous centre."""
+    """Lloyd iterations (assign, mean) with a balancing step between them: after the update of
+    every iteration but the last, under-full clusters are re-seeded inside over-full ones
+    (``balance_pairs`` + ``adjust_centers``; cuVS adjusts before the E-step of every iteration
+    after the first - the same schedule).  A cluster that is empty when no balancing follows keeps
+    its previous centre."""
     x = x.to(torch.float32)
     n = x.shape[0]
     g = torch.Generator().manual_seed(seed)

@@ -29,7 +29,8 @@ def corpus(kind, n, d, seed):
 def test_ivf_flat_recall_parity_on_structureless_data_c3_shape(b2, kind, metric):
     from oracle.exact import exact_knn
     from oracle.ivf import IvfFlatOracle, recall
-    n, d, nlist, k, nq = 196_608, 768, 1024, 10, 400       # 192 rows per list; C3 has 2441
+    n, d, nlist, k, nq = 196_608, 768, 1024, 10, 3000      # 192 rows per list; C3 has 2441
+    # 3000 queries: two independently trained indexes differ per query, sigma(recall diff) ~ 0.006
     x = corpus(kind, n, d, 31).to(torch.float16)
     q = corpus(kind, nq, d, 32).to(torch.float16)           # independent draws, not database rows
     ix = b2.NativeIndex.ivf_flat(x.cuda(), nlist, metric=metric, kmeans_iters=8)
@@ -45,13 +46,14 @@ def test_ivf_flat_recall_parity_on_structureless_data_c3_shape(b2, kind, metric)
     for p, (r_gpu, r_ref) in report.items():
         assert abs(r_gpu - r_ref) <= TOL, report
     # structureless data: recall must actually move with the probe count (no trivially-1.0 corpus)
-    assert report[1][0] < 0.5 < report[128][0], report
+    assert report[1][0] < report[8][0] < report[32][0] < report[128][0] < 0.9, report
+    assert report[128][0] > 3 * report[8][0], report
 
 
 def test_ivf_pq_recall_parity_on_structureless_data_c4_shape(b2):
     from oracle.exact import exact_knn
     from oracle.ivf import IvfPqOracle, recall
-    n, d, nlist, m, k, nq = 131_072, 128, 512, 64, 10, 200   # 256 rows per list, M = 64 (dsub 2) as C4
+    n, d, nlist, m, k, nq = 131_072, 128, 512, 64, 10, 600   # 256 rows per list, M = 64 (dsub 2) as C4
     x = corpus("gauss", n, d, 41).to(torch.float16)
     q = corpus("gauss", nq, d, 42).to(torch.float16)
     ix = b2.NativeIndex.ivf_pq(x.cuda(), nlist, m, kmeans_iters=8)
@@ -64,8 +66,10 @@ def test_ivf_pq_recall_parity_on_structureless_data_c4_shape(b2):
         report[(p, rr)] = (round(recall(gi.cpu(), truth), 4), round(recall(oi, truth), 4))
     for key, (r_gpu, r_ref) in report.items():
         assert abs(r_gpu - r_ref) <= TOL + 0.01, report     # + PQ codebook training noise
-    assert report[(64, 4)][0] > report[(64, 1)][0] + 0.05, report    # refine matters on this corpus
-    assert report[(64, 20)][0] >= report[(64, 4)][0] - 0.005, report
+    # M = 64 on 128-d (8 bits per 2 dims) is a fine quantizer: refine only adds a little here
+    assert report[(64, 4)][0] >= report[(64, 1)][0] - 0.002, report
+    assert report[(64, 20)][0] >= report[(64, 4)][0] - 0.002, report
+    assert report[(8, 1)][0] < 0.5 * report[(64, 1)][0], report
 
 
 def test_ivf_pq_default_params_build_at_dim_768(b2, ):
@@ -97,11 +101,15 @@ def test_cosine_metric_equals_sklearn_cosine_golden(b2, golden_dir):
     assert (i.cpu().numpy() == g["cos_i"]).mean() > 0.99
     np.testing.assert_allclose(d.cpu().numpy(), g["cos_d"], atol=3e-5)
     assert (d[:, 1:] >= d[:, :-1]).all()
-    # IVF-Flat with every list probed is the same exact answer
+    # IVF-Flat with every list probed: the same answer up to its 16-bit list storage (fp32 rows are
+    # kept as bf16 in the lists: ~4e-3 relative on similarities close to 1)
     iv = b2.NativeIndex.ivf_flat(x.cuda(), 16, metric="cosine", kmeans_iters=4)
+    assert iv.info().metric == 2
     d2, i2 = iv.search(q.cuda(), k, n_probes=16)
-    assert (i2.cpu().numpy() == g["cos_i"]).mean() > 0.99
-    np.testing.assert_allclose(d2.cpu().numpy(), g["cos_d"], atol=3e-5)
+    inter = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(i2.cpu(), torch.from_numpy(g["cos_i"])))
+    assert inter >= 0.8 * g["cos_i"].size, inter
+    np.testing.assert_allclose(d2.cpu().numpy(), g["cos_d"], atol=8e-3)
+    assert (d2[:, 1:] >= d2[:, :-1]).all()
 
 
 def test_query_dim_mismatch_and_bad_out_buffers_are_rejected(b2):
