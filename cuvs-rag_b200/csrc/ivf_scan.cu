@@ -272,10 +272,18 @@ __global__ void gather_group_queries_kernel(const uint32_t* __restrict__ row_ite
   }
   if (kSkipPaddingRows && q < 0) return;   // never qualifies (threshold -inf): bytes are don't-care
   if (!split) {
-    uint16_t* orow = out + static_cast<size_t>(v) * dp;
-    for (int j = lane; j < dp; j += 32) {
-      float back;
-      orow[j] = q < 0 ? uint16_t(0) : to_op16(qf[static_cast<size_t>(q) * dp + j], fmt, &back);
+    // dp is a multiple of 8: 16-byte loads of four fp32 values, 8-byte stores of four 16-bit ones
+    uint2* orow = reinterpret_cast<uint2*>(out + static_cast<size_t>(v) * dp);
+    const float4* qrow = reinterpret_cast<const float4*>(qf + static_cast<size_t>(max(q, 0)) * dp);
+    for (int j4 = lane; j4 < (dp >> 2); j4 += 32) {
+      uint2 o = make_uint2(0u, 0u);
+      if (q >= 0) {
+        const float4 x = __ldg(qrow + j4);
+        float back;
+        o.x = static_cast<uint32_t>(to_op16(x.x, fmt, &back)) | (static_cast<uint32_t>(to_op16(x.y, fmt, &back)) << 16);
+        o.y = static_cast<uint32_t>(to_op16(x.z, fmt, &back)) | (static_cast<uint32_t>(to_op16(x.w, fmt, &back)) << 16);
+      }
+      orow[j4] = o;
     }
     return;
   }
@@ -295,34 +303,38 @@ __global__ void gather_group_queries_kernel(const uint32_t* __restrict__ row_ite
   }
 }
 
-// One CTA per query: bitonic sort of the appended candidates in shared memory, first k kept.
-constexpr int kSelectThreads = 256;
+// Per query: the k best of the appended candidates, sorted.  One warp per query keeps a 128-key
+// sorted list in registers (WarpTopK) and is offered the candidates 32 at a time, filtered by the
+// running k-th score: after the first few offers almost every batch is rejected by one compare.
+// (Round 1 sorted the whole buffer in shared memory, one CTA per query: 0.23 ms at C3.)
+constexpr int kSelectThreads = 128;
 __global__ void __launch_bounds__(kSelectThreads)
-ivf_group_select_kernel(const u64* __restrict__ cand, const int* __restrict__ count, int cap, int k,
+ivf_group_select_kernel(const u64* __restrict__ cand, const int* __restrict__ count, int cap, int k, int nq,
                         u64* __restrict__ out_keys, unsigned long long* __restrict__ total_cand) {
-  extern __shared__ u64 sk[];
-  const int q = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
   const int n = count[q];
-  if (threadIdx.x == 0 && total_cand) atomicAdd(total_cand, static_cast<unsigned long long>(n));
+  if (lane == 0 && total_cand) atomicAdd(total_cand, static_cast<unsigned long long>(n));
   if (n > cap) return;  // overflow: left to the rescue kernel
-  int P = 32;
-  while (P < n) P <<= 1;
   const u64* src = cand + static_cast<size_t>(q) * cap;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) sk[i] = i < n ? __ldcg(src + i) : kKeyInf;
-  __syncthreads();
-  for (int size = 2; size <= P; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
-        const int lo = 2 * t - (t & (stride - 1));
-        const int hi = lo + stride;
-        const bool up = (lo & size) == 0;
-        const u64 a = sk[lo], b = sk[hi];
-        if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
-      }
-      __syncthreads();
+  WarpTopK tk;
+  tk.init();
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    u64 ck = kKeyInf;
+    if (i < n) {
+      const u64 v = __ldcg(src + i);
+      if (key_score(v) <= tk.tau) ck = v;   // ties at the k-th score are settled by the key order in the merge
     }
+    tk.offer(ck, k, lane);
   }
-  for (int i = threadIdx.x; i < k; i += blockDim.x) out_keys[static_cast<size_t>(q) * k + i] = i < P ? sk[i] : kKeyInf;
+  u64* out = out_keys + static_cast<size_t>(q) * k;
+#pragma unroll
+  for (int e = 0; e < kListE; ++e) {
+    const int i = lane * kListE + e;
+    if (i < k) out[i] = tk.acc[e];
+  }
 }
 
 // Seed pass -> thresholds.  The tensor-core kernel appended the scores of the first rows of each
@@ -910,13 +922,24 @@ __global__ void gather_group_residuals_kernel(const uint32_t* __restrict__ row_i
   const int q = static_cast<int>(item / static_cast<uint32_t>(n_probes));
   if (lane == 0) row_slot[v] = static_cast<int>(item % static_cast<uint32_t>(n_probes));
   const long long list = probe_ids[item];
-  const float* c = cent + static_cast<size_t>(list < 0 ? 0 : list) * dim;
+  // dim is a multiple of 64 on this path: four dimensions per lane and step (16-byte loads)
+  const float4* c4 = reinterpret_cast<const float4*>(cent + static_cast<size_t>(list < 0 ? 0 : list) * dim);
+  const float4* q4 = reinterpret_cast<const float4*>(qf + static_cast<size_t>(q) * dp);
+  uint2* o2 = reinterpret_cast<uint2*>(orow);
   float acc = 0.f;
-  for (int j = lane; j < dim; j += 32) {
-    const float qv = qf[static_cast<size_t>(q) * dp + j];
-    float back;
-    orow[j] = to_op16(l2 ? qv - c[j] : qv, 1, &back);
-    acc = l2 ? fmaf(back, back, acc) : fmaf(qv, c[j], acc);
+  for (int j4 = lane; j4 < (dim >> 2); j4 += 32) {
+    const float4 qv = __ldg(q4 + j4);
+    const float4 cv = __ldg(c4 + j4);
+    const float in[4] = {l2 ? qv.x - cv.x : qv.x, l2 ? qv.y - cv.y : qv.y, l2 ? qv.z - cv.z : qv.z,
+                         l2 ? qv.w - cv.w : qv.w};
+    float back[4];
+    uint16_t h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = to_op16(in[e], 1, &back[e]);
+    if (l2) acc += back[0] * back[0] + back[1] * back[1] + back[2] * back[2] + back[3] * back[3];
+    else acc += qv.x * cv.x + qv.y * cv.y + qv.z * cv.z + qv.w * cv.w;
+    o2[j4] = make_uint2(static_cast<uint32_t>(h[0]) | (static_cast<uint32_t>(h[1]) << 16),
+                        static_cast<uint32_t>(h[2]) | (static_cast<uint32_t>(h[3]) << 16));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -1046,8 +1069,8 @@ int launch_flat_rescue(const b2vs_index* index, IvfData* d, const long long* pro
 }
 
 int launch_group_select(IvfData* d, int nq, int cap, int k, unsigned long long* total_cand, cudaStream_t st) {
-  ivf_group_select_kernel<<<nq, kSelectThreads, static_cast<size_t>(cap) * sizeof(u64), st>>>(
-      d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), cap, k, d->ws_keys.as<u64>(), total_cand);
+  ivf_group_select_kernel<<<static_cast<unsigned>(ceil_div(nq, kSelectThreads / 32)), kSelectThreads, 0, st>>>(
+      d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), cap, k, nq, d->ws_keys.as<u64>(), total_cand);
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }
