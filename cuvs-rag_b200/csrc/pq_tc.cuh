@@ -241,23 +241,41 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
         const uint32_t w8[8] = {cv0[u][0].x, cv0[u][0].y, cv0[u][0].z, cv0[u][0].w,
                                 cv0[u][1].x, cv0[u][1].y, cv0[u][1].z, cv0[u][1].w};
         const uint32_t unit_base = b_base + static_cast<uint32_t>(2 * dw + u) * 4096u;   // 32 rows x 128 B
+        // The look-ups of a batch of rows are all issued before the first store of the batch: the
+        // store asm statements are ordering points for the compiler, and one look-up latency per
+        // row on the critical path (32 x 2 x ~40 cycles per k-block) was what the decoders cost.
+        constexpr int kBatch = 16 / WPC;           // rows per batch: 16 registers of look-up results
 #pragma unroll
-        for (int r = 0; r < 32; r += RPI) {
-          const uint32_t rr = static_cast<uint32_t>(r) + static_cast<uint32_t>(rph);     // row in the group
-          const uint32_t code = (w8[r >> 2] >> (8u * ((r & 3) + rph))) & 0xFFu;
-          const uint32_t* src = cb_kb + code * wps;
-          const uint32_t swz = rr & 7u;
-          const uint32_t dst = unit_base + (rr >> 3) * 1024u + swz * 128u + (((pc ^ swz) << 4) | pw);
-          if (WPC == 1) {
-            const uint32_t v = src[0];
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(v) : "memory");
-          } else if (WPC == 2) {
-            const uint2 v = *reinterpret_cast<const uint2*>(src);
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(v.x), "r"(v.y) : "memory");
-          } else {
-            const uint4 v = *reinterpret_cast<const uint4*>(src);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z),
-                         "r"(v.w) : "memory");
+        for (int r0 = 0; r0 < 32; r0 += RPI * kBatch) {
+          uint32_t val[kBatch][WPC];
+#pragma unroll
+          for (int b = 0; b < kBatch; ++b) {
+            const int r = r0 + b * RPI;
+            const uint32_t code = (w8[r >> 2] >> (8u * ((r & 3) + rph))) & 0xFFu;
+            const uint32_t* src = cb_kb + code * wps;
+            if (WPC == 1) {
+              val[b][0] = src[0];
+            } else if (WPC == 2) {
+              const uint2 v = *reinterpret_cast<const uint2*>(src);
+              val[b][0] = v.x; val[b][WPC - 1] = v.y;
+            } else {
+              const uint4 v = *reinterpret_cast<const uint4*>(src);
+              val[b][0] = v.x; val[b][1 % WPC] = v.y; val[b][2 % WPC] = v.z; val[b][3 % WPC] = v.w;
+            }
+          }
+#pragma unroll
+          for (int b = 0; b < kBatch; ++b) {
+            const uint32_t rr = static_cast<uint32_t>(r0 + b * RPI) + static_cast<uint32_t>(rph);   // row in the group
+            const uint32_t swz = rr & 7u;
+            const uint32_t dst = unit_base + (rr >> 3) * 1024u + swz * 128u + (((pc ^ swz) << 4) | pw);
+            if (WPC == 1) {
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(val[b][0]));
+            } else if (WPC == 2) {
+              asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(val[b][0]), "r"(val[b][WPC - 1]));
+            } else {
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(val[b][0]),
+                           "r"(val[b][1 % WPC]), "r"(val[b][2 % WPC]), "r"(val[b][3 % WPC]));
+            }
           }
         }
       }
