@@ -211,12 +211,22 @@ struct HitQueue {
 __device__ __forceinline__ void queue_drain(HitQueue& hq, u64* __restrict__ cand, int* __restrict__ count,
                                             int cap, int lane) {
   __syncwarp();
-  for (int e = lane; e < hq.n; e += 32) {
-    const u64 key = hq.keys[e];
-    const int s = hq.slots[e];
-    const int pos = atomicAdd(count + s, 1);
-    if (pos < cap) __stcg(cand + static_cast<size_t>(s) * cap + pos, key);
+  constexpr int kPerLane = (kQueueCap + 31) / 32;
+  u64 key[kPerLane];
+  int slot[kPerLane], pos[kPerLane];
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) {     // every atomic of the batch is issued before any is awaited
+    const int e = lane + 32 * i;
+    pos[i] = cap;
+    if (e < hq.n) {
+      key[i] = hq.keys[e];
+      slot[i] = hq.slots[e];
+      pos[i] = atomicAdd(count + slot[i], 1);
+    }
   }
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i)
+    if (pos[i] < cap) __stcg(cand + static_cast<size_t>(slot[i]) * cap + pos[i], key[i]);
   __syncwarp();
   hq.n = 0;
 }

@@ -174,6 +174,14 @@ __host__ __device__ __forceinline__ size_t pq_code_offset(size_t slot, int m, in
   return ((slot >> 5) * static_cast<size_t>(mp) + static_cast<size_t>(m)) * 32 + (slot & 31);
 }
 
+// Position of the i-th query of a list's group inside the gathered operand: queries are dealt
+// round-robin over the four 32-row quarters of their 128-row block (TMEM lane quarter = epilogue
+// warp), so a partly filled block - the common case: ~40 of 128 rows at C4 - loads the four
+// epilogue warps evenly instead of leaving all its hits to the warp of rows 0-31.
+__host__ __device__ __forceinline__ uint32_t group_row_pos(uint32_t i) {
+  return (i & ~127u) | ((i & 3u) << 5) | ((i >> 2) & 31u);
+}
+
 // ---- kmeans.cu ------------------------------------------------------------------------------
 // Temporaries of one k-means fit.  A caller that fits many small problems in a row (the 64+ PQ
 // sub-codebooks) passes the same workspace to every fit, so device memory is allocated once
@@ -196,7 +204,8 @@ int kmeans_fit_impl(int dev, int dtype, int dim, const void* x, int64_t n, int n
 int launch_histogram(const int* labels, int64_t n, int* sizes, int blocks, cudaStream_t st);
 int launch_scan_sizes(const int* sizes, int n_lists, int pad, uint32_t* offsets, cudaStream_t st);
 int launch_scatter_rows(const int* labels, int64_t n, const uint32_t* offsets, int* cursor,
-                        uint32_t* row_ids, uint32_t* slot_of_row, int blocks, cudaStream_t st);
+                        uint32_t* row_ids, uint32_t* slot_of_row, int blocks, cudaStream_t st,
+                        int deal_quarters = 0);
 int launch_strided_rows(const void* src, void* dst, int dtype, int64_t n_out, int64_t stride, int dim,
                         cudaStream_t st);
 

@@ -24,27 +24,40 @@ def corpus(kind, n, d, seed):
     return x
 
 
+SEEDS = (0, 1, 2)
+
+
 @pytest.mark.parametrize("kind,metric", [("gauss", "sqeuclidean"), ("unit", "sqeuclidean"),
                                          ("unit", "inner_product")])
 def test_ivf_flat_recall_parity_on_structureless_data_c3_shape(b2, kind, metric):
+    """k-means on structureless rows is chaotic: the cluster-size spread of two runs of the SAME
+    implementation differs by ~10 % between seeds (GPU: 60.5 / 69.2 / 77.9, oracle: 65.4 / 65.9 /
+    68.0 on this corpus, profiles/r2_kmeans_seed_spread.txt), which moves recall@10 at 128 probes by
+    +-0.02.  The parity statement is therefore about the MEAN over three independently seeded
+    indexes on each side, same n_lists / n_probes."""
     from oracle.exact import exact_knn
     from oracle.ivf import IvfFlatOracle, recall
-    n, d, nlist, k, nq = 196_608, 768, 1024, 10, 3000      # 192 rows per list; C3 has 2441
-    # 3000 queries: two independently trained indexes differ per query, sigma(recall diff) ~ 0.006
+    n, d, nlist, k, nq = 196_608, 768, 1024, 10, 1000      # 192 rows per list; C3 has 2441
     x = corpus(kind, n, d, 31).to(torch.float16)
     q = corpus(kind, nq, d, 32).to(torch.float16)           # independent draws, not database rows
-    ix = b2.NativeIndex.ivf_flat(x.cuda(), nlist, metric=metric, kmeans_iters=8)
     _, truth = exact_knn(x.float(), q.float(), k, metric)
-    oracle = IvfFlatOracle(x.float(), nlist, metric, iters=8)
     probes = [1, 8, 32, 128]
-    o_ids = oracle.search_many(q.float(), k, probes)
-    report = {}
-    for p in probes:
-        _, gi = ix.search(q.cuda(), k, n_probes=p)
-        r_gpu, r_ref = recall(gi.cpu(), truth), recall(o_ids[p], truth)
-        report[p] = (round(r_gpu, 4), round(r_ref, 4))
+    gpu = {p: [] for p in probes}
+    ref = {p: [] for p in probes}
+    xg, qg = x.cuda(), q.cuda()
+    for seed in SEEDS:
+        ix = b2.NativeIndex.ivf_flat(xg, nlist, metric=metric, kmeans_iters=8, seed=seed)
+        for p in probes:
+            _, gi = ix.search(qg, k, n_probes=p)
+            gpu[p].append(recall(gi.cpu(), truth))
+        ix.destroy()
+        o_ids = IvfFlatOracle(x.float(), nlist, metric, iters=8, seed=seed).search_many(q.float(), k, probes)
+        for p in probes:
+            ref[p].append(recall(o_ids[p], truth))
+    mean = lambda v: sum(v) / len(v)
+    report = {p: (round(mean(gpu[p]), 4), round(mean(ref[p]), 4)) for p in probes}
     for p, (r_gpu, r_ref) in report.items():
-        assert abs(r_gpu - r_ref) <= TOL, report
+        assert abs(r_gpu - r_ref) <= TOL, (report, gpu, ref)
     # structureless data: recall must actually move with the probe count (no trivially-1.0 corpus)
     assert report[1][0] < report[8][0] < report[32][0] < report[128][0] < 0.9, report
     assert report[128][0] > 3 * report[8][0], report
