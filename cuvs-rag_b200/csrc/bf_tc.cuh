@@ -518,12 +518,14 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       float tau = inf;
       int seed_slot = 0;
       bool real_row = true;
+      bool quarter_live = true;   // work mode: false when none of the warp's 32 rows is a real query
       if (kWork) {
         const int query = __ldg(p.row_query + q_row);
         if (p.seed_all) seed_slot = __ldg(p.row_slot + q_row);
         tau = query >= 0 ? p.tau_init[query] : -inf;   // padding rows never qualify
         real_row = query >= 0;
         q_row = static_cast<size_t>(max(query, 0));
+        quarter_live = __any_sync(0xffffffffu, real_row);
       } else if (q_row >= static_cast<size_t>(p.nq)) {
         tau = -inf;            // padding row of the last query block: stays empty, costs nothing
       } else if (p.tau_init != nullptr) {
@@ -547,6 +549,15 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         // work mode: columns past the end of the list belong to the next list (lists are padded
         // to 32 rows, so validity is per 32-column chunk)
         const int nv = kWork ? row_end - static_cast<int>(col0) : kBN;
+        if (kWork && !quarter_live) {   // nothing to score: keep the barrier protocol going
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::mbar_arrive(bar_acc_empty + 8 * as);
+            ptx::mbar_arrive(bar_norm_empty + 8 * as);
+          }
+          continue;
+        }
         // Two register buffers: the TMEM load of chunk c+1 is in flight while chunk c is scored.
         uint32_t ra[32], rb[32];
         const uint32_t tile_taddr = lane_taddr + as * kBN;

@@ -174,12 +174,19 @@ __host__ __device__ __forceinline__ size_t pq_code_offset(size_t slot, int m, in
   return ((slot >> 5) * static_cast<size_t>(mp) + static_cast<size_t>(m)) * 32 + (slot & 31);
 }
 
-// Position of the i-th query of a list's group inside the gathered operand: queries are dealt
-// round-robin over the four 32-row quarters of their 128-row block (TMEM lane quarter = epilogue
-// warp), so a partly filled block - the common case: ~40 of 128 rows at C4 - loads the four
-// epilogue warps evenly instead of leaving all its hits to the warp of rows 0-31.
-__host__ __device__ __forceinline__ uint32_t group_row_pos(uint32_t i) {
-  return (i & ~127u) | ((i & 3u) << 5) | ((i >> 2) & 31u);
+// Position of the i-th of the c queries of a list's group inside the gathered operand.  A 128-row
+// block is four 32-row quarters (TMEM lane quarter = epilogue warp); the queries of a block are
+// dealt round-robin over as FEW quarters as hold them (ceil(rows in block / 32)), so
+//  * a partly filled block - the common case: ~40 of 128 rows at C4 - loads its active epilogue
+//    warps evenly instead of leaving all hits to the warp of rows 0-31, and
+//  * quarters left empty are skipped by their epilogue warps altogether (bf_tc.cuh / pq_tc.cuh).
+// c = 0 (size unknown to the caller): deal over all four quarters.
+__host__ __device__ __forceinline__ uint32_t group_row_pos(uint32_t i, uint32_t c) {
+  const uint32_t blk = i >> 7, j = i & 127u;
+  uint32_t in_block = 128u;
+  if (c != 0u && blk == ((c - 1u) >> 7)) in_block = ((c - 1u) & 127u) + 1u;   // the group's last block
+  const uint32_t nq = c == 0u ? 4u : (in_block + 31u) >> 5;                  // quarters in use: 1..4
+  return (blk << 7) | ((j % nq) << 5) | (j / nq);
 }
 
 // ---- kmeans.cu ------------------------------------------------------------------------------
@@ -205,7 +212,7 @@ int launch_histogram(const int* labels, int64_t n, int* sizes, int blocks, cudaS
 int launch_scan_sizes(const int* sizes, int n_lists, int pad, uint32_t* offsets, cudaStream_t st);
 int launch_scatter_rows(const int* labels, int64_t n, const uint32_t* offsets, int* cursor,
                         uint32_t* row_ids, uint32_t* slot_of_row, int blocks, cudaStream_t st,
-                        int deal_quarters = 0);
+                        const int* deal_sizes = nullptr);
 int launch_strided_rows(const void* src, void* dst, int dtype, int64_t n_out, int64_t stride, int dim,
                         cudaStream_t st);
 

@@ -84,7 +84,7 @@ int sort_items_by_list(IvfData* d, const long long* probe_ids, int items, int st
   return launch_scatter_rows(d->ws_item_lab.as<int>(), items, d->ws_item_off.as<uint32_t>(),
                              cnt + d->n_lists, d->ws_item_perm.as<uint32_t>(),
                              d->ws_item_slot.as<uint32_t>(), static_cast<int>(blocks), st,
-                             group_pad == kGroupRows ? 1 : 0);
+                             group_pad == kGroupRows ? cnt : nullptr);
 }
 
 // Small batches are launch-bound (a Q = 1 search is ~20 tiny kernels), so when the item count is
@@ -189,7 +189,7 @@ ivf_plan_small_kernel(const long long* __restrict__ probe_ids, int items,
   for (int i = t; i < items; i += kPlanThreads) {
     const long long l = probe_ids[i];
     const int r = rank_of_list[l < 0 ? 0 : l];
-    row_item[off[r] + group_row_pos(static_cast<uint32_t>(atomicAdd(&cnt[r], 1)))] = static_cast<uint32_t>(i);
+    row_item[off[r] + group_row_pos(static_cast<uint32_t>(atomicAdd(&cnt[r], 1)), 0u)] = static_cast<uint32_t>(i);
   }
 }
 

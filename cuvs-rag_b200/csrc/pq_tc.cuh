@@ -328,6 +328,9 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
       const size_t qslot = static_cast<size_t>(max(query, 0));
       u64* const row_buf = p.big_cand + qslot * p.big_cap;
       const int seed_slot = p.seed_all ? __ldg(p.row_slot + v_row) : 0;
+      // a quarter without a single real query row (group_row_pos packs the queries of a block into
+      // as few quarters as possible) only keeps the barrier protocol going
+      const bool quarter_live = __any_sync(0xffffffffu, query >= 0);
       for (int ti = 0; ti < t1; ++ti, ++tcount) {
         const uint32_t as = tcount & 1u, aph = (tcount >> 1) & 1u;
         ptx::mbar_wait(bar_acc_full + 8 * as, aph);
@@ -338,6 +341,15 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
         const int nv = row_end - static_cast<int>(col0);
         const uint32_t tile_taddr = lane_taddr + as * kBN;
         uint32_t ra[32];
+        if (!quarter_live) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::mbar_arrive(bar_acc_empty + 8 * as);
+            ptx::mbar_arrive(bar_norm_empty + 8 * as);
+          }
+          continue;
+        }
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           const int col = half * (kBN / 2) + c * 32;
