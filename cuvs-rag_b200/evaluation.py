@@ -22,16 +22,31 @@ def recall_at_k(retrieved: Sequence[int], relevant: Iterable[int], k: int) -> fl
 
 
 class RecallEvaluator:
-    """Same method names as the reference's RecallEvaluator (improved_multi_gpu_rag.py:310-357)."""
+    """THE recall evaluator of the package (``improved_multi_gpu_rag`` re-exports this class):
+    method names, signatures and corner cases exactly as the reference defines them
+    (``improved_multi_gpu_rag.py:310-357``; pinned by ``tests/golden/recall.json``, generated from
+    the imported reference), plus ``batch_recall`` for [Q, k] id matrices."""
 
     @staticmethod
-    def calculate_recall_at_k(retrieved_indices, relevant_indices, k: int) -> float:
-        return recall_at_k(retrieved_indices, relevant_indices, k)
+    def calculate_recall_at_k(retrieved: np.ndarray, relevant: np.ndarray, k: int) -> float:
+        retrieved, relevant = np.asarray(retrieved), np.asarray(relevant)
+        if len(relevant) == 0:
+            return 1.0 if len(retrieved) == 0 else 0.0
+        top_k = retrieved[:k] if len(retrieved) >= k else retrieved
+        return len(np.intersect1d(top_k, relevant)) / len(relevant)
 
     @staticmethod
-    def evaluate_recall_multiple_k(retrieved_indices, relevant_indices,
+    def evaluate_recall_multiple_k(retrieved: np.ndarray, relevant: np.ndarray,
                                    k_values: List[int]) -> Dict[int, float]:
-        return {k: recall_at_k(retrieved_indices, relevant_indices, k) for k in k_values}
+        return {k: RecallEvaluator.calculate_recall_at_k(retrieved, relevant, min(k, len(retrieved)))
+                for k in k_values}
+
+    @staticmethod
+    def generate_synthetic_ground_truth(num_queries: int, index_size: int,
+                                        relevant_per_query: int = 100) -> Dict[int, np.ndarray]:
+        np.random.seed(42)
+        return {i: np.random.choice(index_size, size=min(relevant_per_query, index_size), replace=False)
+                for i in range(num_queries)}
 
     @staticmethod
     def batch_recall(retrieved: np.ndarray, truth: np.ndarray, k: int) -> float:
@@ -42,11 +57,3 @@ class RecallEvaluator:
         for r, t in zip(retrieved, truth):
             hits += len(set(r.tolist()) & set(t.tolist()))
         return hits / float(truth.shape[0] * truth.shape[1])
-
-    @staticmethod
-    def generate_synthetic_ground_truth(num_queries: int, num_documents: int,
-                                        relevance_ratio: float = 0.01, seed: int = 42):
-        rng = np.random.default_rng(seed)
-        per_query = max(1, int(num_documents * relevance_ratio))
-        return [rng.choice(num_documents, size=per_query, replace=False).tolist()
-                for _ in range(num_queries)]

@@ -36,6 +36,7 @@ import numpy as np
 import torch
 
 import _native
+from evaluation import RecallEvaluator  # noqa: F401  (one class, re-exported under the reference's module name)
 
 logger = logging.getLogger(__name__)
 
@@ -274,31 +275,6 @@ class ParallelSearchEngine:
     def __del__(self):
         if hasattr(self, "executor"):
             self.executor.shutdown(wait=False)
-
-
-class RecallEvaluator:
-    """recall@k exactly as the reference defines it (improved_multi_gpu_rag.py:310-357)."""
-
-    @staticmethod
-    def calculate_recall_at_k(retrieved: np.ndarray, relevant: np.ndarray, k: int) -> float:
-        retrieved, relevant = np.asarray(retrieved), np.asarray(relevant)
-        if len(relevant) == 0:
-            return 1.0 if len(retrieved) == 0 else 0.0
-        top_k = retrieved[:k] if len(retrieved) >= k else retrieved
-        return len(np.intersect1d(top_k, relevant)) / len(relevant)
-
-    @staticmethod
-    def evaluate_recall_multiple_k(retrieved: np.ndarray, relevant: np.ndarray,
-                                   k_values: List[int]) -> Dict[int, float]:
-        return {k: RecallEvaluator.calculate_recall_at_k(retrieved, relevant, min(k, len(retrieved)))
-                for k in k_values}
-
-    @staticmethod
-    def generate_synthetic_ground_truth(num_queries: int, index_size: int,
-                                        relevant_per_query: int = 100) -> Dict[int, np.ndarray]:
-        np.random.seed(42)
-        return {i: np.random.choice(index_size, size=min(relevant_per_query, index_size), replace=False)
-                for i in range(num_queries)}
 
 
 def get_memory_stats() -> Dict:
