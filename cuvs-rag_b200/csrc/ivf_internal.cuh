@@ -212,7 +212,7 @@ int launch_histogram(const int* labels, int64_t n, int* sizes, int blocks, cudaS
 int launch_scan_sizes(const int* sizes, int n_lists, int pad, uint32_t* offsets, cudaStream_t st);
 int launch_scatter_rows(const int* labels, int64_t n, const uint32_t* offsets, int* cursor,
                         uint32_t* row_ids, uint32_t* slot_of_row, int blocks, cudaStream_t st,
-                        const int* deal_sizes = nullptr);
+                        const int* deal_sizes = nullptr, int deal_four = 0);
 int launch_strided_rows(const void* src, void* dst, int dtype, int64_t n_out, int64_t stride, int dim,
                         cudaStream_t st);
 
@@ -224,12 +224,17 @@ int pq_prepare_grouped(b2vs_index* index, IvfData* d, cudaStream_t st);
 // ---- ivf_plan.cu ----------------------------------------------------------------------------
 size_t sorted_rows_cap(const IvfData* d, int items, int group_pad);
 int reserve_item_sort(IvfData* d, int items, int group_pad);
+// deal: how the queries of a group are placed inside their 128-row blocks (group_row_pos):
+// kDealPacked = over as few 32-row quarters as hold them (empty quarters are skipped by their
+// epilogue warps: fewest instructions - the HBM-bound IVF-Flat scan), kDealFour = over all four
+// quarters (shortest critical path - the epilogue-bound PQ scan: 1.40 vs 1.57 ms at C4)
+constexpr int kDealPacked = 0, kDealFour = 1;
 int sort_items_by_list(IvfData* d, const long long* probe_ids, int items, int stride, int group_pad,
-                       cudaStream_t st);
+                       cudaStream_t st, int deal = kDealPacked);
 // row_limit > 0: only the first row_limit rows of every list become work (the seed pass)
 int plan_grouped_work(IvfData* d, const long long* probe_ids, int items, int chunk_rows, int slots,
                       int4* work, int* n_work, unsigned long long* counter, cudaStream_t st,
-                      int row_limit = 0);
+                      int row_limit = 0, int deal = kDealPacked);
 void choose_work_split(const b2vs_index* index, const IvfData* d, int items, int* chunk_rows, int* slots);
 bool plan_is_small(const IvfData* d, int items);
 

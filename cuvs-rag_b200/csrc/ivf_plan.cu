@@ -69,7 +69,7 @@ int reserve_item_sort(IvfData* d, int items, int group_pad) {
 }
 
 int sort_items_by_list(IvfData* d, const long long* probe_ids, int items, int stride,
-                              int group_pad, cudaStream_t st) {
+                              int group_pad, cudaStream_t st, int deal) {
   const size_t rows_cap = sorted_rows_cap(d, items, group_pad);
   B2VS_TRY(reserve_item_sort(d, items, group_pad));
   const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div(items, 256), 2048));
@@ -84,7 +84,7 @@ int sort_items_by_list(IvfData* d, const long long* probe_ids, int items, int st
   return launch_scatter_rows(d->ws_item_lab.as<int>(), items, d->ws_item_off.as<uint32_t>(),
                              cnt + d->n_lists, d->ws_item_perm.as<uint32_t>(),
                              d->ws_item_slot.as<uint32_t>(), static_cast<int>(blocks), st,
-                             group_pad == kGroupRows ? cnt : nullptr);
+                             group_pad == kGroupRows ? cnt : nullptr, deal == kDealFour ? 1 : 0);
 }
 
 // Small batches are launch-bound (a Q = 1 search is ~20 tiny kernels), so when the item count is
@@ -201,7 +201,7 @@ bool plan_is_small(const IvfData* d, int items) {
 // counting-sort kernels + build_group_work_kernel.
 int plan_grouped_work(IvfData* d, const long long* probe_ids, int items, int chunk_rows,
                              int slots, int4* work, int* n_work, unsigned long long* counter,
-                             cudaStream_t st, int row_limit) {
+                             cudaStream_t st, int row_limit, int deal) {
   if (plan_is_small(d, items)) {
     B2VS_TRY(reserve_item_sort(d, items, kGroupRows));
     B2VS_CUDA(cudaMemsetAsync(d->ws_item_perm.ptr, 0xFF,
@@ -216,7 +216,7 @@ int plan_grouped_work(IvfData* d, const long long* probe_ids, int items, int chu
     B2VS_CUDA(cudaGetLastError());
     return B2VS_OK;
   }
-  B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, kGroupRows, st));
+  B2VS_TRY(sort_items_by_list(d, probe_ids, items, 1, kGroupRows, st, deal));
   build_group_work_kernel<<<static_cast<unsigned>(ceil_div(d->n_lists, 256)), 256, 0, st>>>(
       d->ws_item_off.as<uint32_t>(), d->offsets.as<uint32_t>(), d->ws_item_cnt.as<int>(),
       d->list_of_rank.as<int>(), d->n_lists, chunk_rows, slots, row_limit, work, n_work, counter);

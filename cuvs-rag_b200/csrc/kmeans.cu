@@ -92,13 +92,13 @@ __global__ void scan_sizes_kernel(const int* __restrict__ sizes, int n_lists, in
 __global__ void scatter_rows_kernel(const int* __restrict__ labels, int64_t n,
                                     const uint32_t* __restrict__ offsets, int* __restrict__ cursor,
                                     uint32_t* __restrict__ row_ids, uint32_t* __restrict__ slot_of_row,
-                                    const int* __restrict__ deal_sizes) {
+                                    const int* __restrict__ deal_sizes, int deal_four) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int c = labels[i];
     if (c < 0) { slot_of_row[i] = kNoRow; continue; }
     uint32_t idx = static_cast<uint32_t>(atomicAdd(cursor + c, 1));
-    if (deal_sizes) idx = group_row_pos(idx, static_cast<uint32_t>(deal_sizes[c]));   // grouped scans
+    if (deal_sizes) idx = group_row_pos(idx, deal_four ? 0u : static_cast<uint32_t>(deal_sizes[c]));   // grouped scans
     const uint32_t slot = offsets[c] + idx;
     row_ids[slot] = static_cast<uint32_t>(i);
     slot_of_row[i] = slot;
@@ -285,7 +285,7 @@ int kmeans_fit_impl(int dev, int dtype, int dim, const void* x, int64_t n, int n
     histogram_kernel<<<acc_blocks, 256, 0, st>>>(lab, n, counts.as<int>());
     scan_sizes_kernel<<<1, 1024, 0, st>>>(counts.as<int>(), ncl, 1, seg_off.as<uint32_t>());
     scatter_rows_kernel<<<acc_blocks, 256, 0, st>>>(lab, n, seg_off.as<uint32_t>(), seg_cur.as<int>(),
-                                                    seg_rows.as<uint32_t>(), seg_slot.as<uint32_t>(), nullptr);
+                                                    seg_rows.as<uint32_t>(), seg_slot.as<uint32_t>(), nullptr, 0);
     KM_CUDA(cudaGetLastError());
     {
       const int tpb = dim >= 256 ? 256 : ((dim + 31) / 32) * 32;
@@ -332,8 +332,9 @@ int launch_scan_sizes(const int* sizes, int n_lists, int pad, uint32_t* offsets,
 }
 int launch_scatter_rows(const int* labels, int64_t n, const uint32_t* offsets, int* cursor,
                         uint32_t* row_ids, uint32_t* slot_of_row, int blocks, cudaStream_t st,
-                        const int* deal_sizes) {
-  scatter_rows_kernel<<<blocks, 256, 0, st>>>(labels, n, offsets, cursor, row_ids, slot_of_row, deal_sizes);
+                        const int* deal_sizes, int deal_four) {
+  scatter_rows_kernel<<<blocks, 256, 0, st>>>(labels, n, offsets, cursor, row_ids, slot_of_row, deal_sizes,
+                                              deal_four);
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }
