@@ -227,8 +227,9 @@ int reserve_item_sort(IvfData* d, int items, int group_pad);
 // deal: how the queries of a group are placed inside their 128-row blocks (group_row_pos):
 // kDealPacked = over as few 32-row quarters as hold them (empty quarters are skipped by their
 // epilogue warps: fewest instructions - the HBM-bound IVF-Flat scan), kDealFour = over all four
-// quarters (shortest critical path - the epilogue-bound PQ scan: 1.40 vs 1.57 ms at C4)
-constexpr int kDealPacked = 0, kDealFour = 1;
+// quarters, kDealNone = in arrival order, contiguous from row 0 (the PQ scan: its queries are the
+// COLUMNS of the accumulator, only the leading 16-column units that hold queries are read back)
+constexpr int kDealPacked = 0, kDealFour = 1, kDealNone = 2;
 int sort_items_by_list(IvfData* d, const long long* probe_ids, int items, int stride, int group_pad,
                        cudaStream_t st, int deal = kDealPacked);
 // row_limit > 0: only the first row_limit rows of every list become work (the seed pass)

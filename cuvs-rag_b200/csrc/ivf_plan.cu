@@ -84,7 +84,8 @@ int sort_items_by_list(IvfData* d, const long long* probe_ids, int items, int st
   return launch_scatter_rows(d->ws_item_lab.as<int>(), items, d->ws_item_off.as<uint32_t>(),
                              cnt + d->n_lists, d->ws_item_perm.as<uint32_t>(),
                              d->ws_item_slot.as<uint32_t>(), static_cast<int>(blocks), st,
-                             group_pad == kGroupRows ? cnt : nullptr, deal == kDealFour ? 1 : 0);
+                             (group_pad == kGroupRows && deal != kDealNone) ? cnt : nullptr,
+                             deal == kDealFour ? 1 : 0);
 }
 
 // Small batches are launch-bound (a Q = 1 search is ~20 tiny kernels), so when the item count is
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(kPlanThreads)
 ivf_plan_small_kernel(const long long* __restrict__ probe_ids, int items,
                       const int* __restrict__ rank_of_list, const int* __restrict__ list_of_rank,
                       const uint32_t* __restrict__ offsets, int n_lists, int chunk_rows, int slots,
-                      int row_limit, uint32_t* __restrict__ row_item, uint32_t* __restrict__ group_off,
+                      int row_limit, int deal_none, uint32_t* __restrict__ row_item, uint32_t* __restrict__ group_off,
                       int4* __restrict__ work, int* __restrict__ n_work,
                       unsigned long long* __restrict__ scanned_rows) {
   extern __shared__ int plan_sm[];
@@ -189,7 +190,8 @@ ivf_plan_small_kernel(const long long* __restrict__ probe_ids, int items,
   for (int i = t; i < items; i += kPlanThreads) {
     const long long l = probe_ids[i];
     const int r = rank_of_list[l < 0 ? 0 : l];
-    row_item[off[r] + group_row_pos(static_cast<uint32_t>(atomicAdd(&cnt[r], 1)), 0u)] = static_cast<uint32_t>(i);
+    const uint32_t idx = static_cast<uint32_t>(atomicAdd(&cnt[r], 1));
+    row_item[off[r] + (deal_none ? idx : group_row_pos(idx, 0u))] = static_cast<uint32_t>(i);
   }
 }
 
@@ -211,7 +213,8 @@ int plan_grouped_work(IvfData* d, const long long* probe_ids, int items, int chu
                                    static_cast<int>(smem)));
     ivf_plan_small_kernel<<<1, kPlanThreads, smem, st>>>(
         probe_ids, items, d->rank_of_list.as<int>(), d->list_of_rank.as<int>(),
-        d->offsets.as<uint32_t>(), d->n_lists, chunk_rows, slots, row_limit, d->ws_item_perm.as<uint32_t>(),
+        d->offsets.as<uint32_t>(), d->n_lists, chunk_rows, slots, row_limit, deal == kDealNone ? 1 : 0,
+        d->ws_item_perm.as<uint32_t>(),
         d->ws_item_off.as<uint32_t>(), work, n_work, counter);
     B2VS_CUDA(cudaGetLastError());
     return B2VS_OK;

@@ -260,7 +260,7 @@ static int run_grouped_pq_scan(b2vs_index* index, IvfData* d, const long long* p
   B2VS_TRY(d->ws_g_bias.reserve(static_cast<size_t>(rows_cap) * sizeof(float)));
   int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
   B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
-                             counter, st, row_limit, kDealFour));
+                             counter, st, row_limit, kDealNone));
   B2VS_TRY(launch_gather_group_residuals(index, d, rows_cap, probe_ids, n_probes, st));
   PqGroupedScanArgs ga{};
   ga.q_mat = d->ws_g_q.ptr; ga.q_rows = rows_cap;

@@ -29,7 +29,7 @@ int launch_pq_grouped_scan(int dev, const PqGroupedScanArgs& a, cudaStream_t st)
   p.k = 1;
   p.tile_stride = 1;
   p.alpha = a.alpha;
-  p.idesc = ptx::make_idesc_f16(1u, kBM, kBN);
+  p.idesc = ptx::make_idesc_f16(1u, kPqM, kPqN);   // M = list rows of a tile, N = query rows of a block
   p.tau_init = a.tau;
   p.big_cand = a.cand;
   p.big_count = a.count;
