@@ -255,9 +255,11 @@ int launch_flat_rescue(const b2vs_index* index, IvfData* d, const long long* pro
 int launch_group_select(IvfData* d, int nq, int cap, int k, unsigned long long* total_cand, cudaStream_t st);
 // thresholds of the full pass from the candidates the seed pass appended (k-th best per query)
 int launch_seed_select(IvfData* d, int nq, int n_keys, int cap, int k, cudaStream_t st);
-int launch_gather_group_queries(IvfData* d, int64_t rows_cap, int n_probes, int q_split, cudaStream_t st);
+// items_sorted > 0: gather by item (the counting-sort kernels ran); 0: walk the rows (one-CTA planner)
+int launch_gather_group_queries(IvfData* d, int64_t rows_cap, int n_probes, int q_split, int items_sorted,
+                                cudaStream_t st);
 int launch_gather_group_residuals(const b2vs_index* index, IvfData* d, int64_t rows_cap,
-                                  const long long* probe_ids, int n_probes, cudaStream_t st);
+                                  const long long* probe_ids, int n_probes, int items_sorted, cudaStream_t st);
 // mode 0 = seed thresholds (ws_g_tau), mode 1 = rescue of overflowed queries (ws_keys)
 int launch_pq_lut_scan(int mode, const b2vs_index* index, IvfData* d, const long long* probe_ids,
                        int n_probes, int nq, int k, int cap, uint32_t seed_rows, const uint32_t* q_perm,

@@ -260,11 +260,22 @@ __global__ void gather_group_queries_kernel(const uint32_t* __restrict__ row_ite
                                             const uint32_t* __restrict__ group_off, int n_lists,
                                             const float* __restrict__ qf, int dp, int n_probes,
                                             int fmt, int split, uint16_t* __restrict__ out,
-                                            int* __restrict__ row_query, int* __restrict__ row_slot) {
+                                            int* __restrict__ row_query, int* __restrict__ row_slot,
+                                            const uint32_t* __restrict__ item_slot, int n_items) {
   const int lane = threadIdx.x & 31;
-  const int64_t v = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (v >= static_cast<int64_t>(group_off[n_lists])) return;
-  const uint32_t item = row_item[v];
+  const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  // by item (large batches): one warp per (query, probe) item, placed at the row the sort gave it -
+  // the group-padding rows (2 M of them for 16 K lists) are never visited; row_query was pre-set to -1
+  int64_t v = wid;
+  uint32_t item;
+  if (item_slot) {
+    if (wid >= n_items) return;
+    item = static_cast<uint32_t>(wid);
+    v = item_slot[wid];
+  } else {
+    if (v >= static_cast<int64_t>(group_off[n_lists])) return;
+    item = row_item[v];
+  }
   const int q = item == kNoRow ? -1 : static_cast<int>(item / static_cast<uint32_t>(n_probes));
   if (lane == 0) {
     row_query[v] = q;
@@ -906,11 +917,20 @@ __global__ void gather_group_residuals_kernel(const uint32_t* __restrict__ row_i
                                               const float* __restrict__ qf, const float* __restrict__ cent,
                                               int dim, int dp, int n_probes, int l2,
                                               uint16_t* __restrict__ out, int* __restrict__ row_query,
-                                              float* __restrict__ row_bias, int* __restrict__ row_slot) {
+                                              float* __restrict__ row_bias, int* __restrict__ row_slot,
+                                              const uint32_t* __restrict__ item_slot, int n_items) {
   const int lane = threadIdx.x & 31;
-  const int64_t v = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (v >= static_cast<int64_t>(group_off[n_lists])) return;
-  const uint32_t item = row_item[v];
+  const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  int64_t v = wid;     // by item / by row: see gather_group_queries_kernel
+  uint32_t item;
+  if (item_slot) {
+    if (wid >= n_items) return;
+    item = static_cast<uint32_t>(wid);
+    v = item_slot[wid];
+  } else {
+    if (v >= static_cast<int64_t>(group_off[n_lists])) return;
+    item = row_item[v];
+  }
   uint16_t* orow = out + static_cast<size_t>(v) * dim;
   if (item == kNoRow) {
     // group padding: the row never qualifies (threshold -inf); its operand bytes are don't-care
@@ -1082,22 +1102,36 @@ int launch_seed_select(IvfData* d, int nq, int n_keys, int cap, int k, cudaStrea
   return B2VS_OK;
 }
 
-int launch_gather_group_queries(IvfData* d, int64_t rows_cap, int n_probes, int q_split, cudaStream_t st) {
-  gather_group_queries_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
+// items > 0: the items were sorted by the counting-sort kernels (ws_item_slot holds every item's
+// row): gather by item.  items == 0 (one-CTA planner): walk the rows.
+static int prepare_by_item(IvfData* d, int64_t rows_cap, int items, cudaStream_t st) {
+  if (items > 0)
+    B2VS_CUDA(cudaMemsetAsync(d->ws_g_rowq.ptr, 0xFF, static_cast<size_t>(rows_cap) * sizeof(int), st));
+  return B2VS_OK;
+}
+
+int launch_gather_group_queries(IvfData* d, int64_t rows_cap, int n_probes, int q_split, int items,
+                                cudaStream_t st) {
+  B2VS_TRY(prepare_by_item(d, rows_cap, items, st));
+  const int64_t warps = items > 0 ? items : rows_cap;
+  gather_group_queries_kernel<<<static_cast<unsigned>(ceil_div(warps, 8)), 256, 0, st>>>(
       d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists, d->ws_qf.as<float>(),
       d->dp, n_probes, d->fmt, q_split, d->ws_g_q.as<uint16_t>(), d->ws_g_rowq.as<int>(),
-      d->ws_g_rowslot.as<int>());
+      d->ws_g_rowslot.as<int>(), items > 0 ? d->ws_item_slot.as<uint32_t>() : nullptr, items);
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }
 
 int launch_gather_group_residuals(const b2vs_index* index, IvfData* d, int64_t rows_cap,
-                                  const long long* probe_ids, int n_probes, cudaStream_t st) {
-  gather_group_residuals_kernel<<<static_cast<unsigned>(ceil_div(rows_cap, 8)), 256, 0, st>>>(
+                                  const long long* probe_ids, int n_probes, int items, cudaStream_t st) {
+  B2VS_TRY(prepare_by_item(d, rows_cap, items, st));
+  const int64_t warps = items > 0 ? items : rows_cap;
+  gather_group_residuals_kernel<<<static_cast<unsigned>(ceil_div(warps, 8)), 256, 0, st>>>(
       d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists, probe_ids,
       d->ws_qf.as<float>(), d->centroids.as<float>(), index->dim, d->dp, n_probes,
       index->metric == B2VS_METRIC_L2 ? 1 : 0, d->ws_g_q.as<uint16_t>(), d->ws_g_rowq.as<int>(),
-      d->ws_g_bias.as<float>(), d->ws_g_rowslot.as<int>());
+      d->ws_g_bias.as<float>(), d->ws_g_rowslot.as<int>(),
+      items > 0 ? d->ws_item_slot.as<uint32_t>() : nullptr, items);
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }

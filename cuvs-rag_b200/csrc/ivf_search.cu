@@ -54,7 +54,7 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
   int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
   B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
                              counter, st, row_limit));
-  B2VS_TRY(launch_gather_group_queries(d, rows_cap, n_probes, q_split, st));
+  B2VS_TRY(launch_gather_group_queries(d, rows_cap, n_probes, q_split, plan_is_small(d, items) ? 0 : items, st));
   GroupedScanArgs ga{};
   ga.q_mat = d->ws_g_q.ptr; ga.q_rows = rows_cap;
   ga.x_mat = d->data.ptr; ga.x_rows = d->n_slots;
@@ -261,7 +261,8 @@ static int run_grouped_pq_scan(b2vs_index* index, IvfData* d, const long long* p
   int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
   B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
                              counter, st, row_limit, kDealNone));
-  B2VS_TRY(launch_gather_group_residuals(index, d, rows_cap, probe_ids, n_probes, st));
+  B2VS_TRY(launch_gather_group_residuals(index, d, rows_cap, probe_ids, n_probes,
+                                         plan_is_small(d, items) ? 0 : items, st));
   PqGroupedScanArgs ga{};
   ga.q_mat = d->ws_g_q.ptr; ga.q_rows = rows_cap;
   ga.dim = index->dim; ga.pq_dim = d->pq_dim; ga.dsub = d->dsub;
