@@ -430,6 +430,7 @@ def run_c1(job, args):
     st = ix.last_stats()
     # parity against the CPU oracle (the whole config runs on CPU in < 1 s)
     from oracle.exact import exact_knn, topk_parity_report
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // job.world))   # torchrun pins OMP_NUM_THREADS=1
     _, ti = exact_knn(db, qs, k, "inner_product")
     rep = topk_parity_report(out[0].cpu(), out[1].cpu(), db, qs, k, metric="inner_product")
     rec = recall_at_k(job, out[1], ti.to(job.dev)) if job.world == 1 else \
@@ -541,8 +542,6 @@ def run_c5(job, args):
     ids, rows = planted_rows(job, x, start, n_total, 16, seed=71)
     sweep = {}
     for nq in (1, 64, 1024, 16384):
-        if job.world > nq:      # fewer queries than ranks: slices would be empty
-            continue
         gq = torch.Generator(device=job.dev).manual_seed(4242 + nq)
         q_all = torch.randn((nq, d), generator=gq, device=job.dev).to(torch.bfloat16)
         n_pl = min(nq, 16)
