@@ -77,6 +77,7 @@ EXPORTS = [
     "b2vs_comm_destroy", "b2vs_partition_even", "b2vs_allgather_queries", "b2vs_allgather_topk",
     "b2vs_allgather_merge_topk", "b2vs_exchange_merge_topk", "b2vs_allreduce_min_f32",
     "b2vs_search_sharded", "b2vs_search_sharded_host", "b2vs_comm_register_index",
+    "b2vs_debug_check_canaries",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -191,6 +192,7 @@ def lib() -> ctypes.CDLL:
                                           vp, vp, vp]
         L.b2vs_search_sharded_host.argtypes = L.b2vs_search_sharded.argtypes
         L.b2vs_comm_register_index.argtypes = [vp, vp, vp]
+        L.b2vs_debug_check_canaries.argtypes = [pi32, pi32]
         for name in EXPORTS:
             if name != "b2vs_last_error":
                 getattr(L, name).restype = i32
@@ -511,6 +513,13 @@ def pool_normalize(hidden: torch.Tensor, attention_mask: Optional[torch.Tensor] 
 def reload_env() -> None:
     """Re-read the B2VS_* switches (the library reads them once; tests flip them in-process)."""
     _check(lib().b2vs_reload_env(), "b2vs_reload_env")
+
+
+def check_canaries() -> Tuple[int, int]:
+    """(live device buffers checked, buffers with an overwritten guard zone); needs B2VS_CANARY=1."""
+    n, bad = ctypes.c_int(0), ctypes.c_int(0)
+    _check(lib().b2vs_debug_check_canaries(ctypes.byref(n), ctypes.byref(bad)), "b2vs_debug_check_canaries")
+    return n.value, bad.value
 
 
 def partition_even_native(n: int, n_parts: int, rank: int) -> Tuple[int, int]:

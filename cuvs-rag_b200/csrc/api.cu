@@ -3,8 +3,10 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
+#include <vector>
 
 #include "common.h"
 #include "ivf.h"
@@ -60,6 +62,7 @@ static EnvConfig read_env() {
   c.no_item_sort = std::getenv("B2VS_NO_ITEM_SORT") != nullptr;
   if (const char* e = std::getenv("B2VS_GRAPH")) c.graph = e[0] == '0' ? 0 : 1;
   if (const char* e = std::getenv("B2VS_IVF_SEED")) c.seed_mode = e[0] == '0' ? 0 : 1;
+  if (const char* e = std::getenv("B2VS_CANARY")) c.canary = e[0] == '1';
   return c;
 }
 static EnvConfig g_env;
@@ -68,6 +71,25 @@ static std::mutex g_env_mutex;
 const EnvConfig& env() {
   std::call_once(g_env_once, [] { g_env = read_env(); });
   return g_env;
+}
+
+// ---- guard-zone registry (B2VS_CANARY=1) -------------------------------------------------------
+static std::mutex g_canary_mutex;
+static std::map<void*, size_t>& canary_map() {
+  static std::map<void*, size_t> m;
+  return m;
+}
+bool canary_enabled() {
+  static const bool on = [] { const char* e = std::getenv("B2VS_CANARY"); return e && e[0] == '1'; }();
+  return on;   // fixed for the life of the process: allocations and frees must agree on the layout
+}
+void canary_register(void* user_ptr, size_t bytes) {
+  std::lock_guard<std::mutex> lock(g_canary_mutex);
+  canary_map()[user_ptr] = bytes;
+}
+void canary_unregister(void* user_ptr) {
+  std::lock_guard<std::mutex> lock(g_canary_mutex);
+  canary_map().erase(user_ptr);
 }
 
 static bool valid_dtype(int d) { return d == B2VS_F32 || d == B2VS_F16 || d == B2VS_BF16; }
@@ -108,6 +130,37 @@ extern "C" int b2vs_reload_env(void) {
   env();  // make sure the once-flag is spent before overwriting
   std::lock_guard<std::mutex> lock(g_env_mutex);
   g_env = read_env();
+  return B2VS_OK;
+}
+
+extern "C" int b2vs_debug_check_canaries(int* n_buffers, int* n_corrupt) {
+  B2VS_CHECK(n_buffers && n_corrupt, B2VS_EINVAL, "NULL argument");
+  *n_buffers = 0;
+  *n_corrupt = 0;
+  B2VS_CHECK(canary_enabled(), B2VS_EUNSUP, "guard zones are off: start the process with B2VS_CANARY=1");
+  std::lock_guard<std::mutex> lock(g_canary_mutex);
+  std::vector<unsigned char> host(2 * kCanaryBytes);
+  for (const auto& kv : canary_map()) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, kv.first) != cudaSuccess) { cudaGetLastError(); continue; }
+    DeviceGuard guard(attr.device);
+    cudaDeviceSynchronize();
+    char* user = static_cast<char*>(kv.first);
+    if (cudaMemcpy(host.data(), user - kCanaryBytes, kCanaryBytes, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(host.data() + kCanaryBytes, user + kv.second, kCanaryBytes, cudaMemcpyDeviceToHost) !=
+            cudaSuccess) {
+      cudaGetLastError();
+      ++*n_corrupt;
+      continue;
+    }
+    ++*n_buffers;
+    bool bad = false;
+    for (unsigned char b : host) bad = bad || b != 0xA5;
+    if (bad) {
+      ++*n_corrupt;
+      set_error("guard zone of a %zu-byte device buffer at %p was overwritten", kv.second, kv.first);
+    }
+  }
   return B2VS_OK;
 }
 

@@ -57,6 +57,16 @@ struct DeviceGuard {
 uint64_t realloc_generation();
 void note_realloc();
 
+// Bounds checking of our own (compute-sanitizer is not available on the GPU pool): with
+// B2VS_CANARY=1 every DevBuf allocation is wrapped in two 256-byte guard zones filled with a
+// pattern, all live allocations are registered, and b2vs_debug_check_canaries() reads the guards
+// back - any kernel that wrote just before or past one of the library's device buffers is caught
+// (tests/test_gpu_canary.py runs every search path under it).
+constexpr size_t kCanaryBytes = 256;
+bool canary_enabled();
+void canary_register(void* user_ptr, size_t bytes);
+void canary_unregister(void* user_ptr);
+
 // Growable device buffer (grow-only; steady-state searches allocate nothing).
 struct DevBuf {
   void* ptr = nullptr;
@@ -64,13 +74,15 @@ struct DevBuf {
   int reserve(size_t need) {
     if (need <= bytes) return B2VS_OK;
     note_realloc();
-    if (ptr) { cudaFree(ptr); ptr = nullptr; bytes = 0; }
-    size_t want = need + need / 8;
-    cudaError_t e = cudaMalloc(&ptr, want);
+    release_raw();
+    const size_t guard = canary_enabled() ? kCanaryBytes : 0;
+    size_t want = (need + need / 8 + 255) & ~static_cast<size_t>(255);
+    void* raw = nullptr;
+    cudaError_t e = cudaMalloc(&raw, want + 2 * guard);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      e = cudaMalloc(&ptr, need);
-      want = need;
+      want = (need + 255) & ~static_cast<size_t>(255);
+      e = cudaMalloc(&raw, want + 2 * guard);
     }
     if (e != cudaSuccess) {
       cudaGetLastError();
@@ -78,13 +90,26 @@ struct DevBuf {
       ptr = nullptr;
       return B2VS_ENOMEM;
     }
+    ptr = static_cast<char*>(raw) + guard;
     bytes = want;
+    if (guard) {
+      cudaMemset(raw, 0xA5, guard);
+      cudaMemset(static_cast<char*>(ptr) + want, 0xA5, guard);
+      canary_register(ptr, want);
+    }
     return B2VS_OK;
   }
-  void release() {
-    if (ptr) { note_realloc(); cudaFree(ptr); }
+  void release_raw() {
+    if (!ptr) return;
+    const size_t guard = canary_enabled() ? kCanaryBytes : 0;
+    if (guard) canary_unregister(ptr);
+    cudaFree(static_cast<char*>(ptr) - guard);
     ptr = nullptr;
     bytes = 0;
+  }
+  void release() {
+    if (ptr) note_realloc();
+    release_raw();
   }
   template <class T> T* as() const { return reinterpret_cast<T*>(ptr); }
 };
@@ -115,6 +140,7 @@ struct EnvConfig {
   bool no_item_sort = false;   // B2VS_NO_ITEM_SORT: per-item scan without the list ordering
   int graph = -1;              // B2VS_GRAPH=0|1: never / always replay small IVF batches as a graph
   int seed_mode = -1;          // B2VS_IVF_SEED=0|1: legacy seed kernels / seeds from the tensor-core pass
+  bool canary = false;         // B2VS_CANARY=1: guard zones around every device buffer (read ONCE, at first use)
 };
 const EnvConfig& env();
 

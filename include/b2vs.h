@@ -117,6 +117,11 @@ int b2vs_device_count(int* count);
 /* Re-reads the B2VS_* environment switches (A/B knobs; they are otherwise read once, at first
  * use, so nothing on the search path calls getenv).  For tests and measurement tools. */
 int b2vs_reload_env(void);
+/* Own bounds checking (compute-sanitizer is unavailable on the GPU pool): in a process started
+ * with B2VS_CANARY=1 every device buffer the library allocates sits between two 256-byte guard
+ * zones; this call reads all of them back: *n_buffers = live buffers checked, *n_corrupt = buffers
+ * whose guards were overwritten (b2vs_last_error names one).  B2VS_EUNSUP when the mode is off. */
+int b2vs_debug_check_canaries(int* n_buffers, int* n_corrupt);
 
 /* Exact (brute-force) index over `db` ([n, dim], `dtype`) resident on device `dev`.
  * 16-bit databases with dim % 8 == 0 are BORROWED (the caller keeps them alive); fp32
