@@ -95,6 +95,7 @@ struct IvfData {
   DevBuf ws_probe_d, ws_probe_i, ws_keys, ws_qf, ws_qnorm, ws_counter, ws_ref_d, ws_ref_i;
   DevBuf ws_item_lab, ws_item_cnt, ws_item_off, ws_item_perm, ws_item_slot;  // list-ordered scan items
   DevBuf ws_g_work, ws_g_q, ws_g_rowq, ws_g_tau, ws_g_cand, ws_g_cnt, ws_g_bias;  // grouped scan
+  DevBuf ws_over, ws_rescue;   // overflow queue of the select kernel; sliced rescue lists
   DevBuf ws_g_rowslot;  // [gathered rows] probe rank of each row inside its query
   DevBuf ws_seed_ids;   // [nq, m] the nearest probes of every query (tensor-core seed pass)
   const void* src_rows = nullptr;  // IVF-PQ: the caller's [n, dim] rows, BORROWED for refine
@@ -132,7 +133,7 @@ struct IvfData {
                       &ws_probe_d, &ws_probe_i, &ws_keys, &ws_qf, &ws_qnorm, &ws_counter,
                       &ws_ref_d, &ws_ref_i, &ws_item_lab, &ws_item_cnt, &ws_item_off, &ws_item_perm,
                       &ws_item_slot, &ws_g_work, &ws_g_q, &ws_g_rowq, &ws_g_tau, &ws_g_cand, &ws_g_cnt,
-                      &ws_g_bias, &ws_g_rowslot, &ws_seed_ids, &cb16, &cb16t, &cbn, &pq_norm, &cq_offsets, &cq_probe, &ws_cq_keys})
+                      &ws_g_bias, &ws_g_rowslot, &ws_seed_ids, &ws_over, &ws_rescue, &cb16, &cb16t, &cbn, &pq_norm, &cq_offsets, &cq_probe, &ws_cq_keys})
       b->release();
   }
 };

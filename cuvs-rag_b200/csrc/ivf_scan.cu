@@ -321,13 +321,17 @@ __global__ void gather_group_queries_kernel(const uint32_t* __restrict__ row_ite
 constexpr int kSelectThreads = 128;
 __global__ void __launch_bounds__(kSelectThreads)
 ivf_group_select_kernel(const u64* __restrict__ cand, const int* __restrict__ count, int cap, int k, int nq,
-                        u64* __restrict__ out_keys, unsigned long long* __restrict__ total_cand) {
+                        u64* __restrict__ out_keys, unsigned long long* __restrict__ total_cand,
+                        int* __restrict__ over) {
   const int lane = threadIdx.x & 31;
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= nq) return;
   const int n = count[q];
   if (lane == 0 && total_cand) atomicAdd(total_cand, static_cast<unsigned long long>(n));
-  if (n > cap) return;  // overflow: left to the rescue kernel
+  if (n > cap) {   // overflow: queued for the rescue kernels (over[0] = how many, over[1..] = which)
+    if (lane == 0) over[1 + atomicAdd(over, 1)] = q;
+    return;
+  }
   const u64* src = cand + static_cast<size_t>(q) * cap;
   WarpTopK tk;
   tk.init();
@@ -377,28 +381,62 @@ ivf_seed_select_kernel(const u64* __restrict__ cand, int n_keys, int cap, int k,
   if (lane == 0) tau[q] = isinf(tk.tau) ? tk.tau : nextafterf(tk.tau, INFINITY);
 }
 
-// One CTA per query whose candidate buffer overflowed: exact scan of all its probes.
+// Rescue of the queries whose candidate buffer overflowed (threshold too loose for their
+// neighbourhood): an exact scan of all their probes.  The select kernel queued them; every queued
+// query is cut into kRescueSlices probe slices, one CTA each (a single CTA per query streamed
+// n_probes whole lists - 240 MB at 64 probes of C3 - and ONE overflowing query cost the batch
+// 5 ms), and a one-warp merge folds the slices' sorted lists.
+constexpr int kRescueSlices = 8;
+constexpr int kRescueCtas = 512;
 template <int FMT, int J>
 __global__ void __launch_bounds__(kScanThreads, 2)
 ivf_flat_rescue_kernel(const uint16_t* __restrict__ data, const float* __restrict__ slot_norm,
                        const uint32_t* __restrict__ offsets, const long long* __restrict__ probe_ids,
                        const float* __restrict__ qf, int dp, int n_probes, int k, float alpha,
-                       const int* __restrict__ count, int cap, u64* __restrict__ out_keys) {
+                       const int* __restrict__ over, u64* __restrict__ slice_keys) {
   __shared__ u64 lists[kScanWarps][32 * kListE];
-  const int q = blockIdx.x;
-  if (count[q] <= cap) return;
+  const int n_over = over[0];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float qr[J][8];
-  load_query_regs<J>(qf, q, dp, lane, qr);
-  WarpTopK tk;
-  tk.init();
-  for (int p = 0; p < n_probes; ++p) {
-    const long long list = probe_ids[static_cast<size_t>(q) * n_probes + p];
-    if (list < 0) continue;
-    scan_list_rows<FMT, J>(reinterpret_cast<const uint4*>(data), slot_norm, offsets[list],
-                           offsets[list + 1], qr, dp >> 3, alpha, tk, k, warp, lane);
+  for (int i = blockIdx.x; i < n_over; i += gridDim.x) {
+    const int q = over[1 + i];
+    float qr[J][8];
+    load_query_regs<J>(qf, q, dp, lane, qr);
+    WarpTopK tk;
+    tk.init();
+    for (int p = blockIdx.y; p < n_probes; p += kRescueSlices) {
+      const long long list = probe_ids[static_cast<size_t>(q) * n_probes + p];
+      if (list < 0) continue;
+      scan_list_rows<FMT, J>(reinterpret_cast<const uint4*>(data), slot_norm, offsets[list],
+                             offsets[list + 1], qr, dp >> 3, alpha, tk, k, warp, lane);
+    }
+    block_merge_and_store(tk, lists, k, warp, lane,
+                          slice_keys + (static_cast<size_t>(i) * kRescueSlices + blockIdx.y) * k);
+    __syncthreads();   // `lists` is reused by the next queued query
   }
-  block_merge_and_store(tk, lists, k, warp, lane, out_keys + static_cast<size_t>(q) * k);
+}
+
+// Folds the kRescueSlices sorted lists of every rescued query into its k answer keys (one warp each).
+__global__ void __launch_bounds__(32)
+ivf_rescue_merge_kernel(const int* __restrict__ over, const u64* __restrict__ slice_keys, int k,
+                        u64* __restrict__ out_keys) {
+  const int lane = threadIdx.x;
+  const int n_over = over[0];
+  for (int i = blockIdx.x; i < n_over; i += gridDim.x) {
+    const int q = over[1 + i];
+    const u64* src = slice_keys + static_cast<size_t>(i) * kRescueSlices * k;
+    WarpTopK tk;
+    tk.init();
+    for (int j0 = 0; j0 < kRescueSlices * k; j0 += 32) {
+      const int j = j0 + lane;
+      const u64 v = j < kRescueSlices * k ? __ldcg(src + j) : kKeyInf;
+      tk.offer((v != kKeyInf && key_score(v) <= tk.tau) ? v : kKeyInf, k, lane);
+    }
+#pragma unroll
+    for (int e = 0; e < kListE; ++e) {
+      const int idx = lane * kListE + e;
+      if (idx < k) out_keys[static_cast<size_t>(q) * k + idx] = tk.acc[e];
+    }
+  }
 }
 
 // One CTA per (query, probe): build the [pq_dim][256] LUT in smem, then every lane scores one
@@ -813,16 +851,25 @@ ivf_pq_lut_scan_kernel(int mode, const uint8_t* __restrict__ codes, const uint32
   __shared__ u64 top[kMaxFusedK];
   __shared__ float red[kScanWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = (mode == 0 && q_perm) ? static_cast<int>(q_perm[blockIdx.x]) : blockIdx.x;
-  if (mode == 1 && count[q] <= cap) return;
+  // mode 1: `count` is the overflow queue of the select kernel (count[0] = how many, count[1..] =
+  // which queries); CTA (x, y) takes the queued queries x, x + gridDim.x, ... and of each the probe
+  // slice y, y + kRescueSlices, ... -> out_keys[(queue position * kRescueSlices + y) * k]
+  int i_over = blockIdx.x;
+  const int n_over = mode == 1 ? count[0] : 0;
   const int l2 = metric == B2VS_METRIC_L2;
+  const int n_chunks = pq_dim >> 4;
+  const int mp = pq_dim;   // the grouped scan requires pq_dim % 16 == 0
+  const int np = mode == 0 ? 1 : n_probes;
+  const int p_first = mode == 0 ? 0 : static_cast<int>(blockIdx.y);
+  const int p_step = mode == 0 ? 1 : kRescueSlices;
+rescue_next:
+  if (mode == 1 && i_over >= n_over) return;
+  const int q = mode == 1 ? count[1 + i_over]
+                          : (q_perm ? static_cast<int>(q_perm[blockIdx.x]) : static_cast<int>(blockIdx.x));
   WarpTopK tk;
   tk.init();
   float bias_first = 0.f;
-  const int np = mode == 0 ? 1 : n_probes;
-  const int n_chunks = pq_dim >> 4;
-  const int mp = pq_dim;   // the grouped scan requires pq_dim % 16 == 0
-  for (int p = 0; p < np; ++p) {
+  for (int p = p_first; p < np; p += p_step) {
     const long long list = probe_ids[static_cast<size_t>(q) * n_probes + p];
     if (list < 0) continue;
     __syncthreads();   // previous probe's LUT no longer in use
@@ -847,7 +894,7 @@ ivf_pq_lut_scan_kernel(int mode, const uint8_t* __restrict__ codes, const uint32
 #pragma unroll
     for (int w = 0; w < kScanWarps; ++w) tot += red[w];
     const float bias = l2 ? tot : -tot;
-    if (p == 0) bias_first = bias;
+    if (p == p_first) bias_first = bias;
     // one entry per thread per step; unrolled so several L2 loads are in flight per thread
     if (dsub == 2) {
       const uint32_t* cbw = reinterpret_cast<const uint32_t*>(cb16);
@@ -888,8 +935,11 @@ ivf_pq_lut_scan_kernel(int mode, const uint8_t* __restrict__ codes, const uint32
     }
   }
   if (mode == 1) {
-    block_merge_and_store(tk, lists, k, warp, lane, out_keys + static_cast<size_t>(q) * k);
-    return;
+    block_merge_and_store(tk, lists, k, warp, lane,
+                          out_keys + (static_cast<size_t>(i_over) * kRescueSlices + blockIdx.y) * k);
+    __syncthreads();   // lists / lut / rq are reused by the next queued query
+    i_over += gridDim.x;
+    goto rescue_next;
   }
   block_merge_and_store(tk, lists, k, warp, lane, top);
   __syncthreads();
@@ -967,6 +1017,7 @@ __global__ void gather_group_residuals_kernel(const uint32_t* __restrict__ row_i
 }
 
 // Instantiation table of the <FMT, J> scan kernels: J = 16-byte chunks of a row owned by a lane.
+// (grid may be an int or a dim3)
 #define FLAT_SCAN_DISPATCH(KERNEL, fmt, j, grid, st, ...)                                    \
   do {                                                                                       \
     if ((fmt) == 0) {                                                                        \
@@ -1076,21 +1127,35 @@ int launch_flat_seed_tau(const b2vs_index* index, IvfData* d, const long long* p
   return B2VS_OK;
 }
 
-int launch_flat_rescue(const b2vs_index* index, IvfData* d, const long long* probe_ids, int n_probes,
-                       int nq, int k, int cap, cudaStream_t st) {
-  const int j = static_cast<int>(ceil_div(d->dp / 8, 32));
-  const float alpha = index->metric == B2VS_METRIC_L2 ? -2.f : -1.f;
-  FLAT_SCAN_DISPATCH(ivf_flat_rescue_kernel, d->fmt, j, nq, st, d->data.as<uint16_t>(),
-                     d->slot_norm.as<float>(), d->offsets.as<uint32_t>(), probe_ids,
-                     d->ws_qf.as<float>(), d->dp, n_probes, k, alpha, d->ws_g_cnt.as<int>(), cap,
-                     d->ws_keys.as<u64>());
+static int launch_rescue_merge(IvfData* d, int nq, int k, cudaStream_t st) {
+  ivf_rescue_merge_kernel<<<std::min(nq, kRescueCtas), 32, 0, st>>>(d->ws_over.as<int>(), d->ws_rescue.as<u64>(), k,
+                                                                   d->ws_keys.as<u64>());
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }
 
+int launch_flat_rescue(const b2vs_index* index, IvfData* d, const long long* probe_ids, int n_probes,
+                       int nq, int k, int cap, cudaStream_t st) {
+  (void)cap;
+  const int j = static_cast<int>(ceil_div(d->dp / 8, 32));
+  const float alpha = index->metric == B2VS_METRIC_L2 ? -2.f : -1.f;
+  B2VS_TRY(d->ws_rescue.reserve(static_cast<size_t>(nq) * kRescueSlices * k * sizeof(u64)));
+  const dim3 grid(static_cast<unsigned>(std::min(nq, kRescueCtas)), kRescueSlices);
+  FLAT_SCAN_DISPATCH(ivf_flat_rescue_kernel, d->fmt, j, grid, st, d->data.as<uint16_t>(),
+                     d->slot_norm.as<float>(), d->offsets.as<uint32_t>(), probe_ids,
+                     d->ws_qf.as<float>(), d->dp, n_probes, k, alpha, d->ws_over.as<int>(),
+                     d->ws_rescue.as<u64>());
+  B2VS_CUDA(cudaGetLastError());
+  return launch_rescue_merge(d, nq, k, st);
+}
+
 int launch_group_select(IvfData* d, int nq, int cap, int k, unsigned long long* total_cand, cudaStream_t st) {
+  // the overflow queue: [0] = count, [1 .. nq] = query ids
+  B2VS_TRY(d->ws_over.reserve((static_cast<size_t>(nq) + 1) * sizeof(int)));
+  B2VS_CUDA(cudaMemsetAsync(d->ws_over.ptr, 0, sizeof(int), st));
   ivf_group_select_kernel<<<static_cast<unsigned>(ceil_div(nq, kSelectThreads / 32)), kSelectThreads, 0, st>>>(
-      d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), cap, k, nq, d->ws_keys.as<u64>(), total_cand);
+      d->ws_g_cand.as<u64>(), d->ws_g_cnt.as<int>(), cap, k, nq, d->ws_keys.as<u64>(), total_cand,
+      d->ws_over.as<int>());
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }
@@ -1142,13 +1207,19 @@ int launch_pq_lut_scan(int mode, const b2vs_index* index, IvfData* d, const long
   const size_t lut_smem = (static_cast<size_t>(d->pq_dim) * 256 + index->dim) * sizeof(float);
   B2VS_CUDA(cudaFuncSetAttribute(ivf_pq_lut_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(lut_smem)));
-  ivf_pq_lut_scan_kernel<<<nq, kScanThreads, lut_smem, st>>>(
+  dim3 grid(static_cast<unsigned>(nq));
+  if (mode == 1) {   // rescue: queued queries x probe slices (see ivf_flat_rescue_kernel)
+    B2VS_TRY(d->ws_rescue.reserve(static_cast<size_t>(nq) * kRescueSlices * k * sizeof(u64)));
+    grid = dim3(static_cast<unsigned>(std::min(nq, kRescueCtas)), kRescueSlices);
+  }
+  ivf_pq_lut_scan_kernel<<<grid, kScanThreads, lut_smem, st>>>(
       mode, d->codes.as<uint8_t>(), d->row_ids.as<uint32_t>(), d->offsets.as<uint32_t>(), probe_ids,
       d->ws_qf.as<float>(), d->centroids.as<float>(), d->cb16.as<uint16_t>(), d->cbn.as<float>(),
       index->dim, d->dp, d->pq_dim, d->dsub, n_probes, k, index->metric, mode == 0 ? seed_rows : 0u,
-      d->max_rhat2, mode == 0 ? q_perm : nullptr, mode == 0 ? nullptr : d->ws_g_cnt.as<int>(), cap,
-      mode == 0 ? d->ws_g_tau.as<float>() : nullptr, mode == 0 ? nullptr : d->ws_keys.as<u64>());
+      d->max_rhat2, mode == 0 ? q_perm : nullptr, mode == 0 ? nullptr : d->ws_over.as<int>(), cap,
+      mode == 0 ? d->ws_g_tau.as<float>() : nullptr, mode == 0 ? nullptr : d->ws_rescue.as<u64>());
   B2VS_CUDA(cudaGetLastError());
+  if (mode == 1) return launch_rescue_merge(d, nq, k, st);
   return B2VS_OK;
 }
 

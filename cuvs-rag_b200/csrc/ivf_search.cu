@@ -16,7 +16,9 @@ constexpr size_t kCounterBytes = 4 * sizeof(unsigned long long);
 // B2VS_IVF_GROUPED_CAP shrinks the buffers so tests can drive the overflow-rescue path.
 static int grouped_cap(int k) {
   if (env().grouped_cap > 0) return env().grouped_cap;
-  return k <= 32 ? 2048 : 4096;
+  (void)k;
+  return 4096;   // 32 KB per query: the tail of the candidate-count distribution (5-10x the mean on
+                 // structureless data) stays inside it; overflowing queries go to the sliced rescue
 }
 static uint32_t grouped_seed_rows(int k) {
   if (env().seed_rows > 0) return static_cast<uint32_t>(env().seed_rows);  // A/B knob
@@ -72,15 +74,17 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
 }
 
 // Thresholds from a tensor-core SEED PASS (batches of kTcSeedMinQueries queries and more): the
-// first kSeedTileRows rows of each query's m nearest lists are scored by the same grouped kernel
-// with no threshold - every score lands in a FIXED slot of the query's buffer (m * 256 <= cap / 4
-// keys, no atomics) - and the k-th best of them becomes the query's threshold for the full pass.  Against the CUDA-core seed kernels (one CTA per query over
+// first kSeedTileRows rows of each query's m nearest lists (m = 2 for k <= 32, else 4) are scored by
+// the same grouped kernel with no threshold - every score lands in a FIXED slot of the query's
+// buffer, no atomics - and the k-th best of them becomes the query's threshold for the full pass.  Against the CUDA-core seed kernels (one CTA per query over
 // the nearest list only) the sample is m times larger - on corpora without cluster structure the
 // nearest list's head alone leaves thousands of candidates per query, overflowing the buffers
 // into the exact rescue scan - it runs on the tensor cores, and it uses the full pass's own
 // arithmetic, so the threshold carries no rounding cushion.
-static int seed_lists(int n_probes, int cap) {
-  return std::max(1, std::min(n_probes, cap / 4 / kSeedTileRows));
+static int seed_lists(int n_probes, int cap, int k) {
+  // two lists (512 sampled rows) for k <= 32, four for larger k; never more than a quarter of the buffer
+  const int want = k <= 32 ? 2 : 4;
+  return std::max(1, std::min(std::min(n_probes, want), cap / 4 / kSeedTileRows));
 }
 static bool use_tc_seed(int nq, int cap) {
   if (cap < 4 * kSeedTileRows) return false;   // shrunken test buffers cannot hold a seed tile
@@ -90,7 +94,7 @@ static bool use_tc_seed(int nq, int cap) {
 template <typename ScanFn>
 static int run_tc_seed(IvfData* d, const long long* probe_ids, int n_probes, int nq, int k, int cap,
                        cudaStream_t st, ScanFn scan) {
-  const int m = seed_lists(n_probes, cap);
+  const int m = seed_lists(n_probes, cap, k);
   B2VS_TRY(d->ws_seed_ids.reserve(static_cast<size_t>(nq) * m * sizeof(int64_t)));
   B2VS_CUDA(cudaMemcpy2DAsync(d->ws_seed_ids.ptr, static_cast<size_t>(m) * sizeof(int64_t), probe_ids,
                               static_cast<size_t>(n_probes) * sizeof(int64_t),

@@ -10,11 +10,14 @@ import bench
 name = sys.argv[1] if len(sys.argv) > 1 else "C3"
 latent = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 scale = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
+npb_override = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 dev = torch.device("cuda:0")
 if name == "C3":
     n, d, nl, npb, rr = int(10_000_000 * scale), 768, 4096, 32, 0
 else:
     n, d, nl, npb, rr = int(12_500_000 * scale), 128, 16384, 64, 4
+if npb_override:
+    npb = npb_override
 x = bench.ivf_corpus(n, d, latent, torch.float16, dev, seed=5000)
 q = bench.ivf_corpus(10_000, d, latent, torch.float16, dev, seed=99)
 ix = b2.NativeIndex.ivf_flat(x, nl, kmeans_iters=20) if name == "C3" else b2.NativeIndex.ivf_pq(x, nl, 64, kmeans_iters=20)
