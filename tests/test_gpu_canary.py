@@ -18,6 +18,7 @@ def test_no_kernel_writes_outside_the_library_buffers():
     env = dict(os.environ, B2VS_CANARY="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_canary_worker.py")], env=env,
                        capture_output=True, text=True, timeout=900)
+    print(r.stdout)     # the per-stage guard-zone reports (pytest -s shows them; kept in profiles/)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     assert "CANARY_OK" in r.stdout and "corrupt" in r.stdout
     assert ", 0 corrupt" in r.stdout.splitlines()[-2]
