@@ -63,6 +63,7 @@ static EnvConfig read_env() {
   if (const char* e = std::getenv("B2VS_GRAPH")) c.graph = e[0] == '0' ? 0 : 1;
   if (const char* e = std::getenv("B2VS_IVF_SEED")) c.seed_mode = e[0] == '0' ? 0 : 1;
   if (const char* e = std::getenv("B2VS_CANARY")) c.canary = e[0] == '1';
+  if (const char* e = std::getenv("B2VS_EPI_GROUPS")) c.epi_groups = (e[0] == '1' || e[0] == '2') ? e[0] - '0' : 0;
   return c;
 }
 static EnvConfig g_env;

@@ -44,25 +44,22 @@ constexpr int kBN = 256;   // db rows per tile (TMEM columns)
 constexpr int kBK = B2VS_BK;
 static_assert(kBK == 64 || kBK == 32, "kBK must be 64 or 32");
 constexpr int kNormBytes = kBN * 4;
-// Epilogue warp groups (compile-time A/B switch, default 1).  With 2 groups (warps 4-7 and 8-11)
-// each group owns one of the two TMEM accumulator buffers, i.e. every other tile, with its own
-// per-row candidate state; an item then leaves one sorted list per group and the split merge
-// folds them.  Measured at C2 on the same box, 15 sustained steps: 2 groups 72.0 K QPS at
-// ~1.2 GHz, 1 group 73.6-74.3 K QPS at ~1.33 GHz - the kernel is power-capped, and the extra
-// warps cost more clock than the shorter accumulator hand-off wins back.
-#ifndef B2VS_EPI_GROUPS
-#define B2VS_EPI_GROUPS 1
-#endif
-constexpr int kEpiGroups = B2VS_EPI_GROUPS;
-static_assert(kEpiGroups == 1 || kEpiGroups == 2, "kEpiGroups");
-constexpr int kTcThreads = 128 + 128 * kEpiGroups;
-
+// Epilogue warp groups: template parameter E of the kernel.  With E = 2 (warps 4-7 and 8-11) each
+// group owns one of the two TMEM accumulator buffers, i.e. every other tile, with its own per-row
+// candidate state; an item then leaves one sorted list per group and the split merge folds them.
+//  * E = 1 for the long database passes: measured at C2 on the same box, 15 sustained steps,
+//    2 groups 72.0 K QPS at ~1.2 GHz vs 1 group 73.6-74.3 K QPS at ~1.33 GHz - that kernel is
+//    power-capped, and the extra warps cost more clock than the shorter accumulator hand-off wins;
+//  * E = 2 for SMALL matrices with a large k - the coarse probes of the IVF indexes (top-64 of
+//    16 384 centroids at C4: 79 CTAs, four epilogue warps each, do ~420 insertions and two 256-key
+//    sorts per query row while the tensor pipe is 5 % busy): the epilogue is the whole kernel there.
+constexpr int kMaxEpiGroups = 2;
 // Work-table (grouped scan) epilogue: hits are staged in a small per-warp shared-memory queue and
 // appended to the queries' global buffers in batches (one atomic round trip per batch instead of
 // one per 32-column chunk on the epilogue's critical path).
 constexpr int kQueueCap = 96;                                 // entries per epilogue warp
 constexpr int kQueueWarpBytes = kQueueCap * (8 + 4);          // keys (u64) + query slots (int)
-constexpr int kQueueBytes = 4 * kEpiGroups * kQueueWarpBytes;
+constexpr int kQueueBytes = 4 * kQueueWarpBytes;              // work mode runs one epilogue group
 
 template <int G> struct TcCfg {
   static constexpr int kBRows = kBN / G;                     // db rows staged by one CTA
@@ -75,8 +72,8 @@ template <int G> struct TcCfg {
 
 struct BfTcParams {
   const float* beta;    // [tiles_total*256] per db row additive term (||x||^2, 0, +inf on padding)
-  u64* cand;            // [grid][kEpiGroups][128][kCap] candidate buffers
-  u64* out_keys;        // [n_splits * kEpiGroups][q_pad][k] sorted ascending, kKeyInf padded
+  u64* cand;            // [grid][E][128][kCap] candidate buffers (E = epilogue groups)
+  u64* out_keys;        // [n_splits * E][q_pad][k] sorted ascending, kKeyInf padded
   int n_qblocks;        // ceil(nq / (128*G))
   int q_pad;            // n_qblocks * 128 * G
   int nq;               // real query rows; rows >= nq are padding and never collect candidates
@@ -311,11 +308,15 @@ __device__ __forceinline__ void score_chunk_seed(const uint32_t (&r)[32], const 
   }
 }
 
-template <int G, bool kWork = false>
-__global__ void __launch_bounds__(kTcThreads, 1)
+constexpr int tc_threads(int epi_groups) { return 128 + 128 * epi_groups; }
+
+template <int G, bool kWork = false, int E = 1>
+__global__ void __launch_bounds__(tc_threads(E), 1)
 bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
              const BfTcParams p) {
-  static_assert(!kWork || G == 1, "work-table mode is single-CTA");
+  static_assert(!kWork || (G == 1 && E == 1), "work-table mode is single-CTA, one epilogue group");
+  static_assert(E == 1 || E == 2, "epilogue groups");
+  constexpr int kEpiGroups = E;
   using Cfg = TcCfg<G>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kStageBytes = Cfg::kStageBytes;

@@ -140,6 +140,7 @@ struct EnvConfig {
   bool no_item_sort = false;   // B2VS_NO_ITEM_SORT: per-item scan without the list ordering
   int graph = -1;              // B2VS_GRAPH=0|1: never / always replay small IVF batches as a graph
   int seed_mode = -1;          // B2VS_IVF_SEED=0|1: legacy seed kernels / seeds from the tensor-core pass
+  int epi_groups = 0;          // B2VS_EPI_GROUPS=1|2: epilogue warp groups of the flat kernel (0 = heuristic)
   bool canary = false;         // B2VS_CANARY=1: guard zones around every device buffer (read ONCE, at first use)
 };
 const EnvConfig& env();
@@ -192,7 +193,7 @@ struct FlatEngine {
              float* out_d, int64_t* out_i, int32_t* out_label, cudaStream_t st, int flags = 0,
              const TauExchange* tau_exchange = nullptr);
   int launch_fused(int group, int grid, const CUtensorMap& tm_q, const BfTcParams& p,
-                   cudaStream_t st) const;
+                   cudaStream_t st, int epi_groups = 1) const;
   void resolve_timing();  // fills stats.kernel_ms once the timed launch has finished
   // 128 < k <= 2048 (bigk.cu): append-mode passes + per-query radix select
   int search_bigk(const void* q_mat, int nq, int q_pad, int group, int k, int64_t id_offset,

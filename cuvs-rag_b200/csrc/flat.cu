@@ -281,17 +281,21 @@ static int choose_splits(int n_qblocks, int64_t tiles, int sms, int k, bool seed
 // One launch of the fused distance + top-k kernel over this engine's matrix: the single-CTA
 // variant, or CTA pairs (cluster of 2, each CTA staging half of every db tile).
 int FlatEngine::launch_fused(int group, int grid, const CUtensorMap& tm_q, const BfTcParams& p,
-                             cudaStream_t st) const {
-  if (group == 1) {
+                             cudaStream_t st, int epi_groups) const {
+  if (group == 1 && epi_groups == 2) {
+    B2VS_CUDA(cudaFuncSetAttribute((bf_tc_kernel<1, false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TcCfg<1>::kSmemBytes));
+    bf_tc_kernel<1, false, 2><<<grid, tc_threads(2), TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_x, p);
+  } else if (group == 1) {
     B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TcCfg<1>::kSmemBytes));
-    bf_tc_kernel<1><<<grid, kTcThreads, TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_x, p);
+    bf_tc_kernel<1><<<grid, tc_threads(1), TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_x, p);
   } else {
     B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TcCfg<2>::kSmemBytes));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kTcThreads);
+    cfg.blockDim = dim3(tc_threads(1));
     cfg.dynamicSmemBytes = TcCfg<2>::kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -344,6 +348,15 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
     group = (k <= kPairMaxK && (nq >= 4096 || (nq > kBM && nq <= 2 * kBM))) ? 2 : kDefaultTcGroup;
   if (flags & B2VS_FLAG_TC_SINGLE) group = 1;
   if (flags & B2VS_FLAG_TC_PAIR) group = 2;
+  // Small matrix + sizeable k (the coarse probes of the IVF indexes): the epilogue's selection work
+  // is the whole kernel, so run it with TWO epilogue warp groups on the single-CTA kernel (which
+  // also fills more SMs than 256-row pair blocks do).  B2VS_EPI_GROUPS=1|2 / B2VS_FLAG_EPI2 force it.
+  const int64_t tiles_all = ceil_div(n, kBN);
+  int epi_groups = (k >= 8 && k <= kMaxFusedK && tiles_all <= 256 && nq >= 256) ? 2 : 1;
+  if (env().epi_groups > 0) epi_groups = env().epi_groups;
+  if (flags & B2VS_FLAG_EPI2) epi_groups = 2;
+  if (k == 1 || k > kMaxFusedK || (flags & B2VS_FLAG_TC_PAIR) || tc_group_override() == 2) epi_groups = 1;
+  if (epi_groups == 2) group = 1;
   const int qrows = kBM * group;
   const int n_qblocks = static_cast<int>(ceil_div(nq, qrows));
   const int q_pad = n_qblocks * qrows;
@@ -429,8 +442,8 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
     n_splits = static_cast<int>(ceil_div(ptiles, tps));
     const int n_items = n_qblocks * n_splits;
     grid = std::min(n_items, units) * group;
-    B2VS_TRY(ws_cand.reserve(static_cast<size_t>(grid) * kEpiGroups * kBM * kCap * sizeof(u64)));
-    B2VS_TRY(ws_keys.reserve(static_cast<size_t>(n_splits) * kEpiGroups * q_pad * k * sizeof(u64)));
+    B2VS_TRY(ws_cand.reserve(static_cast<size_t>(grid) * epi_groups * kBM * kCap * sizeof(u64)));
+    B2VS_TRY(ws_keys.reserve(static_cast<size_t>(n_splits) * epi_groups * q_pad * k * sizeof(u64)));
     p.cand = ws_cand.as<u64>();
     p.out_keys = ws_keys.as<u64>();
     p.n_items = n_items;
@@ -438,15 +451,15 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
     p.tiles_per_split = tps;
     p.tile_stride = stride;
     p.tau_init = (pass > 0) ? ws_tau.as<float>() : nullptr;
-    B2VS_TRY(launch_fused(group, grid, tm_q, p, st));
+    B2VS_TRY(launch_fused(group, grid, tm_q, p, st, epi_groups));
     ++launches;
     if (last && timed) B2VS_CUDA(cudaEventRecord(ev1, st));
     if (last) {
-      B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits * kEpiGroups, q_pad, nq, k, metric,
+      B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits * epi_groups, q_pad, nq, k, metric,
                                    ws_qnorm.as<float>(), id_offset, out_d, out_i, out_label, st));
     } else {
       // sampled pass: only the k-th best raw score per query is kept, as the next pass's threshold
-      B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits * kEpiGroups, q_pad, q_pad, k, metric,
+      B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits * epi_groups, q_pad, q_pad, k, metric,
                                    nullptr, 0, nullptr, nullptr, nullptr, st, nullptr, ws_tau.as<float>()));
       // sharded search: every shard continues with the tightest bound any shard found (a shard's
       // k-th best sampled score bounds the GLOBAL k-th score from above, so the minimum does too)
@@ -490,7 +503,7 @@ int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st) {
   const int grid = std::max(1, std::min(a.max_work, sm_count(dev)));
   B2VS_CUDA(cudaFuncSetAttribute((bf_tc_kernel<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  TcCfg<1>::kSmemBytes));
-  bf_tc_kernel<1, true><<<grid, kTcThreads, TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_xl, p);
+  bf_tc_kernel<1, true><<<grid, tc_threads(1), TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_xl, p);
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }
