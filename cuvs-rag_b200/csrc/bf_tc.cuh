@@ -50,9 +50,10 @@ constexpr int kNormBytes = kBN * 4;
 //  * E = 1 for the long database passes: measured at C2 on the same box, 15 sustained steps,
 //    2 groups 72.0 K QPS at ~1.2 GHz vs 1 group 73.6-74.3 K QPS at ~1.33 GHz - that kernel is
 //    power-capped, and the extra warps cost more clock than the shorter accumulator hand-off wins;
-//  * E = 2 for SMALL matrices with a large k - the coarse probes of the IVF indexes (top-64 of
-//    16 384 centroids at C4: 79 CTAs, four epilogue warps each, do ~420 insertions and two 256-key
-//    sorts per query row while the tensor pipe is 5 % busy): the epilogue is the whole kernel there.
+//  * E = 2 was also tried where the epilogue is the whole kernel - the coarse probes of the IVF
+//    indexes (top-64 of 16 384 centroids at C4: 79 CTAs, tensor pipe 5 % busy): slower too (732 vs
+//    672 us), because two groups with private thresholds insert ~2 k ln(N/2k) candidates instead of
+//    k ln(N/k).  The variant stays reachable (B2VS_FLAG_EPI2 / B2VS_EPI_GROUPS=2) for measurements.
 constexpr int kMaxEpiGroups = 2;
 // Work-table (grouped scan) epilogue: hits are staged in a small per-warp shared-memory queue and
 // appended to the queries' global buffers in batches (one atomic round trip per batch instead of

@@ -348,11 +348,15 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
     group = (k <= kPairMaxK && (nq >= 4096 || (nq > kBM && nq <= 2 * kBM))) ? 2 : kDefaultTcGroup;
   if (flags & B2VS_FLAG_TC_SINGLE) group = 1;
   if (flags & B2VS_FLAG_TC_PAIR) group = 2;
-  // Small matrix + sizeable k (the coarse probes of the IVF indexes): the epilogue's selection work
-  // is the whole kernel, so run it with TWO epilogue warp groups on the single-CTA kernel (which
-  // also fills more SMs than 256-row pair blocks do).  B2VS_EPI_GROUPS=1|2 / B2VS_FLAG_EPI2 force it.
+  // Epilogue warp groups: ONE by default everywhere.  Two groups (alternate tiles, private
+  // thresholds) were tried for the coarse probes of the IVF indexes, whose selection work is the
+  // whole kernel (top-64 of 16 384 centroids: tensor pipe 5 % busy): slower, 732 vs 672 us at C4,
+  // 327 vs 289 us at C3 - each group sees half the columns with its own threshold, so together they
+  // insert ~2 k ln(N / 2k) candidates instead of k ln(N / k).  B2VS_EPI_GROUPS=2 / B2VS_FLAG_EPI2 keep
+  // the variant reachable for measurements.
   const int64_t tiles_all = ceil_div(n, kBN);
-  int epi_groups = (k >= 8 && k <= kMaxFusedK && tiles_all <= 256 && nq >= 256) ? 2 : 1;
+  (void)tiles_all;
+  int epi_groups = 1;
   if (env().epi_groups > 0) epi_groups = env().epi_groups;
   if (flags & B2VS_FLAG_EPI2) epi_groups = 2;
   if (k == 1 || k > kMaxFusedK || (flags & B2VS_FLAG_TC_PAIR) || tc_group_override() == 2) epi_groups = 1;

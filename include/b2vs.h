@@ -84,7 +84,7 @@ typedef struct b2vs_search_params {
 #define B2VS_FLAG_TIME_KERNEL 1
 #define B2VS_FLAG_TC_SINGLE 2   /* flat: force the single-CTA (cta_group::1) kernel */
 #define B2VS_FLAG_TC_PAIR 4     /* flat: force the CTA-pair (cta_group::2) kernel */
-#define B2VS_FLAG_EPI2 16       /* flat, k <= 128: force two epilogue warp groups (default: small matrices, k >= 8) */
+#define B2VS_FLAG_EPI2 16       /* flat, k <= 128: two epilogue warp groups (measurement switch; slower in every case measured) */
 #define B2VS_FLAG_GRAPH 8       /* IVF, nq <= 64, k (and k*refine_ratio) <= 128: replay the call as one
                                    CUDA graph (captured on the second call of a signature
                                    (nq, k, dtype, n_probes, refine_ratio); env B2VS_GRAPH=1/0 forces it
