@@ -62,6 +62,15 @@ static EnvConfig read_env() {
   c.no_item_sort = std::getenv("B2VS_NO_ITEM_SORT") != nullptr;
   if (const char* e = std::getenv("B2VS_GRAPH")) c.graph = e[0] == '0' ? 0 : 1;
   if (const char* e = std::getenv("B2VS_IVF_SEED")) c.seed_mode = e[0] == '0' ? 0 : 1;
+  {
+    const int v = env_int_or("B2VS_IVF_SEED_LISTS", 0);
+    if (v >= 1 && v <= 16) c.seed_lists = v;
+    const int t = env_int_or("B2VS_IVF_SEED_TILE", 0);
+    if (t >= 32 && t <= 256 && t % 32 == 0) c.seed_tile = t;
+  }
+  if (const char* e = std::getenv("B2VS_WORK_EPI")) c.work_epi = (e[0] == '1' || e[0] == '2') ? e[0] - '0' : 0;
+  if (const char* e = std::getenv("B2VS_TWO_PASS")) c.two_pass = e[0] == '0' ? 0 : 1;
+  c.two_pass_chunk_mb = std::max(0, env_int_or("B2VS_TWO_PASS_CHUNK_MB", 0));
   if (const char* e = std::getenv("B2VS_CANARY")) c.canary = e[0] == '1';
   if (const char* e = std::getenv("B2VS_EPI_GROUPS")) c.epi_groups = (e[0] == '1' || e[0] == '2') ? e[0] - '0' : 0;
   return c;

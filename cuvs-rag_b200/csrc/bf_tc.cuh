@@ -60,7 +60,7 @@ constexpr int kMaxEpiGroups = 2;
 // one per 32-column chunk on the epilogue's critical path).
 constexpr int kQueueCap = 96;                                 // entries per epilogue warp
 constexpr int kQueueWarpBytes = kQueueCap * (8 + 4);          // keys (u64) + query slots (int)
-constexpr int kQueueBytes = 4 * kQueueWarpBytes;              // work mode runs one epilogue group
+constexpr int kQueueBytes = 4 * kMaxEpiGroups * kQueueWarpBytes;   // one queue per epilogue warp
 
 template <int G> struct TcCfg {
   static constexpr int kBRows = kBN / G;                     // db rows staged by one CTA
@@ -106,6 +106,14 @@ struct BfTcParams {
   // atomics; the caller pre-fills the buffers with kKeyInf
   int seed_all;
   const int* row_slot;  // [query rows] which of the query's seed lists this gathered row probes
+  // two-pass selection over a small database (work mode; flat.cu: search_two_pass).
+  //  seed_all == 2: only the MINIMUM of every 32-column chunk is stored, at
+  //    chunk_min[query][column / 32] (row stride chunk_ld floats);
+  //  tau_chunk != NULL: the threshold is a (score, chunk) pair - a score equal to tau_init[query]
+  //    qualifies iff its chunk index is <= tau_chunk[query].
+  float* chunk_min;
+  int chunk_ld;
+  const int* tau_chunk;
 };
 constexpr int kSeedSlotRows = 256;   // = one tile: the seed pass scores the first tile of a list
 
@@ -309,13 +317,28 @@ __device__ __forceinline__ void score_chunk_seed(const uint32_t (&r)[32], const 
   }
 }
 
+// Two-pass selection, first pass: the minimum of the chunk's 32 scores.
+__device__ __forceinline__ float score_chunk_min(const uint32_t (&r)[32], const float4* __restrict__ nrm4,
+                                                 float alpha) {
+  float m[8];
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 nb = nrm4[j4];
+    m[j4] = fminf(fminf(fmaf(alpha, __uint_as_float(r[4 * j4 + 0]), nb.x),
+                        fmaf(alpha, __uint_as_float(r[4 * j4 + 1]), nb.y)),
+                  fminf(fmaf(alpha, __uint_as_float(r[4 * j4 + 2]), nb.z),
+                        fmaf(alpha, __uint_as_float(r[4 * j4 + 3]), nb.w)));
+  }
+  return fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])), fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
+}
+
 constexpr int tc_threads(int epi_groups) { return 128 + 128 * epi_groups; }
 
 template <int G, bool kWork = false, int E = 1>
 __global__ void __launch_bounds__(tc_threads(E), 1)
 bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
              const BfTcParams p) {
-  static_assert(!kWork || (G == 1 && E == 1), "work-table mode is single-CTA, one epilogue group");
+  static_assert(!kWork || G == 1, "work-table mode is single-CTA");
   static_assert(E == 1 || E == 2, "epilogue groups");
   constexpr int kEpiGroups = E;
   using Cfg = TcCfg<G>;
@@ -521,13 +544,19 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       int seed_slot = 0;
       bool real_row = true;
       bool quarter_live = true;   // work mode: false when none of the warp's 32 rows is a real query
+      int tie_chunk = -1;         // (score, chunk) thresholds: chunks <= tie_chunk compare inclusively
+      float tau_tie = -inf;
       if (kWork) {
         const int query = __ldg(p.row_query + q_row);
-        if (p.seed_all) seed_slot = __ldg(p.row_slot + q_row);
+        if (p.seed_all == 1) seed_slot = __ldg(p.row_slot + q_row);
         tau = query >= 0 ? p.tau_init[query] : -inf;   // padding rows never qualify
         real_row = query >= 0;
         q_row = static_cast<size_t>(max(query, 0));
         quarter_live = __any_sync(0xffffffffu, real_row);
+        if (p.tau_chunk != nullptr && real_row) {
+          tie_chunk = __ldg(p.tau_chunk + query);
+          tau_tie = nextafterf(tau, inf);
+        }
       } else if (q_row >= static_cast<size_t>(p.nq)) {
         tau = -inf;            // padding row of the last query block: stays empty, costs nothing
       } else if (p.tau_init != nullptr) {
@@ -570,12 +599,16 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
           ptx::tmem_ld_32x32b_x32(tile_taddr + c2 * 64 + 32, rb);
           if (kWork) {
             if (c2 * 64 < nv) {
-              if (p.seed_all) {
+              if (p.seed_all == 2) {
+                const float mn = score_chunk_min(ra, nrm4 + c2 * 16, p.alpha);
+                if (real_row) p.chunk_min[q_row * p.chunk_ld + ((col0 + c2 * 64) >> 5)] = mn;
+              } else if (p.seed_all) {
                 if (real_row)
                   score_chunk_seed(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, 0.f,
                                    row_buf + seed_slot * kSeedSlotRows + (ti * kBN + c2 * 64));
               } else {
-                score_chunk_queue(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, tau, 0.f,
+                const float t = static_cast<int>((col0 + c2 * 64) >> 5) <= tie_chunk ? tau_tie : tau;
+                score_chunk_queue(ra, nrm4 + c2 * 16, p.alpha, col0 + c2 * 64, t, 0.f,
                                   static_cast<int>(q_row), hq, p.big_cand, p.big_count, p.big_cap, lane);
               }
             }
@@ -601,12 +634,16 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
           }
           if (kWork) {
             if (c2 * 64 + 32 < nv) {
-              if (p.seed_all) {
+              if (p.seed_all == 2) {
+                const float mn = score_chunk_min(rb, nrm4 + c2 * 16 + 8, p.alpha);
+                if (real_row) p.chunk_min[q_row * p.chunk_ld + ((col0 + c2 * 64 + 32) >> 5)] = mn;
+              } else if (p.seed_all) {
                 if (real_row)
                   score_chunk_seed(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, 0.f,
                                    row_buf + seed_slot * kSeedSlotRows + (ti * kBN + c2 * 64 + 32));
               } else {
-                score_chunk_queue(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, tau, 0.f,
+                const float t = static_cast<int>((col0 + c2 * 64 + 32) >> 5) <= tie_chunk ? tau_tie : tau;
+                score_chunk_queue(rb, nrm4 + c2 * 16 + 8, p.alpha, col0 + c2 * 64 + 32, t, 0.f,
                                   static_cast<int>(q_row), hq, p.big_cand, p.big_count, p.big_cap, lane);
               }
             }

@@ -141,6 +141,11 @@ struct EnvConfig {
   int graph = -1;              // B2VS_GRAPH=0|1: never / always replay small IVF batches as a graph
   int seed_mode = -1;          // B2VS_IVF_SEED=0|1: legacy seed kernels / seeds from the tensor-core pass
   int epi_groups = 0;          // B2VS_EPI_GROUPS=1|2: epilogue warp groups of the flat kernel (0 = heuristic)
+  int work_epi = 0;            // B2VS_WORK_EPI=1|2: epilogue groups of every work-table launch (0 = per call site)
+  int seed_lists = 0;          // B2VS_IVF_SEED_LISTS: lists per query scored by the seed pass (1..16)
+  int seed_tile = 0;           // B2VS_IVF_SEED_TILE: rows of each seed list that are scored (32..256, multiple of 32)
+  int two_pass = -1;           // B2VS_TWO_PASS=0|1: never / whenever possible the two-pass selection of the flat engine
+  int two_pass_chunk_mb = 0;   // B2VS_TWO_PASS_CHUNK_MB: candidate-buffer bytes per sub-batch of queries
   bool canary = false;         // B2VS_CANARY=1: guard zones around every device buffer (read ONCE, at first use)
 };
 const EnvConfig& env();
@@ -177,7 +182,7 @@ struct FlatEngine {
   CUtensorMap tm_x;       // db map, box = 256 rows (single-CTA kernel)
   CUtensorMap tm_x_half;  // db map, box = 128 rows (CTA-pair kernel: each CTA stages half a tile)
   // workspaces (grow-only)
-  DevBuf ws_cand, ws_keys, ws_q, ws_qnorm, ws_tau, ws_big, ws_bigcnt;
+  DevBuf ws_cand, ws_keys, ws_q, ws_qnorm, ws_tau, ws_big, ws_bigcnt, ws_chunk, ws_work;
   b2vs_search_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // optional timing of the dominant kernel
   bool timing_pending = false;
@@ -198,6 +203,11 @@ struct FlatEngine {
   // 128 < k <= 2048 (bigk.cu): append-mode passes + per-query radix select
   int search_bigk(const void* q_mat, int nq, int q_pad, int group, int k, int64_t id_offset,
                   float* out_d, int64_t* out_i, cudaStream_t st, int* launches);
+  // small database, large k (the coarse probes of the IVF indexes): two tensor-core passes,
+  // per-chunk minima -> exact (score, chunk) threshold -> the <= 32 k survivors per query
+  bool two_pass_applies(int nq, int k, int group_forced, int flags) const;
+  int search_two_pass(const void* q_mat, int64_t q_rows, int nq, int k, int64_t id_offset, float* out_d,
+                      int64_t* out_i, int32_t* out_label, cudaStream_t st, bool timed, int* launches);
   size_t owned_bytes() const { return owned.bytes + beta.bytes; }
   void destroy();
 };
@@ -226,6 +236,12 @@ struct GroupedScanArgs {
   int cap;
   const int* row_slot;    // seed pass (seed_all): which seed list of its query a gathered row probes
   int seed_all;           // 1: every score of the (single-tile) items goes to its fixed slot
+                          // 2: only per-chunk minima are stored (chunk_min)
+  float* chunk_min;       // seed_all == 2: [nq][chunk_ld] minimum of every 32-row chunk
+  int chunk_ld;
+  const int* tau_chunk;   // optional [nq]: thresholds are (score, chunk) pairs (see BfTcParams)
+  int epi_groups;         // 0/1: four epilogue warps; 2: eight (two groups on alternate tiles) for
+                          // launches whose epilogue, not HBM, sets the pace
 };
 int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st);
 
@@ -260,6 +276,15 @@ int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k,
                         const float* qnorm, int64_t id_offset, float* out_d, int64_t* out_i,
                         int32_t* out_label, cudaStream_t st, const uint32_t* remap = nullptr,
                         float* out_tau = nullptr);
+
+// Two-pass selection (flat.cu: search_two_pass).  chunk_tau: per query the k-th smallest
+// (chunk minimum, chunk index) pair -> tau / tau_chunk, and count[q] = 0.  cand_select: the k best
+// of each query's appended candidates, straight to answer rows.
+int launch_chunk_tau(const float* chunk_min, int chunk_ld, int n_chunks, int nq, int k, float* tau,
+                     int* tau_chunk, int* count, cudaStream_t st);
+int launch_cand_select(const u64* cand, const int* count, int cap, int nq, int k, int metric,
+                       const float* qnorm, int64_t id_offset, float* out_d, int64_t* out_i,
+                       int32_t* out_label, cudaStream_t st);
 
 // cosine.cu
 int launch_unit_rows(const void* src, void* dst, int dtype, int64_t n, int dim, cudaStream_t st);

@@ -226,6 +226,8 @@ void FlatEngine::destroy() {
   ws_tau.release();
   ws_big.release();
   ws_bigcnt.release();
+  ws_chunk.release();
+  ws_work.release();
 }
 
 __global__ void fill_missing_kernel(float* out_d, int64_t* out_i, int32_t* out_label, int64_t total,
@@ -394,6 +396,13 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   CUtensorMap tm_q;
   B2VS_TRY(encode_tmap_2d(&tm_q, q_mat, ab_format, borrow_q ? nq : q_pad, kdim, kBM));
 
+  if (!tau_exchange && force_splits <= 0 && two_pass_applies(nq, k, tc_group_override(), flags)) {
+    B2VS_TRY(search_two_pass(q_mat, borrow_q ? nq : q_pad, nq, k, id_offset, out_d, out_i, out_label, st,
+                          (flags & B2VS_FLAG_TIME_KERNEL) != 0, &launches));
+    stats.launches = launches;
+    stats.algo_flops = 2.0 * nq * static_cast<double>(n) * dim;
+    return B2VS_OK;
+  }
   if (k > kMaxFusedK) {
     B2VS_TRY(search_bigk(q_mat, nq, q_pad, group, k, id_offset, out_d, out_i, st, &launches));
     stats.launches = launches;
@@ -482,6 +491,129 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
 }
 
 // ------------------------------------------------------------------------------------------
+// Two-pass selection for a SMALL database searched with a LARGE k - the coarse probes of the IVF
+// indexes (top-64 of 16 384 centroids at C4).  The fused kernel's selection costs ~k ln(N/k)
+// insertions per query, each a divergent slow path of the lane that owns the row; there it is the
+// whole kernel (0.67 ms at C4 with the tensor pipe 5 % busy, and only ceil(Q/128) = 79 of 148 SMs
+// at work, since splitting the rows multiplies the insertions).  The GEMM itself is cheap here, so
+// it runs twice, both times as the work-table kernel over (query block, tile range) items that fill
+// every SM:
+//   pass 1  stores only the minimum of every 32-row chunk (n/32 floats per query);
+//   chunk_tau_kernel: k-th smallest (minimum, chunk) pair = an exact threshold that at most 32 k
+//           elements pass, ties included (merge.cu);
+//   pass 2  appends the elements that pass to the query's buffer (capacity 32 k: cannot overflow);
+//   cand_select_kernel: top-k of those (~k + a few dozen in practice) -> answer rows.
+// (A single pass that stored the whole score matrix - 663 MB at C4 - and selected from it was
+// tried first: 0.31 ms of half-sector stores + 0.28 ms of selection, 0.60 ms in all.)
+constexpr int64_t kTwoPassMaxRows = 65536;
+constexpr int kTwoPassMinK = 16;
+constexpr int kTwoPassMinQueries = 512;
+constexpr size_t kTwoPassCandBytes = 1ull << 30;
+
+bool FlatEngine::two_pass_applies(int nq, int k, int group_forced, int flags) const {
+  if (k < 2 || k > kMaxFusedK || n < k) return false;
+  if (group_forced == 2 || (flags & (B2VS_FLAG_TC_PAIR | B2VS_FLAG_EPI2))) return false;
+  const int ov = env().two_pass;
+  if (ov == 0) return false;
+  if (n > 16 * kTwoPassMaxRows) return false;
+  if (ov == 1) return true;
+  return n <= kTwoPassMaxRows && k >= kTwoPassMinK && nq >= kTwoPassMinQueries;
+}
+
+// Work table of both passes: item = (query block, tile range), range-major so that the CTAs running
+// at one time share database tiles; row_query = identity (-1 on the padding rows of the last block).
+__global__ void two_pass_plan_kernel(int n_qblocks, int n_ranges, int tiles, int tiles_per_range,
+                                     int nq, int4* __restrict__ work, int* __restrict__ n_work,
+                                     int* __restrict__ row_query) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_qblocks * n_ranges) {
+    const int r = i / n_qblocks, qb = i % n_qblocks;
+    const int t0 = r * tiles_per_range, t1 = min(t0 + tiles_per_range, tiles);
+    work[i] = make_int4(qb, t0 * kBN, t1 * kBN, 0);
+  }
+  if (i < n_qblocks * kBM) row_query[i] = i < nq ? i : -1;
+  if (i == 0) *n_work = n_qblocks * n_ranges;
+}
+
+int FlatEngine::search_two_pass(const void* q_mat, int64_t q_rows, int nq, int k, int64_t id_offset,
+                                float* out_d, int64_t* out_i, int32_t* out_label, cudaStream_t st,
+                                bool timed, int* launches) {
+  const int sms = sm_count(dev);
+  const int tiles = static_cast<int>(ceil_div(n, kBN));
+  const int n_chunks = tiles * (kBN / 32);
+  const int cap = 32 * k;
+  const size_t budget = env().two_pass_chunk_mb > 0 ? static_cast<size_t>(env().two_pass_chunk_mb) << 20
+                                                    : kTwoPassCandBytes;
+  const int64_t n_qblocks_all = ceil_div(nq, kBM);
+  const int64_t blocks_per_batch = std::max<int64_t>(
+      1, std::min<int64_t>(n_qblocks_all, static_cast<int64_t>(budget / (static_cast<size_t>(cap) * 8 * kBM))));
+  const int64_t rows_b = blocks_per_batch * kBM;
+  B2VS_TRY(ws_big.reserve(static_cast<size_t>(rows_b) * cap * sizeof(u64)));
+  B2VS_TRY(ws_bigcnt.reserve(static_cast<size_t>(rows_b) * sizeof(int)));
+  B2VS_TRY(ws_chunk.reserve(static_cast<size_t>(rows_b) * n_chunks * sizeof(float)));
+  B2VS_TRY(ws_tau.reserve(static_cast<size_t>(rows_b) * 2 * sizeof(float)));
+  const int max_work = static_cast<int>(blocks_per_batch) * tiles;
+  B2VS_TRY(ws_work.reserve(static_cast<size_t>(max_work) * sizeof(int4) + 16 + static_cast<size_t>(rows_b) * sizeof(int)));
+  int4* work = ws_work.as<int4>();
+  int* n_work = reinterpret_cast<int*>(ws_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
+  int* row_query = n_work + 4;
+  float* tau = ws_tau.as<float>();
+  int* tau_chunk = reinterpret_cast<int*>(tau + rows_b);
+  if (timed) {
+    if (!ev0) {
+      B2VS_CUDA(cudaEventCreate(&ev0));
+      B2VS_CUDA(cudaEventCreate(&ev1));
+    }
+    B2VS_CUDA(cudaEventRecord(ev0, st));
+  }
+  int n_ranges = 1;
+  for (int64_t b0 = 0; b0 < n_qblocks_all; b0 += blocks_per_batch) {
+    const int n_qblocks = static_cast<int>(std::min(blocks_per_batch, n_qblocks_all - b0));
+    const int64_t q0 = b0 * kBM;
+    const int nq_b = static_cast<int>(std::min<int64_t>(nq - q0, static_cast<int64_t>(n_qblocks) * kBM));
+    // tile ranges cost nothing here (no selection state per item): fill the SMs
+    n_ranges = choose_splits(n_qblocks, tiles, sms, /*k=*/1);
+    const int tpr = static_cast<int>(ceil_div(tiles, n_ranges));
+    n_ranges = static_cast<int>(ceil_div(tiles, tpr));
+    const int n_items = n_qblocks * n_ranges;
+    const int plan_threads = std::max(n_items, n_qblocks * kBM);
+    two_pass_plan_kernel<<<static_cast<unsigned>(ceil_div(plan_threads, 256)), 256, 0, st>>>(
+        n_qblocks, n_ranges, tiles, tpr, nq_b, work, n_work, row_query);
+    B2VS_CUDA(cudaGetLastError());
+    GroupedScanArgs ga{};
+    ga.q_mat = static_cast<const uint16_t*>(q_mat) + static_cast<size_t>(q0) * kdim;
+    ga.q_rows = q_rows - q0;
+    ga.x_mat = mat; ga.x_rows = n;
+    ga.kdim = kdim; ga.ab_format = ab_format; ga.q_split = 0;
+    ga.beta = beta.as<float>();
+    ga.alpha = (metric == B2VS_METRIC_L2) ? -2.f : -1.f;
+    ga.work = work; ga.n_work = n_work; ga.max_work = n_items;
+    ga.row_query = row_query;
+    ga.tau = tau;
+    ga.cand = ws_big.as<u64>(); ga.count = ws_bigcnt.as<int>(); ga.cap = cap;
+    ga.seed_all = 2;
+    ga.chunk_min = ws_chunk.as<float>(); ga.chunk_ld = n_chunks;
+    ga.epi_groups = 2;      // both passes are epilogue-bound (the GEMM is a few percent of them)
+    B2VS_TRY(launch_grouped_scan(dev, ga, st));
+    B2VS_TRY(launch_chunk_tau(ws_chunk.as<float>(), n_chunks, n_chunks, nq_b, k, tau, tau_chunk,
+                              ws_bigcnt.as<int>(), st));
+    ga.seed_all = 0;
+    ga.tau_chunk = tau_chunk;
+    B2VS_TRY(launch_grouped_scan(dev, ga, st));
+    const size_t o = static_cast<size_t>(q0) * k;
+    B2VS_TRY(launch_cand_select(ws_big.as<u64>(), ws_bigcnt.as<int>(), cap, nq_b, k, metric,
+                                ws_qnorm.as<float>() + q0, id_offset, out_d ? out_d + o : nullptr,
+                                out_i ? out_i + o : nullptr, out_label ? out_label + o : nullptr, st));
+    *launches += 5;
+  }
+  if (timed) B2VS_CUDA(cudaEventRecord(ev1, st));
+  timing_pending = timed;
+  stats.n_splits = n_ranges;
+  stats.grid = sms;
+  return B2VS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st) {
   CUtensorMap tm_q, tm_xl;
   const int xkb = static_cast<int>(ceil_div(a.kdim, kBK));
@@ -504,10 +636,20 @@ int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st) {
   p.row_query = a.row_query;
   p.row_slot = a.row_slot;
   p.seed_all = a.seed_all;
+  p.chunk_min = a.chunk_min;
+  p.chunk_ld = a.chunk_ld;
+  p.tau_chunk = a.tau_chunk;
   const int grid = std::max(1, std::min(a.max_work, sm_count(dev)));
-  B2VS_CUDA(cudaFuncSetAttribute((bf_tc_kernel<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 TcCfg<1>::kSmemBytes));
-  bf_tc_kernel<1, true><<<grid, tc_threads(1), TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_xl, p);
+  const int epi = env().work_epi > 0 ? env().work_epi : (a.epi_groups == 2 ? 2 : 1);
+  if (epi == 2) {
+    B2VS_CUDA(cudaFuncSetAttribute((bf_tc_kernel<1, true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TcCfg<1>::kSmemBytes));
+    bf_tc_kernel<1, true, 2><<<grid, tc_threads(2), TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_xl, p);
+  } else {
+    B2VS_CUDA(cudaFuncSetAttribute((bf_tc_kernel<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   TcCfg<1>::kSmemBytes));
+    bf_tc_kernel<1, true><<<grid, tc_threads(1), TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_xl, p);
+  }
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }

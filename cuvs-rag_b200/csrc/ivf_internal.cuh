@@ -26,14 +26,13 @@
 #include <vector>
 
 #include "ivf.h"
-#include "topk.cuh"
+#include "warp_select.cuh"
 
 namespace b2vs {
 
 constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
-constexpr int kListE = 4;  // warp-resident sorted list: 32 * 4 = 128 keys
 constexpr int kGroupRows = 128;  // query rows per grouped-scan work item (= the UMMA M extent)
 #ifndef B2VS_SKIP_PAD_ROWS
 #define B2VS_SKIP_PAD_ROWS 1
@@ -139,6 +138,22 @@ struct IvfData {
 };
 
 // ------------------------------------------------------------------------------------------
+// Four consecutive elements (p aligned to 4 elements) as floats: one 8- or 16-byte load.
+template <typename T> __device__ __forceinline__ float4 ld4_f32(const T* p);
+template <> __device__ __forceinline__ float4 ld4_f32<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <> __device__ __forceinline__ float4 ld4_f32<__half>(const __half* p) {
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <> __device__ __forceinline__ float4 ld4_f32<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xFFFF0000u),
+                     __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xFFFF0000u));
+}
 template <typename T> __device__ __forceinline__ float ld_f32(const T* p);
 template <> __device__ __forceinline__ float ld_f32<float>(const float* p) { return *p; }
 template <> __device__ __forceinline__ float ld_f32<__half>(const __half* p) { return __half2float(*p); }

@@ -11,36 +11,6 @@
 
 namespace b2vs {
 
-// ---- warp-resident sorted top-k list -------------------------------------------------------
-struct WarpTopK {
-  u64 acc[kListE];
-  float tau;
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int e = 0; e < kListE; ++e) acc[e] = kKeyInf;
-    tau = __int_as_float(0x7f800000);
-  }
-  // Each lane offers at most one candidate key (kKeyInf = none). Warp-collective.
-  __device__ __forceinline__ void offer(u64 ck, int k, int lane) {
-    if (!__any_sync(0xffffffffu, ck != kKeyInf)) return;
-    u64 c1[1] = {ck};
-    warp_bitonic_sort<1>(c1, lane);
-#pragma unroll
-    for (int e = 0; e < kListE; ++e) {
-      const int i = lane * kListE + e;                       // list element index
-      const u64 r = shfl_u64(c1[0], (32 * kListE - 1 - i) & 31);  // reversed candidate run
-      if (i >= 32 * kListE - 32) acc[e] = acc[e] < r ? acc[e] : r;
-    }
-    warp_bitonic_merge<kListE>(acc, lane);
-    u64 kth = kKeyInf;
-#pragma unroll
-    for (int e = 0; e < kListE; ++e)
-      if (lane * kListE + e == k - 1) kth = acc[e];
-    kth = shfl_u64(kth, (k - 1) / kListE);
-    tau = (kth == kKeyInf) ? __int_as_float(0x7f800000) : key_score(kth);
-  }
-};
-
 // Block epilogue shared by both scans: warps publish their lists, warp 0 folds them and writes
 // the item's k sorted keys.
 __device__ __forceinline__ void block_merge_and_store(WarpTopK& tk, u64 (*lists)[32 * kListE],
@@ -333,17 +303,20 @@ ivf_group_select_kernel(const u64* __restrict__ cand, const int* __restrict__ co
     return;
   }
   const u64* src = cand + static_cast<size_t>(q) * cap;
-  WarpTopK tk;
-  tk.init();
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    const int i = i0 + lane;
-    u64 ck = kKeyInf;
-    if (i < n) {
-      const u64 v = __ldcg(src + i);
-      if (key_score(v) <= tk.tau) ck = v;   // ties at the k-th score are settled by the key order in the merge
-    }
-    tk.offer(ck, k, lane);
+  __shared__ u64 stage_mem[kSelectThreads / 32][kStageKeys];
+  StagedTopK sel;
+  sel.init(stage_mem[threadIdx.x >> 5]);
+  WarpTopK& tk = sel.tk;
+  // two loads per lane in flight; keys are folded in 32 ACCEPTED keys at a time
+  for (int i0 = 0; i0 < n; i0 += 64) {
+    const int ia = i0 + lane, ib = i0 + 32 + lane;
+    const u64 va = ia < n ? __ldcg(src + ia) : kKeyInf;
+    const u64 vb = ib < n ? __ldcg(src + ib) : kKeyInf;
+    // ties at the k-th score are settled by the key order in the merge
+    sel.push((va != kKeyInf && key_score(va) <= tk.tau) ? va : kKeyInf, k, lane);
+    sel.push((vb != kKeyInf && key_score(vb) <= tk.tau) ? vb : kKeyInf, k, lane);
   }
+  sel.flush(k, lane);
   u64* out = out_keys + static_cast<size_t>(q) * k;
 #pragma unroll
   for (int e = 0; e < kListE; ++e) {
@@ -366,17 +339,22 @@ ivf_seed_select_kernel(const u64* __restrict__ cand, int n_keys, int cap, int k,
   if (q >= nq) return;
   const int n = min(n_keys, cap);   // the seed pass fills fixed slots (kKeyInf where a list is short)
   const u64* src = cand + static_cast<size_t>(q) * cap;
-  WarpTopK tk;
-  tk.init();
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    const int i = i0 + lane;
-    u64 ck = kKeyInf;
-    if (i < n) {
-      const u64 v = __ldcg(src + i);
-      if (key_score(v) < tk.tau) ck = v;
+  __shared__ u64 stage_mem[4][kStageKeys];
+  StagedTopK sel;
+  sel.init(stage_mem[threadIdx.x >> 5]);
+  WarpTopK& tk = sel.tk;
+  for (int i0 = 0; i0 < n; i0 += 128) {    // four loads per lane in flight
+    u64 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + 32 * j + lane;
+      v[j] = i < n ? __ldcg(src + i) : kKeyInf;
     }
-    tk.offer(ck, k, lane);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sel.push((v[j] != kKeyInf && key_score(v[j]) < tk.tau) ? v[j] : kKeyInf, k, lane);
   }
+  sel.flush(k, lane);
   // tk.tau = k-th best score (+inf while fewer than k candidates): publish it inclusively
   if (lane == 0) tau[q] = isinf(tk.tau) ? tk.tau : nextafterf(tk.tau, INFINITY);
 }
@@ -745,6 +723,8 @@ __global__ void refine_kernel(const T* __restrict__ rows, int dim, const float* 
 #pragma unroll
   for (int e = 0; e < kListE; ++e) key[e] = kKeyInf;
   const float* qv = qf + static_cast<size_t>(q) * dp;
+  // rows and the fp32 query copy are 16-byte aligned when dim (and so dp) is a multiple of 4
+  const bool vec4 = (dim & 3) == 0 && (dp & 3) == 0 && (reinterpret_cast<uintptr_t>(rows) & 15) == 0;
   // candidate ids: lane l holds candidates l, l + 32, ... (k_in <= 128), broadcast by shuffle, so
   // the row reads do not wait for a dependent id load; kRefineAhead rows are in flight at a time
   // (a single query used to be a chain of k_in dependent HBM round trips: 92 us at k_in = 80)
@@ -767,6 +747,27 @@ __global__ void refine_kernel(const T* __restrict__ rows, int dim, const float* 
       row[b] = j < k_in ? r : -1ll;
       acc[b] = 0.f;
     }
+    if (vec4) {
+      // four dimensions per lane and step: one 8-byte (16-bit rows) / 16-byte load per row
+      for (int t = lane * 4; t < dim; t += 128) {
+        const float4 qt = *reinterpret_cast<const float4*>(qv + t);
+        float4 xv[kRefineAhead];
+#pragma unroll
+        for (int b = 0; b < kRefineAhead; ++b)
+          xv[b] = row[b] >= 0 ? ld4_f32<T>(rows + static_cast<size_t>(row[b]) * dim + t)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int b = 0; b < kRefineAhead; ++b) {
+          if (row[b] < 0) continue;
+          if (metric == B2VS_METRIC_L2) {
+            const float d0 = qt.x - xv[b].x, d1 = qt.y - xv[b].y, d2 = qt.z - xv[b].z, d3 = qt.w - xv[b].w;
+            acc[b] = fmaf(d3, d3, fmaf(d2, d2, fmaf(d1, d1, fmaf(d0, d0, acc[b]))));
+          } else {
+            acc[b] = fmaf(-qt.w, xv[b].w, fmaf(-qt.z, xv[b].z, fmaf(-qt.y, xv[b].y, fmaf(-qt.x, xv[b].x, acc[b]))));
+          }
+        }
+      }
+    } else
     for (int t = lane; t < dim; t += 32) {
       const float qt = qv[t];
       float xv[kRefineAhead];
@@ -1016,6 +1017,60 @@ __global__ void gather_group_residuals_kernel(const uint32_t* __restrict__ row_i
   if (lane == 0) { row_query[v] = q; row_bias[v] = l2 ? acc : -acc; }
 }
 
+// The same by item for 128-d indexes (one float4 per lane and row): a warp takes kGatherIlp
+// consecutive items and issues all their loads before the first use - with one item per warp the
+// kernel was a chain of three dependent loads per 256 bytes written (0.18 ms for the 640 K items
+// of a C4 batch).
+constexpr int kGatherIlp = 4;
+__global__ void __launch_bounds__(256)
+gather_group_residuals128_kernel(const long long* __restrict__ probe_ids, const float* __restrict__ qf,
+                                 const float* __restrict__ cent, int n_probes, int l2,
+                                 uint16_t* __restrict__ out, int* __restrict__ row_query,
+                                 float* __restrict__ row_bias, int* __restrict__ row_slot,
+                                 const uint32_t* __restrict__ item_slot, int n_items) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i0 = ((static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * kGatherIlp;
+  if (i0 >= n_items) return;
+  uint32_t v[kGatherIlp];
+  long long list[kGatherIlp];
+  int q[kGatherIlp];
+#pragma unroll
+  for (int t = 0; t < kGatherIlp; ++t) {
+    const int64_t it = min(i0 + t, static_cast<int64_t>(n_items) - 1);
+    v[t] = __ldg(item_slot + it);
+    list[t] = __ldg(probe_ids + it);
+    q[t] = static_cast<int>(it / n_probes);
+  }
+  float4 qv[kGatherIlp], cv[kGatherIlp];
+#pragma unroll
+  for (int t = 0; t < kGatherIlp; ++t) {
+    qv[t] = __ldg(reinterpret_cast<const float4*>(qf + static_cast<size_t>(q[t]) * 128) + lane);
+    cv[t] = __ldg(reinterpret_cast<const float4*>(cent + static_cast<size_t>(list[t] < 0 ? 0 : list[t]) * 128) + lane);
+  }
+#pragma unroll
+  for (int t = 0; t < kGatherIlp; ++t) {
+    if (i0 + t >= n_items) break;
+    const float in[4] = {l2 ? qv[t].x - cv[t].x : qv[t].x, l2 ? qv[t].y - cv[t].y : qv[t].y,
+                         l2 ? qv[t].z - cv[t].z : qv[t].z, l2 ? qv[t].w - cv[t].w : qv[t].w};
+    float back[4];
+    uint16_t h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = to_op16(in[e], 1, &back[e]);
+    float acc = l2 ? back[0] * back[0] + back[1] * back[1] + back[2] * back[2] + back[3] * back[3]
+                   : qv[t].x * cv[t].x + qv[t].y * cv[t].y + qv[t].z * cv[t].z + qv[t].w * cv[t].w;
+    reinterpret_cast<uint2*>(out + static_cast<size_t>(v[t]) * 128)[lane] =
+        make_uint2(static_cast<uint32_t>(h[0]) | (static_cast<uint32_t>(h[1]) << 16),
+                   static_cast<uint32_t>(h[2]) | (static_cast<uint32_t>(h[3]) << 16));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      row_query[v[t]] = q[t];
+      row_bias[v[t]] = l2 ? acc : -acc;
+      row_slot[v[t]] = static_cast<int>((i0 + t) % n_probes);
+    }
+  }
+}
+
 // Instantiation table of the <FMT, J> scan kernels: J = 16-byte chunks of a row owned by a lane.
 // (grid may be an int or a dim3)
 #define FLAT_SCAN_DISPATCH(KERNEL, fmt, j, grid, st, ...)                                    \
@@ -1190,6 +1245,15 @@ int launch_gather_group_queries(IvfData* d, int64_t rows_cap, int n_probes, int 
 int launch_gather_group_residuals(const b2vs_index* index, IvfData* d, int64_t rows_cap,
                                   const long long* probe_ids, int n_probes, int items, cudaStream_t st) {
   B2VS_TRY(prepare_by_item(d, rows_cap, items, st));
+  if (items > 0 && index->dim == 128 && d->dp == 128) {
+    const int64_t warps128 = ceil_div(static_cast<int64_t>(items), kGatherIlp);
+    gather_group_residuals128_kernel<<<static_cast<unsigned>(ceil_div(warps128, 8)), 256, 0, st>>>(
+        probe_ids, d->ws_qf.as<float>(), d->centroids.as<float>(), n_probes,
+        index->metric == B2VS_METRIC_L2 ? 1 : 0, d->ws_g_q.as<uint16_t>(), d->ws_g_rowq.as<int>(),
+        d->ws_g_bias.as<float>(), d->ws_g_rowslot.as<int>(), d->ws_item_slot.as<uint32_t>(), items);
+    B2VS_CUDA(cudaGetLastError());
+    return B2VS_OK;
+  }
   const int64_t warps = items > 0 ? items : rows_cap;
   gather_group_residuals_kernel<<<static_cast<unsigned>(ceil_div(warps, 8)), 256, 0, st>>>(
       d->ws_item_perm.as<uint32_t>(), d->ws_item_off.as<uint32_t>(), d->n_lists, probe_ids,

@@ -81,9 +81,14 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
 // nearest list's head alone leaves thousands of candidates per query, overflowing the buffers
 // into the exact rescue scan - it runs on the tensor cores, and it uses the full pass's own
 // arithmetic, so the threshold carries no rounding cushion.
+// B2VS_IVF_SEED_LISTS / B2VS_IVF_SEED_TILE: measurement knobs (lists per query, rows per list).
+static int seed_tile_rows() {
+  const int v = env().seed_tile;
+  return v > 0 ? v : kSeedTileRows;
+}
 static int seed_lists(int n_probes, int cap, int k) {
   // two lists (512 sampled rows) for k <= 32, four for larger k; never more than a quarter of the buffer
-  const int want = k <= 32 ? 2 : 4;
+  const int want = env().seed_lists > 0 ? env().seed_lists : (k <= 32 ? 2 : 4);
   return std::max(1, std::min(std::min(n_probes, want), cap / 4 / kSeedTileRows));
 }
 static bool use_tc_seed(int nq, int cap) {
@@ -494,7 +499,7 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
       B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
       if (tc_seed) {
         B2VS_TRY(run_tc_seed(d, probe_ids, n_probes, nq, k, cap, st, [&](const long long* ids, int m) {
-          return run_grouped_flat_scan(index, d, ids, m, nq, cap, nullptr, st, false, kSeedTileRows);
+          return run_grouped_flat_scan(index, d, ids, m, nq, cap, nullptr, st, false, seed_tile_rows());
         }));
         launches += 8;
       } else {
@@ -538,7 +543,7 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
     B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
     if (tc_seed) {
       B2VS_TRY(run_tc_seed(d, probe_ids, n_probes, nq, k, cap, st, [&](const long long* ids, int m) {
-        return run_grouped_pq_scan(index, d, ids, m, nq, cap, nullptr, st, false, kSeedTileRows);
+        return run_grouped_pq_scan(index, d, ids, m, nq, cap, nullptr, st, false, seed_tile_rows());
       }));
       launches += 8;
     } else {

@@ -65,24 +65,37 @@ __global__ void histogram_kernel(const int* __restrict__ labels, int64_t n, int*
   }
 }
 
-// Exclusive scan of list sizes rounded up to `pad`; single block.
-__global__ void scan_sizes_kernel(const int* __restrict__ sizes, int n_lists, int pad,
-                                  uint32_t* __restrict__ offsets) {
-  __shared__ uint32_t part[1024];
-  const int t = threadIdx.x;
+// Exclusive scan of list sizes rounded up to `pad`; single block of 1024 threads: per-thread
+// partial sums, a shuffle scan inside every warp, and warp 0 scanning the 32 warp totals.
+__global__ void __launch_bounds__(1024)
+scan_sizes_kernel(const int* __restrict__ sizes, int n_lists, int pad, uint32_t* __restrict__ offsets) {
+  __shared__ uint32_t warp_tot[32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int per = (n_lists + blockDim.x - 1) / blockDim.x;
   const int lo = t * per, hi = min(n_lists, lo + per);
   uint32_t s = 0;
   for (int i = lo; i < hi; ++i) s += static_cast<uint32_t>((sizes[i] + pad - 1) / pad * pad);
-  part[t] = s;
+  uint32_t inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
   __syncthreads();
-  if (t == 0) {
-    uint32_t run = 0;
-    for (int i = 0; i < blockDim.x; ++i) { const uint32_t v = part[i]; part[i] = run; run += v; }
-    offsets[n_lists] = run;
+  if (warp == 0) {
+    const uint32_t w = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0u;
+    uint32_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += v;
+    }
+    warp_tot[lane] = winc - w;                     // exclusive prefix of the warp totals
+    if (lane == 31) offsets[n_lists] = winc;
   }
   __syncthreads();
-  uint32_t run = part[t];
+  uint32_t run = warp_tot[warp] + inc - s;
   for (int i = lo; i < hi; ++i) {
     offsets[i] = run;
     run += static_cast<uint32_t>((sizes[i] + pad - 1) / pad * pad);

@@ -11,12 +11,39 @@
 #include <cmath>
 
 #include "common.h"
-#include "topk.cuh"
+#include "warp_select.cuh"
 
 namespace b2vs {
 
 constexpr int kMergeE = 4;  // 32 * 4 = 128 = kMaxFusedK
 constexpr int kMergeAhead = 4;  // split lists in flight per warp in merge_splits_kernel
+
+// The sorted keys of one query (4 per lane) -> its row of the answer: distances in the caller's
+// metric, ids shifted into the global numbering (or remapped through the list layout).
+__device__ __forceinline__ void emit_answer_row(const u64 (&acc)[kMergeE], int lane, int q, int k, int metric,
+                                                const float* __restrict__ qnorm, long long id_offset,
+                                                float* __restrict__ out_d, long long* __restrict__ out_i,
+                                                int* __restrict__ out_label,
+                                                const uint32_t* __restrict__ remap) {
+  const float qn = (metric == B2VS_METRIC_L2 && qnorm) ? qnorm[q] : 0.f;
+#pragma unroll
+  for (int e = 0; e < kMergeE; ++e) {
+    const int i = lane * kMergeE + e;
+    if (i >= k) continue;
+    const u64 key = acc[e];
+    const bool valid = key != kKeyInf;
+    const float sc = key_score(key);
+    float d;
+    if (metric == B2VS_METRIC_L2) d = valid ? fmaxf(sc + qn, 0.f) : INFINITY;
+    else d = valid ? -sc : -INFINITY;
+    const size_t o = static_cast<size_t>(q) * k + i;
+    if (out_d) out_d[o] = d;
+    uint32_t id = key_id(key);
+    if (valid && remap) id = remap[id];
+    if (out_i) out_i[o] = valid ? static_cast<long long>(id) + id_offset : -1ll;
+    if (out_label) out_label[o] = valid ? static_cast<int>(id) : -1;
+  }
+}
 
 __global__ void merge_splits_kernel(const u64* __restrict__ keys, int n_splits, int q_pad, int nq,
                                     int k, int metric, const float* __restrict__ qnorm,
@@ -64,24 +91,7 @@ __global__ void merge_splits_kernel(const u64* __restrict__ keys, int n_splits, 
       out_tau[q] = (kth == kKeyInf) ? INFINITY : nextafterf(key_score(kth), INFINITY);
     return;
   }
-  const float qn = (metric == B2VS_METRIC_L2 && qnorm) ? qnorm[q] : 0.f;
-#pragma unroll
-  for (int e = 0; e < kMergeE; ++e) {
-    const int i = lane * kMergeE + e;
-    if (i >= k) continue;
-    const u64 key = acc[e];
-    const bool valid = key != kKeyInf;
-    const float sc = key_score(key);
-    float d;
-    if (metric == B2VS_METRIC_L2) d = valid ? fmaxf(sc + qn, 0.f) : INFINITY;
-    else d = valid ? -sc : -INFINITY;
-    const size_t o = static_cast<size_t>(q) * k + i;
-    if (out_d) out_d[o] = d;
-    uint32_t id = key_id(key);
-    if (valid && remap) id = remap[id];
-    if (out_i) out_i[o] = valid ? static_cast<long long>(id) + id_offset : -1ll;
-    if (out_label) out_label[o] = valid ? static_cast<int>(id) : -1;
-  }
+  emit_answer_row(acc, lane, q, k, metric, qnorm, id_offset, out_d, out_i, out_label, remap);
 }
 
 int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k, int metric,
@@ -93,6 +103,95 @@ int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k,
                                                   id_offset, out_d,
                                                   reinterpret_cast<long long*>(out_i), out_label,
                                                   remap, out_tau);
+  B2VS_CUDA(cudaGetLastError());
+  return B2VS_OK;
+}
+
+// Two-pass selection over a small database (flat.cu: search_two_pass), the scalar side.
+//
+// chunk_tau_kernel: the first tensor-core pass left the minimum of every 32-row chunk of every
+// query's score row.  The k-th smallest (minimum, chunk index) pair T bounds the answer exactly:
+// an element qualifies iff (score, chunk) <= T.  The k chunks whose pair is <= T each hold an
+// element that precedes any non-qualifying one in (score, id) order, so the true top-k all
+// qualify; and every qualifying element lies in one of those k chunks, so at most 32 k elements
+// do - ties included, because chunk indices are distinct.  One warp per query.
+constexpr int kTwoPassThreads = 128;
+__global__ void __launch_bounds__(kTwoPassThreads)
+chunk_tau_kernel(const float* __restrict__ chunk_min, int chunk_ld, int n_chunks, int nq, int k,
+                 float* __restrict__ tau, int* __restrict__ tau_chunk, int* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  __shared__ u64 stage_mem[kTwoPassThreads / 32][kStageKeys];
+  StagedTopK sel;
+  sel.init(stage_mem[threadIdx.x >> 5]);
+  const float* row = chunk_min + static_cast<size_t>(q) * chunk_ld;
+  const float inf = __int_as_float(0x7f800000);
+  for (int c0 = 0; c0 < n_chunks; c0 += 128) {     // four loads per lane in flight
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + 32 * j + lane;
+      v[j] = c < n_chunks ? __ldcs(row + c) : inf;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool hit = v[j] <= sel.tk.tau && v[j] < inf;
+      sel.push(hit ? pack_key(v[j], static_cast<uint32_t>(c0 + 32 * j + lane)) : kKeyInf, k, lane);
+    }
+  }
+  sel.flush(k, lane);
+  u64 kth = kKeyInf;
+#pragma unroll
+  for (int e = 0; e < kListE; ++e)
+    if (lane * kListE + e == k - 1) kth = sel.tk.acc[e];
+  if (lane == (k - 1) / kListE) {
+    // fewer than k finite chunk minima: everything qualifies (n <= 32 * chunks < 32 k)
+    tau[q] = kth == kKeyInf ? inf : key_score(kth);
+    tau_chunk[q] = kth == kKeyInf ? 0x7fffffff : static_cast<int>(key_id(kth));
+    count[q] = 0;
+  }
+}
+
+// The k best of each query's qualifying elements (appended by the second pass), as answer rows.
+__global__ void __launch_bounds__(kTwoPassThreads)
+cand_select_kernel(const u64* __restrict__ cand, const int* __restrict__ count, int cap, int nq, int k,
+                   int metric, const float* __restrict__ qnorm, long long id_offset,
+                   float* __restrict__ out_d, long long* __restrict__ out_i, int* __restrict__ out_label) {
+  static_assert(kMergeE == kListE, "answer rows are emitted from the 128-key list");
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  __shared__ u64 stage_mem[kTwoPassThreads / 32][kStageKeys];
+  StagedTopK sel;
+  sel.init(stage_mem[threadIdx.x >> 5]);
+  const int n = min(count[q], cap);    // count <= 32 k <= cap by construction
+  const u64* src = cand + static_cast<size_t>(q) * cap;
+  for (int i0 = 0; i0 < n; i0 += 64) {
+    const int ia = i0 + lane, ib = i0 + 32 + lane;
+    const u64 va = ia < n ? __ldcg(src + ia) : kKeyInf;
+    const u64 vb = ib < n ? __ldcg(src + ib) : kKeyInf;
+    sel.push((va != kKeyInf && key_score(va) <= sel.tk.tau) ? va : kKeyInf, k, lane);
+    sel.push((vb != kKeyInf && key_score(vb) <= sel.tk.tau) ? vb : kKeyInf, k, lane);
+  }
+  sel.flush(k, lane);
+  emit_answer_row(sel.tk.acc, lane, q, k, metric, qnorm, id_offset, out_d, out_i, out_label, nullptr);
+}
+
+int launch_chunk_tau(const float* chunk_min, int chunk_ld, int n_chunks, int nq, int k, float* tau,
+                     int* tau_chunk, int* count, cudaStream_t st) {
+  const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(nq) * 32, kTwoPassThreads));
+  chunk_tau_kernel<<<blocks, kTwoPassThreads, 0, st>>>(chunk_min, chunk_ld, n_chunks, nq, k, tau, tau_chunk, count);
+  B2VS_CUDA(cudaGetLastError());
+  return B2VS_OK;
+}
+
+int launch_cand_select(const u64* cand, const int* count, int cap, int nq, int k, int metric,
+                       const float* qnorm, int64_t id_offset, float* out_d, int64_t* out_i,
+                       int32_t* out_label, cudaStream_t st) {
+  const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(nq) * 32, kTwoPassThreads));
+  cand_select_kernel<<<blocks, kTwoPassThreads, 0, st>>>(cand, count, cap, nq, k, metric, qnorm, id_offset,
+                                                         out_d, reinterpret_cast<long long*>(out_i), out_label);
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }

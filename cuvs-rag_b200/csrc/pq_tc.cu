@@ -21,7 +21,7 @@ static int launch_one(int grid, const CUtensorMap& tm_q, const PqTcParams& pp, c
 
 int launch_pq_grouped_scan(int dev, const PqGroupedScanArgs& a, cudaStream_t st) {
   CUtensorMap tm_q;
-  B2VS_TRY(encode_tmap_2d(&tm_q, a.q_mat, 1, a.q_rows, a.dim, kBM));
+  B2VS_TRY(encode_tmap_2d(&tm_q, a.q_mat, 1, a.q_rows, a.dim, kPqBoxRows));   // 16-row boxes: loads follow the block's real rows
   PqTcParams pp{};
   BfTcParams& p = pp.tc;
   p.beta = a.beta;

@@ -18,23 +18,33 @@
 // are read back from TMEM at all, every epilogue lane owns a real list row (no idle lane quarters,
 // no straggler warp), and a tile's accumulator is 128 columns, so four of them are in flight.
 //
-// Warp roles (512 threads): warp 0 = TMA producer (query k-blocks + the tile's ||r^||^2 vector),
-// warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 8-11 = decoders (one 32-row group each),
-// warps 4-7 / 12-15 = two epilogue groups taking alternate tiles.  A smem stage = 16 KB decoded
-// list k-block (128 rows x 64 dims) + 16 KB query k-block (TMA); its "full" barrier takes the TMA
-// transaction plus one arrival per decoder warp.  bf16 codebooks of at most 64 KB stay resident in
-// shared memory; larger ones (e.g. 768-d) are looked up in global memory, i.e. L2.
+// The N extent follows the block: a work item carries the number of real query rows c of its block
+// (work.w); the TMA producer loads ceil(c / 16) 16-row boxes of the query k-block instead of all 128
+// rows, and the UMMAs run with N = 16 ceil(c / 16) - at C4 (c ~ 40) that is 3/8 of the tensor-pipe
+// time, of the shared-memory reads of the N operand and of the TMA traffic of a full block.
+//
+// Warp roles (640 threads): warp 0 = TMA producer (query k-blocks + the tile's ||r^||^2 vector),
+// warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 8-11 and 16-19 = two decoder sets taking
+// alternate k-block stages (a warp of a set owns one 32-row group of the stage: the decode of one
+// group is a ~300-instruction chain that a single warp issues at well under one per cycle, and with
+// one set the four decoders, not the issue slots, set the tile rate), warps 4-7 / 12-15 = two
+// epilogue groups taking alternate tiles.  A smem stage = 16 KB decoded list k-block (128 rows x
+// 64 dims) + 16 KB query k-block (TMA); its "full" barrier takes the TMA transaction plus one
+// arrival per decoder warp.  bf16 codebooks of at most 64 KB stay resident in shared memory;
+// larger ones (e.g. 768-d) are looked up in global memory, i.e. L2.
 #pragma once
 #include "bf_tc.cuh"
 
 namespace b2vs {
 
-constexpr int kPqTcThreads = 512;
+constexpr int kPqTcThreads = 640;
 constexpr int kPqM = 128;                                        // list rows per tile (UMMA M)
 constexpr int kPqN = 128;                                        // query rows per block (UMMA N)
 constexpr int kPqTcStages = 4;
 constexpr int kPqListBytes = kPqM * kBK * 2;                     // 16 KB decoded list k-block
 constexpr int kPqQueryBytes = kPqN * kBK * 2;                    // 16 KB query k-block
+constexpr int kPqBoxRows = 16;                                   // TMA box: 16 query rows x 64 dims = one UMMA N unit
+constexpr int kPqBoxBytes = kPqBoxRows * kBK * 2;                // 2 KB
 constexpr int kPqTcStageBytes = kPqListBytes + kPqQueryBytes;    // 32 KB
 constexpr int kPqAcc = 4;                                        // accumulator buffers (4 x 128 TMEM columns)
 constexpr int kPqNormBytes = kPqM * 4;                           // ||r^||^2 of a tile's 128 rows
@@ -46,6 +56,7 @@ constexpr int kPqTcSmemBytes = kPqTcStages * kPqTcStageBytes + kPqAcc * kPqNormB
 static_assert(kPqTcSmemBytes <= 227 * 1024, "pq_tc_kernel shared memory");
 static_assert(kBK == 64, "the decoder writes 128-byte swizzled rows");
 static_assert(kPqN == kBM, "query blocks are the gather kernels' 128-row groups");
+static_assert(kPqTcStages % 2 == 0, "the two decoder sets take alternate stages");
 
 struct PqTcParams {
   BfTcParams tc;            // work table, thresholds, append buffers (see bf_tc.cuh, work mode)
@@ -131,6 +142,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
       const int4 w = __ldg(p.work + item);
       const int q_row0 = w.x * kPqN;
       const int t1 = (w.z - w.y + kPqM - 1) / kPqM;
+      const int n_box = (max(w.w, 1) + 15) >> 4;          // 16-row boxes that hold real queries
       for (int ti = 0; ti < t1; ++ti, ++tcount) {
         const uint32_t ab = tcount & (kPqAcc - 1), aph = (tcount / kPqAcc) & 1u;
         ptx::mbar_wait(bar_norm_empty + 8 * ab, aph ^ 1u);
@@ -143,10 +155,11 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kPqQueryBytes);
+            ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, static_cast<uint32_t>(n_box) * kPqBoxBytes);
             // the query block is re-read for every tile of the list: keep it in L2
-            ptx::tma_load_2d_hint(smem_base + stage * kStageBytes + kPqListBytes, &tm_q, bar_full + 8 * stage,
-                                  kb * kBK, q_row0, ptx::kEvictLast);
+            for (int b = 0; b < n_box; ++b)
+              ptx::tma_load_2d_hint(smem_base + stage * kStageBytes + kPqListBytes + b * kPqBoxBytes, &tm_q,
+                                    bar_full + 8 * stage, kb * kBK, q_row0 + b * kPqBoxRows, ptx::kEvictLast);
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -159,6 +172,9 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
     for (int item = unit; item < n_items; item += n_units) {
       const int4 w = __ldg(p.work + item);
       const int t1 = (w.z - w.y + kPqM - 1) / kPqM;
+      // N extent = the block's real query rows, in 16-column units (instruction descriptor bits [17,23) = N >> 3)
+      const uint32_t n_ext = static_cast<uint32_t>((max(w.w, 1) + 15) & ~15);
+      const uint32_t idesc = (p.idesc & ~(0x3Fu << 17)) | ((n_ext >> 3) << 17);
       for (int t = 0; t < t1; ++t, ++tcount) {
         const uint32_t ab = tcount & (kPqAcc - 1), aph = (tcount / kPqAcc) & 1u;
         ptx::mbar_wait(bar_acc_empty + 8 * ab, aph ^ 1u);
@@ -173,7 +189,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
           if (ptx::elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < kBK / 16; ++kk)
-              ptx::umma_f16(d_tmem, adesc0 + 2u * kk, bdesc0 + 2u * kk, p.idesc, (kb | kk) != 0 ? 1u : 0u);
+              ptx::umma_f16(d_tmem, adesc0 + 2u * kk, bdesc0 + 2u * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
             ptx::umma_commit(bar_empty + 8 * stage);
             if (kb + 1 == p.k_blocks) ptx::umma_commit(bar_acc_full + 8 * ab);
           }
@@ -182,7 +198,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
         }
       }
     }
-  } else if (warp >= 8 && warp < 12) {
+  } else if ((warp >= 8 && warp < 12) || warp >= 16) {
     // ------------------------------------------------------------------ decoders
     // A stage's list k-block = 128 rows x 64 dims = LPR = 64 / DSUB sub-spaces per row; decoder warp
     // dw owns the tile's 32-row group dw.  LANES WALK THE SUB-SPACES of one list row (DSUB 2: 32
@@ -195,7 +211,8 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
     // Codes are stored sub-space major inside 32-row groups (pq_code_offset), so the 32 codes a
     // lane needs for one (group, k-block) unit are ONE 32-byte piece; the pieces of the k-blocks two
     // steps ahead are already in flight while a k-block is decoded.
-    const int dw = warp - 8;
+    const int dw = warp & 3;               // 32-row group of the stage
+    const int ds = warp >= 16 ? 1 : 0;     // decoder set: k-block steps ds, ds + 2, ds + 4, ...
     constexpr int LPR = 64 / DSUB;     // lanes per list row
     constexpr int RPI = 32 / LPR;      // list rows per warp instruction
     constexpr int WPC = DSUB / 2;      // 32-bit words per codebook entry
@@ -204,9 +221,21 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
     const uint32_t wps = static_cast<uint32_t>(pp.mp) * WPC;        // words per code value in cb16t
     const uint32_t piece = static_cast<uint32_t>(sub) * WPC * 4u;   // lane's byte offset in a row line
     const uint32_t pc = piece >> 4, pw = piece & 15u;
+    // Byte offset of the lane's piece inside an 8-row swizzle atom, for the row (k + rph) & 7: the
+    // rows a lane writes are r + rph with r a multiple of RPI, so k = r & 7 is a compile-time
+    // constant at every store and the stores need no address arithmetic beyond base + immediate.
+    uint32_t lane_swz[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t sw = static_cast<uint32_t>(k + rph) & 7u;
+      lane_swz[k] = sw * 128u + (((pc ^ sw) << 4) | pw);
+    }
+    // ONE iterator walks this set's k-block steps (every other step of the CTA's sequence) two
+    // pieces ahead of the decode; a fetched piece carries its k-block index (-1 = past the end).
     struct KbIter { int item, ti, t1, kb; uint32_t g0; };
-    auto seek = [&](KbIter& it, int item) {   // first k-block of the first non-empty item >= item
-      it.ti = 0; it.kb = 0; it.t1 = 0; it.g0 = 0;
+    KbIter it;
+    auto seek = [&](int item) {               // first non-empty item >= item
+      it.ti = 0; it.t1 = 0; it.g0 = 0;
       while (item < n_items) {
         const int4 w = __ldg(p.work + item);
         it.t1 = (w.z - w.y + kPqM - 1) / kPqM;
@@ -216,37 +245,48 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
       }
       it.item = item;
     };
-    auto step = [&](KbIter& it) {
-      if (++it.kb == p.k_blocks) {
-        it.kb = 0;
-        if (++it.ti == it.t1) seek(it, it.item + n_units);
+    auto advance = [&](int steps) {
+      it.kb += steps;
+      while (it.item < n_items && it.kb >= p.k_blocks) {
+        it.kb -= p.k_blocks;
+        if (++it.ti == it.t1) seek(it.item + n_units);
       }
     };
-    // the 32-byte code piece of this warp's group for k-block `it`
-    auto fetch = [&](const KbIter& it, uint4 (&cv)[2]) {
-      cv[0] = make_uint4(0, 0, 0, 0);
-      cv[1] = make_uint4(0, 0, 0, 0);
+    struct Piece { uint4 c0, c1; int kb; };
+    // the 32-byte code piece of this warp's group for the iterator's k-block, then two steps on
+    auto fetch = [&](Piece& pcs) {
+      pcs.c0 = make_uint4(0, 0, 0, 0);
+      pcs.c1 = make_uint4(0, 0, 0, 0);
+      pcs.kb = -1;
+      if (it.item >= n_items) return;
+      pcs.kb = it.kb;
       const uint32_t g = it.g0 + static_cast<uint32_t>(it.ti) * 4u + static_cast<uint32_t>(dw);
-      if (it.item < n_items && g < pp.n_groups) {
+      if (g < pp.n_groups) {
         const uint4* src = reinterpret_cast<const uint4*>(
             pp.codes + (static_cast<size_t>(g) * pp.mp + static_cast<size_t>(it.kb * LPR + sub)) * 32);
-        cv[0] = __ldg(src);
-        cv[1] = __ldg(src + 1);
+        pcs.c0 = __ldg(src);
+        pcs.c1 = __ldg(src + 1);
       }
+      advance(2);
     };
-    KbIter cur, pre;
-    seek(cur, unit);
-    pre = cur;
-    uint4 cv0[2], cv1[2], cv2[2];
-    fetch(pre, cv0); step(pre);
-    fetch(pre, cv1); step(pre);
-    uint32_t stage = 0, phase = 0;
-    while (cur.item < n_items) {
-      fetch(pre, cv2); step(pre);
+    it.kb = 0;
+    seek(unit);
+    if (ds) advance(1);
+    Piece p0, p1, p2;
+    fetch(p0);
+    fetch(p1);
+    uint32_t stage = static_cast<uint32_t>(ds), phase = 0;
+    while (p0.kb >= 0) {
+      fetch(p2);
       ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
       const uint32_t unit_base = smem_base + stage * kStageBytes + static_cast<uint32_t>(dw) * 4096u;  // 32 rows x 128 B
-      const uint32_t* cb_kb = cb_w + static_cast<uint32_t>(cur.kb * LPR + sub) * WPC;
-      const uint32_t w8[8] = {cv0[0].x, cv0[0].y, cv0[0].z, cv0[0].w, cv0[1].x, cv0[1].y, cv0[1].z, cv0[1].w};
+      uint32_t base8[8];
+#pragma unroll
+      for (int k = 0; k < 8; k += RPI) base8[k] = unit_base + lane_swz[k];
+      const uint32_t* cb_kb = cb_w + static_cast<uint32_t>(p0.kb * LPR + sub) * WPC;
+      const uint32_t cb_sa = smem_base + kOffCb + static_cast<uint32_t>(p0.kb * LPR + sub) * WPC * 4u;
+      const uint32_t wps4 = wps * 4u;
+      const uint32_t w8[8] = {p0.c0.x, p0.c0.y, p0.c0.z, p0.c0.w, p0.c1.x, p0.c1.y, p0.c1.z, p0.c1.w};
       // The look-ups of a batch of rows are all issued before the first store of the batch: the
       // store asm statements are ordering points for the compiler.
       constexpr int kBatch = 16 / WPC;           // rows per batch: 16 registers of look-up results
@@ -256,7 +296,20 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
           const int r = r0 + b * RPI;
-          const uint32_t code = (w8[r >> 2] >> (8u * ((r & 3) + rph))) & 0xFFu;
+          const uint32_t code = __byte_perm(w8[r >> 2], 0u, 0x4440u | static_cast<uint32_t>((r & 3) + rph));   // byte (r & 3) + rph
+          if (kCbSmem) {      // resident codebooks: one IMAD gives the shared-space byte address
+            const uint32_t a = cb_sa + code * wps4;
+            if (WPC == 1) {
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(val[b][0]) : "r"(a));
+            } else if (WPC == 2) {
+              asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(val[b][0]), "=r"(val[b][WPC - 1]) : "r"(a));
+            } else {
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(val[b][0]), "=r"(val[b][1 % WPC]), "=r"(val[b][2 % WPC]), "=r"(val[b][3 % WPC])
+                           : "r"(a));
+            }
+            continue;
+          }
           const uint32_t* src = cb_kb + code * wps;
           if (WPC == 1) {
             val[b][0] = src[0];
@@ -270,9 +323,8 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
         }
 #pragma unroll
         for (int b = 0; b < kBatch; ++b) {
-          const uint32_t rr = static_cast<uint32_t>(r0 + b * RPI) + static_cast<uint32_t>(rph);   // row in the group
-          const uint32_t swz = rr & 7u;
-          const uint32_t dst = unit_base + (rr >> 3) * 1024u + swz * 128u + (((pc ^ swz) << 4) | pw);
+          const int r = r0 + b * RPI;                 // compile-time: the lane writes row r + rph of the group
+          const uint32_t dst = base8[r & 7] + static_cast<uint32_t>(r >> 3) * 1024u;   // base + immediate
           if (WPC == 1) {
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(val[b][0]));
           } else if (WPC == 2) {
@@ -287,10 +339,10 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_full + 8 * stage);
-      if (++stage == kStages) { stage = 0; phase ^= 1u; }
-      cv0[0] = cv1[0]; cv0[1] = cv1[1];
-      cv1[0] = cv2[0]; cv1[1] = cv2[1];
-      step(cur);
+      stage += 2;
+      if (stage >= kStages) { stage -= kStages; phase ^= 1u; }
+      p0 = p1;
+      p1 = p2;
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (append mode)
@@ -393,42 +445,34 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
             mask |= (s[4 * j4 + 2] < tv.z ? 1u : 0u) << (4 * j4 + 2);
             mask |= (s[4 * j4 + 3] < tv.w ? 1u : 0u) << (4 * j4 + 3);
           }
-          if (!__any_sync(0xffffffffu, mask != 0u)) continue;      // the common case
-          const int nh = __popc(mask);
-          int inc = nh;
+          // Hits are sparse (a few per 32 x 16 block of scores, rarely two in one lane): every round
+          // takes each lane's lowest remaining hit, and the queue positions come from the vote of
+          // the lanes that still have one - no prefix sum over the warp.  The first vote is the
+          // "nothing here" test.
+          while (true) {
+            const bool has = mask != 0u;
+            const uint32_t votes = __ballot_sync(0xffffffffu, has);
+            if (votes == 0u) break;
+            const int nb = __popc(votes);
+            if (hq.n + nb > kQueueCap) queue_drain(hq, p.big_cand, p.big_count, p.big_cap, lane);
+            if (has) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1;
+              float v8[8], v4[4], v2[2];
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
-          }
-          const int total = __shfl_sync(0xffffffffu, inc, 31);
-          const bool direct = total > kQueueCap;     // a flood (loose threshold): straight to global
-          if (!direct && hq.n + total > kQueueCap) queue_drain(hq, p.big_cand, p.big_count, p.big_cap, lane);
-          int pos = hq.n + inc - nh;
-          while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            float v8[8], v4[4], v2[2];
+              for (int i = 0; i < 8; ++i) v8[i] = (j & 1) ? s[2 * i + 1] : s[2 * i];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v8[i] = (j & 1) ? s[2 * i + 1] : s[2 * i];
+              for (int i = 0; i < 4; ++i) v4[i] = (j & 2) ? v8[2 * i + 1] : v8[2 * i];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v4[i] = (j & 2) ? v8[2 * i + 1] : v8[2 * i];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) v2[i] = (j & 4) ? v4[2 * i + 1] : v4[2 * i];
-            const float v = (j & 8) ? v2[1] : v2[0];
-            const int col = u * 16 + j;
-            const u64 key = pack_key(v + ci_bias[col], static_cast<uint32_t>(slot));
-            const int qs = ci_q[col];
-            if (direct) {
-              const int gp = atomicAdd(p.big_count + qs, 1);
-              if (gp < p.big_cap) __stcg(p.big_cand + static_cast<size_t>(qs) * p.big_cap + gp, key);
-            } else {
-              hq.keys[pos] = key;
-              hq.slots[pos] = qs;
-              ++pos;
+              for (int i = 0; i < 2; ++i) v2[i] = (j & 4) ? v4[2 * i + 1] : v4[2 * i];
+              const float v = (j & 8) ? v2[1] : v2[0];
+              const int col = u * 16 + j;
+              const int pos = hq.n + __popc(votes & ((1u << lane) - 1u));
+              hq.keys[pos] = pack_key(v + ci_bias[col], static_cast<uint32_t>(slot));
+              hq.slots[pos] = ci_q[col];
             }
+            hq.n += nb;
           }
-          if (!direct) hq.n += total;
         }
         if (n_col_units == 0) {      // a block without a real query (never planned, but keep the protocol sound)
           ptx::tc_fence_before();

@@ -212,6 +212,66 @@ def test_adversarial_order_sorted_database(b2):
     assert topk_parity_report(dd.cpu(), ii.cpu(), db.float(), qs.float(), 100, rtol=RTOL)["ok"]
 
 
+# ---- two-pass selection (small database, large k: the IVF coarse-probe shape)
+TWO_PASS_CASES = [
+    # n, d, q, k, dtype, metric
+    (16384, 128, 3000, 64, "fp16", "sqeuclidean"),   # C4 coarse probe
+    (4096, 768, 1000, 32, "fp16", "sqeuclidean"),    # C3 coarse probe
+    (5003, 96, 700, 50, "bf16", "inner_product"),    # ragged rows and queries
+    (1000, 64, 129, 128, "fp32", "sqeuclidean"),     # fp32 source (three-term operand), k = maximum
+    (300, 40, 5, 2, "bf16", "sqeuclidean"),          # a handful of queries, dim % 8 != 0
+]
+
+
+@pytest.mark.parametrize("n,d,q,k,dtype,metric", TWO_PASS_CASES)
+def test_two_pass_selection_parity(b2, setenv, n, d, q, k, dtype, metric):
+    """B2VS_TWO_PASS=1 routes the search through chunk minima -> exact threshold -> survivors:
+    same answer as the oracle and as the fused path, with a sub-batch size that forces several
+    query batches."""
+    db, qs = make(n, d, q, dtype, metric, seed=77)
+    setenv("B2VS_TWO_PASS", "1")
+    setenv("B2VS_TWO_PASS_CHUNK_MB", "8")
+    d1, i1, ix = check(b2, db, qs, k, metric, id_offset=500)
+    assert ix.last_stats().launches >= 5
+    setenv("B2VS_TWO_PASS", "0")
+    d0, i0 = ix.search(qs.cuda(), k)
+    torch.cuda.synchronize()
+    same = (i0.cpu() == i1).float().mean().item()
+    assert same > 0.999, same          # accumulation order is identical: only exact ties may differ
+    assert torch.allclose(d0.cpu(), d1, rtol=1e-5, atol=1e-5)
+
+
+def test_two_pass_default_heuristic_and_ties(b2, setenv):
+    """The coarse-probe shape takes the two-pass path by default; duplicate rows (exact score
+    ties, also at the threshold) come back smaller id first, and padding rows never appear."""
+    g = torch.Generator().manual_seed(5)
+    base = torch.randn(2048, 64, generator=g)
+    db = torch.cat([base, base]).to(torch.float16)          # row i and row i + 2048 are identical
+    qs = torch.randn(600, 64, generator=g).to(torch.float16)
+    ix = b2.NativeIndex.flat(db.cuda())
+    d1, i1 = ix.search(qs.cuda(), 32)
+    torch.cuda.synchronize()
+    i1 = i1.cpu()
+    assert (i1 >= 0).all() and (i1 < 4096).all()
+    assert (i1[:, 0::2] + 2048 == i1[:, 1::2]).all()        # every hit is followed by its duplicate
+    assert (d1.cpu()[:, 0::2] == d1.cpu()[:, 1::2]).all()
+    setenv("B2VS_TWO_PASS", "0")
+    d0, i0 = ix.search(qs.cuda(), 32)
+    torch.cuda.synchronize()
+    assert (i0.cpu() == i1).all()
+
+
+def test_two_pass_all_rows_identical(b2):
+    """Degenerate ties: every row equal, so every chunk minimum ties at the threshold - the
+    (score, chunk) threshold still admits at most 32 k rows and the answer is ids 0..k-1."""
+    db = torch.ones(4096, 64, dtype=torch.float16) * 0.5
+    qs = torch.randn(640, 64, generator=torch.Generator().manual_seed(3)).to(torch.float16)
+    ix = b2.NativeIndex.flat(db.cuda())
+    d1, i1 = ix.search(qs.cuda(), 48)
+    torch.cuda.synchronize()
+    assert (i1.cpu() == torch.arange(48).expand(640, 48)).all()
+
+
 # ---- large k (the reference's top-2000 retrieval mode)
 @pytest.mark.parametrize("k,metric", [(1000, "sqeuclidean"), (2000, "sqeuclidean"), (500, "inner_product")])
 def test_large_k_exact(b2, k, metric):
