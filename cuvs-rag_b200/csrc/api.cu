@@ -68,6 +68,7 @@ static EnvConfig read_env() {
     const int t = env_int_or("B2VS_IVF_SEED_TILE", 0);
     if (t >= 32 && t <= 256 && t % 32 == 0) c.seed_tile = t;
   }
+  c.pq_debug = std::max(0, env_int_or("B2VS_PQ_DEBUG", 0));
   if (const char* e = std::getenv("B2VS_WORK_EPI")) c.work_epi = (e[0] == '1' || e[0] == '2') ? e[0] - '0' : 0;
   if (const char* e = std::getenv("B2VS_TWO_PASS")) c.two_pass = e[0] == '0' ? 0 : 1;
   c.two_pass_chunk_mb = std::max(0, env_int_or("B2VS_TWO_PASS_CHUNK_MB", 0));

@@ -141,6 +141,7 @@ struct EnvConfig {
   int graph = -1;              // B2VS_GRAPH=0|1: never / always replay small IVF batches as a graph
   int seed_mode = -1;          // B2VS_IVF_SEED=0|1: legacy seed kernels / seeds from the tensor-core pass
   int epi_groups = 0;          // B2VS_EPI_GROUPS=1|2: epilogue warp groups of the flat kernel (0 = heuristic)
+  int pq_debug = 0;            // B2VS_PQ_DEBUG: role-skipping bits of pq_tc_kernel (timing experiments only)
   int work_epi = 0;            // B2VS_WORK_EPI=1|2: epilogue groups of every work-table launch (0 = per call site)
   int seed_lists = 0;          // B2VS_IVF_SEED_LISTS: lists per query scored by the seed pass (1..16)
   int seed_tile = 0;           // B2VS_IVF_SEED_TILE: rows of each seed list that are scored (32..256, multiple of 32)

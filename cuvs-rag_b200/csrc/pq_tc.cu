@@ -45,6 +45,8 @@ int launch_pq_grouped_scan(int dev, const PqGroupedScanArgs& a, cudaStream_t st)
   pp.mp = a.pq_dim;
   pp.n_groups = a.n_groups;
   pp.cb_words = a.pq_dim * 256 * a.dsub / 2;
+  pp.debug = env().pq_debug & (7 | 16);
+  pp.qres = (p.k_blocks <= 2 && !(env().pq_debug & 8)) ? 1 : 0;   // B2VS_PQ_DEBUG bit 8: streaming query blocks (A/B)
   const int grid = std::max(1, std::min(a.max_work, sm_count(dev)));
   const bool cb_smem = pp.cb_words * 4 <= kPqTcMaxCbBytes;
   if (a.dsub == 2) return cb_smem ? launch_one<2, true>(grid, tm_q, pp, st) : launch_one<2, false>(grid, tm_q, pp, st);

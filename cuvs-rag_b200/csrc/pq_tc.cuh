@@ -23,6 +23,12 @@
 // rows, and the UMMAs run with N = 16 ceil(c / 16) - at C4 (c ~ 40) that is 3/8 of the tensor-pipe
 // time, of the shared-memory reads of the N operand and of the TMA traffic of a full block.
 //
+// Resident query blocks (dim <= 128, i.e. at most two k-blocks): the query block of a work item
+// is loaded ONCE (double-buffered across items) instead of once per tile - with it in the stage the
+// bare pipeline (no decode, no MMA, no epilogue) took 0.42 ms of the 0.83 ms C4 launch: four stages
+// in flight against the L2 latency of a TMA load per k-block step.  The stages then hold only the
+// decoded list k-blocks.
+//
 // Warp roles (640 threads): warp 0 = TMA producer (query k-blocks + the tile's ||r^||^2 vector),
 // warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 8-11 and 16-19 = two decoder sets taking
 // alternate k-block stages (a warp of a set owns one 32-row group of the stage: the decode of one
@@ -37,7 +43,7 @@
 
 namespace b2vs {
 
-constexpr int kPqTcThreads = 640;
+constexpr int kPqTcThreads = 768;
 constexpr int kPqM = 128;                                        // list rows per tile (UMMA M)
 constexpr int kPqN = 128;                                        // query rows per block (UMMA N)
 constexpr int kPqTcStages = 4;
@@ -48,15 +54,23 @@ constexpr int kPqBoxBytes = kPqBoxRows * kBK * 2;                // 2 KB
 constexpr int kPqTcStageBytes = kPqListBytes + kPqQueryBytes;    // 32 KB
 constexpr int kPqAcc = 4;                                        // accumulator buffers (4 x 128 TMEM columns)
 constexpr int kPqNormBytes = kPqM * 4;                           // ||r^||^2 of a tile's 128 rows
+constexpr int kPqNormRing = 16;                                  // norm vectors in flight: the loads come from DRAM (~1.5 us),
+                                                                 // four in flight capped the kernel at ~0.5 us per tile
 constexpr int kPqTcMaxCbBytes = 64 * 1024;
-constexpr int kPqTcQueueBytes = 8 * kQueueWarpBytes;             // one hit queue per epilogue warp (bf_tc.cuh)
-constexpr int kPqColInfoBytes = kPqN * 16;                       // per epilogue warp: tau', bias, query, seed slot
-constexpr int kPqTcSmemBytes = kPqTcStages * kPqTcStageBytes + kPqAcc * kPqNormBytes + 256 + kPqTcMaxCbBytes +
-                               kPqTcQueueBytes + 8 * kPqColInfoBytes + 1024;
+// Warps 4-7, 12-15 and 20-23 are the epilogue groups, warps 8-11 and 16-19 the two decoder sets.
+// Measured at C4 (main scan launch): 2 sets + 2 groups 0.85 ms, 1 set + 3 groups 0.82 ms (without
+// the epilogue: 0.55 ms with two sets, 0.67 ms with one - both roles sit near the critical path).
+constexpr int kPqEpiGroups = 3;
+constexpr int kPqDecSets = 2;
+constexpr int kPqTcQueueBytes = 4 * kPqEpiGroups * kQueueWarpBytes;   // one hit queue per epilogue warp (bf_tc.cuh)
+constexpr int kPqColInfoBytes = kPqN * 16;                       // column table of one query block: tau', bias, query, seed slot
+constexpr int kPqTabRing = 4;                                    // column tables in flight (built by warp 3, items ahead)
+constexpr int kPqTcSmemBytes = kPqTcStages * kPqTcStageBytes + kPqNormRing * kPqNormBytes + 512 + kPqTcMaxCbBytes +
+                               kPqTcQueueBytes + kPqTabRing * kPqColInfoBytes + 1024;
 static_assert(kPqTcSmemBytes <= 227 * 1024, "pq_tc_kernel shared memory");
 static_assert(kBK == 64, "the decoder writes 128-byte swizzled rows");
 static_assert(kPqN == kBM, "query blocks are the gather kernels' 128-row groups");
-static_assert(kPqTcStages % 2 == 0, "the two decoder sets take alternate stages");
+static_assert(kPqTcStages % kPqDecSets == 0, "decoder sets take alternate stages");
 
 struct PqTcParams {
   BfTcParams tc;            // work table, thresholds, append buffers (see bf_tc.cuh, work mode)
@@ -66,6 +80,10 @@ struct PqTcParams {
   int mp;                   // sub-spaces per row as stored (= pq_dim: the grouped scan needs pq_dim % 16 == 0)
   uint32_t n_groups;        // 32-row groups in `codes`
   int cb_words;             // pq_dim * 256 * DSUB / 2
+  int qres;                 // 1: the query block of a work item stays resident in shared memory for all of the
+                            // item's tiles (dim <= 128); 0: its k-blocks are re-loaded with every tile
+  int debug;                // B2VS_PQ_DEBUG measurement bits: 1 = epilogue only releases the accumulators,
+                            // 2 = decoders skip look-ups and stores, 4 = no UMMAs (results are garbage)
 };
 
 // DSUB = sub-vector length (2, 4 or 8: a code decodes to 4, 8 or 16 bytes of bf16).
@@ -84,8 +102,8 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
   uint8_t* smem = smem_raw + (smem_base - raw_addr);
 
   constexpr int kOffNorm = kStages * kStageBytes;
-  constexpr int kOffBar = kOffNorm + kPqAcc * kPqNormBytes;
-  constexpr int kOffCb = kOffBar + 256;
+  constexpr int kOffBar = kOffNorm + kPqNormRing * kPqNormBytes;
+  constexpr int kOffCb = kOffBar + 512;
   constexpr int kOffQueue = kOffCb + kPqTcMaxCbBytes;
   constexpr int kOffCol = kOffQueue + kPqTcQueueBytes;
   const uint32_t norm_base = smem_base + kOffNorm;
@@ -95,12 +113,25 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
   const uint32_t bar_empty = bar_base + 8 * kStages;                 // [kStages] MMA -> TMA, decoders
   const uint32_t bar_acc_full = bar_base + 16 * kStages;             // [kPqAcc] MMA -> epilogue
   const uint32_t bar_acc_empty = bar_acc_full + 8 * kPqAcc;          // [kPqAcc] epilogue -> MMA
-  const uint32_t bar_norm_full = bar_acc_full + 16 * kPqAcc;         // [kPqAcc] TMA -> epilogue
-  const uint32_t bar_norm_empty = bar_acc_full + 24 * kPqAcc;        // [kPqAcc] epilogue -> TMA
-  const uint32_t tmem_slot = bar_acc_full + 32 * kPqAcc;
-  static_assert(16 * kStages + 32 * kPqAcc + 8 <= 256, "barrier block");
+  const uint32_t bar_norm_full = bar_base + 256;                     // [kPqNormRing] TMA -> epilogue
+  const uint32_t bar_norm_empty = bar_norm_full + 8 * kPqNormRing;   // [kPqNormRing] epilogue -> TMA
+  static_assert(16 * kPqNormRing <= 256, "norm barriers");
+  const uint32_t bar_q_full = bar_acc_full + 16 * kPqAcc;            // [2] TMA -> MMA   (resident query blocks)
+  const uint32_t bar_q_empty = bar_q_full + 16;                      // [2] MMA -> TMA
+  const uint32_t tmem_slot = bar_q_full + 32;
+  const uint32_t bar_tab_full = bar_base + 192;                      // [kPqTabRing] table builder -> epilogue warps
+  const uint32_t bar_tab_empty = bar_tab_full + 8 * kPqTabRing;      // [kPqTabRing] epilogue warps -> table builder
+  static_assert(16 * kPqTabRing <= 64 && 16 * kStages + 16 * kPqAcc + 32 + 8 <= 192, "barrier block");
+  static_assert(16 * kStages + 16 * kPqAcc + 32 + 8 <= 256, "barrier block");
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem + kOffBar + 16 * kStages + 32 * kPqAcc);
+      reinterpret_cast<volatile uint32_t*>(smem + kOffBar + 16 * kStages + 16 * kPqAcc + 32);
+  // resident mode: stages = decoded list k-blocks only (16 KB apart), the two query buffers behind them
+  const bool qres = pp.qres != 0;
+  const uint32_t stage_stride = qres ? kPqListBytes : kStageBytes;
+  const uint32_t qbuf_base = smem_base + kStages * kPqListBytes;
+  constexpr uint32_t kQBufBytes = 2 * kPqQueryBytes;                 // two k-blocks of 128 query rows
+  static_assert(kPqTcStages * kPqListBytes + 2 * 2 * kPqQueryBytes <= kPqTcStages * kPqTcStageBytes,
+                "resident query buffers fit in the streaming stages' footprint");
   uint32_t* cb_s = reinterpret_cast<uint32_t*>(smem + kOffCb);
 
   const int warp = threadIdx.x >> 5;
@@ -110,14 +141,24 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      ptx::mbar_init(bar_full + 8 * i, 1 + 4);   // TMA arrive(+tx) and the four decoder warps
+      ptx::mbar_init(bar_full + 8 * i, qres ? 4 : 1 + 4);   // (TMA arrive(+tx) and) the four decoder warps of a set
       ptx::mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < kPqNormRing; ++i) {
+      ptx::mbar_init(bar_norm_full + 8 * i, 1);
+      ptx::mbar_init(bar_norm_empty + 8 * i, 4);    // the four warps of the epilogue group that owns the tile
+    }
+    for (int i = 0; i < kPqTabRing; ++i) {
+      ptx::mbar_init(bar_tab_full + 8 * i, 1);
+      ptx::mbar_init(bar_tab_empty + 8 * i, 4 * kPqEpiGroups);   // every epilogue warp
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(bar_q_full + 8 * i, 1);
+      ptx::mbar_init(bar_q_empty + 8 * i, 1);
     }
     for (int i = 0; i < kPqAcc; ++i) {
       ptx::mbar_init(bar_acc_full + 8 * i, 1);
       ptx::mbar_init(bar_acc_empty + 8 * i, 4);    // the four warps of the epilogue group that owns the tile
-      ptx::mbar_init(bar_norm_full + 8 * i, 1);
-      ptx::mbar_init(bar_norm_empty + 8 * i, 4);
     }
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tm_q);
@@ -137,21 +178,48 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    uint32_t stage = 0, phase = 0, tcount = 0;
+    uint32_t stage = 0, phase = 0, tcount = 0, icount = 0;
     for (int item = unit; item < n_items; item += n_units) {
       const int4 w = __ldg(p.work + item);
       const int q_row0 = w.x * kPqN;
       const int t1 = (w.z - w.y + kPqM - 1) / kPqM;
+      if (t1 <= 0) continue;
       const int n_box = (max(w.w, 1) + 15) >> 4;          // 16-row boxes that hold real queries
-      for (int ti = 0; ti < t1; ++ti, ++tcount) {
-        const uint32_t ab = tcount & (kPqAcc - 1), aph = (tcount / kPqAcc) & 1u;
-        ptx::mbar_wait(bar_norm_empty + 8 * ab, aph ^ 1u);
+      if (qres) {
+        // the item's whole query block, once: buffer icount & 1 (the MMA warp frees it after the item's last tile)
+        const uint32_t ib = icount & 1u, iph = (icount >> 1) & 1u;
+        ++icount;
+        ptx::mbar_wait(bar_q_empty + 8 * ib, iph ^ 1u);
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(bar_norm_full + 8 * ab, kPqNormBytes);
-          ptx::bulk_load_1d(norm_base + ab * kPqNormBytes, p.beta + static_cast<size_t>(w.y + ti * kPqM),
-                            kPqNormBytes, bar_norm_full + 8 * ab);
+          ptx::mbar_arrive_expect_tx(bar_q_full + 8 * ib, static_cast<uint32_t>(p.k_blocks * n_box) * kPqBoxBytes);
+          for (int kb = 0; kb < p.k_blocks; ++kb)
+            for (int b = 0; b < n_box; ++b)
+              ptx::tma_load_2d_hint(qbuf_base + ib * kQBufBytes + kb * kPqQueryBytes + b * kPqBoxBytes, &tm_q,
+                                    bar_q_full + 8 * ib, kb * kBK, q_row0 + b * kPqBoxRows, ptx::kEvictLast);
         }
         __syncwarp();
+      }
+      for (int ti = 0; ti < t1; ++ti, ++tcount) {
+        const uint32_t nb = tcount & (kPqNormRing - 1), nph = (tcount / kPqNormRing) & 1u;
+        ptx::mbar_wait(bar_norm_empty + 8 * nb, nph ^ 1u);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(bar_norm_full + 8 * nb, kPqNormBytes);
+          ptx::bulk_load_1d(norm_base + nb * kPqNormBytes, p.beta + static_cast<size_t>(w.y + ti * kPqM),
+                            kPqNormBytes, bar_norm_full + 8 * nb);
+        }
+        // The tile's PQ codes (4 groups x mp x 32 bytes, contiguous) into L2 now: this warp runs a
+        // norm ring ahead of the epilogue, i.e. several tiles ahead of the decoders, whose own
+        // register prefetch (two k-block steps) does not cover the DRAM latency.
+        {
+          const size_t tile_off = (static_cast<size_t>(static_cast<uint32_t>(w.y) >> 5) + static_cast<size_t>(ti) * 4u) *
+                                  static_cast<size_t>(pp.mp) * 32u;
+          const size_t end_off = static_cast<size_t>(pp.n_groups) * static_cast<size_t>(pp.mp) * 32u;
+          const uint32_t tile_bytes = 4u * static_cast<uint32_t>(pp.mp) * 32u;
+          for (uint32_t o = static_cast<uint32_t>(lane) * 128u; o < tile_bytes; o += 32u * 128u)
+            if (tile_off + o < end_off) ptx::prefetch_l2(pp.codes + tile_off + o);
+        }
+        __syncwarp();
+        if (qres) continue;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
           if (ptx::elect_one()) {
@@ -168,13 +236,20 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    uint32_t stage = 0, phase = 0, tcount = 0;
+    uint32_t stage = 0, phase = 0, tcount = 0, icount = 0;
     for (int item = unit; item < n_items; item += n_units) {
       const int4 w = __ldg(p.work + item);
       const int t1 = (w.z - w.y + kPqM - 1) / kPqM;
+      if (t1 <= 0) continue;
       // N extent = the block's real query rows, in 16-column units (instruction descriptor bits [17,23) = N >> 3)
       const uint32_t n_ext = static_cast<uint32_t>((max(w.w, 1) + 15) & ~15);
       const uint32_t idesc = (p.idesc & ~(0x3Fu << 17)) | ((n_ext >> 3) << 17);
+      const uint32_t ib = icount & 1u, iph = (icount >> 1) & 1u;
+      ++icount;
+      if (qres) {
+        ptx::mbar_wait(bar_q_full + 8 * ib, iph);
+        ptx::tc_fence_after();
+      }
       for (int t = 0; t < t1; ++t, ++tcount) {
         const uint32_t ab = tcount & (kPqAcc - 1), aph = (tcount / kPqAcc) & 1u;
         ptx::mbar_wait(bar_acc_empty + 8 * ab, aph ^ 1u);
@@ -183,22 +258,72 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           ptx::mbar_wait(bar_full + 8 * stage, phase);
           ptx::tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * kStageBytes;           // decoded list rows: M operand
+          const uint32_t a_addr = smem_base + stage * stage_stride;          // decoded list rows: M operand
+          const uint32_t b_addr = qres ? qbuf_base + ib * kQBufBytes + kb * kPqQueryBytes : a_addr + kPqListBytes;
           const uint64_t adesc0 = ptx::make_kmajor_desc<kBK * 2>(a_addr);
-          const uint64_t bdesc0 = ptx::make_kmajor_desc<kBK * 2>(a_addr + kPqListBytes);   // queries: N operand
+          const uint64_t bdesc0 = ptx::make_kmajor_desc<kBK * 2>(b_addr);    // queries: N operand
           if (ptx::elect_one()) {
+            if (!(pp.debug & 4))
 #pragma unroll
             for (int kk = 0; kk < kBK / 16; ++kk)
               ptx::umma_f16(d_tmem, adesc0 + 2u * kk, bdesc0 + 2u * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
             ptx::umma_commit(bar_empty + 8 * stage);
-            if (kb + 1 == p.k_blocks) ptx::umma_commit(bar_acc_full + 8 * ab);
+            if (kb + 1 == p.k_blocks) {
+              ptx::umma_commit(bar_acc_full + 8 * ab);
+              // the item's last MMAs: the query buffer is free once they retire
+              if (qres && t + 1 == t1) ptx::umma_commit(bar_q_empty + 8 * ib);
+            }
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if ((warp >= 8 && warp < 12) || warp >= 16) {
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ column-table builder
+    // Per work item: threshold minus bias, bias, query slot and seed slot of each of the block's 128
+    // query rows, for ALL epilogue warps, kPqTabRing items ahead of them (each epilogue warp used to
+    // build its own copy at the start of every item: two dependent L2 round trips, ~1.5 us, on the
+    // epilogue's critical path once per ~6 tiles).
+    const float inf = __int_as_float(0x7f800000);
+    uint32_t icount = 0;
+    for (int item = unit; item < n_items; item += n_units) {
+      const int4 w = __ldg(p.work + item);
+      if (w.z - w.y <= 0) continue;
+      const uint32_t slot = icount & (kPqTabRing - 1), tph = (icount / kPqTabRing) & 1u;
+      ++icount;
+      ptx::mbar_wait(bar_tab_empty + 8 * slot, tph ^ 1u);
+      float* const t_tau = reinterpret_cast<float*>(smem + kOffCol + slot * kPqColInfoBytes);
+      float* const t_bias = t_tau + kPqN;
+      int* const t_q = reinterpret_cast<int*>(t_bias + kPqN);
+      int* const t_slot = t_q + kPqN;
+      int query[kPqN / 32];
+#pragma unroll
+      for (int j = 0; j < kPqN / 32; ++j)
+        query[j] = __ldg(p.row_query + static_cast<size_t>(w.x) * kPqN + lane + 32 * j);
+#pragma unroll
+      for (int j = 0; j < kPqN / 32; ++j) {
+        const int col = lane + 32 * j;
+        const size_t v_row = static_cast<size_t>(w.x) * kPqN + col;
+        float tq = -inf, bias = 0.f;
+        if (query[j] >= 0) {
+          bias = __ldg(pp.row_bias + v_row);
+          const float t = p.tau_init[query[j]];
+          // The threshold is on the full score (bias + alpha*acc + beta); the tile part is compared
+          // against tau - bias, widened by a few ulps of the larger magnitude so that a key whose
+          // rounded sum (v + bias) lies at the threshold is never lost to the rounding of
+          // (tau - bias).  A slightly larger candidate set is harmless: the select step is exact.
+          tq = (t - bias) + 4.f * 1.1920929e-7f * fmaxf(fabsf(t), fabsf(bias));
+        }
+        t_tau[col] = tq;
+        t_bias[col] = bias;
+        t_q[col] = max(query[j], 0);
+        t_slot[col] = (p.seed_all && query[j] >= 0) ? __ldg(p.row_slot + v_row) : 0;
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_tab_full + 8 * slot);
+    }
+  } else if ((warp >= 8 && warp < 12) || (warp >= 16 && warp < 20)) {
     // ------------------------------------------------------------------ decoders
     // A stage's list k-block = 128 rows x 64 dims = LPR = 64 / DSUB sub-spaces per row; decoder warp
     // dw owns the tile's 32-row group dw.  LANES WALK THE SUB-SPACES of one list row (DSUB 2: 32
@@ -212,7 +337,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
     // lane needs for one (group, k-block) unit are ONE 32-byte piece; the pieces of the k-blocks two
     // steps ahead are already in flight while a k-block is decoded.
     const int dw = warp & 3;               // 32-row group of the stage
-    const int ds = warp >= 16 ? 1 : 0;     // decoder set: k-block steps ds, ds + 2, ds + 4, ...
+    const int ds = warp >= 16 ? 1 : 0;     // decoder set: k-block steps ds, ds + kPqDecSets, ...
     constexpr int LPR = 64 / DSUB;     // lanes per list row
     constexpr int RPI = 32 / LPR;      // list rows per warp instruction
     constexpr int WPC = DSUB / 2;      // 32-bit words per codebook entry
@@ -267,7 +392,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
         pcs.c0 = __ldg(src);
         pcs.c1 = __ldg(src + 1);
       }
-      advance(2);
+      advance(kPqDecSets);
     };
     it.kb = 0;
     seek(unit);
@@ -279,7 +404,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
     while (p0.kb >= 0) {
       fetch(p2);
       ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-      const uint32_t unit_base = smem_base + stage * kStageBytes + static_cast<uint32_t>(dw) * 4096u;  // 32 rows x 128 B
+      const uint32_t unit_base = smem_base + stage * stage_stride + static_cast<uint32_t>(dw) * 4096u;  // 32 rows x 128 B
       uint32_t base8[8];
 #pragma unroll
       for (int k = 0; k < 8; k += RPI) base8[k] = unit_base + lane_swz[k];
@@ -290,6 +415,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
       // The look-ups of a batch of rows are all issued before the first store of the batch: the
       // store asm statements are ordering points for the compiler.
       constexpr int kBatch = 16 / WPC;           // rows per batch: 16 registers of look-up results
+      if (!(pp.debug & 2))
 #pragma unroll
       for (int r0 = 0; r0 < 32; r0 += RPI * kBatch) {
         uint32_t val[kBatch][WPC];
@@ -339,7 +465,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_full + 8 * stage);
-      stage += 2;
+      stage += kPqDecSets;
       if (stage >= kStages) { stage -= kStages; phase ^= 1u; }
       p0 = p1;
       p1 = p2;
@@ -347,12 +473,11 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (append mode)
     // Thread = one list row of the tile (TMEM lane 32 * ew + lane), columns = the group's queries.
-    // The two groups of four warps (4-7, 12-15) take alternate tiles.  Per work item every warp
-    // builds its own copy of the column table (threshold minus bias, bias, query slot, seed slot of
-    // each of the block's 128 query rows) in shared memory; only the 16-column units that hold real
-    // queries are read back from TMEM.
+    // The groups of four warps take tiles round-robin.  The column table of the item's query block
+    // (threshold minus bias, bias, query slot, seed slot of its 128 rows) comes from warp 3; only
+    // the 16-column units that hold real queries are read back from TMEM.
     const int ew = warp & 3;
-    const uint32_t eg = warp >= 12 ? 1u : 0u;
+    const uint32_t eg = warp < 8 ? 0u : (warp < 16 ? 1u : 2u);   // warps 4-7, 12-15, 20-23
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
     const float inf = __int_as_float(0x7f800000);
     const int wi = ew + 4 * static_cast<int>(eg);
@@ -360,67 +485,60 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
     hq.keys = reinterpret_cast<u64*>(smem + kOffQueue + wi * kQueueWarpBytes);
     hq.slots = reinterpret_cast<int*>(smem + kOffQueue + wi * kQueueWarpBytes + kQueueCap * 8);
     hq.n = 0;
-    float* const ci_tau = reinterpret_cast<float*>(smem + kOffCol + wi * kPqColInfoBytes);
-    float* const ci_bias = ci_tau + kPqN;
-    int* const ci_q = reinterpret_cast<int*>(ci_bias + kPqN);
-    int* const ci_slot = ci_q + kPqN;
-    uint32_t tcount = 0;
+    uint32_t tcount = 0, icount = 0;
     for (int item = unit; item < n_items; item += n_units) {
       const int4 w = __ldg(p.work + item);
       const int row_begin = w.y, row_end = w.z;
       const int t1 = (w.z - w.y + kPqM - 1) / kPqM;
-      // ---- column table of this item's query block (real queries are contiguous from column 0)
-      __syncwarp();
-      int n_real = 0;
-#pragma unroll
-      for (int j = 0; j < kPqN / 32; ++j) {
-        const int col = lane + 32 * j;
-        const size_t v_row = static_cast<size_t>(w.x) * kPqN + col;
-        const int query = __ldg(p.row_query + v_row);
-        float tq = -inf, bias = 0.f;
-        if (query >= 0) {
-          bias = __ldg(pp.row_bias + v_row);
-          const float t = p.tau_init[query];
-          // The threshold is on the full score (bias + alpha*acc + beta); the tile part is compared
-          // against tau - bias, widened by a few ulps of the larger magnitude so that a key whose
-          // rounded sum (v + bias) lies at the threshold is never lost to the rounding of
-          // (tau - bias).  A slightly larger candidate set is harmless: the select step is exact.
-          tq = (t - bias) + 4.f * 1.1920929e-7f * fmaxf(fabsf(t), fabsf(bias));
-        }
-        ci_tau[col] = tq;
-        ci_bias[col] = bias;
-        ci_q[col] = max(query, 0);
-        ci_slot[col] = p.seed_all ? __ldg(p.row_slot + v_row) : 0;
-        n_real += __popc(__ballot_sync(0xffffffffu, query >= 0));
-      }
-      __syncwarp();
+      if (t1 <= 0) continue;
+      const uint32_t tslot = icount & (kPqTabRing - 1), tph = (icount / kPqTabRing) & 1u;
+      ++icount;
+      ptx::mbar_wait(bar_tab_full + 8 * tslot, tph);
+      const float* const ci_tau = reinterpret_cast<const float*>(smem + kOffCol + tslot * kPqColInfoBytes);
+      const float* const ci_bias = ci_tau + kPqN;
+      const int* const ci_q = reinterpret_cast<const int*>(ci_bias + kPqN);
+      const int* const ci_slot = ci_q + kPqN;
+      const int n_real = max(w.w, 0);            // real queries are contiguous from column 0
       const int n_col_units = (n_real + 15) >> 4;
       for (int ti = 0; ti < t1; ++ti, ++tcount) {
-        if ((tcount & 1u) != eg) continue;          // the other epilogue group's tile
+        if (tcount % kPqEpiGroups != eg) continue;  // another epilogue group's tile
         const uint32_t ab = tcount & (kPqAcc - 1), aph = (tcount / kPqAcc) & 1u;
         ptx::mbar_wait(bar_acc_full + 8 * ab, aph);
-        ptx::mbar_wait(bar_norm_full + 8 * ab, aph);
+        const uint32_t nb = tcount & (kPqNormRing - 1), nph = (tcount / kPqNormRing) & 1u;
+        ptx::mbar_wait(bar_norm_full + 8 * nb, nph);
         ptx::tc_fence_after();
+        if (pp.debug & 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::mbar_arrive(bar_acc_empty + 8 * ab);
+            ptx::mbar_arrive(bar_norm_empty + 8 * nb);
+          }
+          continue;
+        }
         const int slot = row_begin + ti * kPqM + ew * 32 + lane;     // this thread's list slot
         // rows past the end of the list (tile tail) belong to the next list: they never qualify
-        const float beta_row = slot < row_end ? norm_ptr[ab * kPqM + ew * 32 + lane] : inf;
+        const float beta_row = slot < row_end ? norm_ptr[nb * kPqM + ew * 32 + lane] : inf;
         const uint32_t tile_taddr = lane_taddr + ab * kPqN;
+        // the TMEM load of unit u + 1 is in flight while unit u is scored
+        uint32_t acc[16];
+        if (n_col_units > 0) ptx::tmem_ld_32x32b_x16(tile_taddr, acc);
         for (int u = 0; u < n_col_units; ++u) {
-          uint32_t acc[16];
-          ptx::tmem_ld_32x32b_x16(tile_taddr + u * 16, acc);
           ptx::tmem_ld_wait();
-          if (u + 1 == n_col_units) {
+          float s[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s[j] = fmaf(p.alpha, __uint_as_float(acc[j]), beta_row);
+          if (u + 1 < n_col_units) {
+            ptx::tmem_ld_32x32b_x16(tile_taddr + (u + 1) * 16, acc);
+          } else {
             // this warp's last TMEM read of the tile has landed: hand the accumulator back
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
               ptx::mbar_arrive(bar_acc_empty + 8 * ab);
-              ptx::mbar_arrive(bar_norm_empty + 8 * ab);
+              ptx::mbar_arrive(bar_norm_empty + 8 * nb);
             }
           }
-          float s[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) s[j] = fmaf(p.alpha, __uint_as_float(acc[j]), beta_row);
           if (p.seed_all) {
             // seed pass: every (real query, list row) score goes to its fixed place
             if (slot < row_end) {
@@ -449,6 +567,7 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
           // takes each lane's lowest remaining hit, and the queue positions come from the vote of
           // the lanes that still have one - no prefix sum over the warp.  The first vote is the
           // "nothing here" test.
+          if (pp.debug & 16) mask = 0u;
           while (true) {
             const bool has = mask != 0u;
             const uint32_t votes = __ballot_sync(0xffffffffu, has);
@@ -479,10 +598,12 @@ pq_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const PqTcParams pp) {
           __syncwarp();
           if (lane == 0) {
             ptx::mbar_arrive(bar_acc_empty + 8 * ab);
-            ptx::mbar_arrive(bar_norm_empty + 8 * ab);
+            ptx::mbar_arrive(bar_norm_empty + 8 * nb);
           }
         }
       }
+      __syncwarp();      // every lane is done with the item's column table
+      if (lane == 0) ptx::mbar_arrive(bar_tab_empty + 8 * tslot);
     }
     queue_drain(hq, p.big_cand, p.big_count, p.big_cap, lane);
   }

@@ -46,7 +46,10 @@ for s in settings:
     for _ in range(20):
         ix.search(q, 10, n_probes=npb, refine_ratio=rr)
     e1.record(); torch.cuda.synchronize()
+    ix.search(q, 10, n_probes=npb, refine_ratio=rr, time_kernel=True)
+    torch.cuda.synchronize()
+    kernel_ms = ix.last_stats().kernel_ms
     hit = (ii.unsqueeze(2) == gt.unsqueeze(1)).any(2).float().mean().item()
     print(json.dumps({"config": name, "n_probes": npb, "refine": rr, "setting": s,
-                      "ms_per_batch": round(e0.elapsed_time(e1) / 20, 4), "recall@10": round(hit, 4),
+                      "ms_per_batch": round(e0.elapsed_time(e1) / 20, 4), "scan_kernel_ms": round(kernel_ms, 4), "recall@10": round(hit, 4),
                       "mean_candidates": round(ix.last_stats().mean_candidates, 1)}), flush=True)
