@@ -61,6 +61,7 @@ static EnvConfig read_env() {
   c.coarse_scan_ctas = env_int_or("B2VS_COARSE_SCAN_CTAS", -1);
   c.no_item_sort = std::getenv("B2VS_NO_ITEM_SORT") != nullptr;
   if (const char* e = std::getenv("B2VS_GRAPH")) c.graph = e[0] == '0' ? 0 : 1;
+  c.graph_maxq = std::max(0, env_int_or("B2VS_GRAPH_MAXQ", 0));
   if (const char* e = std::getenv("B2VS_IVF_SEED")) c.seed_mode = e[0] == '0' ? 0 : 1;
   {
     const int v = env_int_or("B2VS_IVF_SEED_LISTS", 0);

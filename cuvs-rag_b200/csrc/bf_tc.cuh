@@ -114,6 +114,9 @@ struct BfTcParams {
   float* chunk_min;
   int chunk_ld;
   const int* tau_chunk;
+  // work mode: bytes one stage receives when the list-tile map's box is shorter than 256 rows (the
+  // seed pass loads only the head of each list); 0 = a full stage
+  uint32_t stage_tx;
 };
 constexpr int kSeedSlotRows = 256;   // = one tile: the seed pass scores the first tile of a list
 
@@ -442,7 +445,7 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                 ptx::tma_load_2d_2sm_hint(a_dst, &tm_q, fb, kb * kBK, q_row0, ptx::kEvictLast);
                 ptx::tma_load_2d_2sm(a_dst + Cfg::kABytes, &tm_x, fb, kb * kBK, x_row0);
               } else {
-                ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
+                ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, (kWork && p.stage_tx) ? p.stage_tx : kStageBytes);
                 // the query block is re-read for every db tile: ask L2 to keep it (evict-last)
                 ptx::tma_load_2d_hint(a_dst, &tm_q, bar_full + 8 * stage, kb * kBK, q_row0,
                                       ptx::kEvictLast);

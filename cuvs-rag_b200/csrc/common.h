@@ -139,6 +139,7 @@ struct EnvConfig {
   int coarse_scan_ctas = -1;   // B2VS_COARSE_SCAN_CTAS
   bool no_item_sort = false;   // B2VS_NO_ITEM_SORT: per-item scan without the list ordering
   int graph = -1;              // B2VS_GRAPH=0|1: never / always replay small IVF batches as a graph
+  int graph_maxq = 0;          // B2VS_GRAPH_MAXQ: largest batch replayed as a graph (default 64)
   int seed_mode = -1;          // B2VS_IVF_SEED=0|1: legacy seed kernels / seeds from the tensor-core pass
   int epi_groups = 0;          // B2VS_EPI_GROUPS=1|2: epilogue warp groups of the flat kernel (0 = heuristic)
   int pq_debug = 0;            // B2VS_PQ_DEBUG: role-skipping bits of pq_tc_kernel (timing experiments only)
@@ -241,6 +242,8 @@ struct GroupedScanArgs {
   float* chunk_min;       // seed_all == 2: [nq][chunk_ld] minimum of every 32-row chunk
   int chunk_ld;
   const int* tau_chunk;   // optional [nq]: thresholds are (score, chunk) pairs (see BfTcParams)
+  int x_box_rows;         // 0 / 256: whole 256-row list tiles; 64 or 128: only that many rows of each (single-tile)
+                          // item are loaded and multiplied - the seed pass reads just the head of every list
   int epi_groups;         // 0/1: four epilogue warps; 2: eight (two groups on alternate tiles) for
                           // launches whose epilogue, not HBM, sets the pace
 };

@@ -618,7 +618,8 @@ int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st) {
   CUtensorMap tm_q, tm_xl;
   const int xkb = static_cast<int>(ceil_div(a.kdim, kBK));
   B2VS_TRY(encode_tmap_2d(&tm_q, a.q_mat, a.ab_format, a.q_rows, a.q_split ? 2 * xkb * kBK : a.kdim, kBM));
-  B2VS_TRY(encode_tmap_2d(&tm_xl, a.x_mat, a.ab_format, a.x_rows, a.kdim, kBN));
+  const int box = (a.x_box_rows == 64 || a.x_box_rows == 128) ? a.x_box_rows : kBN;
+  B2VS_TRY(encode_tmap_2d(&tm_xl, a.x_mat, a.ab_format, a.x_rows, a.kdim, box));
   BfTcParams p{};
   p.beta = a.beta;
   p.k_blocks = a.q_split ? 2 * xkb : xkb;
@@ -626,7 +627,8 @@ int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st) {
   p.k = 1;
   p.tile_stride = 1;
   p.alpha = a.alpha;
-  p.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(a.ab_format), kBM, kBN);
+  p.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(a.ab_format), kBM, box);   // N = rows of a list tile
+  p.stage_tx = box == kBN ? 0u : static_cast<uint32_t>(TcCfg<1>::kABytes + box * kBK * 2);
   p.tau_init = a.tau;
   p.big_cand = a.cand;
   p.big_count = a.count;

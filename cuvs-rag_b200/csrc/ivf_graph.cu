@@ -115,8 +115,15 @@ int ivf_search(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
   IvfData* d = static_cast<IvfData*>(index->ivf);
   B2VS_CHECK(d != nullptr, B2VS_EINVAL, "IVF index has no list data");
   const int ov = graph_override();
-  const bool want_graph = ov == 1 || (ov < 0 && (sp.flags & B2VS_FLAG_GRAPH) != 0);
-  if (want_graph && nq <= kGraphMaxQueries && k >= 1 && (sp.flags & B2VS_FLAG_TIME_KERNEL) == 0 &&
+  // Graph replay: small batches (nq <= 64) when the call asks with B2VS_FLAG_GRAPH, and large
+  // batches (nq >= 2048, fixed shapes in serving) by default - the ~27 launches of a 10K-query
+  // batch leave ~2 us gaps that add up to 0.03-0.06 ms of a 1.7-3.7 ms step (measured at C3 / C4).
+  // B2VS_GRAPH=1 / =0 force it for every eligible call / never; B2VS_GRAPH_MAXQ moves the upper bound.
+  const bool small = nq <= kGraphMaxQueries, large = nq >= kGraphAutoMinQueries;
+  const bool want_graph = ov == 1 || (ov < 0 && ((small && (sp.flags & B2VS_FLAG_GRAPH) != 0) || large));
+  const int graph_maxq = env().graph_maxq > 0 ? env().graph_maxq : kGraphAutoMaxQueries;
+  if (want_graph && (small || large || ov == 1) && nq <= graph_maxq && k >= 1 &&
+      (sp.flags & B2VS_FLAG_TIME_KERNEL) == 0 &&
       !uses_bigk_path(index, d, k, sp)) {
     bool handled = false;
     B2VS_TRY(ivf_search_graphed(index, d, q, q_dtype, nq, k, sp, out_d, out_i, st, &handled));

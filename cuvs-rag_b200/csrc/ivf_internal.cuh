@@ -64,7 +64,9 @@ struct SearchGraph {
     io = nullptr;
   }
 };
-constexpr int kGraphMaxQueries = 64;   // larger batches are no longer launch-bound
+constexpr int kGraphMaxQueries = 64;   // opt-in (B2VS_FLAG_GRAPH) replay of launch-bound small batches
+constexpr int kGraphAutoMinQueries = 2048;    // large batches are replayed as graphs by default ...
+constexpr int kGraphAutoMaxQueries = 1 << 20; // ... up to here
 constexpr int kGraphMaxEntries = 16;
 
 struct IvfData {

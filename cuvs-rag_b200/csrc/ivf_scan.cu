@@ -1044,7 +1044,11 @@ gather_group_residuals128_kernel(const long long* __restrict__ probe_ids, const 
   float4 qv[kGatherIlp], cv[kGatherIlp];
 #pragma unroll
   for (int t = 0; t < kGatherIlp; ++t) {
-    qv[t] = __ldg(reinterpret_cast<const float4*>(qf + static_cast<size_t>(q[t]) * 128) + lane);
+    // consecutive items are consecutive probes of one query: its row is loaded once per warp
+    if (t == 0 || q[t] != q[0])
+      qv[t] = __ldg(reinterpret_cast<const float4*>(qf + static_cast<size_t>(q[t]) * 128) + lane);
+    else
+      qv[t] = qv[0];
     cv[t] = __ldg(reinterpret_cast<const float4*>(cent + static_cast<size_t>(list[t] < 0 ? 0 : list[t]) * 128) + lane);
   }
 #pragma unroll

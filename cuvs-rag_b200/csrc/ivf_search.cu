@@ -67,6 +67,7 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
   ga.row_query = d->ws_g_rowq.as<int>(); ga.tau = d->ws_g_tau.as<float>();
   ga.cand = d->ws_g_cand.as<u64>(); ga.count = d->ws_g_cnt.as<int>(); ga.cap = cap;
   ga.row_slot = d->ws_g_rowslot.as<int>(); ga.seed_all = row_limit > 0 ? 1 : 0;
+  if (row_limit == 64 || row_limit == 128) ga.x_box_rows = row_limit;   // seed pass: load only the head rows
   if (timed) B2VS_CUDA(cudaEventRecord(d->ev0, st));
   B2VS_TRY(launch_grouped_scan(index->dev, ga, st));
   if (timed) B2VS_CUDA(cudaEventRecord(d->ev1, st));

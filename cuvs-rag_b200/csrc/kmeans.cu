@@ -66,20 +66,34 @@ __global__ void histogram_kernel(const int* __restrict__ labels, int64_t n, int*
 }
 
 // Exclusive scan of list sizes rounded up to `pad`; single block of 1024 threads: per-thread
-// partial sums, a shuffle scan inside every warp, and warp 0 scanning the 32 warp totals.
+// partial sums over a contiguous range, a shuffle scan inside every warp, and warp 0 scanning the
+// 32 warp totals.  A thread's sizes are loaded 16 at a time into registers, all loads in flight
+// together (one load per loop trip made the kernel a chain of n_lists / 1024 L2 round trips:
+// 19 us for 16 K lists, twice per search).
 __global__ void __launch_bounds__(1024)
 scan_sizes_kernel(const int* __restrict__ sizes, int n_lists, int pad, uint32_t* __restrict__ offsets) {
   __shared__ uint32_t warp_tot[32];
+  constexpr int kChunk = 16;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int per = (n_lists + blockDim.x - 1) / blockDim.x;
   const int lo = t * per, hi = min(n_lists, lo + per);
+  const bool one_chunk = per <= kChunk;          // the usual case: everything stays in registers
+  uint32_t v[kChunk];
   uint32_t s = 0;
-  for (int i = lo; i < hi; ++i) s += static_cast<uint32_t>((sizes[i] + pad - 1) / pad * pad);
+  for (int i0 = lo; i0 < hi; i0 += kChunk) {
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k) v[k] = i0 + k < hi ? static_cast<uint32_t>(sizes[i0 + k]) : 0u;
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k) {
+      v[k] = (v[k] + pad - 1) / pad * pad;
+      s += v[k];
+    }
+  }
   uint32_t inc = s;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += v;
+    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
   }
   if (lane == 31) warp_tot[warp] = inc;
   __syncthreads();
@@ -88,17 +102,25 @@ scan_sizes_kernel(const int* __restrict__ sizes, int n_lists, int pad, uint32_t*
     uint32_t winc = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, winc, o);
-      if (lane >= o) winc += v;
+      const uint32_t u = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += u;
     }
     warp_tot[lane] = winc - w;                     // exclusive prefix of the warp totals
     if (lane == 31) offsets[n_lists] = winc;
   }
   __syncthreads();
   uint32_t run = warp_tot[warp] + inc - s;
-  for (int i = lo; i < hi; ++i) {
-    offsets[i] = run;
-    run += static_cast<uint32_t>((sizes[i] + pad - 1) / pad * pad);
+  for (int i0 = lo; i0 < hi; i0 += kChunk) {
+    if (!one_chunk) {
+#pragma unroll
+      for (int k = 0; k < kChunk; ++k)
+        v[k] = i0 + k < hi ? (static_cast<uint32_t>(sizes[i0 + k]) + pad - 1) / pad * pad : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k) {
+      if (i0 + k < hi) offsets[i0 + k] = run;
+      run += v[k];
+    }
   }
 }
 
