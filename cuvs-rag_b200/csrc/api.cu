@@ -62,6 +62,7 @@ static EnvConfig read_env() {
   c.no_item_sort = std::getenv("B2VS_NO_ITEM_SORT") != nullptr;
   if (const char* e = std::getenv("B2VS_GRAPH")) c.graph = e[0] == '0' ? 0 : 1;
   c.graph_maxq = std::max(0, env_int_or("B2VS_GRAPH_MAXQ", 0));
+  if (const char* e = std::getenv("B2VS_PLAN_OVERLAP")) c.plan_overlap = e[0] == '0' ? 0 : 1;
   if (const char* e = std::getenv("B2VS_IVF_SEED")) c.seed_mode = e[0] == '0' ? 0 : 1;
   {
     const int v = env_int_or("B2VS_IVF_SEED_LISTS", 0);
@@ -142,6 +143,7 @@ extern "C" int b2vs_reload_env(void) {
   env();  // make sure the once-flag is spent before overwriting
   std::lock_guard<std::mutex> lock(g_env_mutex);
   g_env = read_env();
+  note_realloc();   // captured search graphs baked the old switches in: have them re-captured
   return B2VS_OK;
 }
 

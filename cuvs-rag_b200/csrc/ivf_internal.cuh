@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "ivf.h"
@@ -99,6 +100,20 @@ struct IvfData {
   DevBuf ws_over, ws_rescue;   // overflow queue of the select kernel; sliced rescue lists
   DevBuf ws_g_rowslot;  // [gathered rows] probe rank of each row inside its query
   DevBuf ws_seed_ids;   // [nq, m] the nearest probes of every query (tensor-core seed pass)
+  // Second set of the planning buffers (item sort, work table, gathered operand): the main pass of a
+  // large batch is planned and gathered on `side` while the seed pass runs on the caller's stream.
+  // swap_plan_ws() exchanges the two sets; launches see whichever is current when they are issued.
+  DevBuf alt_item_lab, alt_item_cnt, alt_item_off, alt_item_perm, alt_item_slot;
+  DevBuf alt_g_work, alt_g_q, alt_g_rowq, alt_g_rowslot, alt_g_bias;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  void swap_plan_ws() {
+    std::swap(ws_item_lab, alt_item_lab); std::swap(ws_item_cnt, alt_item_cnt);
+    std::swap(ws_item_off, alt_item_off); std::swap(ws_item_perm, alt_item_perm);
+    std::swap(ws_item_slot, alt_item_slot); std::swap(ws_g_work, alt_g_work);
+    std::swap(ws_g_q, alt_g_q); std::swap(ws_g_rowq, alt_g_rowq);
+    std::swap(ws_g_rowslot, alt_g_rowslot); std::swap(ws_g_bias, alt_g_bias);
+  }
   const void* src_rows = nullptr;  // IVF-PQ: the caller's [n, dim] rows, BORROWED for refine
   std::vector<int32_t> h_sizes;
   DevBuf rank_of_list, list_of_rank;  // int [n_lists]: lists in descending-size order (scan scheduling)
@@ -129,12 +144,18 @@ struct IvfData {
     graphs.clear();
     if (cap_stream) cudaStreamDestroy(cap_stream);
     cap_stream = nullptr;
+    if (side) cudaStreamDestroy(side);
+    side = nullptr;
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    ev_fork = ev_join = nullptr;
     for (DevBuf* b : {&centroids, &offsets, &sizes, &row_ids, &data, &slot_norm, &codebooks, &codes,
                       &rank_of_list, &list_of_rank,
                       &ws_probe_d, &ws_probe_i, &ws_keys, &ws_qf, &ws_qnorm, &ws_counter,
                       &ws_ref_d, &ws_ref_i, &ws_item_lab, &ws_item_cnt, &ws_item_off, &ws_item_perm,
                       &ws_item_slot, &ws_g_work, &ws_g_q, &ws_g_rowq, &ws_g_tau, &ws_g_cand, &ws_g_cnt,
-                      &ws_g_bias, &ws_g_rowslot, &ws_seed_ids, &ws_over, &ws_rescue, &cb16, &cb16t, &cbn, &pq_norm, &cq_offsets, &cq_probe, &ws_cq_keys})
+                      &ws_g_bias, &ws_g_rowslot, &ws_seed_ids, &alt_item_lab, &alt_item_cnt, &alt_item_off, &alt_item_perm,
+                      &alt_item_slot, &alt_g_work, &alt_g_q, &alt_g_rowq, &alt_g_rowslot, &alt_g_bias, &ws_over, &ws_rescue, &cb16, &cb16t, &cbn, &pq_norm, &cq_offsets, &cq_probe, &ws_cq_keys})
       b->release();
   }
 };

@@ -38,9 +38,14 @@ static int ivf_pq_search_bigk(b2vs_index* index, const void* q, int q_dtype, int
 // Groups the nq * n_probes (query, probe) items by list and runs the tensor-core list scan in
 // append mode against the thresholds in ws_g_tau; candidates land in ws_g_cand / ws_g_cnt (the
 // caller sizes, zeroes and later selects from them).  probe_ids is [nq, n_probes] dense.
+// phase: kPlanAndScan, or the two halves separately - kPlanOnly (sort, work table, gathered operand
+// into the CURRENT planning buffers) and kScanOnly (the tensor-core kernel over buffers prepared by an
+// earlier kPlanOnly call with the same arguments).
+enum { kPlanAndScan = 0, kPlanOnly = 1, kScanOnly = 2 };
 static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long* probe_ids,
                                  int n_probes, int nq, int cap, unsigned long long* counter,
-                                 cudaStream_t st, bool timed = false, int row_limit = 0) {
+                                 cudaStream_t st, bool timed = false, int row_limit = 0,
+                                 int phase = kPlanAndScan) {
   const int items = nq * n_probes;
   const int q_split = index->dtype == B2VS_F32 ? 1 : 0;
   const int q_pitch = q_split ? 2 * static_cast<int>(round_up(d->dp, 64)) : d->dp;
@@ -54,9 +59,12 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
   B2VS_TRY(d->ws_g_rowq.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
   B2VS_TRY(d->ws_g_rowslot.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
   int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
-  B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
-                             counter, st, row_limit));
-  B2VS_TRY(launch_gather_group_queries(d, rows_cap, n_probes, q_split, plan_is_small(d, items) ? 0 : items, st));
+  if (phase != kScanOnly) {
+    B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
+                               counter, st, row_limit));
+    B2VS_TRY(launch_gather_group_queries(d, rows_cap, n_probes, q_split, plan_is_small(d, items) ? 0 : items, st));
+  }
+  if (phase == kPlanOnly) return B2VS_OK;
   GroupedScanArgs ga{};
   ga.q_mat = d->ws_g_q.ptr; ga.q_rows = rows_cap;
   ga.x_mat = d->data.ptr; ga.x_rows = d->n_slots;
@@ -255,7 +263,7 @@ int ivf_search_direct(b2vs_index* index, const void* q, int q_dtype, int nq, int
 // the tensor cores.  Thresholds / candidate buffers (ws_g_tau, ws_g_cand, ws_g_cnt) are the caller's.
 static int run_grouped_pq_scan(b2vs_index* index, IvfData* d, const long long* probe_ids, int n_probes,
                                int nq, int cap, unsigned long long* counter, cudaStream_t st,
-                               bool timed = false, int row_limit = 0) {
+                               bool timed = false, int row_limit = 0, int phase = kPlanAndScan) {
   const int items = nq * n_probes;
   const int l2 = index->metric == B2VS_METRIC_L2 ? 1 : 0;
   int chunk_rows = 0, slots = 1;
@@ -269,10 +277,13 @@ static int run_grouped_pq_scan(b2vs_index* index, IvfData* d, const long long* p
   B2VS_TRY(d->ws_g_rowslot.reserve(static_cast<size_t>(rows_cap) * sizeof(int)));
   B2VS_TRY(d->ws_g_bias.reserve(static_cast<size_t>(rows_cap) * sizeof(float)));
   int* n_work = reinterpret_cast<int*>(d->ws_g_work.as<char>() + static_cast<size_t>(max_work) * sizeof(int4));
-  B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
-                             counter, st, row_limit, kDealNone));
-  B2VS_TRY(launch_gather_group_residuals(index, d, rows_cap, probe_ids, n_probes,
-                                         plan_is_small(d, items) ? 0 : items, st));
+  if (phase != kScanOnly) {
+    B2VS_TRY(plan_grouped_work(d, probe_ids, items, chunk_rows, slots, d->ws_g_work.as<int4>(), n_work,
+                               counter, st, row_limit, kDealNone));
+    B2VS_TRY(launch_gather_group_residuals(index, d, rows_cap, probe_ids, n_probes,
+                                           plan_is_small(d, items) ? 0 : items, st));
+  }
+  if (phase == kPlanOnly) return B2VS_OK;
   PqGroupedScanArgs ga{};
   ga.q_mat = d->ws_g_q.ptr; ga.q_rows = rows_cap;
   ga.dim = index->dim; ga.pq_dim = d->pq_dim; ga.dsub = d->dsub;
@@ -429,6 +440,32 @@ static int coarse_probe_scan(b2vs_index* index, IvfData* d, int nq, int n_probes
                              d->ws_probe_i.as<int64_t>(), nullptr, st);
 }
 
+// Large batches: the main pass's planning + gather (0.14-0.2 ms at C3 / C4) depends only on the
+// coarse probe, so it runs on a side stream - into the second set of planning buffers - while the
+// seed pass (0.3-0.4 ms) runs on the caller's stream.  B2VS_PLAN_OVERLAP=0 keeps everything in line.
+static bool plan_overlap_enabled(int nq) { return env().plan_overlap != 0 && nq >= kTcSeedMinQueries; }
+static int plan_fork(IvfData* d, cudaStream_t st) {
+  if (!d->side) {
+    B2VS_CUDA(cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking));
+    B2VS_CUDA(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+    B2VS_CUDA(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
+  }
+  B2VS_CUDA(cudaEventRecord(d->ev_fork, st));
+  B2VS_CUDA(cudaStreamWaitEvent(d->side, d->ev_fork, 0));
+  d->swap_plan_ws();      // the side stream's launches fill the other set
+  return B2VS_OK;
+}
+static int plan_fork_done(IvfData* d) {
+  B2VS_CUDA(cudaEventRecord(d->ev_join, d->side));
+  d->swap_plan_ws();      // back: the seed pass plans into the first set
+  return B2VS_OK;
+}
+static int plan_join(IvfData* d, cudaStream_t st) {
+  B2VS_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
+  d->swap_plan_ws();      // the main scan reads what the side stream prepared
+  return B2VS_OK;
+}
+
 static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int nq, int k,
                             const b2vs_search_params& sp, float* out_d, int64_t* out_i,
                             cudaStream_t st) {
@@ -498,6 +535,12 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
       B2VS_TRY(d->ws_g_cand.reserve(static_cast<size_t>(nq) * cap * sizeof(u64)));
       B2VS_TRY(d->ws_g_cnt.reserve(static_cast<size_t>(nq) * sizeof(int)));
       B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
+      const bool overlap = tc_seed && plan_overlap_enabled(nq);
+      if (overlap) {
+        B2VS_TRY(plan_fork(d, st));
+        B2VS_TRY(run_grouped_flat_scan(index, d, probe_ids, n_probes, nq, cap, counter, d->side, false, 0, kPlanOnly));
+        B2VS_TRY(plan_fork_done(d));
+      }
       if (tc_seed) {
         B2VS_TRY(run_tc_seed(d, probe_ids, n_probes, nq, k, cap, st, [&](const long long* ids, int m) {
           return run_grouped_flat_scan(index, d, ids, m, nq, cap, nullptr, st, false, seed_tile_rows());
@@ -508,7 +551,9 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
                                       q_split ? 1e-5f : 0.f,
                                       order_seeds ? d->ws_item_perm.as<uint32_t>() : nullptr, st));
       }
-      B2VS_TRY(run_grouped_flat_scan(index, d, probe_ids, n_probes, nq, cap, counter, st, timed));
+      if (overlap) B2VS_TRY(plan_join(d, st));
+      B2VS_TRY(run_grouped_flat_scan(index, d, probe_ids, n_probes, nq, cap, counter, st, timed, 0,
+                                     overlap ? kScanOnly : kPlanAndScan));
       scan_timed_inside = true;
       B2VS_TRY(launch_group_select(d, nq, cap, k, counter + 1, st));
       B2VS_TRY(launch_flat_rescue(index, d, probe_ids, n_probes, nq, k, cap, st));
@@ -542,6 +587,12 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
     B2VS_TRY(d->ws_g_cand.reserve(static_cast<size_t>(nq) * cap * sizeof(u64)));
     B2VS_TRY(d->ws_g_cnt.reserve(static_cast<size_t>(nq) * sizeof(int)));
     B2VS_CUDA(cudaMemsetAsync(d->ws_g_cnt.ptr, 0, static_cast<size_t>(nq) * sizeof(int), st));
+    const bool overlap = tc_seed && plan_overlap_enabled(nq);
+    if (overlap) {
+      B2VS_TRY(plan_fork(d, st));
+      B2VS_TRY(run_grouped_pq_scan(index, d, probe_ids, n_probes, nq, cap, counter, d->side, false, 0, kPlanOnly));
+      B2VS_TRY(plan_fork_done(d));
+    }
     if (tc_seed) {
       B2VS_TRY(run_tc_seed(d, probe_ids, n_probes, nq, k, cap, st, [&](const long long* ids, int m) {
         return run_grouped_pq_scan(index, d, ids, m, nq, cap, nullptr, st, false, seed_tile_rows());
@@ -551,7 +602,9 @@ static int ivf_search_batch(b2vs_index* index, const void* q, int q_dtype, int n
       B2VS_TRY(launch_pq_lut_scan(0, index, d, probe_ids, n_probes, nq, k, cap, grouped_seed_rows(k),
                                   order_seeds ? d->ws_item_perm.as<uint32_t>() : nullptr, st));
     }
-    B2VS_TRY(run_grouped_pq_scan(index, d, probe_ids, n_probes, nq, cap, counter, st, timed));
+    if (overlap) B2VS_TRY(plan_join(d, st));
+    B2VS_TRY(run_grouped_pq_scan(index, d, probe_ids, n_probes, nq, cap, counter, st, timed, 0,
+                                 overlap ? kScanOnly : kPlanAndScan));
     scan_timed_inside = true;
     B2VS_TRY(launch_group_select(d, nq, cap, k, counter + 1, st));
     B2VS_TRY(launch_pq_lut_scan(1, index, d, probe_ids, n_probes, nq, k, cap, 0u, nullptr, st));
