@@ -62,6 +62,7 @@ static EnvConfig read_env() {
   c.no_item_sort = std::getenv("B2VS_NO_ITEM_SORT") != nullptr;
   if (const char* e = std::getenv("B2VS_GRAPH")) c.graph = e[0] == '0' ? 0 : 1;
   c.graph_maxq = std::max(0, env_int_or("B2VS_GRAPH_MAXQ", 0));
+  if (const char* e = std::getenv("B2VS_TAIL_BOXES")) c.tail_boxes = e[0] == '0' ? 0 : 1;
   if (const char* e = std::getenv("B2VS_PLAN_OVERLAP")) c.plan_overlap = e[0] == '0' ? 0 : 1;
   if (const char* e = std::getenv("B2VS_IVF_SEED")) c.seed_mode = e[0] == '0' ? 0 : 1;
   {

@@ -117,6 +117,7 @@ struct BfTcParams {
   // work mode: bytes one stage receives when the list-tile map's box is shorter than 256 rows (the
   // seed pass loads only the head of each list); 0 = a full stage
   uint32_t stage_tx;
+  int tail_boxes;       // work mode: use the TailMaps (128 / 64-row boxes) for the last tile of every item
 };
 constexpr int kSeedSlotRows = 256;   // = one tile: the seed pass scores the first tile of a list
 
@@ -267,20 +268,9 @@ __device__ __forceinline__ void score_chunk_queue(const uint32_t (&r)[32], const
 #pragma unroll
   for (int j = 0; j < 32; ++j) mask |= (sc[j] < tau) ? (1u << j) : 0u;
   const int nh = __popc(mask);
-  int inc = nh;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += v;
-  }
-  const int total = __shfl_sync(0xffffffffu, inc, 31);
-  const bool direct = total > kQueueCap;               // a flood (loose threshold): straight to global
-  if (!direct && hq.n + total > kQueueCap) queue_drain(hq, cand, count, cap, lane);
-  int pos = direct ? (nh ? atomicAdd(count + qslot, nh) : 0) : hq.n + inc - nh;
-  u64* const row_buf = cand + static_cast<size_t>(qslot) * cap;
-  while (mask) {
-    const int j = __ffs(mask) - 1;
-    mask &= mask - 1;
+  const int total = __reduce_add_sync(0xffffffffu, nh);
+  // pulls score j out of the register array with a 5-level select tree
+  auto pick = [&](int j) {
     float v16[16], v8[8], v4[4], v2[2];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v16[i] = (j & 1) ? sc[2 * i + 1] : sc[2 * i];
@@ -290,17 +280,36 @@ __device__ __forceinline__ void score_chunk_queue(const uint32_t (&r)[32], const
     for (int i = 0; i < 4; ++i) v4[i] = (j & 4) ? v8[2 * i + 1] : v8[2 * i];
 #pragma unroll
     for (int i = 0; i < 2; ++i) v2[i] = (j & 8) ? v4[2 * i + 1] : v4[2 * i];
-    const float v = (j & 16) ? v2[1] : v2[0];
-    const u64 key = pack_key(v + bias, col + j);
-    if (direct) {
-      if (pos < cap) __stcg(row_buf + pos, key);
-    } else {
-      hq.keys[pos] = key;
+    return (j & 16) ? v2[1] : v2[0];
+  };
+  if (total > kQueueCap) {
+    // a flood (loose threshold): every lane reserves its slots in the query's buffer directly
+    int pos = nh ? atomicAdd(count + qslot, nh) : 0;
+    u64* const row_buf = cand + static_cast<size_t>(qslot) * cap;
+    while (mask) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1;
+      if (pos < cap) __stcg(row_buf + pos, pack_key(pick(j) + bias, col + j));
+      ++pos;
+    }
+    return;
+  }
+  // Sparse hits (rarely two in one lane): every round takes each lane's lowest remaining hit, and
+  // the queue positions come from the vote of the lanes that still have one - no prefix sum.
+  if (hq.n + total > kQueueCap) queue_drain(hq, cand, count, cap, lane);
+  while (true) {
+    const bool has = mask != 0u;
+    const uint32_t votes = __ballot_sync(0xffffffffu, has);
+    if (votes == 0u) break;
+    if (has) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int pos = hq.n + __popc(votes & ((1u << lane) - 1u));
+      hq.keys[pos] = pack_key(pick(j) + bias, col + j);
       hq.slots[pos] = qslot;
     }
-    ++pos;
+    hq.n += __popc(votes);
   }
-  if (!direct) hq.n += total;
 }
 
 // Seed pass: all 32 scores of the chunk go to their fixed places (dst = the row's slot + column).
@@ -335,12 +344,20 @@ __device__ __forceinline__ float score_chunk_min(const uint32_t (&r)[32], const 
   return fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])), fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
 }
 
+// Work mode: list-tile maps with 128- and 64-row boxes for the LAST tile of an item.  A 256-row box
+// always reads 256 rows, i.e. on average 128 rows of the NEXT list behind every list's tail: 0.8 GB
+// of a 15.4 GB C3 batch.  Rows the short box leaves stale in the stage only feed accumulator
+// columns past the item's end, which the epilogue never scores.
+struct alignas(64) TailMaps {
+  CUtensorMap m128, m64;
+};
+
 constexpr int tc_threads(int epi_groups) { return 128 + 128 * epi_groups; }
 
 template <int G, bool kWork = false, int E = 1>
 __global__ void __launch_bounds__(tc_threads(E), 1)
 bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
-             const BfTcParams p) {
+             const BfTcParams p, const __grid_constant__ TailMaps tails) {
   static_assert(!kWork || G == 1, "work-table mode is single-CTA");
   static_assert(E == 1 || E == 2, "epilogue groups");
   constexpr int kEpiGroups = E;
@@ -388,6 +405,10 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tm_q);
     ptx::prefetch_tmap(&tm_x);
+    if (kWork && p.tail_boxes) {
+      ptx::prefetch_tmap(&tails.m128);
+      ptx::prefetch_tmap(&tails.m64);
+    }
   }
   if (warp == 2) {
     if (G == 2) {
@@ -411,10 +432,10 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       const uint32_t full_leader = (G == 2) ? ptx::mapa_cluster(bar_full, 0) : bar_full;
       const int n_items = kWork ? *p.n_work : p.n_items;
       for (int item = unit; item < n_items; item += n_units) {
-        int qb, t0, t1, row_begin = 0;
+        int qb, t0, t1, row_begin = 0, row_end = 0;
         if (kWork) {
           const int4 w = __ldg(p.work + item);
-          qb = w.x; row_begin = w.y; t0 = 0; t1 = (w.z - w.y + kBN - 1) / kBN;
+          qb = w.x; row_begin = w.y; row_end = w.z; t0 = 0; t1 = (w.z - w.y + kBN - 1) / kBN;
         } else {
           qb = item % p.n_qblocks;
           t0 = (item / p.n_qblocks) * p.tiles_per_split;
@@ -445,14 +466,22 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                 ptx::tma_load_2d_2sm_hint(a_dst, &tm_q, fb, kb * kBK, q_row0, ptx::kEvictLast);
                 ptx::tma_load_2d_2sm(a_dst + Cfg::kABytes, &tm_x, fb, kb * kBK, x_row0);
               } else {
-                ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, (kWork && p.stage_tx) ? p.stage_tx : kStageBytes);
+                // work mode, last tile of the item: the shortest box that covers the rows left
+                const CUtensorMap* tmx = &tm_x;
+                uint32_t tx = (kWork && p.stage_tx) ? p.stage_tx : kStageBytes;
+                if (kWork && p.tail_boxes) {
+                  const int left = row_end - x_row0;
+                  if (left <= 64) { tmx = &tails.m64; tx = Cfg::kABytes + 64 * kBK * 2; }
+                  else if (left <= 128) { tmx = &tails.m128; tx = Cfg::kABytes + 128 * kBK * 2; }
+                }
+                ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, tx);
                 // the query block is re-read for every db tile: ask L2 to keep it (evict-last)
                 ptx::tma_load_2d_hint(a_dst, &tm_q, bar_full + 8 * stage, kb * kBK, q_row0,
                                       ptx::kEvictLast);
                 const int xkb = (kWork && p.x_kblocks > 0 && kb >= p.x_kblocks) ? kb - p.x_kblocks : kb;
                 // work mode streams every list once: keep it from evicting the query blocks in L2
                 if (kWork && !kWorkNoHint)
-                  ptx::tma_load_2d_hint(a_dst + Cfg::kABytes, &tm_x, bar_full + 8 * stage, xkb * kBK,
+                  ptx::tma_load_2d_hint(a_dst + Cfg::kABytes, tmx, bar_full + 8 * stage, xkb * kBK,
                                         x_row0, ptx::kEvictFirst);
                 else
                   ptx::tma_load_2d(a_dst + Cfg::kABytes, &tm_x, bar_full + 8 * stage, xkb * kBK, x_row0);

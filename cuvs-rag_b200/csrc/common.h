@@ -139,6 +139,7 @@ struct EnvConfig {
   int coarse_scan_ctas = -1;   // B2VS_COARSE_SCAN_CTAS
   bool no_item_sort = false;   // B2VS_NO_ITEM_SORT: per-item scan without the list ordering
   int graph = -1;              // B2VS_GRAPH=0|1: never / always replay small IVF batches as a graph
+  int tail_boxes = -1;         // B2VS_TAIL_BOXES=0: always load whole 256-row list tiles in the grouped IVF-Flat scan
   int plan_overlap = -1;       // B2VS_PLAN_OVERLAP=0: plan the main IVF pass in line instead of on the side stream
   int graph_maxq = 0;          // B2VS_GRAPH_MAXQ: largest batch replayed as a graph (default 64)
   int seed_mode = -1;          // B2VS_IVF_SEED=0|1: legacy seed kernels / seeds from the tensor-core pass

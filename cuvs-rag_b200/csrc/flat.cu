@@ -287,11 +287,11 @@ int FlatEngine::launch_fused(int group, int grid, const CUtensorMap& tm_q, const
   if (group == 1 && epi_groups == 2) {
     B2VS_CUDA(cudaFuncSetAttribute((bf_tc_kernel<1, false, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TcCfg<1>::kSmemBytes));
-    bf_tc_kernel<1, false, 2><<<grid, tc_threads(2), TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_x, p);
+    bf_tc_kernel<1, false, 2><<<grid, tc_threads(2), TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_x, p, TailMaps{});
   } else if (group == 1) {
     B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TcCfg<1>::kSmemBytes));
-    bf_tc_kernel<1><<<grid, tc_threads(1), TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_x, p);
+    bf_tc_kernel<1><<<grid, tc_threads(1), TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_x, p, TailMaps{});
   } else {
     B2VS_CUDA(cudaFuncSetAttribute(bf_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TcCfg<2>::kSmemBytes));
@@ -307,7 +307,7 @@ int FlatEngine::launch_fused(int group, int grid, const CUtensorMap& tm_q, const
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    B2VS_CUDA(cudaLaunchKernelEx(&cfg, bf_tc_kernel<2>, tm_q, tm_x_half, p));
+    B2VS_CUDA(cudaLaunchKernelEx(&cfg, bf_tc_kernel<2>, tm_q, tm_x_half, p, TailMaps{}));
   }
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
@@ -629,6 +629,13 @@ int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st) {
   p.alpha = a.alpha;
   p.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(a.ab_format), kBM, box);   // N = rows of a list tile
   p.stage_tx = box == kBN ? 0u : static_cast<uint32_t>(TcCfg<1>::kABytes + box * kBK * 2);
+  // whole-tile launches: short boxes for the last tile of every item (B2VS_TAIL_BOXES=0: A/B switch)
+  TailMaps tails{};
+  p.tail_boxes = (box == kBN && !a.q_split && env().tail_boxes != 0) ? 1 : 0;
+  if (p.tail_boxes) {
+    B2VS_TRY(encode_tmap_2d(&tails.m128, a.x_mat, a.ab_format, a.x_rows, a.kdim, 128));
+    B2VS_TRY(encode_tmap_2d(&tails.m64, a.x_mat, a.ab_format, a.x_rows, a.kdim, 64));
+  }
   p.tau_init = a.tau;
   p.big_cand = a.cand;
   p.big_count = a.count;
@@ -646,11 +653,11 @@ int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st) {
   if (epi == 2) {
     B2VS_CUDA(cudaFuncSetAttribute((bf_tc_kernel<1, true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TcCfg<1>::kSmemBytes));
-    bf_tc_kernel<1, true, 2><<<grid, tc_threads(2), TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_xl, p);
+    bf_tc_kernel<1, true, 2><<<grid, tc_threads(2), TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_xl, p, tails);
   } else {
     B2VS_CUDA(cudaFuncSetAttribute((bf_tc_kernel<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    TcCfg<1>::kSmemBytes));
-    bf_tc_kernel<1, true><<<grid, tc_threads(1), TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_xl, p);
+    bf_tc_kernel<1, true><<<grid, tc_threads(1), TcCfg<1>::kSmemBytes, st>>>(tm_q, tm_xl, p, tails);
   }
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;

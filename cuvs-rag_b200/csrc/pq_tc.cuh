@@ -24,20 +24,30 @@
 // time, of the shared-memory reads of the N operand and of the TMA traffic of a full block.
 //
 // Resident query blocks (dim <= 128, i.e. at most two k-blocks): the query block of a work item
-// is loaded ONCE (double-buffered across items) instead of once per tile - with it in the stage the
-// bare pipeline (no decode, no MMA, no epilogue) took 0.42 ms of the 0.83 ms C4 launch: four stages
-// in flight against the L2 latency of a TMA load per k-block step.  The stages then hold only the
-// decoded list k-blocks.
+// is loaded ONCE (double-buffered across items) instead of once per tile, and the stages hold only
+// the decoded list k-blocks.  (Measured neutral at C4 - the per-step loads were hidden - but it
+// removes 2/3 of the kernel's TMA traffic.)
 //
-// Warp roles (640 threads): warp 0 = TMA producer (query k-blocks + the tile's ||r^||^2 vector),
-// warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 8-11 and 16-19 = two decoder sets taking
-// alternate k-block stages (a warp of a set owns one 32-row group of the stage: the decode of one
-// group is a ~300-instruction chain that a single warp issues at well under one per cycle, and with
-// one set the four decoders, not the issue slots, set the tile rate), warps 4-7 / 12-15 = two
-// epilogue groups taking alternate tiles.  A smem stage = 16 KB decoded list k-block (128 rows x
-// 64 dims) + 16 KB query k-block (TMA); its "full" barrier takes the TMA transaction plus one
-// arrival per decoder warp.  bf16 codebooks of at most 64 KB stay resident in shared memory;
-// larger ones (e.g. 768-d) are looked up in global memory, i.e. L2.
+// Warp roles (768 threads):
+//   warp 0        TMA producer: query blocks / k-blocks, the tile's ||r^||^2 vector (a ring of 16:
+//                 those loads come from DRAM), and an L2 prefetch of the tile's codes
+//   warp 1        MMA issuer
+//   warp 2        TMEM allocator
+//   warp 3        column-table builder: per work item the threshold-minus-bias, bias, query slot and
+//                 seed slot of the block's 128 query rows, for all epilogue warps, a ring of four
+//                 items ahead (each epilogue warp used to build its own copy at the start of every
+//                 item: two dependent L2 round trips on its critical path)
+//   warps 8-11, 16-19    two decoder sets taking alternate k-block stages; a warp owns one 32-row
+//                 group of the stage
+//   warps 4-7, 12-15, 20-23    three epilogue groups taking tiles round-robin
+// A stage's "full" barrier takes one arrival per decoder warp of the set (plus the TMA transaction
+// when query k-blocks are streamed).  bf16 codebooks of at most 64 KB stay resident in shared
+// memory; larger ones (e.g. 768-d) are looked up in global memory, i.e. L2.
+//
+// Where the time goes (C4 main pass, B2VS_PQ_DEBUG role-skipping runs, profiles/r2_c4_pq_tc_roles.jsonl):
+// bare pipeline 0.35 ms (the decoders' code fetches: three 32-byte pieces in flight per lane against
+// ~0.8 us of L2 latency; registers, 80 of 85 at 768 threads, cap the depth), + UMMAs 0.06, + decode
+// 0.08, + TMEM loads / scoring / hit masks 0.14, + hit queueing 0.14 = 0.78 ms.
 #pragma once
 #include "bf_tc.cuh"
 
