@@ -488,7 +488,7 @@ def run_ivf(job, args, name):
     _, truth = sharded_search(job, flat, q_all, q_slice, k)
     truth = truth.clone()
     flat.destroy()
-    steps, warm = 20, 3
+    steps, warm = 40, 15   # the exact ground-truth search above leaves the GPU power-capped: let the IVF steps reach their own steady state
     hbm = job.peaks["hbm_gbs"]
     kernel = "bf_tc_kernel<1,true> (grouped list scan)" if kind == "ivf_flat" else "pq_tc_kernel (grouped PQ scan)"
 
