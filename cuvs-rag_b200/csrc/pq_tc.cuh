@@ -45,10 +45,9 @@
 // memory; larger ones (e.g. 768-d) are looked up in global memory, i.e. L2.
 //
 // Where the time goes (C4 main pass, B2VS_PQ_DEBUG role-skipping runs, profiles/r2_c4_pq_tc_roles.jsonl):
-// bare pipeline 0.35 ms (~245 ns per k-block step: the barrier hand-offs decoder -> MMA -> decoder
-// with two stages per decoder set; a deeper register prefetch of the codes - five pieces in flight
-// instead of three - made it SLOWER, 0.39 ms, so the code fetches are not it), + UMMAs 0.06, + decode
-// 0.08, + TMEM loads / scoring / hit masks 0.14, + hit queueing 0.14 = 0.78 ms.
+// bare pipeline 0.35 ms (~245 ns per k-block step; neither a deeper register prefetch of the codes
+// nor whole-tile stages - one hand-off per tile - nor prefetched work entries moved it: DESIGN.md §9),
+// + UMMAs 0.06, + decode 0.08, + TMEM loads / scoring / hit masks 0.14, + hit queueing 0.14 = 0.78 ms.
 #pragma once
 #include "bf_tc.cuh"
 
