@@ -53,7 +53,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
+#ifdef B2VS_WAIT_SPIN   /* A/B build: spin instead of sleeping (measured equal on pq_tc_kernel) */
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+#endif
       "selp.u32 %0, 1, 0, p;\n\t"
       "}"
       : "=r"(ok)
