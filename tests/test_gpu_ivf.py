@@ -417,6 +417,39 @@ def test_small_batch_cuda_graph_replay_equals_direct_search(b2, kind):
     assert torch.equal(wi, si) and torch.allclose(wd, sd, rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize("kind", ["flat", "pq"])
+def test_large_batch_graph_replay_and_plan_overlap_equal_the_in_line_search(b2, setenv, kind):
+    """Batches of 2048 queries and more are replayed as CUDA graphs by default, with the main pass
+    planned on a side stream into the second set of planning buffers while the seed pass runs.
+    Direct launches (B2VS_GRAPH=0), with and without the overlap, must give the same answers as
+    the default path on fresh queries in every call (first call direct, capture, replays)."""
+    n, d, nlist = 120000, 128, 256
+    x = clustered(n, d, 300, 31).to(torch.float16).cuda()
+    if kind == "flat":
+        ix = b2.NativeIndex.ivf_flat(x, nlist, kmeans_iters=5, id_offset=9)
+        kw = dict(n_probes=12)
+    else:
+        ix = b2.NativeIndex.ivf_pq(x, nlist, 64, kmeans_iters=5, id_offset=9)
+        kw = dict(n_probes=12, refine_ratio=2)
+    qs = [queries_from(x.float().cpu(), 2500, 50 + t).to(torch.float16).cuda() for t in range(5)]
+    setenv("B2VS_GRAPH", "0")
+    setenv("B2VS_PLAN_OVERLAP", "0")
+    want = [tuple(t.clone() for t in ix.search(q, 10, **kw)) for q in qs]
+    setenv("B2VS_PLAN_OVERLAP", None)
+    overlapped = [tuple(t.clone() for t in ix.search(q, 10, **kw)) for q in qs]
+    setenv("B2VS_GRAPH", None)
+    graphed = [tuple(t.clone() for t in ix.search(q, 10, **kw)) for q in qs]
+    torch.cuda.synchronize()
+    for (wd, wi), (od, oi), (gd, gi) in zip(want, overlapped, graphed):
+        assert torch.equal(wi, oi) and torch.equal(wi, gi)
+        assert torch.allclose(wd, od, rtol=1e-6, atol=0) and torch.allclose(wd, gd, rtol=1e-6, atol=0)
+    # a different batch size in between (workspaces may move), then the first size again
+    ix.search(queries_from(x.float().cpu(), 5000, 99).to(torch.float16).cuda(), 10, **kw)
+    gd, gi = ix.search(qs[0], 10, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(want[0][1], gi)
+
+
 @pytest.mark.parametrize("kind,dtype,metric,d", [("flat", torch.float16, "sqeuclidean", 128),
                                                   ("flat", torch.bfloat16, "inner_product", 72),
                                                   ("flat", torch.float32, "sqeuclidean", 200),
