@@ -75,6 +75,12 @@ struct BfTcParams {
   const float* beta;    // [tiles_total*256] per db row additive term (||x||^2, 0, +inf on padding)
   u64* cand;            // [grid][E][128][kCap] candidate buffers (E = epilogue groups)
   u64* out_keys;        // [n_splits * E][q_pad][k] sorted ascending, kKeyInf padded
+  // raw emission (k > 1, buffer mode): every item owns its candidate buffers,
+  // cand[((item * G + cta_rank) * E + group) * 128 + row][kCap], and ends by storing the rows' fill
+  // levels in raw_count (same indexing) - no final sort, no copy; merge_raw_kernel (merge.cu)
+  // selects from the unsorted lists with the whole GPU instead of four warps per SM while the
+  // tensor pipe waits (0.8 ms of an 18.3 ms search of a 1.25 M-row shard)
+  int* raw_count;
   int n_qblocks;        // ceil(nq / (128*G))
   int q_pad;            // n_qblocks * 128 * G
   int nq;               // real query rows; rows >= nq are padding and never collect candidates
@@ -117,6 +123,7 @@ struct BfTcParams {
   // work mode: bytes one stage receives when the list-tile map's box is shorter than 256 rows (the
   // seed pass loads only the head of each list); 0 = a full stage
   uint32_t stage_tx;
+  int debug_skip_emit;  // B2VS_K0_DEBUG=1 (timing experiments): items skip their final sort + emission
   int tail_boxes;       // work mode: use the TailMaps (128 / 64-row boxes) for the last tile of every item
 };
 constexpr int kSeedSlotRows = 256;   // = one tile: the seed pass scores the first tile of a list
@@ -548,9 +555,7 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     const int ew = warp & 3;                // TMEM lane quarter == warp % 4
     const uint32_t eg = static_cast<uint32_t>(warp - 4) >> 2;   // epilogue group = accumulator buffer
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-    u64* const cand_warp =
-        p.cand + ((static_cast<size_t>(blockIdx.x) * kEpiGroups + eg) * kBM + ew * 32) * kCap;
-    u64* const my_cand = cand_warp + static_cast<size_t>(lane) * kCap;
+    const bool raw_out = !kWork && p.raw_count != nullptr;
     const uint32_t acc_empty_leader =
         (G == 2) ? ptx::mapa_cluster(bar_acc_empty, 0) : bar_acc_empty;
     const float inf = __int_as_float(0x7f800000);
@@ -571,6 +576,11 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         t0 = s * p.tiles_per_split;
         t1 = min(t0 + p.tiles_per_split, p.tiles_total);
       }
+      // candidate buffers: the CTA's (re-used by its items), or - raw emission - the item's own
+      const size_t cand_slot = raw_out ? (static_cast<size_t>(item) * G + cta_rank) * kEpiGroups + eg
+                                       : static_cast<size_t>(blockIdx.x) * kEpiGroups + eg;
+      u64* const cand_warp = p.cand + (cand_slot * kBM + ew * 32) * kCap;
+      u64* const my_cand = cand_warp + static_cast<size_t>(lane) * kCap;
       size_t q_row = static_cast<size_t>(qb) * (kBM * G) + cta_rank * kBM + ew * 32 + lane;
       float tau = inf;
       int seed_slot = 0;
@@ -694,6 +704,11 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
         }
       }
       if (mode == kModeAppend) continue;  // candidates sit in the query's global buffer / the warp's queue
+      if (p.debug_skip_emit) continue;
+      if (raw_out && mode == kModeBuffer) {
+        p.raw_count[cand_slot * kBM + ew * 32 + lane] = cnt;
+        continue;
+      }
       // ---- item done: emit this (split, query block)'s sorted top-k keys
       const size_t q_row0 = static_cast<size_t>(qb) * (kBM * G) + cta_rank * kBM + ew * 32;
       u64* out_blk = p.out_keys + ((static_cast<size_t>(s) * kEpiGroups + eg) * p.q_pad + q_row0) * p.k;

@@ -144,6 +144,8 @@ struct EnvConfig {
   int graph_maxq = 0;          // B2VS_GRAPH_MAXQ: largest batch replayed as a graph (default 64)
   int seed_mode = -1;          // B2VS_IVF_SEED=0|1: legacy seed kernels / seeds from the tensor-core pass
   int epi_groups = 0;          // B2VS_EPI_GROUPS=1|2: epilogue warp groups of the flat kernel (0 = heuristic)
+  int raw_emit = -1;           // B2VS_RAW_EMIT=0: the fused kernel's items sort and emit their own top-k lists
+  int k0_debug = 0;            // B2VS_K0_DEBUG: 1 = the fused kernel's items skip their final sort + emission (timing only)
   int pq_debug = 0;            // B2VS_PQ_DEBUG: role-skipping bits of pq_tc_kernel (timing experiments only)
   int work_epi = 0;            // B2VS_WORK_EPI=1|2: epilogue groups of every work-table launch (0 = per call site)
   int seed_lists = 0;          // B2VS_IVF_SEED_LISTS: lists per query scored by the seed pass (1..16)
@@ -186,7 +188,7 @@ struct FlatEngine {
   CUtensorMap tm_x;       // db map, box = 256 rows (single-CTA kernel)
   CUtensorMap tm_x_half;  // db map, box = 128 rows (CTA-pair kernel: each CTA stages half a tile)
   // workspaces (grow-only)
-  DevBuf ws_cand, ws_keys, ws_q, ws_qnorm, ws_tau, ws_big, ws_bigcnt, ws_chunk, ws_work;
+  DevBuf ws_cand, ws_keys, ws_q, ws_qnorm, ws_tau, ws_big, ws_bigcnt, ws_chunk, ws_work, ws_rawcnt;
   b2vs_search_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // optional timing of the dominant kernel
   bool timing_pending = false;
@@ -283,6 +285,10 @@ int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k,
                         int32_t* out_label, cudaStream_t st, const uint32_t* remap = nullptr,
                         float* out_tau = nullptr);
 
+// Raw emission of the fused kernel: top-k (or the k-th score) per query from the unsorted per-item lists.
+int launch_merge_raw(const u64* cand, const int* count, int n_splits, int n_qblocks, int group,
+                     int epi_groups, int nq, int k, int metric, const float* qnorm, int64_t id_offset,
+                     float* out_d, int64_t* out_i, int32_t* out_label, float* out_tau, cudaStream_t st);
 // Two-pass selection (flat.cu: search_two_pass).  chunk_tau: per query the k-th smallest
 // (chunk minimum, chunk index) pair -> tau / tau_chunk, and count[q] = 0.  cand_select: the k best
 // of each query's appended candidates, straight to answer rows.

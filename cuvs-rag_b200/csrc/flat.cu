@@ -227,6 +227,7 @@ void FlatEngine::destroy() {
   ws_big.release();
   ws_bigcnt.release();
   ws_chunk.release();
+  ws_rawcnt.release();
   ws_work.release();
 }
 
@@ -240,6 +241,7 @@ __global__ void fill_missing_kernel(float* out_d, int64_t* out_i, int32_t* out_l
 }
 
 constexpr int kDefaultTcGroup = 1;
+constexpr size_t kMaxRawBytes = 3ull << 30;   // raw emission: upper bound of the per-item candidate buffers
 constexpr int kPairMaxK = 32;   // largest k served by the CTA-pair kernel by default
 
 // B2VS_TC_GROUP=1|2 forces the single-CTA / CTA-pair kernel (bring-up and A/B measurements).
@@ -434,6 +436,7 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   p.k = k;
   p.alpha = (metric == B2VS_METRIC_L2) ? -2.f : -1.f;
   p.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(ab_format), qrows, kBN);
+  p.debug_skip_emit = env().k0_debug & 1;
 
   const bool timed = (flags & B2VS_FLAG_TIME_KERNEL) != 0;
   if (timed) {
@@ -455,10 +458,21 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
     n_splits = static_cast<int>(ceil_div(ptiles, tps));
     const int n_items = n_qblocks * n_splits;
     grid = std::min(n_items, units) * group;
-    B2VS_TRY(ws_cand.reserve(static_cast<size_t>(grid) * epi_groups * kBM * kCap * sizeof(u64)));
-    B2VS_TRY(ws_keys.reserve(static_cast<size_t>(n_splits) * epi_groups * q_pad * k * sizeof(u64)));
+    // Raw emission (k > 1): per-ITEM candidate buffers that double as the pass's output - no final
+    // sort inside the kernel; merge_raw_kernel selects from them.  Falls back to the sorted per-item
+    // lists when the buffers would be out of proportion (2 KB per item row).
+    const size_t raw_rows = static_cast<size_t>(n_items) * group * epi_groups * kBM;
+    const bool raw = k > 1 && env().raw_emit != 0 && raw_rows * kCap * sizeof(u64) <= kMaxRawBytes;
+    if (raw) {
+      B2VS_TRY(ws_cand.reserve(raw_rows * kCap * sizeof(u64)));
+      B2VS_TRY(ws_rawcnt.reserve(raw_rows * sizeof(int)));
+    } else {
+      B2VS_TRY(ws_cand.reserve(static_cast<size_t>(grid) * epi_groups * kBM * kCap * sizeof(u64)));
+      B2VS_TRY(ws_keys.reserve(static_cast<size_t>(n_splits) * epi_groups * q_pad * k * sizeof(u64)));
+    }
     p.cand = ws_cand.as<u64>();
     p.out_keys = ws_keys.as<u64>();
+    p.raw_count = raw ? ws_rawcnt.as<int>() : nullptr;
     p.n_items = n_items;
     p.tiles_total = static_cast<int>(ptiles);
     p.tiles_per_split = tps;
@@ -468,12 +482,21 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
     ++launches;
     if (last && timed) B2VS_CUDA(cudaEventRecord(ev1, st));
     if (last) {
-      B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits * epi_groups, q_pad, nq, k, metric,
-                                   ws_qnorm.as<float>(), id_offset, out_d, out_i, out_label, st));
+      if (raw)
+        B2VS_TRY(launch_merge_raw(ws_cand.as<u64>(), ws_rawcnt.as<int>(), n_splits, n_qblocks, group, epi_groups,
+                                  nq, k, metric, ws_qnorm.as<float>(), id_offset, out_d, out_i, out_label,
+                                  nullptr, st));
+      else
+        B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits * epi_groups, q_pad, nq, k, metric,
+                                     ws_qnorm.as<float>(), id_offset, out_d, out_i, out_label, st));
     } else {
       // sampled pass: only the k-th best raw score per query is kept, as the next pass's threshold
-      B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits * epi_groups, q_pad, q_pad, k, metric,
-                                   nullptr, 0, nullptr, nullptr, nullptr, st, nullptr, ws_tau.as<float>()));
+      if (raw)
+        B2VS_TRY(launch_merge_raw(ws_cand.as<u64>(), ws_rawcnt.as<int>(), n_splits, n_qblocks, group, epi_groups,
+                                  q_pad, k, metric, nullptr, 0, nullptr, nullptr, nullptr, ws_tau.as<float>(), st));
+      else
+        B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits * epi_groups, q_pad, q_pad, k, metric,
+                                     nullptr, 0, nullptr, nullptr, nullptr, st, nullptr, ws_tau.as<float>()));
       // sharded search: every shard continues with the tightest bound any shard found (a shard's
       // k-th best sampled score bounds the GLOBAL k-th score from above, so the minimum does too)
       if (tau_exchange) B2VS_TRY(tau_exchange->fn(tau_exchange->ctx, ws_tau.as<float>(), q_pad, st));

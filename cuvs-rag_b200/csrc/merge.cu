@@ -196,6 +196,63 @@ int launch_cand_select(const u64* cand, const int* count, int cap, int nq, int k
   return B2VS_OK;
 }
 
+// Raw emission of the fused kernel (bf_tc.cuh: raw_count): every (split, query block) item left the
+// UNSORTED contents of its rows' candidate buffers and their fill levels.  One warp per query streams
+// the lists of all its splits through the staged selector (the items' final thresholds already cut
+// them to ~k..256 keys each) and emits the answer row - or, for a sampled pass, the next threshold.
+// Slot of (split s, query q): item = s * n_qblocks + q / (128 G); buffers ((item * G + rank) * E + e) * 128 + q % 128.
+__global__ void __launch_bounds__(kTwoPassThreads)
+merge_raw_kernel(const u64* __restrict__ cand, const int* __restrict__ count, int n_splits, int n_qblocks,
+                 int group, int epi_groups, int nq, int k, int metric, const float* __restrict__ qnorm,
+                 long long id_offset, float* __restrict__ out_d, long long* __restrict__ out_i,
+                 int* __restrict__ out_label, float* __restrict__ out_tau) {
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  __shared__ u64 stage_mem[kTwoPassThreads / 32][kStageKeys];
+  StagedTopK sel;
+  sel.init(stage_mem[threadIdx.x >> 5]);
+  const int qb = q / (128 * group), rank = (q / 128) % group, r = q % 128;
+  for (int s = 0; s < n_splits; ++s) {
+    for (int e = 0; e < epi_groups; ++e) {
+      const size_t slot = ((static_cast<size_t>(s) * n_qblocks + qb) * group + rank) * epi_groups + e;
+      const size_t row = slot * 128 + r;
+      const int n = min(__ldg(count + row), kCap);
+      const u64* src = cand + row * kCap;
+      for (int i0 = 0; i0 < n; i0 += 64) {
+        const int ia = i0 + lane, ib = i0 + 32 + lane;
+        const u64 va = ia < n ? __ldcg(src + ia) : kKeyInf;
+        const u64 vb = ib < n ? __ldcg(src + ib) : kKeyInf;
+        sel.push((va != kKeyInf && key_score(va) <= sel.tk.tau) ? va : kKeyInf, k, lane);
+        sel.push((vb != kKeyInf && key_score(vb) <= sel.tk.tau) ? vb : kKeyInf, k, lane);
+      }
+    }
+  }
+  sel.flush(k, lane);
+  if (out_tau) {
+    // threshold-seeding pass: publish one ulp above the k-th best raw score (inclusive bound)
+    u64 kth = kKeyInf;
+#pragma unroll
+    for (int e = 0; e < kListE; ++e)
+      if (lane * kListE + e == k - 1) kth = sel.tk.acc[e];
+    if (lane == (k - 1) / kListE)
+      out_tau[q] = (kth == kKeyInf) ? INFINITY : nextafterf(key_score(kth), INFINITY);
+    return;
+  }
+  emit_answer_row(sel.tk.acc, lane, q, k, metric, qnorm, id_offset, out_d, out_i, out_label, nullptr);
+}
+
+int launch_merge_raw(const u64* cand, const int* count, int n_splits, int n_qblocks, int group,
+                     int epi_groups, int nq, int k, int metric, const float* qnorm, int64_t id_offset,
+                     float* out_d, int64_t* out_i, int32_t* out_label, float* out_tau, cudaStream_t st) {
+  const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(nq) * 32, kTwoPassThreads));
+  merge_raw_kernel<<<blocks, kTwoPassThreads, 0, st>>>(cand, count, n_splits, n_qblocks, group, epi_groups,
+                                                       nq, k, metric, qnorm, id_offset, out_d,
+                                                       reinterpret_cast<long long*>(out_i), out_label, out_tau);
+  B2VS_CUDA(cudaGetLastError());
+  return B2VS_OK;
+}
+
 // Cross-shard merge.  Key = (orderable distance, position in the concatenated candidate row) so
 // equal distances keep the lower part / lower rank first, exactly like a stable argsort over the
 // concatenation.  Positions index d_all / i_all for the final gather.
