@@ -124,6 +124,9 @@ struct BfTcParams {
   // seed pass loads only the head of each list); 0 = a full stage
   uint32_t stage_tx;
   int debug_skip_emit;  // B2VS_K0_DEBUG=1 (timing experiments): items skip their final sort + emission
+  int a_quarter_boxes;  // work mode: the query map's box is 32 rows; a stage loads only the block's leading quarters
+                        // that hold queries (work.w rows, dealt over ceil(w / 32) quarters by the planner) - the
+                        // seed pass's blocks hold ~5 queries: 3/4 of its query-operand traffic was padding
   int tail_boxes;       // work mode: use the TailMaps (128 / 64-row boxes) for the last tile of every item
 };
 constexpr int kSeedSlotRows = 256;   // = one tile: the seed pass scores the first tile of a list
@@ -439,10 +442,12 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
       const uint32_t full_leader = (G == 2) ? ptx::mapa_cluster(bar_full, 0) : bar_full;
       const int n_items = kWork ? *p.n_work : p.n_items;
       for (int item = unit; item < n_items; item += n_units) {
-        int qb, t0, t1, row_begin = 0, row_end = 0;
+        int qb, t0, t1, row_begin = 0, row_end = 0, a_quarters = 4;
         if (kWork) {
           const int4 w = __ldg(p.work + item);
           qb = w.x; row_begin = w.y; row_end = w.z; t0 = 0; t1 = (w.z - w.y + kBN - 1) / kBN;
+          // .w = query rows of the block, which the planner placed in its first ceil(w / 32) quarters
+          a_quarters = (w.w > 0 && w.w < kBM) ? (w.w + 31) >> 5 : 4;
         } else {
           qb = item % p.n_qblocks;
           t0 = (item / p.n_qblocks) * p.tiles_per_split;
@@ -481,10 +486,19 @@ bf_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                   if (left <= 64) { tmx = &tails.m64; tx = Cfg::kABytes + 64 * kBK * 2; }
                   else if (left <= 128) { tmx = &tails.m128; tx = Cfg::kABytes + 128 * kBK * 2; }
                 }
-                ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, tx);
-                // the query block is re-read for every db tile: ask L2 to keep it (evict-last)
-                ptx::tma_load_2d_hint(a_dst, &tm_q, bar_full + 8 * stage, kb * kBK, q_row0,
-                                      ptx::kEvictLast);
+                if (kWork && p.a_quarter_boxes) {
+                  // the query map's box is one 32-row quarter: only the quarters that hold queries
+                  tx -= static_cast<uint32_t>(4 - a_quarters) * (32u * kBK * 2u);
+                  ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, tx);
+                  for (int aq = 0; aq < a_quarters; ++aq)
+                    ptx::tma_load_2d_hint(a_dst + aq * (32 * kBK * 2), &tm_q, bar_full + 8 * stage, kb * kBK,
+                                          q_row0 + aq * 32, ptx::kEvictLast);
+                } else {
+                  ptx::mbar_arrive_expect_tx(bar_full + 8 * stage, tx);
+                  // the query block is re-read for every db tile: ask L2 to keep it (evict-last)
+                  ptx::tma_load_2d_hint(a_dst, &tm_q, bar_full + 8 * stage, kb * kBK, q_row0,
+                                        ptx::kEvictLast);
+                }
                 const int xkb = (kWork && p.x_kblocks > 0 && kb >= p.x_kblocks) ? kb - p.x_kblocks : kb;
                 // work mode streams every list once: keep it from evicting the query blocks in L2
                 if (kWork && !kWorkNoHint)

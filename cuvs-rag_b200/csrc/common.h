@@ -144,6 +144,7 @@ struct EnvConfig {
   int graph_maxq = 0;          // B2VS_GRAPH_MAXQ: largest batch replayed as a graph (default 64)
   int seed_mode = -1;          // B2VS_IVF_SEED=0|1: legacy seed kernels / seeds from the tensor-core pass
   int epi_groups = 0;          // B2VS_EPI_GROUPS=1|2: epilogue warp groups of the flat kernel (0 = heuristic)
+  int a_quarters = -1;         // B2VS_A_QUARTERS=0: always load whole 128-row query blocks in the grouped IVF-Flat scan
   int raw_emit = -1;           // B2VS_RAW_EMIT=0: the fused kernel's items sort and emit their own top-k lists
   int k0_debug = 0;            // B2VS_K0_DEBUG: 1 = the fused kernel's items skip their final sort + emission (timing only)
   int pq_debug = 0;            // B2VS_PQ_DEBUG: role-skipping bits of pq_tc_kernel (timing experiments only)
@@ -246,6 +247,8 @@ struct GroupedScanArgs {
   float* chunk_min;       // seed_all == 2: [nq][chunk_ld] minimum of every 32-row chunk
   int chunk_ld;
   const int* tau_chunk;   // optional [nq]: thresholds are (score, chunk) pairs (see BfTcParams)
+  int rows_in_work;       // 1: work[i].w = query rows of the block, placed in its leading ceil(w / 32) quarters
+                          // (packed or contiguous dealing): the kernel loads only those quarters
   int x_box_rows;         // 0 / 256: whole 256-row list tiles; 64 or 128: only that many rows of each (single-tile)
                           // item are loaded and multiplied - the seed pass reads just the head of every list
   int epi_groups;         // 0/1: four epilogue warps; 2: eight (two groups on alternate tiles) for

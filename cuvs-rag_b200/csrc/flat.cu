@@ -640,7 +640,10 @@ int FlatEngine::search_two_pass(const void* q_mat, int64_t q_rows, int nq, int k
 int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st) {
   CUtensorMap tm_q, tm_xl;
   const int xkb = static_cast<int>(ceil_div(a.kdim, kBK));
-  B2VS_TRY(encode_tmap_2d(&tm_q, a.q_mat, a.ab_format, a.q_rows, a.q_split ? 2 * xkb * kBK : a.kdim, kBM));
+  // query rows come in 32-row quarter boxes when the plan says how many rows a block holds
+  const bool quarter_boxes = a.rows_in_work && env().a_quarters != 0;
+  B2VS_TRY(encode_tmap_2d(&tm_q, a.q_mat, a.ab_format, a.q_rows, a.q_split ? 2 * xkb * kBK : a.kdim,
+                          quarter_boxes ? 32 : kBM));
   const int box = (a.x_box_rows == 64 || a.x_box_rows == 128) ? a.x_box_rows : kBN;
   B2VS_TRY(encode_tmap_2d(&tm_xl, a.x_mat, a.ab_format, a.x_rows, a.kdim, box));
   BfTcParams p{};
@@ -668,6 +671,7 @@ int launch_grouped_scan(int dev, const GroupedScanArgs& a, cudaStream_t st) {
   p.row_query = a.row_query;
   p.row_slot = a.row_slot;
   p.seed_all = a.seed_all;
+  p.a_quarter_boxes = quarter_boxes ? 1 : 0;
   p.chunk_min = a.chunk_min;
   p.chunk_ld = a.chunk_ld;
   p.tau_chunk = a.tau_chunk;

@@ -76,6 +76,9 @@ static int run_grouped_flat_scan(b2vs_index* index, IvfData* d, const long long*
   ga.cand = d->ws_g_cand.as<u64>(); ga.count = d->ws_g_cnt.as<int>(); ga.cap = cap;
   ga.row_slot = d->ws_g_rowslot.as<int>(); ga.seed_all = row_limit > 0 ? 1 : 0;
   if (row_limit == 64 || row_limit == 128) ga.x_box_rows = row_limit;   // seed pass: load only the head rows
+  // the counting-sort planner deals a block's rows over its leading ceil(w / 32) quarters (kDealPacked);
+  // the one-CTA planner of small batches deals over all four
+  ga.rows_in_work = plan_is_small(d, items) ? 0 : 1;
   if (timed) B2VS_CUDA(cudaEventRecord(d->ev0, st));
   B2VS_TRY(launch_grouped_scan(index->dev, ga, st));
   if (timed) B2VS_CUDA(cudaEventRecord(d->ev1, st));
