@@ -1,6 +1,6 @@
 """Exact search (K0) on one shard of the 8-GPU C2 run (1.25M x 768 bf16, 10K queries, k = 100) and
 on the 1-GPU size, under B2VS_* settings: ms per batch and the full pass alone.
-usage: k0_shard_probe.py "A=1;B=2;..." [rows]"""
+usage: k0_shard_probe.py "A=1&B=2;C=3;..." [rows]   (settings separated by ;, variables of a setting by &)"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -18,8 +18,8 @@ for s in settings:
     for kname in touched:
         os.environ.pop(kname, None)
     touched = set()
-    for kv in filter(None, s.split(",")):
-        kname, v = kv.split("=")
+    for kv in filter(None, s.split("&")):
+        kname, v = kv.split("=", 1)
         os.environ[kname] = v
         touched.add(kname)
     _native.reload_env()
