@@ -239,7 +239,8 @@ int ivf_search_direct(b2vs_index* index, const void* q, int q_dtype, int nq, int
     const int k_scan = (pq && sp.refine_ratio > 1) ? std::min(kMaxFusedK, k * sp.refine_ratio) : k;
     const size_t op_row = static_cast<size_t>(pq ? index->dim : d->dp) * 2 * (index->dtype == B2VS_F32 && !pq ? 2 : 1);
     const size_t per_query = static_cast<size_t>(grouped_cap(k_scan)) * sizeof(u64) +
-                             static_cast<size_t>(n_probes) * (op_row + 40) +
+                             2 * static_cast<size_t>(n_probes) * (op_row + 40) +   // two sets of planning buffers
+
                              static_cast<size_t>(d->dp) * sizeof(float) + static_cast<size_t>(k_scan) * 32;
     const int64_t by_bytes = static_cast<int64_t>(kMaxWorkspaceBytes / per_query);
     chunk = static_cast<int>(std::min<int64_t>(chunk, std::max<int64_t>(1024, by_bytes)));
