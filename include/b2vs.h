@@ -88,7 +88,12 @@ typedef struct b2vs_search_params {
 #define B2VS_FLAG_GRAPH 8       /* IVF, nq <= 64, k (and k*refine_ratio) <= 128: replay the call as one
                                    CUDA graph (captured on the second call of a signature
                                    (nq, k, dtype, n_probes, refine_ratio); env B2VS_GRAPH=1/0 forces it
-                                   on / off for every call) */
+                                   on / off for every call).  IVF batches of 2048 queries and more are
+                                   replayed as graphs WITHOUT the flag (unless B2VS_GRAPH=0 or
+                                   B2VS_FLAG_TIME_KERNEL is set): queries and results pass through
+                                   library-owned staging buffers, any pointers may be given.  Large IVF
+                                   batches also use an internal side stream (joined before the call
+                                   returns to the caller's stream order) */
 
 typedef struct b2vs_index_info {
   int32_t kind, device, metric, dtype, dim, n_lists, pq_dim, pq_bits;
