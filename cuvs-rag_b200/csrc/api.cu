@@ -73,6 +73,7 @@ static EnvConfig read_env() {
   }
   c.pq_debug = std::max(0, env_int_or("B2VS_PQ_DEBUG", 0));
   c.k0_debug = std::max(0, env_int_or("B2VS_K0_DEBUG", 0));
+  if (const char* e = std::getenv("B2VS_SAMPLE_UNION")) c.sample_union = e[0] == '0' ? 0 : 1;
   if (const char* e = std::getenv("B2VS_A_QUARTERS")) c.a_quarters = e[0] == '0' ? 0 : 1;
   if (const char* e = std::getenv("B2VS_RAW_EMIT")) c.raw_emit = e[0] == '0' ? 0 : 1;
   if (const char* e = std::getenv("B2VS_WORK_EPI")) c.work_epi = (e[0] == '1' || e[0] == '2') ? e[0] - '0' : 0;

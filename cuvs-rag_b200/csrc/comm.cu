@@ -102,7 +102,7 @@ struct b2vs_comm {
   ncclComm_t comm = nullptr;
   int n_ranks = 1, rank = 0, dev = 0;
   // grow-only workspaces of the exchange calls
-  b2vs::DevBuf recv_d, recv_i, q_all, loc_d, loc_i, io;
+  b2vs::DevBuf recv_d, recv_i, q_all, loc_d, loc_i, io, samp_all;
 };
 
 using namespace b2vs;
@@ -179,7 +179,8 @@ extern "C" int b2vs_comm_destroy(b2vs_comm* comm) {
   DeviceGuard guard(comm->dev);
   cudaDeviceSynchronize();
   if (comm->comm && nccl().ok) nccl().CommDestroy(comm->comm);
-  for (DevBuf* b : {&comm->recv_d, &comm->recv_i, &comm->q_all, &comm->loc_d, &comm->loc_i, &comm->io})
+  for (DevBuf* b : {&comm->recv_d, &comm->recv_i, &comm->q_all, &comm->loc_d, &comm->loc_i, &comm->io,
+                    &comm->samp_all})
     b->release();
   delete comm;
   return B2VS_OK;
@@ -313,6 +314,16 @@ namespace {
 int tau_exchange_cb(void* ctx, float* tau, int64_t n, cudaStream_t st) {
   return b2vs_allreduce_min_f32(static_cast<b2vs_comm*>(ctx), tau, n, st);
 }
+// Union exchange of a sampled pass: all-gather every rank's k best sampled scores per query, then the
+// k-th best of the union is everybody's threshold (merge.cu: union_kth_kernel).
+int tau_union_cb(void* ctx, const float* scores, int64_t n, int k, float* tau, cudaStream_t st) {
+  b2vs_comm* comm = static_cast<b2vs_comm*>(ctx);
+  const size_t cnt = static_cast<size_t>(n) * k;
+  B2VS_TRY(comm->samp_all.reserve(cnt * comm->n_ranks * sizeof(float)));
+  B2VS_NCCL(nccl().AllGather(scores, comm->samp_all.ptr, cnt, ncclFloat32, comm->comm, st));
+  return launch_union_kth(comm->samp_all.as<float>(), comm->n_ranks, static_cast<int>(n), k, tau, st);
+}
+bool union_exchange_enabled() { return env().sample_union != 0; }
 }  // namespace
 }  // namespace b2vs
 
@@ -360,9 +371,13 @@ extern "C" int b2vs_search_sharded(b2vs_comm* comm, b2vs_index* index, const voi
   // Threshold exchange needs every rank to run the same pass schedule: it is derived from the
   // smallest shard's size, agreed once by b2vs_comm_register_index (unregistered indexes - and
   // jobs with an empty shard - keep private thresholds: no collective inside the search).
+  // pooled samples (union exchange) when the sparser schedule still has a sampled pass, else the MIN
+  // exchange of k-th scores on the single-shard schedule
+  const bool pooled = union_exchange_enabled() && flat_exchanges_tau(index->sharded_min_rows, k, comm->n_ranks);
   if (index->kind == B2VS_KIND_FLAT && comm->n_ranks > 1 && index->n > 0 &&
-      flat_exchanges_tau(index->sharded_min_rows, k)) {
-    TauExchange tx{tau_exchange_cb, comm, index->sharded_min_rows};
+      (pooled || flat_exchanges_tau(index->sharded_min_rows, k, 1))) {
+    TauExchange tx{tau_exchange_cb, comm, index->sharded_min_rows, comm->n_ranks,
+                   pooled ? tau_union_cb : nullptr};
     rc = index->flat.search(comm->q_all.ptr, q_dtype, nq_total, k, sp.n_splits, index->id_offset,
                             comm->loc_d.as<float>(), comm->loc_i.as<int64_t>(), nullptr, st, sp.flags, &tx);
   } else {

@@ -144,6 +144,7 @@ struct EnvConfig {
   int graph_maxq = 0;          // B2VS_GRAPH_MAXQ: largest batch replayed as a graph (default 64)
   int seed_mode = -1;          // B2VS_IVF_SEED=0|1: legacy seed kernels / seeds from the tensor-core pass
   int epi_groups = 0;          // B2VS_EPI_GROUPS=1|2: epilogue warp groups of the flat kernel (0 = heuristic)
+  int sample_union = -1;       // B2VS_SAMPLE_UNION=0: sharded searches exchange k-th scores (MIN) instead of sampled top-k lists
   int a_quarters = -1;         // B2VS_A_QUARTERS=0: always load whole 128-row query blocks in the grouped IVF-Flat scan
   int raw_emit = -1;           // B2VS_RAW_EMIT=0: the fused kernel's items sort and emit their own top-k lists
   int k0_debug = 0;            // B2VS_K0_DEBUG: 1 = the fused kernel's items skip their final sort + emission (timing only)
@@ -169,10 +170,17 @@ struct TauExchange {
   void* ctx;
   int64_t schedule_rows;   // rows of the SMALLEST shard: the pass schedule (= number of exchanges)
                            // is derived from it, so every rank makes the same collective calls
+  // Union mode (world > 1 and union_fn set): a sampled pass hands over its k best raw SCORES per
+  // query ([n][k], ascending, +inf padded); union_fn all-gathers them and writes the k-th best of
+  // the union (+ one ulp) to tau.  The sample of the job is then `world` times larger than a rank's
+  // own, so the sampled passes run at `world` times the stride.
+  int world;
+  int (*union_fn)(void* ctx, const float* scores, int64_t n, int k, float* tau, cudaStream_t st);
 };
 // True when a flat search over at least `min_rows` rows with this k runs a sampled pass before
 // the full one, i.e. has thresholds to exchange (must evaluate identically on every rank).
-bool flat_exchanges_tau(int64_t min_rows, int k);
+// stride_mult = the factor applied to the sampled passes' strides (union mode: the world size).
+bool flat_exchanges_tau(int64_t min_rows, int k, int stride_mult = 1);
 
 struct FlatEngine {
   int dev = 0;
@@ -189,7 +197,7 @@ struct FlatEngine {
   CUtensorMap tm_x;       // db map, box = 256 rows (single-CTA kernel)
   CUtensorMap tm_x_half;  // db map, box = 128 rows (CTA-pair kernel: each CTA stages half a tile)
   // workspaces (grow-only)
-  DevBuf ws_cand, ws_keys, ws_q, ws_qnorm, ws_tau, ws_big, ws_bigcnt, ws_chunk, ws_work, ws_rawcnt;
+  DevBuf ws_cand, ws_keys, ws_q, ws_qnorm, ws_tau, ws_big, ws_bigcnt, ws_chunk, ws_work, ws_rawcnt, ws_samp;
   b2vs_search_stats stats{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // optional timing of the dominant kernel
   bool timing_pending = false;
@@ -286,12 +294,15 @@ int launch_pq_grouped_scan(int dev, const PqGroupedScanArgs& a, cudaStream_t st)
 int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k, int metric,
                         const float* qnorm, int64_t id_offset, float* out_d, int64_t* out_i,
                         int32_t* out_label, cudaStream_t st, const uint32_t* remap = nullptr,
-                        float* out_tau = nullptr);
+                        float* out_tau = nullptr, float* out_scores = nullptr);
 
 // Raw emission of the fused kernel: top-k (or the k-th score) per query from the unsorted per-item lists.
 int launch_merge_raw(const u64* cand, const int* count, int n_splits, int n_qblocks, int group,
                      int epi_groups, int nq, int k, int metric, const float* qnorm, int64_t id_offset,
-                     float* out_d, int64_t* out_i, int32_t* out_label, float* out_tau, cudaStream_t st);
+                     float* out_d, int64_t* out_i, int32_t* out_label, float* out_tau, cudaStream_t st,
+                     float* out_scores = nullptr);
+// k-th best (+ one ulp) of the union of n_ranks sorted raw-score lists per query (sharded sampled pass)
+int launch_union_kth(const float* all_scores, int n_ranks, int nq, int k, float* tau, cudaStream_t st);
 // Two-pass selection (flat.cu: search_two_pass).  chunk_tau: per query the k-th smallest
 // (chunk minimum, chunk index) pair -> tau / tau_chunk, and count[q] = 0.  cand_select: the k best
 // of each query's appended candidates, straight to answer rows.

@@ -228,6 +228,7 @@ void FlatEngine::destroy() {
   ws_bigcnt.release();
   ws_chunk.release();
   ws_rawcnt.release();
+  ws_samp.release();
   ws_work.release();
 }
 
@@ -249,7 +250,7 @@ static int tc_group_override() { return env().tc_group; }
 
 // Tile strides of the passes of one search (see FlatEngine::search).  B2VS_PASSES="16,1" etc.
 // overrides the heuristic for A/B measurements.
-static int pass_strides(int64_t tiles, int k, int* strides) {
+static int pass_strides(int64_t tiles, int k, int* strides, int mult = 1) {
   const int env_n = env().pass_n;
   const int* env_s = env().pass_s;
   if (k == 1) { strides[0] = 1; return 1; }        // arg-min keeps its state in registers
@@ -259,9 +260,12 @@ static int pass_strides(int64_t tiles, int k, int* strides) {
       if (env_s[i] == 1 || tiles / env_s[i] >= 8) strides[m++] = env_s[i];
     return m;
   }
+  // mult > 1 (sharded search, union exchange): the sampled passes of `mult` shards pool their
+  // samples, so each shard samples `mult` times more sparsely; a pass whose sample would shrink
+  // below 8 tiles is dropped
   int m = 0;
-  if (tiles >= 8192) strides[m++] = 256;
-  if (tiles >= 256) strides[m++] = 16;
+  if (tiles >= 8192 && tiles / (256 * mult) >= 8) strides[m++] = 256 * mult;
+  if (tiles >= 256 && tiles / (16 * mult) >= 8) strides[m++] = 16 * mult;
   strides[m++] = 1;
   return m;
 }
@@ -315,10 +319,10 @@ int FlatEngine::launch_fused(int group, int grid, const CUtensorMap& tm_q, const
   return B2VS_OK;
 }
 
-bool flat_exchanges_tau(int64_t min_rows, int k) {
+bool flat_exchanges_tau(int64_t min_rows, int k, int stride_mult) {
   if (k <= 1 || k > kMaxFusedK) return false;
   int strides[3];
-  return pass_strides(ceil_div(std::max<int64_t>(min_rows, 1), kBN), k, strides) >= 2;
+  return pass_strides(ceil_div(std::max<int64_t>(min_rows, 1), kBN), k, strides, std::max(1, stride_mult)) >= 2;
 }
 
 int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_splits,
@@ -424,7 +428,9 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
   // sharded search with threshold exchange: the schedule follows the smallest shard of the job,
   // so that every rank runs the same number of passes (= collective calls)
   const int64_t sched_tiles = tau_exchange ? ceil_div(std::max<int64_t>(tau_exchange->schedule_rows, 1), kBN) : tiles;
-  int n_pass = pass_strides(sched_tiles, k, strides);
+  const bool union_mode = tau_exchange && tau_exchange->union_fn && tau_exchange->world > 1;
+  int n_pass = pass_strides(sched_tiles, k, strides, union_mode ? tau_exchange->world : 1);
+  if (union_mode) B2VS_TRY(ws_samp.reserve(static_cast<size_t>(q_pad) * k * sizeof(float)));
   B2VS_TRY(ws_tau.reserve(static_cast<size_t>(q_pad) * sizeof(float)));
 
   BfTcParams p{};
@@ -491,12 +497,21 @@ int FlatEngine::search(const void* q, int q_dtype, int nq, int k, int force_spli
                                      ws_qnorm.as<float>(), id_offset, out_d, out_i, out_label, st));
     } else {
       // sampled pass: only the k-th best raw score per query is kept, as the next pass's threshold
+      // (union mode: the k best raw scores, for the exchange below)
+      float* const samp = union_mode ? ws_samp.as<float>() : nullptr;
       if (raw)
         B2VS_TRY(launch_merge_raw(ws_cand.as<u64>(), ws_rawcnt.as<int>(), n_splits, n_qblocks, group, epi_groups,
-                                  q_pad, k, metric, nullptr, 0, nullptr, nullptr, nullptr, ws_tau.as<float>(), st));
+                                  q_pad, k, metric, nullptr, 0, nullptr, nullptr, nullptr, ws_tau.as<float>(), st,
+                                  samp));
       else
         B2VS_TRY(launch_merge_splits(ws_keys.as<u64>(), n_splits * epi_groups, q_pad, q_pad, k, metric,
-                                     nullptr, 0, nullptr, nullptr, nullptr, st, nullptr, ws_tau.as<float>()));
+                                     nullptr, 0, nullptr, nullptr, nullptr, st, nullptr, ws_tau.as<float>(), samp));
+      if (union_mode) {
+        // every shard continues with the k-th best score of the POOLED samples of all shards
+        B2VS_TRY(tau_exchange->union_fn(tau_exchange->ctx, samp, q_pad, k, ws_tau.as<float>(), st));
+        ++launches;
+        continue;
+      }
       // sharded search: every shard continues with the tightest bound any shard found (a shard's
       // k-th best sampled score bounds the GLOBAL k-th score from above, so the minimum does too)
       if (tau_exchange) B2VS_TRY(tau_exchange->fn(tau_exchange->ctx, ws_tau.as<float>(), q_pad, st));

@@ -45,12 +45,23 @@ __device__ __forceinline__ void emit_answer_row(const u64 (&acc)[kMergeE], int l
   }
 }
 
+// Sampled pass of a sharded search: the k best RAW scores of the query, ascending, +inf padded
+// (comm.cu all-gathers them and takes the k-th best of the union as every shard's threshold).
+__device__ __forceinline__ void emit_raw_scores(const u64 (&acc)[kMergeE], int lane, int q, int k,
+                                                float* __restrict__ out_scores) {
+#pragma unroll
+  for (int e = 0; e < kMergeE; ++e) {
+    const int i = lane * kMergeE + e;
+    if (i < k) out_scores[static_cast<size_t>(q) * k + i] = acc[e] == kKeyInf ? INFINITY : key_score(acc[e]);
+  }
+}
+
 __global__ void merge_splits_kernel(const u64* __restrict__ keys, int n_splits, int q_pad, int nq,
                                     int k, int metric, const float* __restrict__ qnorm,
                                     long long id_offset, float* __restrict__ out_d,
                                     long long* __restrict__ out_i, int* __restrict__ out_label,
                                     const uint32_t* __restrict__ remap,
-                                    float* __restrict__ out_tau) {
+                                    float* __restrict__ out_tau, float* __restrict__ out_scores) {
   const int lane = threadIdx.x & 31;
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= nq) return;
@@ -81,6 +92,10 @@ __global__ void merge_splits_kernel(const u64* __restrict__ keys, int n_splits, 
       }
     }
   }
+  if (out_scores) {
+    emit_raw_scores(acc, lane, q, k, out_scores);
+    return;
+  }
   if (out_tau) {
     // threshold-seeding pass: publish one ulp above the k-th best raw score (inclusive bound)
     u64 kth = kKeyInf;
@@ -96,13 +111,14 @@ __global__ void merge_splits_kernel(const u64* __restrict__ keys, int n_splits, 
 
 int launch_merge_splits(const u64* keys, int n_splits, int q_pad, int nq, int k, int metric,
                         const float* qnorm, int64_t id_offset, float* out_d, int64_t* out_i,
-                        int32_t* out_label, cudaStream_t st, const uint32_t* remap, float* out_tau) {
+                        int32_t* out_label, cudaStream_t st, const uint32_t* remap, float* out_tau,
+                        float* out_scores) {
   const int threads = 128;
   const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(nq) * 32, threads));
   merge_splits_kernel<<<blocks, threads, 0, st>>>(keys, n_splits, q_pad, nq, k, metric, qnorm,
                                                   id_offset, out_d,
                                                   reinterpret_cast<long long*>(out_i), out_label,
-                                                  remap, out_tau);
+                                                  remap, out_tau, out_scores);
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }
@@ -205,7 +221,7 @@ __global__ void __launch_bounds__(kTwoPassThreads)
 merge_raw_kernel(const u64* __restrict__ cand, const int* __restrict__ count, int n_splits, int n_qblocks,
                  int group, int epi_groups, int nq, int k, int metric, const float* __restrict__ qnorm,
                  long long id_offset, float* __restrict__ out_d, long long* __restrict__ out_i,
-                 int* __restrict__ out_label, float* __restrict__ out_tau) {
+                 int* __restrict__ out_label, float* __restrict__ out_tau, float* __restrict__ out_scores) {
   const int lane = threadIdx.x & 31;
   const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= nq) return;
@@ -229,6 +245,10 @@ merge_raw_kernel(const u64* __restrict__ cand, const int* __restrict__ count, in
     }
   }
   sel.flush(k, lane);
+  if (out_scores) {
+    emit_raw_scores(sel.tk.acc, lane, q, k, out_scores);
+    return;
+  }
   if (out_tau) {
     // threshold-seeding pass: publish one ulp above the k-th best raw score (inclusive bound)
     u64 kth = kKeyInf;
@@ -244,11 +264,51 @@ merge_raw_kernel(const u64* __restrict__ cand, const int* __restrict__ count, in
 
 int launch_merge_raw(const u64* cand, const int* count, int n_splits, int n_qblocks, int group,
                      int epi_groups, int nq, int k, int metric, const float* qnorm, int64_t id_offset,
-                     float* out_d, int64_t* out_i, int32_t* out_label, float* out_tau, cudaStream_t st) {
+                     float* out_d, int64_t* out_i, int32_t* out_label, float* out_tau, cudaStream_t st,
+                     float* out_scores) {
   const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(nq) * 32, kTwoPassThreads));
   merge_raw_kernel<<<blocks, kTwoPassThreads, 0, st>>>(cand, count, n_splits, n_qblocks, group, epi_groups,
                                                        nq, k, metric, qnorm, id_offset, out_d,
-                                                       reinterpret_cast<long long*>(out_i), out_label, out_tau);
+                                                       reinterpret_cast<long long*>(out_i), out_label, out_tau,
+                                                       out_scores);
+  B2VS_CUDA(cudaGetLastError());
+  return B2VS_OK;
+}
+
+// Sharded search, sampled pass: all_scores = [n_ranks][nq][k] raw scores (each rank's k best of ITS
+// sample, ascending, +inf padded).  The k-th best of the union bounds the global k-th score from above
+// like any rank's own k-th best does, but it is the k-th best of a sample n_ranks times larger: the
+// ranks can sample n_ranks times more sparsely for the same threshold quality.  One warp per query.
+__global__ void __launch_bounds__(kTwoPassThreads)
+union_kth_kernel(const float* __restrict__ all_scores, int n_ranks, int nq, int k, float* __restrict__ tau) {
+  const int lane = threadIdx.x & 31;
+  const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  __shared__ u64 stage_mem[kTwoPassThreads / 32][kStageKeys];
+  StagedTopK sel;
+  sel.init(stage_mem[threadIdx.x >> 5]);
+  const float inf = __int_as_float(0x7f800000);
+  for (int r = 0; r < n_ranks; ++r) {
+    const float* src = all_scores + (static_cast<size_t>(r) * nq + q) * k;
+    for (int i0 = 0; i0 < k; i0 += 32) {
+      const int i = i0 + lane;
+      const float v = i < k ? __ldcg(src + i) : inf;
+      const bool hit = v <= sel.tk.tau && v < inf;
+      sel.push(hit ? pack_key(v, static_cast<uint32_t>(r * k + i)) : kKeyInf, k, lane);
+    }
+  }
+  sel.flush(k, lane);
+  u64 kth = kKeyInf;
+#pragma unroll
+  for (int e = 0; e < kListE; ++e)
+    if (lane * kListE + e == k - 1) kth = sel.tk.acc[e];
+  if (lane == (k - 1) / kListE)
+    tau[q] = (kth == kKeyInf) ? INFINITY : nextafterf(key_score(kth), INFINITY);
+}
+
+int launch_union_kth(const float* all_scores, int n_ranks, int nq, int k, float* tau, cudaStream_t st) {
+  const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(nq) * 32, kTwoPassThreads));
+  union_kth_kernel<<<blocks, kTwoPassThreads, 0, st>>>(all_scores, n_ranks, nq, k, tau);
   B2VS_CUDA(cudaGetLastError());
   return B2VS_OK;
 }
