@@ -677,7 +677,7 @@ def main():
         step_device(time_kernel=True)
         st = index.last_stats()   # resolves the event pair of this step's fused kernel
         kernel_ms.append(st.kernel_ms)
-        launches += st.launches + (4 if world > 1 else 0)   # + query all-gather, tau all-reduce, exchange, merge
+        launches += st.launches + (4 if world > 1 else 0)   # + query all-gather, threshold exchange, list exchange, merge
     e1.record()
     job.sync_all()
     ms_total = job.max_over_ranks(e0.elapsed_time(e1))
@@ -786,9 +786,9 @@ def main():
                        "k": args.k, "rows_per_gpu": n_local, "parallelism": f"shard{world}",
                        "l2_policy": "inputs larger than L2 (db shard >= 1.9 GB vs 126 MB L2), no flush",
                        "exchange": ("none (one shard)" if world == 1 else
-                                    "b2vs_search_sharded: NCCL all-gather of query slices, MIN all-reduce of "
-                                    "thresholds between passes, all-to-all of per-shard lists + merge of each "
-                                    "rank's slice"),
+                                    "b2vs_search_sharded: NCCL all-gather of query slices, pooled sampled-pass "
+                                    "thresholds (all-gather of the k best sampled scores, k-th best of the union), "
+                                    "all-to-all of per-shard lists + merge of each rank's slice"),
                        "n_splits": stats.n_splits, "grid": stats.grid},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"],
                          "unit": "TFLOP/s", "frac": (achieved / peaks["tflops"]) if achieved else None,

@@ -271,8 +271,10 @@ int b2vs_allreduce_min_f32(b2vs_comm* comm, float* values, int64_t n, void* stre
 int b2vs_comm_register_index(b2vs_comm* comm, b2vs_index* index, void* stream);
 
 /* The whole sharded step behind one call: all-gather of the query slices, local search of this
- * rank's shard - flat indexes exchange their per-query thresholds after the sampled pass, so
- * every shard runs its full pass against the GLOBAL k-th bound - then all-to-all + merge.
+ * rank's shard - flat indexes pool the samples of their sampled passes (all-gather of each rank's k
+ * best sampled scores, k-th best of the union = every shard's threshold; B2VS_SAMPLE_UNION=0: MIN
+ * all-reduce of the per-shard k-th scores), so every shard runs its full pass against the GLOBAL
+ * k-th bound - then all-to-all + merge.
  * q_local: this rank's query slice (device); out_d / out_i [slice rows, k] device.
  * The local per-shard result is NOT the shard's full top-k in this mode (rows that cannot be in
  * the global top-k are skipped), which is why it is not returned. */
